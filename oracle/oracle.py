@@ -1,0 +1,147 @@
+"""ctypes loader for the CPU oracle (oracle/_build/libvpl_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never from the product package.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libvpl_oracle.so")
+
+KEYLINE_DTYPE = np.dtype(
+    [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+     ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+     ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+     ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+     ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYLINE_DTYPE.itemsize == 68
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if (not force and os.path.exists(_SO)
+            and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs)):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        L.orc_fast_atan2.restype = ctypes.c_float
+        L.orc_fast_atan2.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.orc_lsd_detect.restype = ctypes.c_int
+        L.orc_lsd_detector_detect.restype = ctypes.c_int
+        L.orc_lbd_compute.restype = ctypes.c_int
+        L.orc_frontend_sequence.restype = ctypes.c_int64
+        L.orc_frontend_sequence_mt.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u8(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+def gaussian_blur5(img):
+    img = _u8(img); out = np.empty_like(img)
+    lib().orc_gaussian_blur5(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def gaussian_blur7(img):
+    img = _u8(img); out = np.empty_like(img)
+    lib().orc_gaussian_blur7_s075(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def resize08(img):
+    img = _u8(img); h, w = img.shape
+    dw, dh = ctypes.c_int(), ctypes.c_int()
+    lib().orc_resize_08(_p(img), w, h, None, ctypes.byref(dw), ctypes.byref(dh))
+    out = np.empty((dh.value, dw.value), np.uint8)
+    lib().orc_resize_08(_p(img), w, h, _p(out), ctypes.byref(dw), ctypes.byref(dh))
+    return out
+
+
+def pyrdown(img):
+    img = _u8(img); h, w = img.shape
+    out = np.empty((h // 2, w // 2), np.uint8)
+    lib().orc_pyrdown_half(_p(img), w, h, _p(out))
+    return out
+
+
+def sobel3(img):
+    img = _u8(img); h, w = img.shape
+    dx = np.empty((h, w), np.int16); dy = np.empty((h, w), np.int16)
+    lib().orc_sobel3(_p(img), w, h, _p(dx), _p(dy))
+    return dx, dy
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def lsd_detect(img, refine=2, scale08=True, cap=1 << 16):
+    """cv::LineSegmentDetector::detect -> (seg[n,4] f32, width[n], prec[n], nfa[n])."""
+    img = _u8(img); h, w = img.shape
+    seg = np.zeros((cap, 4), np.float32)
+    wd = np.zeros(cap); pr = np.zeros(cap); nf = np.zeros(cap)
+    n = lib().orc_lsd_detect(_p(img), w, h, int(refine), int(bool(scale08)), _p(seg), _p(wd), _p(pr),
+                             _p(nf), cap)
+    n = min(n, cap)
+    return seg[:n].copy(), wd[:n].copy(), pr[:n].copy(), nf[:n].copy()
+
+
+def lsd_detector_detect(img, scale=2, num_octaves=1, blur_first=True, cap=1 << 16):
+    """LSDDetector::detect -> structured array of KeyLine."""
+    img = _u8(img); h, w = img.shape
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    n = lib().orc_lsd_detector_detect(_p(img), w, h, int(scale), int(num_octaves), int(bool(blur_first)),
+                                      _p(kl), cap)
+    return kl[:min(n, cap)].copy()
+
+
+def lbd_compute(img, keylines, return_float=False):
+    """BinaryDescriptor::compute -> desc[n,32] u8 (and [n,72] f32 if return_float)."""
+    img = _u8(img); h, w = img.shape
+    kl = np.ascontiguousarray(keylines, dtype=KEYLINE_DTYPE)
+    n = len(kl)
+    desc = np.zeros((n, 32), np.uint8)
+    fd = np.zeros((n, 72), np.float32)
+    if n:
+        lib().orc_lbd_compute(_p(img), w, h, _p(kl), n, _p(desc), _p(fd))
+    return (desc, fd) if return_float else desc
+
+
+def hamming_knn(q, t, k=1):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.full((len(q), k), -1, np.int32); dist = np.full((len(q), k), -1, np.int32)
+    if len(q):
+        lib().orc_hamming_knn(_p(q), len(q), _p(t), len(t), int(k), _p(idx), _p(dist))
+    return idx, dist
+
+
+def frontend_sequence(frames, num_octaves=1, max_lines=8192, threads=1):
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    return int(lib().orc_frontend_sequence_mt(_p(frames), n, w, h, int(num_octaves), int(max_lines),
+                                              int(threads)))

@@ -1,0 +1,50 @@
+/*
+ * orc_threads.c -- CPU oracle: run the whole front end (LSDDetector::detect ->
+ * BinaryDescriptor::compute -> brute-force match against the previous frame)
+ * over a frame sequence on T host threads, for the CPU baseline of bench.py.
+ * TEST / BASELINE INFRASTRUCTURE ONLY (see vpl_oracle.h).  Frames are split in
+ * contiguous chunks with a one-frame halo, the same partition the multi-GPU
+ * driver uses.
+ */
+#define _GNU_SOURCE
+#include "vpl_oracle.h"
+#include <pthread.h>
+#include <stdlib.h>
+
+typedef struct {
+  const uint8_t* frames;
+  int f0, f1, w, h, num_octaves, max_lines;
+  int64_t total;
+} Job;
+
+static void* worker(void* a) {
+  Job* j = (Job*)a;
+  /* halo: also describe frame f0-1 so that pair (f0-1, f0) is matched here */
+  int start = j->f0 > 0 ? j->f0 - 1 : 0;
+  j->total = orc_frontend_sequence(j->frames + (size_t)start * j->w * j->h, j->f1 - start, j->w,
+                                   j->h, j->num_octaves, j->max_lines);
+  return NULL;
+}
+
+int64_t orc_frontend_sequence_mt(const uint8_t* frames, int n_frames, int w, int h,
+                                 int num_octaves, int max_lines, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_frames) n_threads = n_frames;
+  pthread_t* th = (pthread_t*)malloc((size_t)n_threads * sizeof(pthread_t));
+  Job* jobs = (Job*)malloc((size_t)n_threads * sizeof(Job));
+  for (int t = 0; t < n_threads; ++t) {
+    jobs[t].frames = frames;
+    jobs[t].f0 = (int)((int64_t)n_frames * t / n_threads);
+    jobs[t].f1 = (int)((int64_t)n_frames * (t + 1) / n_threads);
+    jobs[t].w = w; jobs[t].h = h; jobs[t].num_octaves = num_octaves; jobs[t].max_lines = max_lines;
+    jobs[t].total = 0;
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  int64_t total = 0;
+  for (int t = 0; t < n_threads; ++t) {
+    pthread_join(th[t], NULL);
+    total += jobs[t].total;
+  }
+  free(th); free(jobs);
+  return total;
+}

@@ -1,0 +1,91 @@
+/*
+ * vpl_oracle.h -- CPU ORACLE for the line front end (LSD -> LBD -> Hamming kNN).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call it.  The product path
+ * (vplines-slam_b200/csrc) never links it and has no CPU fallback.
+ *
+ * What it restates (the north-star path is NOT in /root/reference, see SURVEY.md
+ * section 0; the arithmetic lives in un-vendored third-party code):
+ *   - opencv imgproc  (pinned by the reference: "OpenCV 3.4.2", README.md:5;
+ *     find_package(OpenCV 3.4 REQUIRED), vins_estimator/CMakeLists.txt:18):
+ *     GaussianBlur / pyrDown / resize(INTER_LINEAR_EXACT) / Sobel / LSD (lsd.cpp).
+ *     Only cv2 4.13 is obtainable in this image, so cv2 4.13 semantics are the
+ *     pin (its rect_nfa differs from 3.4.2's): every function below is checked
+ *     bit-for-bit against cv2 4.13 by tests/test_oracle_*.py and by the golden
+ *     vectors under tests/golden/ (made by tests/golden/make_golden.py).
+ *   - opencv_contrib 3.4 line_descriptor (LSDDetector.cpp, binary_descriptor.cpp,
+ *     binary_descriptor_matcher.cpp): restated from the published algorithm.
+ *     cv2.line_descriptor is absent here => LBD / KeyLine packing are
+ *     "PARITY UNPINNED" (no upstream vectors exist; the reference has no test
+ *     on this path).  Hamming kNN is pinned against
+ *     cv2.BFMatcher(NORM_HAMMING).
+ *   - the reference's own nfa()/log_gamma (line_matching/src/edline_detector.h:
+ *     210-348) are the same formulas LSD uses; cited where followed.
+ */
+#ifndef VPL_ORACLE_H
+#define VPL_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* KeyLine exactly as opencv_contrib line_descriptor lays it out (17 x 4 B). */
+typedef struct {
+  float angle;
+  int32_t class_id;
+  int32_t octave;
+  float pt_x, pt_y;
+  float response;
+  float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength;
+  int32_t numOfPixels;
+} OrcKeyLine;
+
+/* ---- image primitives (bit-exact vs cv2 4.13) ---------- */
+void orc_gaussian_blur5(const uint8_t* src, int w, int h, uint8_t* dst);     /* 5x5 sigma=1   */
+void orc_gaussian_blur7_s075(const uint8_t* src, int w, int h, uint8_t* dst);/* 7x7 sigma=.75 */
+void orc_resize_08(const uint8_t* src, int w, int h, uint8_t* dst, int* dw, int* dh);
+void orc_pyrdown_half(const uint8_t* src, int w, int h, uint8_t* dst);       /* -> (w/2,h/2)  */
+void orc_sobel3(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy);
+float orc_fast_atan2(float y, float x);
+
+/* ---- LSD (cv::LineSegmentDetector, LSD_REFINE_ADV by default) ------------- */
+/* refine: 0 NONE, 1 STD, 2 ADV.  scale08: 1 => internal 0.8 scaling (default),
+ * 0 => scale 1.  Outputs up to cap segments; returns the number found (may
+ * exceed cap, in which case only cap were written). */
+int orc_lsd_detect(const uint8_t* img, int w, int h, int refine, int scale08,
+                   float* seg4, double* width, double* prec, double* nfa, int cap);
+
+/* ---- LSDDetector::detect (opencv_contrib LSDDetector.cpp) ----------------- */
+int orc_lsd_detector_detect(const uint8_t* img, int w, int h, int scale, int num_octaves,
+                            int blur_first, OrcKeyLine* out, int cap);
+
+/* ---- BinaryDescriptor::compute (opencv_contrib binary_descriptor.cpp) ----- */
+/* desc: n x 32 bytes; fdesc (optional, may be NULL): n x 72 floats. */
+int orc_lbd_compute(const uint8_t* img, int w, int h, const OrcKeyLine* kl, int n,
+                    uint8_t* desc, float* fdesc);
+
+/* ---- BinaryDescriptorMatcher brute force -------------- */
+/* idx/dist: nq x k, ascending distance, lowest train index on ties; -1 pad. */
+void orc_hamming_knn(const uint8_t* q, int nq, const uint8_t* t, int nt, int k,
+                     int32_t* idx, int32_t* dist);
+
+/* Whole front end on a frame sequence (for the CPU baseline timing).  Returns
+ * total keylines over the sequence (each frame is matched k=1 against the
+ * previous one; results are discarded, this entry point exists for timing). */
+int64_t orc_frontend_sequence(const uint8_t* frames, int n_frames, int w, int h,
+                              int num_octaves, int max_lines);
+
+/* Same, frames split over n_threads host threads in contiguous chunks with a
+ * one-frame halo (orc_threads.c). */
+int64_t orc_frontend_sequence_mt(const uint8_t* frames, int n_frames, int w, int h,
+                                 int num_octaves, int max_lines, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
