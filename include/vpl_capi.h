@@ -1,0 +1,183 @@
+/*
+ * vpl_capi.h -- C ABI of libvplines_b200.so: the B200-native line front end
+ * (LSD line segments -> LBD binary descriptors -> brute-force Hamming kNN).
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b).  The reference links
+ * its line primitives as a C++ static library (libline_matching.a,
+ * /root/reference/feature_tracker/CMakeLists.txt:51-57) and reaches them through
+ * two private seams of LineFeatureTracker::readImage:
+ *     void edline_detect(cv::Mat&, std::vector<Line>&, const bool&)
+ *     void match_line_match(const cv::Mat&, const cv::Mat&, std::vector<Line>&,
+ *                           std::vector<Line>&, std::vector<int>&)
+ *   (/root/reference/feature_tracker/include/linefeature_tracker.h:74-79, called
+ *   at feature_tracker/src/line_feature_tracker.cpp:87 and :115).
+ * The north star puts the OpenCV-3.4 line_descriptor surface at that position:
+ *     LSDDetector::detect(const Mat&, vector<KeyLine>&, int scale, int numOctaves, const Mat& mask)
+ *     BinaryDescriptor::compute(const Mat&, vector<KeyLine>&, Mat& descriptors, bool returnFloatDescr)
+ *     BinaryDescriptorMatcher::match / knnMatch(const Mat& q, const Mat& t, ...)
+ *   (opencv_contrib 3.4 modules/line_descriptor/include/opencv2/line_descriptor/
+ *   descriptor.hpp; only the dead includes at feature_tracker/include/
+ *   vanishing_point_detection.h:17-18 remain of it in the reference tree).
+ * Each entry point below names the interface it replaces.  The header-only C++
+ * facade vplines-slam_b200/compat/line_descriptor.hpp maps that surface (and the
+ * Line / vector<int> seam, compat/vplines_seam.hpp) onto these calls.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function
+ * returns 0 on success or a negative VPL_E_* code and never throws;
+ * vpl_last_error() gives the message.  All device memory, pinned staging and
+ * streams belong to the context; nothing is allocated on the per-batch path.
+ * There is NO CPU fallback: without a CUDA device vpl_create fails.
+ * A context is not re-entrant (same as the reference's detector/matcher objects,
+ * SURVEY.md 8b "Threading"); use one context per host thread per GPU.
+ */
+#ifndef VPL_CAPI_H
+#define VPL_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPL_OK 0
+#define VPL_E_INVALID (-1)  /* bad argument                                   */
+#define VPL_E_CUDA (-2)     /* CUDA runtime error (message has the detail)     */
+#define VPL_E_CAPACITY (-3) /* batch/line/image larger than the context allows */
+#define VPL_E_NODEVICE (-4) /* no usable CUDA device: there is no CPU path     */
+
+/* cv::line_descriptor::KeyLine, field for field (17 x 4 bytes, no padding). */
+typedef struct VplKeyLine {
+  float angle;
+  int32_t class_id;
+  int32_t octave;
+  float pt_x, pt_y;
+  float response;
+  float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength;
+  int32_t numOfPixels;
+} VplKeyLine;
+
+/* cv::DMatch */
+typedef struct VplDMatch {
+  int32_t queryIdx, trainIdx, imgIdx;
+  float distance;
+} VplDMatch;
+
+/* One raw LSD segment (cv::LineSegmentDetector::detect outputs _lines, width,
+ * prec, nfa). */
+typedef struct VplSegment {
+  float x1, y1, x2, y2;
+  double width, prec, nfa;
+} VplSegment;
+
+typedef struct VplContext VplContext;
+
+typedef struct VplConfig {
+  int32_t device;       /* CUDA device ordinal                                   */
+  int32_t max_width;    /* largest image the context accepts                     */
+  int32_t max_height;
+  int32_t max_octaves;  /* >= numOctaves of any call (1..4)                      */
+  int32_t max_lines;    /* KeyLine capacity per frame (all octaves together)     */
+  int32_t max_batch;    /* frames per batch                                      */
+  int32_t num_slots;    /* batches in flight for submit/collect (1..4)           */
+  int32_t blur_first;   /* 1: LSDDetector blurs octave 0 with GaussianBlur 5x5   */
+  int32_t profile;      /* 1: record per-stage CUDA-event timings                */
+} VplConfig;
+
+/* ---- lifetime -------------------------------------------------------------- */
+void vpl_default_config(VplConfig* cfg);
+int vpl_create(const VplConfig* cfg, VplContext** out);
+void vpl_destroy(VplContext* ctx);
+const char* vpl_last_error(const VplContext* ctx); /* ctx may be NULL: last create error */
+const char* vpl_version(void);
+int vpl_device_count(void);
+
+/* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
+/* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
+ * keylines: n * cap entries, frame f at keylines + f*cap; counts[f] = number found
+ * (<= cap; if a frame has more than cap lines the call returns VPL_E_CAPACITY). */
+int vpl_lsd_detect_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                         size_t stride, int scale, int num_octaves, VplKeyLine* keylines,
+                         int32_t* counts, int cap);
+
+/* ---- BinaryDescriptor::compute --------------------------------------------- */
+/* keylines/counts laid out as above (caller-supplied, any detector). desc: n*cap*32
+ * bytes, row i of frame f at desc + (f*cap+i)*32 (CV_8UC1 rows of 32). */
+int vpl_lbd_compute_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                          size_t stride, const VplKeyLine* keylines, const int32_t* counts,
+                          int cap, uint8_t* desc);
+
+/* ---- BinaryDescriptorMatcher::match / knnMatch (replaces match_line_match,
+ *      linefeature_tracker.h:76-79) ------------------------------------------- */
+/* n_pairs independent (query, train) problems.  q: n_pairs*cap_q*32 bytes, pair p at
+ * q + p*cap_q*32 with nq[p] valid rows; t likewise.  Brute force, ascending
+ * distance, lowest train index on ties.  out: n_pairs*cap_q*k DMatch; entries
+ * beyond nt[p] candidates have trainIdx=-1. */
+int vpl_match_batch(VplContext* ctx, const uint8_t* q, const int32_t* nq, int cap_q,
+                    const uint8_t* t, const int32_t* nt, int cap_t, int n_pairs, int k,
+                    VplDMatch* out);
+
+/* ---- the fused path: detect + compute + match(t, t-1), one batch ----------- */
+/* Equivalent to the three calls above on n consecutive frames with everything
+ * kept in HBM in between.  matches: n*cap*k entries; frame f (f>=1) is matched
+ * (query) against frame f-1 (train); frame 0 is matched against the last frame of
+ * the previous batch on this context if `chain` is non-zero, otherwise it gets
+ * trainIdx=-1.  Any of keylines/desc/matches may be NULL to skip its download. */
+int vpl_frontend_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                       size_t stride, int scale, int num_octaves, int k, int chain,
+                       VplKeyLine* keylines, int32_t* counts, int cap, uint8_t* desc,
+                       VplDMatch* matches);
+
+/* Pipelined form: submit() uploads and enqueues batch work on slot s and returns
+ * without waiting; collect() waits for slot s and downloads.  Up to num_slots
+ * batches may be in flight. imgs must stay valid until submit returns (they are
+ * staged into pinned memory inside submit). */
+int vpl_frontend_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h,
+                        size_t stride, int scale, int num_octaves, int k, int chain);
+int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_t* counts, int cap,
+                         uint8_t* desc, VplDMatch* matches);
+
+/* Device-resident form used to time the kernels alone: runs the fused path on
+ * n frames already in the context's device input buffer of slot s (filled by the
+ * last submit on that slot), leaves results in HBM, does not synchronise. */
+int vpl_frontend_run_resident(VplContext* ctx, int slot, int k);
+int vpl_sync(VplContext* ctx);
+
+/* ---- raw stages, exported for the parity tests ------------------------------ */
+/* cv::LineSegmentDetector(LSD_REFINE_ADV)::detect on one image (no pyramid blur). */
+int vpl_lsd_raw(VplContext* ctx, const uint8_t* img, int w, int h, size_t stride, VplSegment* out,
+                int32_t* count, int cap);
+/* Image primitives on one image: which = 0 GaussianBlur5x5 s1 (u8), 1 pyrDown half
+ * (u8, (w/2)x(h/2)), 2 Sobel dx,dy (int16 interleaved, 2*w*h), 3 LSD 0.8 scaling
+ * (u8, out_w x out_h), 4 level-line angle in degrees (float, <0 undefined) of the
+ * 0.8-scaled image, 5 pseudo-ordered pixel indices of the 0.8-scaled image (int32;
+ * out_w = count). out must hold the result; out_w/out_h receive its size. */
+int vpl_debug_stage(VplContext* ctx, int which, const uint8_t* img, int w, int h, size_t stride,
+                    void* out, size_t out_bytes, int32_t* out_w, int32_t* out_h);
+
+/* ---- measurement ------------------------------------------------------------ */
+#define VPL_STAGE_H2D 0
+#define VPL_STAGE_PYRAMID 1   /* blur5+sobel, pyrDown+sobel          */
+#define VPL_STAGE_SCALE 2     /* LSD 7x7 blur + 0.8 resize           */
+#define VPL_STAGE_ANGLE 3     /* gradient / level-line angle         */
+#define VPL_STAGE_ORDER 4     /* pseudo-ordering                     */
+#define VPL_STAGE_REGION 5    /* region growing + rect + refine      */
+#define VPL_STAGE_NFA 6       /* rectangle NFA validation            */
+#define VPL_STAGE_PACK 7      /* compaction + KeyLine packing        */
+#define VPL_STAGE_LBD 8
+#define VPL_STAGE_MATCH 9
+#define VPL_STAGE_D2H 10
+#define VPL_NUM_STAGES 11
+/* Accumulated device milliseconds and launch counts per stage since the last
+ * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
+int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);
+int vpl_reset_stage_times(VplContext* ctx);
+/* Total kernels launched by this context since creation. */
+int64_t vpl_kernel_launches(const VplContext* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPL_CAPI_H */

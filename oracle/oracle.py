@@ -43,6 +43,7 @@ def lib():
         L.orc_fast_atan2.argtypes = [ctypes.c_float, ctypes.c_float]
         L.orc_lsd_detect.restype = ctypes.c_int
         L.orc_lsd_detector_detect.restype = ctypes.c_int
+        L.orc_lsd_stages.restype = ctypes.c_int
         L.orc_lbd_compute.restype = ctypes.c_int
         L.orc_frontend_sequence.restype = ctypes.c_int64
         L.orc_frontend_sequence_mt.restype = ctypes.c_int64
@@ -108,6 +109,18 @@ def lsd_detect(img, refine=2, scale08=True, cap=1 << 16):
                              _p(nf), cap)
     n = min(n, cap)
     return seg[:n].copy(), wd[:n].copy(), pr[:n].copy(), nf[:n].copy()
+
+
+def lsd_stages(img):
+    """-> (scaled u8 [hs,ws], angle degrees f32 [hs,ws] (-1024 undefined), ordered defined pixel indices)."""
+    img = _u8(img); h, w = img.shape
+    ws, hs = ctypes.c_int(), ctypes.c_int()
+    lib().orc_resize_08(_p(img), w, h, None, ctypes.byref(ws), ctypes.byref(hs))
+    scaled = np.zeros((hs.value, ws.value), np.uint8)
+    ang = np.zeros((hs.value, ws.value), np.float32)
+    order = np.zeros(hs.value * ws.value, np.int32)
+    n = lib().orc_lsd_stages(_p(img), w, h, _p(scaled), _p(ang), _p(order), ctypes.byref(ws), ctypes.byref(hs))
+    return scaled, ang, order[:n].copy()
 
 
 def lsd_detector_detect(img, scale=2, num_octaves=1, blur_first=True, cap=1 << 16):

@@ -487,3 +487,49 @@ int orc_lsd_detect(const uint8_t* img, int w0, int h0, int refine_mode, int scal
   free(scaled); free(L.angles); free(L.modgrad); free(L.used); free(L.order); free(L.reg);
   return nout;
 }
+
+/* Stage dump for the per-stage GPU parity tests: the 0.8-scaled image, the
+ * level-line angle in DEGREES (float, -1024 where undefined) and the pseudo-ordered
+ * list restricted to defined pixels (the only ones that can seed a region). */
+int orc_lsd_stages(const uint8_t* img, int w0, int h0, uint8_t* scaled_out, float* ang_deg_out,
+                   int* order_out, int* ws_out, int* hs_out) {
+  const double prec = ORC_PI * 22.5 / 180;
+  const double rho = 2.0 / sin(prec);
+  Lsd L;
+  memset(&L, 0, sizeof(L));
+  uint8_t* g = (uint8_t*)malloc((size_t)w0 * h0);
+  orc_gaussian_blur7_s075(img, w0, h0, g);
+  orc_resize_08(g, w0, h0, NULL, &L.w, &L.h);
+  uint8_t* scaled = (uint8_t*)malloc((size_t)L.w * L.h);
+  orc_resize_08(g, w0, h0, scaled, &L.w, &L.h);
+  free(g);
+  const size_t np = (size_t)L.w * L.h;
+  L.angles = (double*)malloc(np * sizeof(double));
+  L.modgrad = (double*)malloc(np * sizeof(double));
+  L.order = (int*)malloc(np * sizeof(int));
+  ll_angle(&L, scaled, rho, 1024);
+  *ws_out = L.w;
+  *hs_out = L.h;
+  if (scaled_out) memcpy(scaled_out, scaled, np);
+  if (ang_deg_out) {
+    for (int y = 0; y < L.h; ++y)
+      for (int x = 0; x < L.w; ++x) {
+        float a = -1024.0f;
+        if (L.angles[(size_t)y * L.w + x] != NOTDEF) {
+          const uint8_t* r0 = scaled + (size_t)y * L.w;
+          const uint8_t* r1 = r0 + L.w;
+          int DA = r1[x + 1] - r0[x], BC = r0[x + 1] - r1[x];
+          a = orc_fast_atan2((float)(DA + BC), (float)-(DA - BC));
+        }
+        ang_deg_out[(size_t)y * L.w + x] = a;
+      }
+  }
+  int n = 0;
+  for (int i = 0; i < L.n_order; ++i)
+    if (L.angles[L.order[i]] != NOTDEF) {
+      if (order_out) order_out[n] = L.order[i];
+      n++;
+    }
+  free(scaled); free(L.angles); free(L.modgrad); free(L.order);
+  return n;
+}

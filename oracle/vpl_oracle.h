@@ -60,6 +60,11 @@ float orc_fast_atan2(float y, float x);
 int orc_lsd_detect(const uint8_t* img, int w, int h, int refine, int scale08,
                    float* seg4, double* width, double* prec, double* nfa, int cap);
 
+/* Stage dump (0.8-scaled image, angle in degrees / -1024, ordered defined pixels);
+ * returns the number of ordered pixels.  Any output may be NULL. */
+int orc_lsd_stages(const uint8_t* img, int w, int h, uint8_t* scaled, float* ang_deg, int* order,
+                   int* ws, int* hs);
+
 /* ---- LSDDetector::detect (opencv_contrib LSDDetector.cpp) ----------------- */
 int orc_lsd_detector_detect(const uint8_t* img, int w, int h, int scale, int num_octaves,
                             int blur_first, OrcKeyLine* out, int cap);

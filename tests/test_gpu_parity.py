@@ -1,0 +1,199 @@
+"""GPU parity tests proper: every stage of the CUDA path (through the C ABI) against the
+CPU oracle on the same inputs.  Bars: bit-exact for the integer/byte/index stages
+(image primitives, ordering, Hamming), bit-exact LBD on identical keylines, and for LSD
+the north-star bar (one-to-one, endpoints within 0.5 px for >= 99 %) -- in practice the
+engine reproduces the sequential algorithm exactly, which the tests also record."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(vpl):
+    c = vpl.Context(max_width=1280, max_height=720, max_octaves=2, max_lines=4096, max_batch=8, num_slots=2,
+                    profile=True)
+    yield c
+    c.close()
+
+
+def kl_fields_equal(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[n], b[n]) for n in a.dtype.names)
+
+
+def match_segments(got, exp, tol=0.5):
+    """one-to-one greedy match of segments by endpoint distance; fraction of exp matched within tol."""
+    if len(exp) == 0:
+        return 1.0 if len(got) == 0 else 0.0
+    used = np.zeros(len(got), bool)
+    ok = 0
+    for e in exp:
+        d = np.maximum(np.hypot(got[:, 0] - e[0], got[:, 1] - e[1]), np.hypot(got[:, 2] - e[2], got[:, 3] - e[3]))
+        d[used] = np.inf
+        j = int(np.argmin(d)) if len(d) else -1
+        if j >= 0 and d[j] <= tol:
+            used[j] = True
+            ok += 1
+    return ok / len(exp)
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (61, 83), (720, 1280), (100, 36)])
+def test_image_primitives_bit_exact(ctx, orc, shape):
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(ctx.debug_stage(0, img), orc.gaussian_blur5(img))
+    assert np.array_equal(ctx.debug_stage(1, img), orc.pyrdown(img))
+    dx, dy = ctx.debug_stage(2, img)
+    odx, ody = orc.sobel3(img)
+    assert np.array_equal(dx, odx) and np.array_equal(dy, ody)
+    assert np.array_equal(ctx.debug_stage(3, img), orc.resize08(orc.gaussian_blur7(img)))
+
+
+def test_lsd_stages_bit_exact(ctx, orc, mh04):
+    img = mh04[0]
+    scaled, ang, order = orc.lsd_stages(img)
+    assert np.array_equal(ctx.debug_stage(3, img), scaled)
+    assert np.array_equal(ctx.debug_stage(4, img), ang)
+    assert np.array_equal(ctx.debug_stage(5, img), order)
+
+
+@pytest.mark.parametrize("k", [1, 5, 10])
+def test_lsd_raw_vs_oracle_and_cv2_golden(ctx, orc, golden, mh04, k):
+    blurred = orc.gaussian_blur5(mh04[k - 1])
+    got = ctx.lsd_raw(blurred)
+    seg, width, prec, nfa = orc.lsd_detect(blurred, refine=2)
+    g = np.stack([got["x1"], got["y1"], got["x2"], got["y2"]], 1)
+    # north-star bar
+    assert len(g) == len(seg)
+    assert match_segments(g, seg, 0.5) >= 0.99
+    # what the engine actually delivers: the sequential result, bit for bit
+    assert np.array_equal(g, seg)
+    assert np.array_equal(g, golden["cv2_lsd"][f"adv{k}_lines"])
+    assert np.allclose(got["width"], width, rtol=1e-12, atol=0)
+    assert np.array_equal(got["prec"], prec)
+    assert np.allclose(got["nfa"], nfa, rtol=1e-9, atol=1e-9)
+
+
+def test_lsd_raw_synthetic_and_degenerate(ctx, orc, synth):
+    for seed in (3, 4):
+        img = synth.sequence(1, w=640, h=400, seed=seed, n_quads=25, n_strokes=40)[0]
+        got = ctx.lsd_raw(img)
+        seg = orc.lsd_detect(img, refine=2)[0]
+        assert np.array_equal(np.stack([got["x1"], got["y1"], got["x2"], got["y2"]], 1), seg)
+    assert len(ctx.lsd_raw(np.zeros((64, 64), np.uint8))) == 0
+    assert len(ctx.lsd_raw(np.full((40, 50), 255, np.uint8))) == 0
+    step = np.full((200, 200), 50, np.uint8); step[:, 100:] = 200
+    got = ctx.lsd_raw(step)
+    assert len(got) == 1
+    assert np.array_equal(np.array([got["x1"][0], got["y1"][0], got["x2"][0], got["y2"][0]]),
+                          orc.lsd_detect(step, refine=2)[0][0])
+
+
+@pytest.mark.parametrize("octaves", [1, 2])
+def test_lsd_detector_keylines_bit_exact(ctx, orc, mh04, octaves):
+    frames = mh04[3:7]
+    got = ctx.lsd_detect_batch(frames, scale=2, num_octaves=octaves)
+    for f, img in enumerate(frames):
+        exp = orc.lsd_detector_detect(img, scale=2, num_octaves=octaves)
+        assert kl_fields_equal(got[f], exp), f"frame {f}"
+
+
+def test_lbd_bit_exact_on_identical_keylines(ctx, orc, mh04):
+    frames = mh04[0:3]
+    kls = [orc.lsd_detector_detect(img, scale=2, num_octaves=2) for img in frames]
+    got = ctx.lbd_compute_batch(frames, kls)
+    for f, img in enumerate(frames):
+        assert np.array_equal(got[f], orc.lbd_compute(img, kls[f])), f"frame {f}"
+
+
+def test_lbd_edge_keylines(ctx, orc, mh04):
+    """lines hugging the border / very short / long: the clamped sampling must agree."""
+    img = mh04[2]
+    kl = orc.lsd_detector_detect(img, scale=2, num_octaves=1)
+    sel = np.argsort(kl["lineLength"])
+    pick = np.concatenate([sel[:20], sel[-20:], np.argsort(kl["pt_y"])[:20], np.argsort(-kl["pt_x"])[:20]])
+    k = kl[np.unique(pick)]
+    assert np.array_equal(ctx.lbd_compute_batch(img[None], [k])[0], orc.lbd_compute(img, k))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_hamming_bit_exact(ctx, orc, golden, k):
+    g = golden["cv2_hamming"]
+    rng = np.random.default_rng(9)
+    qs = [g["q"], rng.integers(0, 4, (300, 32), dtype=np.uint8), rng.integers(0, 256, (1, 32), dtype=np.uint8),
+          rng.integers(0, 256, (33, 32), dtype=np.uint8)]
+    ts = [g["t"], rng.integers(0, 4, (513, 32), dtype=np.uint8), rng.integers(0, 256, (700, 32), dtype=np.uint8),
+          rng.integers(0, 256, (2, 32), dtype=np.uint8)]
+    got = ctx.match_batch(qs, ts, k=k)
+    for q, t, m in zip(qs, ts, got):
+        idx, dist = orc.hamming_knn(q, t, k)
+        assert np.array_equal(m["trainIdx"], idx)
+        valid = idx >= 0
+        assert np.array_equal(m["distance"][valid].astype(np.int32), dist[valid])
+        assert np.array_equal(m["queryIdx"], np.repeat(np.arange(len(q))[:, None], k, 1))
+    if k == 3:
+        assert np.array_equal(got[0]["trainIdx"], g["idx"])  # cv2.BFMatcher golden, incl. planted ties
+
+
+def test_frontend_fused_equals_oracle_chain(ctx, orc, mh04):
+    """C1: the bundled mh04 frames, detect + describe + match(t, t-1), batches chained."""
+    frames = mh04[:10]
+    fe = __import__("vplines_slam_b200").FrontEnd(ctx, scale=2, num_octaves=1, k=2)
+    kls, descs, ms = fe.run(frames)           # max_batch=8 -> two batches, chained
+    prev = None
+    for f, img in enumerate(frames):
+        ekl = orc.lsd_detector_detect(img, 2, 1)
+        edesc = orc.lbd_compute(img, ekl)
+        assert kl_fields_equal(kls[f], ekl), f"keylines frame {f}"
+        assert np.array_equal(descs[f], edesc), f"descriptors frame {f}"
+        if prev is None:
+            assert (ms[f]["trainIdx"] == -1).all()
+        else:
+            idx, dist = orc.hamming_knn(edesc, prev, 2)
+            assert np.array_equal(ms[f]["trainIdx"], idx), f"matches frame {f}"
+            assert np.array_equal(ms[f]["distance"].astype(np.int32), dist)
+        prev = edesc
+
+
+def test_screenshot_pair_5_10(ctx, orc, mh04):
+    """C1's (5,10) pair: same pipeline through the OpenCV-shaped surface."""
+    import vplines_slam_b200 as v
+    det, bd, bm = v.LSDDetector.createLSDDetector(), v.BinaryDescriptor.createBinaryDescriptor(), \
+        v.BinaryDescriptorMatcher.createBinaryDescriptorMatcher()
+    k5 = det.detect(mh04[4], 2, 1, as_records=True); k10 = det.detect(mh04[9], 2, 1, as_records=True)
+    d5 = bd.compute(mh04[4], k5); d10 = bd.compute(mh04[9], k10)
+    m = bm.match(d10, d5)
+    idx, dist = orc.hamming_knn(orc.lbd_compute(mh04[9], orc.lsd_detector_detect(mh04[9], 2, 1)),
+                                orc.lbd_compute(mh04[4], orc.lsd_detector_detect(mh04[4], 2, 1)), 1)
+    assert [x.trainIdx for x in m] == list(idx[:, 0]) and [int(x.distance) for x in m] == list(dist[:, 0])
+
+
+def test_batch_invariance_and_determinism(ctx, synth):
+    """Results do not depend on batching (size-independent property used at full size)."""
+    frames = synth.config_sequence("C2_euroc_752x480", 6)
+    a = ctx.lsd_detect_batch(frames)
+    b = [ctx.lsd_detect_batch(frames[i:i + 1])[0] for i in range(len(frames))]
+    c = ctx.lsd_detect_batch(frames)
+    for x, y, z in zip(a, b, c):
+        assert kl_fields_equal(x, y) and kl_fields_equal(x, z)
+
+
+def test_two_octave_synthetic_c3(ctx, orc, synth):
+    frames = synth.config_sequence("C3_d455_1280x720", 2)
+    kls, descs, ms = ctx.frontend_batch(frames, scale=2, num_octaves=2, k=2)
+    for f, img in enumerate(frames):
+        ekl = orc.lsd_detector_detect(img, 2, 2)
+        assert kl_fields_equal(kls[f], ekl)
+        assert np.array_equal(descs[f], orc.lbd_compute(img, ekl))
+    idx, dist = orc.hamming_knn(descs[1], descs[0], 2)
+    assert np.array_equal(ms[1]["trainIdx"], idx)
+
+
+def test_errors(ctx, vpl):
+    with pytest.raises(vpl.VplError):
+        ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context
+    with pytest.raises(vpl.VplError):
+        ctx.lsd_detect_batch(np.zeros((64, 64, 64), np.uint8))          # batch > max_batch
+    with pytest.raises(RuntimeError):
+        vpl.LSDDetector.createLSDDetector().detect(np.zeros((64, 64), np.float32), 2, 1)
+    assert vpl.BinaryDescriptorMatcher().match(np.zeros((0, 32), np.uint8), np.zeros((4, 32), np.uint8)) == []

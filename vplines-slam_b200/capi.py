@@ -1,0 +1,263 @@
+"""ctypes binding of libvplines_b200.so (the C ABI in include/vpl_capi.h).
+
+This is the thin host-side shim the tests and bench.py call through; it adds no
+computation.  Loading fails loudly when the library has not been built, and
+Context() fails loudly when there is no CUDA device: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvplines_b200.so")
+
+VPL_OK, VPL_E_INVALID, VPL_E_CUDA, VPL_E_CAPACITY, VPL_E_NODEVICE = 0, -1, -2, -3, -4
+STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h"]
+
+KEYLINE_DTYPE = np.dtype(
+    [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+     ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+     ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+     ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+     ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+SEGMENT_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"),
+                          ("width", "<f8"), ("prec", "<f8"), ("nfa", "<f8")])
+assert KEYLINE_DTYPE.itemsize == 68 and DMATCH_DTYPE.itemsize == 16 and SEGMENT_DTYPE.itemsize == 40
+
+
+class VplConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
+                ("max_octaves", C.c_int32), ("max_lines", C.c_int32), ("max_batch", C.c_int32),
+                ("num_slots", C.c_int32), ("blur_first", C.c_int32), ("profile", C.c_int32)]
+
+
+EXPORTS = [
+    "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
+    "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
+    "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
+    "vpl_debug_stage", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
+]
+
+_lib = None
+
+
+class VplError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vpl error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen the library (no CUDA call is made until a context is created)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.vpl_default_config.argtypes = [C.POINTER(VplConfig)]
+    L.vpl_default_config.restype = None
+    L.vpl_create.argtypes = [C.POINTER(VplConfig), C.POINTER(vp)]
+    L.vpl_destroy.argtypes = [vp]
+    L.vpl_destroy.restype = None
+    L.vpl_last_error.argtypes = [vp]
+    L.vpl_last_error.restype = C.c_char_p
+    L.vpl_version.restype = C.c_char_p
+    L.vpl_lsd_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, vp, vp, i32]
+    L.vpl_lbd_compute_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32, vp]
+    L.vpl_match_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
+    L.vpl_frontend_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.vpl_frontend_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32, i32, i32, i32]
+    L.vpl_frontend_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp]
+    L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
+    L.vpl_sync.argtypes = [vp]
+    L.vpl_lsd_raw.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32]
+    L.vpl_debug_stage.argtypes = [vp, i32, vp, i32, i32, sz, vp, sz, vp, vp]
+    L.vpl_get_stage_times.argtypes = [vp, vp, vp]
+    L.vpl_reset_stage_times.argtypes = [vp]
+    L.vpl_kernel_launches.argtypes = [vp]
+    L.vpl_kernel_launches.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _img_ptrs(frames):
+    """frames: (n,h,w) uint8 C-contiguous array or list of 2-D uint8 arrays -> (array of pointers, keepalive, n, w, h, stride)."""
+    if isinstance(frames, np.ndarray) and frames.ndim == 3:
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        base = frames.ctypes.data
+        ptrs = (C.c_void_p * n)(*[base + i * h * w for i in range(n)])
+        return ptrs, frames, n, w, h, w
+    arrs = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    n = len(arrs)
+    h, w = arrs[0].shape
+    assert all(a.shape == (h, w) for a in arrs)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    return ptrs, arrs, n, w, h, w
+
+
+class Context:
+    """One GPU, `num_slots` batches in flight.  Mirrors VplContext."""
+
+    def __init__(self, device=0, max_width=752, max_height=480, max_octaves=1, max_lines=2048, max_batch=64,
+                 num_slots=2, blur_first=True, profile=False):
+        L = load()
+        cfg = VplConfig()
+        L.vpl_default_config(C.byref(cfg))
+        cfg.device, cfg.max_width, cfg.max_height = device, max_width, max_height
+        cfg.max_octaves, cfg.max_lines, cfg.max_batch = max_octaves, max_lines, max_batch
+        cfg.num_slots, cfg.blur_first, cfg.profile = num_slots, int(blur_first), int(profile)
+        self.cfg = cfg
+        self._L = L
+        h = C.c_void_p()
+        r = L.vpl_create(C.byref(cfg), C.byref(h))
+        if r != 0:
+            raise VplError(r, L.vpl_last_error(None).decode())
+        self._h = h
+        self.max_lines = max_lines
+        self.max_batch = max_batch
+        self.num_slots = num_slots
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vpl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, r):
+        if r != 0:
+            raise VplError(r, self._L.vpl_last_error(self._h).decode())
+
+    # -- LSDDetector::detect -------------------------------------------------
+    def lsd_detect_batch(self, frames, scale=2, num_octaves=1, cap=None):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        cap = cap or self.max_lines
+        kl = np.zeros((n, cap), KEYLINE_DTYPE)
+        counts = np.zeros(n, np.int32)
+        self._ck(self._L.vpl_lsd_detect_batch(self._h, ptrs, n, w, h, stride, scale, num_octaves, _ptr(kl),
+                                              _ptr(counts), cap))
+        return [kl[f, :counts[f]].copy() for f in range(n)]
+
+    # -- BinaryDescriptor::compute --------------------------------------------
+    def lbd_compute_batch(self, frames, keylines, cap=None):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        assert len(keylines) == n
+        cap = cap or max(1, max(len(k) for k in keylines))
+        kl = np.zeros((n, cap), KEYLINE_DTYPE)
+        counts = np.array([len(k) for k in keylines], np.int32)
+        for f, k in enumerate(keylines):
+            kl[f, :len(k)] = k
+        desc = np.zeros((n, cap, 32), np.uint8)
+        self._ck(self._L.vpl_lbd_compute_batch(self._h, ptrs, n, w, h, stride, _ptr(kl), _ptr(counts), cap,
+                                               _ptr(desc)))
+        return [desc[f, :counts[f]].copy() for f in range(n)]
+
+    # -- BinaryDescriptorMatcher::match / knnMatch ------------------------------
+    def match_batch(self, queries, trains, k=1):
+        n = len(queries)
+        assert len(trains) == n
+        cap_q = max(1, max(len(q) for q in queries))
+        cap_t = max(1, max(len(t) for t in trains))
+        q = np.zeros((n, cap_q, 32), np.uint8)
+        t = np.zeros((n, cap_t, 32), np.uint8)
+        nq = np.array([len(x) for x in queries], np.int32)
+        nt = np.array([len(x) for x in trains], np.int32)
+        for i in range(n):
+            q[i, :nq[i]] = np.asarray(queries[i], np.uint8).reshape(-1, 32)
+            t[i, :nt[i]] = np.asarray(trains[i], np.uint8).reshape(-1, 32)
+        out = np.zeros((n, cap_q, k), DMATCH_DTYPE)
+        self._ck(self._L.vpl_match_batch(self._h, _ptr(q), _ptr(nq), cap_q, _ptr(t), _ptr(nt), cap_t, n, k,
+                                         _ptr(out)))
+        return [out[i, :nq[i]].copy() for i in range(n)]
+
+    # -- fused front end ---------------------------------------------------------
+    def frontend_batch(self, frames, scale=2, num_octaves=1, k=1, chain=False, cap=None):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        cap = cap or self.max_lines
+        kl = np.zeros((n, cap), KEYLINE_DTYPE)
+        counts = np.zeros(n, np.int32)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        m = np.zeros((n, cap, max(k, 1)), DMATCH_DTYPE)
+        self._ck(self._L.vpl_frontend_batch(self._h, ptrs, n, w, h, stride, scale, num_octaves, k, int(chain),
+                                            _ptr(kl), _ptr(counts), cap, _ptr(desc), _ptr(m)))
+        return ([kl[f, :counts[f]].copy() for f in range(n)], [desc[f, :counts[f]].copy() for f in range(n)],
+                [m[f, :counts[f]].copy() for f in range(n)])
+
+    def submit(self, slot, frames, scale=2, num_octaves=1, k=1, chain=False):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        self._ck(self._L.vpl_frontend_submit(self._h, slot, ptrs, n, w, h, stride, scale, num_octaves, k,
+                                             int(chain)))
+        return n
+
+    def collect_into(self, slot, kl, counts, cap, desc, matches):
+        self._ck(self._L.vpl_frontend_collect(self._h, slot, _ptr(kl), _ptr(counts), cap, _ptr(desc),
+                                              _ptr(matches)))
+
+    def run_resident(self, slot, k=1):
+        self._ck(self._L.vpl_frontend_run_resident(self._h, slot, k))
+
+    def sync(self):
+        self._ck(self._L.vpl_sync(self._h))
+
+    # -- raw stages ----------------------------------------------------------------
+    def lsd_raw(self, img, cap=1 << 15):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.zeros(cap, SEGMENT_DTYPE)
+        cnt = C.c_int32(0)
+        self._ck(self._L.vpl_lsd_raw(self._h, _ptr(img), w, h, w, _ptr(out), C.byref(cnt), cap))
+        return out[:cnt.value].copy()
+
+    def debug_stage(self, which, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        buf = np.zeros(w * h * 4 + 64, np.uint8)
+        ow, oh = C.c_int32(0), C.c_int32(0)
+        self._ck(self._L.vpl_debug_stage(self._h, which, _ptr(img), w, h, w, _ptr(buf), buf.nbytes, C.byref(ow),
+                                         C.byref(oh)))
+        ow, oh = ow.value, oh.value
+        if which in (0, 1, 3):
+            return buf[:ow * oh].reshape(oh, ow).copy()
+        if which == 2:
+            g = buf[:ow * oh * 4].view(np.int16).reshape(oh, ow, 2)
+            return g[..., 0].copy(), g[..., 1].copy()
+        if which == 4:
+            return buf[:ow * oh * 4].view(np.float32).reshape(oh, ow).copy()
+        return buf[:ow * 4].view(np.int32).copy()
+
+    # -- measurement -----------------------------------------------------------------
+    def stage_times(self):
+        ms = np.zeros(len(STAGES), np.float64)
+        ln = np.zeros(len(STAGES), np.int64)
+        self._ck(self._L.vpl_get_stage_times(self._h, _ptr(ms), _ptr(ln)))
+        return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(STAGES)}
+
+    def reset_stage_times(self):
+        self._ck(self._L.vpl_reset_stage_times(self._h))
+
+    def kernel_launches(self):
+        return int(self._L.vpl_kernel_launches(self._h))
+
+
+def device_count():
+    return int(load().vpl_device_count())

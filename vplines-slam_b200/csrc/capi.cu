@@ -1,0 +1,833 @@
+// capi.cu -- context, memory plan and the C ABI of libvplines_b200.so (see
+// include/vpl_capi.h for what each entry point replaces in the reference).
+//
+// One context = one GPU, `num_slots` independent batch slots.  A slot owns every
+// device buffer a batch needs (layout in vpl_common.cuh), a pinned staging area
+// and a stream, so consecutive batches overlap: while slot s runs its region
+// engine, slot s+1 uploads and runs its streaming kernels.  Nothing is allocated
+// after vpl_create.  There is no CPU path.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "vpl_common.cuh"
+
+using namespace vpl;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct OctBuf {
+  uint8_t* pyr = nullptr;
+  short2* grad = nullptr;
+  uint8_t* scl = nullptr;
+  float* ang = nullptr;
+  Pix* pix = nullptr;
+  int* ord = nullptr;
+  int* n_ord = nullptr;
+  RegEnt* reg = nullptr;
+  RectCand* cand = nullptr;
+  int* n_cand = nullptr;
+  unsigned int* maxq = nullptr;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;        // everything of the batch finished
+  cudaEvent_t last_ready = nullptr;  // last-frame descriptors copied to last_desc
+  cudaEvent_t match_done = nullptr;  // this slot's match kernels finished
+  cudaEvent_t ev[VPL_NUM_STAGES][2];
+  bool ev_used[VPL_NUM_STAGES];
+  uint8_t* d_img = nullptr;
+  OctBuf oct[kMaxOctaves];
+  VplKeyLine* d_kl = nullptr;
+  int* d_counts = nullptr;
+  uint8_t* d_desc = nullptr;
+  VplDMatch* d_match = nullptr;
+  uint8_t* d_last_desc = nullptr;  // descriptors of the last frame of the batch
+  int* d_last_count = nullptr;
+  int* d_flags = nullptr;  // [0] candidate overflow, [1] keyline overflow
+  VplSegment* d_seg = nullptr;
+  int* d_seg_count = nullptr;
+  // pinned host staging
+  uint8_t* h_img = nullptr;
+  VplKeyLine* h_kl = nullptr;
+  int* h_counts = nullptr;
+  uint8_t* h_desc = nullptr;
+  VplDMatch* h_match = nullptr;
+  int* h_flags = nullptr;
+  // state of the batch in flight
+  int n = 0, w = 0, h = 0, num_octaves = 0, scale = 2, k = 0;
+  bool in_flight = false;
+  int last_consumer = -1;  // slot whose match reads our last_desc
+};
+
+}  // namespace
+
+struct VplContext {
+  VplConfig cfg;
+  int cand_cap = 0;
+  int max_k = 8;
+  std::vector<Slot> slots;
+  std::string err;
+  LsdConst lc;
+  double stage_ms[VPL_NUM_STAGES];
+  int64_t stage_launches[VPL_NUM_STAGES];
+  int64_t launches = 0;
+  int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
+  bool have_prev = false;
+};
+
+namespace {
+
+int fail(VplContext* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, VPL_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t count) {
+  return cudaMalloc((void**)p, count * sizeof(T) + 256);
+}
+template <typename T>
+cudaError_t hmalloc(T** p, size_t count) {
+  return cudaMallocHost((void**)p, count * sizeof(T) + 256);
+}
+
+void octave_geom(int w, int h, int o, int& wo, int& ho, int& ws, int& hs) {
+  wo = w; ho = h;
+  for (int i = 0; i < o; ++i) { wo /= 2; ho /= 2; }
+  ws = (int)lrint(wo * 0.8);
+  hs = (int)lrint(ho * 0.8);
+}
+
+// Built with FMA contraction?  (a*b+c differs between fused and unfused here.)
+__global__ void fma_probe_kernel(float a, float b, float c, float* out) { *out = a * b + c; }
+
+struct StageTimer {
+  Slot& s;
+  VplContext* c;
+  int stage;
+  bool on;
+  StageTimer(VplContext* c_, Slot& s_, int stage_) : s(s_), c(c_), stage(stage_), on(c_->cfg.profile != 0) {
+    if (on) { cudaEventRecord(s.ev[stage][0], s.stream); }
+  }
+  void launches(int n) { c->launches += n; c->stage_launches[stage] += n; }
+  ~StageTimer() {
+    if (on) { cudaEventRecord(s.ev[stage][1], s.stream); s.ev_used[stage] = true; }
+  }
+};
+
+void harvest_times(VplContext* c, Slot& s) {
+  if (!c->cfg.profile) return;
+  for (int i = 0; i < VPL_NUM_STAGES; ++i) {
+    if (!s.ev_used[i]) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.ev[i][0], s.ev[i][1]) == cudaSuccess) c->stage_ms[i] += ms;
+    s.ev_used[i] = false;
+  }
+}
+
+int check_dims(VplContext* c, int n, int w, int h, int num_octaves, int scale) {
+  if (!c) return VPL_E_INVALID;
+  if (n < 0 || w <= 0 || h <= 0) return fail(c, VPL_E_INVALID, "bad batch/image size n=%d w=%d h=%d", n, w, h);
+  if (n > c->cfg.max_batch) return fail(c, VPL_E_CAPACITY, "batch %d > max_batch %d", n, c->cfg.max_batch);
+  if (w > c->cfg.max_width || h > c->cfg.max_height)
+    return fail(c, VPL_E_CAPACITY, "image %dx%d larger than the context's %dx%d", w, h, c->cfg.max_width,
+                c->cfg.max_height);
+  if (num_octaves < 1 || num_octaves > c->cfg.max_octaves)
+    return fail(c, VPL_E_CAPACITY, "numOctaves %d outside 1..%d", num_octaves, c->cfg.max_octaves);
+  if (num_octaves > 1 && scale != 2)
+    return fail(c, VPL_E_INVALID, "scale must be 2 with more than one octave (pyrDown), got %d", scale);
+  if (scale < 1) return fail(c, VPL_E_INVALID, "scale must be >= 1");
+  int wo, ho, ws, hs;
+  octave_geom(w, h, num_octaves - 1, wo, ho, ws, hs);
+  if (ws < 4 || hs < 4) return fail(c, VPL_E_INVALID, "image too small for %d octaves", num_octaves);
+  return VPL_OK;
+}
+
+// ---- pipeline pieces (all asynchronous on the slot stream) -------------------
+void stage_images(Slot& s, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
+  for (int f = 0; f < n; ++f) {
+    uint8_t* dst = s.h_img + (size_t)f * w * h;
+    if (stride == (size_t)w) memcpy(dst, imgs[f], (size_t)w * h);
+    else
+      for (int y = 0; y < h; ++y) memcpy(dst + (size_t)y * w, imgs[f] + (size_t)y * stride, (size_t)w);
+  }
+}
+
+void run_pyramid(VplContext* c, Slot& s, int do_blur) {
+  StageTimer t(c, s, VPL_STAGE_PYRAMID);
+  launch_blur5_sobel(s.d_img, s.oct[0].pyr, s.oct[0].grad, s.w, s.h, s.n, do_blur, s.stream);
+  t.launches(1);
+  int wo = s.w, ho = s.h;
+  for (int o = 1; o < s.num_octaves; ++o) {
+    launch_pyrdown(s.oct[o - 1].pyr, s.oct[o].pyr, wo, ho, s.n, s.stream);
+    wo /= 2; ho /= 2;
+    launch_sobel(s.oct[o].pyr, s.oct[o].grad, wo, ho, s.n, s.stream);
+    t.launches(2);
+  }
+}
+
+void fill_engine_args(VplContext* c, Slot& s, EngineArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.num_octaves = s.num_octaves;
+  a.cand_cap = c->cand_cap;
+  a.batch = s.n;
+  a.lc = c->lc;
+  a.overflow = s.d_flags;
+  for (int o = 0; o < s.num_octaves; ++o) {
+    int wo, ho, ws, hs;
+    octave_geom(s.w, s.h, o, wo, ho, ws, hs);
+    EngineOct& e = a.oct[o];
+    e.pix = s.oct[o].pix; e.ang = s.oct[o].ang; e.ord = s.oct[o].ord; e.n_ord = s.oct[o].n_ord;
+    e.reg = s.oct[o].reg; e.cand = s.oct[o].cand; e.n_cand = s.oct[o].n_cand;
+    e.ws = ws; e.hs = hs;
+    e.log_nt = 5 * (log10((double)ws) + log10((double)hs)) / 2 + log10(11.0);
+    e.min_reg_size = (int)(-e.log_nt / log10(c->lc.p));
+  }
+}
+
+// LSD on the pyramid already in s.oct[*].pyr -> candidates validated (cand, n_cand)
+void run_lsd(VplContext* c, Slot& s) {
+  cudaMemsetAsync(s.d_flags, 0, 2 * sizeof(int), s.stream);
+  int wo[kMaxOctaves], ho[kMaxOctaves], ws[kMaxOctaves], hs[kMaxOctaves];
+  for (int o = 0; o < s.num_octaves; ++o) {
+    octave_geom(s.w, s.h, o, wo[o], ho[o], ws[o], hs[o]);
+    cudaMemsetAsync(s.oct[o].maxq, 0, (size_t)s.n * sizeof(unsigned int), s.stream);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_SCALE);
+    for (int o = 0; o < s.num_octaves; ++o)
+      launch_scale08(s.oct[o].pyr, s.oct[o].scl, wo[o], ho[o], ws[o], hs[o], s.n, s.stream);
+    t.launches(s.num_octaves);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_ANGLE);
+    for (int o = 0; o < s.num_octaves; ++o)
+      launch_ll_angle(s.oct[o].scl, s.oct[o].ang, s.oct[o].pix, s.oct[o].maxq, ws[o], hs[o], s.n, c->lc.rho, s.stream);
+    t.launches(s.num_octaves);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_ORDER);
+    for (int o = 0; o < s.num_octaves; ++o)
+      launch_order(s.oct[o].scl, s.oct[o].maxq, s.oct[o].ord, s.oct[o].n_ord, ws[o], hs[o], s.n, c->lc.rho, s.stream);
+    t.launches(s.num_octaves);
+  }
+  EngineArgs a;
+  fill_engine_args(c, s, a);
+  {
+    StageTimer t(c, s, VPL_STAGE_REGION);
+    launch_region_engine(a, s.stream);
+    t.launches(1);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_NFA);
+    launch_rect_nfa(a, s.stream);
+    t.launches(1);
+  }
+}
+
+void run_pack(VplContext* c, Slot& s) {
+  StageTimer t(c, s, VPL_STAGE_PACK);
+  PackArgs p;
+  memset(&p, 0, sizeof(p));
+  p.num_octaves = s.num_octaves;
+  p.scale = s.scale;
+  p.cand_cap = c->cand_cap;
+  for (int o = 0; o < s.num_octaves; ++o) {
+    int wo, ho, ws, hs;
+    octave_geom(s.w, s.h, o, wo, ho, ws, hs);
+    p.cand[o] = s.oct[o].cand; p.n_cand[o] = s.oct[o].n_cand;
+    p.w[o] = wo; p.h[o] = ho;
+  }
+  launch_pack_keylines(p, s.d_kl, s.d_counts, s.d_flags + 1, c->cfg.max_lines, s.n, s.stream);
+  t.launches(1);
+}
+
+void run_lbd(VplContext* c, Slot& s, int num_octaves) {
+  StageTimer t(c, s, VPL_STAGE_LBD);
+  LbdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.num_octaves = num_octaves;
+  for (int o = 0; o < num_octaves; ++o) {
+    int wo, ho, ws, hs;
+    octave_geom(s.w, s.h, o, wo, ho, ws, hs);
+    a.grad[o] = s.oct[o].grad; a.w[o] = wo; a.h[o] = ho;
+  }
+  launch_lbd(a, s.d_kl, s.d_counts, c->cfg.max_lines, s.d_desc, s.n, s.stream);
+  t.launches(1);
+}
+
+__global__ void fill_nomatch_kernel(VplDMatch* m, const int* counts, int k) {
+  int n = counts[0] * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    VplDMatch d;
+    d.queryIdx = i / k; d.trainIdx = -1; d.imgIdx = 0; d.distance = 3.402823466e+38f;
+    m[i] = d;
+  }
+}
+
+int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
+  Slot& s = c->slots[slot];
+  const int cap = c->cfg.max_lines;
+  run_pyramid(c, s, c->cfg.blur_first ? 1 : 0);
+  run_lsd(c, s);
+  run_pack(c, s);
+  if (!c->cfg.blur_first) run_pyramid(c, s, 1);  // BinaryDescriptor always blurs its own pyramid
+  run_lbd(c, s, s.num_octaves);
+  if (k > 0) {
+    StageTimer t(c, s, VPL_STAGE_MATCH);
+    if (s.n > 1) {
+      launch_hamming_knn(s.d_desc + (size_t)cap * 32, s.d_counts + 1, cap, s.d_desc, s.d_counts, cap, s.n - 1, k,
+                         s.d_match + (size_t)cap * k, s.stream);
+      t.launches(1);
+    }
+    if (chain && c->have_prev) {
+      // frame 0 against the last frame of the previously submitted batch
+      Slot& p = c->slots[c->prev_slot];
+      if (c->prev_slot != slot) {
+        cudaStreamWaitEvent(s.stream, p.last_ready, 0);
+        p.last_consumer = slot;
+      }
+      launch_hamming_knn(s.d_desc, s.d_counts, cap, p.d_last_desc, p.d_last_count, cap, 1, k, s.d_match, s.stream);
+    } else {
+      fill_nomatch_kernel<<<8, 256, 0, s.stream>>>(s.d_match, s.d_counts, k);
+    }
+    t.launches(1);
+    cudaEventRecord(s.match_done, s.stream);
+  }
+  // keep the last frame's descriptors for the next batch (after our own chain match
+  // has read the previous content, and after any other slot that still reads it)
+  if (s.last_consumer >= 0) {
+    cudaStreamWaitEvent(s.stream, c->slots[s.last_consumer].match_done, 0);
+    s.last_consumer = -1;
+  }
+  cudaMemcpyAsync(s.d_last_desc, s.d_desc + (size_t)(s.n - 1) * cap * 32, (size_t)cap * 32,
+                  cudaMemcpyDeviceToDevice, s.stream);
+  cudaMemcpyAsync(s.d_last_count, s.d_counts + (s.n - 1), sizeof(int), cudaMemcpyDeviceToDevice, s.stream);
+  cudaEventRecord(s.last_ready, s.stream);
+  c->prev_slot = slot;
+  c->have_prev = true;
+  s.k = k;
+  return VPL_OK;
+}
+
+int enqueue_download(VplContext* c, Slot& s, bool kl, bool desc, bool match) {
+  StageTimer t(c, s, VPL_STAGE_D2H);
+  const size_t cap = (size_t)c->cfg.max_lines;
+  cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_flags, s.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  if (kl) cudaMemcpyAsync(s.h_kl, s.d_kl, (size_t)s.n * cap * sizeof(VplKeyLine), cudaMemcpyDeviceToHost, s.stream);
+  if (desc) cudaMemcpyAsync(s.h_desc, s.d_desc, (size_t)s.n * cap * 32, cudaMemcpyDeviceToHost, s.stream);
+  if (match && s.k > 0)
+    cudaMemcpyAsync(s.h_match, s.d_match, (size_t)s.n * cap * s.k * sizeof(VplDMatch), cudaMemcpyDeviceToHost,
+                    s.stream);
+  return VPL_OK;
+}
+
+int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
+  if (stride < (size_t)w) return fail(c, VPL_E_INVALID, "stride %zu < width %d", stride, w);
+  for (int f = 0; f < n; ++f)
+    if (!imgs || !imgs[f]) return fail(c, VPL_E_INVALID, "null image pointer at frame %d", f);
+  stage_images(s, imgs, n, w, h, stride);
+  StageTimer t(c, s, VPL_STAGE_H2D);
+  CK(c, cudaMemcpyAsync(s.d_img, s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
+  return VPL_OK;
+}
+
+int finish(VplContext* c, Slot& s) {
+  CK(c, cudaStreamSynchronize(s.stream));
+  CK(c, cudaGetLastError());
+  harvest_times(c, s);
+  s.in_flight = false;
+  return VPL_OK;
+}
+
+void copy_rows(void* dst, const void* src, const int* counts, int n, size_t cap_src, size_t cap_dst, size_t elem,
+               size_t per_line = 1) {
+  for (int f = 0; f < n; ++f) {
+    size_t cnt = (size_t)counts[f] * per_line;
+    memcpy((char*)dst + (size_t)f * cap_dst * per_line * elem, (const char*)src + (size_t)f * cap_src * per_line * elem,
+           cnt * elem);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vpl_version(void) { return "vplines_b200 0.1 (sm_100a)"; }
+
+int vpl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void vpl_default_config(VplConfig* cfg) {
+  if (!cfg) return;
+  cfg->device = 0;
+  cfg->max_width = 752;
+  cfg->max_height = 480;
+  cfg->max_octaves = 1;
+  cfg->max_lines = 2048;
+  cfg->max_batch = 64;
+  cfg->num_slots = 2;
+  cfg->blur_first = 1;
+  cfg->profile = 0;
+}
+
+const char* vpl_last_error(const VplContext* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void vpl_destroy(VplContext* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  for (Slot& s : c->slots) {
+    cudaFree(s.d_img);
+    for (int o = 0; o < kMaxOctaves; ++o) {
+      OctBuf& b = s.oct[o];
+      cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.ord);
+      cudaFree(b.n_ord); cudaFree(b.reg); cudaFree(b.cand); cudaFree(b.n_cand); cudaFree(b.maxq);
+    }
+    cudaFree(s.d_kl); cudaFree(s.d_counts); cudaFree(s.d_desc); cudaFree(s.d_match); cudaFree(s.d_last_desc);
+    cudaFree(s.d_last_count); cudaFree(s.d_flags); cudaFree(s.d_seg); cudaFree(s.d_seg_count);
+    cudaFreeHost(s.h_img); cudaFreeHost(s.h_kl); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_desc);
+    cudaFreeHost(s.h_match); cudaFreeHost(s.h_flags);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.last_ready) cudaEventDestroy(s.last_ready);
+    if (s.match_done) cudaEventDestroy(s.match_done);
+    for (int i = 0; i < VPL_NUM_STAGES; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (s.ev[i][j]) cudaEventDestroy(s.ev[i][j]);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  delete c;
+}
+
+int vpl_create(const VplConfig* cfg, VplContext** out) {
+  if (!cfg || !out) return fail(nullptr, VPL_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->max_width < 8 || cfg->max_height < 8 || cfg->max_octaves < 1 || cfg->max_octaves > kMaxOctaves ||
+      cfg->max_lines < 1 || cfg->max_lines > (1 << 20) - 1 || cfg->max_batch < 1 || cfg->num_slots < 1 ||
+      cfg->num_slots > 4)
+    return fail(nullptr, VPL_E_INVALID, "bad configuration");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, VPL_E_NODEVICE,
+                "no usable CUDA device (count=%d, requested %d, %s): libvplines_b200 has no CPU path", ndev,
+                cfg->device, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  VplContext* c = new VplContext();
+  c->cfg = *cfg;
+  c->cand_cap = 4 * cfg->max_lines;
+  memset(c->stage_ms, 0, sizeof(c->stage_ms));
+  memset(c->stage_launches, 0, sizeof(c->stage_launches));
+  c->lc.prec = VPL_PI * 22.5 / 180;
+  c->lc.p = 22.5 / 180;
+  c->lc.rho = 2.0 / sin(c->lc.prec);
+#define CKC(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      int r_ = fail(nullptr, VPL_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));          \
+      vpl_destroy(c);                                                                              \
+      return r_;                                                                                   \
+    }                                                                                              \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  // refuse to run if the build contracted a*b+c (the exact float sequences need -fmad=false)
+  {
+    float* d = nullptr;
+    CKC(cudaMalloc((void**)&d, sizeof(float)));
+    // (1+2^-12)^2 = 1 + 2^-11 + 2^-24 rounds to 1 + 2^-11: unfused a*b+c is 0, fused 2^-24
+    const float a = 1.0f + 1.0f / 4096.0f, cc = -(1.0f + 1.0f / 2048.0f);
+    fma_probe_kernel<<<1, 1>>>(a, a, cc, d);
+    float r = 1.0f;
+    CKC(cudaMemcpy(&r, d, sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (r != 0.0f) {
+      vpl_destroy(c);
+      return fail(nullptr, VPL_E_INVALID, "library built with FMA contraction (needs nvcc -fmad=false)");
+    }
+  }
+  lbd_init_tables();
+  const size_t B = (size_t)cfg->max_batch, cap = (size_t)cfg->max_lines;
+  const size_t P0 = (size_t)cfg->max_width * cfg->max_height;
+  c->slots.resize(cfg->num_slots);
+  for (Slot& s : c->slots) {
+    memset(s.ev, 0, sizeof(s.ev));
+    memset(s.ev_used, 0, sizeof(s.ev_used));
+    CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&s.last_ready, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&s.match_done, cudaEventDisableTiming));
+    for (int i = 0; i < VPL_NUM_STAGES; ++i)
+      for (int j = 0; j < 2; ++j) CKC(cudaEventCreate(&s.ev[i][j]));
+    CKC(dmalloc(&s.d_img, B * P0));
+    for (int o = 0; o < cfg->max_octaves; ++o) {
+      // worst case over aspect ratios with the same area: size by area with slack
+      size_t Po = (P0 >> (2 * o)) + 64;
+      size_t So = (size_t)((double)Po * 0.64) + 2 * (size_t)(cfg->max_width + cfg->max_height) + 64;
+      OctBuf& b = s.oct[o];
+      CKC(dmalloc(&b.pyr, B * Po));
+      CKC(dmalloc(&b.grad, B * Po));
+      CKC(dmalloc(&b.scl, B * So));
+      CKC(dmalloc(&b.ang, B * So));
+      CKC(dmalloc(&b.pix, B * So));
+      CKC(dmalloc(&b.ord, B * So));
+      CKC(dmalloc(&b.reg, B * So));
+      CKC(dmalloc(&b.n_ord, B));
+      CKC(dmalloc(&b.cand, B * c->cand_cap));
+      CKC(dmalloc(&b.n_cand, B));
+      CKC(dmalloc(&b.maxq, B));
+    }
+    CKC(dmalloc(&s.d_kl, B * cap));
+    CKC(dmalloc(&s.d_counts, B));
+    CKC(dmalloc(&s.d_desc, B * cap * 32));
+    CKC(dmalloc(&s.d_match, B * cap * c->max_k));
+    CKC(dmalloc(&s.d_last_desc, cap * 32));
+    CKC(dmalloc(&s.d_last_count, 1));
+    CKC(dmalloc(&s.d_flags, 4));
+    CKC(dmalloc(&s.d_seg, (size_t)c->cand_cap));
+    CKC(dmalloc(&s.d_seg_count, 1));
+    CKC(hmalloc(&s.h_img, B * P0));
+    CKC(hmalloc(&s.h_kl, B * cap));
+    CKC(hmalloc(&s.h_counts, B));
+    CKC(hmalloc(&s.h_desc, B * cap * 32));
+    CKC(hmalloc(&s.h_match, B * cap * c->max_k));
+    CKC(hmalloc(&s.h_flags, 4));
+  }
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = c;
+  return VPL_OK;
+}
+
+// ---- fused path ---------------------------------------------------------------
+int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                        int scale, int num_octaves, int k, int chain) {
+  int r = check_dims(c, n, w, h, num_octaves, scale);
+  if (r) return r;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (k < 0 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 0..%d", k, c->max_k);
+  if (n == 0) return fail(c, VPL_E_INVALID, "empty batch");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  s.n = n; s.w = w; s.h = h; s.num_octaves = num_octaves; s.scale = scale; s.k = k;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  r = enqueue_frontend(c, slot, k, chain);
+  if (r) return r;
+  enqueue_download(c, s, true, true, true);
+  CK(c, cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t* counts, int cap, uint8_t* desc,
+                         VplDMatch* matches) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight) return fail(c, VPL_E_INVALID, "slot %d has no batch in flight", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = finish(c, s);
+  if (r) return r;
+  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
+  if (s.h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
+  if (counts) {
+    for (int f = 0; f < s.n; ++f) {
+      if (s.h_counts[f] > cap) return fail(c, VPL_E_CAPACITY, "frame %d has %d keylines > cap %d", f, s.h_counts[f], cap);
+      counts[f] = s.h_counts[f];
+    }
+  }
+  const size_t mc = (size_t)c->cfg.max_lines;
+  if (keylines) copy_rows(keylines, s.h_kl, s.h_counts, s.n, mc, (size_t)cap, sizeof(VplKeyLine));
+  if (desc) copy_rows(desc, s.h_desc, s.h_counts, s.n, mc, (size_t)cap, 32);
+  if (matches && s.k > 0) copy_rows(matches, s.h_match, s.h_counts, s.n, mc, (size_t)cap, sizeof(VplDMatch), (size_t)s.k);
+  return VPL_OK;
+}
+
+int vpl_frontend_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int scale,
+                       int num_octaves, int k, int chain, VplKeyLine* keylines, int32_t* counts, int cap,
+                       uint8_t* desc, VplDMatch* matches) {
+  if (!c) return VPL_E_INVALID;
+  // alternate slots so that chaining can read the previous batch's last frame
+  int slot = 0;
+  if (c->slots.size() > 1 && c->have_prev) slot = (c->prev_slot + 1) % (int)c->slots.size();
+  int r = vpl_frontend_submit(c, slot, imgs, n, w, h, stride, scale, num_octaves, k, chain);
+  if (r) return r;
+  return vpl_frontend_collect(c, slot, keylines, counts, cap, desc, matches);
+}
+
+int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no frames: submit+collect a batch first", slot);
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = enqueue_frontend(c, slot, k, 0);
+  if (r) return r;
+  CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_sync(VplContext* c) {
+  if (!c) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots) {
+    CK(c, cudaStreamSynchronize(s.stream));
+    harvest_times(c, s);
+  }
+  CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+// ---- the three OpenCV-shaped calls ----------------------------------------------
+int vpl_lsd_detect_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int scale,
+                         int num_octaves, VplKeyLine* keylines, int32_t* counts, int cap) {
+  int r = check_dims(c, n, w, h, num_octaves, scale);
+  if (r) return r;
+  if (n == 0) return VPL_OK;
+  if (!keylines || !counts) return fail(c, VPL_E_INVALID, "null output");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  s.n = n; s.w = w; s.h = h; s.num_octaves = num_octaves; s.scale = scale; s.k = 0;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  run_pyramid(c, s, c->cfg.blur_first ? 1 : 0);
+  run_lsd(c, s);
+  run_pack(c, s);
+  enqueue_download(c, s, true, false, false);
+  r = finish(c, s);
+  if (r) return r;
+  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
+  if (s.h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
+  for (int f = 0; f < n; ++f) {
+    if (s.h_counts[f] > cap) return fail(c, VPL_E_CAPACITY, "frame %d has %d keylines > cap %d", f, s.h_counts[f], cap);
+    counts[f] = s.h_counts[f];
+  }
+  copy_rows(keylines, s.h_kl, s.h_counts, n, (size_t)c->cfg.max_lines, (size_t)cap, sizeof(VplKeyLine));
+  return VPL_OK;
+}
+
+int vpl_lbd_compute_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                          const VplKeyLine* keylines, const int32_t* counts, int cap, uint8_t* desc) {
+  if (!c) return VPL_E_INVALID;
+  if (!keylines || !counts || !desc) return fail(c, VPL_E_INVALID, "null argument");
+  int max_oct = 0;
+  for (int f = 0; f < n; ++f) {
+    if (counts[f] < 0 || counts[f] > cap || counts[f] > c->cfg.max_lines)
+      return fail(c, VPL_E_CAPACITY, "frame %d: %d keylines (cap %d, max_lines %d)", f, counts[f], cap, c->cfg.max_lines);
+    for (int i = 0; i < counts[f]; ++i) {
+      const VplKeyLine& k = keylines[(size_t)f * cap + i];
+      if (k.octave < 0) return fail(c, VPL_E_INVALID, "negative octave");
+      if (k.octave > max_oct) max_oct = k.octave;
+      if (k.numOfPixels < 0 || k.numOfPixels > 32767) return fail(c, VPL_E_INVALID, "numOfPixels out of range");
+    }
+  }
+  int r = check_dims(c, n, w, h, max_oct + 1, 2);
+  if (r) return r;
+  if (n == 0) return VPL_OK;
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  s.n = n; s.w = w; s.h = h; s.num_octaves = max_oct + 1; s.scale = 2; s.k = 0;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  const size_t mc = (size_t)c->cfg.max_lines;
+  copy_rows(s.h_kl, keylines, counts, n, (size_t)cap, mc, sizeof(VplKeyLine));
+  memcpy(s.h_counts, counts, (size_t)n * sizeof(int));
+  CK(c, cudaMemcpyAsync(s.d_kl, s.h_kl, (size_t)n * mc * sizeof(VplKeyLine), cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaMemcpyAsync(s.d_counts, s.h_counts, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  run_pyramid(c, s, 1);
+  run_lbd(c, s, s.num_octaves);
+  CK(c, cudaMemsetAsync(s.d_flags, 0, 2 * sizeof(int), s.stream));
+  enqueue_download(c, s, false, true, false);
+  r = finish(c, s);
+  if (r) return r;
+  copy_rows(desc, s.h_desc, counts, n, mc, (size_t)cap, 32);
+  return VPL_OK;
+}
+
+int vpl_match_batch(VplContext* c, const uint8_t* q, const int32_t* nq, int cap_q, const uint8_t* t,
+                    const int32_t* nt, int cap_t, int n_pairs, int k, VplDMatch* out) {
+  if (!c) return VPL_E_INVALID;
+  if (!q || !nq || !t || !nt || !out) return fail(c, VPL_E_INVALID, "null argument");
+  if (k < 1 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 1..%d", k, c->max_k);
+  if (n_pairs < 0 || cap_q < 1 || cap_t < 1) return fail(c, VPL_E_INVALID, "bad sizes");
+  if (n_pairs == 0) return VPL_OK;
+  // the train set reuses the descriptor buffer of slot 0, the query set that of the
+  // last slot (or the second half of the same buffer if there is one slot)
+  const size_t mc = (size_t)c->cfg.max_lines, B = (size_t)c->cfg.max_batch;
+  if ((size_t)cap_q > mc * B / std::max<size_t>(1, (size_t)n_pairs) ||
+      (size_t)cap_t > mc * B / std::max<size_t>(1, (size_t)n_pairs))
+    return fail(c, VPL_E_CAPACITY, "n_pairs*cap exceeds max_batch*max_lines");
+  if (n_pairs > c->cfg.max_batch) return fail(c, VPL_E_CAPACITY, "n_pairs %d > max_batch", n_pairs);
+  if (cap_t >= (1 << 20)) return fail(c, VPL_E_CAPACITY, "train set too large");
+  for (int p = 0; p < n_pairs; ++p)
+    if (nq[p] < 0 || nq[p] > cap_q || nt[p] < 0 || nt[p] > cap_t) return fail(c, VPL_E_INVALID, "bad counts in pair %d", p);
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  // device scratch: q -> d_desc, t -> reuse d_kl region (B*cap*68 B >= B*cap*32 B), counts -> d_counts / n_ord
+  uint8_t* d_q = s.d_desc;
+  uint8_t* d_t = reinterpret_cast<uint8_t*>(s.d_kl);
+  int* d_nq = s.d_counts;
+  int* d_nt = s.oct[0].n_ord;
+  const size_t qb = (size_t)n_pairs * cap_q * 32, tb = (size_t)n_pairs * cap_t * 32;
+  memcpy(s.h_desc, q, qb);
+  memcpy(s.h_kl, t, tb);
+  memcpy(s.h_counts, nq, (size_t)n_pairs * sizeof(int));
+  CK(c, cudaMemcpyAsync(d_q, s.h_desc, qb, cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaMemcpyAsync(d_t, s.h_kl, tb, cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaMemcpyAsync(d_nq, s.h_counts, (size_t)n_pairs * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaStreamSynchronize(s.stream));
+  memcpy(s.h_counts, nt, (size_t)n_pairs * sizeof(int));
+  CK(c, cudaMemcpyAsync(d_nt, s.h_counts, (size_t)n_pairs * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  {
+    StageTimer tm(c, s, VPL_STAGE_MATCH);
+    launch_hamming_knn(d_q, d_nq, cap_q, d_t, d_nt, cap_t, n_pairs, k, s.d_match, s.stream);
+    tm.launches(1);
+  }
+  const size_t ob = (size_t)n_pairs * cap_q * k * sizeof(VplDMatch);
+  CK(c, cudaMemcpyAsync(s.h_match, s.d_match, ob, cudaMemcpyDeviceToHost, s.stream));
+  int r = finish(c, s);
+  if (r) return r;
+  for (int p = 0; p < n_pairs; ++p)
+    memcpy(out + (size_t)p * cap_q * k, s.h_match + (size_t)p * cap_q * k, (size_t)nq[p] * k * sizeof(VplDMatch));
+  return VPL_OK;
+}
+
+// ---- raw stages for the parity tests -------------------------------------------
+int vpl_lsd_raw(VplContext* c, const uint8_t* img, int w, int h, size_t stride, VplSegment* out, int32_t* count,
+                int cap) {
+  int r = check_dims(c, 1, w, h, 1, 1);
+  if (r) return r;
+  if (!img || !out || !count) return fail(c, VPL_E_INVALID, "null argument");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  s.n = 1; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 1; s.k = 0;
+  const uint8_t* one[1] = {img};
+  r = upload(c, s, one, 1, w, h, stride);
+  if (r) return r;
+  run_pyramid(c, s, 0);  // no pyramid blur: plain cv::LineSegmentDetector on the image
+  run_lsd(c, s);
+  launch_pack_segments(s.oct[0].cand, s.oct[0].n_cand, c->cand_cap, s.d_seg, s.d_seg_count, c->cand_cap, 1, s.stream);
+  c->launches += 1;
+  int n = 0;
+  CK(c, cudaMemcpyAsync(&n, s.d_seg_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  r = finish(c, s);
+  if (r) return r;
+  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "more than %d LSD candidates", c->cand_cap);
+  *count = n;
+  if (n > cap) return fail(c, VPL_E_CAPACITY, "%d segments > cap %d", n, cap);
+  CK(c, cudaMemcpy(out, s.d_seg, (size_t)n * sizeof(VplSegment), cudaMemcpyDeviceToHost));
+  return VPL_OK;
+}
+
+int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, size_t stride, void* out,
+                    size_t out_bytes, int32_t* out_w, int32_t* out_h) {
+  int r = check_dims(c, 1, w, h, which == 1 ? 2 : 1, 2);
+  if (r) return r;
+  if (!img || !out || !out_w || !out_h) return fail(c, VPL_E_INVALID, "null argument");
+  if (which == 1 && c->cfg.max_octaves < 2) return fail(c, VPL_E_CAPACITY, "pyrDown stage needs max_octaves >= 2");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  s.n = 1; s.w = w; s.h = h; s.num_octaves = (which == 1) ? 2 : 1; s.scale = 2; s.k = 0;
+  const uint8_t* one[1] = {img};
+  r = upload(c, s, one, 1, w, h, stride);
+  if (r) return r;
+  int wo, ho, ws, hs;
+  octave_geom(w, h, 0, wo, ho, ws, hs);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  int n_ord = 0;
+  switch (which) {
+    case 0:  // GaussianBlur 5x5
+      run_pyramid(c, s, 1);
+      src = s.oct[0].pyr; bytes = (size_t)w * h; *out_w = w; *out_h = h;
+      break;
+    case 1:  // pyrDown of the UNBLURRED image
+      s.num_octaves = 2;
+      run_pyramid(c, s, 0);
+      src = s.oct[1].pyr; bytes = (size_t)(w / 2) * (h / 2); *out_w = w / 2; *out_h = h / 2;
+      break;
+    case 2:  // Sobel of the unblurred image
+      run_pyramid(c, s, 0);
+      src = s.oct[0].grad; bytes = (size_t)w * h * sizeof(short2); *out_w = w; *out_h = h;
+      break;
+    case 3:
+    case 4:
+    case 5:
+      run_pyramid(c, s, 0);
+      CK(c, cudaMemsetAsync(s.oct[0].maxq, 0, sizeof(unsigned int), s.stream));
+      launch_scale08(s.oct[0].pyr, s.oct[0].scl, w, h, ws, hs, 1, s.stream);
+      c->launches += 1;
+      if (which == 3) { src = s.oct[0].scl; bytes = (size_t)ws * hs; *out_w = ws; *out_h = hs; break; }
+      launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].pix, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
+      c->launches += 1;
+      if (which == 4) { src = s.oct[0].ang; bytes = (size_t)ws * hs * sizeof(float); *out_w = ws; *out_h = hs; break; }
+      launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, ws, hs, 1, c->lc.rho, s.stream);
+      c->launches += 1;
+      CK(c, cudaMemcpyAsync(&n_ord, s.oct[0].n_ord, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      CK(c, cudaStreamSynchronize(s.stream));
+      src = s.oct[0].ord; bytes = (size_t)n_ord * sizeof(int); *out_w = n_ord; *out_h = 1;
+      break;
+    default:
+      return fail(c, VPL_E_INVALID, "unknown stage %d", which);
+  }
+  r = finish(c, s);
+  if (r) return r;
+  if (bytes > out_bytes) return fail(c, VPL_E_CAPACITY, "output needs %zu bytes, %zu given", bytes, out_bytes);
+  CK(c, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+  return VPL_OK;
+}
+
+// ---- measurement -------------------------------------------------------------------
+int vpl_get_stage_times(VplContext* c, double* ms, int64_t* launches) {
+  if (!c) return VPL_E_INVALID;
+  for (int i = 0; i < VPL_NUM_STAGES; ++i) {
+    if (ms) ms[i] = c->stage_ms[i];
+    if (launches) launches[i] = c->stage_launches[i];
+  }
+  return VPL_OK;
+}
+
+int vpl_reset_stage_times(VplContext* c) {
+  if (!c) return VPL_E_INVALID;
+  memset(c->stage_ms, 0, sizeof(c->stage_ms));
+  memset(c->stage_launches, 0, sizeof(c->stage_launches));
+  return VPL_OK;
+}
+
+int64_t vpl_kernel_launches(const VplContext* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// lsd_engine.cu -- LSD region engine (sm_100a): region growing, region -> rectangle,
+// refine (density test, re-grow with tighter tolerance, radius reduction).
+//
+// Restates the main loop of cv::LineSegmentDetectorImpl::flsd and region_grow /
+// region2rect / get_theta / refine / reduce_region_radius (opencv imgproc lsd.cpp;
+// SURVEY.md Appendix A.4-A.6; CPU restatement oracle/orc_lsd.c).  rect_improve /
+// rect_nfa do not feed back into the `used` map, so they run afterwards in a
+// separate, fully parallel kernel (lsd_nfa.cu) on the candidates emitted here.
+//
+// Execution model: ONE WARP PER (frame, octave).  The seed loop of a frame is
+// sequential by definition (first-come pixel ownership, running float32 mean
+// angle, double sums in list order), so the warp keeps exactly that order and
+// uses its 32 lanes for everything that is order-free:
+//   * seed scan: 32 ordered seeds per step, one 128-bit gather each;
+//   * growth: the 8 neighbours of up to three FIFO pixels are gathered with one
+//     128-bit load per lane (27 lanes); acceptance is then resolved in lane order,
+//     which is exactly the sequential (FIFO, yy, xx) order;
+//   * rectangle sums: per-entry products in parallel, the additions themselves in
+//     list order (shuffle broadcast) so the double results equal the sequential
+//     sums bit for bit;
+//   * min/max projections, used-bit clearing, radius compaction: lane-parallel.
+// Throughput comes from frame-level parallelism (thousands of warps in flight),
+// not from speculation; results are bit-identical to the sequential algorithm.
+//
+// Compile with -fmad=false: the double/float expressions below mirror the CPU
+// sequence operation by operation and must not be contracted.
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+constexpr int RING = 256;  // per-warp FIFO window kept in shared memory
+
+struct Eng {
+  Pix* pix;
+  RegEnt* reg;
+  int* ring;  // shared memory, RING ints
+  int ws, hs;
+  int lane;
+};
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __forceinline__ double dist_d(double x1, double y1, double x2, double y2) {
+  return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+}
+__device__ __forceinline__ double dist_sq_d(double x1, double y1, double x2, double y2) {
+  return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
+}
+__device__ __forceinline__ double angle_diff_signed_d(double a, double b) {
+  double d = a - b;
+  while (d <= -VPL_PI) d += VPL_2PI;
+  while (d > VPL_PI) d -= VPL_2PI;
+  return d;
+}
+
+// isAligned on an angle already converted to radians
+__device__ __forceinline__ bool aligned_rad(double a, double theta, double prec) {
+  double n_theta = theta - a;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > VPL_3_2_PI) {
+    n_theta -= VPL_2PI;
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+// ---------------------------------------------------------------------------
+// region_grow (A.4).  Returns the region size; reg[0..n) holds the region in
+// acceptance order; *reg_angle_out is the final running angle.
+// ---------------------------------------------------------------------------
+__device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angle_out) {
+  const int lane = e.lane, ws = e.ws, hs = e.hs;
+  Pix* pix = e.pix;
+  // seed (uniform load; it is defined and currently unused)
+  Pix sp = pix[seed];
+  float seed_deg = __uint_as_float(sp.ang & 0x7fffffffu);
+  if (lane == 0) {
+    pix[seed].ang = sp.ang | kUsedBit;
+    RegEnt r;
+    r.idx = seed; r.ang = seed_deg; r.q = sp.q; r.pad = 0;
+    e.reg[0] = r;
+    e.ring[0] = seed;
+  }
+  double reg_angle = (double)seed_deg * VPL_DEG2RAD;
+  float sumdx = (float)cos(reg_angle);
+  float sumdy = (float)sin(reg_angle);
+  int n = 1, i = 0;
+  __syncwarp();
+
+  const int g = lane / 9;       // which FIFO pixel of this step (0..2), lanes 27..31 idle
+  const int k = lane - 9 * g;   // neighbour 0..8 in (yy outer, xx inner) order
+  const int ddx = k % 3 - 1, ddy = k / 3 - 1;
+
+  while (i < n) {
+    int take = n - i;
+    if (take > 3) take = 3;
+    const bool act = (lane < 27) && (g < take) && (k != 4);
+    int nidx = -1;
+    uint32_t ab = 0xffffffffu;
+    float cs = 0.f, sn = 0.f;
+    uint32_t q = 0;
+    if (act) {
+      int j = i + g;
+      int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : e.reg[j].idx;
+      int py = cur / ws, px = cur - py * ws;
+      int nx = px + ddx, ny = py + ddy;
+      if (nx >= 0 && nx < ws && ny >= 0 && ny < hs) {
+        nidx = ny * ws + nx;
+        Pix p = pix[nidx];
+        ab = p.ang; cs = p.cs; sn = p.sn; q = p.q;
+      }
+    }
+    bool cand = (nidx >= 0) && !(ab & kUsedBit);
+    const double a = (double)__uint_as_float(ab) * VPL_DEG2RAD;
+    // resolve acceptances in lane order == sequential order
+    while (true) {
+      bool al = cand && aligned_rad(a, reg_angle, prec);
+      unsigned m = __ballot_sync(0xffffffffu, al);
+      if (m == 0) break;
+      int f = __ffs(m) - 1;
+      int acc = __shfl_sync(0xffffffffu, nidx, f);
+      if (lane == f) {
+        pix[nidx].ang = ab | kUsedBit;
+        RegEnt r;
+        r.idx = nidx; r.ang = __uint_as_float(ab); r.q = q; r.pad = 0;
+        e.reg[n] = r;
+        e.ring[n & (RING - 1)] = nidx;
+      }
+      float fcs = __shfl_sync(0xffffffffu, cs, f);
+      float fsn = __shfl_sync(0xffffffffu, sn, f);
+      sumdx += fcs;
+      sumdy += fsn;
+      reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * VPL_DEG2RAD;
+      ++n;
+      // lanes up to f were tested (and rejected) with the angle valid at their
+      // turn; the same pixel reached through a later FIFO entry is now used.
+      cand = cand && (lane > f) && (nidx != acc);
+    }
+    __syncwarp();
+    i += take;
+  }
+  *reg_angle_out = reg_angle;
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// region2rect + get_theta (A.5).  Sequential double sums in list order.
+// ---------------------------------------------------------------------------
+__device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
+  const int lane = e.lane, ws = e.ws;
+  double x = 0, y = 0, sum = 0;
+  for (int base = 0; base < n; base += 32) {
+    int j = base + lane;
+    double wx = 0, wy = 0, wt = 0;
+    if (j < n) {
+      RegEnt r = e.reg[j];
+      int py = r.idx / ws, px = r.idx - py * ws;
+      wt = sqrt((double)(int)r.q / 4.0);
+      wx = (double)px * wt;
+      wy = (double)py * wt;
+    }
+    int cnt = min(32, n - base);
+    for (int t = 0; t < cnt; ++t) {
+      x += shfl_d(wx, t);
+      y += shfl_d(wy, t);
+      sum += shfl_d(wt, t);
+    }
+  }
+  x /= sum;
+  y /= sum;
+  // get_theta
+  double Ixx = 0.0, Iyy = 0.0, Ixy = 0.0;
+  for (int base = 0; base < n; base += 32) {
+    int j = base + lane;
+    double t1 = 0, t2 = 0, t3 = 0;
+    if (j < n) {
+      RegEnt r = e.reg[j];
+      int py = r.idx / ws, px = r.idx - py * ws;
+      double weight = sqrt((double)(int)r.q / 4.0);
+      double dx = (double)px - x, dy = (double)py - y;
+      t1 = dy * dy * weight;
+      t2 = dx * dx * weight;
+      t3 = dx * dy * weight;
+    }
+    int cnt = min(32, n - base);
+    for (int t = 0; t < cnt; ++t) {
+      Ixx += shfl_d(t1, t);
+      Iyy += shfl_d(t2, t);
+      Ixy -= shfl_d(t3, t);
+    }
+  }
+  double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+  theta *= VPL_DEG2RAD;
+  if (fabs(angle_diff_signed_d(theta, reg_angle)) > prec) theta += VPL_PI;
+  double dx = cos(theta), dy = sin(theta);
+  // length / width: min and max are order-free
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int j = lane; j < n; j += 32) {
+    RegEnt r = e.reg[j];
+    int py = r.idx / ws, px = r.idx - py * ws;
+    double regdx = (double)px - x, regdy = (double)py - y;
+    double l = regdx * dx + regdy * dy;
+    double w = regdy * dx - regdx * dy;
+    l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+    w_max = fmax(w_max, w); w_min = fmin(w_min, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, o));
+    l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
+    w_max = fmax(w_max, __shfl_xor_sync(0xffffffffu, w_max, o));
+    w_min = fmin(w_min, __shfl_xor_sync(0xffffffffu, w_min, o));
+  }
+  rec.x1 = x + l_min * dx;
+  rec.y1 = y + l_min * dy;
+  rec.x2 = x + l_max * dx;
+  rec.y2 = y + l_max * dy;
+  rec.width = w_max - w_min;
+  rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy;
+  rec.prec = prec; rec.p = p;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+// ---------------------------------------------------------------------------
+// reduce_region_radius (A.6): "swap with last, pop, re-test" removal of the points
+// farther than the radius.  Its result is: kept points stay in place; the k-th
+// hole (ascending) among the first n_in positions receives the k-th kept point
+// counted from the end.  Done as three lane-parallel passes.
+// ---------------------------------------------------------------------------
+__device__ int compact_radius(const Eng& e, int n, double xc, double yc, double radSq) {
+  const int lane = e.lane, ws = e.ws;
+  const unsigned lt = (1u << lane) - 1u;
+  int n_in = 0;
+  for (int base = 0; base < n; base += 32) {
+    int j = base + lane;
+    bool in = false;
+    if (j < n) {
+      RegEnt r = e.reg[j];
+      int py = r.idx / ws, px = r.idx - py * ws;
+      in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
+      if (!in) e.pix[r.idx].ang &= ~kUsedBit;
+    }
+    n_in += __popc(__ballot_sync(0xffffffffu, in));
+  }
+  if (n_in == n) return n;
+  // fillers: kept points at positions >= n_in, from the end; k-th goes to n-1-k
+  int kf = 0;
+  for (int top = n; top > n_in; top -= 32) {
+    int j = top - 1 - lane;
+    bool in = false;
+    RegEnt r;
+    r.idx = 0; r.ang = 0; r.q = 0; r.pad = 0;
+    if (j >= n_in) {
+      r = e.reg[j];
+      int py = r.idx / ws, px = r.idx - py * ws;
+      in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    int rank = kf + __popc(m & lt);
+    __syncwarp();
+    if (in) e.reg[n - 1 - rank] = r;
+    kf += __popc(m);
+    __syncwarp();
+  }
+  // holes among the first n_in positions, ascending
+  int kh = 0;
+  for (int base = 0; base < n_in; base += 32) {
+    int j = base + lane;
+    bool hole = false;
+    if (j < n_in) {
+      RegEnt r = e.reg[j];
+      int py = r.idx / ws, px = r.idx - py * ws;
+      hole = dist_sq_d(xc, yc, (double)px, (double)py) > radSq;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hole);
+    int rank = kh + __popc(m & lt);
+    if (hole) e.reg[j] = e.reg[n - 1 - rank];
+    kh += __popc(m);
+  }
+  __syncwarp();
+  return n_in;
+}
+
+__device__ bool reduce_region_radius(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
+                                     double density, double density_th) {
+  int s0 = e.reg[0].idx;
+  int yc_i = s0 / e.ws, xc_i = s0 - yc_i * e.ws;
+  double xc = (double)xc_i, yc = (double)yc_i;
+  double radSq1 = dist_sq_d(xc, yc, rec.x1, rec.y1);
+  double radSq2 = dist_sq_d(xc, yc, rec.x2, rec.y2);
+  double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+  while (density < density_th) {
+    radSq *= 0.75 * 0.75;
+    n = compact_radius(e, n, xc, yc, radSq);
+    if (n < 2) return false;
+    region2rect(e, n, reg_angle, prec, p, rec);
+    density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  }
+  return true;
+}
+
+__device__ bool refine(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
+                       double density_th) {
+  const int lane = e.lane, ws = e.ws;
+  double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density >= density_th) return true;
+  RegEnt r0 = e.reg[0];
+  int yc_i = r0.idx / ws, xc_i = r0.idx - yc_i * ws;
+  double xc = (double)xc_i, yc = (double)yc_i;
+  double ang_c = (double)r0.ang * VPL_DEG2RAD;
+  double sum = 0, s_sum = 0;
+  int cnt = 0;
+  for (int base = 0; base < n; base += 32) {
+    int j = base + lane;
+    bool flag = false;
+    double ang_d = 0, sq = 0;
+    if (j < n) {
+      RegEnt r = e.reg[j];
+      e.pix[r.idx].ang &= ~kUsedBit;
+      int py = r.idx / ws, px = r.idx - py * ws;
+      if (dist_d(xc, yc, (double)px, (double)py) < rec.width) {
+        flag = true;
+        ang_d = angle_diff_signed_d((double)r.ang * VPL_DEG2RAD, ang_c);
+        sq = ang_d * ang_d;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    while (m) {
+      int t = __ffs(m) - 1;
+      m &= m - 1;
+      sum += shfl_d(ang_d, t);
+      s_sum += shfl_d(sq, t);
+      ++cnt;
+    }
+  }
+  __syncwarp();
+  double mean_angle = sum / (double)cnt;
+  double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+  n = region_grow(e, r0.idx, tau, &reg_angle);
+  if (n < 2) return false;
+  region2rect(e, n, reg_angle, prec, p, rec);
+  density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+  if (density < density_th) return reduce_region_radius(e, n, reg_angle, prec, p, rec, density, density_th);
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// The engine kernel: blockDim = 32 (one warp), grid = (batch, num_octaves).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+region_engine_kernel(EngineArgs A) {
+  __shared__ int s_ring[RING];
+  const int f = blockIdx.x;
+  const EngineOct& O = A.oct[blockIdx.y];
+  const size_t npx = (size_t)O.ws * O.hs;
+  Eng e;
+  e.pix = O.pix + (size_t)f * npx;
+  e.reg = O.reg + (size_t)f * npx;
+  e.ring = s_ring;
+  e.ws = O.ws; e.hs = O.hs;
+  e.lane = threadIdx.x;
+  const int lane = e.lane;
+  const int* ord = O.ord + (size_t)f * npx;
+  const int n_ord = O.n_ord[f];
+  RectCand* cand = O.cand + (size_t)f * A.cand_cap;
+  const double prec = A.lc.prec, p = A.lc.p;
+  const double DENSITY_TH = 0.7;
+  int n_cand = 0;
+
+  for (int base = 0; base < n_ord; base += 32) {
+    int my = (base + lane < n_ord) ? ord[base + lane] : -1;
+    bool free_ = false;
+    if (my >= 0) free_ = !(e.pix[my].ang & kUsedBit);
+    unsigned todo = __ballot_sync(0xffffffffu, free_);
+    while (todo) {
+      int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      int seed = __shfl_sync(0xffffffffu, my, l);
+      // the seed may have been absorbed by a region grown earlier in this chunk
+      if (e.pix[seed].ang & kUsedBit) continue;
+      double reg_angle;
+      int n = region_grow(e, seed, prec, &reg_angle);
+      if (n < O.min_reg_size) continue;
+      RectCand rec;
+      region2rect(e, n, reg_angle, prec, p, rec);
+      if (!refine(e, n, reg_angle, prec, p, rec, DENSITY_TH)) continue;
+      if (n_cand < A.cand_cap) {
+        if (lane == 0) {
+          rec.nfa = -1.0; rec.accepted = 0; rec.pad = 0;
+          cand[n_cand] = rec;
+        }
+      } else if (lane == 0) {
+        *A.overflow = 1;
+      }
+      ++n_cand;
+    }
+  }
+  if (lane == 0) O.n_cand[f] = n_cand < A.cand_cap ? n_cand : A.cand_cap;
+}
+
+void launch_region_engine(const EngineArgs& a, cudaStream_t st) {
+  dim3 grid(a.batch, a.num_octaves);
+  region_engine_kernel<<<grid, 32, 0, st>>>(a);
+}
+
+}  // namespace vpl

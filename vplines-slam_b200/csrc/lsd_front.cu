@@ -1,0 +1,179 @@
+// lsd_front.cu -- LSD stages before region growing (sm_100a):
+//   K3 ll_angle : 2x2 gradient, level-line angle (cv::fastAtan2), per-frame max
+//   K4 order    : pseudo-ordering = stable counting sort of the defined pixels by
+//                 descending gradient bin (1024 bins), raster order inside a bin
+// Restates cv::LineSegmentDetectorImpl::ll_angle (opencv imgproc lsd.cpp; SURVEY.md
+// Appendix A.3; CPU restatement: oracle/orc_lsd.c ll_angle).  Exact: integer
+// gradient, one float32 polynomial without FMA contraction, IEEE double sqrt/mul.
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+// gradient of the scaled image at (x,y), x<ws-1, y<hs-1
+__device__ __forceinline__ void grad2x2(const uint8_t* __restrict__ s, int ws, int x, int y, int& gx, int& gy) {
+  const uint8_t* r0 = s + (size_t)y * ws + x;
+  const uint8_t* r1 = r0 + ws;
+  int a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r1), d = __ldg(r1 + 1);
+  int DA = d - a, BC = b - c;
+  gx = DA + BC;
+  gy = DA - BC;
+}
+
+// ---------------------------------------------------------------------------
+// K3.  One thread per pixel.  Writes ang (4 B) and the engine record pix (16 B)
+// of every pixel, reduces max(gx^2+gy^2) per frame with one atomicMax per warp.
+// Algorithmic bytes: read S, write 20 S.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* __restrict__ pix,
+                unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const size_t fo = (size_t)blockIdx.z * ws * hs;
+  unsigned int q = 0;
+  if (x < ws && y < hs) {
+    float a = kNotDefDeg;
+    Pix u;
+    u.ang = __float_as_uint(kNotDefDeg);
+    u.cs = 0.f; u.sn = 0.f; u.q = 0u;
+    if (x < ws - 1 && y < hs - 1) {
+      int gx, gy;
+      grad2x2(scl + fo, ws, x, y, gx, gy);
+      unsigned int qq = (unsigned int)(gx * gx + gy * gy);
+      double norm = sqrt((double)(int)qq / 4.0);
+      if (!(norm <= rho)) {
+        q = qq;
+        a = fast_atan2_deg((float)gx, (float)-gy);
+        // cos(float(angle)) / sin(float(angle)) of the radian angle, float overloads:
+        // correctly rounded float of the double function.
+        float ar = (float)((double)a * VPL_DEG2RAD);
+        u.ang = __float_as_uint(a);
+        u.cs = (float)cos((double)ar);
+        u.sn = (float)sin((double)ar);
+        u.q = qq;
+      }
+    }
+    ang[fo + (size_t)y * ws + x] = a;
+    pix[fo + (size_t)y * ws + x] = u;
+  }
+  // warp max -> one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q = max(q, __shfl_xor_sync(0xffffffffu, q, o));
+  if ((threadIdx.x & 31) == 0 && q > 0) atomicMax(maxq + blockIdx.z, q);
+}
+
+void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
+                     int batch, double rho, cudaStream_t st) {
+  dim3 grid((ws + 31) / 32, (hs + 7) / 8, batch);
+  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, maxq, ws, hs, rho);
+}
+
+// ---------------------------------------------------------------------------
+// K4.  One 1024-thread CTA per frame.  Warp w owns the raster segment
+// [w*C, (w+1)*C) of the frame; phase A builds per-warp histograms in shared
+// memory, phase B turns them into per-(warp,bin) output offsets (bins descending,
+// warps ascending => raster order inside a bin), phase C re-walks the segment and
+// scatters with a match_any rank.  No global atomics, deterministic.
+// Algorithmic bytes: read 2 S (twice the u8 image), write 4 B per defined pixel.
+// ---------------------------------------------------------------------------
+constexpr int ORD_THREADS = 1024;
+constexpr int ORD_WARPS = ORD_THREADS / 32;
+
+__device__ __forceinline__ int pixel_bin(const uint8_t* __restrict__ s, int ws, int hs, int idx, double rho,
+                                         double bin_coef) {
+  int y = idx / ws, x = idx - y * ws;
+  if (x >= ws - 1 || y >= hs - 1) return -1;
+  int gx, gy;
+  grad2x2(s, ws, x, y, gx, gy);
+  double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
+  if (norm <= rho) return -1;
+  return (int)(norm * bin_coef);
+}
+
+__global__ void __launch_bounds__(ORD_THREADS, 1)
+order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ maxq, int* __restrict__ ord,
+             int* __restrict__ n_ord, int ws, int hs, double rho) {
+  extern __shared__ unsigned int s_cnt[];  // [ORD_WARPS][kBins]
+  __shared__ unsigned int s_scan[ORD_WARPS];
+  const int f = blockIdx.x;
+  const uint8_t* s = scl + (size_t)f * ws * hs;
+  int* out = ord + (size_t)f * ws * hs;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = ws * hs;
+  const unsigned int mq = maxq[f];
+  if (mq == 0) {
+    if (tid == 0) n_ord[f] = 0;
+    return;
+  }
+  const double max_grad = sqrt((double)(int)mq / 4.0);
+  const double bin_coef = (double)(kBins - 1) / max_grad;
+
+  for (int i = tid; i < ORD_WARPS * kBins; i += ORD_THREADS) s_cnt[i] = 0;
+  __syncthreads();
+
+  const int C = (N + ORD_WARPS - 1) / ORD_WARPS;
+  const int beg = wid * C, end = min(N, beg + C);
+  unsigned int* mycnt = s_cnt + wid * kBins;
+
+  // phase A: per-warp histogram (warp-private => plain increments via match_any)
+  for (int base = beg; base < end; base += 32) {
+    int idx = base + lane;
+    int b = (idx < end) ? pixel_bin(s, ws, hs, idx, rho, bin_coef) : -1;
+    unsigned int grp = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // phase B: thread b owns bin b.  total[b], then suffix scan over bins.
+  unsigned int total = 0;
+  for (int w = 0; w < ORD_WARPS; ++w) total += s_cnt[w * kBins + tid];
+  // inclusive suffix sum over bins (higher bins first): scan reversed index r = 1023 - tid
+  // implemented as an inclusive prefix scan over threads in reversed order.
+  unsigned int v = total;
+  // warp-level inclusive scan from high lane to low lane
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  if (lane == 0) s_scan[wid] = v;  // sum of this warp's 32 bins
+  __syncthreads();
+  unsigned int higher = 0;  // bins in higher warps
+  for (int w = wid + 1; w < ORD_WARPS; ++w) higher += s_scan[w];
+  // start[b] = number of points in bins > b
+  unsigned int start = higher + v - total;
+  if (tid == 0) n_ord[f] = (int)(higher + v);
+  // per-(warp,bin) offsets, in place
+  unsigned int run = start;
+  for (int w = 0; w < ORD_WARPS; ++w) {
+    unsigned int c = s_cnt[w * kBins + tid];
+    s_cnt[w * kBins + tid] = run;
+    run += c;
+  }
+  __syncthreads();
+
+  // phase C: stable scatter
+  for (int base = beg; base < end; base += 32) {
+    int idx = base + lane;
+    int b = (idx < end) ? pixel_bin(s, ws, hs, idx, rho, bin_coef) : -1;
+    unsigned int grp = __match_any_sync(0xffffffffu, b);
+    if (b >= 0) {
+      unsigned int rank = __popc(grp & ((1u << lane) - 1u));
+      unsigned int off = mycnt[b];
+      out[off + rank] = idx;
+    }
+    __syncwarp();
+    if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
+    __syncwarp();
+  }
+}
+
+void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, int ws, int hs,
+                  int batch, double rho, cudaStream_t st) {
+  const size_t smem = (size_t)ORD_WARPS * kBins * sizeof(unsigned int);
+  cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  order_kernel<<<batch, ORD_THREADS, smem, st>>>(scl, maxq, ord, n_ord, ws, hs, rho);
+}
+
+}  // namespace vpl

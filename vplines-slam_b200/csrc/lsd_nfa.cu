@@ -1,0 +1,433 @@
+// lsd_nfa.cu -- rectangle NFA validation (rect_improve / rect_nfa / nfa) and the
+// deterministic compaction + KeyLine packing (sm_100a).
+//
+// Restates cv::LineSegmentDetectorImpl::rect_improve / rect_nfa / nfa (opencv
+// imgproc lsd.cpp, cv2 4.13 behaviour: double vertices, ceil-guarded slopes;
+// SURVEY.md Appendix A.7; the nfa/log_gamma formulas are the ones the reference
+// also carries at line_matching/src/edline_detector.h:210-348) and
+// LSDDetector::detectImpl's KeyLine packing (opencv_contrib 3.4 LSDDetector.cpp;
+// CPU restatement oracle/orc_lsd.c, oracle/orc_lbd.c).
+//
+// rect_improve never touches the `used` map, so every candidate rectangle of
+// every frame is validated independently: ONE WARP PER CANDIDATE, lanes over the
+// rows (or the columns, for flat rectangles) of the scanned rectangle.  Scans
+// that share a geometry (the initial test and the five "finer precision" steps,
+// and again the last five) are folded into one pass with several thresholds.
+// Compaction keeps seed order: one warp per frame, ballot prefix.
+#include <float.h>
+
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+__device__ __forceinline__ bool double_equal_d(double a, double b) {
+  if (a == b) return true;
+  double abs_diff = fabs(a - b);
+  double aa = fabs(a), bb = fabs(b);
+  double abs_max = aa > bb ? aa : bb;
+  if (abs_max < DBL_MIN) abs_max = DBL_MIN;
+  return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
+}
+
+__device__ double log_gamma_lanczos_d(double x) {
+  const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705,
+                       1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+  double b = 0;
+  for (int n = 0; n < 7; ++n) {
+    a -= log(x + (double)n);
+    b += q[n] * pow(x, (double)n);
+  }
+  return a + log(b);
+}
+__device__ double log_gamma_windschitl_d(double x) {
+  return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+}
+__device__ __forceinline__ double log_gamma_d(double x) {
+  return x > 15.0 ? log_gamma_windschitl_d(x) : log_gamma_lanczos_d(x);
+}
+
+// per-lane scalar; lanes may carry different (n,k,p)
+__device__ double nfa_d(int n, int k, double p, double LOG_NT) {
+  if (n == 0 || k == 0) return -LOG_NT;
+  if (n == k) return -LOG_NT - (double)n * log10(p);
+  double p_term = p / (1 - p);
+  double log1term = log_gamma_d((double)n + 1) - log_gamma_d((double)k + 1) - log_gamma_d((double)(n - k) + 1) +
+                    (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+  double term = exp(log1term);
+  if (double_equal_d(term, 0)) {
+    if (k > n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+    else return -LOG_NT;
+  }
+  double bin_tail = term;
+  const double tolerance = 0.1;
+  for (int i = k + 1; i <= n; ++i) {
+    double bin_term = (double)(n - i + 1) / (double)i;
+    double mult_term = bin_term * p_term;
+    term *= mult_term;
+    bin_tail += term;
+    if (bin_term < 1) {
+      double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+      if (err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+    }
+  }
+  return -log10(bin_tail) - LOG_NT;
+}
+
+struct RGeo {
+  double x1, y1, x2, y2, width, dx, dy, theta;
+};
+
+// Count the pixels inside the rectangle and, for each of np thresholds, those
+// aligned with theta within precs[t].  Integer results: order-free.
+constexpr int NT = 6;
+__device__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r, const double* precs,
+                           int np, int lane, int& total_out, int* alg_out) {
+  double half_width = r.width / 2.0;
+  double dyhw = r.dy * half_width;
+  double dxhw = r.dx * half_width;
+  double vx[4], vy[4];
+  vx[0] = r.x1 - dyhw; vy[0] = r.y1 + dxhw;
+  vx[1] = r.x2 - dyhw; vy[1] = r.y2 + dxhw;
+  vx[2] = r.x2 + dyhw; vy[2] = r.y2 - dxhw;
+  vx[3] = r.x1 + dyhw; vy[3] = r.y1 - dxhw;
+  int off = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    double by = (off == 0) ? vy[0] : (off == 1) ? vy[1] : (off == 2) ? vy[2] : vy[3];
+    double bx = (off == 0) ? vx[0] : (off == 1) ? vx[1] : (off == 2) ? vx[2] : vx[3];
+    if (vy[i] < by || (vy[i] == by && vx[i] < bx)) off = i;
+  }
+  double ox[4], oy[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int s = (off + i) & 3;
+    ox[i] = (s == 0) ? vx[0] : (s == 1) ? vx[1] : (s == 2) ? vx[2] : vx[3];
+    oy[i] = (s == 0) ? vy[0] : (s == 1) ? vy[1] : (s == 2) ? vy[2] : vy[3];
+  }
+  const int c0 = (int)ceil(oy[0]), c1 = (int)ceil(oy[1]), c2 = (int)ceil(oy[2]), c3 = (int)ceil(oy[3]);
+  const double flstep = (c0 != c1) ? (ox[1] - ox[0]) / (oy[1] - oy[0]) : 0;
+  const double slstep = (c1 != c2) ? (ox[2] - ox[1]) / (oy[2] - oy[1]) : 0;
+  const double frstep = (c0 != c3) ? (ox[3] - ox[0]) / (oy[3] - oy[0]) : 0;
+  const double srstep = (c3 != c2) ? (ox[2] - ox[3]) / (oy[2] - oy[3]) : 0;
+  const int ys = c0, ye = c2;
+  const int n_rows = ye - ys + 1;
+  int total = 0;
+  int alg[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) alg[t] = 0;
+
+  const bool by_row = n_rows >= 16;
+  const int row_step = by_row ? 32 : 1;
+  for (int rr = by_row ? lane : 0; rr < n_rows; rr += row_step) {
+    int y = ys + rr;
+    if (y < 0 || y >= hs) continue;
+    double left = (y <= c1) ? ox[0] + ((double)y - oy[0]) * flstep : ox[1] + ((double)y - oy[1]) * slstep;
+    double right = (y < c3) ? ox[0] + ((double)y - oy[0]) * frstep : ox[3] + ((double)y - oy[3]) * srstep;
+    int xs = (int)ceil(left), xe = (int)right;
+    if (xs < 0) xs = 0;
+    if (xe > ws - 1) xe = ws - 1;
+    const float* row = ang + (size_t)y * ws;
+    for (int x = by_row ? xs : xs + lane; x <= xe; x += by_row ? 1 : 32) {
+      ++total;
+      float ad = __ldg(row + x);
+      if (ad >= 0.f) {
+        double a = (double)ad * VPL_DEG2RAD;
+        double n_theta = r.theta - a;
+        if (n_theta < 0) n_theta = -n_theta;
+        if (n_theta > VPL_3_2_PI) {
+          n_theta -= VPL_2PI;
+          if (n_theta < 0) n_theta = -n_theta;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          if (t < np && n_theta <= precs[t]) ++alg[t];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) alg[t] += __shfl_xor_sync(0xffffffffu, alg[t], o);
+  }
+  total_out = total;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) alg_out[t] = alg[t];
+}
+
+struct RState {  // the fields rect_improve mutates
+  RGeo g;
+  double prec, p;
+};
+
+__device__ __forceinline__ double rect_nfa1(const float* ang, int ws, int hs, const RState& r, double log_nt,
+                                            int lane) {
+  double precs[NT];
+  precs[0] = r.prec;
+#pragma unroll
+  for (int t = 1; t < NT; ++t) precs[t] = 0;
+  int total, alg[NT];
+  rect_count(ang, ws, hs, r.g, precs, 1, lane, total, alg);
+  return nfa_d(total, alg[0], r.p, log_nt);
+}
+
+constexpr int NFA_WARPS = 4;
+
+__global__ void __launch_bounds__(NFA_WARPS * 32)
+rect_nfa_kernel(EngineArgs A) {
+  const EngineOct& O = A.oct[blockIdx.z];
+  const int f = blockIdx.y;
+  const int ci = blockIdx.x * NFA_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ci >= O.n_cand[f]) return;
+  RectCand* cp = O.cand + (size_t)f * A.cand_cap + ci;
+  const float* ang = O.ang + (size_t)f * O.ws * O.hs;
+  const int ws = O.ws, hs = O.hs;
+  const double LOG_NT = O.log_nt;
+  const double LOG_EPS = 0;
+  const double delta = 0.5, delta_2 = delta / 2.0;
+
+  RState rec;
+  rec.g.x1 = cp->x1; rec.g.y1 = cp->y1; rec.g.x2 = cp->x2; rec.g.y2 = cp->y2;
+  rec.g.width = cp->width; rec.g.dx = cp->dx; rec.g.dy = cp->dy; rec.g.theta = cp->theta;
+  rec.prec = cp->prec; rec.p = cp->p;
+
+  double log_nfa;
+  {
+    // initial test + "finer precision" x5 share the geometry: one scan, six thresholds
+    double precs[NT], ps[NT];
+    precs[0] = rec.prec; ps[0] = rec.p;
+    double pp = rec.p;
+#pragma unroll
+    for (int t = 1; t < NT; ++t) {
+      pp /= 2;
+      ps[t] = pp;
+      precs[t] = pp * VPL_PI;
+    }
+    int total, alg[NT];
+    rect_count(ang, ws, hs, rec.g, precs, NT, lane, total, alg);
+    // lane t evaluates nfa(total, alg[t], ps[t])
+    int myk = 0;
+    double myp = ps[0];
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      if (lane == t) { myk = alg[t]; myp = ps[t]; }
+    double myv = nfa_d(total, myk, myp, LOG_NT);
+    log_nfa = __shfl_sync(0xffffffffu, myv, 0);
+    if (!(log_nfa > LOG_EPS)) {
+      RState r = rec;
+      for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        r.prec = r.p * VPL_PI;
+        double v = __shfl_sync(0xffffffffu, myv, n + 1);
+        if (v > log_nfa) { log_nfa = v; rec = r; }
+      }
+    }
+  }
+  if (!(log_nfa > LOG_EPS)) {
+    // reduce width
+    RState r = rec;
+    for (int n = 0; n < 5; ++n) {
+      if ((r.g.width - delta) >= 0.5) {
+        r.g.width -= delta;
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+  }
+  if (!(log_nfa > LOG_EPS)) {
+    // reduce one side
+    RState r = rec;
+    for (int n = 0; n < 5; ++n) {
+      if ((r.g.width - delta) >= 0.5) {
+        r.g.x1 += -r.g.dy * delta_2; r.g.y1 += r.g.dx * delta_2;
+        r.g.x2 += -r.g.dy * delta_2; r.g.y2 += r.g.dx * delta_2;
+        r.g.width -= delta;
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+  }
+  if (!(log_nfa > LOG_EPS)) {
+    // reduce the other side
+    RState r = rec;
+    for (int n = 0; n < 5; ++n) {
+      if ((r.g.width - delta) >= 0.5) {
+        r.g.x1 -= -r.g.dy * delta_2; r.g.y1 -= r.g.dx * delta_2;
+        r.g.x2 -= -r.g.dy * delta_2; r.g.y2 -= r.g.dx * delta_2;
+        r.g.width -= delta;
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+  }
+  if (!(log_nfa > LOG_EPS)) {
+    // finer precision again: geometry fixed, five thresholds in one scan
+    RState r = rec;
+    if ((r.g.width - delta) >= 0.5) {
+      double precs[NT], ps[NT];
+      double pp = r.p;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        pp /= 2;
+        ps[t] = pp;
+        precs[t] = pp * VPL_PI;
+      }
+      precs[5] = 0; ps[5] = pp;
+      int total, alg[NT];
+      rect_count(ang, ws, hs, r.g, precs, 5, lane, total, alg);
+      int myk = 0;
+      double myp = ps[0];
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (lane == t) { myk = alg[t]; myp = ps[t]; }
+      double myv = nfa_d(total, myk, myp, LOG_NT);
+      for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        r.prec = r.p * VPL_PI;
+        double v = __shfl_sync(0xffffffffu, myv, n);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+  }
+  if (lane == 0) {
+    cp->x1 = rec.g.x1; cp->y1 = rec.g.y1; cp->x2 = rec.g.x2; cp->y2 = rec.g.y2;
+    cp->width = rec.g.width; cp->prec = rec.prec; cp->p = rec.p;
+    cp->nfa = log_nfa;
+    cp->accepted = (log_nfa > LOG_EPS) ? 1 : 0;
+  }
+}
+
+void launch_rect_nfa(const EngineArgs& a, cudaStream_t st) {
+  dim3 grid((a.cand_cap + NFA_WARPS - 1) / NFA_WARPS, a.batch, a.num_octaves);
+  rect_nfa_kernel<<<grid, NFA_WARPS * 32, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------
+// Compaction + KeyLine packing.  One warp per frame; octaves in order, candidates
+// in seed order => class_id is the running index exactly as LSDDetector assigns it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void final_segment(const RectCand& c, float e[4], double& width) {
+  const double SCALE = 0.8;
+  double x1 = c.x1 + 0.5, y1 = c.y1 + 0.5, x2 = c.x2 + 0.5, y2 = c.y2 + 0.5;
+  x1 /= SCALE; y1 /= SCALE; x2 /= SCALE; y2 /= SCALE;
+  width = c.width / SCALE;
+  e[0] = (float)x1; e[1] = (float)y1; e[2] = (float)x2; e[3] = (float)y2;
+}
+
+struct PackParams {
+  PackArgs a;
+  float octave_scale[kMaxOctaves];
+};
+
+__global__ void __launch_bounds__(32)
+pack_keylines_kernel(PackParams P, VplKeyLine* __restrict__ kl_, int* __restrict__ counts, int* overflow, int cap) {
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1u;
+  VplKeyLine* kl = kl_ + (size_t)f * cap;
+  int nout = 0;
+  for (int o = 0; o < P.a.num_octaves; ++o) {
+    const RectCand* cand = P.a.cand[o] + (size_t)f * P.a.cand_cap;
+    const int nc = P.a.n_cand[o][f];
+    const int cols = P.a.w[o], rows = P.a.h[o];
+    const float octaveScale = P.octave_scale[o];
+    for (int base = 0; base < nc; base += 32) {
+      int j = base + lane;
+      bool acc = (j < nc) && cand[j].accepted;
+      unsigned m = __ballot_sync(0xffffffffu, acc);
+      int pos = nout + __popc(m & lt);
+      if (acc) {
+        if (pos < cap) {
+          float e[4];
+          double width;
+          final_segment(cand[j], e, width);
+          // checkLineExtremes
+          if (e[0] < 0) e[0] = 0;
+          if (e[0] >= cols) e[0] = (float)cols - 1.0f;
+          if (e[2] < 0) e[2] = 0;
+          if (e[2] >= cols) e[2] = (float)cols - 1.0f;
+          if (e[1] < 0) e[1] = 0;
+          if (e[1] >= rows) e[1] = (float)rows - 1.0f;
+          if (e[3] < 0) e[3] = 0;
+          if (e[3] >= rows) e[3] = (float)rows - 1.0f;
+          VplKeyLine k;
+          k.startPointX = e[0] * octaveScale;
+          k.startPointY = e[1] * octaveScale;
+          k.endPointX = e[2] * octaveScale;
+          k.endPointY = e[3] * octaveScale;
+          k.sPointInOctaveX = e[0];
+          k.sPointInOctaveY = e[1];
+          k.ePointInOctaveX = e[2];
+          k.ePointInOctaveY = e[3];
+          double da = (double)(e[0] - e[2]), db = (double)(e[1] - e[3]);
+          k.lineLength = (float)sqrt(da * da + db * db);
+          int ix0 = __float2int_rn(e[0]), iy0 = __float2int_rn(e[1]);
+          int ix1 = __float2int_rn(e[2]), iy1 = __float2int_rn(e[3]);
+          int adx = abs(ix1 - ix0), ady = abs(iy1 - iy0);
+          k.numOfPixels = (adx > ady ? adx : ady) + 1;
+          k.angle = (float)atan2((double)(k.endPointY - k.startPointY), (double)(k.endPointX - k.startPointX));
+          k.class_id = pos;
+          k.octave = o;
+          k.size = (k.endPointX - k.startPointX) * (k.endPointY - k.startPointY);
+          k.response = k.lineLength / (float)(cols > rows ? cols : rows);
+          k.pt_x = (k.endPointX + k.startPointX) / 2;
+          k.pt_y = (k.endPointY + k.startPointY) / 2;
+          kl[pos] = k;
+        } else {
+          *overflow = 1;
+        }
+      }
+      nout += __popc(m);
+    }
+  }
+  if (lane == 0) counts[f] = nout < cap ? nout : cap;
+}
+
+void launch_pack_keylines(const PackArgs& a, VplKeyLine* kl, int* counts, int* overflow, int cap, int batch,
+                          cudaStream_t st) {
+  PackParams P;
+  P.a = a;
+  float s = 1.0f;
+  for (int o = 0; o < kMaxOctaves; ++o) {
+    P.octave_scale[o] = s;  // (float)pow((float)scale, o)
+    s *= (float)a.scale;
+  }
+  pack_keylines_kernel<<<batch, 32, 0, st>>>(P, kl, counts, overflow, cap);
+}
+
+// Raw LSD output (cv::LineSegmentDetector::detect): segments + width/prec/nfa.
+__global__ void __launch_bounds__(32)
+pack_segments_kernel(const RectCand* __restrict__ cand_, const int* __restrict__ n_cand, int cand_cap,
+                     VplSegment* __restrict__ out_, int* __restrict__ count, int cap) {
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1u;
+  const RectCand* cand = cand_ + (size_t)f * cand_cap;
+  VplSegment* out = out_ + (size_t)f * cap;
+  const int nc = n_cand[f];
+  int nout = 0;
+  for (int base = 0; base < nc; base += 32) {
+    int j = base + lane;
+    bool acc = (j < nc) && cand[j].accepted;
+    unsigned m = __ballot_sync(0xffffffffu, acc);
+    int pos = nout + __popc(m & lt);
+    if (acc && pos < cap) {
+      float e[4];
+      double width;
+      final_segment(cand[j], e, width);
+      VplSegment s;
+      s.x1 = e[0]; s.y1 = e[1]; s.x2 = e[2]; s.y2 = e[3];
+      s.width = width; s.prec = cand[j].p; s.nfa = cand[j].nfa;
+      out[pos] = s;
+    }
+    nout += __popc(m);
+  }
+  if (lane == 0) count[f] = nout;
+}
+
+void launch_pack_segments(const RectCand* cand, const int* n_cand, int cand_cap, VplSegment* out, int* count,
+                          int cap, int batch, cudaStream_t st) {
+  pack_segments_kernel<<<batch, 32, 0, st>>>(cand, n_cand, cand_cap, out, count, cap);
+}
+
+}  // namespace vpl

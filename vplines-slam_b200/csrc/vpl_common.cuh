@@ -1,0 +1,162 @@
+// vpl_common.cuh -- shared device/host declarations of libvplines_b200 (sm_100a).
+//
+// Data layout in HBM (one "slot" = one batch of B frames, per octave o):
+//   img      B x H  x W      u8      raw frames (octave 0 only)
+//   pyr[o]   B x Ho x Wo     u8      Gaussian pyramid (octave 0 = blur5(img) if blur_first)
+//   grad[o]  B x Ho x Wo     short2  Sobel (dx,dy) of pyr[o]            (LBD)
+//   scl[o]   B x Hs x Ws     u8      LSD working image: blur7 + 0.8 resize
+//   ang[o]   B x Hs x Ws     f32     level-line angle in degrees, -1024 = NOTDEF (read-only
+//                                    copy for the NFA scans)
+//   pix[o]   B x Hs x Ws     16 B    {angle bits | USED bit31, cosf, sinf, gx^2+gy^2}: one
+//                                    128-bit gather per neighbour in the region engine
+//   ord[o]   B x Hs x Ws     i32     pseudo-ordered seed list (defined pixels only)
+//   reg[o]   B x Hs x Ws     16 B    region scratch of the frame's engine warp
+//   cand[o]  B x cap         rects   post-refine rectangles in seed order
+//   keylines B x cap x 68 B, desc B x cap x 32 B, matches B x cap x k
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vpl_capi.h"
+
+namespace vpl {
+
+constexpr int kMaxOctaves = 4;
+constexpr int kBins = 1024;
+constexpr float kNotDefDeg = -1024.0f;
+constexpr uint32_t kUsedBit = 0x80000000u;
+
+// Per-pixel record of the region engine.  ang: float bits of the level-line angle
+// in degrees ([0,360]); NOTDEF is -1024.0f (bit31 set, so "not a candidate");
+// bit31 set on a defined pixel = USED.  q = gx^2+gy^2 (modgrad = sqrt(q/4)).
+struct __align__(16) Pix {
+  uint32_t ang;
+  float cs, sn;
+  uint32_t q;
+};
+
+struct __align__(16) RegEnt {
+  int idx;
+  float ang;  // degrees
+  uint32_t q;
+  uint32_t pad;
+};
+
+// A rectangle candidate produced by the region engine (cv lsd.cpp `struct rect`).
+struct __align__(16) RectCand {
+  double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
+  double nfa;      // filled by the NFA kernel
+  int accepted;    // filled by the NFA kernel
+  int pad;
+};
+
+// Per-(frame, octave) LSD geometry, constant over a batch.
+struct OctaveGeom {
+  int w, h;          // pyramid image size
+  int ws, hs;        // 0.8-scaled size
+  double log_nt;     // 5*(log10 ws + log10 hs)/2 + log10(11)
+  int min_reg_size;  // int(-log_nt / log10(p))
+};
+
+struct LsdConst {
+  double prec;  // pi * 22.5 / 180
+  double p;     // 22.5 / 180
+  double rho;   // 2 / sin(prec)
+};
+
+#define VPL_DEG2RAD (3.1415926535897932384626433832795 / 180.0)
+#define VPL_PI 3.1415926535897932384626433832795
+#define VPL_3_2_PI 4.71238898038468985769
+#define VPL_2PI 6.28318530717958647692
+
+__host__ __device__ inline int refl101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    else i = 2 * n - 2 - i;
+  }
+  return i;
+}
+
+// cv::fastAtan2 scalar path: float32, explicit round-to-nearest mul/add so that
+// nothing is contracted into an FMA (must equal oracle/orc_prims.c orc_fast_atan2).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale;
+  const float p3 = -0.3258083974640975f * scale;
+  const float p5 = 0.1555786518463281f * scale;
+  const float p7 = -0.04432655554792128f * scale;
+  const float eps = (float)2.2204460492503131e-16;
+  float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// Kernel launchers (host side, defined in the .cu files).
+void launch_blur5_sobel(const uint8_t* img, uint8_t* pyr, short2* grad, int w, int h, int batch,
+                        int do_blur, cudaStream_t st);
+void launch_pyrdown(const uint8_t* src, uint8_t* dst, int w, int h, int batch, cudaStream_t st);
+void launch_sobel(const uint8_t* src, short2* grad, int w, int h, int batch, cudaStream_t st);
+void launch_scale08(const uint8_t* src, uint8_t* dst, int w, int h, int ws, int hs, int batch,
+                    cudaStream_t st);
+void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
+                     int batch, double rho, cudaStream_t st);
+void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, int ws, int hs,
+                  int batch, double rho, cudaStream_t st);
+struct EngineOct {
+  Pix* pix;          // B x hs x ws
+  const float* ang;  // B x hs x ws (NFA kernel)
+  const int* ord;    // B x hs x ws
+  const int* n_ord;  // B
+  RegEnt* reg;       // B x hs x ws
+  RectCand* cand;    // B x cand_cap
+  int* n_cand;       // B
+  int ws, hs;
+  double log_nt;
+  int min_reg_size;
+};
+struct EngineArgs {
+  EngineOct oct[kMaxOctaves];
+  int num_octaves;
+  int cand_cap;
+  int batch;
+  LsdConst lc;
+  int* overflow;  // set to 1 if a frame produced more than cand_cap candidates
+};
+void launch_region_engine(const EngineArgs& a, cudaStream_t st);
+void launch_rect_nfa(const EngineArgs& a, cudaStream_t st);
+struct PackArgs {
+  const RectCand* cand[kMaxOctaves];
+  const int* n_cand[kMaxOctaves];
+  int w[kMaxOctaves], h[kMaxOctaves];
+  int num_octaves;
+  int scale;
+  int cand_cap;
+};
+void launch_pack_keylines(const PackArgs& a, VplKeyLine* kl, int* counts, int* overflow, int cap, int batch,
+                          cudaStream_t st);
+void launch_pack_segments(const RectCand* cand, const int* n_cand, int cand_cap, VplSegment* out, int* count,
+                          int cap, int batch, cudaStream_t st);
+struct LbdArgs {
+  const short2* grad[kMaxOctaves];
+  int w[kMaxOctaves], h[kMaxOctaves];
+  int num_octaves;
+};
+void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, int batch,
+                cudaStream_t st);
+void launch_hamming_knn(const uint8_t* q, const int* nq, int cap_q, const uint8_t* t, const int* nt, int cap_t,
+                        int n_pairs, int k, VplDMatch* out, cudaStream_t st);
+void lbd_init_tables();
+
+}  // namespace vpl
