@@ -157,6 +157,11 @@ int vpl_lsd_raw(VplContext* ctx, const uint8_t* img, int w, int h, size_t stride
 int vpl_debug_stage(VplContext* ctx, int which, const uint8_t* img, int w, int h, size_t stride,
                     void* out, size_t out_bytes, int32_t* out_w, int32_t* out_h);
 
+/* Candidate rectangles of the last vpl_lsd_raw call (post-refine rectangles in seed order;
+ * after NFA validation the geometry is the improved one): 16 doubles each =
+ * x1 y1 x2 y2 width x y theta dx dy prec p nfa accepted 0 0.  count receives the number. */
+int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
+
 /* ---- measurement ------------------------------------------------------------ */
 #define VPL_STAGE_H2D 0
 #define VPL_STAGE_PYRAMID 1   /* blur5+sobel, pyrDown+sobel          */

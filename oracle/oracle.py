@@ -44,6 +44,7 @@ def lib():
         L.orc_lsd_detect.restype = ctypes.c_int
         L.orc_lsd_detector_detect.restype = ctypes.c_int
         L.orc_lsd_stages.restype = ctypes.c_int
+        L.orc_lsd_candidates.restype = ctypes.c_int
         L.orc_lbd_compute.restype = ctypes.c_int
         L.orc_frontend_sequence.restype = ctypes.c_int64
         L.orc_frontend_sequence_mt.restype = ctypes.c_int64
@@ -109,6 +110,13 @@ def lsd_detect(img, refine=2, scale08=True, cap=1 << 16):
                              _p(nf), cap)
     n = min(n, cap)
     return seg[:n].copy(), wd[:n].copy(), pr[:n].copy(), nf[:n].copy()
+
+
+def lsd_candidates(img, cap=1 << 16):
+    img = _u8(img); h, w = img.shape
+    out = np.zeros((cap, 16), np.float64)
+    n = lib().orc_lsd_candidates(_p(img), w, h, _p(out), cap)
+    return out[:min(n, cap)].copy()
 
 
 def lsd_stages(img):

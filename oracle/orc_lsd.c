@@ -13,6 +13,7 @@
  * double sums must not be fused.
  */
 #include "vpl_oracle.h"
+#include "orc_sincos.h"
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -242,7 +243,16 @@ static void region2rect(const Lsd* L, double reg_angle, double prec, double p, R
   x /= sum;
   y /= sum;
   double theta = get_theta(L, x, y, reg_angle, prec);
-  double dx = cos(theta), dy = sin(theta);
+  /* cos/sin through the deterministic correctly-rounded sincos (orc_sincos.h): the
+   * rectangle edges pass through pixel centres, so rect_nfa's ceil()/trunc() limits are
+   * sensitive to the last bit of dx, dy; libm is not correctly rounded in ~0.1 % of
+   * cases and the device library in more.  ORC_LIBM_TRIG=1 restores plain libm. */
+  double dx, dy;
+#ifdef ORC_LIBM_TRIG
+  dx = cos(theta); dy = sin(theta);
+#else
+  vpl_sincos_cr(theta, &dy, &dx);
+#endif
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = 0; i < L->nreg; ++i) {
     double regdx = (double)reg[i].x - x;
@@ -421,6 +431,11 @@ static double rect_improve(const Lsd* L, Rect* rec) {
   return log_nfa;
 }
 
+/* debug sink: candidate rectangles after refine(), before rect_improve():
+ * 16 doubles each = x1 y1 x2 y2 width x y theta dx dy prec p | nfa accepted region_size seed_index */
+static double* g_cand_sink = NULL;
+static int g_cand_cap = 0, g_cand_n = 0;
+
 int orc_lsd_detect(const uint8_t* img, int w0, int h0, int refine_mode, int scale08, float* seg4,
                    double* width_out, double* prec_out, double* nfa_out, int cap) {
   const double ANG_TH = 22.5, QUANT = 2.0, DENSITY_TH = 0.7, LOG_EPS = 0, SCALE = 0.8;
@@ -467,7 +482,16 @@ int orc_lsd_detect(const uint8_t* img, int w0, int h0, int refine_mode, int scal
     if (refine_mode > 0) {
       if (!refine(&L, reg_angle, prec, p, &rec, DENSITY_TH)) continue;
       if (refine_mode >= 2) {
+        double* sink = NULL;
+        if (g_cand_sink && g_cand_n < g_cand_cap) {
+          sink = g_cand_sink + 16 * (size_t)g_cand_n;
+          const double v[12] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p};
+          memcpy(sink, v, sizeof(v));
+          sink[14] = (double)L.nreg; sink[15] = (double)pi;
+        }
+        g_cand_n++;
         log_nfa = rect_improve(&L, &rec);
+        if (sink) { sink[12] = log_nfa; sink[13] = (log_nfa > LOG_EPS) ? 1.0 : 0.0; }
         if (log_nfa <= LOG_EPS) continue;
       }
     }
@@ -532,4 +556,15 @@ int orc_lsd_stages(const uint8_t* img, int w0, int h0, uint8_t* scaled_out, floa
     }
   free(scaled); free(L.angles); free(L.modgrad); free(L.order);
   return n;
+}
+
+/* Candidate dump (see g_cand_sink): runs LSD (ADV, 0.8 scaling) and returns the number of
+ * candidates; out holds 16 doubles per candidate.  Not thread safe (test use only). */
+int orc_lsd_candidates(const uint8_t* img, int w, int h, double* out, int cap) {
+  float* seg = (float*)malloc((size_t)4 * 65536 * sizeof(float));
+  g_cand_sink = out; g_cand_cap = cap; g_cand_n = 0;
+  orc_lsd_detect(img, w, h, 2, 1, seg, NULL, NULL, NULL, 65536);
+  g_cand_sink = NULL;
+  free(seg);
+  return g_cand_n;
 }

@@ -60,6 +60,10 @@ float orc_fast_atan2(float y, float x);
 int orc_lsd_detect(const uint8_t* img, int w, int h, int refine, int scale08,
                    float* seg4, double* width, double* prec, double* nfa, int cap);
 
+/* Candidate rectangles after refine(), before rect_improve (16 doubles each: x1 y1 x2 y2
+ * width x y theta dx dy prec p | final nfa, accepted, region size, seed pixel index). */
+int orc_lsd_candidates(const uint8_t* img, int w, int h, double* out, int cap);
+
 /* Stage dump (0.8-scaled image, angle in degrees / -1024, ordered defined pixels);
  * returns the number of ordered pixels.  Any output may be NULL. */
 int orc_lsd_stages(const uint8_t* img, int w, int h, uint8_t* scaled, float* ang_deg, int* order,

@@ -15,7 +15,7 @@ SOURCES = ["prims.cu", "lsd_front.cu", "lsd_engine.cu", "lsd_nfa.cu", "lbd_match
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "4",
-]
+] + os.environ.get("VPL_EXTRA_NVCC", "").split()
 
 
 def nvcc():

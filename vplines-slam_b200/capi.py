@@ -37,7 +37,7 @@ EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
-    "vpl_debug_stage", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
+    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
 _lib = None
@@ -77,6 +77,7 @@ def load():
     L.vpl_sync.argtypes = [vp]
     L.vpl_lsd_raw.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32]
     L.vpl_debug_stage.argtypes = [vp, i32, vp, i32, i32, sz, vp, sz, vp, vp]
+    L.vpl_debug_candidates.argtypes = [vp, vp, vp, i32]
     L.vpl_get_stage_times.argtypes = [vp, vp, vp]
     L.vpl_reset_stage_times.argtypes = [vp]
     L.vpl_kernel_launches.argtypes = [vp]
@@ -244,6 +245,12 @@ class Context:
         if which == 4:
             return buf[:ow * oh * 4].view(np.float32).reshape(oh, ow).copy()
         return buf[:ow * 4].view(np.int32).copy()
+
+    def debug_candidates(self, cap=1 << 16):
+        out = np.zeros((cap, 16), np.float64)
+        cnt = C.c_int32(0)
+        self._ck(self._L.vpl_debug_candidates(self._h, _ptr(out), C.byref(cnt), cap))
+        return out[:min(cnt.value, cap)].copy()
 
     # -- measurement -----------------------------------------------------------------
     def stage_times(self):

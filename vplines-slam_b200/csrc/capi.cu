@@ -811,6 +811,29 @@ int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, 
   return VPL_OK;
 }
 
+int vpl_debug_candidates(VplContext* c, double* out, int32_t* count, int cap) {
+  if (!c || !out || !count) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  int n = 0;
+  CK(c, cudaMemcpy(&n, s.oct[0].n_cand, sizeof(int), cudaMemcpyDeviceToHost));
+  *count = n;
+  if (n > cap) n = cap;
+  std::vector<RectCand> tmp((size_t)n);
+  CK(c, cudaMemcpy(tmp.data(), s.oct[0].cand, (size_t)n * sizeof(RectCand), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    const RectCand& r = tmp[i];
+    const double v[16] = {r.x1, r.y1, r.x2, r.y2, r.width, r.x, r.y, r.theta, r.dx, r.dy, r.prec, r.p,
+                          r.nfa, (double)r.accepted, 0, 0};
+    memcpy(out + (size_t)16 * i, v, sizeof(v));
+  }
+  return VPL_OK;
+}
+
+#ifdef VPL_DEBUG_NFA
+extern "C" int vpl_debug_set_nfa_cand(int c) { vpl::debug_set_cand(c); return 0; }
+#endif
+
 // ---- measurement -------------------------------------------------------------------
 int vpl_get_stage_times(VplContext* c, double* ms, int64_t* launches) {
   if (!c) return VPL_E_INVALID;

@@ -25,6 +25,7 @@
 // Compile with -fmad=false: the double/float expressions below mirror the CPU
 // sequence operation by operation and must not be contracted.
 #include "vpl_common.cuh"
+#include "vpl_sincos.cuh"
 
 namespace vpl {
 
@@ -194,7 +195,11 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
                                          : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
   theta *= VPL_DEG2RAD;
   if (fabs(angle_diff_signed_d(theta, reg_angle)) > prec) theta += VPL_PI;
-  double dx = cos(theta), dy = sin(theta);
+  // dx = cos(theta), dy = sin(theta) through the deterministic correctly rounded sincos:
+  // rect_nfa's row limits sit within an ulp of integers (the rectangle edges pass through
+  // the centres of its extreme pixels), so the last bit of dx, dy decides pixel membership.
+  double dx, dy;
+  vpl_sincos_cr(theta, &dy, &dx);
   // length / width: min and max are order-free
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int j = lane; j < n; j += 32) {

@@ -15,6 +15,7 @@
 // and again the last five) are folded into one pass with several thresholds.
 // Compaction keeps seed order: one warp per frame, ballot prefix.
 #include <float.h>
+#include <stdio.h>
 
 #include "vpl_common.cuh"
 
@@ -81,6 +82,10 @@ struct RGeo {
 // Count the pixels inside the rectangle and, for each of np thresholds, those
 // aligned with theta within precs[t].  Integer results: order-free.
 constexpr int NT = 6;
+#ifdef VPL_DEBUG_NFA
+__device__ int g_dbg_cand = -1;
+__device__ int g_dbg_now = 0;
+#endif
 __device__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r, const double* precs,
                            int np, int lane, int& total_out, int* alg_out) {
   double half_width = r.width / 2.0;
@@ -127,6 +132,11 @@ __device__ void rect_count(const float* __restrict__ ang, int ws, int hs, const 
     int xs = (int)ceil(left), xe = (int)right;
     if (xs < 0) xs = 0;
     if (xe > ws - 1) xe = ws - 1;
+#ifdef VPL_DEBUG_NFA
+    if (g_dbg_now && (by_row || lane == 0))
+      printf("DBG row y=%d left=%.17g right=%.17g xs=%d xe=%d by_row=%d c=[%d %d %d %d] o0=(%.17g,%.17g) o1=(%.17g,%.17g) o2=(%.17g,%.17g) o3=(%.17g,%.17g)\n",
+             y, left, right, xs, xe, (int)by_row, c0, c1, c2, c3, ox[0], oy[0], ox[1], oy[1], ox[2], oy[2], ox[3], oy[3]);
+#endif
     const float* row = ang + (size_t)y * ws;
     for (int x = by_row ? xs : xs + lane; x <= xe; x += by_row ? 1 : 32) {
       ++total;
@@ -206,7 +216,23 @@ rect_nfa_kernel(EngineArgs A) {
       precs[t] = pp * VPL_PI;
     }
     int total, alg[NT];
+#ifdef VPL_DEBUG_NFA
+    if (ci == g_dbg_cand) {
+      g_dbg_now = 1;
+      if (lane == 0) printf("DBG cand %d geo x1=%.17g y1=%.17g x2=%.17g y2=%.17g w=%.17g dx=%.17g dy=%.17g th=%.17g\n", ci,
+                            rec.g.x1, rec.g.y1, rec.g.x2, rec.g.y2, rec.g.width, rec.g.dx, rec.g.dy, rec.g.theta);
+    }
+    __syncwarp();
+#endif
     rect_count(ang, ws, hs, rec.g, precs, NT, lane, total, alg);
+#ifdef VPL_DEBUG_NFA
+    __syncwarp();
+    if (ci == g_dbg_cand) {
+      if (lane == 0) printf("DBG cand %d total=%d alg=%d %d %d %d %d %d\n", ci, total, alg[0], alg[1], alg[2], alg[3], alg[4], alg[5]);
+      g_dbg_now = 0;
+    }
+    __syncwarp();
+#endif
     // lane t evaluates nfa(total, alg[t], ps[t])
     int myk = 0;
     double myp = ps[0];
@@ -298,6 +324,10 @@ rect_nfa_kernel(EngineArgs A) {
     cp->accepted = (log_nfa > LOG_EPS) ? 1 : 0;
   }
 }
+
+#ifdef VPL_DEBUG_NFA
+void debug_set_cand(int c) { cudaMemcpyToSymbol(g_dbg_cand, &c, sizeof(int)); }
+#endif
 
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st) {
   dim3 grid((a.cand_cap + NFA_WARPS - 1) / NFA_WARPS, a.batch, a.num_octaves);

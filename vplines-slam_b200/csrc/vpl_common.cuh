@@ -158,5 +158,8 @@ void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int c
 void launch_hamming_knn(const uint8_t* q, const int* nq, int cap_q, const uint8_t* t, const int* nt, int cap_t,
                         int n_pairs, int k, VplDMatch* out, cudaStream_t st);
 void lbd_init_tables();
+#ifdef VPL_DEBUG_NFA
+void debug_set_cand(int c);
+#endif
 
 }  // namespace vpl
