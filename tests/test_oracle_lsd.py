@@ -66,5 +66,5 @@ def test_lsd_live_cv2_synthetic(orc, synth, seed):
     assert np.array_equal(seg, lines.reshape(-1, 4))
     assert np.allclose(w2, width.ravel(), rtol=1e-13, atol=0)
     # NFA values are equal unless libm's last-bit error on cos/sin(theta) moved one pixel in or
-    # out of a rectangle in cv2 (see module docstring): allow 1 % of the segments to differ.
-    assert (n2 != nfa.ravel()).mean() <= 0.01
+    # out of a rectangle in cv2 (see module docstring): allow max(1, 1 %) segments to differ.
+    assert (n2 != nfa.ravel()).sum() <= max(1, len(n2) // 100)
