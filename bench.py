@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- line front-end throughput (LSD + LBD + Hamming match), frames/s.
+
+Workload (BASELINE.json configs[1], "C2"): synthetic EuRoC-shaped 752x480 mono frames,
+single-octave LSDDetector::detect + BinaryDescriptor::compute + consecutive-frame
+match (k=1).  One STEP = one batch of --batch frames through the whole hot path.
+
+  value  whole-job frames/s with the batch already resident in HBM (kernels only,
+         results left in HBM), batches pipelined over the context's slots;
+  e2e    the same through the reference-facing C ABI with HOST buffers:
+         vpl_frontend_submit/collect, pinned staging + H2D + kernels + D2H inside the
+         timed region;
+  roofline      dominant kernel (the LSD region engine): algorithmic bytes / its mean
+                launch duration (CUDA events on its own stream) vs the measured HBM peak;
+  cpu_baseline  the CPU oracle (port of the path, oracle/) on the host cores, bounded sample.
+
+`--impl reference` times the CPU implementation of the path alone (the reference's
+own line_descriptor binary cannot be built here: no OpenCV C++ / contrib; the oracle
+port stands in).
+
+Multi-GPU: one process per GPU (torchrun), frames sharded by contiguous range with a
+one-frame halo, no data-path collective; timing is max over ranks.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2_euroc_752x480"
+METRIC = "line front-end frames/sec (LSD+LBD+match) at 752x480"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_frames(n_unique, seed):
+    synth = importlib.import_module("vplines-slam_b200.synth")
+    return synth.config_sequence(WORKLOAD, n_unique, seed=seed)
+
+
+def tile_frames(unique, n):
+    reps = (n + len(unique) - 1) // len(unique)
+    return np.ascontiguousarray(np.concatenate([unique] * reps)[:n])
+
+
+def cpu_baseline(unique, seconds=12.0, threads=None):
+    """The oracle (CPU port of the path) on the host cores: bounded sample of the same frames."""
+    from oracle import oracle as O
+    O.build()
+    threads = threads or os.cpu_count() or 1
+    t = time.time()
+    O.frontend_sequence(unique[:4], num_octaves=1, max_lines=4096, threads=1)
+    per_frame = max((time.time() - t) / 4, 1e-3)
+    n = int(max(threads * 2, min(seconds / per_frame * threads, 4096)))
+    frames = tile_frames(unique, n)
+    t = time.time()
+    total = O.frontend_sequence(frames, num_octaves=1, max_lines=4096, threads=threads)
+    dt = time.time() - t
+    return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{n} frames of {WORKLOAD} ({total} keylines) in {dt:.1f}s; CPU oracle (C port of cv2-4.13 LSD + "
+                      f"opencv_contrib-3.4 LBD + brute-force Hamming), {threads} pthreads, contiguous chunks + 1-frame halo",
+            "single_thread_frames_per_s": 1.0 / per_frame}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores, nothing else."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    unique = make_frames(min(args.unique, 32), args.seed)
+    from oracle import oracle as O
+    O.build()
+    threads = os.cpu_count() or 1
+    t = time.time()
+    O.frontend_sequence(unique[:4], num_octaves=1, max_lines=4096, threads=1)
+    per_frame = max((time.time() - t) / 4, 1e-3)
+    # bounded sample per step: ~6 s of wall time
+    n = int(max(threads * 2, min(6.0 / per_frame * threads, 2048)))
+    frames = tile_frames(unique, n)
+    for _ in range(args.warmup):
+        O.frontend_sequence(frames[:max(threads, n // 4)], num_octaves=1, max_lines=4096, threads=threads)
+    t0 = time.time()
+    for _ in range(args.steps):
+        O.frontend_sequence(frames, num_octaves=1, max_lines=4096, threads=threads)
+    dt = time.time() - t0
+    fps = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": n, "octaves": 1, "match_k": 1,
+                       "note": "CPU oracle port; the reference's OpenCV-3.4 line_descriptor binary is not buildable here"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} frames/step x {args.steps} steps"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="frames per step")
+    ap.add_argument("--slots", type=int, default=2)
+    ap.add_argument("--max-lines", type=int, default=1024)
+    ap.add_argument("--unique", type=int, default=96, help="distinct synthetic frames generated (tiled to fill a batch)")
+    ap.add_argument("--seed", type=int, default=20240601)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    vpl = importlib.import_module("vplines_slam_b200")
+    capi = vpl.capi
+    cfgw = importlib.import_module("vplines-slam_b200.synth").CONFIGS[WORKLOAD]
+    W, H = cfgw["w"], cfgw["h"]
+    B, S, cap, K = args.batch, args.slots, args.max_lines, 1
+
+    # weak scaling: every rank owns `steps*batch` frames of the sequence; its shard starts one
+    # frame early (halo) so that the pair across the shard boundary is matched exactly once.
+    unique = make_frames(args.unique, args.seed + 17 * rank)
+    batch_frames = tile_frames(unique, B)
+    halo = 1 if rank > 0 else 0
+
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap,
+                       max_batch=B + 1, num_slots=S, blur_first=True, profile=True)
+    kl = [np.zeros((B + 1, cap), capi.KEYLINE_DTYPE) for _ in range(S)]
+    counts = [np.zeros(B + 1, np.int32) for _ in range(S)]
+    desc = [np.zeros((B + 1, cap, 32), np.uint8) for _ in range(S)]
+    mt = [np.zeros((B + 1, cap, K), capi.DMATCH_DTYPE) for _ in range(S)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_steps(n_steps, first_has_halo):
+        """n_steps batches through submit/collect, pipelined over the slots."""
+        pending = []
+        lines = 0
+        for i in range(n_steps):
+            s = i % S
+            if len(pending) == S:
+                ps = pending.pop(0)
+                ctx.collect_into(ps, kl[ps], counts[ps], cap, desc[ps], mt[ps])
+            fr = batch_frames
+            if i == 0 and first_has_halo:
+                fr = np.ascontiguousarray(np.concatenate([batch_frames[-1:], batch_frames]))
+            ctx.submit(s, fr, scale=2, num_octaves=1, k=K, chain=(i > 0))
+            pending.append(s)
+        while pending:
+            ps = pending.pop(0)
+            ctx.collect_into(ps, kl[ps], counts[ps], cap, desc[ps], mt[ps])
+            lines = int(counts[ps][:B].sum())
+        return lines
+
+    # ---- warm-up (also leaves a batch resident in every slot)
+    e2e_steps(max(args.warmup, S), False)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- e2e: host buffers in, host buffers out
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    lines_last = e2e_steps(args.steps, halo == 1)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+
+    # ---- value: batches resident in HBM, kernels only
+    for w in range(max(args.warmup, S)):
+        ctx.run_resident(w % S, k=K)
+    ctx.sync()
+    ctx.reset_stage_times()
+    l0 = ctx.kernel_launches()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ctx.run_resident(i % S, k=K)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - l0
+    stage = ctx.stage_times()
+    clocks = sampler.stop()
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+
+    frames_total = B * args.steps * world
+    value = frames_total / (dev_ms * 1e-3)
+    e2e_value = frames_total / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (region engine), rank 0's launches
+    peak, peak_kind = measured_peak()
+    ws, hs = int(round(W * 0.8)), int(round(H * 0.8))
+    S_px = ws * hs
+    # DESIGN.md "algorithmic bytes": region engine = 8 B per scaled pixel per frame
+    # (grow: 4 B angle read + 1 B used read + 1 B used write per pixel = 6; rectangle moments: 2)
+    eng_ms, eng_n = stage["region"]
+    eng_bytes = 8.0 * S_px * B
+    eng_dur = eng_ms / max(eng_n, 1)
+    achieved = eng_bytes / (eng_dur * 1e-3) / 1e9 if eng_dur > 0 else 0.0
+    stage_share = {k: round(v[0] / max(sum(x[0] for x in stage.values()), 1e-9), 4) for k, v in stage.items()}
+    roofline = {"bound": "hbm", "kernel": "region_engine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "ms_per_launch": eng_dur, "algorithmic_bytes_per_launch": eng_bytes,
+                "note": "latency-bound by the sequential seed/FIFO order of LSD region growing; see DESIGN.md",
+                "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},
+                "stage_share": stage_share}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": B, "width": W, "height": H, "octaves": 1, "match_k": K,
+                       "unique_frames": args.unique, "slots": S, "max_lines": cap, "parallelism": f"frames x{world}",
+                       "lines_per_frame": round(lines_last / B, 1),
+                       "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (B * W * H / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": B * cap * (68 + 32 + 16 * K) + 4 * B + 8},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(unique)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

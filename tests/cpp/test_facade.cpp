@@ -1,0 +1,63 @@
+// C++ facade check: drives LSDDetector / BinaryDescriptor / BinaryDescriptorMatcher and the
+// Line / vector<int> seam through libvplines_b200.so on a PGM-less synthetic image pair and
+// prints a digest that the Python side compares with the ctypes path.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../vplines-slam_b200/compat/vplines_seam.hpp"
+
+static void make_image(cv::Mat& m, int w, int h, int shift) {
+  m.create(h, w, CV_8UC1);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int v = 110 + ((x / 7 + y / 11) % 3) * 4;
+      if (x + shift > 60 && x + shift < 200 && y > 40 && y < 150) v = 40;
+      if (y > 170 && y < 178 && x > 30) v = 220;
+      if ((x + shift) - y > 150 && (x + shift) - y < 160) v = 230;
+      m.at<unsigned char>(y, x) = (unsigned char)v;
+    }
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--compile-only") return 0;
+  try {
+    cv::Mat a, b;
+    make_image(a, 320, 240, 0);
+    make_image(b, 320, 240, 3);
+    vplines::B200LineFrontEnd fe;
+    std::vector<vplines::Line> la, lb;
+    std::vector<int> prev_to_cur;
+    fe.detect(a, la);
+    fe.detect(b, lb);
+    fe.match(prev_to_cur);
+    int matched = 0;
+    for (int v : prev_to_cur) matched += v >= 0;
+    std::printf("FACADE lines_a=%zu lines_b=%zu matched=%d\n", la.size(), lb.size(), matched);
+    // raw surface
+    auto det = cv::line_descriptor::LSDDetector::createLSDDetector();
+    std::vector<cv::line_descriptor::KeyLine> kl;
+    det->detect(a, kl, 2, 2);
+    cv::Mat desc;
+    cv::line_descriptor::BinaryDescriptor::createBinaryDescriptor()->compute(a, kl, desc);
+    std::vector<std::vector<cv::DMatch>> knn;
+    cv::line_descriptor::BinaryDescriptorMatcher::createBinaryDescriptorMatcher()->knnMatch(desc, desc, knn, 2);
+    int self = 0;
+    for (size_t i = 0; i < knn.size(); ++i) self += (!knn[i].empty() && knn[i][0].distance == 0.0f);
+    unsigned long digest = 1469598103934665603ul;
+    for (int i = 0; i < desc.rows; ++i)
+      for (int c = 0; c < 32; ++c) digest = (digest ^ desc.at<unsigned char>(i, c)) * 1099511628211ul;
+    std::printf("FACADE keylines=%zu self_matches=%d desc_digest=%lu\n", kl.size(), self, digest);
+    cv::Mat f32(4, 4, CV_32FC1);
+    try {
+      det->detect(f32, kl, 2, 1);
+      std::printf("FACADE depth_check=missing\n");
+    } catch (const std::runtime_error& e) {
+      std::printf("FACADE depth_check=%s\n", e.what());
+    }
+  } catch (const std::exception& e) {
+    std::printf("FACADE error: %s\n", e.what());
+    return 2;
+  }
+  return 0;
+}

@@ -1,0 +1,62 @@
+"""The header-only C++ facade (compat/line_descriptor.hpp, compat/vplines_seam.hpp): compiles
+against the C ABI without OpenCV; on the GPU it must produce what the ctypes path produces."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "vplines-slam_b200")
+
+
+def build_facade(tmp_path):
+    exe = str(tmp_path / "test_facade")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_facade.cpp"),
+           "-L", PKG, "-lvplines_b200", f"-Wl,-rpath,{PKG}"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def make_image(w, h, shift):
+    y, x = np.mgrid[0:h, 0:w]
+    v = 110 + ((x // 7 + y // 11) % 3) * 4
+    v = np.where((x + shift > 60) & (x + shift < 200) & (y > 40) & (y < 150), 40, v)
+    v = np.where((y > 170) & (y < 178) & (x > 30), 220, v)
+    v = np.where(((x + shift) - y > 150) & ((x + shift) - y < 160), 230, v)
+    return v.astype(np.uint8)
+
+
+def test_facade_compiles_and_fails_loudly_without_gpu(vpl, tmp_path):
+    exe = build_facade(tmp_path)
+    assert subprocess.run([exe, "--compile-only"]).returncode == 0
+    if vpl.capi.device_count() == 0:
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU path" in r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_matches_ctypes_path(vpl, orc, tmp_path):
+    exe = build_facade(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    a, b = make_image(320, 240, 0), make_image(320, 240, 3)
+    ekl = orc.lsd_detector_detect(a, 2, 2)
+    edesc = orc.lbd_compute(a, ekl)
+    digest = 1469598103934665603
+    for v in edesc.reshape(-1):
+        digest = ((digest ^ int(v)) * 1099511628211) % (1 << 64)
+    m = re.search(r"keylines=(\d+) self_matches=(\d+) desc_digest=(\d+)", out)
+    assert m, out
+    assert int(m.group(1)) == len(ekl) and int(m.group(3)) == digest
+    # every descriptor's nearest neighbour in its own set is at distance 0
+    assert int(m.group(2)) == len(ekl)
+    la = orc.lsd_detector_detect(a, 2, 1); lb = orc.lsd_detector_detect(b, 2, 1)
+    m2 = re.search(r"lines_a=(\d+) lines_b=(\d+) matched=(\d+)", out)
+    assert int(m2.group(1)) == len(la) and int(m2.group(2)) == len(lb)
+    idx, dist = orc.hamming_knn(orc.lbd_compute(b, lb), orc.lbd_compute(a, la), 1)
+    exp = len(set(int(t) for t, d in zip(idx[:, 0], dist[:, 0]) if d < 30))
+    assert int(m2.group(3)) == exp
+    assert "depth_check=Error, depth image!= 0" in out

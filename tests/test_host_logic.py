@@ -1,0 +1,145 @@
+"""Host-side logic without a GPU: frame sharding with a one-frame halo, the pipelined batch
+driver, and the N>1 path over gloo (world_size 2).  The CUDA context is replaced by a
+stand-in that answers from the CPU oracle -- test infrastructure only; the product driver
+never sees the oracle."""
+import importlib
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleContext:
+    """Quacks like capi.Context (submit / collect_into) but computes with the oracle."""
+
+    def __init__(self, orc, capi, max_batch=4, num_slots=2, max_lines=1024):
+        self.orc, self.capi = orc, capi
+        self.max_batch, self.num_slots, self.max_lines = max_batch, num_slots, max_lines
+        self.pending = {}
+        self.prev_desc = None
+        self.submitted = []
+
+    def submit(self, slot, frames, scale=2, num_octaves=1, k=1, chain=False):
+        assert slot not in self.pending and len(frames) <= self.max_batch
+        out = []
+        prev = self.prev_desc if chain else None
+        for img in frames:
+            kl = self.orc.lsd_detector_detect(img, scale, num_octaves)
+            d = self.orc.lbd_compute(img, kl)
+            m = np.zeros((len(kl), k), self.capi.DMATCH_DTYPE)
+            m["queryIdx"] = np.arange(len(kl))[:, None]
+            m["trainIdx"] = -1
+            if prev is not None:
+                idx, dist = self.orc.hamming_knn(d, prev, k)
+                m["trainIdx"] = idx
+                m["distance"] = dist
+            out.append((kl, d, m))
+            prev = d
+        self.prev_desc = prev
+        self.pending[slot] = out
+        self.submitted.append(len(frames))
+        return len(frames)
+
+    def collect_into(self, slot, kl, counts, cap, desc, matches):
+        for i, (k_, d, m) in enumerate(self.pending.pop(slot)):
+            counts[i] = len(k_)
+            kl[i, :len(k_)] = k_
+            desc[i, :len(k_)] = d
+            matches[i, :len(k_)] = m
+
+
+def test_shard_range_partitions_every_pair_once(vpl):
+    for n in (1, 2, 7, 100, 20000):
+        for world in (1, 2, 3, 4, 8):
+            covered, pairs = [], []
+            for r in range(world):
+                s, e, halo = vpl.shard_range(n, r, world)
+                covered += list(range(s, e))
+                lo = s - halo
+                pairs += [(f - 1, f) for f in range(lo + 1, e)]
+                assert halo in (0, 1) and (halo == 0 or s > 0)
+            assert covered == list(range(n))
+            assert sorted(pairs) == [(f - 1, f) for f in range(1, n)], (n, world)
+
+
+def test_driver_pipelining_and_chaining(vpl, orc, synth):
+    frames = synth.sequence(7, w=192, h=128, seed=5, n_quads=6, n_strokes=10)
+    ctx = OracleContext(orc, vpl.capi, max_batch=3, num_slots=2)
+    kls, descs, ms = vpl.FrontEnd(ctx, k=2).run(frames)
+    assert ctx.submitted == [3, 3, 1] and len(kls) == 7
+    prev = None
+    for f, img in enumerate(frames):
+        ekl = orc.lsd_detector_detect(img, 2, 1)
+        ed = orc.lbd_compute(img, ekl)
+        assert all(np.array_equal(kls[f][n], ekl[n]) for n in ekl.dtype.names)
+        assert np.array_equal(descs[f], ed)
+        if prev is None:
+            assert (ms[f]["trainIdx"] == -1).all()
+        else:
+            idx, _ = orc.hamming_knn(ed, prev, 2)
+            assert np.array_equal(ms[f]["trainIdx"], idx)
+        prev = ed
+
+
+def test_sharded_run_equals_single_run(vpl, orc, synth):
+    frames = synth.sequence(9, w=160, h=120, seed=8, n_quads=5, n_strokes=8)
+    full = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=4), k=1).run(frames)
+    for world in (2, 3):
+        got = ([], [], [])
+        for r in range(world):
+            s, e, halo = vpl.shard_range(len(frames), r, world)
+            part = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=2), k=1).run(frames, s, e, halo)
+            for a, b in zip(got, part):
+                a.extend(b)
+        for a, b in zip(got, full):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype and np.array_equal(x, y) if x.dtype.names is None else \
+                    all(np.array_equal(x[n], y[n]) for n in x.dtype.names)
+
+
+def _gloo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    vpl = importlib.import_module("vplines_slam_b200")
+    synth = importlib.import_module("vplines-slam_b200.synth")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = synth.sequence(6, w=160, h=120, seed=21, n_quads=5, n_strokes=8)
+    s, e, halo = vpl.shard_range(len(frames), rank, world)
+    kls, descs, ms = vpl.FrontEnd(OracleContext(O, vpl.capi, max_batch=2), k=1).run(frames, s, e, halo)
+    # no data-path collective: the host only gathers results (here: per-frame line counts and match sums)
+    mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum())] for k, m in zip(kls, ms)], dtype=torch.int64)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64))
+    pad = torch.zeros((len(frames), 2), dtype=torch.int64)
+    pad[:len(mine)] = mine
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    if rank == 0:
+        q.put(torch.cat([p[:int(n)] for p, n in zip(parts, sizes)]).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather(vpl, orc, synth):
+    world, port = 2, 29000 + os.getpid() % 2000
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    frames = synth.sequence(6, w=160, h=120, seed=21, n_quads=5, n_strokes=8)
+    kls, descs, ms = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=8), k=1).run(frames)
+    exp = np.array([[len(k), int(m["trainIdx"].astype(np.int64).sum())] for k, m in zip(kls, ms)])
+    assert np.array_equal(got, exp)

@@ -79,6 +79,8 @@ struct VplContext {
   double stage_ms[VPL_NUM_STAGES];
   int64_t stage_launches[VPL_NUM_STAGES];
   int64_t launches = 0;
+  double* d_lgam = nullptr;  // log_gamma table for the NFA kernel
+  int lgam_n = 0;
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -117,6 +119,22 @@ void octave_geom(int w, int h, int o, int& wo, int& ho, int& ws, int& hs) {
   for (int i = 0; i < o; ++i) { wo /= 2; ho /= 2; }
   ws = (int)lrint(wo * 0.8);
   hs = (int)lrint(ho * 0.8);
+}
+
+// log-Gamma exactly as LSD computes it (lsd.cpp log_gamma_lanczos / log_gamma_windschitl; the
+// reference carries the same two formulas at line_matching/src/edline_detector.h:210-240).
+double host_log_gamma(double x) {
+  if (x > 15.0)
+    return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+  static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705,
+                              1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+  double b = 0;
+  for (int n = 0; n < 7; ++n) {
+    a -= log(x + (double)n);
+    b += q[n] * pow(x, (double)n);
+  }
+  return a + log(b);
 }
 
 // Built with FMA contraction?  (a*b+c differs between fused and unfused here.)
@@ -194,6 +212,8 @@ void fill_engine_args(VplContext* c, Slot& s, EngineArgs& a) {
   a.batch = s.n;
   a.lc = c->lc;
   a.overflow = s.d_flags;
+  a.lgam = c->d_lgam;
+  a.lgam_n = c->lgam_n;
   for (int o = 0; o < s.num_octaves; ++o) {
     int wo, ho, ws, hs;
     octave_geom(s.w, s.h, o, wo, ho, ws, hs);
@@ -289,6 +309,15 @@ __global__ void fill_nomatch_kernel(VplDMatch* m, const int* counts, int k) {
 int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
   Slot& s = c->slots[slot];
   const int cap = c->cfg.max_lines;
+  if (c->cfg.profile) {
+    // the slot's stage events are about to be re-recorded: bank the previous batch's times
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) {
+      cudaStreamSynchronize(s.stream);
+      harvest_times(c, s);
+    }
+  }
   run_pyramid(c, s, c->cfg.blur_first ? 1 : 0);
   run_lsd(c, s);
   run_pack(c, s);
@@ -402,6 +431,7 @@ void vpl_destroy(VplContext* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
+  cudaFree(c->d_lgam);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img);
     for (int o = 0; o < kMaxOctaves; ++o) {
@@ -471,6 +501,14 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     }
   }
   lbd_init_tables();
+  {
+    // a rectangle holds at most every pixel of the largest 0.8-scaled image
+    c->lgam_n = (int)((double)cfg->max_width * cfg->max_height * 0.64) + 2 * (cfg->max_width + cfg->max_height) + 16;
+    std::vector<double> tab((size_t)c->lgam_n, 0.0);
+    for (int m = 1; m < c->lgam_n; ++m) tab[m] = host_log_gamma((double)m);
+    CKC(cudaMalloc((void**)&c->d_lgam, tab.size() * sizeof(double)));
+    CKC(cudaMemcpy(c->d_lgam, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   const size_t B = (size_t)cfg->max_batch, cap = (size_t)cfg->max_lines;
   const size_t P0 = (size_t)cfg->max_width * cfg->max_height;
   c->slots.resize(cfg->num_slots);

@@ -75,12 +75,14 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
   // seed (uniform load; it is defined and currently unused)
   Pix sp = pix[seed];
   float seed_deg = __uint_as_float(sp.ang & 0x7fffffffu);
+  const int seed_y = seed / ws, seed_x = seed - seed_y * ws;
+  const int seed_xy = seed_x | (seed_y << 16);
   if (lane == 0) {
     pix[seed].ang = sp.ang | kUsedBit;
     RegEnt r;
-    r.idx = seed; r.ang = seed_deg; r.q = sp.q; r.pad = 0;
+    r.idx = seed; r.ang = seed_deg; r.q = sp.q; r.pad = (uint32_t)seed_xy;
     e.reg[0] = r;
-    e.ring[0] = seed;
+    e.ring[0] = seed_xy;
   }
   double reg_angle = (double)seed_deg * VPL_DEG2RAD;
   float sumdx = (float)cos(reg_angle);
@@ -96,17 +98,17 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
     int take = n - i;
     if (take > 3) take = 3;
     const bool act = (lane < 27) && (g < take) && (k != 4);
-    int nidx = -1;
+    int nidx = -1, nxy = 0;
     uint32_t ab = 0xffffffffu;
     float cs = 0.f, sn = 0.f;
     uint32_t q = 0;
     if (act) {
       int j = i + g;
-      int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : e.reg[j].idx;
-      int py = cur / ws, px = cur - py * ws;
-      int nx = px + ddx, ny = py + ddy;
+      int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : (int)e.reg[j].pad;  // packed x | y << 16
+      int nx = (cur & 0xffff) + ddx, ny = (cur >> 16) + ddy;
       if (nx >= 0 && nx < ws && ny >= 0 && ny < hs) {
         nidx = ny * ws + nx;
+        nxy = nx | (ny << 16);
         Pix p = pix[nidx];
         ab = p.ang; cs = p.cs; sn = p.sn; q = p.q;
       }
@@ -123,9 +125,9 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
       if (lane == f) {
         pix[nidx].ang = ab | kUsedBit;
         RegEnt r;
-        r.idx = nidx; r.ang = __uint_as_float(ab); r.q = q; r.pad = 0;
+        r.idx = nidx; r.ang = __uint_as_float(ab); r.q = q; r.pad = (uint32_t)nxy;
         e.reg[n] = r;
-        e.ring[n & (RING - 1)] = nidx;
+        e.ring[n & (RING - 1)] = nxy;
       }
       float fcs = __shfl_sync(0xffffffffu, cs, f);
       float fsn = __shfl_sync(0xffffffffu, sn, f);
@@ -148,14 +150,14 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
 // region2rect + get_theta (A.5).  Sequential double sums in list order.
 // ---------------------------------------------------------------------------
 __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
-  const int lane = e.lane, ws = e.ws;
+  const int lane = e.lane;
   double x = 0, y = 0, sum = 0;
   for (int base = 0; base < n; base += 32) {
     int j = base + lane;
     double wx = 0, wy = 0, wt = 0;
     if (j < n) {
       RegEnt r = e.reg[j];
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       wt = sqrt((double)(int)r.q / 4.0);
       wx = (double)px * wt;
       wy = (double)py * wt;
@@ -176,7 +178,7 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
     double t1 = 0, t2 = 0, t3 = 0;
     if (j < n) {
       RegEnt r = e.reg[j];
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       double weight = sqrt((double)(int)r.q / 4.0);
       double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * weight;
@@ -204,7 +206,7 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int j = lane; j < n; j += 32) {
     RegEnt r = e.reg[j];
-    int py = r.idx / ws, px = r.idx - py * ws;
+    int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
     double regdx = (double)px - x, regdy = (double)py - y;
     double l = regdx * dx + regdy * dy;
     double w = regdy * dx - regdx * dy;
@@ -235,7 +237,7 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
 // counted from the end.  Done as three lane-parallel passes.
 // ---------------------------------------------------------------------------
 __device__ int compact_radius(const Eng& e, int n, double xc, double yc, double radSq) {
-  const int lane = e.lane, ws = e.ws;
+  const int lane = e.lane;
   const unsigned lt = (1u << lane) - 1u;
   int n_in = 0;
   for (int base = 0; base < n; base += 32) {
@@ -243,7 +245,7 @@ __device__ int compact_radius(const Eng& e, int n, double xc, double yc, double 
     bool in = false;
     if (j < n) {
       RegEnt r = e.reg[j];
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
       if (!in) e.pix[r.idx].ang &= ~kUsedBit;
     }
@@ -259,7 +261,7 @@ __device__ int compact_radius(const Eng& e, int n, double xc, double yc, double 
     r.idx = 0; r.ang = 0; r.q = 0; r.pad = 0;
     if (j >= n_in) {
       r = e.reg[j];
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
     }
     unsigned m = __ballot_sync(0xffffffffu, in);
@@ -276,7 +278,7 @@ __device__ int compact_radius(const Eng& e, int n, double xc, double yc, double 
     bool hole = false;
     if (j < n_in) {
       RegEnt r = e.reg[j];
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       hole = dist_sq_d(xc, yc, (double)px, (double)py) > radSq;
     }
     unsigned m = __ballot_sync(0xffffffffu, hole);
@@ -290,8 +292,8 @@ __device__ int compact_radius(const Eng& e, int n, double xc, double yc, double 
 
 __device__ bool reduce_region_radius(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
                                      double density, double density_th) {
-  int s0 = e.reg[0].idx;
-  int yc_i = s0 / e.ws, xc_i = s0 - yc_i * e.ws;
+  uint32_t s0 = e.reg[0].pad;
+  int xc_i = (int)(s0 & 0xffffu), yc_i = (int)(s0 >> 16);
   double xc = (double)xc_i, yc = (double)yc_i;
   double radSq1 = dist_sq_d(xc, yc, rec.x1, rec.y1);
   double radSq2 = dist_sq_d(xc, yc, rec.x2, rec.y2);
@@ -308,11 +310,11 @@ __device__ bool reduce_region_radius(const Eng& e, int& n, double reg_angle, dou
 
 __device__ bool refine(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
                        double density_th) {
-  const int lane = e.lane, ws = e.ws;
+  const int lane = e.lane;
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
   RegEnt r0 = e.reg[0];
-  int yc_i = r0.idx / ws, xc_i = r0.idx - yc_i * ws;
+  int xc_i = (int)(r0.pad & 0xffffu), yc_i = (int)(r0.pad >> 16);
   double xc = (double)xc_i, yc = (double)yc_i;
   double ang_c = (double)r0.ang * VPL_DEG2RAD;
   double sum = 0, s_sum = 0;
@@ -324,7 +326,7 @@ __device__ bool refine(const Eng& e, int& n, double reg_angle, double prec, doub
     if (j < n) {
       RegEnt r = e.reg[j];
       e.pix[r.idx].ang &= ~kUsedBit;
-      int py = r.idx / ws, px = r.idx - py * ws;
+      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
       if (dist_d(xc, yc, (double)px, (double)py) < rec.width) {
         flag = true;
         ang_d = angle_diff_signed_d((double)r.ang * VPL_DEG2RAD, ang_c);

@@ -48,12 +48,22 @@ __device__ __forceinline__ double log_gamma_d(double x) {
   return x > 15.0 ? log_gamma_windschitl_d(x) : log_gamma_lanczos_d(x);
 }
 
+// log_gamma of a positive integer argument: table built once on the host with the same
+// Lanczos/Windschitl formulas (capi.cu); arguments beyond the table are evaluated directly.
+struct LgamTab {
+  const double* tab;  // tab[m] = log_gamma((double)m), m = 0..n-1 (tab[0] unused)
+  int n;
+};
+__device__ __forceinline__ double log_gamma_int(const LgamTab& T, int m) {
+  return (m < T.n) ? __ldg(T.tab + m) : log_gamma_d((double)m);
+}
+
 // per-lane scalar; lanes may carry different (n,k,p)
-__device__ double nfa_d(int n, int k, double p, double LOG_NT) {
+__device__ __noinline__ double nfa_d(int n, int k, double p, double LOG_NT, LgamTab T) {
   if (n == 0 || k == 0) return -LOG_NT;
   if (n == k) return -LOG_NT - (double)n * log10(p);
   double p_term = p / (1 - p);
-  double log1term = log_gamma_d((double)n + 1) - log_gamma_d((double)k + 1) - log_gamma_d((double)(n - k) + 1) +
+  double log1term = log_gamma_int(T, n + 1) - log_gamma_int(T, k + 1) - log_gamma_int(T, n - k + 1) +
                     (double)k * log(p) + (double)(n - k) * log(1.0 - p);
   double term = exp(log1term);
   if (double_equal_d(term, 0)) {
@@ -86,7 +96,7 @@ constexpr int NT = 6;
 __device__ int g_dbg_cand = -1;
 __device__ int g_dbg_now = 0;
 #endif
-__device__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r, const double* precs,
+__device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r, const double* precs,
                            int np, int lane, int& total_out, int* alg_out) {
   double half_width = r.width / 2.0;
   double dyhw = r.dy * half_width;
@@ -172,14 +182,14 @@ struct RState {  // the fields rect_improve mutates
 };
 
 __device__ __forceinline__ double rect_nfa1(const float* ang, int ws, int hs, const RState& r, double log_nt,
-                                            int lane) {
+                                            int lane, const LgamTab& T) {
   double precs[NT];
   precs[0] = r.prec;
 #pragma unroll
   for (int t = 1; t < NT; ++t) precs[t] = 0;
   int total, alg[NT];
   rect_count(ang, ws, hs, r.g, precs, 1, lane, total, alg);
-  return nfa_d(total, alg[0], r.p, log_nt);
+  return nfa_d(total, alg[0], r.p, log_nt, T);
 }
 
 constexpr int NFA_WARPS = 4;
@@ -188,11 +198,13 @@ __global__ void __launch_bounds__(NFA_WARPS * 32)
 rect_nfa_kernel(EngineArgs A) {
   const EngineOct& O = A.oct[blockIdx.z];
   const int f = blockIdx.y;
-  const int ci = blockIdx.x * NFA_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (ci >= O.n_cand[f]) return;
-  RectCand* cp = O.cand + (size_t)f * A.cand_cap + ci;
+  const int n_cand = O.n_cand[f];
+  LgamTab T;
+  T.tab = A.lgam; T.n = A.lgam_n;
   const float* ang = O.ang + (size_t)f * O.ws * O.hs;
+  for (int ci = blockIdx.x * NFA_WARPS + (threadIdx.x >> 5); ci < n_cand; ci += gridDim.x * NFA_WARPS) {
+  RectCand* cp = O.cand + (size_t)f * A.cand_cap + ci;
   const int ws = O.ws, hs = O.hs;
   const double LOG_NT = O.log_nt;
   const double LOG_EPS = 0;
@@ -239,7 +251,7 @@ rect_nfa_kernel(EngineArgs A) {
 #pragma unroll
     for (int t = 0; t < NT; ++t)
       if (lane == t) { myk = alg[t]; myp = ps[t]; }
-    double myv = nfa_d(total, myk, myp, LOG_NT);
+    double myv = nfa_d(total, myk, myp, LOG_NT, T);
     log_nfa = __shfl_sync(0xffffffffu, myv, 0);
     if (!(log_nfa > LOG_EPS)) {
       RState r = rec;
@@ -257,7 +269,7 @@ rect_nfa_kernel(EngineArgs A) {
     for (int n = 0; n < 5; ++n) {
       if ((r.g.width - delta) >= 0.5) {
         r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
         if (v > log_nfa) { rec = r; log_nfa = v; }
       }
     }
@@ -270,7 +282,7 @@ rect_nfa_kernel(EngineArgs A) {
         r.g.x1 += -r.g.dy * delta_2; r.g.y1 += r.g.dx * delta_2;
         r.g.x2 += -r.g.dy * delta_2; r.g.y2 += r.g.dx * delta_2;
         r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
         if (v > log_nfa) { rec = r; log_nfa = v; }
       }
     }
@@ -283,7 +295,7 @@ rect_nfa_kernel(EngineArgs A) {
         r.g.x1 -= -r.g.dy * delta_2; r.g.y1 -= r.g.dx * delta_2;
         r.g.x2 -= -r.g.dy * delta_2; r.g.y2 -= r.g.dx * delta_2;
         r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane);
+        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
         if (v > log_nfa) { rec = r; log_nfa = v; }
       }
     }
@@ -308,7 +320,7 @@ rect_nfa_kernel(EngineArgs A) {
 #pragma unroll
       for (int t = 0; t < 5; ++t)
         if (lane == t) { myk = alg[t]; myp = ps[t]; }
-      double myv = nfa_d(total, myk, myp, LOG_NT);
+      double myv = nfa_d(total, myk, myp, LOG_NT, T);
       for (int n = 0; n < 5; ++n) {
         r.p /= 2;
         r.prec = r.p * VPL_PI;
@@ -323,6 +335,7 @@ rect_nfa_kernel(EngineArgs A) {
     cp->nfa = log_nfa;
     cp->accepted = (log_nfa > LOG_EPS) ? 1 : 0;
   }
+  }  // candidate loop
 }
 
 #ifdef VPL_DEBUG_NFA
@@ -330,7 +343,12 @@ void debug_set_cand(int c) { cudaMemcpyToSymbol(g_dbg_cand, &c, sizeof(int)); }
 #endif
 
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st) {
-  dim3 grid((a.cand_cap + NFA_WARPS - 1) / NFA_WARPS, a.batch, a.num_octaves);
+  // ~16 CTAs per SM in flight over (frames x octaves); warps stride over a frame's candidates
+  int per_frame = (148 * 16 + a.batch * a.num_octaves - 1) / (a.batch * a.num_octaves);
+  int max_pf = (a.cand_cap + NFA_WARPS - 1) / NFA_WARPS;
+  if (per_frame < 1) per_frame = 1;
+  if (per_frame > max_pf) per_frame = max_pf;
+  dim3 grid(per_frame, a.batch, a.num_octaves);
   rect_nfa_kernel<<<grid, NFA_WARPS * 32, 0, st>>>(a);
 }
 

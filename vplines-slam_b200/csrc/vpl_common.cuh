@@ -133,6 +133,8 @@ struct EngineArgs {
   int batch;
   LsdConst lc;
   int* overflow;  // set to 1 if a frame produced more than cand_cap candidates
+  const double* lgam;  // lgam[m] = log_gamma((double)m) for the NFA kernel
+  int lgam_n;
 };
 void launch_region_engine(const EngineArgs& a, cudaStream_t st);
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st);
