@@ -139,6 +139,15 @@ int vpl_frontend_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, i
 int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_t* counts, int cap,
                          uint8_t* desc, VplDMatch* matches);
 
+/* Optional: pin a host buffer that holds frames (cudaHostRegister).  A submit whose frames
+ * are contiguous (stride == w, imgs[f] == imgs[0] + f*w*h) and lie inside a registered range
+ * is uploaded straight from it, asynchronously, without the staging copy -- the caller must
+ * then leave those frames untouched until the slot is collected. */
+int vpl_host_register(VplContext* ctx, const void* ptr, size_t bytes);
+int vpl_host_unregister(VplContext* ctx, const void* ptr);
+/* Bytes the last collect on `slot` copied device -> host. */
+int64_t vpl_last_d2h_bytes(const VplContext* ctx, int slot);
+
 /* Device-resident form used to time the kernels alone: runs the fused path on
  * n frames already in the context's device input buffer of slot s (filled by the
  * last submit on that slot), leaves results in HBM, does not synchronise. */

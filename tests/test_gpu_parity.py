@@ -189,6 +189,23 @@ def test_two_octave_synthetic_c3(ctx, orc, synth):
     assert np.array_equal(ms[1]["trainIdx"], idx)
 
 
+def test_registered_host_buffer_path(ctx, vpl, synth):
+    """vpl_host_register: frames uploaded straight from pinned caller memory give the same
+    results as the staged path; d2h is the dense size."""
+    frames = np.ascontiguousarray(synth.config_sequence("C2_euroc_752x480", 5))
+    a = ctx.frontend_batch(frames, k=2)
+    ctx.host_register(frames)
+    try:
+        b = ctx.frontend_batch(frames, k=2)
+    finally:
+        ctx.host_unregister(frames)
+    for x, y in zip(a, b):
+        for p, q in zip(x, y):
+            assert p.tobytes() == q.tobytes()
+    total = sum(len(k) for k in a[0])
+    assert total * (68 + 32 + 2 * 16) <= ctx.last_d2h_bytes(0) + ctx.last_d2h_bytes(1)
+
+
 def test_errors(ctx, vpl):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context

@@ -37,6 +37,7 @@ EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
+    "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -75,6 +76,10 @@ def load():
     L.vpl_frontend_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
     L.vpl_sync.argtypes = [vp]
+    L.vpl_host_register.argtypes = [vp, vp, sz]
+    L.vpl_host_unregister.argtypes = [vp, vp]
+    L.vpl_last_d2h_bytes.argtypes = [vp, i32]
+    L.vpl_last_d2h_bytes.restype = C.c_int64
     L.vpl_lsd_raw.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32]
     L.vpl_debug_stage.argtypes = [vp, i32, vp, i32, i32, sz, vp, sz, vp, vp]
     L.vpl_debug_candidates.argtypes = [vp, vp, vp, i32]
@@ -213,6 +218,16 @@ class Context:
     def collect_into(self, slot, kl, counts, cap, desc, matches):
         self._ck(self._L.vpl_frontend_collect(self._h, slot, _ptr(kl), _ptr(counts), cap, _ptr(desc),
                                               _ptr(matches)))
+
+    def host_register(self, arr):
+        """Pin a numpy frame buffer so that submits from it skip the staging copy."""
+        self._ck(self._L.vpl_host_register(self._h, _ptr(arr), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._ck(self._L.vpl_host_unregister(self._h, _ptr(arr)))
+
+    def last_d2h_bytes(self, slot):
+        return int(self._L.vpl_last_d2h_bytes(self._h, slot))
 
     def run_resident(self, slot, k=1):
         self._ck(self._L.vpl_frontend_run_resident(self._h, slot, k))

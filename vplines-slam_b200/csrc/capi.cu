@@ -51,6 +51,13 @@ struct Slot {
   VplDMatch* d_match = nullptr;
   uint8_t* d_last_desc = nullptr;  // descriptors of the last frame of the batch
   int* d_last_count = nullptr;
+  int* d_offsets = nullptr;          // exclusive prefix of counts (n+1), dense output layout
+  VplKeyLine* d_kl_dense = nullptr;  // outputs compacted frame after frame for the download
+  uint8_t* d_desc_dense = nullptr;
+  VplDMatch* d_match_dense = nullptr;
+  int* h_offsets = nullptr;
+  bool dense = false;                // this batch's outputs are downloaded in dense form at collect
+  int64_t last_d2h_bytes = 0;
   int* d_flags = nullptr;  // [0] candidate overflow, [1] keyline overflow
   VplSegment* d_seg = nullptr;
   int* d_seg_count = nullptr;
@@ -81,6 +88,7 @@ struct VplContext {
   int64_t launches = 0;
   double* d_lgam = nullptr;  // log_gamma table for the NFA kernel
   int lgam_n = 0;
+  std::vector<std::pair<const uint8_t*, size_t>> pinned;  // vpl_host_register ranges
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -249,7 +257,8 @@ void run_lsd(VplContext* c, Slot& s) {
   {
     StageTimer t(c, s, VPL_STAGE_ORDER);
     for (int o = 0; o < s.num_octaves; ++o)
-      launch_order(s.oct[o].scl, s.oct[o].maxq, s.oct[o].ord, s.oct[o].n_ord, ws[o], hs[o], s.n, c->lc.rho, s.stream);
+      launch_order(s.oct[o].scl, s.oct[o].maxq, s.oct[o].ord, s.oct[o].n_ord, s.oct[o].reg,
+                   (size_t)ws[o] * hs[o] * sizeof(RegEnt), ws[o], hs[o], s.n, c->lc.rho, s.stream);
     t.launches(s.num_octaves);
   }
   EngineArgs a;
@@ -303,6 +312,44 @@ __global__ void fill_nomatch_kernel(VplDMatch* m, const int* counts, int k) {
     VplDMatch d;
     d.queryIdx = i / k; d.trainIdx = -1; d.imgIdx = 0; d.distance = 3.402823466e+38f;
     m[i] = d;
+  }
+}
+
+// exclusive prefix of counts[0..n) -> offsets[0..n] (single block; n <= a few thousand)
+__global__ void offsets_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x, per = (n + 1023) / 1024;
+  int sum = 0;
+  for (int i = tid * per; i < min(n, (tid + 1) * per); ++i) sum += counts[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) { int v = s_part[i]; s_part[i] = run; run += v; }
+    offsets[n] = run;
+  }
+  __syncthreads();
+  int run = s_part[tid];
+  for (int i = tid * per; i < min(n, (tid + 1) * per); ++i) { offsets[i] = run; run += counts[i]; }
+}
+
+// frame f's rows -> dense arrays at offsets[f]; everything is moved as 32-bit words
+__global__ void compact_outputs_kernel(const uint32_t* __restrict__ kl, const uint32_t* __restrict__ desc,
+                                       const uint32_t* __restrict__ match, const int* __restrict__ counts,
+                                       const int* __restrict__ offsets, int cap, int k, uint32_t* __restrict__ kl_d,
+                                       uint32_t* __restrict__ desc_d, uint32_t* __restrict__ match_d) {
+  const int f = blockIdx.x, c = counts[f];
+  const size_t off = (size_t)offsets[f];
+  const uint32_t* a = kl + (size_t)f * cap * 17;
+  uint32_t* ad = kl_d + off * 17;
+  for (int i = threadIdx.x; i < c * 17; i += blockDim.x) ad[i] = a[i];
+  const uint32_t* b = desc + (size_t)f * cap * 8;
+  uint32_t* bd = desc_d + off * 8;
+  for (int i = threadIdx.x; i < c * 8; i += blockDim.x) bd[i] = b[i];
+  if (k > 0) {
+    const uint32_t* m = match + (size_t)f * cap * k * 4;
+    uint32_t* md = match_d + off * k * 4;
+    for (int i = threadIdx.x; i < c * k * 4; i += blockDim.x) md[i] = m[i];
   }
 }
 
@@ -373,13 +420,41 @@ int enqueue_download(VplContext* c, Slot& s, bool kl, bool desc, bool match) {
   return VPL_OK;
 }
 
+// compaction + download of counts/offsets; the dense rows themselves are fetched at collect,
+// once their total size is known
+void enqueue_dense_download(VplContext* c, Slot& s) {
+  StageTimer t(c, s, VPL_STAGE_D2H);
+  const int cap = c->cfg.max_lines;
+  offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_counts, s.n, s.d_offsets);
+  compact_outputs_kernel<<<s.n, 256, 0, s.stream>>>(
+      reinterpret_cast<const uint32_t*>(s.d_kl), reinterpret_cast<const uint32_t*>(s.d_desc),
+      reinterpret_cast<const uint32_t*>(s.d_match), s.d_counts, s.d_offsets, cap, s.k,
+      reinterpret_cast<uint32_t*>(s.d_kl_dense), reinterpret_cast<uint32_t*>(s.d_desc_dense),
+      reinterpret_cast<uint32_t*>(s.d_match_dense));
+  t.launches(2);
+  cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_offsets, s.d_offsets, (size_t)(s.n + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_flags, s.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  s.dense = true;
+}
+
+bool in_registered_range(const VplContext* c, const uint8_t* p, size_t bytes) {
+  for (auto& r : c->pinned)
+    if (p >= r.first && p + bytes <= r.first + r.second) return true;
+  return false;
+}
+
 int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
   if (stride < (size_t)w) return fail(c, VPL_E_INVALID, "stride %zu < width %d", stride, w);
   for (int f = 0; f < n; ++f)
     if (!imgs || !imgs[f]) return fail(c, VPL_E_INVALID, "null image pointer at frame %d", f);
-  stage_images(s, imgs, n, w, h, stride);
+  // frames that are contiguous and lie in memory pinned through vpl_host_register go to
+  // the device directly; anything else is staged through the slot's pinned buffer
+  bool direct = (stride == (size_t)w) && in_registered_range(c, imgs[0], (size_t)n * w * h);
+  for (int f = 1; direct && f < n; ++f) direct = (imgs[f] == imgs[0] + (size_t)f * w * h);
+  if (!direct) stage_images(s, imgs, n, w, h, stride);
   StageTimer t(c, s, VPL_STAGE_H2D);
-  CK(c, cudaMemcpyAsync(s.d_img, s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaMemcpyAsync(s.d_img, direct ? imgs[0] : s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
   return VPL_OK;
 }
 
@@ -431,6 +506,7 @@ void vpl_destroy(VplContext* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
+  for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
   cudaFree(c->d_lgam);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img);
@@ -441,6 +517,8 @@ void vpl_destroy(VplContext* c) {
     }
     cudaFree(s.d_kl); cudaFree(s.d_counts); cudaFree(s.d_desc); cudaFree(s.d_match); cudaFree(s.d_last_desc);
     cudaFree(s.d_last_count); cudaFree(s.d_flags); cudaFree(s.d_seg); cudaFree(s.d_seg_count);
+    cudaFree(s.d_offsets); cudaFree(s.d_kl_dense); cudaFree(s.d_desc_dense); cudaFree(s.d_match_dense);
+    cudaFreeHost(s.h_offsets);
     cudaFreeHost(s.h_img); cudaFreeHost(s.h_kl); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_desc);
     cudaFreeHost(s.h_match); cudaFreeHost(s.h_flags);
     if (s.done) cudaEventDestroy(s.done);
@@ -546,6 +624,11 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     CKC(dmalloc(&s.d_last_desc, cap * 32));
     CKC(dmalloc(&s.d_last_count, 1));
     CKC(dmalloc(&s.d_flags, 4));
+    CKC(dmalloc(&s.d_offsets, B + 1));
+    CKC(dmalloc(&s.d_kl_dense, B * cap));
+    CKC(dmalloc(&s.d_desc_dense, B * cap * 32));
+    CKC(dmalloc(&s.d_match_dense, B * cap * c->max_k));
+    CKC(hmalloc(&s.h_offsets, B + 1));
     CKC(dmalloc(&s.d_seg, (size_t)c->cand_cap));
     CKC(dmalloc(&s.d_seg_count, 1));
     CKC(hmalloc(&s.h_img, B * P0));
@@ -577,7 +660,7 @@ int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int
   if (r) return r;
   r = enqueue_frontend(c, slot, k, chain);
   if (r) return r;
-  enqueue_download(c, s, true, true, true);
+  enqueue_dense_download(c, s);
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
   CK(c, cudaGetLastError());
@@ -601,10 +684,23 @@ int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t*
       counts[f] = s.h_counts[f];
     }
   }
-  const size_t mc = (size_t)c->cfg.max_lines;
-  if (keylines) copy_rows(keylines, s.h_kl, s.h_counts, s.n, mc, (size_t)cap, sizeof(VplKeyLine));
-  if (desc) copy_rows(desc, s.h_desc, s.h_counts, s.n, mc, (size_t)cap, 32);
-  if (matches && s.k > 0) copy_rows(matches, s.h_match, s.h_counts, s.n, mc, (size_t)cap, sizeof(VplDMatch), (size_t)s.k);
+  // dense rows: now that the total is known, fetch exactly that much and scatter it into the
+  // caller's frame-major layout
+  const size_t total = (size_t)s.h_offsets[s.n];
+  if (total > 0) {
+    if (keylines) CK(c, cudaMemcpyAsync(s.h_kl, s.d_kl_dense, total * sizeof(VplKeyLine), cudaMemcpyDeviceToHost, s.stream));
+    if (desc) CK(c, cudaMemcpyAsync(s.h_desc, s.d_desc_dense, total * 32, cudaMemcpyDeviceToHost, s.stream));
+    if (matches && s.k > 0)
+      CK(c, cudaMemcpyAsync(s.h_match, s.d_match_dense, total * s.k * sizeof(VplDMatch), cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaStreamSynchronize(s.stream));
+  }
+  for (int f = 0; f < s.n; ++f) {
+    const size_t off = (size_t)s.h_offsets[f], cnt = (size_t)s.h_counts[f];
+    if (keylines) memcpy(keylines + (size_t)f * cap, s.h_kl + off, cnt * sizeof(VplKeyLine));
+    if (desc) memcpy(desc + (size_t)f * cap * 32, s.h_desc + off * 32, cnt * 32);
+    if (matches && s.k > 0) memcpy(matches + (size_t)f * cap * s.k, s.h_match + off * s.k, cnt * s.k * sizeof(VplDMatch));
+  }
+  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)s.k * sizeof(VplDMatch)) + (2 * (size_t)s.n + 3) * sizeof(int));
   return VPL_OK;
 }
 
@@ -631,6 +727,32 @@ int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
   if (r) return r;
   CK(c, cudaGetLastError());
   return VPL_OK;
+}
+
+int vpl_host_register(VplContext* c, const void* ptr, size_t bytes) {
+  if (!c || !ptr || bytes == 0) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable));
+  c->pinned.emplace_back((const uint8_t*)ptr, bytes);
+  return VPL_OK;
+}
+
+int vpl_host_unregister(VplContext* c, const void* ptr) {
+  if (!c || !ptr) return VPL_E_INVALID;
+  for (size_t i = 0; i < c->pinned.size(); ++i)
+    if (c->pinned[i].first == (const uint8_t*)ptr) {
+      // no batch may still be reading from the range
+      for (Slot& s : c->slots) cudaStreamSynchronize(s.stream);
+      cudaHostUnregister(const_cast<void*>(ptr));
+      c->pinned.erase(c->pinned.begin() + (long)i);
+      return VPL_OK;
+    }
+  return fail(c, VPL_E_INVALID, "pointer was not registered");
+}
+
+int64_t vpl_last_d2h_bytes(const VplContext* c, int slot) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size()) return 0;
+  return c->slots[slot].last_d2h_bytes;
 }
 
 int vpl_sync(VplContext* c) {
@@ -833,7 +955,8 @@ int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, 
       launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].pix, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
       c->launches += 1;
       if (which == 4) { src = s.oct[0].ang; bytes = (size_t)ws * hs * sizeof(float); *out_w = ws; *out_h = hs; break; }
-      launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, ws, hs, 1, c->lc.rho, s.stream);
+      launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, s.oct[0].reg, (size_t)ws * hs * sizeof(RegEnt), ws,
+                   hs, 1, c->lc.rho, s.stream);
       c->launches += 1;
       CK(c, cudaMemcpyAsync(&n_ord, s.oct[0].n_ord, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
       CK(c, cudaStreamSynchronize(s.stream));

@@ -12,8 +12,8 @@
 // angle, double sums in list order), so the warp keeps exactly that order and
 // uses its 32 lanes for everything that is order-free:
 //   * seed scan: 32 ordered seeds per step, one 128-bit gather each;
-//   * growth: the 8 neighbours of up to three FIFO pixels are gathered with one
-//     128-bit load per lane (27 lanes); acceptance is then resolved in lane order,
+//   * growth: the 8 neighbours of up to four FIFO pixels are gathered with one
+//     128-bit load per lane (32 lanes); acceptance is then resolved in lane order,
 //     which is exactly the sequential (FIFO, yy, xx) order;
 //   * rectangle sums: per-entry products in parallel, the additions themselves in
 //     list order (shuffle broadcast) so the double results equal the sequential
@@ -35,6 +35,7 @@ struct Eng {
   Pix* pix;
   RegEnt* reg;
   int* ring;  // shared memory, RING ints
+  double* bc;  // shared memory, 3 x 32 doubles: broadcast buffer for the in-order sums
   int ws, hs;
   int lane;
 };
@@ -69,7 +70,7 @@ __device__ __forceinline__ bool aligned_rad(double a, double theta, double prec)
 // region_grow (A.4).  Returns the region size; reg[0..n) holds the region in
 // acceptance order; *reg_angle_out is the final running angle.
 // ---------------------------------------------------------------------------
-__device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angle_out) {
+__device__ __noinline__ int region_grow(const Eng& e, int seed, double prec, double* reg_angle_out) {
   const int lane = e.lane, ws = e.ws, hs = e.hs;
   Pix* pix = e.pix;
   // seed (uniform load; it is defined and currently unused)
@@ -90,14 +91,15 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
   int n = 1, i = 0;
   __syncwarp();
 
-  const int g = lane / 9;       // which FIFO pixel of this step (0..2), lanes 27..31 idle
-  const int k = lane - 9 * g;   // neighbour 0..8 in (yy outer, xx inner) order
+  const int g = lane >> 3;                  // which FIFO pixel of this step (0..3)
+  const int k8 = lane & 7;                  // its 8 neighbours in (yy outer, xx inner) order,
+  const int k = k8 < 4 ? k8 : k8 + 1;       // skipping the centre
   const int ddx = k % 3 - 1, ddy = k / 3 - 1;
 
   while (i < n) {
     int take = n - i;
-    if (take > 3) take = 3;
-    const bool act = (lane < 27) && (g < take) && (k != 4);
+    if (take > 4) take = 4;
+    const bool act = (g < take);
     int nidx = -1, nxy = 0;
     uint32_t ab = 0xffffffffu;
     float cs = 0.f, sn = 0.f;
@@ -149,7 +151,7 @@ __device__ int region_grow(const Eng& e, int seed, double prec, double* reg_angl
 // ---------------------------------------------------------------------------
 // region2rect + get_theta (A.5).  Sequential double sums in list order.
 // ---------------------------------------------------------------------------
-__device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
+__device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
   const int lane = e.lane;
   double x = 0, y = 0, sum = 0;
   for (int base = 0; base < n; base += 32) {
@@ -162,12 +164,16 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
       wx = (double)px * wt;
       wy = (double)py * wt;
     }
+    // additions in list order: every lane reads entry t (shared-memory broadcast)
+    e.bc[lane] = wx; e.bc[32 + lane] = wy; e.bc[64 + lane] = wt;
+    __syncwarp();
     int cnt = min(32, n - base);
     for (int t = 0; t < cnt; ++t) {
-      x += shfl_d(wx, t);
-      y += shfl_d(wy, t);
-      sum += shfl_d(wt, t);
+      x += e.bc[t];
+      y += e.bc[32 + t];
+      sum += e.bc[64 + t];
     }
+    __syncwarp();
   }
   x /= sum;
   y /= sum;
@@ -185,12 +191,15 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
       t2 = dx * dx * weight;
       t3 = dx * dy * weight;
     }
+    e.bc[lane] = t1; e.bc[32 + lane] = t2; e.bc[64 + lane] = t3;
+    __syncwarp();
     int cnt = min(32, n - base);
     for (int t = 0; t < cnt; ++t) {
-      Ixx += shfl_d(t1, t);
-      Iyy += shfl_d(t2, t);
-      Ixy -= shfl_d(t3, t);
+      Ixx += e.bc[t];
+      Iyy += e.bc[32 + t];
+      Ixy -= e.bc[64 + t];
     }
+    __syncwarp();
   }
   double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
   double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
@@ -236,7 +245,7 @@ __device__ void region2rect(const Eng& e, int n, double reg_angle, double prec, 
 // hole (ascending) among the first n_in positions receives the k-th kept point
 // counted from the end.  Done as three lane-parallel passes.
 // ---------------------------------------------------------------------------
-__device__ int compact_radius(const Eng& e, int n, double xc, double yc, double radSq) {
+__device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, double yc, double radSq) {
   const int lane = e.lane;
   const unsigned lt = (1u << lane) - 1u;
   int n_in = 0;
@@ -308,7 +317,7 @@ __device__ bool reduce_region_radius(const Eng& e, int& n, double reg_angle, dou
   return true;
 }
 
-__device__ bool refine(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
+__device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
                        double density_th) {
   const int lane = e.lane;
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -359,6 +368,7 @@ __device__ bool refine(const Eng& e, int& n, double reg_angle, double prec, doub
 __global__ void __launch_bounds__(32)
 region_engine_kernel(EngineArgs A) {
   __shared__ int s_ring[RING];
+  __shared__ double s_bc[96];
   const int f = blockIdx.x;
   const EngineOct& O = A.oct[blockIdx.y];
   const size_t npx = (size_t)O.ws * O.hs;
@@ -366,6 +376,7 @@ region_engine_kernel(EngineArgs A) {
   e.pix = O.pix + (size_t)f * npx;
   e.reg = O.reg + (size_t)f * npx;
   e.ring = s_ring;
+  e.bc = s_bc;
   e.ws = O.ws; e.hs = O.hs;
   e.lane = threadIdx.x;
   const int lane = e.lane;

@@ -69,37 +69,26 @@ void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* max
 }
 
 // ---------------------------------------------------------------------------
-// K4.  One 1024-thread CTA per frame.  Warp w owns the raster segment
-// [w*C, (w+1)*C) of the frame; phase A builds per-warp histograms in shared
-// memory, phase B turns them into per-(warp,bin) output offsets (bins descending,
-// warps ascending => raster order inside a bin), phase C re-walks the segment and
-// scatters with a match_any rank.  No global atomics, deterministic.
-// Algorithmic bytes: read 2 S (twice the u8 image), write 4 B per defined pixel.
+// K4.  One 1024-thread CTA per frame.  Warp w owns a contiguous block of rows; phase A
+// computes every pixel's bin (kept as u16 in a scratch plane) and builds per-warp
+// histograms in shared memory, phase B turns them into per-(warp,bin) output offsets
+// (bins descending, warps ascending => raster order inside a bin), phase C re-walks
+// the rows and scatters with a match_any rank.  No global atomics, deterministic.
+// Algorithmic bytes: read S (u8) + 2 S write + 2 S read (u16 bins), write 4 B per defined pixel.
 // ---------------------------------------------------------------------------
 constexpr int ORD_THREADS = 1024;
 constexpr int ORD_WARPS = ORD_THREADS / 32;
 
-__device__ __forceinline__ int pixel_bin(const uint8_t* __restrict__ s, int ws, int hs, int idx, double rho,
-                                         double bin_coef) {
-  int y = idx / ws, x = idx - y * ws;
-  if (x >= ws - 1 || y >= hs - 1) return -1;
-  int gx, gy;
-  grad2x2(s, ws, x, y, gx, gy);
-  double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
-  if (norm <= rho) return -1;
-  return (int)(norm * bin_coef);
-}
-
 __global__ void __launch_bounds__(ORD_THREADS, 1)
 order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ maxq, int* __restrict__ ord,
-             int* __restrict__ n_ord, int ws, int hs, double rho) {
+             int* __restrict__ n_ord, uint16_t* __restrict__ bins_, size_t bins_stride, int ws, int hs, double rho) {
   extern __shared__ unsigned int s_cnt[];  // [ORD_WARPS][kBins]
   __shared__ unsigned int s_scan[ORD_WARPS];
   const int f = blockIdx.x;
   const uint8_t* s = scl + (size_t)f * ws * hs;
   int* out = ord + (size_t)f * ws * hs;
+  uint16_t* bins = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(bins_) + (size_t)f * bins_stride);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int N = ws * hs;
   const unsigned int mq = maxq[f];
   if (mq == 0) {
     if (tid == 0) n_ord[f] = 0;
@@ -111,27 +100,38 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
   for (int i = tid; i < ORD_WARPS * kBins; i += ORD_THREADS) s_cnt[i] = 0;
   __syncthreads();
 
-  const int C = (N + ORD_WARPS - 1) / ORD_WARPS;
-  const int beg = wid * C, end = min(N, beg + C);
+  // warp w owns the rows [w*R, (w+1)*R): a contiguous raster segment
+  const int rows = hs - 1;
+  const int R = (rows + ORD_WARPS - 1) / ORD_WARPS;
+  const int y0 = wid * R, y1 = min(rows, y0 + R);
   unsigned int* mycnt = s_cnt + wid * kBins;
 
-  // phase A: per-warp histogram (warp-private => plain increments via match_any)
-  for (int base = beg; base < end; base += 32) {
-    int idx = base + lane;
-    int b = (idx < end) ? pixel_bin(s, ws, hs, idx, rho, bin_coef) : -1;
-    unsigned int grp = __match_any_sync(0xffffffffu, b);
-    if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
-    __syncwarp();
+  // phase A: bin of every pixel (kept as u16 for phase C) + per-warp histogram
+  for (int y = y0; y < y1; ++y) {
+    const uint8_t* r0 = s + (size_t)y * ws;
+    const uint8_t* r1 = r0 + ws;
+    for (int xb = 0; xb < ws - 1; xb += 32) {
+      int x = xb + lane;
+      int b = -1;
+      if (x < ws - 1) {
+        int a = __ldg(r0 + x), bb = __ldg(r0 + x + 1), c = __ldg(r1 + x), d = __ldg(r1 + x + 1);
+        int DA = d - a, BC = bb - c;
+        int gx = DA + BC, gy = DA - BC;
+        double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
+        if (!(norm <= rho)) b = (int)(norm * bin_coef);
+        bins[(size_t)y * ws + x] = (uint16_t)b;  // 0xffff = undefined
+      }
+      unsigned int grp = __match_any_sync(0xffffffffu, b);
+      if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
+      __syncwarp();
+    }
   }
   __syncthreads();
 
-  // phase B: thread b owns bin b.  total[b], then suffix scan over bins.
+  // phase B: thread b owns bin b.  total[b], then suffix scan over bins (descending order).
   unsigned int total = 0;
   for (int w = 0; w < ORD_WARPS; ++w) total += s_cnt[w * kBins + tid];
-  // inclusive suffix sum over bins (higher bins first): scan reversed index r = 1023 - tid
-  // implemented as an inclusive prefix scan over threads in reversed order.
   unsigned int v = total;
-  // warp-level inclusive scan from high lane to low lane
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
@@ -139,12 +139,10 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
   }
   if (lane == 0) s_scan[wid] = v;  // sum of this warp's 32 bins
   __syncthreads();
-  unsigned int higher = 0;  // bins in higher warps
+  unsigned int higher = 0;  // points in the bins of higher warps
   for (int w = wid + 1; w < ORD_WARPS; ++w) higher += s_scan[w];
-  // start[b] = number of points in bins > b
-  unsigned int start = higher + v - total;
+  unsigned int start = higher + v - total;  // number of points in bins > b
   if (tid == 0) n_ord[f] = (int)(higher + v);
-  // per-(warp,bin) offsets, in place
   unsigned int run = start;
   for (int w = 0; w < ORD_WARPS; ++w) {
     unsigned int c = s_cnt[w * kBins + tid];
@@ -153,27 +151,33 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
   }
   __syncthreads();
 
-  // phase C: stable scatter
-  for (int base = beg; base < end; base += 32) {
-    int idx = base + lane;
-    int b = (idx < end) ? pixel_bin(s, ws, hs, idx, rho, bin_coef) : -1;
-    unsigned int grp = __match_any_sync(0xffffffffu, b);
-    if (b >= 0) {
-      unsigned int rank = __popc(grp & ((1u << lane) - 1u));
-      unsigned int off = mycnt[b];
-      out[off + rank] = idx;
+  // phase C: stable scatter (raster order inside a bin: rows ascend with the warp index)
+  for (int y = y0; y < y1; ++y) {
+    const uint16_t* br = bins + (size_t)y * ws;
+    for (int xb = 0; xb < ws - 1; xb += 32) {
+      int x = xb + lane;
+      int b = -1;
+      if (x < ws - 1) {
+        unsigned int u = br[x];
+        b = (u == 0xffffu) ? -1 : (int)u;
+      }
+      unsigned int grp = __match_any_sync(0xffffffffu, b);
+      if (b >= 0) {
+        unsigned int rank = __popc(grp & ((1u << lane) - 1u));
+        out[mycnt[b] + rank] = y * ws + x;
+      }
+      __syncwarp();
+      if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
+      __syncwarp();
     }
-    __syncwarp();
-    if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
-    __syncwarp();
   }
 }
 
-void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, int ws, int hs,
-                  int batch, double rho, cudaStream_t st) {
+void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, void* scratch,
+                  size_t scratch_stride, int ws, int hs, int batch, double rho, cudaStream_t st) {
   const size_t smem = (size_t)ORD_WARPS * kBins * sizeof(unsigned int);
   cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  order_kernel<<<batch, ORD_THREADS, smem, st>>>(scl, maxq, ord, n_ord, ws, hs, rho);
+  order_kernel<<<batch, ORD_THREADS, smem, st>>>(scl, maxq, ord, n_ord, (uint16_t*)scratch, scratch_stride, ws, hs, rho);
 }
 
 }  // namespace vpl

@@ -112,8 +112,10 @@ void launch_scale08(const uint8_t* src, uint8_t* dst, int w, int h, int ws, int 
                     cudaStream_t st);
 void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
                      int batch, double rho, cudaStream_t st);
-void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, int ws, int hs,
-                  int batch, double rho, cudaStream_t st);
+// scratch: >= 2*ws*hs bytes per frame, frames `scratch_stride` bytes apart (the region
+// scratch `reg` is free until the engine runs and is used for this)
+void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, void* scratch,
+                  size_t scratch_stride, int ws, int hs, int batch, double rho, cudaStream_t st);
 struct EngineOct {
   Pix* pix;          // B x hs x ws
   const float* ang;  // B x hs x ws (NFA kernel)
