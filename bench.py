@@ -38,6 +38,13 @@ if ROOT not in sys.path:
 
 WORKLOAD = "C2_euroc_752x480"
 METRIC = "line front-end frames/sec (LSD+LBD+match) at 752x480"
+# other parity/bench cases of BASELINE.json (not the headline): --workload C1|C3|C4
+WORKLOADS = {
+    "C2": dict(name="C2_euroc_752x480", w=752, h=480, octaves=1, k=1, max_lines=1024),
+    "C1": dict(name="C1_mh04_real_752x480", w=752, h=480, octaves=1, k=1, max_lines=2048),
+    "C3": dict(name="C3_d455_1280x720", w=1280, h=720, octaves=2, k=2, max_lines=2048),
+    "C4": dict(name="C4_manhattan_1920x1080", w=1920, h=1080, octaves=1, k=2, max_lines=6144),
+}
 
 
 def measured_peak():
@@ -99,9 +106,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_frames(n_unique, seed):
+def make_frames(n_unique, seed, workload="C2"):
+    if workload == "C1":  # the reference's bundled EuRoC MH_04 frames (tests/golden/mh04_frames.npz)
+        return np.load(os.path.join(ROOT, "tests", "golden", "mh04_frames.npz"))["frames"]
     synth = importlib.import_module("vplines-slam_b200.synth")
-    return synth.config_sequence(WORKLOAD, n_unique, seed=seed)
+    return synth.config_sequence(WORKLOADS[workload]["name"], n_unique, seed=seed)
 
 
 def tile_frames(unique, n):
@@ -109,21 +118,21 @@ def tile_frames(unique, n):
     return np.ascontiguousarray(np.concatenate([unique] * reps)[:n])
 
 
-def cpu_baseline(unique, seconds=12.0, threads=None):
+def cpu_baseline(unique, seconds=12.0, threads=None, octaves=1, name=WORKLOAD):
     """The oracle (CPU port of the path) on the host cores: bounded sample of the same frames."""
     from oracle import oracle as O
     O.build()
     threads = threads or os.cpu_count() or 1
     t = time.time()
-    O.frontend_sequence(unique[:4], num_octaves=1, max_lines=4096, threads=1)
+    O.frontend_sequence(unique[:4], num_octaves=octaves, max_lines=16384, threads=1)
     per_frame = max((time.time() - t) / 4, 1e-3)
     n = int(max(threads * 2, min(seconds / per_frame * threads, 4096)))
     frames = tile_frames(unique, n)
     t = time.time()
-    total = O.frontend_sequence(frames, num_octaves=1, max_lines=4096, threads=threads)
+    total = O.frontend_sequence(frames, num_octaves=octaves, max_lines=16384, threads=threads)
     dt = time.time() - t
     return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{n} frames of {WORKLOAD} ({total} keylines) in {dt:.1f}s; CPU oracle (C port of cv2-4.13 LSD + "
+            "sample": f"{n} frames of {name} ({total} keylines) in {dt:.1f}s; CPU oracle (C port of cv2-4.13 LSD + "
                       f"opencv_contrib-3.4 LBD + brute-force Hamming), {threads} pthreads, contiguous chunks + 1-frame halo",
             "single_thread_frames_per_s": 1.0 / per_frame}
 
@@ -170,7 +179,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="frames per step")
     ap.add_argument("--slots", type=int, default=2)
-    ap.add_argument("--max-lines", type=int, default=1024)
+    ap.add_argument("--max-lines", type=int, default=0, help="KeyLine capacity per frame (0 = workload default)")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--unique", type=int, default=96, help="distinct synthetic frames generated (tiled to fill a batch)")
     ap.add_argument("--seed", type=int, default=20240601)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -192,19 +202,22 @@ def main():
 
     vpl = importlib.import_module("vplines_slam_b200")
     capi = vpl.capi
-    cfgw = importlib.import_module("vplines-slam_b200.synth").CONFIGS[WORKLOAD]
-    W, H = cfgw["w"], cfgw["h"]
-    B, S, cap, K = args.batch, args.slots, args.max_lines, 1
+    wl = WORKLOADS[args.workload]
+    W, H, OCT = wl["w"], wl["h"], wl["octaves"]
+    B, S, cap, K = args.batch, args.slots, (args.max_lines or wl["max_lines"]), wl["k"]
+    wl_name = wl["name"]
 
     # weak scaling: every rank owns `steps*batch` frames of the sequence; its shard starts one
     # frame early (halo) so that the pair across the shard boundary is matched exactly once.
-    unique = make_frames(args.unique, args.seed + 17 * rank)
-    batch_frames = tile_frames(unique, B)
+    unique = make_frames(args.unique, args.seed + 17 * rank, args.workload)
     halo = 1 if rank > 0 else 0
+    # one pinned host buffer: [halo frame | B frames]; the shard's first step starts at the halo
+    host_buf = np.ascontiguousarray(np.concatenate([unique[-1:], tile_frames(unique, B)]))
+    batch_frames = host_buf[1:]
 
-    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap,
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=OCT, max_lines=cap,
                        max_batch=B + 1, num_slots=S, blur_first=True, profile=True)
-    ctx.host_register(batch_frames)  # frames live in pinned host memory: uploaded without a staging copy
+    ctx.host_register(host_buf)  # frames live in pinned host memory: uploaded without a staging copy
     kl = [np.zeros((B + 1, cap), capi.KEYLINE_DTYPE) for _ in range(S)]
     counts = [np.zeros(B + 1, np.int32) for _ in range(S)]
     desc = [np.zeros((B + 1, cap, 32), np.uint8) for _ in range(S)]
@@ -225,10 +238,8 @@ def main():
             if len(pending) == S:
                 ps = pending.pop(0)
                 ctx.collect_into(ps, kl[ps], counts[ps], cap, desc[ps], mt[ps])
-            fr = batch_frames
-            if i == 0 and first_has_halo:
-                fr = np.ascontiguousarray(np.concatenate([batch_frames[-1:], batch_frames]))
-            ctx.submit(s, fr, scale=2, num_octaves=1, k=K, chain=(i > 0))
+            fr = host_buf if (i == 0 and first_has_halo) else batch_frames
+            ctx.submit(s, fr, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
             pending.append(s)
         while pending:
             ps = pending.pop(0)
@@ -287,8 +298,9 @@ def main():
 
     # ---- roofline of the dominant kernel (region engine), rank 0's launches
     peak, peak_kind = measured_peak()
-    ws, hs = int(round(W * 0.8)), int(round(H * 0.8))
-    S_px = ws * hs
+    S_px = 0
+    for o in range(OCT):
+        S_px += int(round((W >> o) * 0.8)) * int(round((H >> o) * 0.8))
     # DESIGN.md "algorithmic bytes": region engine = 8 B per scaled pixel per frame
     # (grow: 4 B angle read + 1 B used read + 1 B used write per pixel = 6; rectangle moments: 2)
     eng_ms, eng_n = stage["region"]
@@ -296,8 +308,15 @@ def main():
     eng_dur = eng_ms / max(eng_n, 1)
     achieved = eng_bytes / (eng_dur * 1e-3) / 1e9 if eng_dur > 0 else 0.0
     stage_share = {k: round(v[0] / max(sum(x[0] for x in stage.values()), 1e-9), 4) for k, v in stage.items()}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "engine_traffic.json")
+    if os.path.exists(tp) and args.workload == "C2":
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per frame
+            traffic = float(json.load(open(tp))["dram_bytes_per_frame"]) * B
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": "region_engine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "ms_per_launch": eng_dur, "algorithmic_bytes_per_launch": eng_bytes,
                 "note": "latency-bound by the sequential seed/FIFO order of LSD region growing; see DESIGN.md",
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},
@@ -306,7 +325,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": B, "width": W, "height": H, "octaves": 1, "match_k": K,
+            "config": {"workload": wl_name, "frames_per_step": B, "width": W, "height": H, "octaves": OCT, "match_k": K,
                        "unique_frames": args.unique, "slots": S, "max_lines": cap, "parallelism": f"frames x{world}",
                        "lines_per_frame": round(lines_last / B, 1),
                        "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (B * W * H / 1e6)},
@@ -316,7 +335,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(unique)
+            line["cpu_baseline"] = cpu_baseline(unique, octaves=OCT, name=wl_name)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

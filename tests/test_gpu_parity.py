@@ -206,6 +206,30 @@ def test_registered_host_buffer_path(ctx, vpl, synth):
     assert total * (68 + 32 + 2 * 16) <= ctx.last_d2h_bytes(0) + ctx.last_d2h_bytes(1)
 
 
+def test_c4_manhattan_1080p_full_size(vpl, orc, synth):
+    """C4 at full size: 1920x1080 Manhattan scene (~2000 lines).  One frame against the
+    oracle bit for bit; the 2000x2000 brute-force match through size-independent properties
+    (self-match: distance 0 at the lowest duplicate index; k=2 ordering) and against the oracle."""
+    frames = synth.config_sequence("C4_manhattan_1920x1080", 2)
+    with vpl.Context(max_width=1920, max_height=1080, max_octaves=1, max_lines=6144, max_batch=2, num_slots=2) as c:
+        kls, descs, ms = c.frontend_batch(frames, scale=2, num_octaves=1, k=2)
+        ekl = orc.lsd_detector_detect(frames[0], 2, 1)
+        assert 1200 < len(ekl) < 6144
+        assert kl_fields_equal(kls[0], ekl)
+        assert np.array_equal(descs[0], orc.lbd_compute(frames[0], ekl))
+        idx, dist = orc.hamming_knn(descs[1], descs[0], 2)
+        assert np.array_equal(ms[1]["trainIdx"], idx)
+        assert np.array_equal(ms[1]["distance"].astype(np.int32), dist)
+        # self match: every code finds itself (or an identical earlier code) at distance 0
+        m = c.match_batch([descs[0]], [descs[0]], k=2)[0]
+        assert (m["distance"][:, 0] == 0).all()
+        assert (m["trainIdx"][:, 0] <= np.arange(len(descs[0]))).all()
+        assert (m["distance"][:, 0] <= m["distance"][:, 1]).all()
+        # determinism / batch invariance at full size
+        again = c.lsd_detect_batch(frames[1:2])[0]
+        assert kl_fields_equal(again, kls[1])
+
+
 def test_errors(ctx, vpl):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context

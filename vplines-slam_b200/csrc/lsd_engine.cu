@@ -35,7 +35,8 @@ struct Eng {
   Pix* pix;
   RegEnt* reg;
   int* ring;  // shared memory, RING ints
-  double* bc;  // shared memory, 3 x 32 doubles: broadcast buffer for the in-order sums
+  double* bc;    // shared memory, 32 doubles  } broadcast buffers for the in-order sums
+  double2* bc2;  // shared memory, 32 double2  }
   int ws, hs;
   int lane;
 };
@@ -70,11 +71,13 @@ __device__ __forceinline__ bool aligned_rad(double a, double theta, double prec)
 // region_grow (A.4).  Returns the region size; reg[0..n) holds the region in
 // acceptance order; *reg_angle_out is the final running angle.
 // ---------------------------------------------------------------------------
-__device__ __noinline__ int region_grow(const Eng& e, int seed, double prec, double* reg_angle_out) {
+__device__ __noinline__ int region_grow(const Eng& e, int seed, uint32_t sp_ang, uint32_t sp_q, double prec,
+                                        double* reg_angle_out) {
   const int lane = e.lane, ws = e.ws, hs = e.hs;
   Pix* pix = e.pix;
-  // seed (uniform load; it is defined and currently unused)
-  Pix sp = pix[seed];
+  // seed: defined and currently unused; its record was fetched by the caller
+  Pix sp;
+  sp.ang = sp_ang; sp.q = sp_q; sp.cs = 0.f; sp.sn = 0.f;
   float seed_deg = __uint_as_float(sp.ang & 0x7fffffffu);
   const int seed_y = seed / ws, seed_x = seed - seed_y * ws;
   const int seed_xy = seed_x | (seed_y << 16);
@@ -85,9 +88,20 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, double prec, dou
     e.reg[0] = r;
     e.ring[0] = seed_xy;
   }
-  double reg_angle = (double)seed_deg * VPL_DEG2RAD;
-  float sumdx = (float)cos(reg_angle);
-  float sumdy = (float)sin(reg_angle);
+  // The running region angle is always (double)reg_deg * DEG2RAD with reg_deg the float32
+  // fastAtan2 result, so the alignment test is first decided in float32 on the degrees and
+  // only falls back to the exact double sequence inside a guard band around the thresholds
+  // (float error on the difference is < 1e-4 deg; the band is 1e-2 deg): same decisions,
+  // a fraction of the FP64 work.
+  float reg_deg = seed_deg;
+  float sumdx, sumdy;
+  {
+    double reg_angle0 = (double)seed_deg * VPL_DEG2RAD;
+    sumdx = (float)cos(reg_angle0);
+    sumdy = (float)sin(reg_angle0);
+  }
+  const float prec_deg = (float)(prec * (180.0 / VPL_PI));
+  const float GUARD = 1e-2f;
   int n = 1, i = 0;
   __syncwarp();
 
@@ -116,18 +130,24 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, double prec, dou
       }
     }
     bool cand = (nidx >= 0) && !(ab & kUsedBit);
-    const double a = (double)__uint_as_float(ab) * VPL_DEG2RAD;
+    const float adeg = __uint_as_float(ab);
     // resolve acceptances in lane order == sequential order
     while (true) {
-      bool al = cand && aligned_rad(a, reg_angle, prec);
+      bool al = false;
+      if (cand) {
+        float d = fabsf(reg_deg - adeg);
+        float dd = (d > 270.f) ? fabsf(d - 360.f) : d;
+        if (fabsf(dd - prec_deg) > GUARD && fabsf(d - 270.f) > GUARD) al = dd < prec_deg;
+        else al = aligned_rad((double)adeg * VPL_DEG2RAD, (double)reg_deg * VPL_DEG2RAD, prec);
+      }
       unsigned m = __ballot_sync(0xffffffffu, al);
       if (m == 0) break;
       int f = __ffs(m) - 1;
-      int acc = __shfl_sync(0xffffffffu, nidx, f);
+      int accxy = __shfl_sync(0xffffffffu, nxy, f);
       if (lane == f) {
         pix[nidx].ang = ab | kUsedBit;
         RegEnt r;
-        r.idx = nidx; r.ang = __uint_as_float(ab); r.q = q; r.pad = (uint32_t)nxy;
+        r.idx = nidx; r.ang = adeg; r.q = q; r.pad = (uint32_t)nxy;
         e.reg[n] = r;
         e.ring[n & (RING - 1)] = nxy;
       }
@@ -135,16 +155,16 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, double prec, dou
       float fsn = __shfl_sync(0xffffffffu, sn, f);
       sumdx += fcs;
       sumdy += fsn;
-      reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * VPL_DEG2RAD;
+      reg_deg = fast_atan2_deg(sumdy, sumdx);
       ++n;
       // lanes up to f were tested (and rejected) with the angle valid at their
       // turn; the same pixel reached through a later FIFO entry is now used.
-      cand = cand && (lane > f) && (nidx != acc);
+      cand = cand && (lane > f) && (nxy != accxy);
     }
     __syncwarp();
     i += take;
   }
-  *reg_angle_out = reg_angle;
+  *reg_angle_out = (double)reg_deg * VPL_DEG2RAD;
   return n;
 }
 
@@ -165,13 +185,24 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
       wy = (double)py * wt;
     }
     // additions in list order: every lane reads entry t (shared-memory broadcast)
-    e.bc[lane] = wx; e.bc[32 + lane] = wy; e.bc[64 + lane] = wt;
+    e.bc2[lane] = make_double2(wx, wy); e.bc[lane] = wt;
     __syncwarp();
     int cnt = min(32, n - base);
-    for (int t = 0; t < cnt; ++t) {
-      x += e.bc[t];
-      y += e.bc[32 + t];
-      sum += e.bc[64 + t];
+    int t = 0;
+    for (; t + 4 <= cnt; t += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double2 v = e.bc2[t + u];
+        x += v.x;
+        y += v.y;
+        sum += e.bc[t + u];
+      }
+    }
+    for (; t < cnt; ++t) {
+      double2 v = e.bc2[t];
+      x += v.x;
+      y += v.y;
+      sum += e.bc[t];
     }
     __syncwarp();
   }
@@ -191,13 +222,24 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
       t2 = dx * dx * weight;
       t3 = dx * dy * weight;
     }
-    e.bc[lane] = t1; e.bc[32 + lane] = t2; e.bc[64 + lane] = t3;
+    e.bc2[lane] = make_double2(t1, t2); e.bc[lane] = t3;
     __syncwarp();
     int cnt = min(32, n - base);
-    for (int t = 0; t < cnt; ++t) {
-      Ixx += e.bc[t];
-      Iyy += e.bc[32 + t];
-      Ixy -= e.bc[64 + t];
+    int t = 0;
+    for (; t + 4 <= cnt; t += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double2 v = e.bc2[t + u];
+        Ixx += v.x;
+        Iyy += v.y;
+        Ixy -= e.bc[t + u];
+      }
+    }
+    for (; t < cnt; ++t) {
+      double2 v = e.bc2[t];
+      Ixx += v.x;
+      Iyy += v.y;
+      Ixy -= e.bc[t];
     }
     __syncwarp();
   }
@@ -354,7 +396,7 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
   __syncwarp();
   double mean_angle = sum / (double)cnt;
   double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(e, r0.idx, tau, &reg_angle);
+  n = region_grow(e, r0.idx, __float_as_uint(r0.ang), r0.q, tau, &reg_angle);
   if (n < 2) return false;
   region2rect(e, n, reg_angle, prec, p, rec);
   density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -368,7 +410,8 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
 __global__ void __launch_bounds__(32)
 region_engine_kernel(EngineArgs A) {
   __shared__ int s_ring[RING];
-  __shared__ double s_bc[96];
+  __shared__ double s_bc[32];
+  __shared__ double2 s_bc2[32];
   const int f = blockIdx.x;
   const EngineOct& O = A.oct[blockIdx.y];
   const size_t npx = (size_t)O.ws * O.hs;
@@ -377,6 +420,7 @@ region_engine_kernel(EngineArgs A) {
   e.reg = O.reg + (size_t)f * npx;
   e.ring = s_ring;
   e.bc = s_bc;
+  e.bc2 = s_bc2;
   e.ws = O.ws; e.hs = O.hs;
   e.lane = threadIdx.x;
   const int lane = e.lane;
@@ -397,9 +441,10 @@ region_engine_kernel(EngineArgs A) {
       todo &= todo - 1;
       int seed = __shfl_sync(0xffffffffu, my, l);
       // the seed may have been absorbed by a region grown earlier in this chunk
-      if (e.pix[seed].ang & kUsedBit) continue;
+      Pix sp = e.pix[seed];
+      if (sp.ang & kUsedBit) continue;
       double reg_angle;
-      int n = region_grow(e, seed, prec, &reg_angle);
+      int n = region_grow(e, seed, sp.ang, sp.q, prec, &reg_angle);
       if (n < O.min_reg_size) continue;
       RectCand rec;
       region2rect(e, n, reg_angle, prec, p, rec);

@@ -20,41 +20,59 @@ __device__ __forceinline__ void grad2x2(const uint8_t* __restrict__ s, int ws, i
 }
 
 // ---------------------------------------------------------------------------
-// K3.  One thread per pixel.  Writes ang (4 B) and the engine record pix (16 B)
+// K3.  Four consecutive pixels per thread.  Writes ang (4 B) and the engine record pix (16 B)
 // of every pixel, reduces max(gx^2+gy^2) per frame with one atomicMax per warp.
 // Algorithmic bytes: read S, write 20 S.
 // ---------------------------------------------------------------------------
+constexpr int LLA_PX = 4;  // consecutive pixels per thread
+
 __global__ void __launch_bounds__(256)
 ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* __restrict__ pix,
                 unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  // pixel k of a thread is x0 + 32 k: every load/store instruction of the warp is contiguous
+  const int x0 = blockIdx.x * (32 * LLA_PX) + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const size_t fo = (size_t)blockIdx.z * ws * hs;
   unsigned int q = 0;
-  if (x < ws && y < hs) {
-    float a = kNotDefDeg;
-    Pix u;
-    u.ang = __float_as_uint(kNotDefDeg);
-    u.cs = 0.f; u.sn = 0.f; u.q = 0u;
-    if (x < ws - 1 && y < hs - 1) {
-      int gx, gy;
-      grad2x2(scl + fo, ws, x, y, gx, gy);
-      unsigned int qq = (unsigned int)(gx * gx + gy * gy);
-      double norm = sqrt((double)(int)qq / 4.0);
-      if (!(norm <= rho)) {
-        q = qq;
-        a = fast_atan2_deg((float)gx, (float)-gy);
-        // cos(float(angle)) / sin(float(angle)) of the radian angle, float overloads:
-        // correctly rounded float of the double function.
-        float ar = (float)((double)a * VPL_DEG2RAD);
-        u.ang = __float_as_uint(a);
-        u.cs = (float)cos((double)ar);
-        u.sn = (float)sin((double)ar);
-        u.q = qq;
-      }
+  if (y < hs) {
+    const uint8_t* r0 = scl + fo + (size_t)y * ws;
+    const bool has_next_row = (y < hs - 1);
+    const uint8_t* r1 = has_next_row ? r0 + ws : r0;
+    int pa[LLA_PX], pb[LLA_PX], pc[LLA_PX], pd[LLA_PX];
+#pragma unroll
+    for (int k = 0; k < LLA_PX; ++k) {
+      int xa = min(x0 + 32 * k, ws - 1), xb = min(x0 + 32 * k + 1, ws - 1);
+      pa[k] = __ldg(r0 + xa); pb[k] = __ldg(r0 + xb);
+      pc[k] = __ldg(r1 + xa); pd[k] = __ldg(r1 + xb);
     }
-    ang[fo + (size_t)y * ws + x] = a;
-    pix[fo + (size_t)y * ws + x] = u;
+#pragma unroll
+    for (int k = 0; k < LLA_PX; ++k) {
+      const int x = x0 + 32 * k;
+      if (x >= ws) break;
+      float a = kNotDefDeg;
+      Pix u;
+      u.ang = __float_as_uint(kNotDefDeg);
+      u.cs = 0.f; u.sn = 0.f; u.q = 0u;
+      if (x < ws - 1 && has_next_row) {
+        int DA = pd[k] - pa[k], BC = pb[k] - pc[k];
+        int gx = DA + BC, gy = DA - BC;
+        unsigned int qq = (unsigned int)(gx * gx + gy * gy);
+        double norm = sqrt((double)(int)qq / 4.0);
+        if (!(norm <= rho)) {
+          q = max(q, qq);
+          a = fast_atan2_deg((float)gx, (float)-gy);
+          // cos(float(angle)) / sin(float(angle)) of the radian angle, float overloads:
+          // correctly rounded float of the double function.
+          float ar = (float)((double)a * VPL_DEG2RAD);
+          u.ang = __float_as_uint(a);
+          u.cs = (float)cos((double)ar);
+          u.sn = (float)sin((double)ar);
+          u.q = qq;
+        }
+      }
+      ang[fo + (size_t)y * ws + x] = a;
+      pix[fo + (size_t)y * ws + x] = u;
+    }
   }
   // warp max -> one atomic per warp
 #pragma unroll
@@ -64,7 +82,7 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
 
 void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
                      int batch, double rho, cudaStream_t st) {
-  dim3 grid((ws + 31) / 32, (hs + 7) / 8, batch);
+  dim3 grid((ws + 32 * LLA_PX - 1) / (32 * LLA_PX), (hs + 7) / 8, batch);
   ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, maxq, ws, hs, rho);
 }
 

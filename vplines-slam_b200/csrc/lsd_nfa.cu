@@ -96,8 +96,9 @@ constexpr int NT = 6;
 __device__ int g_dbg_cand = -1;
 __device__ int g_dbg_now = 0;
 #endif
-__device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r, const double* precs,
-                           int np, int lane, int& total_out, int* alg_out) {
+template <int NP>
+__device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, int hs, const RGeo& r,
+                                        const double* precs, int lane, int& total_out, int* alg_out) {
   double half_width = r.width / 2.0;
   double dyhw = r.dy * half_width;
   double dxhw = r.dx * half_width;
@@ -128,13 +129,25 @@ __device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, i
   const int ys = c0, ye = c2;
   const int n_rows = ye - ys + 1;
   int total = 0;
-  int alg[NT];
+  int alg[NP];
 #pragma unroll
-  for (int t = 0; t < NT; ++t) alg[t] = 0;
+  for (int t = 0; t < NP; ++t) alg[t] = 0;
+  // The alignment test is decided in float32 on degrees; only inside a guard band around a
+  // threshold (or the 270-degree wrap point) is the exact double sequence evaluated, so the
+  // counts equal the all-double ones (float error on the difference < 1e-4 deg, band 1e-2).
+  const float theta_deg = (float)(r.theta * (180.0 / VPL_PI));
+  float pdeg[NP];
+#pragma unroll
+  for (int t = 0; t < NP; ++t) pdeg[t] = (float)(precs[t] * (180.0 / VPL_PI));
+  const float GUARD = 1e-2f;
 
-  const bool by_row = n_rows >= 16;
-  const int row_step = by_row ? 32 : 1;
-  for (int rr = by_row ? lane : 0; rr < n_rows; rr += row_step) {
+  // lanes = RL rows x XP column phases, RL the power of two (4..32) covering n_rows: tall
+  // rectangles get a lane per row, flat ones several lanes along each row
+  int RL = 4;
+  while (RL < 32 && RL < n_rows) RL <<= 1;
+  const int XP = 32 / RL;
+  const int lrow = lane / XP, lph = lane - lrow * XP;
+  for (int rr = lrow; rr < n_rows; rr += RL) {
     int y = ys + rr;
     if (y < 0 || y >= hs) continue;
     double left = (y <= c1) ? ox[0] + ((double)y - oy[0]) * flstep : ox[1] + ((double)y - oy[1]) * slstep;
@@ -143,25 +156,35 @@ __device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, i
     if (xs < 0) xs = 0;
     if (xe > ws - 1) xe = ws - 1;
 #ifdef VPL_DEBUG_NFA
-    if (g_dbg_now && (by_row || lane == 0))
-      printf("DBG row y=%d left=%.17g right=%.17g xs=%d xe=%d by_row=%d c=[%d %d %d %d] o0=(%.17g,%.17g) o1=(%.17g,%.17g) o2=(%.17g,%.17g) o3=(%.17g,%.17g)\n",
-             y, left, right, xs, xe, (int)by_row, c0, c1, c2, c3, ox[0], oy[0], ox[1], oy[1], ox[2], oy[2], ox[3], oy[3]);
+    if (g_dbg_now && lph == 0)
+      printf("DBG row y=%d left=%.17g right=%.17g xs=%d xe=%d\n", y, left, right, xs, xe);
 #endif
     const float* row = ang + (size_t)y * ws;
-    for (int x = by_row ? xs : xs + lane; x <= xe; x += by_row ? 1 : 32) {
+    for (int x = xs + lph; x <= xe; x += XP) {
       ++total;
       float ad = __ldg(row + x);
       if (ad >= 0.f) {
-        double a = (double)ad * VPL_DEG2RAD;
-        double n_theta = r.theta - a;
-        if (n_theta < 0) n_theta = -n_theta;
-        if (n_theta > VPL_3_2_PI) {
-          n_theta -= VPL_2PI;
-          if (n_theta < 0) n_theta = -n_theta;
-        }
+        float d = fabsf(theta_deg - ad);
+        float dd = (d > 270.f) ? fabsf(d - 360.f) : d;
+        bool near = fabsf(d - 270.f) <= GUARD;
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-          if (t < np && n_theta <= precs[t]) ++alg[t];
+        for (int t = 0; t < NP; ++t) near |= fabsf(dd - pdeg[t]) <= GUARD;
+        if (!near) {
+#pragma unroll
+          for (int t = 0; t < NP; ++t)
+            if (dd < pdeg[t]) ++alg[t];
+        } else {
+          double a = (double)ad * VPL_DEG2RAD;
+          double n_theta = r.theta - a;
+          if (n_theta < 0) n_theta = -n_theta;
+          if (n_theta > VPL_3_2_PI) {
+            n_theta -= VPL_2PI;
+            if (n_theta < 0) n_theta = -n_theta;
+          }
+#pragma unroll
+          for (int t = 0; t < NP; ++t)
+            if (n_theta <= precs[t]) ++alg[t];
+        }
       }
     }
   }
@@ -169,11 +192,11 @@ __device__ __noinline__ void rect_count(const float* __restrict__ ang, int ws, i
   for (int o = 16; o > 0; o >>= 1) {
     total += __shfl_xor_sync(0xffffffffu, total, o);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) alg[t] += __shfl_xor_sync(0xffffffffu, alg[t], o);
+    for (int t = 0; t < NP; ++t) alg[t] += __shfl_xor_sync(0xffffffffu, alg[t], o);
   }
   total_out = total;
 #pragma unroll
-  for (int t = 0; t < NT; ++t) alg_out[t] = alg[t];
+  for (int t = 0; t < NP; ++t) alg_out[t] = alg[t];
 }
 
 struct RState {  // the fields rect_improve mutates
@@ -181,15 +204,19 @@ struct RState {  // the fields rect_improve mutates
   double prec, p;
 };
 
-__device__ __forceinline__ double rect_nfa1(const float* ang, int ws, int hs, const RState& r, double log_nt,
-                                            int lane, const LgamTab& T) {
-  double precs[NT];
-  precs[0] = r.prec;
-#pragma unroll
-  for (int t = 1; t < NT; ++t) precs[t] = 0;
-  int total, alg[NT];
-  rect_count(ang, ws, hs, r.g, precs, 1, lane, total, alg);
-  return nfa_d(total, alg[0], r.p, log_nt, T);
+// One "shrink" step of rect_improve's stages 2-4 (mode 0: width, 1: one side, 2: other side).
+__device__ __forceinline__ bool shrink_step(RState& r, int mode) {
+  const double delta = 0.5, delta_2 = delta / 2.0;
+  if (!((r.g.width - delta) >= 0.5)) return false;
+  if (mode == 1) {
+    r.g.x1 += -r.g.dy * delta_2; r.g.y1 += r.g.dx * delta_2;
+    r.g.x2 += -r.g.dy * delta_2; r.g.y2 += r.g.dx * delta_2;
+  } else if (mode == 2) {
+    r.g.x1 -= -r.g.dy * delta_2; r.g.y1 -= r.g.dx * delta_2;
+    r.g.x2 -= -r.g.dy * delta_2; r.g.y2 -= r.g.dx * delta_2;
+  }
+  r.g.width -= delta;
+  return true;
 }
 
 constexpr int NFA_WARPS = 4;
@@ -208,7 +235,7 @@ rect_nfa_kernel(EngineArgs A) {
   const int ws = O.ws, hs = O.hs;
   const double LOG_NT = O.log_nt;
   const double LOG_EPS = 0;
-  const double delta = 0.5, delta_2 = delta / 2.0;
+  const double delta = 0.5;
 
   RState rec;
   rec.g.x1 = cp->x1; rec.g.y1 = cp->y1; rec.g.x2 = cp->x2; rec.g.y2 = cp->y2;
@@ -236,7 +263,7 @@ rect_nfa_kernel(EngineArgs A) {
     }
     __syncwarp();
 #endif
-    rect_count(ang, ws, hs, rec.g, precs, NT, lane, total, alg);
+    rect_count<NT>(ang, ws, hs, rec.g, precs, lane, total, alg);
 #ifdef VPL_DEBUG_NFA
     __syncwarp();
     if (ci == g_dbg_cand) {
@@ -263,41 +290,41 @@ rect_nfa_kernel(EngineArgs A) {
       }
     }
   }
-  if (!(log_nfa > LOG_EPS)) {
-    // reduce width
+  // Stages 2-4 (reduce width / one side / the other side).  Inside a stage the five trial
+  // rectangles do not depend on the NFA outcomes (r shrinks whether or not it improved), so
+  // the five scans run back to back and the five nfa() evaluations run on five lanes at once;
+  // the selection then replays the sequential "if (v > log_nfa)" order.
+#pragma unroll 1
+  for (int mode = 0; mode < 3; ++mode) {
+    if (log_nfa > LOG_EPS) break;
     RState r = rec;
+    int tot[5], alg5[5];
+    unsigned valid = 0;
+#pragma unroll
     for (int n = 0; n < 5; ++n) {
-      if ((r.g.width - delta) >= 0.5) {
-        r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
-        if (v > log_nfa) { rec = r; log_nfa = v; }
+      tot[n] = 0; alg5[n] = 0;
+      if (shrink_step(r, mode)) {
+        valid |= 1u << n;
+        double pr[1] = {r.prec};
+        int a1[1];
+        rect_count<1>(ang, ws, hs, r.g, pr, lane, tot[n], a1);
+        alg5[n] = a1[0];
       }
     }
-  }
-  if (!(log_nfa > LOG_EPS)) {
-    // reduce one side
-    RState r = rec;
+    int myn = 0, myk = 0;
+#pragma unroll
+    for (int n = 0; n < 5; ++n)
+      if (lane == n) { myn = tot[n]; myk = alg5[n]; }
+    double myv = nfa_d(myn, myk, rec.p, LOG_NT, T);
+    int best = -1;
+#pragma unroll
     for (int n = 0; n < 5; ++n) {
-      if ((r.g.width - delta) >= 0.5) {
-        r.g.x1 += -r.g.dy * delta_2; r.g.y1 += r.g.dx * delta_2;
-        r.g.x2 += -r.g.dy * delta_2; r.g.y2 += r.g.dx * delta_2;
-        r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
-        if (v > log_nfa) { rec = r; log_nfa = v; }
-      }
+      double v = __shfl_sync(0xffffffffu, myv, n);
+      if (((valid >> n) & 1u) && v > log_nfa) { log_nfa = v; best = n; }
     }
-  }
-  if (!(log_nfa > LOG_EPS)) {
-    // reduce the other side
-    RState r = rec;
-    for (int n = 0; n < 5; ++n) {
-      if ((r.g.width - delta) >= 0.5) {
-        r.g.x1 -= -r.g.dy * delta_2; r.g.y1 -= r.g.dx * delta_2;
-        r.g.x2 -= -r.g.dy * delta_2; r.g.y2 -= r.g.dx * delta_2;
-        r.g.width -= delta;
-        double v = rect_nfa1(ang, ws, hs, r, LOG_NT, lane, T);
-        if (v > log_nfa) { rec = r; log_nfa = v; }
-      }
+    if (best >= 0) {
+      // re-apply the same shrink steps: identical operations, identical rectangle
+      for (int n = 0; n <= best; ++n) shrink_step(rec, mode);
     }
   }
   if (!(log_nfa > LOG_EPS)) {
@@ -312,9 +339,10 @@ rect_nfa_kernel(EngineArgs A) {
         ps[t] = pp;
         precs[t] = pp * VPL_PI;
       }
-      precs[5] = 0; ps[5] = pp;
+      ps[5] = pp;
       int total, alg[NT];
-      rect_count(ang, ws, hs, r.g, precs, 5, lane, total, alg);
+      precs[5] = -1.0;  // never counted
+      rect_count<NT>(ang, ws, hs, r.g, precs, lane, total, alg);
       int myk = 0;
       double myp = ps[0];
 #pragma unroll
