@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="frames per step")
+    ap.add_argument("--batch", type=int, default=4096, help="frames per step")
     ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--max-lines", type=int, default=0, help="KeyLine capacity per frame (0 = workload default)")
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -218,10 +218,14 @@ def main():
     ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=OCT, max_lines=cap,
                        max_batch=B + 1, num_slots=S, blur_first=True, profile=True)
     ctx.host_register(host_buf)  # frames live in pinned host memory: uploaded without a staging copy
-    kl = [np.zeros((B + 1, cap), capi.KEYLINE_DTYPE) for _ in range(S)]
+    # host result buffers (dense: rows of all frames of a step packed back to back), pinned too
+    rows = (B + 1) * cap
+    kl = [np.zeros(rows, capi.KEYLINE_DTYPE) for _ in range(S)]
     counts = [np.zeros(B + 1, np.int32) for _ in range(S)]
-    desc = [np.zeros((B + 1, cap, 32), np.uint8) for _ in range(S)]
-    mt = [np.zeros((B + 1, cap, K), capi.DMATCH_DTYPE) for _ in range(S)]
+    desc = [np.zeros((rows, 32), np.uint8) for _ in range(S)]
+    mt = [np.zeros((rows, K), capi.DMATCH_DTYPE) for _ in range(S)]
+    for a in kl + desc + mt:
+        ctx.host_register(a)
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,13 +241,13 @@ def main():
             s = i % S
             if len(pending) == S:
                 ps = pending.pop(0)
-                ctx.collect_into(ps, kl[ps], counts[ps], cap, desc[ps], mt[ps])
+                ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
             fr = host_buf if (i == 0 and first_has_halo) else batch_frames
             ctx.submit(s, fr, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
             pending.append(s)
         while pending:
             ps = pending.pop(0)
-            ctx.collect_into(ps, kl[ps], counts[ps], cap, desc[ps], mt[ps])
+            ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
             lines = int(counts[ps][:B].sum())
         return lines
 

@@ -139,6 +139,13 @@ int vpl_frontend_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, i
 int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_t* counts, int cap,
                          uint8_t* desc, VplDMatch* matches);
 
+/* Dense form of collect: the batch's KeyLines / descriptors / matches come back packed frame
+ * after frame (frame f's rows start at sum(counts[0..f))), cap_total rows of capacity,
+ * *total = rows written.  Output buffers registered with vpl_host_register are written by
+ * the device-to-host copy itself (no staging copy). */
+int vpl_frontend_collect_dense(VplContext* ctx, int slot, int32_t* counts, VplKeyLine* keylines,
+                               uint8_t* desc, VplDMatch* matches, int64_t cap_total, int64_t* total);
+
 /* Optional: pin a host buffer that holds frames (cudaHostRegister).  A submit whose frames
  * are contiguous (stride == w, imgs[f] == imgs[0] + f*w*h) and lie inside a registered range
  * is uploaded straight from it, asynchronously, without the staging copy -- the caller must

@@ -230,6 +230,29 @@ def test_c4_manhattan_1080p_full_size(vpl, orc, synth):
         assert kl_fields_equal(again, kls[1])
 
 
+def test_dense_collect_equals_frame_major(ctx, vpl, synth):
+    frames = np.ascontiguousarray(synth.config_sequence("C2_euroc_752x480", 4))
+    kls, descs, ms = ctx.frontend_batch(frames, k=1)
+    n = ctx.submit(0, frames, k=1, chain=False)
+    cap = ctx.max_lines
+    counts = np.zeros(n, np.int32)
+    kl = np.zeros(n * cap, vpl.capi.KEYLINE_DTYPE); d = np.zeros((n * cap, 32), np.uint8)
+    m = np.zeros((n * cap, 1), vpl.capi.DMATCH_DTYPE)
+    ctx.host_register(d)
+    try:
+        total = ctx.collect_dense_into(0, counts, kl, d, m)
+    finally:
+        ctx.host_unregister(d)
+    assert total == sum(len(k) for k in kls) and list(counts) == [len(k) for k in kls]
+    off = 0
+    for f in range(n):
+        c = counts[f]
+        assert kl[off:off + c].tobytes() == kls[f].tobytes()
+        assert np.array_equal(d[off:off + c], descs[f])
+        assert m[off:off + c].tobytes() == ms[f].tobytes()
+        off += c
+
+
 def test_errors(ctx, vpl):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context

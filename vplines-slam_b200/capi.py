@@ -37,7 +37,7 @@ EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
-    "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes",
+    "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -76,6 +76,7 @@ def load():
     L.vpl_frontend_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
     L.vpl_sync.argtypes = [vp]
+    L.vpl_frontend_collect_dense.argtypes = [vp, i32, vp, vp, vp, vp, C.c_int64, vp]
     L.vpl_host_register.argtypes = [vp, vp, sz]
     L.vpl_host_unregister.argtypes = [vp, vp]
     L.vpl_last_d2h_bytes.argtypes = [vp, i32]
@@ -218,6 +219,13 @@ class Context:
     def collect_into(self, slot, kl, counts, cap, desc, matches):
         self._ck(self._L.vpl_frontend_collect(self._h, slot, _ptr(kl), _ptr(counts), cap, _ptr(desc),
                                               _ptr(matches)))
+
+    def collect_dense_into(self, slot, counts, kl, desc, matches):
+        """Dense collect: rows of all frames packed back to back; returns the total row count."""
+        total = C.c_int64(0)
+        self._ck(self._L.vpl_frontend_collect_dense(self._h, slot, _ptr(counts), _ptr(kl), _ptr(desc), _ptr(matches),
+                                                    len(kl), C.byref(total)))
+        return int(total.value)
 
     def host_register(self, arr):
         """Pin a numpy frame buffer so that submits from it skip the staging copy."""

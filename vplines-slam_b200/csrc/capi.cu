@@ -704,6 +704,38 @@ int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t*
   return VPL_OK;
 }
 
+int vpl_frontend_collect_dense(VplContext* c, int slot, int32_t* counts, VplKeyLine* keylines, uint8_t* desc,
+                               VplDMatch* matches, int64_t cap_total, int64_t* total_out) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight) return fail(c, VPL_E_INVALID, "slot %d has no batch in flight", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = finish(c, s);
+  if (r) return r;
+  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
+  if (s.h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
+  const size_t total = (size_t)s.h_offsets[s.n];
+  if (total_out) *total_out = (int64_t)total;
+  if ((int64_t)total > cap_total) return fail(c, VPL_E_CAPACITY, "%zu keylines in the batch > cap_total %lld", total, (long long)cap_total);
+  if (counts) memcpy(counts, s.h_counts, (size_t)s.n * sizeof(int));
+  struct Out { void* user; const void* dev; void* stage; size_t bytes; };
+  const Out outs[3] = {{keylines, s.d_kl_dense, s.h_kl, total * sizeof(VplKeyLine)},
+                       {desc, s.d_desc_dense, s.h_desc, total * 32},
+                       {(s.k > 0) ? matches : nullptr, s.d_match_dense, s.h_match, total * (size_t)s.k * sizeof(VplDMatch)}};
+  bool direct[3] = {false, false, false};
+  for (int i = 0; i < 3; ++i) {
+    if (!outs[i].user || outs[i].bytes == 0) continue;
+    direct[i] = in_registered_range(c, (const uint8_t*)outs[i].user, outs[i].bytes);
+    CK(c, cudaMemcpyAsync(direct[i] ? outs[i].user : outs[i].stage, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  CK(c, cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < 3; ++i)
+    if (outs[i].user && outs[i].bytes && !direct[i]) memcpy(outs[i].user, outs[i].stage, outs[i].bytes);
+  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)s.k * sizeof(VplDMatch)) + (2 * (size_t)s.n + 3) * sizeof(int));
+  return VPL_OK;
+}
+
 int vpl_frontend_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int scale,
                        int num_octaves, int k, int chain, VplKeyLine* keylines, int32_t* counts, int cap,
                        uint8_t* desc, VplDMatch* matches) {
