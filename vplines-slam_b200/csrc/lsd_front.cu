@@ -139,6 +139,7 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
         if (!(norm <= rho)) b = (int)(norm * bin_coef);
         bins[(size_t)y * ws + x] = (uint16_t)b;  // 0xffff = undefined
       }
+      if (__ballot_sync(0xffffffffu, b >= 0) == 0) continue;  // nothing to count in these 32 pixels
       unsigned int grp = __match_any_sync(0xffffffffu, b);
       if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
       __syncwarp();
@@ -179,6 +180,7 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
         unsigned int u = br[x];
         b = (u == 0xffffu) ? -1 : (int)u;
       }
+      if (__ballot_sync(0xffffffffu, b >= 0) == 0) continue;
       unsigned int grp = __match_any_sync(0xffffffffu, b);
       if (b >= 0) {
         unsigned int rank = __popc(grp & ((1u << lane) - 1u));

@@ -60,14 +60,13 @@ blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
     for (int i = tid; i < B5_IH * (B5_TW + 2); i += B5_THREADS) {
       int r = i / (B5_TW + 2), c = i % (B5_TW + 2);
       const uint8_t* p = &s_in[r][c + 3 - 2];  // gx = x0-1+c -> col c+3
-      s_hb[r][c] = (uint16_t)(14 * p[0] + 62 * p[1] + 104 * p[2] + 62 * p[3] + 14 * p[4]);
+      s_hb[r][c] = (uint16_t)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
     }
     __syncthreads();
     // ---- vertical pass: rows y0-1 .. y0+TH
     for (int i = tid; i < (B5_TH + 2) * (B5_TW + 2); i += B5_THREADS) {
       int r = i / (B5_TW + 2), c = i % (B5_TW + 2);
-      uint32_t s = 14u * s_hb[r][c] + 62u * s_hb[r + 1][c] + 104u * s_hb[r + 2][c] + 62u * s_hb[r + 3][c] +
-                   14u * s_hb[r + 4][c];
+      uint32_t s = 14u * (s_hb[r][c] + s_hb[r + 4][c]) + 62u * (s_hb[r + 1][c] + s_hb[r + 3][c]) + 104u * s_hb[r + 2][c];
       s_bl[r][c + 1] = (uint8_t)((s + 32768u) >> 16);
     }
   } else {
@@ -80,7 +79,7 @@ blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
 
   // ---- Sobel + stores: each thread handles 4 consecutive pixels of a row
   for (int i = tid; i < B5_TH * (B5_TW / 4); i += B5_THREADS) {
-    int r = i / (B5_TW / 4), c = 4 * (i % (B5_TW / 4));
+    int r = i >> 4, c = 4 * (i & 15);  // B5_TW / 4 == 16
     int gy = y0 + r, gx = x0 + c;
     if (gy >= h || gx >= w) continue;
     uint32_t packed = 0;
@@ -193,26 +192,26 @@ scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int
   const int dx0 = blockIdx.x * SC_TW, dy0 = blockIdx.y * SC_TH;
   const int sx0 = (10 * dx0 + 1) >> 3, sy0 = (10 * dy0 + 1) >> 3;  // first source col/row of the tile
   const int tid = threadIdx.x;
-  for (int i = tid; i < SC_IH * SC_IW; i += SC_THREADS) {
-    int r = i / SC_IW, c = i % SC_IW;
-    s_in[r][c] = __ldg(src + (size_t)refl101(sy0 - 2 + r, h) * w + refl101(sx0 - 2 + c, w));
+  const int tx = tid & 31, ty = tid >> 5;  // 32 x 8 threads
+  for (int r = ty; r < SC_IH; r += 8) {
+    const uint8_t* srow = src + (size_t)refl101(sy0 - 2 + r, h) * w;
+    for (int c = tx; c < SC_IW; c += 32) s_in[r][c] = __ldg(srow + refl101(sx0 - 2 + c, w));
   }
   __syncthreads();
-  for (int i = tid; i < SC_IH * SC_GW; i += SC_THREADS) {
-    int r = i / SC_GW, c = i % SC_GW;
-    const uint8_t* p = &s_in[r][c];
-    s_hb[r][c] = (uint16_t)(4 * p[0] + 56 * p[1] + 136 * p[2] + 56 * p[3] + 4 * p[4]);
-  }
+  for (int r = ty; r < SC_IH; r += 8)
+    for (int c = tx; c < SC_GW; c += 32) {
+      const uint8_t* p = &s_in[r][c];
+      s_hb[r][c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
+    }
   __syncthreads();
-  for (int i = tid; i < SC_GH * SC_GW; i += SC_THREADS) {
-    int r = i / SC_GW, c = i % SC_GW;
-    uint32_t s = 4u * s_hb[r][c] + 56u * s_hb[r + 1][c] + 136u * s_hb[r + 2][c] + 56u * s_hb[r + 3][c] +
-                 4u * s_hb[r + 4][c];
-    s_g[r][c] = (uint8_t)((s + 32768u) >> 16);
-  }
+  for (int r = ty; r < SC_GH; r += 8)
+    for (int c = tx; c < SC_GW; c += 32) {
+      uint32_t s = 4u * (s_hb[r][c] + s_hb[r + 4][c]) + 56u * (s_hb[r + 1][c] + s_hb[r + 3][c]) + 136u * s_hb[r + 2][c];
+      s_g[r][c] = (uint8_t)((s + 32768u) >> 16);
+    }
   __syncthreads();
   for (int i = tid; i < SC_TH * SC_TW; i += SC_THREADS) {
-    int r = i / SC_TW, c = i % SC_TW;
+    int r = i >> 6, c = i & 63;  // SC_TW == 64
     int dx = dx0 + c, dy = dy0 + r;
     if (dx >= ws || dy >= hs) continue;
     int fx8 = 10 * dx + 1, fy8 = 10 * dy + 1;
