@@ -253,6 +253,52 @@ def test_dense_collect_equals_frame_major(ctx, vpl, synth):
         off += c
 
 
+def test_three_octaves_and_unblurred_variant(vpl, orc, mh04):
+    img = mh04[7]
+    with vpl.Context(max_width=752, max_height=480, max_octaves=3, max_lines=4096, max_batch=2) as c:
+        got = c.lsd_detect_batch(img[None], scale=2, num_octaves=3)[0]
+        exp = orc.lsd_detector_detect(img, 2, 3)
+        assert set(np.unique(exp["octave"])) == {0, 1, 2}
+        assert kl_fields_equal(got, exp)
+        assert np.array_equal(c.lbd_compute_batch(img[None], [exp])[0], orc.lbd_compute(img, exp))
+    # LSDDetector variant with the pyramid blur commented out (VplConfig.blur_first = 0); BinaryDescriptor
+    # still blurs its own pyramid
+    with vpl.Context(max_width=752, max_height=480, max_octaves=2, max_lines=4096, max_batch=2, blur_first=False) as c:
+        kls, descs, _ = c.frontend_batch(img[None], scale=2, num_octaves=2, k=1)
+        exp = orc.lsd_detector_detect(img, 2, 2, blur_first=False)
+        assert kl_fields_equal(kls[0], exp)
+        assert np.array_equal(descs[0], orc.lbd_compute(img, exp))
+
+
+def test_strided_input_and_knn_k5(ctx, vpl, orc, mh04):
+    import ctypes as C
+    big = np.zeros((480, 800), np.uint8)
+    big[:, :752] = mh04[2]
+    view = big[:, :752]                      # row pitch 800 bytes
+    L = vpl.capi.load()
+    cap = 4096
+    kl = np.zeros(cap, vpl.capi.KEYLINE_DTYPE); cnt = np.zeros(1, np.int32)
+    ptrs = (C.c_void_p * 1)(view.ctypes.data)
+    r = L.vpl_lsd_detect_batch(ctx._h, ptrs, 1, 752, 480, 800, 2, 1, kl.ctypes.data_as(C.c_void_p),
+                               cnt.ctypes.data_as(C.c_void_p), cap)
+    assert r == 0
+    exp = orc.lsd_detector_detect(mh04[2], 2, 1)
+    assert kl_fields_equal(kl[:cnt[0]], exp)
+    d = orc.lbd_compute(mh04[2], exp)
+    m = ctx.match_batch([d[:300]], [d[100:500]], k=5)[0]
+    idx, dist = orc.hamming_knn(d[:300], d[100:500], 5)
+    assert np.array_equal(m["trainIdx"], idx) and np.array_equal(m["distance"].astype(np.int32), dist)
+
+
+def test_capacity_errors_are_loud(vpl, mh04):
+    with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=64, max_batch=2) as c:
+        with pytest.raises(vpl.VplError) as e:
+            c.lsd_detect_batch(mh04[:1])     # ~800 lines > max_lines
+        assert e.value.code == vpl.capi.VPL_E_CAPACITY
+        # the context stays usable afterwards
+        assert len(c.lsd_detect_batch(np.zeros((1, 480, 752), np.uint8))[0]) == 0
+
+
 def test_errors(ctx, vpl):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context

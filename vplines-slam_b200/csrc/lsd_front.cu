@@ -57,7 +57,9 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
         int DA = pd[k] - pa[k], BC = pb[k] - pc[k];
         int gx = DA + BC, gy = DA - BC;
         unsigned int qq = (unsigned int)(gx * gx + gy * gy);
-        double norm = sqrt((double)(int)qq / 4.0);
+        // sqrt(q/4) <= rho = 5.2262... for every q < 100 (sqrt(25) = 5): skip the FP64 work there;
+        // q >= 100 takes the exact double comparison
+        double norm = (qq < 100u) ? 0.0 : sqrt((double)(int)qq / 4.0);
         if (!(norm <= rho)) {
           q = max(q, qq);
           a = fast_atan2_deg((float)gx, (float)-gy);
@@ -135,8 +137,11 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
         int a = __ldg(r0 + x), bb = __ldg(r0 + x + 1), c = __ldg(r1 + x), d = __ldg(r1 + x + 1);
         int DA = d - a, BC = bb - c;
         int gx = DA + BC, gy = DA - BC;
-        double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
-        if (!(norm <= rho)) b = (int)(norm * bin_coef);
+        int qq = gx * gx + gy * gy;
+        if (qq >= 100) {  // below that sqrt(q/4) <= 5 < rho: undefined without FP64 work
+          double norm = sqrt((double)qq / 4.0);
+          if (!(norm <= rho)) b = (int)(norm * bin_coef);
+        }
         bins[(size_t)y * ws + x] = (uint16_t)b;  // 0xffff = undefined
       }
       if (__ballot_sync(0xffffffffu, b >= 0) == 0) continue;  // nothing to count in these 32 pixels
