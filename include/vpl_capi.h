@@ -94,6 +94,19 @@ const char* vpl_last_error(const VplContext* ctx); /* ctx may be NULL: last crea
 const char* vpl_version(void);
 int vpl_device_count(void);
 
+/* ---- pre-processing in front of the path ----------------------- */
+/* Replaces cv::remap(_img, img, undist_map1_, undist_map2_, CV_INTER_LINEAR) and
+ * cv::createCLAHE(3.0, Size(8,8))->apply (LineFeatureTracker::readImage,
+ * feature_tracker/src/line_feature_tracker.cpp:62, :64-68).  mapx/mapy: the CV_32FC1 maps of
+ * initUndistortRectifyMap (w x h floats each; both NULL = no remap).  clahe_clip <= 0 = no CLAHE
+ * (the reference uses 3.0 with an 8x8 grid when EQUALIZE is set).  Once set, every call that takes
+ * frames (detect / compute / frontend) applies it to the uploaded frames on the device first. */
+int vpl_set_preprocess(VplContext* ctx, const float* mapx, const float* mapy, int w, int h,
+                       double clahe_clip, int clahe_tiles);
+/* The pre-processed frames themselves (n*w*h bytes), for the parity tests. */
+int vpl_preprocess_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                         size_t stride, uint8_t* out);
+
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
  * keylines: n * cap entries, frame f at keylines + f*cap; counts[f] = number found
@@ -190,7 +203,8 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_LBD 8
 #define VPL_STAGE_MATCH 9
 #define VPL_STAGE_D2H 10
-#define VPL_NUM_STAGES 11
+#define VPL_STAGE_PREPROC 11  /* remap + CLAHE (optional)           */
+#define VPL_NUM_STAGES 12
 /* Accumulated device milliseconds and launch counts per stage since the last
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);

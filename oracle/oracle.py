@@ -97,6 +97,24 @@ def sobel3(img):
     return dx, dy
 
 
+def remap_linear(img, mapx, mapy):
+    """cv::remap(img, mapx, mapy, INTER_LINEAR) with float32 maps, constant-0 border."""
+    img = _u8(img); h, w = img.shape
+    mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_remap_linear(_p(img), w, h, _p(mapx), _p(mapy), dw, dh, _p(out))
+    return out
+
+
+def clahe(img, clip_limit=3.0, tiles=8):
+    """cv::createCLAHE(clip_limit, (tiles, tiles)).apply(img)."""
+    img = _u8(img); h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_clahe(_p(img), w, h, ctypes.c_double(clip_limit), int(tiles), _p(out))
+    return out
+
+
 def fast_atan2(y, x):
     return lib().orc_fast_atan2(float(y), float(x))
 

@@ -53,6 +53,14 @@ void orc_pyrdown_half(const uint8_t* src, int w, int h, uint8_t* dst);       /* 
 void orc_sobel3(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy);
 float orc_fast_atan2(float y, float x);
 
+/* ---- pre-processing in front of the path (readImage, line_feature_tracker.cpp:62-68) ---- */
+/* cv::remap(src, dst, mapx, mapy, INTER_LINEAR, BORDER_CONSTANT 0) with CV_32FC1 maps of dw x dh */
+void orc_remap_linear(const uint8_t* src, int w, int h, const float* mapx, const float* mapy, int dw,
+                      int dh, uint8_t* dst);
+void orc_remap_weight_table(uint16_t* tab /* 1024 x 4 */);
+/* cv::createCLAHE(clip_limit, Size(tiles,tiles))->apply on CV_8UC1 */
+void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles, uint8_t* dst);
+
 /* ---- LSD (cv::LineSegmentDetector, LSD_REFINE_ADV by default) ------------- */
 /* refine: 0 NONE, 1 STD, 2 ADV.  scale08: 1 => internal 0.8 scaling (default),
  * 0 => scale 1.  Outputs up to cap segments; returns the number found (may

@@ -11,6 +11,10 @@ container, where /root/reference and cv2 4.13 exist; the GPU box has neither nee
   cv2_prims.npz     cv2 4.13 GaussianBlur(5x5,1), GaussianBlur(7x7,.75), resize(.8,
                     INTER_LINEAR_EXACT), pyrDown(w/2,h/2), Sobel dx/dy on a seeded random
                     image (full arrays) and sha256 of the same on frame 1; fastAtan2 samples.
+  cv2_preproc.npz   cv2 4.13 remap(INTER_LINEAR, float32 maps, constant border) with a EuRoC-like
+                    radial-tangential undistortion map and with a jittered map on a small image, and
+                    createCLAHE(3.0,(8,8)) / (2.0,(4,4)) on frame 1 and on sizes that are not multiples
+                    of the grid (sha256 for the full frames, arrays for the small ones).
   cv2_hamming.npz   cv2.BFMatcher(NORM_HAMMING).knnMatch (k=3) on seeded random 256-bit codes
                     with planted exact duplicates (tie cases).
 
@@ -83,6 +87,29 @@ def main():
     pr["atan_yx"] = yx
     pr["atan_deg"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in yx], np.float32)
     np.savez_compressed(os.path.join(HERE, "cv2_prims.npz"), **pr)
+
+    # ---- pre-processing
+    h, w = 480, 752
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375        # EuRoC cam0 intrinsics (config/euroc)
+    k1, k2, p1, p2 = -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05
+    x = (xx - cx) / fx; y = (yy - cy) / fy; r2 = x * x + y * y; rad = 1 + k1 * r2 + k2 * r2 * r2
+    mapx = ((x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)) * fx + cx).astype(np.float32)
+    mapy = ((y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y) * fy + cy).astype(np.float32)
+    und = cv2.remap(f1, mapx, mapy, cv2.INTER_LINEAR)
+    pp = {"euroc_mapx": mapx.astype(np.float16).astype(np.float32), "f1_remap_sha": np.array([sha(und)]),
+          "f1_clahe_sha": np.array([sha(cv2.createCLAHE(3.0, (8, 8)).apply(f1))]),
+          "f1_remap_clahe_sha": np.array([sha(cv2.createCLAHE(3.0, (8, 8)).apply(und))])}
+    del pp["euroc_mapx"]  # the map is regenerated from the formula above in the tests
+    rng2 = np.random.default_rng(4321)  # own stream: the vectors above/below do not move
+    small = rng2.integers(0, 256, (75, 100), dtype=np.uint8)
+    smx = (np.arange(100)[None, :] + rng2.uniform(-4, 4, (75, 100))).astype(np.float32)
+    smy = (np.arange(75)[:, None] + rng2.uniform(-4, 4, (75, 100))).astype(np.float32)
+    smx[::7, ::5] = np.round(smx[::7, ::5]); smy[::7, ::5] = np.round(smy[::7, ::5])   # exact-integer coordinates
+    pp.update(small=small, smx=smx, smy=smy, small_remap=cv2.remap(small, smx, smy, cv2.INTER_LINEAR),
+              small_clahe=cv2.createCLAHE(3.0, (8, 8)).apply(small),
+              small_clahe_2_4=cv2.createCLAHE(2.0, (4, 4)).apply(small))
+    np.savez_compressed(os.path.join(HERE, "cv2_preproc.npz"), **pp)
 
     q = rng.integers(0, 256, (97, 32), dtype=np.uint8)
     t = rng.integers(0, 256, (131, 32), dtype=np.uint8)

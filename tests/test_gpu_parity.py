@@ -299,6 +299,41 @@ def test_capacity_errors_are_loud(vpl, mh04):
         assert len(c.lsd_detect_batch(np.zeros((1, 480, 752), np.uint8))[0]) == 0
 
 
+def test_preprocess_remap_clahe_bit_exact(vpl, orc, mh04):
+    """undistortion remap + CLAHE(3.0, 8x8) on the device, and the front end fed by it,
+    against the oracle (which is pinned to cv2.remap / cv2.CLAHE)."""
+    from test_oracle_preproc import euroc_maps
+    mapx, mapy = euroc_maps()
+    frames = mh04[:3]
+    with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=4096, max_batch=4) as c:
+        c.set_preprocess(mapx, mapy, clahe_clip=3.0, clahe_tiles=8)
+        got = c.preprocess_batch(frames)
+        exp = [orc.clahe(orc.remap_linear(f, mapx, mapy), 3.0, 8) for f in frames]
+        for g, e in zip(got, exp):
+            assert np.array_equal(g, e)
+        kls, descs, _ = c.frontend_batch(frames, k=1)
+        for f in range(3):
+            ekl = orc.lsd_detector_detect(exp[f], 2, 1)
+            assert kl_fields_equal(kls[f], ekl)
+            assert np.array_equal(descs[f], orc.lbd_compute(exp[f], ekl))
+        # remap only / CLAHE only / off again
+        c.set_preprocess(mapx, mapy, clahe_clip=0.0)
+        assert np.array_equal(c.preprocess_batch(frames[:1])[0], orc.remap_linear(frames[0], mapx, mapy))
+        c.set_preprocess(None, None, size=(752, 480), clahe_clip=3.0, clahe_tiles=8)
+        assert np.array_equal(c.preprocess_batch(frames[:1])[0], orc.clahe(frames[0], 3.0, 8))
+        c.set_preprocess(None, None, size=(752, 480), clahe_clip=0.0)
+        assert np.array_equal(c.preprocess_batch(frames[:1])[0], frames[0])
+    # sizes that are not a multiple of the CLAHE grid, jittered maps with exact-integer coordinates
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (75, 100), dtype=np.uint8)
+    mx = (np.arange(100)[None, :] + rng.uniform(-4, 4, (75, 100))).astype(np.float32)
+    my = (np.arange(75)[:, None] + rng.uniform(-4, 4, (75, 100))).astype(np.float32)
+    mx[::5, ::3] = np.round(mx[::5, ::3]); my[::5, ::3] = np.round(my[::5, ::3])
+    with vpl.Context(max_width=100, max_height=75, max_octaves=1, max_lines=512, max_batch=2) as c:
+        c.set_preprocess(mx, my, clahe_clip=2.0, clahe_tiles=4)
+        assert np.array_equal(c.preprocess_batch(img[None])[0], orc.clahe(orc.remap_linear(img, mx, my), 2.0, 4))
+
+
 def test_errors(ctx, vpl):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(np.zeros((1, 2000, 2000), np.uint8))       # larger than the context

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvplines_b200.so")
 
 VPL_OK, VPL_E_INVALID, VPL_E_CUDA, VPL_E_CAPACITY, VPL_E_NODEVICE = 0, -1, -2, -3, -4
-STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h"]
+STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h", "preproc"]
 
 KEYLINE_DTYPE = np.dtype(
     [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
@@ -38,6 +38,7 @@ EXPORTS = [
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
     "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
+    "vpl_set_preprocess", "vpl_preprocess_batch",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -77,6 +78,8 @@ def load():
     L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
     L.vpl_sync.argtypes = [vp]
     L.vpl_frontend_collect_dense.argtypes = [vp, i32, vp, vp, vp, vp, C.c_int64, vp]
+    L.vpl_set_preprocess.argtypes = [vp, vp, vp, i32, i32, C.c_double, i32]
+    L.vpl_preprocess_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp]
     L.vpl_host_register.argtypes = [vp, vp, sz]
     L.vpl_host_unregister.argtypes = [vp, vp]
     L.vpl_last_d2h_bytes.argtypes = [vp, i32]
@@ -226,6 +229,22 @@ class Context:
         self._ck(self._L.vpl_frontend_collect_dense(self._h, slot, _ptr(counts), _ptr(kl), _ptr(desc), _ptr(matches),
                                                     len(kl), C.byref(total)))
         return int(total.value)
+
+    def set_preprocess(self, mapx=None, mapy=None, size=None, clahe_clip=0.0, clahe_tiles=8):
+        """Undistortion maps (float32 HxW each, or None) and CLAHE clip limit (<= 0: off)."""
+        if mapx is not None:
+            mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+            h, w = mapx.shape
+        else:
+            w, h = size
+        self._keep_maps = (mapx, mapy)
+        self._ck(self._L.vpl_set_preprocess(self._h, _ptr(mapx), _ptr(mapy), w, h, float(clahe_clip), clahe_tiles))
+
+    def preprocess_batch(self, frames):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        out = np.zeros((n, h, w), np.uint8)
+        self._ck(self._L.vpl_preprocess_batch(self._h, ptrs, n, w, h, stride, _ptr(out)))
+        return out
 
     def host_register(self, arr):
         """Pin a numpy frame buffer so that submits from it skip the staging copy."""

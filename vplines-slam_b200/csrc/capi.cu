@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,8 @@ struct Slot {
   cudaEvent_t ev[VPL_NUM_STAGES][2];
   bool ev_used[VPL_NUM_STAGES];
   uint8_t* d_img = nullptr;
+  uint8_t* d_pre = nullptr;   // remap output (pre-processing scratch)
+  uint8_t* d_lut = nullptr;   // CLAHE tile LUTs, B x 256 tiles max x 256
   OctBuf oct[kMaxOctaves];
   VplKeyLine* d_kl = nullptr;
   int* d_counts = nullptr;
@@ -89,6 +92,13 @@ struct VplContext {
   double* d_lgam = nullptr;  // log_gamma table for the NFA kernel
   int lgam_n = 0;
   std::vector<std::pair<const uint8_t*, size_t>> pinned;  // vpl_host_register ranges
+  // optional pre-processing (readImage: remap + CLAHE)
+  float* d_mapx = nullptr;
+  float* d_mapy = nullptr;
+  uint16_t* d_wtab = nullptr;
+  int pre_w = 0, pre_h = 0, pre_tiles = 8;
+  bool pre_remap = false;
+  double pre_clip = 0.0;
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -453,8 +463,27 @@ int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int
   bool direct = (stride == (size_t)w) && in_registered_range(c, imgs[0], (size_t)n * w * h);
   for (int f = 1; direct && f < n; ++f) direct = (imgs[f] == imgs[0] + (size_t)f * w * h);
   if (!direct) stage_images(s, imgs, n, w, h, stride);
-  StageTimer t(c, s, VPL_STAGE_H2D);
-  CK(c, cudaMemcpyAsync(s.d_img, direct ? imgs[0] : s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
+  {
+    StageTimer t(c, s, VPL_STAGE_H2D);
+    CK(c, cudaMemcpyAsync(s.d_img, direct ? imgs[0] : s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
+  }
+  if (c->pre_remap || c->pre_clip > 0.0) {
+    if (w != c->pre_w || h != c->pre_h)
+      return fail(c, VPL_E_INVALID, "pre-processing was configured for %dx%d images, got %dx%d", c->pre_w, c->pre_h, w, h);
+    StageTimer t(c, s, VPL_STAGE_PREPROC);
+    const uint8_t* cur = s.d_img;
+    if (c->pre_remap) {
+      launch_remap(s.d_img, s.d_pre, c->d_mapx, c->d_mapy, c->d_wtab, w, h, n, s.stream);
+      t.launches(1);
+      cur = s.d_pre;
+    }
+    if (c->pre_clip > 0.0) {
+      launch_clahe(cur, s.d_img, s.d_lut, w, h, c->pre_clip, c->pre_tiles, n, s.stream);  // in place when cur == d_img
+      t.launches(2);
+    } else {
+      CK(c, cudaMemcpyAsync(s.d_img, s.d_pre, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
+    }
+  }
   return VPL_OK;
 }
 
@@ -507,9 +536,10 @@ void vpl_destroy(VplContext* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
+  cudaFree(c->d_mapx); cudaFree(c->d_mapy); cudaFree(c->d_wtab);
   cudaFree(c->d_lgam);
   for (Slot& s : c->slots) {
-    cudaFree(s.d_img);
+    cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
       cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.ord);
@@ -600,6 +630,8 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     for (int i = 0; i < VPL_NUM_STAGES; ++i)
       for (int j = 0; j < 2; ++j) CKC(cudaEventCreate(&s.ev[i][j]));
     CKC(dmalloc(&s.d_img, B * P0));
+    CKC(dmalloc(&s.d_pre, B * P0));
+    CKC(dmalloc(&s.d_lut, B * 256 * 256));
     for (int o = 0; o < cfg->max_octaves; ++o) {
       // worst case over aspect ratios with the same area: size by area with slack
       size_t Po = (P0 >> (2 * o)) + 64;
@@ -758,6 +790,80 @@ int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
   int r = enqueue_frontend(c, slot, k, 0);
   if (r) return r;
   CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_set_preprocess(VplContext* c, const float* mapx, const float* mapy, int w, int h, double clahe_clip,
+                       int clahe_tiles) {
+  if (!c) return VPL_E_INVALID;
+  if (w <= 0 || h <= 0 || w > c->cfg.max_width || h > c->cfg.max_height)
+    return fail(c, VPL_E_CAPACITY, "pre-processing size %dx%d outside the context's %dx%d", w, h, c->cfg.max_width, c->cfg.max_height);
+  if ((mapx == nullptr) != (mapy == nullptr)) return fail(c, VPL_E_INVALID, "give both maps or neither");
+  if (clahe_clip > 0.0 && (clahe_tiles < 1 || clahe_tiles > 16)) return fail(c, VPL_E_INVALID, "CLAHE grid must be 1..16 tiles per side");
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots) CK(c, cudaStreamSynchronize(s.stream));
+  cudaFree(c->d_mapx); cudaFree(c->d_mapy);
+  c->d_mapx = c->d_mapy = nullptr;
+  c->pre_remap = false;
+  if (mapx) {
+    const size_t bytes = (size_t)w * h * sizeof(float);
+    CK(c, cudaMalloc((void**)&c->d_mapx, bytes));
+    CK(c, cudaMalloc((void**)&c->d_mapy, bytes));
+    CK(c, cudaMemcpy(c->d_mapx, mapx, bytes, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_mapy, mapy, bytes, cudaMemcpyHostToDevice));
+    if (!c->d_wtab) {
+      // OpenCV's bilinear weight table (initInterTab2D): 32x32 x 4 weights summing to 32768
+      std::vector<uint16_t> tab(32 * 32 * 4);
+      for (int i = 0; i < 32; ++i) {
+        float fy = (float)i / 32.0f;
+        for (int j = 0; j < 32; ++j) {
+          float fx = (float)j / 32.0f;
+          float wy[2] = {1.0f - fy, fy}, wx[2] = {1.0f - fx, fx};
+          int it[4], isum = 0;
+          for (int k = 0; k < 4; ++k) {
+            volatile float v = wy[k >> 1] * wx[k & 1];
+            long r = lrintf(v * 32768.0f);
+            it[k] = (int)std::min<long>(32767, std::max<long>(-32768, r));
+            isum += it[k];
+          }
+          if (isum != 32768) {
+            int diff = isum - 32768, kmax = 0, kmin = 0;
+            for (int k = 1; k < 4; ++k) {
+              if (it[k] > it[kmax]) kmax = k;
+              if (it[k] < it[kmin]) kmin = k;
+            }
+            if (diff < 0) it[kmax] -= diff;
+            else it[kmin] -= diff;
+          }
+          for (int k = 0; k < 4; ++k) tab[(size_t)(i * 32 + j) * 4 + k] = (uint16_t)it[k];
+        }
+      }
+      CK(c, cudaMalloc((void**)&c->d_wtab, tab.size() * sizeof(uint16_t)));
+      CK(c, cudaMemcpy(c->d_wtab, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    c->pre_remap = true;
+  }
+  c->pre_clip = clahe_clip > 0.0 ? clahe_clip : 0.0;
+  c->pre_tiles = clahe_tiles;
+  c->pre_w = w; c->pre_h = h;
+  return VPL_OK;
+}
+
+int vpl_preprocess_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, uint8_t* out) {
+  int r = check_dims(c, n, w, h, 1, 2);
+  if (r) return r;
+  if (!out) return fail(c, VPL_E_INVALID, "null output");
+  if (n == 0) return VPL_OK;
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  s.n = n; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 2; s.k = 0;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  CK(c, cudaMemcpyAsync(s.h_img, s.d_img, (size_t)n * w * h, cudaMemcpyDeviceToHost, s.stream));
+  r = finish(c, s);
+  if (r) return r;
+  memcpy(out, s.h_img, (size_t)n * w * h);
   return VPL_OK;
 }
 

@@ -162,6 +162,11 @@ void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int c
 void launch_hamming_knn(const uint8_t* q, const int* nq, int cap_q, const uint8_t* t, const int* nt, int cap_t,
                         int n_pairs, int k, VplDMatch* out, cudaStream_t st);
 void lbd_init_tables();
+void launch_remap(const uint8_t* src, uint8_t* dst, const float* mapx, const float* mapy, const uint16_t* wtab,
+                  int w, int h, int batch, cudaStream_t st);
+// lut: batch x tiles x tiles x 256 bytes of scratch
+void launch_clahe(const uint8_t* src, uint8_t* dst, uint8_t* lut, int w, int h, double clip, int tiles, int batch,
+                  cudaStream_t st);
 #ifdef VPL_DEBUG_NFA
 void debug_set_cand(int c);
 #endif
