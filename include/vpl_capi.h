@@ -122,6 +122,11 @@ int vpl_lbd_compute_batch(VplContext* ctx, const uint8_t* const* imgs, int n, in
                           size_t stride, const VplKeyLine* keylines, const int32_t* counts,
                           int cap, uint8_t* desc);
 
+/* Same with returnFloatDescr = true: fdesc holds n*cap*72 floats (CV_32FC1 rows of 72). */
+int vpl_lbd_compute_float_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                                size_t stride, const VplKeyLine* keylines, const int32_t* counts,
+                                int cap, float* fdesc);
+
 /* ---- BinaryDescriptorMatcher::match / knnMatch (replaces match_line_match,
  *      linefeature_tracker.h:76-79) ------------------------------------------- */
 /* n_pairs independent (query, train) problems.  q: n_pairs*cap_q*32 bytes, pair p at

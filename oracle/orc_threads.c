@@ -8,6 +8,7 @@
  */
 #define _GNU_SOURCE
 #include "vpl_oracle.h"
+#include <malloc.h>
 #include <pthread.h>
 #include <stdlib.h>
 
@@ -30,6 +31,10 @@ int64_t orc_frontend_sequence_mt(const uint8_t* frames, int n_frames, int w, int
                                  int num_octaves, int max_lines, int n_threads) {
   if (n_threads < 1) n_threads = 1;
   if (n_threads > n_frames) n_threads = n_frames;
+  /* the per-frame scratch images are MBs each: keep them in the per-thread arenas instead of
+   * mmap/munmap per frame, which serialises the threads in the kernel (a fair CPU baseline) */
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
   pthread_t* th = (pthread_t*)malloc((size_t)n_threads * sizeof(pthread_t));
   Job* jobs = (Job*)malloc((size_t)n_threads * sizeof(Job));
   for (int t = 0; t < n_threads; ++t) {

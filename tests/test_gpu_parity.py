@@ -106,6 +106,15 @@ def test_lbd_bit_exact_on_identical_keylines(ctx, orc, mh04):
         assert np.array_equal(got[f], orc.lbd_compute(img, kls[f])), f"frame {f}"
 
 
+def test_lbd_float_descriptors_bit_exact(ctx, orc, mh04):
+    """returnFloatDescr=true: the 72-float LBD vectors, bit for bit."""
+    img = mh04[1]
+    kl = orc.lsd_detector_detect(img, 2, 2)
+    _, fd = orc.lbd_compute(img, kl, return_float=True)
+    got = ctx.lbd_compute_float_batch(img[None], [kl])[0]
+    assert got.shape == fd.shape and got.tobytes() == fd.tobytes()
+
+
 def test_lbd_edge_keylines(ctx, orc, mh04):
     """lines hugging the border / very short / long: the clamped sampling must agree."""
     img = mh04[2]

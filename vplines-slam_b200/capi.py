@@ -35,7 +35,7 @@ class VplConfig(C.Structure):
 
 EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
-    "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch", "vpl_frontend_batch",
+    "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_lbd_compute_float_batch", "vpl_match_batch", "vpl_frontend_batch",
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
     "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
     "vpl_set_preprocess", "vpl_preprocess_batch",
@@ -71,6 +71,7 @@ def load():
     L.vpl_version.restype = C.c_char_p
     L.vpl_lsd_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, vp, vp, i32]
     L.vpl_lbd_compute_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32, vp]
+    L.vpl_lbd_compute_float_batch.argtypes = [vp, vp, i32, i32, i32, sz, vp, vp, i32, vp]
     L.vpl_match_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
     L.vpl_frontend_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32, i32, i32, i32]
@@ -181,6 +182,19 @@ class Context:
         self._ck(self._L.vpl_lbd_compute_batch(self._h, ptrs, n, w, h, stride, _ptr(kl), _ptr(counts), cap,
                                                _ptr(desc)))
         return [desc[f, :counts[f]].copy() for f in range(n)]
+
+    def lbd_compute_float_batch(self, frames, keylines, cap=None):
+        """BinaryDescriptor::compute(..., returnFloatDescr=True): [n_lines, 72] float32 per frame."""
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        cap = cap or max(1, max(len(k) for k in keylines))
+        kl = np.zeros((n, cap), KEYLINE_DTYPE)
+        counts = np.array([len(k) for k in keylines], np.int32)
+        for f, k in enumerate(keylines):
+            kl[f, :len(k)] = k
+        fd = np.zeros((n, cap, 72), np.float32)
+        self._ck(self._L.vpl_lbd_compute_float_batch(self._h, ptrs, n, w, h, stride, _ptr(kl), _ptr(counts), cap,
+                                                     _ptr(fd)))
+        return [fd[f, :counts[f]].copy() for f in range(n)]
 
     # -- BinaryDescriptorMatcher::match / knnMatch ------------------------------
     def match_batch(self, queries, trains, k=1):

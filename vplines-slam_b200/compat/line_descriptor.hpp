@@ -167,15 +167,21 @@ class BinaryDescriptor {
   int descriptorSize() const { return 32; }
   void compute(const Mat& image, std::vector<KeyLine>& keylines, Mat& descriptors, bool returnFloatDescr = false) const {
     detail::check_u8(image);
-    if (returnFloatDescr) throw std::runtime_error("vplines_b200: returnFloatDescr=true is not produced by the B200 path");
     if (keylines.empty()) { std::printf("Error: keypoint list is empty\n"); return; }
     int maxOct = 0;
     for (const KeyLine& k : keylines) maxOct = std::max(maxOct, k.octave);
     const int n = (int)keylines.size();
     VplContext* h = detail::ctx().get(image.cols, image.rows, maxOct + 1, n);
-    descriptors.create(n, 32, CV_8UC1);
     const uint8_t* p[1] = {image.data};
     int32_t count = n;
+    if (returnFloatDescr) {
+      descriptors.create(n, 72, CV_32FC1);
+      detail::check(h, vpl_lbd_compute_float_batch(h, p, 1, image.cols, image.rows, image.step,
+                                                   reinterpret_cast<const VplKeyLine*>(keylines.data()), &count, n,
+                                                   reinterpret_cast<float*>(descriptors.data)));
+      return;
+    }
+    descriptors.create(n, 32, CV_8UC1);
     detail::check(h, vpl_lbd_compute_batch(h, p, 1, image.cols, image.rows, image.step,
                                            reinterpret_cast<const VplKeyLine*>(keylines.data()), &count, n, descriptors.data));
   }

@@ -302,7 +302,7 @@ void run_pack(VplContext* c, Slot& s) {
   t.launches(1);
 }
 
-void run_lbd(VplContext* c, Slot& s, int num_octaves) {
+void run_lbd(VplContext* c, Slot& s, int num_octaves, float* fdesc = nullptr) {
   StageTimer t(c, s, VPL_STAGE_LBD);
   LbdArgs a;
   memset(&a, 0, sizeof(a));
@@ -312,7 +312,7 @@ void run_lbd(VplContext* c, Slot& s, int num_octaves) {
     octave_geom(s.w, s.h, o, wo, ho, ws, hs);
     a.grad[o] = s.oct[o].grad; a.w[o] = wo; a.h[o] = ho;
   }
-  launch_lbd(a, s.d_kl, s.d_counts, c->cfg.max_lines, s.d_desc, s.n, s.stream);
+  launch_lbd(a, s.d_kl, s.d_counts, c->cfg.max_lines, s.d_desc, fdesc, s.n, s.stream);
   t.launches(1);
 }
 
@@ -969,6 +969,35 @@ int vpl_lbd_compute_batch(VplContext* c, const uint8_t* const* imgs, int n, int 
   r = finish(c, s);
   if (r) return r;
   copy_rows(desc, s.h_desc, counts, n, mc, (size_t)cap, 32);
+  return VPL_OK;
+}
+
+int vpl_lbd_compute_float_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                                const VplKeyLine* keylines, const int32_t* counts, int cap, float* fdesc) {
+  // BinaryDescriptor::compute(..., returnFloatDescr = true): the 72-float LBD vectors.
+  if (!c) return VPL_E_INVALID;
+  if (!keylines || !counts || !fdesc) return fail(c, VPL_E_INVALID, "null argument");
+  const size_t mc = (size_t)c->cfg.max_lines;
+  // float rows live in the octave-0 region scratch (16 B per scaled pixel per frame), which is idle here
+  std::vector<uint8_t> bytes((size_t)std::max(n, 1) * cap * 32);
+  int wo, ho, ws, hs;
+  octave_geom(w, h, 0, wo, ho, ws, hs);
+  if (mc * 72 * sizeof(float) > (size_t)ws * hs * sizeof(RegEnt))
+    return fail(c, VPL_E_CAPACITY, "max_lines too large for the float-descriptor scratch at this image size");
+  // run the byte path first (validates arguments, uploads, builds the pyramid), then re-run LBD with the float sink
+  int r = vpl_lbd_compute_batch(c, imgs, n, w, h, stride, keylines, counts, cap, bytes.data());
+  if (r) return r;
+  if (n == 0) return VPL_OK;
+  Slot& s = c->slots[0];
+  // frames are `ws*hs*sizeof(RegEnt)` apart in the scratch, rows mc*72 floats: use a compact stride of mc*72 floats
+  float* d_f = reinterpret_cast<float*>(s.oct[0].reg);
+  run_lbd(c, s, s.num_octaves, d_f);
+  std::vector<float> tmp((size_t)n * mc * 72);
+  CK(c, cudaMemcpyAsync(tmp.data(), d_f, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+  r = finish(c, s);
+  if (r) return r;
+  for (int f = 0; f < n; ++f)
+    memcpy(fdesc + (size_t)f * cap * 72, tmp.data() + (size_t)f * mc * 72, (size_t)counts[f] * 72 * sizeof(float));
   return VPL_OK;
 }
 

@@ -59,7 +59,7 @@ constexpr int LBD_WARPS = 4;
 
 __global__ void __launch_bounds__(LBD_WARPS * 32)
 lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict__ counts, int cap,
-           uint8_t* __restrict__ desc_) {
+           uint8_t* __restrict__ desc_, float* __restrict__ fdesc_) {
   __shared__ float s_row[LBD_WARPS][LSP_H][8];
   __shared__ float s_des[LBD_WARPS][72];
   const int f = blockIdx.y;
@@ -173,7 +173,10 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
   for (int i = 0; i < 72; ++i) temp += des[i] * des[i];
   temp = 1.0f / sqrtf(temp);
   __syncwarp();
-  for (int i = lane; i < 72; i += 32) des[i] = des[i] * temp;
+  for (int i = lane; i < 72; i += 32) {
+    des[i] = des[i] * temp;
+    if (fdesc_) fdesc_[((size_t)f * cap + li) * 72 + i] = des[i];  // returnFloatDescr = true
+  }
   __syncwarp();
   // binarisation: lane c -> byte c
   {
@@ -187,10 +190,10 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
   }
 }
 
-void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, int batch,
-                cudaStream_t st) {
+void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, float* fdesc,
+                int batch, cudaStream_t st) {
   dim3 grid((cap + LBD_WARPS - 1) / LBD_WARPS, batch);
-  lbd_kernel<<<grid, LBD_WARPS * 32, 0, st>>>(a, kl, counts, cap, desc);
+  lbd_kernel<<<grid, LBD_WARPS * 32, 0, st>>>(a, kl, counts, cap, desc, fdesc);
 }
 
 // ---------------------------------------------------------------------------

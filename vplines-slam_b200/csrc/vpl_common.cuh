@@ -157,8 +157,8 @@ struct LbdArgs {
   int w[kMaxOctaves], h[kMaxOctaves];
   int num_octaves;
 };
-void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, int batch,
-                cudaStream_t st);
+void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, float* fdesc,
+                int batch, cudaStream_t st);
 void launch_hamming_knn(const uint8_t* q, const int* nq, int cap_q, const uint8_t* t, const int* nt, int cap_t,
                         int n_pairs, int k, VplDMatch* out, cudaStream_t st);
 void lbd_init_tables();

@@ -145,14 +145,14 @@ class BinaryDescriptor:
     def compute(self, image, keylines, returnFloatDescr=False):
         """void compute(const Mat& image, std::vector<KeyLine>& keylines, Mat& descriptors, bool returnFloatDescr)"""
         image = _gray_u8(image, "BinaryDescriptor::compute")
-        if returnFloatDescr:
-            raise NotImplementedError("returnFloatDescr=true is not produced by the B200 path")
         if len(keylines) == 0:
             print("Error: keypoint list is empty")
             return np.zeros((0, 32), np.uint8)
         rec = records_from_keylines(keylines)
         h, w = image.shape
         ctx = _context(w, h, int(rec["octave"].max()) + 1, max(4096, len(rec)))
+        if returnFloatDescr:
+            return ctx.lbd_compute_float_batch(image[None], [rec])[0]
         return ctx.lbd_compute_batch(image[None], [rec])[0]
 
 
