@@ -13,24 +13,88 @@
 namespace vpl {
 
 // ---------------------------------------------------------------------------
+// Separable 5-tap fixed-point Gaussian (taps W0 W1 W2 W1 W0, sum 256) of a byte tile held in
+// shared memory, with packed arithmetic.  Both passes are exact integer sums and there is a
+// single rounding at the end, so doing the vertical pass first gives the same bytes as
+// OpenCV's row-then-column order.
+//   vertical pass  : one 32-bit word = 4 pixels; even and odd bytes are split into two
+//                    16-bit lanes each (SWAR): 14*(E0+E4) + 62*(E1+E3) + 104*E2 never exceeds
+//                    255*256 = 65280 per lane, so there is no carry between lanes;
+//   horizontal pass: the 16-bit column sums are consumed two at a time by dp2a (u16 x u8 dot
+//                    product, 32-bit accumulate), four output pixels per thread, then
+//                    (v + 32768) >> 16.
+// s_in : in_rows x (4*in_words) bytes, pitch in_pitch bytes (multiple of 4)
+// s_v  : (in_rows-4) x (4*in_words) u16, pitch v_pitch elements (multiple of 4)
+// s_out: (in_rows-4) x 4*(in_words-1) bytes; s_out[r][c] is the blurred pixel of input
+//        position (r+2, c+2); pitch out_pitch bytes (multiple of 4)
+// ---------------------------------------------------------------------------
+template <int W0, int W1, int W2>
+__device__ __forceinline__ void blur5_tile_packed(const uint8_t* s_in, int in_pitch, int in_rows, int in_words,
+                                                  uint16_t* s_v, int v_pitch, uint8_t* s_out, int out_pitch,
+                                                  int tid, int nthreads) {
+  const int vrows = in_rows - 4;
+  for (int i = tid; i < vrows * in_words; i += nthreads) {
+    const int r = i / in_words, wc = i - r * in_words;
+    const uint8_t* p = s_in + r * in_pitch + 4 * wc;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(p);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(p + in_pitch);
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(p + 2 * in_pitch);
+    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(p + 3 * in_pitch);
+    const uint32_t w4 = *reinterpret_cast<const uint32_t*>(p + 4 * in_pitch);
+    const uint32_t M = 0x00ff00ffu;
+    uint32_t e = (uint32_t)W0 * ((w0 & M) + (w4 & M)) + (uint32_t)W1 * ((w1 & M) + (w3 & M)) + (uint32_t)W2 * (w2 & M);
+    uint32_t o = (uint32_t)W0 * (((w0 >> 8) & M) + ((w4 >> 8) & M)) + (uint32_t)W1 * (((w1 >> 8) & M) + ((w3 >> 8) & M)) +
+                 (uint32_t)W2 * ((w2 >> 8) & M);
+    // e = (px0, px2), o = (px1, px3) as 16-bit lanes -> natural order (px0,px1), (px2,px3)
+    uint2 v;
+    v.x = __byte_perm(e, o, 0x5410);
+    v.y = __byte_perm(e, o, 0x7632);
+    *reinterpret_cast<uint2*>(s_v + r * v_pitch + 4 * wc) = v;
+  }
+  __syncthreads();
+  constexpr uint32_t B01 = (uint32_t)W0 | ((uint32_t)W1 << 8);  // (W0, W1)
+  constexpr uint32_t B21 = (uint32_t)W2 | ((uint32_t)W1 << 8);  // (W2, W1)
+  constexpr uint32_t B0_ = (uint32_t)W0;                         // (W0, 0)
+  constexpr uint32_t B_0 = ((uint32_t)W0 << 8);                  // (0, W0)
+  constexpr uint32_t B12 = (uint32_t)W1 | ((uint32_t)W2 << 8);  // (W1, W2)
+  constexpr uint32_t B10 = (uint32_t)W1 | ((uint32_t)W0 << 8);  // (W1, W0)
+  const int groups = in_words - 1;
+  for (int i = tid; i < vrows * groups; i += nthreads) {
+    const int r = i / groups, g = i - r * groups;
+    const uint2 a = *reinterpret_cast<const uint2*>(s_v + r * v_pitch + 4 * g);      // v0..v3
+    const uint2 c = *reinterpret_cast<const uint2*>(s_v + r * v_pitch + 4 * g + 4);  // v4..v7
+    uint32_t o0 = __dp2a_lo(a.x, B01, __dp2a_lo(a.y, B21, __dp2a_lo(c.x, B0_, 32768u)));
+    uint32_t o1 = __dp2a_lo(a.x, B_0, __dp2a_lo(a.y, B12, __dp2a_lo(c.x, B10, 32768u)));
+    uint32_t o2 = __dp2a_lo(a.y, B01, __dp2a_lo(c.x, B21, __dp2a_lo(c.y, B0_, 32768u)));
+    uint32_t o3 = __dp2a_lo(a.y, B_0, __dp2a_lo(c.x, B12, __dp2a_lo(c.y, B10, 32768u)));
+    // bits 16..23 of each sum are the result bytes
+    uint32_t lo = __byte_perm(o0, o1, 0x0062);  // byte2(o0), byte2(o1)
+    uint32_t hi = __byte_perm(o2, o3, 0x0062);
+    *reinterpret_cast<uint32_t*>(s_out + r * out_pitch + 4 * g) = __byte_perm(lo, hi, 0x5410);
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
 // K1: GaussianBlur(5x5, sigma 1) fused with Sobel 3x3 (dx,dy int16).
-// Fixed-point kernel [14 62 104 62 14]/256: horizontal pass exact in 8.8,
-// vertical in 16.16, (v + 32768) >> 16.  BORDER_REFLECT_101 on both stages; the
-// reflect-extended input is symmetric about the border pixel and the kernel is
-// symmetric, so blurring the extended tile yields exactly the reflected blurred
-// halo the Sobel stage needs.
+// Fixed-point kernel [14 62 104 62 14]/256, (v + 32768) >> 16.  BORDER_REFLECT_101 on both
+// stages; the reflect-extended input is symmetric about the border pixel and the kernel is
+// symmetric, so blurring the extended tile yields exactly the reflected blurred halo the
+// Sobel stage needs.  64x32 output tile, input tile 72x38 bytes loaded as 32-bit words.
 // Algorithmic bytes: read P, write P (pyr) + 4P (grad) = 6P per frame.
 // ---------------------------------------------------------------------------
 constexpr int B5_TW = 64, B5_TH = 32, B5_THREADS = 256;
-constexpr int B5_IW = B5_TW + 8;  // input tile: x0-4 .. x0+TW+4 (word aligned)
-constexpr int B5_IH = B5_TH + 6;  // y0-3 .. y0+TH+3
+constexpr int B5_IW = B5_TW + 8;  // input tile: x0-4 .. x0+TW+3 (word aligned), 18 words
+constexpr int B5_IH = B5_TH + 6;  // y0-3 .. y0+TH+2
+constexpr int B5_OW = B5_IW - 4;  // blurred tile: 68 columns, column c <-> gx = x0-2+c
+constexpr int B5_OH = B5_IH - 4;  // 34 rows, row r <-> gy = y0-1+r
 
 __global__ void __launch_bounds__(B5_THREADS)
 blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
                    short2* __restrict__ grad, int w, int h, int do_blur) {
   __shared__ __align__(16) uint8_t s_in[B5_IH][B5_IW];
-  __shared__ uint16_t s_hb[B5_IH][B5_TW + 2];
-  __shared__ __align__(4) uint8_t s_bl[B5_TH + 2][B5_TW + 4];  // [.][1 + x], x=-1..TW
+  __shared__ __align__(16) uint16_t s_v[B5_OH][B5_IW];
+  __shared__ __align__(16) uint8_t s_bl[B5_OH][B5_IW];
 
   const size_t frame = (size_t)blockIdx.z * w * h;
   const uint8_t* src = img + frame;
@@ -56,45 +120,44 @@ blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
   __syncthreads();
 
   if (do_blur) {
-    // ---- horizontal pass: columns x0-1 .. x0+TW  (s_in column = gx - (x0-4))
-    for (int i = tid; i < B5_IH * (B5_TW + 2); i += B5_THREADS) {
-      int r = i / (B5_TW + 2), c = i % (B5_TW + 2);
-      const uint8_t* p = &s_in[r][c + 3 - 2];  // gx = x0-1+c -> col c+3
-      s_hb[r][c] = (uint16_t)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
+    blur5_tile_packed<14, 62, 104>(&s_in[0][0], B5_IW, B5_IH, B5_IW / 4, &s_v[0][0], B5_IW, &s_bl[0][0], B5_IW, tid,
+                                   B5_THREADS);
+  } else {
+    for (int i = tid; i < B5_OH * (B5_OW / 4); i += B5_THREADS) {
+      int r = i / (B5_OW / 4), c = 4 * (i % (B5_OW / 4));
+      // s_bl[r][c] = s_in[r+2][c+2]: unaligned by two bytes
+      uint32_t lo = *reinterpret_cast<const uint32_t*>(&s_in[r + 2][c]);
+      uint32_t hi = *reinterpret_cast<const uint32_t*>(&s_in[r + 2][c + 4]);
+      *reinterpret_cast<uint32_t*>(&s_bl[r][c]) = __byte_perm(lo, hi, 0x5432);
     }
     __syncthreads();
-    // ---- vertical pass: rows y0-1 .. y0+TH
-    for (int i = tid; i < (B5_TH + 2) * (B5_TW + 2); i += B5_THREADS) {
-      int r = i / (B5_TW + 2), c = i % (B5_TW + 2);
-      uint32_t s = 14u * (s_hb[r][c] + s_hb[r + 4][c]) + 62u * (s_hb[r + 1][c] + s_hb[r + 3][c]) + 104u * s_hb[r + 2][c];
-      s_bl[r][c + 1] = (uint8_t)((s + 32768u) >> 16);
-    }
-  } else {
-    for (int i = tid; i < (B5_TH + 2) * (B5_TW + 2); i += B5_THREADS) {
-      int r = i / (B5_TW + 2), c = i % (B5_TW + 2);
-      s_bl[r][c + 1] = s_in[r + 2][c + 3];
-    }
   }
-  __syncthreads();
 
-  // ---- Sobel + stores: each thread handles 4 consecutive pixels of a row
+  // ---- Sobel + stores: each thread handles 4 consecutive pixels of a row.
+  // output pixel (x0+c+k, y0+r) is blurred column c+k+2, row r+1 of s_bl
   for (int i = tid; i < B5_TH * (B5_TW / 4); i += B5_THREADS) {
     int r = i >> 4, c = 4 * (i & 15);  // B5_TW / 4 == 16
     int gy = y0 + r, gx = x0 + c;
     if (gy >= h || gx >= w) continue;
-    uint32_t packed = 0;
+    // bytes c .. c+7 of the three rows; the window needed is columns c+1 .. c+6
+    uint2 ra, rm, rb;  // (c is a multiple of 4 only: two 32-bit loads per row)
+    ra.x = *reinterpret_cast<const uint32_t*>(&s_bl[r][c]);     ra.y = *reinterpret_cast<const uint32_t*>(&s_bl[r][c + 4]);
+    rm.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c]); rm.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c + 4]);
+    rb.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c]); rb.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c + 4]);
+    int C[6], D[6];  // column sums a+2m+b and column differences b-a for columns c+1 .. c+6
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int bi = j + 1;
+      const int a = (bi < 4) ? (int)((ra.x >> (8 * bi)) & 0xff) : (int)((ra.y >> (8 * (bi - 4))) & 0xff);
+      const int m = (bi < 4) ? (int)((rm.x >> (8 * bi)) & 0xff) : (int)((rm.y >> (8 * (bi - 4))) & 0xff);
+      const int b = (bi < 4) ? (int)((rb.x >> (8 * bi)) & 0xff) : (int)((rb.y >> (8 * (bi - 4))) & 0xff);
+      C[j] = a + 2 * m + b;
+      D[j] = b - a;
+    }
     short2 g[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // blurred pixel (gx+k, gy) is s_bl[r+1][c+k+2]
-      const uint8_t* a = &s_bl[r][c + k + 1];      // row above, x-1
-      const uint8_t* m = &s_bl[r + 1][c + k + 1];  // same row
-      const uint8_t* b = &s_bl[r + 2][c + k + 1];  // row below
-      int dx = (a[2] + 2 * m[2] + b[2]) - (a[0] + 2 * m[0] + b[0]);
-      int dy = (b[0] + 2 * b[1] + b[2]) - (a[0] + 2 * a[1] + a[2]);
-      g[k] = make_short2((short)dx, (short)dy);
-      packed |= (uint32_t)m[1] << (8 * k);
-    }
+    for (int k = 0; k < 4; ++k) g[k] = make_short2((short)(C[k + 2] - C[k]), (short)(D[k] + 2 * D[k + 1] + D[k + 2]));
+    const uint32_t packed = __byte_perm(rm.x, rm.y, 0x5432);  // blurred centre pixels c+2 .. c+5
     size_t o = frame + (size_t)gy * w + gx;
     if (wordable && gx + 3 < w) {
       *reinterpret_cast<uint32_t*>(pyr + o) = packed;
@@ -179,37 +242,38 @@ void launch_sobel(const uint8_t* src, short2* grad, int w, int h, int batch, cud
 // Algorithmic bytes: read P, write 0.64 P.
 // ---------------------------------------------------------------------------
 constexpr int SC_TW = 64, SC_TH = 16, SC_THREADS = 256;
-constexpr int SC_GW = 81, SC_GH = 21;        // blurred block
-constexpr int SC_IW = SC_GW + 4, SC_IH = SC_GH + 4;
+constexpr int SC_GH = 21;                // blurred block: columns sx0-2 .. sx0+81 (81 needed), rows sy0 .. sy0+20
+constexpr int SC_IW = 88, SC_IH = 25;   // input block: columns sx0-4 .. sx0+83 (22 words), rows sy0-2 .. sy0+22
 
 __global__ void __launch_bounds__(SC_THREADS)
 scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int w, int h, int ws, int hs) {
-  __shared__ uint8_t s_in[SC_IH][SC_IW + 3];
-  __shared__ uint16_t s_hb[SC_IH][SC_GW + 1];
-  __shared__ uint8_t s_g[SC_GH][SC_GW + 3];
+  __shared__ __align__(16) uint8_t s_in[SC_IH][SC_IW];
+  __shared__ __align__(16) uint16_t s_v[SC_GH][SC_IW];
+  __shared__ __align__(16) uint8_t s_g[SC_GH][SC_IW];  // s_g[r][c]: blurred pixel (sx0 - 2 + c, sy0 + r)
   const uint8_t* src = src_ + (size_t)blockIdx.z * w * h;
   uint8_t* dst = dst_ + (size_t)blockIdx.z * ws * hs;
   const int dx0 = blockIdx.x * SC_TW, dy0 = blockIdx.y * SC_TH;
-  const int sx0 = (10 * dx0 + 1) >> 3, sy0 = (10 * dy0 + 1) >> 3;  // first source col/row of the tile
+  const int sx0 = (10 * dx0 + 1) >> 3, sy0 = (10 * dy0 + 1) >> 3;  // first source col/row of the tile (sx0 % 4 == 0)
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;  // 32 x 8 threads
+  const bool wordable = ((w & 3) == 0);
   for (int r = ty; r < SC_IH; r += 8) {
     const uint8_t* srow = src + (size_t)refl101(sy0 - 2 + r, h) * w;
-    for (int c = tx; c < SC_IW; c += 32) s_in[r][c] = __ldg(srow + refl101(sx0 - 2 + c, w));
+    if (tx < SC_IW / 4) {
+      const int gx = sx0 - 4 + 4 * tx;
+      uint32_t v;
+      if (wordable && gx >= 0 && gx + 3 < w) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(srow + gx));
+      } else {
+        v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v |= (uint32_t)__ldg(srow + refl101(gx + b, w)) << (8 * b);
+      }
+      *reinterpret_cast<uint32_t*>(&s_in[r][4 * tx]) = v;
+    }
   }
   __syncthreads();
-  for (int r = ty; r < SC_IH; r += 8)
-    for (int c = tx; c < SC_GW; c += 32) {
-      const uint8_t* p = &s_in[r][c];
-      s_hb[r][c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
-    }
-  __syncthreads();
-  for (int r = ty; r < SC_GH; r += 8)
-    for (int c = tx; c < SC_GW; c += 32) {
-      uint32_t s = 4u * (s_hb[r][c] + s_hb[r + 4][c]) + 56u * (s_hb[r + 1][c] + s_hb[r + 3][c]) + 136u * s_hb[r + 2][c];
-      s_g[r][c] = (uint8_t)((s + 32768u) >> 16);
-    }
-  __syncthreads();
+  blur5_tile_packed<4, 56, 136>(&s_in[0][0], SC_IW, SC_IH, SC_IW / 4, &s_v[0][0], SC_IW, &s_g[0][0], SC_IW, tid, SC_THREADS);
   for (int i = tid; i < SC_TH * SC_TW; i += SC_THREADS) {
     int r = i >> 6, c = i & 63;  // SC_TW == 64
     int dx = dx0 + c, dy = dy0 + r;
@@ -219,7 +283,7 @@ scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int
     if (ix >= w - 1) { ix = w - 1; ax = 0; }
     if (iy >= h - 1) { iy = h - 1; ay = 0; }
     int ix1 = min(ix + 1, w - 1), iy1 = min(iy + 1, h - 1);
-    int lx = ix - sx0, lx1 = ix1 - sx0, ly = iy - sy0, ly1 = iy1 - sy0;
+    int lx = ix - sx0 + 2, lx1 = ix1 - sx0 + 2, ly = iy - sy0, ly1 = iy1 - sy0;
     int s = (8 - ay) * ((8 - ax) * s_g[ly][lx] + ax * s_g[ly][lx1]) +
             ay * ((8 - ax) * s_g[ly1][lx] + ax * s_g[ly1][lx1]);
     dst[(size_t)dy * ws + dx] = (uint8_t)((s + 32) >> 6);
