@@ -209,7 +209,8 @@ def main():
 
     # weak scaling: every rank owns `steps*batch` frames of the sequence; its shard starts one
     # frame early (halo) so that the pair across the shard boundary is matched exactly once.
-    unique = make_frames(args.unique, args.seed + 17 * rank, args.workload)
+    # the sequence is a tiling of `unique` distinct frames, so every rank's shard holds the same frames
+    unique = make_frames(args.unique, args.seed, args.workload)
     halo = 1 if rank > 0 else 0
     # one pinned host buffer: [halo frame | B frames]; the shard's first step starts at the halo
     host_buf = np.ascontiguousarray(np.concatenate([unique[-1:], tile_frames(unique, B)]))
