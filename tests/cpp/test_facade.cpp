@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "../../vplines-slam_b200/compat/vplines_batch.hpp"
 #include "../../vplines-slam_b200/compat/vplines_seam.hpp"
 
 static void make_image(cv::Mat& m, int w, int h, int shift) {
@@ -48,6 +49,31 @@ int main(int argc, char** argv) {
     for (int i = 0; i < desc.rows; ++i)
       for (int c = 0; c < 32; ++c) digest = (digest ^ desc.at<unsigned char>(i, c)) * 1099511628211ul;
     std::printf("FACADE keylines=%zu self_matches=%d desc_digest=%lu\n", kl.size(), self, digest);
+    // batch driver: 5 frames in batches of 2 over 2 slots, plus the same sequence as two shards
+    {
+      std::vector<cv::Mat> seq(5);
+      std::vector<const uint8_t*> ptrs;
+      for (int i = 0; i < 5; ++i) { make_image(seq[(size_t)i], 320, 240, 2 * i); ptrs.push_back(seq[(size_t)i].data); }
+      unsigned long dg[2] = {1469598103934665603ul, 1469598103934665603ul};
+      long lines[2] = {0, 0}, matched[2] = {0, 0};
+      auto mix = [&](int which) {
+        return [&, which](int64_t, const vplines::FrameResult& r) {
+          lines[which] += (long)r.keylines.size();
+          for (uint8_t b : r.descriptors) dg[which] = (dg[which] ^ b) * 1099511628211ul;
+          for (const VplDMatch& m : r.matches) { matched[which] += m.trainIdx >= 0; dg[which] = (dg[which] ^ (unsigned long)(m.trainIdx + 7)) * 1099511628211ul; }
+        };
+      };
+      vplines::BatchFrontEnd be(0, 320, 240, 1, 2048, 2, 2);
+      be.run(ptrs.data(), 320, 0, 5, 0, 2, 1, mix(0));
+      for (int rank = 0; rank < 2; ++rank) {
+        int64_t s, e; int halo;
+        vplines::shard_range(5, rank, 2, s, e, halo);
+        vplines::BatchFrontEnd shard(0, 320, 240, 1, 2048, 2, 2);
+        shard.run(ptrs.data(), 320, s, e, halo, 2, 1, mix(1));
+      }
+      std::printf("FACADE batch lines=%ld matched=%ld digest=%lu sharded_equal=%d\n", lines[0], matched[0], dg[0],
+                  (int)(dg[0] == dg[1] && lines[0] == lines[1] && matched[0] == matched[1]));
+    }
     cv::Mat f32(4, 4, CV_32FC1);
     try {
       det->detect(f32, kl, 2, 1);

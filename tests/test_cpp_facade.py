@@ -60,3 +60,12 @@ def test_facade_matches_ctypes_path(vpl, orc, tmp_path):
     exp = len(set(int(t) for t, d in zip(idx[:, 0], dist[:, 0]) if d < 30))
     assert int(m2.group(3)) == exp
     assert "depth_check=Error, depth image!= 0" in out
+    # C++ batch driver: the sharded run (2 ranks, one-frame halo) equals the single run, and both equal the oracle
+    mb = re.search(r"batch lines=(\d+) matched=(\d+) digest=(\d+) sharded_equal=(\d)", out)
+    assert mb and mb.group(4) == "1", out
+    seq = [make_image(320, 240, 2 * i) for i in range(5)]
+    kls = [orc.lsd_detector_detect(f, 2, 1) for f in seq]
+    ds = [orc.lbd_compute(f, k) for f, k in zip(seq, kls)]
+    assert int(mb.group(1)) == sum(len(k) for k in kls)
+    exp_matched = sum(len(ds[i]) for i in range(1, 5) if len(ds[i - 1]))
+    assert int(mb.group(2)) == exp_matched

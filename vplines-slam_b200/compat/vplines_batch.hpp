@@ -1,0 +1,94 @@
+// vplines_batch.hpp -- C++ batch driver over the C ABI: streams a frame sequence through
+// vpl_frontend_submit / vpl_frontend_collect in pipelined batches, chaining consecutive batches
+// so that every frame is matched against its predecessor, and shards a sequence over GPUs by
+// contiguous range with a one-frame halo.  It does for a whole sequence
+// what LineFeatureTracker::readImage does per frame
+// (/root/reference/feature_tracker/src/line_feature_tracker.cpp:84-126: detect, describe, match
+// to the previous frame).  No collective: the host only gathers results.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vpl_capi.h"
+
+namespace vplines {
+
+struct FrameResult {
+  std::vector<VplKeyLine> keylines;
+  std::vector<uint8_t> descriptors;  // keylines.size() x 32
+  std::vector<VplDMatch> matches;    // keylines.size() x k, vs the previous frame (trainIdx -1: none)
+};
+
+// Frames [start, end) owned by `rank`; halo = 1 if frame start-1 must also be processed here so
+// that the pair (start-1, start) is matched on exactly one GPU.
+inline void shard_range(int64_t n_frames, int rank, int world, int64_t& start, int64_t& end, int& halo) {
+  start = n_frames * rank / world;
+  end = n_frames * (rank + 1) / world;
+  halo = (start > 0 && end > start) ? 1 : 0;
+}
+
+class BatchFrontEnd {
+ public:
+  BatchFrontEnd(int device, int width, int height, int octaves, int max_lines, int max_batch, int num_slots = 2)
+      : w_(width), h_(height), octaves_(octaves), cap_(max_lines), batch_(max_batch), slots_(num_slots) {
+    VplConfig c;
+    vpl_default_config(&c);
+    c.device = device; c.max_width = width; c.max_height = height; c.max_octaves = octaves;
+    c.max_lines = max_lines; c.max_batch = max_batch; c.num_slots = num_slots;
+    if (vpl_create(&c, &ctx_) != VPL_OK) throw std::runtime_error(std::string("vplines_b200: ") + vpl_last_error(nullptr));
+    kl_.resize((size_t)max_batch * max_lines);
+    desc_.resize((size_t)max_batch * max_lines * 32);
+    counts_.resize((size_t)max_batch);
+  }
+  ~BatchFrontEnd() { if (ctx_) vpl_destroy(ctx_); }
+  BatchFrontEnd(const BatchFrontEnd&) = delete;
+  BatchFrontEnd& operator=(const BatchFrontEnd&) = delete;
+  VplContext* context() { return ctx_; }
+
+  // frames: n pointers to w x h CV_8UC1 images with row pitch `stride`.  Processes frames
+  // [start - halo, end); calls sink(frame_index, result) for frames [start, end) in order.
+  void run(const uint8_t* const* frames, size_t stride, int64_t start, int64_t end, int halo, int scale, int k,
+           const std::function<void(int64_t, const FrameResult&)>& sink) {
+    matches_.resize((size_t)batch_ * cap_ * std::max(k, 1));
+    struct Pending { int slot; int64_t first; int n; };
+    std::vector<Pending> pending;
+    const int64_t lo = start - halo;
+    int slot = 0;
+    auto collect = [&](const Pending& p) {
+      check(vpl_frontend_collect(ctx_, p.slot, kl_.data(), counts_.data(), cap_, desc_.data(), k > 0 ? matches_.data() : nullptr));
+      for (int i = 0; i < p.n; ++i) {
+        if (p.first + i < start) continue;  // halo frame: only there to be matched against
+        FrameResult r;
+        const int c = counts_[(size_t)i];
+        r.keylines.assign(kl_.begin() + (size_t)i * cap_, kl_.begin() + (size_t)i * cap_ + c);
+        r.descriptors.assign(desc_.begin() + (size_t)i * cap_ * 32, desc_.begin() + ((size_t)i * cap_ + c) * 32);
+        if (k > 0) r.matches.assign(matches_.begin() + (size_t)i * cap_ * k, matches_.begin() + ((size_t)i * cap_ + c) * k);
+        sink(p.first + i, r);
+      }
+    };
+    for (int64_t f = lo; f < end;) {
+      const int n = (int)std::min<int64_t>(batch_, end - f);
+      if ((int)pending.size() == slots_) { collect(pending.front()); pending.erase(pending.begin()); }
+      check(vpl_frontend_submit(ctx_, slot, frames + f, n, w_, h_, stride, scale, octaves_, k, f > lo ? 1 : 0));
+      pending.push_back({slot, f, n});
+      slot = (slot + 1) % slots_;
+      f += n;
+    }
+    for (const Pending& p : pending) collect(p);
+  }
+
+ private:
+  void check(int r) { if (r != VPL_OK) throw std::runtime_error(std::string("vplines_b200: ") + vpl_last_error(ctx_)); }
+  VplContext* ctx_ = nullptr;
+  int w_, h_, octaves_, cap_, batch_, slots_;
+  std::vector<VplKeyLine> kl_;
+  std::vector<uint8_t> desc_;
+  std::vector<VplDMatch> matches_;
+  std::vector<int32_t> counts_;
+};
+
+}  // namespace vplines
