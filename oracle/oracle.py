@@ -179,6 +179,99 @@ def hamming_knn(q, t, k=1):
     return idx, dist
 
 
+# ---- the reference's real detector: EDLines (orc_edlines.c) -------------------------------
+LINE_DTYPE = np.dtype([("endpoint", "<f4", 4), ("equation", "<f8", 3), ("center", "<f4", 2),
+                       ("length", "<f4"), ("pad_", "<f4")])
+assert LINE_DTYPE.itemsize == 56
+
+
+class EDLineParam(ctypes.Structure):
+    """EDLineParam (line_matching/src/edline_detector.h:32-40).  Defaults = the tracker node's
+    (feature_tracker/src/line_feature_tracker_node.cpp:203 with the EuRoC yaml)."""
+    _fields_ = [("ksize", ctypes.c_int), ("sigma", ctypes.c_float), ("gradientThreshold", ctypes.c_float),
+                ("anchorThreshold", ctypes.c_float), ("scanIntervals", ctypes.c_int),
+                ("minLineLen", ctypes.c_int), ("lineFitErrThreshold", ctypes.c_double)]
+
+    def __init__(self, ksize=5, sigma=1.0, gradientThreshold=30, anchorThreshold=5, scanIntervals=2,
+                 minLineLen=35, lineFitErrThreshold=1.8):
+        super().__init__(ksize, sigma, gradientThreshold, anchorThreshold, scanIntervals, minLineLen,
+                         lineFitErrThreshold)
+
+
+def _edline_call(fn, img, param, smoothed, cap):
+    img = _u8(img); h, w = img.shape
+    out = np.zeros(cap, LINE_DTYPE)
+    xy = np.zeros(2 * (w * h // 5) + 16, np.uint32); sid = np.zeros(w * h // 100 + 2, np.uint32)
+    npx, nch = ctypes.c_int(), ctypes.c_int()
+    return img, w, h, out, xy, sid, npx, nch
+
+
+def edline_detect(img, param=None, smoothed=True, cap=1 << 14, stages=False):
+    """EDLineDetector::EDline -> Line records (LINE_DTYPE) in (chain, position) order;
+    with stages=True also (chain_xy, chain_sid)."""
+    param = param or EDLineParam()
+    img, w, h, out, xy, sid, npx, nch = _edline_call(None, img, param, smoothed, cap)
+    L = lib(); L.orc_edline_detect.restype = ctypes.c_int
+    n = L.orc_edline_detect(_p(img), w, h, ctypes.byref(param), int(bool(smoothed)), _p(out), cap, _p(xy), _p(sid),
+                            ctypes.byref(npx), ctypes.byref(nch))
+    lines = out[:min(n, cap)].copy()
+    if stages:
+        return lines, xy[:npx.value].copy(), sid[:nch.value + 1].copy()
+    return lines
+
+
+_REF_SO = os.path.join(_HERE, "_ref", "libref_edlines.so")
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(_REF_SO) or os.path.isdir("/root/reference/line_matching/src")
+
+
+def build_ref():
+    """oracle/_ref/libref_edlines.so = the reference's own edline_detector.cpp compiled against
+    oracle/cvshim.  Only possible where /root/reference exists; elsewhere the prebuilt file is used."""
+    if os.path.isdir("/root/reference/line_matching/src"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_SO):
+            build_ref()
+        _ref = ctypes.CDLL(_REF_SO)
+        _ref.ref_edline_detect.restype = ctypes.c_int
+        _ref.ref_edline_sequence_mt.restype = ctypes.c_longlong
+    return _ref
+
+
+def ref_edline_detect(img, param=None, smoothed=True, cap=1 << 14, stages=False):
+    """The same call through the reference's own code (oracle/_ref)."""
+    param = param or EDLineParam()
+    img, w, h, out, xy, sid, npx, nch = _edline_call(None, img, param, smoothed, cap)
+    n = ref_lib().ref_edline_detect(_p(img), w, h, ctypes.byref(param), int(bool(smoothed)), _p(out), cap,
+                                    _p(xy), len(xy), _p(sid), len(sid) - 1, ctypes.byref(npx), ctypes.byref(nch))
+    lines = out[:min(n, cap)].copy()
+    if stages:
+        return lines, xy[:npx.value].copy(), sid[:nch.value + 1].copy()
+    return lines
+
+
+def edline_sequence(frames, param=None, smoothed=True, threads=1, use_ref=False):
+    """Total lines over a frame stack, frames spread over host threads (CPU baseline timing)."""
+    param = param or EDLineParam()
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    if use_ref:
+        return int(ref_lib().ref_edline_sequence_mt(_p(frames), n, w, h, ctypes.byref(param),
+                                                    int(bool(smoothed)), int(threads)))
+    L = lib(); L.orc_edline_sequence_mt.restype = ctypes.c_int64
+    return int(L.orc_edline_sequence_mt(_p(frames), n, w, h, ctypes.byref(param), int(bool(smoothed)),
+                                        int(threads)))
+
+
 def frontend_sequence(frames, num_octaves=1, max_lines=8192, threads=1):
     frames = np.ascontiguousarray(frames, np.uint8)
     n, h, w = frames.shape

@@ -53,3 +53,45 @@ int64_t orc_frontend_sequence_mt(const uint8_t* frames, int n_frames, int w, int
   free(th); free(jobs);
   return total;
 }
+
+/* EDLines over a frame sequence on n_threads host threads (frames are independent). */
+typedef struct {
+  const uint8_t* frames;
+  int f0, f1, w, h, smoothed;
+  const OrcEDLineParam* p;
+  int64_t total;
+} EdJob;
+
+static void* ed_worker(void* a) {
+  EdJob* j = (EdJob*)a;
+  OrcLine* out = (OrcLine*)malloc(sizeof(OrcLine) * 8192);
+  for (int f = j->f0; f < j->f1; ++f)
+    j->total += orc_edline_detect(j->frames + (size_t)f * j->w * j->h, j->w, j->h, j->p, j->smoothed, out, 8192,
+                                  NULL, NULL, NULL, NULL);
+  free(out);
+  return NULL;
+}
+
+int64_t orc_edline_sequence_mt(const uint8_t* frames, int n_frames, int w, int h, const OrcEDLineParam* p,
+                               int smoothed, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_frames) n_threads = n_frames > 0 ? n_frames : 1;
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  pthread_t* th = (pthread_t*)malloc((size_t)n_threads * sizeof(pthread_t));
+  EdJob* jobs = (EdJob*)malloc((size_t)n_threads * sizeof(EdJob));
+  for (int t = 0; t < n_threads; ++t) {
+    jobs[t].frames = frames;
+    jobs[t].f0 = (int)((int64_t)n_frames * t / n_threads);
+    jobs[t].f1 = (int)((int64_t)n_frames * (t + 1) / n_threads);
+    jobs[t].w = w; jobs[t].h = h; jobs[t].smoothed = smoothed; jobs[t].p = p; jobs[t].total = 0;
+    pthread_create(&th[t], NULL, ed_worker, &jobs[t]);
+  }
+  int64_t total = 0;
+  for (int t = 0; t < n_threads; ++t) {
+    pthread_join(th[t], NULL);
+    total += jobs[t].total;
+  }
+  free(th); free(jobs);
+  return total;
+}

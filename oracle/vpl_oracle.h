@@ -91,6 +91,39 @@ int orc_lbd_compute(const uint8_t* img, int w, int h, const OrcKeyLine* kl, int 
 void orc_hamming_knn(const uint8_t* q, int nq, const uint8_t* t, int nt, int k,
                      int32_t* idx, int32_t* dist);
 
+/* ---- the reference's real detector: EDLineDetector::EDline (orc_edlines.c) ---- */
+typedef struct { /* EDLineParam, line_matching/src/edline_detector.h:32-40 */
+  int ksize;
+  float sigma;
+  float gradientThreshold;
+  float anchorThreshold;
+  int scanIntervals;
+  int minLineLen;
+  double lineFitErrThreshold;
+} OrcEDLineParam;
+typedef struct { /* the numeric fields of struct Line, line_matching/src/line.h:8-12 (56 bytes) */
+  float endpoint[4];
+  double equation[3];
+  float center[2];
+  float length;
+  float pad_;
+} OrcLine;
+/* Returns the number of lines found (at most cap written), in (edge chain, position) order.
+ * Optional stage outputs: chain_xy (x | y << 16 per edge pixel; room for 2*(w*h/5)), chain_sid
+ * (room for w*h/100 + 1), their counts. */
+int orc_edline_detect(const uint8_t* img, int w, int h, const OrcEDLineParam* p, int smoothed,
+                      OrcLine* out, int cap, uint32_t* chain_xy, uint32_t* chain_sid, int* n_px,
+                      int* n_chains);
+int orc_edge_drawing(const uint8_t* img, int w, int h, const OrcEDLineParam* p, int smoothed,
+                     int16_t* dx, int16_t* dy, uint8_t* dir, uint32_t* chain_xy, uint32_t* chain_sid,
+                     int* n_px, int* n_chains);
+void orc_ed_gradient_maps(const uint8_t* img, int w, int h, int smoothed, int grad_thresh,
+                          int16_t* dx, int16_t* dy, int16_t* g, uint8_t* dir);
+double orc_ed_nfa(int n, int k, double p, double logNT);
+/* n_frames frames over n_threads host threads (timing); returns the total number of lines */
+int64_t orc_edline_sequence_mt(const uint8_t* frames, int n_frames, int w, int h,
+                               const OrcEDLineParam* p, int smoothed, int n_threads);
+
 /* Whole front end on a frame sequence (for the CPU baseline timing).  Returns
  * total keylines over the sequence (each frame is matched k=1 against the
  * previous one; results are discarded, this entry point exists for timing). */
