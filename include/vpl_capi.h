@@ -72,6 +72,27 @@ typedef struct VplSegment {
   double width, prec, nfa;
 } VplSegment;
 
+/* The numeric fields of the reference's struct Line (line_matching/src/line.h:8-12): endpoints
+ * in pixels, unit-normal line equation w1 x + w2 y + w3 = 0, centre, length.  56 bytes. */
+typedef struct VplLine {
+  float endpoint[4];
+  double equation[3];
+  float center[2];
+  float length;
+  int32_t reserved; /* 0 */
+} VplLine;
+
+/* EDLineParam, field for field (line_matching/src/edline_detector.h:32-40). */
+typedef struct VplEDLineParam {
+  int32_t ksize;            /* Gaussian kernel size, only used when smoothed == 0 (5 supported) */
+  float sigma;              /* ... and its sigma (1.0 supported)                                */
+  float gradientThreshold;  /* stored as short by the detector (edline_detector.h:118)          */
+  float anchorThreshold;    /* stored as unsigned char (:122)                                   */
+  int32_t scanIntervals;
+  int32_t minLineLen;
+  double lineFitErrThreshold;
+} VplEDLineParam;
+
 typedef struct VplContext VplContext;
 
 typedef struct VplConfig {
@@ -106,6 +127,38 @@ int vpl_set_preprocess(VplContext* ctx, const float* mapx, const float* mapy, in
 /* The pre-processed frames themselves (n*w*h bytes), for the parity tests. */
 int vpl_preprocess_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
                          size_t stride, uint8_t* out);
+
+/* ---- EDLineDetector::EDline: the detector the reference really runs ------ */
+/* vpl_edlines_configure = EDLineDetector(EDLineParam) (line_matching/src/edline_detector.cpp:30-40;
+ * the tracker node builds it with {5, 1.0, 30, 5, 2, min_line_length, line_fit_err},
+ * feature_tracker/src/line_feature_tracker_node.cpp:203).  Allocates the detector's device
+ * buffers for the context's max image size and batch; call it before the first detect and not
+ * while batches are in flight. */
+void vpl_edlines_default_param(VplEDLineParam* p);
+int vpl_edlines_configure(VplContext* ctx, const VplEDLineParam* p);
+/* = int EDLineDetector::EDline(cv::Mat& image, std::vector<Line>& lines, bool smoothed)
+ * (edline_detector.cpp:1176-1198), i.e. the tracker's edline_detect seam
+ * (feature_tracker/src/line_feature_tracker.cpp:315-321), on n frames.  lines: n * cap entries,
+ * frame f at lines + f*cap, counts[f] valid, in (edge chain, position) order = the reference's
+ * single-thread order (its multi-thread order is unspecified).  status (may be NULL): per frame 1,
+ * or -1 where EdgeDrawing returns -1 (no anchors / capacity limits W*H/5, W*H/100,
+ * edline_detector.cpp:166-169, :655-670) -- such a frame yields 0 lines.  More than cap lines in a
+ * frame -> VPL_E_CAPACITY.  smoothed == 0 blurs with GaussianBlur(ksize 5, sigma 1) first. */
+int vpl_edlines_detect_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h,
+                             size_t stride, int smoothed, VplLine* lines, int32_t* counts, int cap,
+                             int32_t* status);
+/* Pipelined form (same slot rules as vpl_frontend_submit/collect). */
+int vpl_edlines_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h,
+                       size_t stride, int smoothed);
+int vpl_edlines_collect(VplContext* ctx, int slot, VplLine* lines, int32_t* counts, int cap,
+                        int32_t* status);
+/* Re-runs the detector on the frames already resident in slot's device input buffer (kernel
+ * timing); results stay in HBM; does not synchronise. */
+int vpl_edlines_run_resident(VplContext* ctx, int slot);
+/* Edge chains of frame `frame` of the last batch on slot 0 (EdgeChains, edline_detector.h:17-22):
+ * xy = x | y << 16 per edge pixel (cap_px entries), sid = chain starts (cap_chains + 1 entries). */
+int vpl_debug_edge_chains(VplContext* ctx, int frame, uint32_t* xy, int cap_px, uint32_t* sid,
+                          int cap_chains, int32_t* n_px, int32_t* n_chains);
 
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
@@ -209,7 +262,11 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_MATCH 9
 #define VPL_STAGE_D2H 10
 #define VPL_STAGE_PREPROC 11  /* remap + CLAHE (optional)           */
-#define VPL_NUM_STAGES 12
+#define VPL_STAGE_ED_GRAD 12    /* EDLines: gradient/direction map */
+#define VPL_STAGE_ED_ANCHOR 13  /* anchor bitmap                   */
+#define VPL_STAGE_ED_WALK 14    /* smart routing (edge chains)     */
+#define VPL_STAGE_ED_FIT 15     /* line fit + validation + compaction */
+#define VPL_NUM_STAGES 16
 /* Accumulated device milliseconds and launch counts per stage since the last
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);

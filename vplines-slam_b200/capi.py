@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvplines_b200.so")
 
 VPL_OK, VPL_E_INVALID, VPL_E_CUDA, VPL_E_CAPACITY, VPL_E_NODEVICE = 0, -1, -2, -3, -4
-STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h", "preproc"]
+STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h", "preproc",
+          "ed_grad", "ed_anchor", "ed_walk", "ed_fit"]
 
 KEYLINE_DTYPE = np.dtype(
     [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
@@ -24,7 +25,24 @@ KEYLINE_DTYPE = np.dtype(
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 SEGMENT_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"),
                           ("width", "<f8"), ("prec", "<f8"), ("nfa", "<f8")])
+# struct Line's numeric fields (line_matching/src/line.h:8-12) / VplLine
+LINE_DTYPE = np.dtype([("endpoint", "<f4", 4), ("equation", "<f8", 3), ("center", "<f4", 2),
+                       ("length", "<f4"), ("reserved", "<i4")])
 assert KEYLINE_DTYPE.itemsize == 68 and DMATCH_DTYPE.itemsize == 16 and SEGMENT_DTYPE.itemsize == 40
+assert LINE_DTYPE.itemsize == 56
+
+
+class EDLineParam(C.Structure):
+    """EDLineParam (line_matching/src/edline_detector.h:32-40) / VplEDLineParam; defaults are the
+    tracker node's (feature_tracker/src/line_feature_tracker_node.cpp:203, EuRoC yaml)."""
+    _fields_ = [("ksize", C.c_int32), ("sigma", C.c_float), ("gradientThreshold", C.c_float),
+                ("anchorThreshold", C.c_float), ("scanIntervals", C.c_int32), ("minLineLen", C.c_int32),
+                ("lineFitErrThreshold", C.c_double)]
+
+    def __init__(self, ksize=5, sigma=1.0, gradientThreshold=30, anchorThreshold=5, scanIntervals=2,
+                 minLineLen=35, lineFitErrThreshold=1.8):
+        super().__init__(ksize, sigma, gradientThreshold, anchorThreshold, scanIntervals, minLineLen,
+                         lineFitErrThreshold)
 
 
 class VplConfig(C.Structure):
@@ -39,6 +57,8 @@ EXPORTS = [
     "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
     "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
     "vpl_set_preprocess", "vpl_preprocess_batch",
+    "vpl_edlines_default_param", "vpl_edlines_configure", "vpl_edlines_detect_batch", "vpl_edlines_submit",
+    "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -92,6 +112,14 @@ def load():
     L.vpl_reset_stage_times.argtypes = [vp]
     L.vpl_kernel_launches.argtypes = [vp]
     L.vpl_kernel_launches.restype = C.c_int64
+    L.vpl_edlines_default_param.argtypes = [C.POINTER(EDLineParam)]
+    L.vpl_edlines_default_param.restype = None
+    L.vpl_edlines_configure.argtypes = [vp, C.POINTER(EDLineParam)]
+    L.vpl_edlines_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, vp, i32, vp]
+    L.vpl_edlines_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32]
+    L.vpl_edlines_collect.argtypes = [vp, i32, vp, vp, i32, vp]
+    L.vpl_edlines_run_resident.argtypes = [vp, i32]
+    L.vpl_debug_edge_chains.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -275,6 +303,43 @@ class Context:
 
     def sync(self):
         self._ck(self._L.vpl_sync(self._h))
+
+    # -- EDLineDetector::EDline (the detector the reference really runs) ----------------
+    def edlines_configure(self, param=None):
+        self._edp = param or EDLineParam()
+        self._ck(self._L.vpl_edlines_configure(self._h, C.byref(self._edp)))
+
+    def edlines_detect_batch(self, frames, smoothed=True, cap=None, with_status=False):
+        """-> list of LINE_DTYPE arrays (one per frame, (chain, position) order) [, status per frame]."""
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        cap = cap or self.max_lines
+        lines = np.zeros((n, cap), LINE_DTYPE)
+        counts = np.zeros(n, np.int32)
+        status = np.zeros(n, np.int32)
+        self._ck(self._L.vpl_edlines_detect_batch(self._h, ptrs, n, w, h, stride, int(bool(smoothed)), _ptr(lines),
+                                                  _ptr(counts), cap, _ptr(status)))
+        out = [lines[f, :counts[f]].copy() for f in range(n)]
+        return (out, status) if with_status else out
+
+    def edlines_submit(self, slot, frames, smoothed=True):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        self._ck(self._L.vpl_edlines_submit(self._h, slot, ptrs, n, w, h, stride, int(bool(smoothed))))
+        return n
+
+    def edlines_collect_into(self, slot, lines, counts, cap, status=None):
+        self._ck(self._L.vpl_edlines_collect(self._h, slot, _ptr(lines), _ptr(counts), cap, _ptr(status)))
+
+    def edlines_run_resident(self, slot):
+        self._ck(self._L.vpl_edlines_run_resident(self._h, slot))
+
+    def edge_chains(self, frame, w, h):
+        """Edge chains of `frame` of the last EDLines batch on slot 0 -> (xy u32 = x | y << 16, sid)."""
+        xy = np.zeros(2 * (w * h // 5) + 16, np.uint32)
+        sid = np.zeros(w * h // 100 + 2, np.uint32)
+        npx, nch = C.c_int32(0), C.c_int32(0)
+        self._ck(self._L.vpl_debug_edge_chains(self._h, frame, _ptr(xy), len(xy), _ptr(sid), len(sid) - 1,
+                                               C.byref(npx), C.byref(nch)))
+        return xy[:npx.value].copy(), sid[:nch.value + 1].copy()
 
     # -- raw stages ----------------------------------------------------------------
     def lsd_raw(self, img, cap=1 << 15):

@@ -61,7 +61,14 @@ struct Slot {
   int* h_offsets = nullptr;
   bool dense = false;                // this batch's outputs are downloaded in dense form at collect
   int64_t last_d2h_bytes = 0;
-  int* d_flags = nullptr;  // [0] candidate overflow, [1] keyline overflow
+  int* d_flags = nullptr;  // [0] candidate overflow, [1] keyline overflow, [2] EDLines line overflow
+  // EDLines (allocated by vpl_edlines_configure)
+  EdBuffers ed = {};
+  VplLine* d_lines = nullptr;
+  VplLine* h_lines = nullptr;
+  int* h_ed_status = nullptr;
+  int ed_smoothed = 1;
+  bool ed_batch = false;  // the batch in flight on this slot is an EDLines batch
   VplSegment* d_seg = nullptr;
   int* d_seg_count = nullptr;
   // pinned host staging
@@ -99,6 +106,8 @@ struct VplContext {
   int pre_w = 0, pre_h = 0, pre_tiles = 8;
   bool pre_remap = false;
   double pre_clip = 0.0;
+  bool ed_ready = false;  // vpl_edlines_configure has run
+  VplEDLineParam edp;
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -504,6 +513,96 @@ void copy_rows(void* dst, const void* src, const int* counts, int n, size_t cap_
   }
 }
 
+
+// ---- EDLines ---------------------------------------------------------------------
+EdGeom ed_geom(int w, int h, const VplEDLineParam& p) {
+  EdGeom G;
+  memset(&G, 0, sizeof(G));
+  G.w = w; G.h = h;
+  G.scan = p.scanIntervals;
+  G.nW = w > 2 ? (w - 2 + G.scan - 1) / G.scan : 0;
+  G.nH = h > 2 ? (h - 2 + G.scan - 1) / G.scan : 0;
+  G.bm_words = (G.nW * G.nH + 31) / 32 + 1;
+  G.cap_px = (int)((unsigned)w * (unsigned)h / 5);
+  G.cap_edges = G.cap_px / 20;
+  G.part_cap = (G.cap_px > p.minLineLen ? G.cap_px : p.minLineLen) + 2;
+  G.nslots = 2 * G.cap_px / p.minLineLen + 1;
+  G.min_len = p.minLineLen;
+  G.logNT = 2.0 * (log10((double)(unsigned)w) + log10((double)(unsigned)h));
+  return G;
+}
+
+void ed_free(Slot& s) {
+  cudaFree(s.ed.gmap); cudaFree(s.ed.bitmap); cudaFree(s.ed.n_anchor); cudaFree(s.ed.first); cudaFree(s.ed.second);
+  cudaFree(s.ed.xy); cudaFree(s.ed.sid); cudaFree(s.ed.n_chain); cudaFree(s.ed.n_px); cudaFree(s.ed.status);
+  cudaFree(s.ed.slots); cudaFree(s.ed.slot_valid); cudaFree(s.d_lines);
+  cudaFreeHost(s.h_lines); cudaFreeHost(s.h_ed_status);
+  s.ed = EdBuffers{};
+  s.d_lines = nullptr; s.h_lines = nullptr; s.h_ed_status = nullptr;
+}
+
+// gradient map -> anchors -> edge chains -> lines, all asynchronous on the slot stream
+void run_edlines(VplContext* c, Slot& s) {
+  const VplEDLineParam& p = c->edp;
+  const EdGeom G = ed_geom(s.w, s.h, p);
+  const int cap = c->cfg.max_lines;
+  cudaMemsetAsync(s.d_flags + 2, 0, sizeof(int), s.stream);
+  {
+    StageTimer t(c, s, VPL_STAGE_ED_GRAD);
+    // Sobel pair (and the 5x5 blur when the caller's image is not smoothed yet), ed.cpp:82-126
+    launch_blur5_sobel(s.d_img, s.oct[0].pyr, s.oct[0].grad, s.w, s.h, s.n, s.ed_smoothed ? 0 : 1, s.stream);
+    launch_ed_gmap(s.oct[0].grad, s.ed.gmap, (size_t)s.n * s.w * s.h, (int)(short)p.gradientThreshold, s.stream);
+    t.launches(2);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_ED_ANCHOR);
+    launch_ed_anchor(s.ed, G, (int)(unsigned char)p.anchorThreshold, s.n, s.stream);
+    t.launches(1);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_ED_WALK);
+    launch_ed_walk(s.ed, G, s.n, s.stream);
+    t.launches(1);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_ED_FIT);
+    launch_ed_fit(s.ed, G, p.lineFitErrThreshold, s.oct[0].grad, c->d_lgam, s.n, s.stream);
+    launch_ed_compact(s.ed, G, s.d_lines, s.d_counts, cap, s.d_flags + 2, s.n, s.stream);
+    t.launches(2);
+  }
+}
+
+void ed_enqueue_download(VplContext* c, Slot& s) {
+  StageTimer t(c, s, VPL_STAGE_D2H);
+  const size_t cap = (size_t)c->cfg.max_lines;
+  cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_ed_status, s.ed.status, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_flags, s.d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(s.h_lines, s.d_lines, (size_t)s.n * cap * sizeof(VplLine), cudaMemcpyDeviceToHost, s.stream);
+  s.last_d2h_bytes = (int64_t)((size_t)s.n * cap * sizeof(VplLine) + (size_t)s.n * 8 + 12);
+}
+
+int ed_check(VplContext* c, int n, int w, int h, int smoothed) {
+  int r = check_dims(c, n, w, h, 1, 1);
+  if (r) return r;
+  if (!c->ed_ready) return fail(c, VPL_E_INVALID, "call vpl_edlines_configure first");
+  if (w < 3 || h < 3 || w > 65535 || h > 65535) return fail(c, VPL_E_INVALID, "EDLines: image size %dx%d unsupported", w, h);
+  if (!smoothed && !(c->edp.ksize == 5 && c->edp.sigma == 1.0f))
+    return fail(c, VPL_E_INVALID, "EDLines: smoothed=0 needs ksize 5 / sigma 1 (got %d / %g)", c->edp.ksize, (double)c->edp.sigma);
+  return VPL_OK;
+}
+
+int ed_deliver(VplContext* c, Slot& s, VplLine* lines, int32_t* counts, int cap, int32_t* status) {
+  if (s.h_flags[2]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d lines", c->cfg.max_lines);
+  for (int f = 0; f < s.n; ++f) {
+    if (s.h_counts[f] > cap) return fail(c, VPL_E_CAPACITY, "frame %d has %d lines > cap %d", f, s.h_counts[f], cap);
+    counts[f] = s.h_counts[f];
+    if (status) status[f] = s.h_ed_status[f];
+  }
+  copy_rows(lines, s.h_lines, s.h_counts, s.n, (size_t)c->cfg.max_lines, (size_t)cap, sizeof(VplLine));
+  return VPL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -548,6 +647,7 @@ void vpl_destroy(VplContext* c) {
     cudaFree(s.d_kl); cudaFree(s.d_counts); cudaFree(s.d_desc); cudaFree(s.d_match); cudaFree(s.d_last_desc);
     cudaFree(s.d_last_count); cudaFree(s.d_flags); cudaFree(s.d_seg); cudaFree(s.d_seg_count);
     cudaFree(s.d_offsets); cudaFree(s.d_kl_dense); cudaFree(s.d_desc_dense); cudaFree(s.d_match_dense);
+    ed_free(s);
     cudaFreeHost(s.h_offsets);
     cudaFreeHost(s.h_img); cudaFreeHost(s.h_kl); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_desc);
     cudaFreeHost(s.h_match); cudaFreeHost(s.h_flags);
@@ -704,7 +804,7 @@ int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t*
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight) return fail(c, VPL_E_INVALID, "slot %d has no batch in flight", slot);
+  if (!s.in_flight || s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
   if (r) return r;
@@ -741,7 +841,7 @@ int vpl_frontend_collect_dense(VplContext* c, int slot, int32_t* counts, VplKeyL
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight) return fail(c, VPL_E_INVALID, "slot %d has no batch in flight", slot);
+  if (!s.in_flight || s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
   if (r) return r;
@@ -1047,6 +1147,140 @@ int vpl_match_batch(VplContext* c, const uint8_t* q, const int32_t* nq, int cap_
   if (r) return r;
   for (int p = 0; p < n_pairs; ++p)
     memcpy(out + (size_t)p * cap_q * k, s.h_match + (size_t)p * cap_q * k, (size_t)nq[p] * k * sizeof(VplDMatch));
+  return VPL_OK;
+}
+
+
+// ---- EDLines: the reference's real detector -------------------------------------
+void vpl_edlines_default_param(VplEDLineParam* p) {
+  if (!p) return;
+  // the tracker node's parameters with the EuRoC configuration
+  // (feature_tracker/src/line_feature_tracker_node.cpp:203, config/euroc/euroc_config.yaml:84,87)
+  p->ksize = 5; p->sigma = 1.0f; p->gradientThreshold = 30; p->anchorThreshold = 5; p->scanIntervals = 2;
+  p->minLineLen = 35; p->lineFitErrThreshold = 1.8;
+}
+
+int vpl_edlines_configure(VplContext* c, const VplEDLineParam* p) {
+  if (!c || !p) return VPL_E_INVALID;
+  if (p->scanIntervals < 1 || p->minLineLen < 2 || !(p->lineFitErrThreshold >= 0) || p->gradientThreshold < 0 ||
+      p->gradientThreshold > 32000 || p->anchorThreshold < 0 || p->anchorThreshold > 255)
+    return fail(c, VPL_E_INVALID, "bad EDLineParam");
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots)
+    if (s.in_flight) return fail(c, VPL_E_INVALID, "vpl_edlines_configure while a batch is in flight");
+  CK(c, cudaDeviceSynchronize());
+  c->ed_ready = false;
+  c->edp = *p;
+  const EdGeom G = ed_geom(c->cfg.max_width, c->cfg.max_height, *p);
+  const size_t B = (size_t)c->cfg.max_batch, P0 = (size_t)c->cfg.max_width * c->cfg.max_height;
+  // buffer sizes must dominate every smaller image: all EdGeom sizes are monotone in w and h
+  // except the scan grid of a shape with the same area but another aspect; size it by area
+  const size_t bm_words = (P0 / ((size_t)p->scanIntervals * p->scanIntervals) + 2 * (c->cfg.max_width + c->cfg.max_height)) / 32 + 8;
+  for (Slot& s : c->slots) {
+    ed_free(s);
+    CK(c, dmalloc(&s.ed.gmap, B * P0));
+    CK(c, dmalloc(&s.ed.bitmap, B * bm_words));
+    CK(c, dmalloc(&s.ed.n_anchor, B));
+    CK(c, dmalloc(&s.ed.first, B * (size_t)G.part_cap));
+    CK(c, dmalloc(&s.ed.second, B * (size_t)G.part_cap));
+    CK(c, dmalloc(&s.ed.xy, B * 2 * (size_t)G.cap_px));
+    CK(c, dmalloc(&s.ed.sid, B * ((size_t)G.cap_edges + 2)));
+    CK(c, dmalloc(&s.ed.n_chain, B));
+    CK(c, dmalloc(&s.ed.n_px, B));
+    CK(c, dmalloc(&s.ed.status, B));
+    CK(c, dmalloc(&s.ed.slots, B * (size_t)G.nslots));
+    CK(c, dmalloc(&s.ed.slot_valid, B * (size_t)G.nslots));
+    CK(c, dmalloc(&s.d_lines, B * (size_t)c->cfg.max_lines));
+    CK(c, hmalloc(&s.h_lines, B * (size_t)c->cfg.max_lines));
+    CK(c, hmalloc(&s.h_ed_status, B));
+  }
+  c->ed_ready = true;
+  return VPL_OK;
+}
+
+int vpl_edlines_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                       int smoothed) {
+  int r = ed_check(c, n, w, h, smoothed);
+  if (r) return r;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (n == 0) return fail(c, VPL_E_INVALID, "empty batch");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  s.n = n; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 1; s.k = 0; s.ed_smoothed = smoothed ? 1 : 0;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  run_edlines(c, s);
+  ed_enqueue_download(c, s);
+  CK(c, cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  s.ed_batch = true;
+  return VPL_OK;
+}
+
+int vpl_edlines_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* status) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight || !s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no EDLines batch in flight", slot);
+  if (!lines || !counts) return fail(c, VPL_E_INVALID, "null output");
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = finish(c, s);
+  s.ed_batch = false;
+  if (r) return r;
+  return ed_deliver(c, s, lines, counts, cap, status);
+}
+
+int vpl_edlines_detect_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                             int smoothed, VplLine* lines, int32_t* counts, int cap, int32_t* status) {
+  int r = ed_check(c, n, w, h, smoothed);
+  if (r) return r;
+  if (n == 0) return VPL_OK;
+  r = vpl_edlines_submit(c, 0, imgs, n, w, h, stride, smoothed);
+  if (r) return r;
+  return vpl_edlines_collect(c, 0, lines, counts, cap, status);
+}
+
+int vpl_edlines_run_resident(VplContext* c, int slot) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->ed_ready) return fail(c, VPL_E_INVALID, "call vpl_edlines_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no frames", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  run_edlines(c, s);
+  return VPL_OK;
+}
+
+int vpl_debug_edge_chains(VplContext* c, int frame, uint32_t* xy, int cap_px, uint32_t* sid, int cap_chains,
+                          int32_t* n_px, int32_t* n_chains) {
+  if (!c || !n_px || !n_chains) return VPL_E_INVALID;
+  if (!c->ed_ready) return fail(c, VPL_E_INVALID, "call vpl_edlines_configure first");
+  Slot& s = c->slots[0];
+  if (frame < 0 || frame >= s.n) return fail(c, VPL_E_INVALID, "frame %d outside the last batch", frame);
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaStreamSynchronize(s.stream));
+  const EdGeom G = ed_geom(s.w, s.h, c->edp);
+  int np = 0, nc = 0;
+  CK(c, cudaMemcpy(&np, s.ed.n_px + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(c, cudaMemcpy(&nc, s.ed.n_chain + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_px = np; *n_chains = nc;
+  if (np > cap_px || nc > cap_chains) return fail(c, VPL_E_CAPACITY, "edge chains: %d px / %d chains exceed the buffers", np, nc);
+  if (xy && np) CK(c, cudaMemcpy(xy, s.ed.xy + (size_t)frame * 2 * G.cap_px, (size_t)np * 4, cudaMemcpyDeviceToHost));
+  if (sid) {
+    if (nc) CK(c, cudaMemcpy(sid, s.ed.sid + (size_t)frame * (G.cap_edges + 2), ((size_t)nc + 1) * 4, cudaMemcpyDeviceToHost));
+    else sid[0] = 0;
+  }
   return VPL_OK;
 }
 

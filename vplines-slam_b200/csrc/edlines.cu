@@ -1,0 +1,506 @@
+// edlines.cu -- the reference's real line detector on the device (sm_100a).
+//
+// Replaces EDLineDetector::EDline (/root/reference/line_matching/src/edline_detector.cpp:1176;
+// cited below as ed.cpp:line, ed.h = edline_detector.h), which the tracker calls through
+// edline_detect (feature_tracker/src/line_feature_tracker.cpp:87, :315-321).  CPU restatement:
+// oracle/orc_edlines.c (pinned bit for bit against the reference's own code).
+//
+// Stages (batch of B frames, all of them one launch over the whole batch):
+//   ed_gmap_kernel    |dx|+|dy| -> threshold -> /4 (round half even) + direction bit, one u16 per
+//                     pixel, from the Sobel pair the pyramid kernel already wrote   (ed.cpp:128-136)
+//   ed_anchor_kernel  anchor test on the scan grid -> column-major bitmap           (ed.cpp:148-164)
+//   ed_walk_kernel    smart routing.  Chains are claimed in anchor order and a walk stops at any
+//                     earlier edge pixel, so it is sequential per frame: ONE WARP PER FRAME, lane 0
+//                     walks (3 independent u16 loads per step: gradient, direction and edge mark
+//                     share the word), the warp scans the anchor bitmap and re-packs each chain
+//                                                                                    (ed.cpp:191-706)
+//   ed_fit_kernel     ONE WARP PER EDGE CHAIN: least-squares fit of the first minLineLen pixels
+//                     (integer sums, exact), extension 32 pixels per step with a ballot for the
+//                     "4 consecutive outliers" rule, refits, Helmholtz validation   (ed.cpp:983-1173)
+//   ed_compact_kernel lines into (chain, position) order -- the order the reference gives on one
+//                     thread (its multi-threaded order is a race, ed.cpp:1081-1083)
+// Everything is integer or IEEE double/float with -fmad=false, so the output equals the oracle's
+// byte for byte (atan2/exp/log10/pow only feed threshold tests that sit far from their thresholds).
+#include <float.h>
+
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+namespace {
+
+constexpr unsigned kG = 0x01ffu;     // (|dx|+|dy|)/4 <= 510
+constexpr unsigned kEdge = 0x2000u;  // edge mark (pEdgeImg)
+constexpr unsigned kDir = 0x8000u;   // set = Horizontal (|dx| < |dy|), ed.cpp:5-6, :136
+enum { UP = 1, RIGHT = 2, DOWN = 3, LEFT = 4 };  // ed.cpp:7-10
+constexpr int kTryTime = 6;                      // ed.cpp:11
+constexpr int kSkipEdgePoint = 2;                // ed.cpp:12
+
+__device__ __forceinline__ unsigned gmap_value(short2 d, int grad_thresh) {
+  int ax = abs((int)d.x), ay = abs((int)d.y);
+  int s = ax + ay;
+  if (!(s > grad_thresh + 1)) s = 0;  // threshold(THRESH_TOZERO, gradienThreshold_ + 1), ed.cpp:133
+  int q = s >> 2, r = s & 3;          // Mat / 4 = convertTo(alpha .25): cvRound, ties to even
+  if (r == 3 || (r == 2 && (q & 1))) q++;
+  return (unsigned)q | (ax < ay ? kDir : 0u);
+}
+
+__global__ void ed_gmap_kernel(const short2* __restrict__ grad, uint16_t* __restrict__ gmap, size_t total,
+                               int grad_thresh) {
+  size_t quads = total >> 2;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += stride) {
+    int4 v = reinterpret_cast<const int4*>(grad)[i];
+    short2 a = *reinterpret_cast<short2*>(&v.x), b = *reinterpret_cast<short2*>(&v.y);
+    short2 c = *reinterpret_cast<short2*>(&v.z), d = *reinterpret_cast<short2*>(&v.w);
+    uint2 o;
+    o.x = gmap_value(a, grad_thresh) | (gmap_value(b, grad_thresh) << 16);
+    o.y = gmap_value(c, grad_thresh) | (gmap_value(d, grad_thresh) << 16);
+    reinterpret_cast<uint2*>(gmap)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
+    size_t i = (quads << 2) + threadIdx.x;
+    gmap[i] = (uint16_t)gmap_value(grad[i], grad_thresh);
+  }
+}
+
+// one thread per scan-grid point, x fastest (coalesced reads); bit (ix*nH + iy) of the frame's
+// bitmap = anchor, i.e. the bitmap is in the reference's column-major visiting order
+__global__ void ed_anchor_kernel(const uint16_t* __restrict__ gmap, unsigned* __restrict__ bitmap,
+                                 int* __restrict__ n_anchor, EdGeom G, int anchor_thresh) {
+  int f = blockIdx.y;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G.nW * G.nH) return;
+  int iy = t / G.nW, ix = t - iy * G.nW;
+  int x = 1 + ix * G.scan, y = 1 + iy * G.scan;
+  const uint16_t* g = gmap + (size_t)f * G.w * G.h;
+  int i = y * G.w + x;
+  unsigned v = g[i];
+  int gv = v & kG;
+  int a, b;
+  if (v & kDir) { a = g[i - G.w] & kG; b = g[i + G.w] & kG; }
+  else { a = g[i - 1] & kG; b = g[i + 1] & kG; }
+  if (gv >= a + anchor_thresh && gv >= b + anchor_thresh) {
+    int bit = ix * G.nH + iy;
+    atomicOr(&bitmap[(size_t)f * G.bm_words + (bit >> 5)], 1u << (bit & 31));
+    atomicAdd(&n_anchor[f], 1);
+  }
+}
+
+// ---- smart routing ---------------------------------------------------------------------------
+struct WalkMem {
+  unsigned last_x, last_y;  // ed.cpp:184-185
+};
+
+// One directional walk by a single thread (ed.cpp:211-312 and its three copies).  Returns the
+// number of pixels recorded, or -1 if `cap` would be exceeded.
+__device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsigned x, unsigned y, int last_dir,
+                                    uint32_t* __restrict__ out, int cap, WalkMem& wm) {
+  int n = 0;
+  int idx = (int)y * W + (int)x;
+  unsigned v = g[idx];
+  while ((v & kG) != 0 && !(v & kEdge)) {
+    if (n >= cap) return -1;
+    g[idx] = (uint16_t)(v | kEdge);
+    out[n++] = x | (y << 16);
+    int should_go = 0;
+    int dmain, dperp, mx, my, px, py;
+    if (v & kDir) {  // horizontal pixel: go left or right
+      if (last_dir == UP || last_dir == DOWN) should_go = x > wm.last_x ? RIGHT : LEFT;
+      wm.last_x = x; wm.last_y = y;
+      if (last_dir == RIGHT || should_go == RIGHT) {
+        if (x == (unsigned)W - 1 || y == 0 || y == (unsigned)H - 1) break;
+        mx = 1; last_dir = RIGHT;
+      } else {
+        if (x == 0 || y == 0 || y == (unsigned)H - 1) break;
+        mx = -1; last_dir = LEFT;
+      }
+      my = 0; px = 0; py = -1;  // candidate 1 = up-, candidate 3 = down-
+      dmain = mx; dperp = -W;
+    } else {  // vertical pixel: go up or down
+      if (last_dir == RIGHT || last_dir == LEFT) should_go = y > wm.last_y ? DOWN : UP;
+      wm.last_x = x; wm.last_y = y;
+      if (last_dir == DOWN || should_go == DOWN) {
+        if (x == 0 || x == (unsigned)W - 1 || y == (unsigned)H - 1) break;
+        my = 1; last_dir = DOWN;
+      } else {
+        if (x == 0 || x == (unsigned)W - 1 || y == 0) break;
+        my = -1; last_dir = UP;
+      }
+      mx = 0; px = 1; py = 0;  // candidate 1 = -right, candidate 3 = -left
+      dmain = my * W; dperp = 1;
+    }
+    int i2 = idx + dmain;
+    unsigned v1 = g[i2 + dperp], v2 = g[i2], v3 = g[i2 - dperp];
+    unsigned g1 = v1 & 0xffu, g2 = v2 & 0xffu, g3 = v3 & 0xffu;  // the (unsigned char) casts, ed.cpp:231-233
+    if (g1 >= g2 && g1 >= g3) { x += mx + px; y += my + py; idx = i2 + dperp; v = v1; }
+    else if (g3 >= g2 && g3 >= g1) { x += mx - px; y += my - py; idx = i2 - dperp; v = v3; }
+    else { x += mx; y += my; idx = i2; v = v2; }
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(32) ed_walk_kernel(EdBuffers B, EdGeom G, int min_len, int batch) {
+  const int f = blockIdx.x;
+  if (f >= batch) return;
+  const int lane = threadIdx.x;
+  uint16_t* g = B.gmap + (size_t)f * G.w * G.h;
+  const unsigned* bm = B.bitmap + (size_t)f * G.bm_words;
+  uint32_t* first = B.first + (size_t)f * G.part_cap;
+  uint32_t* second = B.second + (size_t)f * G.part_cap;
+  uint32_t* xy = B.xy + (size_t)f * 2 * G.cap_px;
+  uint32_t* sid = B.sid + (size_t)f * (G.cap_edges + 2);
+  int status = 1;
+  if (B.n_anchor[f] > G.cap_px) status = -1;  // ed.cpp:166-169
+  int off1 = 0, off2 = 0, n_edge = 0, k = 0;
+  WalkMem wm = {0u, 0u};
+  for (int base = 0; status == 1 && base < G.bm_words; base += 32) {
+    unsigned word = (base + lane < G.bm_words) ? bm[base + lane] : 0u;
+    unsigned any = __ballot_sync(0xffffffffu, word != 0u);
+    while (any && status == 1) {
+      int src = __ffs(any) - 1;
+      any &= any - 1;
+      unsigned wv = __shfl_sync(0xffffffffu, word, src);
+      while (wv && status == 1) {
+        int b = __ffs(wv) - 1;
+        wv &= wv - 1;
+        int cand = ((base + src) << 5) + b;
+        int ix = cand / G.nH, iy = cand - ix * G.nH;
+        unsigned x = 1 + ix * G.scan, y = 1 + iy * G.scan;
+        int len1 = 0, len2 = 0;
+        if (lane == 0) {
+          int idx = (int)y * G.w + (int)x;
+          unsigned v = g[idx];
+          if (v & kEdge) {
+            len1 = -2;  // already an edge pixel, ed.cpp:195
+          } else {
+            bool horizontal = (v & kDir) != 0;
+            len1 = ed_walk(g, G.w, G.h, x, y, horizontal ? RIGHT : DOWN, first, G.part_cap, wm);
+            g[idx] = (uint16_t)(g[idx] & ~kEdge);  // the anchor is walked again, ed.cpp:317 / :533
+            len2 = ed_walk(g, G.w, G.h, x, y, horizontal ? LEFT : UP, second, G.part_cap, wm);
+          }
+        }
+        len1 = __shfl_sync(0xffffffffu, len1, 0);
+        len2 = __shfl_sync(0xffffffffu, len2, 0);
+        if (len1 == -2) continue;
+        if (len1 < 0 || len2 < 0) { status = -1; break; }
+        if (len1 + len2 < min_len + 1) continue;  // short edge: records dropped, marks stay, ed.cpp:641-643
+        off1 += len1; off2 += len2;
+        if (off1 > G.cap_px || off2 > G.cap_px || n_edge + 1 > G.cap_edges) { status = -1; break; }  // ed.cpp:655-666
+        // re-pack: first part reversed, then the second part without the anchor, ed.cpp:687-702
+        if (lane == 0) sid[n_edge] = k;
+        for (int i = lane; i < len1; i += 32) xy[k + i] = first[len1 - 1 - i];
+        for (int i = lane; i < len2 - 1; i += 32) xy[k + len1 + i] = second[1 + i];
+        k += len1 + (len2 > 0 ? len2 - 1 : 0);
+        n_edge++;
+        __syncwarp();
+      }
+    }
+  }
+  if (!(off1 && off2)) status = -1;  // ed.cpp:667 "lines not found"
+  if (lane == 0) {
+    if (status == 1) sid[n_edge] = k;
+    B.n_chain[f] = status == 1 ? n_edge : 0;
+    B.n_px[f] = status == 1 ? k : 0;
+    B.status[f] = status;
+  }
+}
+
+// ---- per-chain line extraction ------------------------------------------------------------------
+__device__ __forceinline__ bool ed_double_equal(double a, double b) {  // ed.h:171-187
+  if (a == b) return true;
+  double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
+  double abs_max = aa > bb ? aa : bb;
+  if (abs_max < DBL_MIN) abs_max = DBL_MIN;
+  return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
+}
+
+// nfa(n, k, p, logNT), ed.h:275-348.  log_gamma of integer arguments comes from the table the
+// host built with the same Lanczos/Windschitl formulas (ed.h:210-240, capi.cu host_log_gamma).
+__device__ __noinline__ double ed_nfa(int n, int k, double p, double logNT, const double* __restrict__ lgam) {
+  if (n == 0 || k == 0) return -logNT;
+  if (n == k) return -logNT - (double)n * log10(p);
+  double p_term = p / (1.0 - p);
+  double log1term = lgam[n + 1] - lgam[k + 1] - lgam[n - k + 1] + (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+  double term = exp(log1term);
+  if (ed_double_equal(term, 0.0)) {
+    if ((double)k > (double)n * p) return -log1term / 2.30258509299404568402 - logNT;
+    return -logNT;
+  }
+  double bin_tail = term;
+  for (int i = k + 1; i <= n; i++) {
+    double bin_term = (double)(n - i + 1) / (double)i;
+    double mult_term = bin_term * p_term;
+    term *= mult_term;
+    bin_tail += term;
+    if (bin_term < 1.0) {
+      double err = term * ((1.0 - pow(mult_term, (double)(n - i + 1))) / (1.0 - mult_term) - 1.0);
+      if (err < 0.1 * fabs(-log10(bin_tail) - logNT) * bin_tail) break;
+    }
+  }
+  return -log10(bin_tail) - logNT;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sums of the normal equations over chain pixels [s, e): exact integers, cast to float once
+// (= cv::gemm's double accumulators on integer-valued floats, ed.cpp:757-758 / :843-844)
+__device__ __forceinline__ void ed_normal_sums(const uint32_t* __restrict__ xy, unsigned s, unsigned e, bool horizontal,
+                                               int lane, float ata[4], float atv[2]) {
+  long long suu = 0, suv = 0;
+  int su = 0, sv = 0;
+  for (unsigned i = s + lane; i < e; i += 32) {
+    unsigned p = xy[i];
+    int x = p & 0xffff, y = p >> 16;
+    int u = horizontal ? x : y, v = horizontal ? y : x;
+    suu += (long long)u * u; suv += (long long)u * v; su += u; sv += v;
+  }
+  suu = warp_sum_ll(suu); suv = warp_sum_ll(suv); su = warp_sum_i(su); sv = warp_sum_i(sv);
+  ata[0] = (float)(double)suu; ata[1] = (float)(double)su; ata[2] = ata[1]; ata[3] = (float)(double)(int)(e - s);
+  atv[0] = (float)(double)suv; atv[1] = (float)(double)sv;
+}
+__device__ __forceinline__ void ed_fit_solve(const float a[4], const float v[2], double& eq0, double& eq1) {  // ed.cpp:761-764
+  double coef = 1.0 / ((double)a[0] * (double)a[3] - (double)a[1] * (double)a[2]);
+  eq0 = coef * ((double)a[3] * (double)v[0] - (double)a[1] * (double)v[1]);
+  eq1 = coef * ((double)a[0] * (double)v[1] - (double)a[2] * (double)v[0]);
+}
+
+__global__ void __launch_bounds__(128) ed_fit_kernel(EdBuffers B, EdGeom G, int min_len, double thr,
+                                                     const short2* __restrict__ grad, const double* __restrict__ lgam) {
+  __shared__ double s_sq[4][32];
+  const int f = blockIdx.y;
+  if (B.status[f] != 1) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chain = B.n_chain[f];
+  const uint16_t* g = B.gmap + (size_t)f * G.w * G.h;
+  const short2* gr = grad + (size_t)f * G.w * G.h;
+  const uint32_t* xy = B.xy + (size_t)f * 2 * G.cap_px;
+  const uint32_t* sid = B.sid + (size_t)f * (G.cap_edges + 2);
+  VplLine* slots = B.slots + (size_t)f * G.nslots;
+  uint8_t* valid = B.slot_valid + (size_t)f * G.nslots;
+  const unsigned m = (unsigned)min_len;
+  double* sq = s_sq[warp];
+
+  for (int e = blockIdx.x * 4 + warp; e < n_chain; e += gridDim.x * 4) {
+    unsigned S = sid[e];
+    const unsigned E = sid[e + 1];
+    double eq0 = 0, eq1 = 0, fit_err = 0;
+    float ata[4], atv[2];
+    while (E > S + m) {  // ed.cpp:987
+      bool horizontal = false;
+      while (E > S + m) {  // find an initial segment, ed.cpp:989-995
+        unsigned p0 = xy[S];
+        horizontal = (g[(p0 >> 16) * G.w + (p0 & 0xffff)] & kDir) != 0;
+        ed_normal_sums(xy, S, S + m, horizontal, lane, ata, atv);
+        ed_fit_solve(ata, atv, eq0, eq1);
+        double err = 0;  // sum of squared residuals in pixel order, ed.cpp:767-770
+        for (unsigned base = 0; base < m; base += 32) {
+          unsigned i = base + lane;
+          double c2 = 0;
+          if (i < m) {
+            unsigned p = xy[S + i];
+            double x = (double)(p & 0xffff), y = (double)(p >> 16);
+            double c = horizontal ? y - x * eq0 - eq1 : x - y * eq0 - eq1;
+            c2 = c * c;
+          }
+          sq[lane] = c2;
+          __syncwarp();
+          int cnt = min(32u, m - base);
+          for (int j = 0; j < cnt; j++) err += sq[j];
+          __syncwarp();
+          // the partial sums only grow: once sqrt(partial) > thr the verdict is final
+          if (sqrt(err) > thr) break;
+        }
+        fit_err = sqrt(err);
+        if (fit_err <= thr) break;
+        S += kSkipEdgePoint;
+      }
+      if (fit_err > thr) break;  // ed.cpp:996
+      // extend, ed.cpp:1008-1039 / :1090-1120
+      const unsigned S0 = S;
+      double coef1 = 0;
+      bool extended = true, first_try = true;
+      int tries = 0, outliers = 0;
+      unsigned new_s = 0;
+      while (extended) {
+        tries++;
+        if (first_try) {
+          first_try = false;
+          S += m;
+        } else {  // incremental refit with the pixels [new_s, S), ed.cpp:805-891
+          float a2[4], v2[2];
+          ed_normal_sums(xy, new_s, S, horizontal, lane, a2, v2);
+#pragma unroll
+          for (int i = 0; i < 4; i++) ata[i] = ata[i] + a2[i];
+          atv[0] = atv[0] + v2[0]; atv[1] = atv[1] + v2[1];
+          ed_fit_solve(ata, atv, eq0, eq1);
+        }
+        coef1 = 1 / sqrt(eq0 * eq0 + 1);
+        outliers = 0;
+        new_s = S;
+        bool stop = false;
+        while (E > S && !stop) {
+          unsigned i = S + lane;
+          bool in = i < E, far = false;
+          if (in) {
+            unsigned p = xy[i];
+            unsigned X = p & 0xffff, Y = p >> 16;
+            double d = horizontal ? fabs(eq0 * X - Y + eq1) * coef1 : fabs(X - eq0 * Y - eq1) * coef1;
+            far = d > thr;
+          }
+          unsigned mo = __ballot_sync(0xffffffffu, far);
+          int nin = __popc(__ballot_sync(0xffffffffu, in));
+          // bits 0..2: the run of outliers carried in (right-aligned against bit 3 = pixel 0)
+          unsigned long long wd = ((unsigned long long)mo << 3) | (unsigned long long)(((1u << outliers) - 1u) << (3 - outliers));
+          unsigned long long r4 = wd & (wd >> 1) & (wd >> 2) & (wd >> 3);
+          if (r4) {  // fourth consecutive outlier at pixel j: numOfOutlier > 3, ed.cpp:1027
+            int j = __ffsll((long long)r4) - 1;
+            S += (unsigned)j + 1;
+            outliers = 4;
+            stop = true;
+          } else {
+            S += (unsigned)nin;
+            int top = nin + 2;  // highest bit in use
+            outliers = __clzll((long long)~(wd << (63 - top)));
+          }
+        }
+        S -= (unsigned)outliers;  // pop the trailing outliers, ed.cpp:1034
+        if (!(S != new_s && tries < kTryTime)) extended = false;
+      }
+      double le0, le1, le2;
+      if (horizontal) { le0 = eq0 * coef1; le1 = -1 * coef1; le2 = eq1 * coef1; }  // ed.cpp:1041-1044
+      else { le0 = 1 * coef1; le1 = -eq0 * coef1; le2 = -eq1 * coef1; }            // ed.cpp:1122-1125
+      // LineValidation, ed.cpp:893-958
+      const int n = (int)(S - S0);
+      int mgx = 0, mgy = 0;
+      for (unsigned i = S0 + lane; i < S; i += 32) {
+        unsigned p = xy[i];
+        short2 d = gr[(p >> 16) * G.w + (p & 0xffff)];
+        mgx += d.x; mgy += d.y;
+      }
+      mgx = warp_sum_i(mgx); mgy = warp_sum_i(mgy);
+      bool ok = !(mgx == 0 && mgy == 0);
+      float direction = 0.f;
+      if (ok) {
+        double adx = fabs(le1), ady = fabs(le0);
+        if (mgx > 0 && mgy >= 0) direction = (float)atan2(-ady, adx);
+        if (mgx <= 0 && mgy > 0) direction = (float)atan2(ady, adx);
+        if (mgx < 0 && mgy <= 0) direction = (float)atan2(ady, -adx);
+        if (mgx >= 0 && mgy < 0) direction = (float)atan2(-ady, -adx);
+        double fd = fabs((double)direction);
+        if (fd < 0.15 || VPL_PI - fd < 0.15)
+          if (fabs(le2) < 10 || fabs((double)(unsigned)G.h - fabs(le2)) < 10) ok = false;
+        if (ok && fabs(fd - VPL_PI * 0.5) < 0.15)
+          if (fabs(le2) < 10 || fabs((double)(unsigned)G.w - fabs(le2)) < 10) ok = false;
+      }
+      if (ok) {
+        int k = 0;
+        for (unsigned i = S0 + lane; i < S; i += 32) {
+          unsigned p = xy[i];
+          short2 d = gr[(p >> 16) * G.w + (p & 0xffff)];
+          double pd = atan2(-(double)d.x, (double)d.y);
+          double dis = fabs((double)direction - pd);
+          if (fabs(2 * VPL_PI - dis) < 0.392699 || dis < 0.392699) k++;
+        }
+        k = warp_sum_i(k);
+        ok = ed_nfa(n, k, 0.125, G.logNT, lgam) > 0;
+      }
+      if (ok && lane == 0) {  // endpoints = projections of the first and last pixel, ed.cpp:1056-1079
+        double a1 = le1 * le1, a2 = le0 * le0, a3 = le0 * le1, a4 = le2 * le0, a5 = le2 * le1;
+        unsigned p = xy[S0];
+        unsigned Px = p & 0xffff, Py = p >> 16;
+        float x1 = (float)(a1 * Px - a3 * Py - a4), y1 = (float)(a2 * Py - a3 * Px - a5);
+        p = xy[S - 1];
+        Px = p & 0xffff; Py = p >> 16;
+        float x2 = (float)(a1 * Px - a3 * Py - a4), y2 = (float)(a2 * Py - a3 * Px - a5);
+        VplLine L;
+        L.endpoint[0] = x1; L.endpoint[1] = y1; L.endpoint[2] = x2; L.endpoint[3] = y2;
+        L.equation[0] = le0; L.equation[1] = le1; L.equation[2] = le2;
+        L.center[0] = (float)((double)(x1 + x2) / 2.0);
+        L.center[1] = (float)((double)(y1 + y2) / 2.0);
+        double ddx = (double)(x2 - x1), ddy = (double)(y2 - y1);
+        L.length = (float)sqrt(ddx * ddx + ddy * ddy);
+        L.reserved = 0;
+        // lines of a frame start >= minLineLen pixels apart, so S0 / minLineLen is a free slot
+        // and slots are in (chain, position) order
+        unsigned slot = S0 / m;
+        slots[slot] = L;
+        valid[slot] = 1;
+      }
+    }
+  }
+}
+
+// one warp per frame: valid slots -> dense rows, order kept
+__global__ void __launch_bounds__(32) ed_compact_kernel(EdBuffers B, EdGeom G, VplLine* __restrict__ out,
+                                                        int* __restrict__ counts, int cap, int* __restrict__ overflow,
+                                                        int batch) {
+  const int f = blockIdx.x;
+  if (f >= batch) return;
+  const int lane = threadIdx.x;
+  const VplLine* slots = B.slots + (size_t)f * G.nslots;
+  const uint8_t* valid = B.slot_valid + (size_t)f * G.nslots;
+  int n = 0;
+  if (B.status[f] == 1) {
+    int used = B.n_px[f] / G.min_len + 1;
+    if (used > G.nslots) used = G.nslots;
+    for (int base = 0; base < used; base += 32) {
+      int i = base + lane;
+      bool v = i < used && valid[i];
+      unsigned mask = __ballot_sync(0xffffffffu, v);
+      int pos = n + __popc(mask & ((1u << lane) - 1u));
+      if (v && pos < cap) out[(size_t)f * cap + pos] = slots[i];
+      n += __popc(mask);
+    }
+  }
+  if (lane == 0) {
+    if (n > cap) { *overflow = 1; }
+    counts[f] = n > cap ? cap : n;
+  }
+}
+
+}  // namespace
+
+void launch_ed_gmap(const short2* grad, uint16_t* gmap, size_t total, int grad_thresh, cudaStream_t st) {
+  size_t quads = (total + 3) / 4;
+  int blocks = (int)((quads + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  ed_gmap_kernel<<<blocks, 256, 0, st>>>(grad, gmap, total, grad_thresh);
+}
+
+void launch_ed_anchor(const EdBuffers& B, const EdGeom& G, int anchor_thresh, int batch, cudaStream_t st) {
+  cudaMemsetAsync(B.bitmap, 0, (size_t)batch * G.bm_words * sizeof(unsigned), st);
+  cudaMemsetAsync(B.n_anchor, 0, (size_t)batch * sizeof(int), st);
+  int pts = G.nW * G.nH;
+  if (pts <= 0) return;
+  dim3 grid((pts + 255) / 256, batch);
+  ed_anchor_kernel<<<grid, 256, 0, st>>>(B.gmap, B.bitmap, B.n_anchor, G, anchor_thresh);
+}
+
+void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st) {
+  ed_walk_kernel<<<batch, 32, 0, st>>>(B, G, G.min_len, batch);
+}
+
+void launch_ed_fit(const EdBuffers& B, const EdGeom& G, double fit_thr, const short2* grad, const double* lgam,
+                   int batch, cudaStream_t st) {
+  cudaMemsetAsync(B.slot_valid, 0, (size_t)batch * G.nslots, st);
+  dim3 grid(16, batch);  // 64 warps per frame over its chains
+  ed_fit_kernel<<<grid, 128, 0, st>>>(B, G, G.min_len, fit_thr, grad, lgam);
+}
+
+void launch_ed_compact(const EdBuffers& B, const EdGeom& G, VplLine* out, int* counts, int cap, int* overflow,
+                       int batch, cudaStream_t st) {
+  ed_compact_kernel<<<batch, 32, 0, st>>>(B, G, out, counts, cap, overflow, batch);
+}
+
+}  // namespace vpl

@@ -167,6 +167,43 @@ void launch_remap(const uint8_t* src, uint8_t* dst, const float* mapx, const flo
 // lut: batch x tiles x tiles x 256 bytes of scratch
 void launch_clahe(const uint8_t* src, uint8_t* dst, uint8_t* lut, int w, int h, double clip, int tiles, int batch,
                   cudaStream_t st);
+// ---- EDLines (edlines.cu) ---------------------------------------------------------------------
+// Per-frame geometry of one EDLines batch (all frames of a batch share it).
+struct EdGeom {
+  int w, h;
+  int scan;            // scanIntervals_
+  int nW, nH;          // scan-grid size: x = 1 + ix*scan < w-1, y = 1 + iy*scan < h-1
+  int bm_words;        // 32-bit words of the column-major anchor bitmap
+  int cap_px;          // w*h/5   (edgePixelArraySize, edline_detector.cpp:92)
+  int cap_edges;       // cap_px/20 (maxNumOfEdge, :93)
+  int part_cap;        // per-walk scratch entries
+  int nslots;          // line slots per frame: 2*cap_px / minLineLen + 1
+  int min_len;
+  double logNT;        // 2*(log10 w + log10 h), :1186
+};
+// Device buffers of one slot (frame f's part of each array starts at f * the per-frame size
+// that EdGeom gives for the batch's image size).
+struct EdBuffers {
+  uint16_t* gmap;      // B x h x w: bits 0-8 gradient/4, bit 13 edge mark, bit 15 horizontal
+  unsigned* bitmap;    // B x bm_words
+  int* n_anchor;       // B
+  uint32_t* first;     // B x part_cap   x | y << 16 of the current chain's first part
+  uint32_t* second;    // B x part_cap
+  uint32_t* xy;        // B x 2*cap_px   edge chains, re-packed
+  uint32_t* sid;       // B x (cap_edges + 2) chain starts
+  int* n_chain;        // B
+  int* n_px;           // B
+  int* status;         // B: 1, or -1 where EdgeDrawing returns -1
+  VplLine* slots;      // B x nslots
+  uint8_t* slot_valid; // B x nslots
+};
+void launch_ed_gmap(const short2* grad, uint16_t* gmap, size_t total, int grad_thresh, cudaStream_t st);
+void launch_ed_anchor(const EdBuffers& B, const EdGeom& G, int anchor_thresh, int batch, cudaStream_t st);
+void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st);
+void launch_ed_fit(const EdBuffers& B, const EdGeom& G, double fit_thr, const short2* grad, const double* lgam,
+                   int batch, cudaStream_t st);
+void launch_ed_compact(const EdBuffers& B, const EdGeom& G, VplLine* out, int* counts, int cap, int* overflow,
+                       int batch, cudaStream_t st);
 #ifdef VPL_DEBUG_NFA
 void debug_set_cand(int c);
 #endif
