@@ -44,7 +44,12 @@ WORKLOADS = {
     "C1": dict(name="C1_mh04_real_752x480", w=752, h=480, octaves=1, k=1, max_lines=2048),
     "C3": dict(name="C3_d455_1280x720", w=1280, h=720, octaves=2, k=2, max_lines=2048),
     "C4": dict(name="C4_manhattan_1920x1080", w=1920, h=1080, octaves=1, k=2, max_lines=6144),
+    # the detector the reference really runs (EDLineDetector::EDline with the tracker
+    # node's parameters, smoothed=true) on the C2 frames / on the reference's bundled frames
+    "E1": dict(name="E1_edlines_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2"),
+    "E1r": dict(name="E1r_edlines_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1"),
 }
+ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
 
 def measured_peak():
@@ -107,6 +112,7 @@ class ClockSampler:
 
 
 def make_frames(n_unique, seed, workload="C2"):
+    workload = WORKLOADS[workload].get("frames", workload)
     if workload == "C1":  # the reference's bundled EuRoC MH_04 frames (tests/golden/mh04_frames.npz)
         return np.load(os.path.join(ROOT, "tests", "golden", "mh04_frames.npz"))["frames"]
     synth = importlib.import_module("vplines-slam_b200.synth")
@@ -137,11 +143,196 @@ def cpu_baseline(unique, seconds=12.0, threads=None, octaves=1, name=WORKLOAD):
             "single_thread_frames_per_s": 1.0 / per_frame}
 
 
+def ed_cpu_baseline(unique, seconds=10.0, threads=None, name="E1"):
+    """EDLines on the host cores: the reference's own edline_detector.cpp (oracle/_ref, built in the
+    authoring container against oracle/cvshim) when that library travelled here, else the oracle port."""
+    from oracle import oracle as O
+    O.build()
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_edlines.so"))
+    threads = threads or os.cpu_count() or 1
+    t = time.time()
+    O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)
+    per_frame = max((time.time() - t) / 8, 1e-4)
+    n = int(max(threads * 4, min(seconds / per_frame * threads, 16384)))
+    frames = tile_frames(unique, n)
+    t = time.time()
+    total = O.edline_sequence(frames, threads=threads, use_ref=use_ref)
+    dt = time.time() - t
+    what = ("the reference's own line_matching/src/edline_detector.cpp compiled against oracle/cvshim (OpenCV stand-in)"
+            if use_ref else "CPU oracle port of edline_detector.cpp (oracle/orc_edlines.c)")
+    return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"{n} frames of {name} ({total} lines) in {dt:.1f}s; {what}, one detector per thread, "
+                      f"{threads} threads over contiguous frame chunks",
+            "single_thread_frames_per_s": 1.0 / per_frame}
+
+
+def run_reference_edlines(args):
+    from oracle import oracle as O
+    O.build()
+    wl = WORKLOADS[args.workload]
+    unique = make_frames(min(args.unique, 32), args.seed, args.workload)
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_edlines.so"))
+    threads = os.cpu_count() or 1
+    t = time.time()
+    O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)
+    per_frame = max((time.time() - t) / 8, 1e-4)
+    n = int(max(threads * 4, min(5.0 / per_frame * threads, 16384)))
+    frames = tile_frames(unique, n)
+    for _ in range(args.warmup):
+        O.edline_sequence(frames[:max(threads, n // 4)], threads=threads, use_ref=use_ref)
+    t0 = time.time()
+    for _ in range(args.steps):
+        O.edline_sequence(frames, threads=threads, use_ref=use_ref)
+    dt = time.time() - t0
+    fps = n * args.steps / dt
+    kind = "reference" if use_ref else "port"
+    line = {"impl": "reference", "metric": ED_METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16/f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_step": n,
+                       "note": "edline_detector.cpp of the reference compiled against oracle/cvshim" if use_ref
+                       else "CPU oracle port (oracle/_ref not present)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": f"{n} frames/step x {args.steps} steps"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_edlines(args, torch, dist, rank, local_rank, world):
+    """--workload E1 / E1r: EDLineDetector::EDline (tracker-node parameters, smoothed=true) over a batch."""
+    vpl = importlib.import_module("vplines_slam_b200")
+    capi = vpl.capi
+    wl = WORKLOADS[args.workload]
+    W, H = wl["w"], wl["h"]
+    B, S, cap = args.batch, args.slots, (args.max_lines or wl["max_lines"])
+    unique = make_frames(args.unique, args.seed, args.workload)
+    host_buf = tile_frames(unique, B)
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap, max_batch=B,
+                       num_slots=S, blur_first=True, profile=True)
+    param = capi.EDLineParam()
+    ctx.edlines_configure(param)
+    ctx.host_register(host_buf)
+    lines = [np.zeros((B, cap), capi.LINE_DTYPE) for _ in range(S)]
+    counts = [np.zeros(B, np.int32) for _ in range(S)]
+    status = [np.zeros(B, np.int32) for _ in range(S)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_steps(n_steps):
+        pending = []
+        for i in range(n_steps):
+            s = i % S
+            if len(pending) == S:
+                ps = pending.pop(0)
+                ctx.edlines_collect_into(ps, lines[ps], counts[ps], cap, status[ps])
+            ctx.edlines_submit(s, host_buf, smoothed=True)
+            pending.append(s)
+        while pending:
+            ps = pending.pop(0)
+            ctx.edlines_collect_into(ps, lines[ps], counts[ps], cap, status[ps])
+        return int(counts[ps].sum())
+
+    e2e_steps(max(args.warmup, S))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    n_lines = e2e_steps(args.steps)
+    d2h_bytes = ctx.last_d2h_bytes((args.steps - 1) % S)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    ctx.edlines_submit(0, host_buf[:1], smoothed=True)  # frame 0's edge pixels, for the byte counts below
+    ctx.edlines_collect_into(0, lines[0], counts[0], cap, status[0])
+    xy0, _ = ctx.edge_chains(0, W, H)
+    ctx.edlines_submit(0, host_buf, smoothed=True)       # leave a full batch resident in slot 0 again
+    ctx.edlines_collect_into(0, lines[0], counts[0], cap, status[0])
+
+    for w in range(max(args.warmup, S)):
+        ctx.edlines_run_resident(w % S)
+    ctx.sync()
+    ctx.reset_stage_times()
+    l0 = ctx.kernel_launches()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ctx.edlines_run_resident(i % S)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - l0
+    stage = ctx.stage_times()
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+    frames_total = B * args.steps * world
+    value = frames_total / (dev_ms * 1e-3)
+    e2e_value = frames_total / (e2e_ms * 1e-3)
+
+    # roofline of the dominant EDLines kernel; algorithmic bytes per frame (DESIGN.md section 3):
+    P = W * H
+    edge_px = float(len(xy0))  # frame 0 of the last batch (frames are a tiling of `unique`)
+    alg = {"ed_grad": 12.0 * P,                                   # blur/copy+Sobel: r P, w P + 4P; gmap: r 4P, w 2P
+           "ed_anchor": 6.0 * P / (param.scanIntervals ** 2) + P / (param.scanIntervals ** 2) / 8,
+           "ed_walk": 20.0 * edge_px,                              # 3 u16 reads + mark + record, re-pack r+w
+           "ed_fit": 20.0 * edge_px}                               # chain pixel 3 x 4 B + Sobel pair 2 x 4 B
+    ed = {k: stage[k] for k in alg}
+    dom = max(ed, key=lambda k: ed[k][0])
+    peak, peak_kind = measured_peak()
+    launches_in_stage = {"ed_grad": 2, "ed_anchor": 1, "ed_walk": 1, "ed_fit": 2}[dom]
+    dur = ed[dom][0] / max(ed[dom][1] / launches_in_stage, 1)
+    achieved = alg[dom] * B / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
+    tot = max(sum(x[0] for x in stage.values()), 1e-9)
+    roofline = {"bound": "hbm", "kernel": {"ed_grad": "blur5_sobel_kernel+ed_gmap_kernel", "ed_anchor": "ed_anchor_kernel",
+                                           "ed_walk": "ed_walk_kernel", "ed_fit": "ed_fit_kernel+ed_compact_kernel"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "ms_per_launch": dur,
+                "algorithmic_bytes_per_launch": alg[dom] * B,
+                "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items() if v[1]},
+                "stage_share": {k: round(v[0] / tot, 4) for k, v in stage.items() if v[1]}}
+    line = {"metric": ED_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/s16/f64", "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
+            "config": {"workload": wl["name"], "frames_per_step": B, "width": W, "height": H, "slots": S, "max_lines": cap,
+                       "unique_frames": len(unique), "parallelism": f"frames x{world}", "smoothed": True,
+                       "edline_param": [param.ksize, param.sigma, param.gradientThreshold, param.anchorThreshold,
+                                        param.scanIntervals, param.minLineLen, param.lineFitErrThreshold],
+                       "lines_per_frame": round(n_lines / B, 1), "edge_px_frame0": int(edge_px),
+                       "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (B * W * H / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+    if rank == 0:
+        line["cpu_baseline"] = ed_cpu_baseline(unique, name=wl["name"]) if (world == 1 and not args.no_cpu_baseline) else None
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores, nothing else."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload.startswith("E"):
+        return run_reference_edlines(args)
     unique = make_frames(min(args.unique, 32), args.seed)
     from oracle import oracle as O
     O.build()
@@ -199,6 +390,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+
+    if args.workload.startswith("E"):
+        return run_edlines(args, torch, dist, rank, local_rank, world)
 
     vpl = importlib.import_module("vplines_slam_b200")
     capi = vpl.capi

@@ -10,9 +10,11 @@
 //                     pixel, from the Sobel pair the pyramid kernel already wrote   (ed.cpp:128-136)
 //   ed_anchor_kernel  anchor test on the scan grid -> column-major bitmap           (ed.cpp:148-164)
 //   ed_walk_kernel    smart routing.  Chains are claimed in anchor order and a walk stops at any
-//                     earlier edge pixel, so it is sequential per frame: ONE WARP PER FRAME, lane 0
-//                     walks (3 independent u16 loads per step: gradient, direction and edge mark
-//                     share the word), the warp scans the anchor bitmap and re-packs each chain
+//                     earlier edge pixel, so it is sequential per frame: ONE WARP PER FRAME.  The warp
+//                     expands the anchor bitmap 32 words at a time, tests 32 anchors for "already
+//                     an edge pixel" with one gather, walks in lockstep (3 independent u16 loads
+//                     per step: gradient, direction and edge mark share the word) while its lanes
+//                     prefetch a strip of rows ahead of the walker, and re-packs each kept chain
 //                                                                                    (ed.cpp:191-706)
 //   ed_fit_kernel     ONE WARP PER EDGE CHAIN: least-squares fit of the first minLineLen pixels
 //                     (integer sums, exact), extension 32 pixels per step with a ballot for the
@@ -90,19 +92,42 @@ __global__ void ed_anchor_kernel(const uint16_t* __restrict__ gmap, unsigned* __
 // ---- smart routing ---------------------------------------------------------------------------
 struct WalkMem {
   unsigned last_x, last_y;  // ed.cpp:184-185
+  int pfx, pfy;             // centre of the last prefetched strip
 };
 
-// One directional walk by a single thread (ed.cpp:211-312 and its three copies).  Returns the
-// number of pixels recorded, or -1 if `cap` would be exceeded.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// A walk is a chain of dependent loads; when it runs across rows every step touches a new cache
+// line (DRAM latency per pixel).  The 32 lanes therefore keep a strip of 32 rows x ~100 columns
+// ahead of the walker on its way into L1: one prefetch per lane, three columns, re-issued when the
+// walker leaves the inner box of the strip.
+__device__ __forceinline__ void ed_prefetch_strip(const uint16_t* __restrict__ g, int W, int H, int x, int y, int mx,
+                                                  int my, int lane, WalkMem& wm) {
+  if (abs(x - wm.pfx) > 24 || abs(y - wm.pfy) > 8) {
+    wm.pfx = x + 16 * mx;
+    wm.pfy = y + 8 * my;
+    int ry = min(max(wm.pfy - 16 + lane, 0), H - 1);
+    const uint16_t* row = g + (size_t)ry * W;
+    prefetch_l1(row + min(max(wm.pfx - 40, 0), W - 1));
+    prefetch_l1(row + min(max(wm.pfx, 0), W - 1));
+    prefetch_l1(row + min(max(wm.pfx + 40, 0), W - 1));
+  }
+}
+
+// One directional walk (ed.cpp:211-312 and its three copies), executed by the whole warp in
+// lockstep on identical state (SIMT issues one instruction stream either way; the loads are
+// broadcasts).  Every lane stores the edge mark it will read back later; lane 0 records the pixel.
+// Returns the number of pixels recorded, or -1 if `cap` would be exceeded.
 __device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsigned x, unsigned y, int last_dir,
-                                    uint32_t* __restrict__ out, int cap, WalkMem& wm) {
+                                    uint32_t* __restrict__ out, int cap, WalkMem& wm, int lane) {
   int n = 0;
   int idx = (int)y * W + (int)x;
   unsigned v = g[idx];
   while ((v & kG) != 0 && !(v & kEdge)) {
     if (n >= cap) return -1;
     g[idx] = (uint16_t)(v | kEdge);
-    out[n++] = x | (y << 16);
+    if (lane == 0) out[n] = x | (y << 16);
+    n++;
     int should_go = 0;
     int dmain, dperp, mx, my, px, py;
     if (v & kDir) {  // horizontal pixel: go left or right
@@ -132,6 +157,7 @@ __device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsi
     }
     int i2 = idx + dmain;
     unsigned v1 = g[i2 + dperp], v2 = g[i2], v3 = g[i2 - dperp];
+    ed_prefetch_strip(g, W, H, (int)x, (int)y, mx, my, lane, wm);
     unsigned g1 = v1 & 0xffu, g2 = v2 & 0xffu, g3 = v3 & 0xffu;  // the (unsigned char) casts, ed.cpp:231-233
     if (g1 >= g2 && g1 >= g3) { x += mx + px; y += my + py; idx = i2 + dperp; v = v1; }
     else if (g3 >= g2 && g3 >= g1) { x += mx - px; y += my - py; idx = i2 - dperp; v = v3; }
@@ -141,6 +167,7 @@ __device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsi
 }
 
 __global__ void __launch_bounds__(32) ed_walk_kernel(EdBuffers B, EdGeom G, int min_len, int batch) {
+  __shared__ uint32_t s_anchor[1024];  // anchors of the current 32 bitmap words, in visiting order
   const int f = blockIdx.x;
   if (f >= batch) return;
   const int lane = threadIdx.x;
@@ -153,36 +180,50 @@ __global__ void __launch_bounds__(32) ed_walk_kernel(EdBuffers B, EdGeom G, int 
   int status = 1;
   if (B.n_anchor[f] > G.cap_px) status = -1;  // ed.cpp:166-169
   int off1 = 0, off2 = 0, n_edge = 0, k = 0;
-  WalkMem wm = {0u, 0u};
+  WalkMem wm = {0u, 0u, -1000000, -1000000};
   for (int base = 0; status == 1 && base < G.bm_words; base += 32) {
+    // expand the set bits of 32 words into the anchor list (column-major order = bit order)
     unsigned word = (base + lane < G.bm_words) ? bm[base + lane] : 0u;
-    unsigned any = __ballot_sync(0xffffffffu, word != 0u);
-    while (any && status == 1) {
-      int src = __ffs(any) - 1;
-      any &= any - 1;
-      unsigned wv = __shfl_sync(0xffffffffu, word, src);
-      while (wv && status == 1) {
+    int cnt = __popc(word), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    {
+      int o = incl - cnt;
+      unsigned wv = word;
+      while (wv) {
         int b = __ffs(wv) - 1;
         wv &= wv - 1;
-        int cand = ((base + src) << 5) + b;
+        int cand = ((base + lane) << 5) + b;
         int ix = cand / G.nH, iy = cand - ix * G.nH;
-        unsigned x = 1 + ix * G.scan, y = 1 + iy * G.scan;
-        int len1 = 0, len2 = 0;
-        if (lane == 0) {
-          int idx = (int)y * G.w + (int)x;
-          unsigned v = g[idx];
-          if (v & kEdge) {
-            len1 = -2;  // already an edge pixel, ed.cpp:195
-          } else {
-            bool horizontal = (v & kDir) != 0;
-            len1 = ed_walk(g, G.w, G.h, x, y, horizontal ? RIGHT : DOWN, first, G.part_cap, wm);
-            g[idx] = (uint16_t)(g[idx] & ~kEdge);  // the anchor is walked again, ed.cpp:317 / :533
-            len2 = ed_walk(g, G.w, G.h, x, y, horizontal ? LEFT : UP, second, G.part_cap, wm);
-          }
-        }
-        len1 = __shfl_sync(0xffffffffu, len1, 0);
-        len2 = __shfl_sync(0xffffffffu, len2, 0);
-        if (len1 == -2) continue;
+        s_anchor[o++] = (unsigned)(1 + ix * G.scan) | ((unsigned)(1 + iy * G.scan) << 16);
+      }
+    }
+    __syncwarp();
+    for (int a0 = 0; status == 1 && a0 < total; a0 += 32) {
+      // 32 anchors at a time: one gather tells which are already edge pixels (ed.cpp:195); the
+      // gather is repeated for the remaining ones after every walk, since a walk sets marks
+      const bool have = a0 + lane < total;
+      const unsigned axy = have ? s_anchor[a0 + lane] : 0u;
+      const int aidx = (int)(axy >> 16) * G.w + (int)(axy & 0xffff);
+      unsigned todo = __ballot_sync(0xffffffffu, have && !(g[aidx] & kEdge));
+      while (todo && status == 1) {
+        const int src = __ffs(todo) - 1;
+        const unsigned a = __shfl_sync(0xffffffffu, axy, src);
+        const unsigned x = a & 0xffff, y = a >> 16;
+        const int idx = (int)y * G.w + (int)x;
+        const bool horizontal = (g[idx] & kDir) != 0;
+        const int len1 = ed_walk(g, G.w, G.h, x, y, horizontal ? RIGHT : DOWN, first, G.part_cap, wm, lane);
+        g[idx] = (uint16_t)(g[idx] & ~kEdge);  // the anchor is walked again, ed.cpp:317 / :533
+        const int len2 = ed_walk(g, G.w, G.h, x, y, horizontal ? LEFT : UP, second, G.part_cap, wm, lane);
+        __syncwarp();
+        // anchors after this one that the two walks have just covered drop out
+        const unsigned later = src == 31 ? 0u : (0xffffffffu << (src + 1));
+        todo = __ballot_sync(0xffffffffu, have && !(g[aidx] & kEdge)) & todo & later;
         if (len1 < 0 || len2 < 0) { status = -1; break; }
         if (len1 + len2 < min_len + 1) continue;  // short edge: records dropped, marks stay, ed.cpp:641-643
         off1 += len1; off2 += len2;
@@ -196,6 +237,7 @@ __global__ void __launch_bounds__(32) ed_walk_kernel(EdBuffers B, EdGeom G, int 
         __syncwarp();
       }
     }
+    __syncwarp();
   }
   if (!(off1 && off2)) status = -1;  // ed.cpp:667 "lines not found"
   if (lane == 0) {
