@@ -148,7 +148,7 @@ def ed_cpu_baseline(unique, seconds=10.0, threads=None, name="E1"):
     authoring container against oracle/cvshim) when that library travelled here, else the oracle port."""
     from oracle import oracle as O
     O.build()
-    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_edlines.so"))
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_linefront.so"))
     threads = threads or os.cpu_count() or 1
     t = time.time()
     O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)
@@ -171,7 +171,7 @@ def run_reference_edlines(args):
     O.build()
     wl = WORKLOADS[args.workload]
     unique = make_frames(min(args.unique, 32), args.seed, args.workload)
-    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_edlines.so"))
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_linefront.so"))
     threads = os.cpu_count() or 1
     t = time.time()
     O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)

@@ -4,6 +4,8 @@
  * A stand-in for the handful of OpenCV-3.4 C++ names that the reference's line primitives
  * library uses, so that the reference's OWN sources
  *     /root/reference/line_matching/src/edline_detector.{h,cpp}, line.h
+ * and  line_matching.{h,cpp}, lk_tracker_invoker_2d.cpp, klt.h (+ the first 40 lines of klt.cpp:
+ * getImageNormParams and the KLT constructor)
  * compile unmodified, from where they lie, into oracle/_ref/ (recipe: oracle/Makefile target
  * `ref`).  OpenCV C++ itself is not in this image, so the *library* calls are
  * answered here; everything the reference wrote itself (edge drawing walk, least-squares fit,
@@ -21,12 +23,21 @@
  *       accumulators, result cast to float (modules/core/src/matmul.cpp, from memory; for the
  *       integer pixel coordinates the reference multiplies, the double sums are exact, so the
  *       accumulation order does not matter).
+ *   meanStdDev(CV_16S): integer sum, double sum of squares, mean = s * (1/N),
+ *       sd = sqrt(max(q * (1/N) - mean^2, 0))                 [pinned bit-exact on cv2 4.13, 2000 windows]
+ *   cvFloor / cvRound(float): the SSE forms (INT_MIN on NaN / overflow, nearest-even).
+ *   KLT::calc2D's own OpenCV calls (buildOpticalFlowPyramid, copyMakeBorder) are NOT emulated: the
+ *       glue (oracle/ref_linematch_glue.cpp) defines KLT::calc2D on top of the oracle's pyramid and
+ *       Scharr code (pinned against cv2.buildOpticalFlowPyramid / cv2.Scharr) and runs the
+ *       reference's LKTrackerInvoker2D on it level by level, as klt.cpp:598-627 does.
+ *   drawing / GUI calls (only reachable with debug_show > 0) are no-ops.
  *   parallel_for_: runs the body once over the whole range on the calling thread (the order the
  *       reference produces with one thread; with more threads its output order is a race,
  *       edline_detector.cpp:1081-1083).
  */
 #ifndef VPL_CVSHIM_OPENCV_HPP
 #define VPL_CVSHIM_OPENCV_HPP
+#include <algorithm>
 #include <array>
 #include <cfloat>
 #include <cmath>
@@ -34,6 +45,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
 #include <iostream>
 #include <memory>
 #include <sstream>
@@ -46,6 +58,14 @@ void orc_sobel3(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy);
 }
 
 typedef unsigned char uchar;
+#define CV_8U 0
+#define CV_8S 1
+#define CV_16U 2
+#define CV_16S 3
+#define CV_32S 4
+#define CV_32F 5
+#define CV_64F 6
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << 3))
 #define CV_8UC1 0
 #define CV_8SC1 1
 #define CV_16UC1 2
@@ -53,7 +73,10 @@ typedef unsigned char uchar;
 #define CV_32SC1 4
 #define CV_32FC1 5
 #define CV_64FC1 6
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16SC2 CV_MAKETYPE(CV_16S, 2)
 #define CV_AA 16
+#define CV_CPU_SSE2 3
 #define CV_Assert(expr)                                                        \
   do {                                                                         \
     if (!(expr)) {                                                             \
@@ -76,18 +99,57 @@ struct Size {
   int width, height;
   Size() : width(0), height(0) {}
   Size(int w, int h) : width(w), height(h) {}
+  int area() const { return width * height; }
+  bool operator==(const Size& o) const { return width == o.width && height == o.height; }
+};
+struct Size2f {
+  float width, height;
+  Size2f() : width(0), height(0) {}
+  Size2f(float w, float h) : width(w), height(h) {}
 };
 template <class T>
 struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}
   Point_(T a, T b) : x(a), y(b) {}
+  template <class U>
+  Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
+  Point_& operator+=(const Point_& o) { x += o.x; y += o.y; return *this; }
+  Point_& operator-=(const Point_& o) { x -= o.x; y -= o.y; return *this; }
+  double ddot(const Point_& o) const { return (double)x * o.x + (double)y * o.y; }
 };
+template <class T> static inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
+template <class T> static inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+static inline Point_<float> operator*(const Point_<float>& a, float b) { return Point_<float>(a.x * b, a.y * b); }
 typedef Point_<float> Point2f;
 typedef Point_<int> Point;
+typedef Point_<int> Point2i;
+struct Rect {
+  int x, y, width, height;
+  Rect() : x(0), y(0), width(0), height(0) {}
+  Rect(double x_, double y_, double w, double h) : x((int)x_), y((int)y_), width((int)w), height((int)h) {}
+};
+struct Scalar {
+  double val[4];
+  Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+  double& operator[](int i) { return val[i]; }
+  const double& operator[](int i) const { return val[i]; }
+};
+struct TermCriteria {
+  enum { COUNT = 1, MAX_ITER = 1, EPS = 2 };
+  int type, maxCount;
+  double epsilon;
+  TermCriteria() : type(0), maxCount(0), epsilon(0) {}
+  TermCriteria(int t, int n, double e) : type(t), maxCount(n), epsilon(e) {}
+};
+enum { OPTFLOW_USE_INITIAL_FLOW = 4, OPTFLOW_LK_GET_MIN_EIGENVALS = 8 };
+enum { COLOR_GRAY2BGR = 8, FONT_HERSHEY_TRIPLEX = 4 };
+static inline bool checkHardwareSupport(int) { return false; }
 template <class T, int N>
 struct Vec {
   T val[N];
+  Vec() { for (int i = 0; i < N; i++) val[i] = T(); }
+  Vec(T a, T b) { val[0] = a; val[1] = b; }
   T& operator[](int i) { return val[i]; }
   const T& operator[](int i) const { return val[i]; }
 };
@@ -98,10 +160,11 @@ struct Range {
   Range(int s, int e) : start(s), end(e) {}
 };
 
-static inline size_t cvshimElemSize(int type) {
-  static const size_t sz[7] = {1, 1, 2, 2, 4, 4, 8};
-  return sz[type];
+static inline size_t cvshimElemSize1(int type) {
+  static const size_t sz[8] = {1, 1, 2, 2, 4, 4, 8, 0};
+  return sz[type & 7];
 }
+static inline size_t cvshimElemSize(int type) { return cvshimElemSize1(type) * (size_t)((type >> 3) + 1); }
 template <class T>
 struct DataType;
 template <>
@@ -112,45 +175,68 @@ template <>
 struct DataType<int> {
   enum { type = CV_32SC1 };
 };
+template <>
+struct DataType<short> {
+  enum { type = CV_16SC1, depth = CV_16S };
+};
 
 class Mat {
  public:
   int rows, cols;
   uchar* data;
-  Mat() : rows(0), cols(0), data(nullptr), type_(0) {}
-  Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), type_(0) { create(r, c, type); }
-  /* header over caller memory (no copy), like cv::Mat(rows, cols, type, void*) */
-  Mat(int r, int c, int type, void* ext) : rows(r), cols(c), data((uchar*)ext), type_(type) {}
+  size_t step; /* bytes per row */
+  Mat() : rows(0), cols(0), data(nullptr), step(0), type_(0) {}
+  Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), step(0), type_(0) { create(r, c, type); }
+  /* header over caller memory (no copy), like cv::Mat(rows, cols, type, void*, step) */
+  Mat(int r, int c, int type, void* ext, size_t step_ = 0)
+      : rows(r), cols(c), data((uchar*)ext), step(step_ ? step_ : (size_t)c * cvshimElemSize(type)), type_(type) {}
+  Mat(Size sz, int type, void* ext)
+      : rows(sz.height), cols(sz.width), data((uchar*)ext), step((size_t)sz.width * cvshimElemSize(type)), type_(type) {}
   void create(int r, int c, int type) {
     if (data && r == rows && c == cols && type == type_) return; /* same as cv::Mat::create */
     buf_.reset(new std::vector<uchar>((size_t)r * c * cvshimElemSize(type), 0));
     rows = r;
     cols = c;
     type_ = type;
+    step = (size_t)c * cvshimElemSize(type);
     data = buf_->data();
   }
-  static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+  static Mat zeros(double r, double c, int type) { return Mat((int)r, (int)c, type); }
   int type() const { return type_; }
+  int depth() const { return type_ & 7; }
+  int channels() const { return (type_ >> 3) + 1; }
   size_t elemSize() const { return cvshimElemSize(type_); }
+  size_t elemSize1() const { return cvshimElemSize1(type_); }
+  Size size() const { return Size(cols, rows); }
   bool empty() const { return data == nullptr || rows * cols == 0; }
+  bool isContinuous() const { return step == (size_t)cols * elemSize(); }
   template <class T>
   T* ptr(int r = 0) {
-    return (T*)(data + (size_t)r * cols * elemSize());
+    return (T*)(data + (size_t)r * step);
   }
   template <class T>
   const T* ptr(int r = 0) const {
-    return (const T*)(data + (size_t)r * cols * elemSize());
+    return (const T*)(data + (size_t)r * step);
   }
-  uchar* ptr(int r = 0) { return data + (size_t)r * cols * elemSize(); }
-  const uchar* ptr(int r = 0) const { return data + (size_t)r * cols * elemSize(); }
+  uchar* ptr(int r = 0) { return data + (size_t)r * step; }
+  const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+  template <class T>
+  T& at(int r, int c) {
+    return ((T*)(data + (size_t)r * step))[c];
+  }
+  template <class T>
+  const T& at(int r, int c) const {
+    return ((const T*)(data + (size_t)r * step))[c];
+  }
+  Mat operator()(const Rect&) const { return *this; } /* only reached from debug drawing */
   Mat& setTo(int v) {
     if (v != 0 && elemSize() != 1) CVSHIM_UNSUPPORTED("Mat::setTo(nonzero) on a multi-byte type");
-    std::memset(data, v, (size_t)rows * cols * elemSize());
+    for (int r = 0; r < rows; r++) std::memset(ptr(r), v, (size_t)cols * elemSize());
     return *this;
   }
   Mat clone() const {
     Mat m(rows, cols, type_);
-    std::memcpy(m.data, data, (size_t)rows * cols * elemSize());
+    for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize());
     return m;
   }
 
@@ -295,6 +381,127 @@ class FileStorage {
   }
   void release() {}
 };
+
+/* ---- what klt.h / lk_tracker_invoker_2d.cpp / line_matching.cpp need ------------------------ */
+static inline int cvFloor(float v) { /* SSE cvFloor: INT_MIN on NaN / overflow */
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
+  int i = (int)v;
+  return i - (v < (float)i);
+}
+static inline int cvFloor(double v) {
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+  int i = (int)v;
+  return i - (v < (double)i);
+}
+static inline int cvRound(float v) { /* _mm_cvtss_si32 */
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
+  return (int)lrintf(v);
+}
+static inline int cvRound(double v) {
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+  return (int)lrint(v);
+}
+static inline int cvRound(int v) { return v; }
+
+template <class T>
+class AutoBuffer {
+ public:
+  explicit AutoBuffer(size_t n) : v_(n) {}
+  operator T*() { return v_.data(); }
+
+ private:
+  std::vector<T> v_;
+};
+
+static inline void meanStdDev(const Mat& src, Mat& mean, Mat& sd) {
+  if (src.type() != CV_16SC1) CVSHIM_UNSUPPORTED("meanStdDev on a type other than CV_16SC1");
+  long long s = 0;
+  double q = 0;
+  for (int r = 0; r < src.rows; r++) {
+    const short* p = src.ptr<short>(r);
+    for (int c = 0; c < src.cols; c++) {
+      s += p[c];
+      q += (double)p[c] * p[c];
+    }
+  }
+  double scale = 1.0 / ((double)src.rows * src.cols);
+  double m = (double)s * scale;
+  double var = q * scale - m * m;
+  mean.create(1, 1, CV_64FC1);
+  sd.create(1, 1, CV_64FC1);
+  mean.at<double>(0, 0) = m;
+  sd.at<double>(0, 0) = std::sqrt(var > 0 ? var : 0);
+}
+
+/* Input/Output array proxies: just enough to carry the argument types Matching() passes */
+class _InputArray {
+ public:
+  enum { NONE = 0, MAT = 1, STD_VECTOR = 3, STD_VECTOR_MAT = 5 };
+  _InputArray() : m(nullptr), vp(nullptr), vu(nullptr), vf(nullptr) {}
+  _InputArray(const Mat& a) : m(&a), vp(nullptr), vu(nullptr), vf(nullptr) {}
+  _InputArray(const std::vector<Point2f>& a) : m(nullptr), vp((std::vector<Point2f>*)&a), vu(nullptr), vf(nullptr) {}
+  _InputArray(const std::vector<uchar>& a) : m(nullptr), vp(nullptr), vu((std::vector<uchar>*)&a), vf(nullptr) {}
+  _InputArray(const std::vector<float>& a) : m(nullptr), vp(nullptr), vu(nullptr), vf((std::vector<float>*)&a) {}
+  int kind() const { return m ? MAT : (vp || vu || vf) ? STD_VECTOR : NONE; }
+  bool needed() const { return kind() != NONE; }
+  const Mat* m;
+  std::vector<Point2f>* vp;
+  std::vector<uchar>* vu;
+  std::vector<float>* vf;
+};
+typedef _InputArray _OutputArray;
+typedef _InputArray _InputOutputArray;
+typedef const _InputArray& InputArray;
+typedef const _InputArray& OutputArray;
+typedef const _InputArray& InputOutputArray;
+static inline const _InputArray& noArray() {
+  static _InputArray none;
+  return none;
+}
+
+class SparsePyrLKOpticalFlow {
+ public:
+  virtual ~SparsePyrLKOpticalFlow() {}
+};
+
+template <class T>
+class Ptr : public std::shared_ptr<T> {
+ public:
+  Ptr() {}
+  Ptr(const std::shared_ptr<T>& p) : std::shared_ptr<T>(p) {}
+  void release() { this->reset(); }
+};
+template <class T, class... A>
+static inline Ptr<T> makePtr(A&&... a) {
+  return Ptr<T>(std::make_shared<T>(std::forward<A>(a)...));
+}
+
+/* drawing / GUI: reachable only with debug_show > 0 -- no-ops */
+struct RotatedRect {
+  RotatedRect(const Point2f&, const Size2f&, float) {}
+  void points(Point2f* p) const { for (int i = 0; i < 4; i++) p[i] = Point2f(); }
+};
+class LineIterator {
+ public:
+  template <class A, class B>
+  LineIterator(const Mat&, A, B, int = 8) : count(0) {}
+  int count;
+  uchar* operator*() { return dummy_; }
+  LineIterator& operator++() { return *this; }
+  LineIterator operator++(int) { return *this; }
+
+ private:
+  uchar dummy_[4];
+};
+template <class... A> static inline void line(A&&...) {}
+template <class... A> static inline void circle(A&&...) {}
+template <class... A> static inline void arrowedLine(A&&...) {}
+template <class... A> static inline void putText(A&&...) {}
+template <class... A> static inline void cvtColor(A&&...) {}
+template <class... A> static inline void addWeighted(A&&...) {}
+template <class... A> static inline void imshow(A&&...) {}
+template <class... A> static inline bool imwrite(A&&...) { return true; }
+static inline int waitKey(int = 0) { return -1; }
 
 }  // namespace cv
 #endif

@@ -220,7 +220,7 @@ def edline_detect(img, param=None, smoothed=True, cap=1 << 14, stages=False):
     return lines
 
 
-_REF_SO = os.path.join(_HERE, "_ref", "libref_edlines.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libref_linefront.so")
 _ref = None
 
 
@@ -229,8 +229,8 @@ def ref_available():
 
 
 def build_ref():
-    """oracle/_ref/libref_edlines.so = the reference's own edline_detector.cpp compiled against
-    oracle/cvshim.  Only possible where /root/reference exists; elsewhere the prebuilt file is used."""
+    """oracle/_ref/libref_linefront.so = the reference's own edline_detector.cpp, line_matching.cpp and
+    lk_tracker_invoker_2d.cpp compiled against oracle/cvshim.  Only possible where /root/reference exists; elsewhere the prebuilt file is used."""
     if os.path.isdir("/root/reference/line_matching/src"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return _REF_SO if os.path.exists(_REF_SO) else None
@@ -244,6 +244,8 @@ def ref_lib():
         _ref = ctypes.CDLL(_REF_SO)
         _ref.ref_edline_detect.restype = ctypes.c_int
         _ref.ref_edline_sequence_mt.restype = ctypes.c_longlong
+        _ref.ref_line_matching.restype = ctypes.c_int
+        _ref.ref_linefront_sequence_mt.restype = ctypes.c_longlong
     return _ref
 
 
@@ -270,6 +272,96 @@ def edline_sequence(frames, param=None, smoothed=True, threads=1, use_ref=False)
     L = lib(); L.orc_edline_sequence_mt.restype = ctypes.c_int64
     return int(L.orc_edline_sequence_mt(_p(frames), n, w, h, ctypes.byref(param), int(bool(smoothed)),
                                         int(threads)))
+
+
+# ---- the reference's real matcher: LineMatching::Matching (orc_linematch.c) ---------------------
+class LineMatchParam(ctypes.Structure):
+    _fields_ = [("step", ctypes.c_int), ("closest_line_threshold", ctypes.c_float),
+                ("line_matching_ratio", ctypes.c_float), ("line_distance_error_ratio", ctypes.c_float),
+                ("klt_error_threshold", ctypes.c_float), ("win", ctypes.c_int), ("max_level", ctypes.c_int),
+                ("max_count", ctypes.c_int), ("epsilon", ctypes.c_double), ("min_eig", ctypes.c_float),
+                ("topo_distance_threshold", ctypes.c_float), ("topo_length_ratio", ctypes.c_float),
+                ("topo_violation_ratio", ctypes.c_float)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().orc_lm_default_param(ctypes.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def pyrdown_std(img):
+    img = _u8(img); h, w = img.shape
+    out = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyrdown_std(_p(img), w, h, _p(out))
+    return out
+
+
+def klt_calc2d(img_ref, img_cur, pts, win=13, max_level=3, max_count=30, epsilon=0.001, min_eig=1e-4, illum=True):
+    """KLT::calc2D (flags 0) -> (next_pts [n,2] f32, status u8, err f32)."""
+    img_ref = _u8(img_ref); img_cur = _u8(img_cur); h, w = img_ref.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    n = len(pts)
+    nxt = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    lib().orc_klt_calc2d(_p(img_ref), _p(img_cur), w, h, _p(pts), n, int(win), int(max_level), int(max_count),
+                         ctypes.c_double(epsilon), ctypes.c_float(min_eig), int(bool(illum)), _p(nxt), _p(st), _p(err))
+    return nxt, st, err
+
+
+def line_matching(img_ref, img_cur, lines_ref, lines_cur, param=None, illum=True, topo=True, details=False):
+    """LineMatching::Matching -> ref_to_cur int32[n_ref] (None when the reference returns false);
+    details=True adds a dict with the per-anchor arrays."""
+    param = param or LineMatchParam()
+    img_ref = _u8(img_ref); img_cur = _u8(img_cur); h, w = img_ref.shape
+    lr = np.ascontiguousarray(lines_ref, LINE_DTYPE); lc = np.ascontiguousarray(lines_cur, LINE_DTYPE)
+    cap = int(sum(int(l / max(param.step, 1)) + 2 for l in lr["length"])) + 8 if len(lr) else 8
+    r2c = np.full(len(lr), -1, np.int32)
+    kr = np.zeros((cap, 2), np.float32); kc = np.zeros((cap, 2), np.float32)
+    st = np.zeros(cap, np.uint8); er = np.zeros(cap, np.float32); k2l = np.zeros(cap, np.int32)
+    nkp = ctypes.c_int()
+    L = lib(); L.orc_line_matching.restype = ctypes.c_int
+    ok = L.orc_line_matching(_p(img_ref), _p(img_cur), w, h, _p(lr), len(lr), _p(lc), len(lc), ctypes.byref(param),
+                             int(bool(illum)), int(bool(topo)), _p(r2c), _p(kr), _p(kc), _p(st), _p(er), _p(k2l), cap,
+                             ctypes.byref(nkp))
+    res = r2c if ok else None
+    if details:
+        n = nkp.value
+        return res, dict(kps_ref=kr[:n].copy(), kps_cur=kc[:n].copy(), status=st[:n].copy(), err=er[:n].copy(),
+                         kp2line=k2l[:n].copy())
+    return res
+
+
+def ref_line_matching(img_ref, img_cur, lines_ref, lines_cur, illum=True, topo=True, details=False):
+    """The same call through the reference's own line_matching.cpp / lk_tracker_invoker_2d.cpp (oracle/_ref)."""
+    img_ref = _u8(img_ref); img_cur = _u8(img_cur); h, w = img_ref.shape
+    lr = np.ascontiguousarray(lines_ref, LINE_DTYPE); lc = np.ascontiguousarray(lines_cur, LINE_DTYPE)
+    cap = int(sum(int(l / 10) + 2 for l in lr["length"])) + 8 if len(lr) else 8
+    r2c = np.full(len(lr), -1, np.int32)
+    kr = np.zeros((cap, 2), np.float32); kc = np.zeros((cap, 2), np.float32)
+    st = np.zeros(cap, np.uint8); er = np.zeros(cap, np.float32); k2l = np.zeros(cap, np.int32)
+    nkp = ctypes.c_int()
+    ok = ref_lib().ref_line_matching(_p(img_ref), _p(img_cur), w, h, _p(lr), len(lr), _p(lc), len(lc), int(bool(illum)),
+                                     int(bool(topo)), _p(r2c), _p(kr), _p(kc), _p(st), _p(er), _p(k2l), cap,
+                                     ctypes.byref(nkp))
+    res = r2c if ok else None
+    if details:
+        n = nkp.value
+        return res, dict(kps_ref=kr[:n].copy(), kps_cur=kc[:n].copy(), status=st[:n].copy(), err=er[:n].copy(),
+                         kp2line=k2l[:n].copy())
+    return res
+
+
+def linefront_sequence(frames, param=None, smoothed=True, threads=1, use_ref=False):
+    """EDLines on every frame + Matching(prev, cur) on every consecutive pair (the tracker's hot loop),
+    frames over host threads in contiguous chunks with a one-frame halo -> number of matched lines."""
+    param = param or EDLineParam()
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    if use_ref:
+        return int(ref_lib().ref_linefront_sequence_mt(_p(frames), n, w, h, ctypes.byref(param), int(bool(smoothed)),
+                                                       int(threads)))
+    L = lib(); L.orc_linefront_sequence_mt.restype = ctypes.c_int64
+    return int(L.orc_linefront_sequence_mt(_p(frames), n, w, h, ctypes.byref(param), int(bool(smoothed)), int(threads)))
 
 
 def frontend_sequence(frames, num_octaves=1, max_lines=8192, threads=1):

@@ -9,7 +9,7 @@
  * instead of cv::Mat_ products (exactly equal, see fit_solve), explicit output order.
  * PINNED: tests/test_oracle_edlines.py compares every output (edge chains and lines, bit for bit)
  * with the reference's own edline_detector.cpp compiled against oracle/cvshim
- * (oracle/_ref/libref_edlines.so, built by `make -C oracle ref`) and with the golden vectors that
+ * (oracle/_ref/libref_linefront.so, built by `make -C oracle ref`) and with the golden vectors that
  * build produced (tests/golden/ref_edlines.npz).
  *
  * OpenCV calls inside EdgeDrawing (ed.cpp:125-136) are restated with the semantics probed on

@@ -3,7 +3,7 @@
  *
  * extern "C" door into the reference's own EDLines detector, compiled from
  * /root/reference/line_matching/src/edline_detector.cpp (unmodified, where it lies) against
- * oracle/cvshim (see that header for what is substituted).  Output: oracle/_ref/libref_edlines.so.
+ * oracle/cvshim (see that header for what is substituted).  Output: part of oracle/_ref/libref_linefront.so.
  * Used to (1) pin oracle/orc_edlines.c, (2) generate tests/golden/ref_edlines.npz
  * (tests/golden/make_golden_edlines.py) and (3) serve as the "reference" CPU baseline of
  * bench.py's EDLines workload.  Never loaded by the product.

@@ -124,6 +124,45 @@ double orc_ed_nfa(int n, int k, double p, double logNT);
 int64_t orc_edline_sequence_mt(const uint8_t* frames, int n_frames, int w, int h,
                                const OrcEDLineParam* p, int smoothed, int n_threads);
 
+/* ---- the reference's real matcher: LineMatching::Matching (orc_linematch.c) ---- */
+typedef struct {
+  /* LineMatching ctor defaults, line_matching/src/line_matching.h:14-18 */
+  int step;
+  float closest_line_threshold, line_matching_ratio, line_distance_error_ratio, klt_error_threshold;
+  /* KLT as Matching configures it, line_matching.cpp:14, :630-631 */
+  int win, max_level, max_count;
+  double epsilon;
+  float min_eig;
+  /* TopologicalFilter defaults, line_matching.h:45-47 */
+  float topo_distance_threshold, topo_length_ratio, topo_violation_ratio;
+} OrcLineMatchParam;
+void orc_lm_default_param(OrcLineMatchParam* p);
+/* One level of cv::buildOpticalFlowPyramid(img, winSize, maxLevel, withDerivatives=false) plus the
+ * zero-padded Scharr derivative KLT::calc2D adds for the previous image (klt.cpp:598-613). */
+typedef struct {
+  int w, h, pad;   /* level size and border (= winSize) */
+  int stride;      /* w + 2 pad, in pixels */
+  uint8_t* img;    /* (h + 2 pad) x stride, BORDER_REFLECT_101 */
+  int16_t* deriv;  /* (h + 2 pad) x stride x 2 (dIx, dIy), zero border; NULL when not requested */
+} OrcKltLevel;
+/* levels: room for 8; returns the top level index (<= max_level). */
+int orc_klt_build_levels(const uint8_t* img, int w, int h, int win, int max_level, int with_deriv, OrcKltLevel* levels);
+void orc_klt_free_levels(OrcKltLevel* levels, int top);
+void orc_pyrdown_std(const uint8_t* src, int w, int h, uint8_t* dst); /* cv::pyrDown -> ((w+1)/2,(h+1)/2) */
+/* KLT::calc2D with flags = 0 (klt.cpp:491-628): prev_pts/next_pts n x 2 floats */
+void orc_klt_calc2d(const uint8_t* img_ref, const uint8_t* img_cur, int w, int h, const float* prev_pts, int n,
+                    int win, int max_level, int max_count, double epsilon, float min_eig, int illumination_adapt,
+                    float* next_pts, uint8_t* status, float* err);
+int orc_lm_anchors(const OrcLine* lines, int n_lines, int step, float* kps, int32_t* line_kp_num, int cap);
+/* ref_to_cur: n_ref entries (-1 = unmatched).  Optional per-anchor outputs (cap_kp entries). */
+int orc_line_matching(const uint8_t* img_ref, const uint8_t* img_cur, int w, int h, const OrcLine* lines_ref, int n_ref,
+                      const OrcLine* lines_cur, int n_cur, const OrcLineMatchParam* P, int illumination_adapt,
+                      int topological_filter, int32_t* ref_to_cur, float* kps_ref, float* kps_cur, uint8_t* status,
+                      float* err, int32_t* kp2line_cur, int cap_kp, int* n_kp);
+
+int64_t orc_linefront_sequence_mt(const uint8_t* frames, int n_frames, int w, int h, const OrcEDLineParam* p,
+                                  int smoothed, int n_threads);
+
 /* Whole front end on a frame sequence (for the CPU baseline timing).  Returns
  * total keylines over the sequence (each frame is matched k=1 against the
  * previous one; results are discarded, this entry point exists for timing). */

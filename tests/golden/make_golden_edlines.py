@@ -1,6 +1,6 @@
 """Generates tests/golden/ref_edlines.npz: outputs of the REFERENCE'S OWN EDLines detector
 (/root/reference/line_matching/src/edline_detector.cpp compiled against oracle/cvshim into
-oracle/_ref/libref_edlines.so, `make -C oracle ref`) -- run in the authoring container, where
+oracle/_ref/libref_linefront.so, `make -C oracle ref`) -- run in the authoring container, where
 /root/reference exists.  The GPU box has neither; tests read only the .npz.
 
 Cases (Line records in single-thread order + edge-chain pixels + chain starts):

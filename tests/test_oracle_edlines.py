@@ -1,7 +1,7 @@
 """Oracle for SURVEY 8f-1 (EDLines, oracle/orc_edlines.c) pinned against the reference's OWN code:
 tests/golden/ref_edlines.npz was produced by /root/reference/line_matching/src/edline_detector.cpp
 compiled against oracle/cvshim (tests/golden/make_golden_edlines.py); where that build exists
-(oracle/_ref/libref_edlines.so) it is also called live.  Bar: bit-exact -- edge-chain pixels,
+(oracle/_ref/libref_linefront.so) it is also called live.  Bar: bit-exact -- edge-chain pixels,
 chain starts and every byte of every Line record, in single-thread order."""
 import importlib.util
 import os
@@ -31,7 +31,7 @@ def test_edlines_golden(orc, gold, name):
 
 
 def test_edlines_live_reference_build(orc, mh04, synth):
-    if not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_edlines.so")):
+    if not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_linefront.so")):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     imgs = [(mh04[k], orc.EDLineParam(), True) for k in (2, 7, 12)]
     imgs += [(f, orc.EDLineParam(minLineLen=18), False) for f in synth.sequence(3, w=320, h=200, seed=77, n_quads=10, n_strokes=16)]
