@@ -105,6 +105,8 @@ typedef struct VplConfig {
   int32_t num_slots;    /* batches in flight for submit/collect (1..4)           */
   int32_t blur_first;   /* 1: LSDDetector blurs octave 0 with GaussianBlur 5x5   */
   int32_t profile;      /* 1: record per-stage CUDA-event timings                */
+  int32_t lsd_path;     /* 1 (default): allocate the LSD/LBD/Hamming buffers; 0: a context for the
+                           EDLines + KLT line matching front end only (saves ~13 MB per frame)    */
 } VplConfig;
 
 /* ---- lifetime -------------------------------------------------------------- */
@@ -159,6 +161,56 @@ int vpl_edlines_run_resident(VplContext* ctx, int slot);
  * xy = x | y << 16 per edge pixel (cap_px entries), sid = chain starts (cap_chains + 1 entries). */
 int vpl_debug_edge_chains(VplContext* ctx, int frame, uint32_t* xy, int cap_px, uint32_t* sid,
                           int cap_chains, int32_t* n_px, int32_t* n_chains);
+
+/* ---- LineMatching::Matching: the matcher the reference really runs ------- */
+/* LineMatching's constructor defaults (line_matching/src/line_matching.h:14-18), the KLT it builds
+ * and reconfigures in Matching() (line_matching.cpp:14, :630-631: window 13x13 -- fixed here --,
+ * maxLevel 3, 30 iterations, eps 0.001, minEig 1e-4, flags 0), TopologicalFilter's defaults
+ * (line_matching.h:45-47) and the two switches the tracker passes as true
+ * (feature_tracker/src/line_feature_tracker.cpp:307-308). */
+typedef struct VplLineMatchParam {
+  int32_t step;
+  float closest_line_threshold, line_matching_ratio, line_distance_error_ratio, klt_error_threshold;
+  int32_t max_level, max_count;
+  double epsilon;
+  float min_eig;
+  float topo_distance_threshold, topo_length_ratio, topo_violation_ratio;
+  int32_t illumination_adapt, topological_filter;
+  int32_t max_anchors; /* capacity: anchor points per frame pair (sum over lines of len/step + 2) */
+} VplLineMatchParam;
+void vpl_linematch_default_param(VplLineMatchParam* p);
+/* = LineMatching(...) + its KLT: allocates the pyramids and anchor buffers for the context's max
+ * image size and batch.  Call before the first match, not while batches are in flight. */
+int vpl_linematch_configure(VplContext* ctx, const VplLineMatchParam* p);
+/* = bool LineMatching::Matching(img_ref, img_cur, lines_ref, lines_cur, line_ref_to_line_cur, NULL,
+ * NULL, NULL, illumination_adapt, topological_filter, 0) (line_matching.cpp:605-690), i.e. the
+ * tracker's match_line_match seam (feature_tracker/src/line_feature_tracker.cpp:291-313), on n_pairs
+ * independent pairs.  lines_ref: n_pairs * cap entries (pair p at + p*cap, n_ref[p] valid), lines_cur
+ * likewise; ref_to_cur: n_pairs * cap, entry i of pair p = index of the current line matched to
+ * reference line i, or -1 (all -1 when a side is empty, where Matching returns false).
+ * n_pairs <= max_batch / 2. */
+int vpl_linematch_batch(VplContext* ctx, const uint8_t* const* imgs_ref, const uint8_t* const* imgs_cur,
+                        int n_pairs, int w, int h, size_t stride, const VplLine* lines_ref,
+                        const int32_t* n_ref, const VplLine* lines_cur, const int32_t* n_cur, int cap,
+                        int32_t* ref_to_cur);
+/* Per-anchor results of pair `pair` of the last match on slot 0 (LineMatching::getPointMatchResult
+ * + status_/errors_): cap entries each; *n = number of anchors. */
+int vpl_debug_linematch_points(VplContext* ctx, int pair, float* kps_ref, float* kps_cur,
+                               uint8_t* status, float* err, int32_t* kp2line_cur, int cap, int32_t* n);
+
+/* ---- the reference's per-frame hot loop, fused: EDline on every frame + Matching(frame f-1,
+ *      frame f) (LineFeatureTracker::readImage, line_feature_tracker.cpp:87 and :115) --------- */
+/* n consecutive frames; lines/counts as vpl_edlines_detect_batch; prev_to_cur: n * cap, row f
+ * (f >= 1) maps the lines of frame f-1 to the lines of frame f (-1 = unmatched; row 0 is all -1:
+ * a caller that cuts a sequence into batches overlaps them by one frame).  Needs both
+ * vpl_edlines_configure and vpl_linematch_configure. */
+int vpl_linefront_batch(VplContext* ctx, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                        int smoothed, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur);
+int vpl_linefront_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h,
+                         size_t stride, int smoothed);
+int vpl_linefront_collect(VplContext* ctx, int slot, VplLine* lines, int32_t* counts, int cap,
+                          int32_t* prev_to_cur);
+int vpl_linefront_run_resident(VplContext* ctx, int slot);
 
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
@@ -266,7 +318,10 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_ED_ANCHOR 13  /* anchor bitmap                   */
 #define VPL_STAGE_ED_WALK 14    /* smart routing (edge chains)     */
 #define VPL_STAGE_ED_FIT 15     /* line fit + validation + compaction */
-#define VPL_NUM_STAGES 16
+#define VPL_STAGE_LM_PYRAMID 16 /* line matching: KLT pyramids + Scharr */
+#define VPL_STAGE_LM_TRACK 17   /* anchors + pyramidal LK               */
+#define VPL_STAGE_LM_VOTE 18    /* closest line, vote, topological filter */
+#define VPL_NUM_STAGES 19
 /* Accumulated device milliseconds and launch counts per stage since the last
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);

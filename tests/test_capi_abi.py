@@ -18,7 +18,8 @@ def declared_functions():
 def test_header_declares_expected_surface():
     names = declared_functions()
     for n in ("vpl_create", "vpl_destroy", "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_match_batch",
-              "vpl_frontend_batch", "vpl_last_error"):
+              "vpl_frontend_batch", "vpl_last_error", "vpl_edlines_detect_batch", "vpl_linematch_batch",
+              "vpl_linefront_batch"):
         assert n in names
 
 
@@ -33,7 +34,9 @@ def test_struct_layouts(vpl):
     assert vpl.capi.KEYLINE_DTYPE.itemsize == 68   # cv::line_descriptor::KeyLine, 17 x 4 B
     assert vpl.capi.DMATCH_DTYPE.itemsize == 16    # cv::DMatch
     assert vpl.capi.SEGMENT_DTYPE.itemsize == 40
-    assert ctypes.sizeof(vpl.capi.VplConfig) == 36
+    assert ctypes.sizeof(vpl.capi.VplConfig) == 40
+    assert vpl.capi.LINE_DTYPE.itemsize == 56      # struct Line's numeric fields (line.h:8-12)
+    assert ctypes.sizeof(vpl.capi.EDLineParam) == 32 and ctypes.sizeof(vpl.capi.LineMatchParam) == 72
     assert b"sm_100a" in vpl.capi.load().vpl_version()
 
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvplines_b200.so")
 
 VPL_OK, VPL_E_INVALID, VPL_E_CUDA, VPL_E_CAPACITY, VPL_E_NODEVICE = 0, -1, -2, -3, -4
 STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h", "preproc",
-          "ed_grad", "ed_anchor", "ed_walk", "ed_fit"]
+          "ed_grad", "ed_anchor", "ed_walk", "ed_fit", "lm_pyramid", "lm_track", "lm_vote"]
 
 KEYLINE_DTYPE = np.dtype(
     [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
@@ -48,7 +48,25 @@ class EDLineParam(C.Structure):
 class VplConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
                 ("max_octaves", C.c_int32), ("max_lines", C.c_int32), ("max_batch", C.c_int32),
-                ("num_slots", C.c_int32), ("blur_first", C.c_int32), ("profile", C.c_int32)]
+                ("num_slots", C.c_int32), ("blur_first", C.c_int32), ("profile", C.c_int32),
+                ("lsd_path", C.c_int32)]
+
+
+class LineMatchParam(C.Structure):
+    """VplLineMatchParam: LineMatching / KLT / TopologicalFilter defaults of the reference
+    (line_matching/src/line_matching.h:14-18, :45-47; line_matching.cpp:14, :630-631)."""
+    _fields_ = [("step", C.c_int32), ("closest_line_threshold", C.c_float), ("line_matching_ratio", C.c_float),
+                ("line_distance_error_ratio", C.c_float), ("klt_error_threshold", C.c_float),
+                ("max_level", C.c_int32), ("max_count", C.c_int32), ("epsilon", C.c_double), ("min_eig", C.c_float),
+                ("topo_distance_threshold", C.c_float), ("topo_length_ratio", C.c_float),
+                ("topo_violation_ratio", C.c_float), ("illumination_adapt", C.c_int32),
+                ("topological_filter", C.c_int32), ("max_anchors", C.c_int32)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        load().vpl_linematch_default_param(C.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
 
 
 EXPORTS = [
@@ -59,6 +77,8 @@ EXPORTS = [
     "vpl_set_preprocess", "vpl_preprocess_batch",
     "vpl_edlines_default_param", "vpl_edlines_configure", "vpl_edlines_detect_batch", "vpl_edlines_submit",
     "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
+    "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
+    "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -120,6 +140,15 @@ def load():
     L.vpl_edlines_collect.argtypes = [vp, i32, vp, vp, i32, vp]
     L.vpl_edlines_run_resident.argtypes = [vp, i32]
     L.vpl_debug_edge_chains.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
+    L.vpl_linematch_default_param.argtypes = [vp]
+    L.vpl_linematch_default_param.restype = None
+    L.vpl_linematch_configure.argtypes = [vp, vp]
+    L.vpl_linematch_batch.argtypes = [vp, vp, vp, i32, i32, i32, sz, vp, vp, vp, vp, i32, vp]
+    L.vpl_debug_linematch_points.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
+    L.vpl_linefront_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, vp, i32, vp]
+    L.vpl_linefront_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32]
+    L.vpl_linefront_collect.argtypes = [vp, i32, vp, vp, i32, vp]
+    L.vpl_linefront_run_resident.argtypes = [vp, i32]
     _lib = L
     return L
 
@@ -148,13 +177,14 @@ class Context:
     """One GPU, `num_slots` batches in flight.  Mirrors VplContext."""
 
     def __init__(self, device=0, max_width=752, max_height=480, max_octaves=1, max_lines=2048, max_batch=64,
-                 num_slots=2, blur_first=True, profile=False):
+                 num_slots=2, blur_first=True, profile=False, lsd_path=True):
         L = load()
         cfg = VplConfig()
         L.vpl_default_config(C.byref(cfg))
         cfg.device, cfg.max_width, cfg.max_height = device, max_width, max_height
         cfg.max_octaves, cfg.max_lines, cfg.max_batch = max_octaves, max_lines, max_batch
         cfg.num_slots, cfg.blur_first, cfg.profile = num_slots, int(blur_first), int(profile)
+        cfg.lsd_path = int(lsd_path)
         self.cfg = cfg
         self._L = L
         h = C.c_void_p()
@@ -340,6 +370,62 @@ class Context:
         self._ck(self._L.vpl_debug_edge_chains(self._h, frame, _ptr(xy), len(xy), _ptr(sid), len(sid) - 1,
                                                C.byref(npx), C.byref(nch)))
         return xy[:npx.value].copy(), sid[:nch.value + 1].copy()
+
+    # -- LineMatching::Matching (the matcher the reference really runs) -------------------
+    def linematch_configure(self, param=None):
+        self._lmp = param or LineMatchParam()
+        self._ck(self._L.vpl_linematch_configure(self._h, C.byref(self._lmp)))
+
+    def linematch_batch(self, imgs_ref, imgs_cur, lines_ref, lines_cur):
+        """n independent pairs -> list of int32 arrays ref_to_cur (one per pair)."""
+        pr, keep_r, n, w, h, stride = _img_ptrs(imgs_ref)
+        pc, keep_c, n2, w2, h2, _ = _img_ptrs(imgs_cur)
+        assert n == n2 == len(lines_ref) == len(lines_cur) and (w, h) == (w2, h2)
+        cap = max(1, max(max(len(a), len(b)) for a, b in zip(lines_ref, lines_cur)))
+        lr = np.zeros((n, cap), LINE_DTYPE); lc = np.zeros((n, cap), LINE_DTYPE)
+        nr = np.array([len(a) for a in lines_ref], np.int32); nc = np.array([len(a) for a in lines_cur], np.int32)
+        for p in range(n):
+            lr[p, :nr[p]] = np.asarray(lines_ref[p]).view(LINE_DTYPE).reshape(-1)
+            lc[p, :nc[p]] = np.asarray(lines_cur[p]).view(LINE_DTYPE).reshape(-1)
+        out = np.full((n, cap), -1, np.int32)
+        self._ck(self._L.vpl_linematch_batch(self._h, pr, pc, n, w, h, stride, _ptr(lr), _ptr(nr), _ptr(lc), _ptr(nc),
+                                             cap, _ptr(out)))
+        return [out[p, :nr[p]].copy() for p in range(n)]
+
+    def linematch_points(self, pair, cap=1 << 15):
+        """Per-anchor results of `pair` of the last match on slot 0."""
+        kr = np.zeros((cap, 2), np.float32); kc = np.zeros((cap, 2), np.float32)
+        st = np.zeros(cap, np.uint8); er = np.zeros(cap, np.float32); k2l = np.zeros(cap, np.int32)
+        n = C.c_int32(0)
+        self._ck(self._L.vpl_debug_linematch_points(self._h, pair, _ptr(kr), _ptr(kc), _ptr(st), _ptr(er), _ptr(k2l),
+                                                    cap, C.byref(n)))
+        n = n.value
+        return dict(kps_ref=kr[:n].copy(), kps_cur=kc[:n].copy(), status=st[:n].copy(), err=er[:n].copy(),
+                    kp2line=k2l[:n].copy())
+
+    # -- fused: EDline on every frame + Matching(frame f-1, frame f) ----------------------
+    def linefront_batch(self, frames, smoothed=True, cap=None):
+        """-> (lines per frame, prev_to_cur per frame; entry 0 is empty)."""
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        cap = cap or self.max_lines
+        lines = np.zeros((n, cap), LINE_DTYPE)
+        counts = np.zeros(n, np.int32)
+        p2c = np.full((n, cap), -1, np.int32)
+        self._ck(self._L.vpl_linefront_batch(self._h, ptrs, n, w, h, stride, int(bool(smoothed)), _ptr(lines),
+                                             _ptr(counts), cap, _ptr(p2c)))
+        return ([lines[f, :counts[f]].copy() for f in range(n)],
+                [p2c[f, :counts[f - 1]].copy() if f else p2c[0, :0].copy() for f in range(n)])
+
+    def linefront_submit(self, slot, frames, smoothed=True):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        self._ck(self._L.vpl_linefront_submit(self._h, slot, ptrs, n, w, h, stride, int(bool(smoothed))))
+        return n
+
+    def linefront_collect_into(self, slot, lines, counts, cap, prev_to_cur):
+        self._ck(self._L.vpl_linefront_collect(self._h, slot, _ptr(lines), _ptr(counts), cap, _ptr(prev_to_cur)))
+
+    def linefront_run_resident(self, slot):
+        self._ck(self._L.vpl_linefront_run_resident(self._h, slot))
 
     # -- raw stages ----------------------------------------------------------------
     def lsd_raw(self, img, cap=1 << 15):

@@ -69,6 +69,14 @@ struct Slot {
   int* h_ed_status = nullptr;
   int ed_smoothed = 1;
   bool ed_batch = false;  // the batch in flight on this slot is an EDLines batch
+  // line matching (allocated by vpl_linematch_configure)
+  uint8_t* lm_pyr = nullptr;
+  short2* lm_deriv = nullptr;
+  LmBuffers lm = {};
+  int* h_r2c = nullptr;
+  int* d_lm_counts = nullptr;  // line counts of the standalone match call (2 per pair)
+  bool lf_batch = false;       // the batch in flight is a fused EDLines + matching batch
+  int lm_pairs = 0, lm_pstride = 1;
   VplSegment* d_seg = nullptr;
   int* d_seg_count = nullptr;
   // pinned host staging
@@ -108,6 +116,8 @@ struct VplContext {
   double pre_clip = 0.0;
   bool ed_ready = false;  // vpl_edlines_configure has run
   VplEDLineParam edp;
+  bool lm_ready = false;  // vpl_linematch_configure has run
+  VplLineMatchParam lmp;
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -191,8 +201,10 @@ void harvest_times(VplContext* c, Slot& s) {
   }
 }
 
-int check_dims(VplContext* c, int n, int w, int h, int num_octaves, int scale) {
+int check_dims(VplContext* c, int n, int w, int h, int num_octaves, int scale, bool lsd = false) {
   if (!c) return VPL_E_INVALID;
+  if (lsd && !c->cfg.lsd_path)
+    return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0 (EDLines / KLT front end only)");
   if (n < 0 || w <= 0 || h <= 0) return fail(c, VPL_E_INVALID, "bad batch/image size n=%d w=%d h=%d", n, w, h);
   if (n > c->cfg.max_batch) return fail(c, VPL_E_CAPACITY, "batch %d > max_batch %d", n, c->cfg.max_batch);
   if (w > c->cfg.max_width || h > c->cfg.max_height)
@@ -603,6 +615,86 @@ int ed_deliver(VplContext* c, Slot& s, VplLine* lines, int32_t* counts, int cap,
   return VPL_OK;
 }
 
+
+// ---- line matching -----------------------------------------------------------------
+KltGeom klt_geom(int w, int h, int max_level) {
+  KltGeom G;
+  memset(&G, 0, sizeof(G));
+  G.pad = 13;
+  int cw = w, ch = h, level;
+  size_t off = 0;
+  if (max_level > kKltMaxLevels - 1) max_level = kKltMaxLevels - 1;
+  for (level = 0; level <= max_level; ++level) {
+    G.w[level] = cw; G.h[level] = ch; G.stride[level] = cw + 2 * G.pad;
+    G.img_off[level] = off; G.deriv_off[level] = off;
+    off += (size_t)G.stride[level] * (ch + 2 * G.pad);
+    off = (off + 63) & ~(size_t)63;
+    int nw = (cw + 1) / 2, nh = (ch + 1) / 2;
+    // cv::buildOpticalFlowPyramid stops when the next level would not exceed the window
+    if (nw <= G.pad || nh <= G.pad || level == max_level) break;
+    cw = nw; ch = nh;
+  }
+  G.top = level > max_level ? max_level : level;
+  G.img_frame = off; G.deriv_frame = off;
+  return G;
+}
+
+LmParams lm_params(const VplLineMatchParam& p) {
+  LmParams P;
+  memset(&P, 0, sizeof(P));
+  P.step = p.step; P.closest = p.closest_line_threshold; P.ratio = p.line_matching_ratio;
+  P.dist_ratio = p.line_distance_error_ratio; P.klt_err = p.klt_error_threshold;
+  // KLT's constructor clamps and squares the criteria (klt.cpp:22-36)
+  P.max_count = p.max_count < 0 ? 0 : p.max_count > 100 ? 100 : p.max_count;
+  double e = p.epsilon < 0 ? 0 : p.epsilon > 10 ? 10 : p.epsilon;
+  P.eps2 = e * e;
+  P.min_eig = p.min_eig;
+  P.topo_dist = p.topo_distance_threshold; P.topo_len = p.topo_length_ratio; P.topo_viol = p.topo_violation_ratio;
+  P.illum = p.illumination_adapt != 0; P.topo = p.topological_filter != 0;
+  return P;
+}
+
+void lm_free(Slot& s) {
+  cudaFree(s.lm_pyr); cudaFree(s.lm_deriv); cudaFree(s.lm.kps); cudaFree(s.lm.nxt); cudaFree(s.lm.status);
+  cudaFree(s.lm.err); cudaFree(s.lm.kp2line); cudaFree(s.lm.kp_start); cudaFree(s.lm.n_kp); cudaFree(s.lm.r2c);
+  cudaFree(s.lm.matched); cudaFree(s.d_lm_counts);
+  cudaFreeHost(s.h_r2c);
+  s.lm_pyr = nullptr; s.lm_deriv = nullptr; s.lm = LmBuffers{}; s.h_r2c = nullptr; s.d_lm_counts = nullptr;
+}
+
+// pyramids of the n frames in d_img, anchors, LK, votes: pair p = (frame p*pstride, the next one)
+void run_linematch(VplContext* c, Slot& s, const int* d_counts, int n_frames, int n_pairs, int pstride) {
+  const KltGeom G = klt_geom(s.w, s.h, c->lmp.max_level);
+  const LmParams P = lm_params(c->lmp);
+  const int cap = c->cfg.max_lines;
+  s.lm.overflow = s.d_flags + 3;
+  cudaMemsetAsync(s.d_flags + 3, 0, sizeof(int), s.stream);
+  s.lm_pairs = n_pairs; s.lm_pstride = pstride;
+  if (n_pairs <= 0) return;
+  {
+    StageTimer t(c, s, VPL_STAGE_LM_PYRAMID);
+    launch_klt_pyramid(s.d_img, s.lm_pyr, s.lm_deriv, G, s.w, s.h, n_frames, s.stream);
+    t.launches(2 * (G.top + 1));
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_LM_TRACK);
+    launch_lm_anchors(s.d_lines, d_counts, cap, s.lm, P, pstride, n_pairs, s.stream);
+    launch_klt_track(s.lm_pyr, s.lm_deriv, G, s.lm, P, pstride, n_pairs, s.stream);
+    t.launches(2 + G.top);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_LM_VOTE);
+    launch_lm_vote(s.d_lines, d_counts, cap, s.lm, P, pstride, n_pairs, s.stream);
+    t.launches(1);
+  }
+}
+
+int lm_check(VplContext* c) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->lm_ready) return fail(c, VPL_E_INVALID, "call vpl_linematch_configure first");
+  return VPL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -626,6 +718,7 @@ void vpl_default_config(VplConfig* cfg) {
   cfg->num_slots = 2;
   cfg->blur_first = 1;
   cfg->profile = 0;
+  cfg->lsd_path = 1;
 }
 
 const char* vpl_last_error(const VplContext* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -648,6 +741,7 @@ void vpl_destroy(VplContext* c) {
     cudaFree(s.d_last_count); cudaFree(s.d_flags); cudaFree(s.d_seg); cudaFree(s.d_seg_count);
     cudaFree(s.d_offsets); cudaFree(s.d_kl_dense); cudaFree(s.d_desc_dense); cudaFree(s.d_match_dense);
     ed_free(s);
+    lm_free(s);
     cudaFreeHost(s.h_offsets);
     cudaFreeHost(s.h_img); cudaFreeHost(s.h_kl); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_desc);
     cudaFreeHost(s.h_match); cudaFreeHost(s.h_flags);
@@ -739,6 +833,7 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
       OctBuf& b = s.oct[o];
       CKC(dmalloc(&b.pyr, B * Po));
       CKC(dmalloc(&b.grad, B * Po));
+      if (!cfg->lsd_path) continue;  // EDLines / KLT front end only: pyramid image + Sobel pair of octave 0 suffice
       CKC(dmalloc(&b.scl, B * So));
       CKC(dmalloc(&b.ang, B * So));
       CKC(dmalloc(&b.pix, B * So));
@@ -749,13 +844,17 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
       CKC(dmalloc(&b.n_cand, B));
       CKC(dmalloc(&b.maxq, B));
     }
-    CKC(dmalloc(&s.d_kl, B * cap));
     CKC(dmalloc(&s.d_counts, B));
+    CKC(dmalloc(&s.d_flags, 4));
+    CKC(hmalloc(&s.h_img, B * P0));
+    CKC(hmalloc(&s.h_counts, B));
+    CKC(hmalloc(&s.h_flags, 4));
+    if (!cfg->lsd_path) continue;
+    CKC(dmalloc(&s.d_kl, B * cap));
     CKC(dmalloc(&s.d_desc, B * cap * 32));
     CKC(dmalloc(&s.d_match, B * cap * c->max_k));
     CKC(dmalloc(&s.d_last_desc, cap * 32));
     CKC(dmalloc(&s.d_last_count, 1));
-    CKC(dmalloc(&s.d_flags, 4));
     CKC(dmalloc(&s.d_offsets, B + 1));
     CKC(dmalloc(&s.d_kl_dense, B * cap));
     CKC(dmalloc(&s.d_desc_dense, B * cap * 32));
@@ -763,12 +862,9 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     CKC(hmalloc(&s.h_offsets, B + 1));
     CKC(dmalloc(&s.d_seg, (size_t)c->cand_cap));
     CKC(dmalloc(&s.d_seg_count, 1));
-    CKC(hmalloc(&s.h_img, B * P0));
     CKC(hmalloc(&s.h_kl, B * cap));
-    CKC(hmalloc(&s.h_counts, B));
     CKC(hmalloc(&s.h_desc, B * cap * 32));
     CKC(hmalloc(&s.h_match, B * cap * c->max_k));
-    CKC(hmalloc(&s.h_flags, 4));
   }
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -779,7 +875,7 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
 // ---- fused path ---------------------------------------------------------------
 int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
                         int scale, int num_octaves, int k, int chain) {
-  int r = check_dims(c, n, w, h, num_octaves, scale);
+  int r = check_dims(c, n, w, h, num_octaves, scale, true);
   if (r) return r;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   if (k < 0 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 0..%d", k, c->max_k);
@@ -882,6 +978,7 @@ int vpl_frontend_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, 
 
 int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
   if (!c) return VPL_E_INVALID;
+  if (!c->cfg.lsd_path) return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0");
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
   if (s.n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no frames: submit+collect a batch first", slot);
@@ -1007,7 +1104,7 @@ int vpl_sync(VplContext* c) {
 // ---- the three OpenCV-shaped calls ----------------------------------------------
 int vpl_lsd_detect_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int scale,
                          int num_octaves, VplKeyLine* keylines, int32_t* counts, int cap) {
-  int r = check_dims(c, n, w, h, num_octaves, scale);
+  int r = check_dims(c, n, w, h, num_octaves, scale, true);
   if (r) return r;
   if (n == 0) return VPL_OK;
   if (!keylines || !counts) return fail(c, VPL_E_INVALID, "null output");
@@ -1048,7 +1145,7 @@ int vpl_lbd_compute_batch(VplContext* c, const uint8_t* const* imgs, int n, int 
       if (k.numOfPixels < 0 || k.numOfPixels > 32767) return fail(c, VPL_E_INVALID, "numOfPixels out of range");
     }
   }
-  int r = check_dims(c, n, w, h, max_oct + 1, 2);
+  int r = check_dims(c, n, w, h, max_oct + 1, 2, true);
   if (r) return r;
   if (n == 0) return VPL_OK;
   CK(c, cudaSetDevice(c->cfg.device));
@@ -1104,6 +1201,7 @@ int vpl_lbd_compute_float_batch(VplContext* c, const uint8_t* const* imgs, int n
 int vpl_match_batch(VplContext* c, const uint8_t* q, const int32_t* nq, int cap_q, const uint8_t* t,
                     const int32_t* nt, int cap_t, int n_pairs, int k, VplDMatch* out) {
   if (!c) return VPL_E_INVALID;
+  if (!c->cfg.lsd_path) return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0");
   if (!q || !nq || !t || !nt || !out) return fail(c, VPL_E_INVALID, "null argument");
   if (k < 1 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 1..%d", k, c->max_k);
   if (n_pairs < 0 || cap_q < 1 || cap_t < 1) return fail(c, VPL_E_INVALID, "bad sizes");
@@ -1227,7 +1325,7 @@ int vpl_edlines_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || !s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no EDLines batch in flight", slot);
+  if (!s.in_flight || !s.ed_batch || s.lf_batch) return fail(c, VPL_E_INVALID, "slot %d has no EDLines batch in flight", slot);
   if (!lines || !counts) return fail(c, VPL_E_INVALID, "null output");
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
@@ -1284,10 +1382,217 @@ int vpl_debug_edge_chains(VplContext* c, int frame, uint32_t* xy, int cap_px, ui
   return VPL_OK;
 }
 
+
+// ---- LineMatching::Matching: the reference's real matcher ------------------------
+void vpl_linematch_default_param(VplLineMatchParam* p) {
+  if (!p) return;
+  p->step = 10; p->closest_line_threshold = 0.5f; p->line_matching_ratio = 0.4f; p->line_distance_error_ratio = 3.f;
+  p->klt_error_threshold = 40.f;                                  // line_matching.h:14-18
+  p->max_level = 3; p->max_count = 30; p->epsilon = 0.001; p->min_eig = 1e-4f;  // line_matching.cpp:14
+  p->topo_distance_threshold = 15.f; p->topo_length_ratio = 0.2f; p->topo_violation_ratio = 0.05f;  // line_matching.h:45-47
+  p->illumination_adapt = 1; p->topological_filter = 1;          // line_feature_tracker.cpp:307-308
+  p->max_anchors = 4096;
+}
+
+int vpl_linematch_configure(VplContext* c, const VplLineMatchParam* p) {
+  if (!c || !p) return VPL_E_INVALID;
+  if (p->step < 1 || p->max_level < 0 || p->max_level > kKltMaxLevels - 1 || p->max_anchors < 1 || p->max_count < 0)
+    return fail(c, VPL_E_INVALID, "bad VplLineMatchParam");
+  if (c->cfg.max_lines > 4096) return fail(c, VPL_E_INVALID, "line matching supports max_lines <= 4096");
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots)
+    if (s.in_flight) return fail(c, VPL_E_INVALID, "vpl_linematch_configure while a batch is in flight");
+  CK(c, cudaDeviceSynchronize());
+  c->lm_ready = false;
+  c->lmp = *p;
+  // pyramid size by area with slack: any w x h inside the context's limits must fit
+  const KltGeom G = klt_geom(c->cfg.max_width, c->cfg.max_height, p->max_level);
+  const size_t frame = G.img_frame + 4096;
+  const size_t B = (size_t)c->cfg.max_batch, cap = (size_t)c->cfg.max_lines, ck = (size_t)p->max_anchors;
+  for (Slot& s : c->slots) {
+    lm_free(s);
+    CK(c, dmalloc(&s.lm_pyr, B * frame));
+    CK(c, dmalloc(&s.lm_deriv, B * frame));
+    s.lm.cap_kp = p->max_anchors;
+    CK(c, dmalloc(&s.lm.kps, B * ck));
+    CK(c, dmalloc(&s.lm.nxt, B * ck));
+    CK(c, dmalloc(&s.lm.status, B * ck));
+    CK(c, dmalloc(&s.lm.err, B * ck));
+    CK(c, dmalloc(&s.lm.kp2line, B * ck));
+    CK(c, dmalloc(&s.lm.kp_start, B * (cap + 1)));
+    CK(c, dmalloc(&s.lm.n_kp, B));
+    CK(c, dmalloc(&s.lm.r2c, B * cap));
+    CK(c, dmalloc(&s.lm.matched, B));
+    CK(c, dmalloc(&s.d_lm_counts, B));
+    CK(c, hmalloc(&s.h_r2c, B * cap));
+    if (!s.d_lines) {  // line storage is shared with the EDLines detector
+      CK(c, dmalloc(&s.d_lines, B * cap));
+      CK(c, hmalloc(&s.h_lines, B * cap));
+      CK(c, hmalloc(&s.h_ed_status, B));
+    }
+  }
+  c->lm_ready = true;
+  return VPL_OK;
+}
+
+int vpl_linematch_batch(VplContext* c, const uint8_t* const* imgs_ref, const uint8_t* const* imgs_cur, int n_pairs,
+                        int w, int h, size_t stride, const VplLine* lines_ref, const int32_t* n_ref,
+                        const VplLine* lines_cur, const int32_t* n_cur, int cap, int32_t* ref_to_cur) {
+  int r = lm_check(c);
+  if (r) return r;
+  r = check_dims(c, 2 * n_pairs, w, h, 1, 1);
+  if (r) return r;
+  if (n_pairs == 0) return VPL_OK;
+  if (!imgs_ref || !imgs_cur || !lines_ref || !lines_cur || !n_ref || !n_cur || !ref_to_cur)
+    return fail(c, VPL_E_INVALID, "null argument");
+  const int mcap = c->cfg.max_lines;
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[0];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  for (int p = 0; p < n_pairs; ++p)
+    if (n_ref[p] < 0 || n_cur[p] < 0 || n_ref[p] > cap || n_cur[p] > cap || n_ref[p] > mcap || n_cur[p] > mcap)
+      return fail(c, VPL_E_CAPACITY, "pair %d: %d / %d lines exceed cap %d or max_lines %d", p, n_ref[p], n_cur[p], cap, mcap);
+  // frames interleaved (ref, cur) per pair; lines staged the same way
+  std::vector<const uint8_t*> ptrs((size_t)2 * n_pairs);
+  for (int p = 0; p < n_pairs; ++p) { ptrs[2 * p] = imgs_ref[p]; ptrs[2 * p + 1] = imgs_cur[p]; }
+  s.n = 2 * n_pairs; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 1; s.k = 0;
+  r = upload(c, s, ptrs.data(), 2 * n_pairs, w, h, stride);
+  if (r) return r;
+  for (int p = 0; p < n_pairs; ++p) {
+    memcpy(s.h_lines + (size_t)(2 * p) * mcap, lines_ref + (size_t)p * cap, (size_t)n_ref[p] * sizeof(VplLine));
+    memcpy(s.h_lines + (size_t)(2 * p + 1) * mcap, lines_cur + (size_t)p * cap, (size_t)n_cur[p] * sizeof(VplLine));
+    s.h_counts[2 * p] = n_ref[p]; s.h_counts[2 * p + 1] = n_cur[p];
+  }
+  CK(c, cudaMemcpyAsync(s.d_lines, s.h_lines, (size_t)2 * n_pairs * mcap * sizeof(VplLine), cudaMemcpyHostToDevice, s.stream));
+  CK(c, cudaMemcpyAsync(s.d_lm_counts, s.h_counts, (size_t)2 * n_pairs * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  run_linematch(c, s, s.d_lm_counts, 2 * n_pairs, n_pairs, 2);
+  CK(c, cudaMemcpyAsync(s.h_r2c, s.lm.r2c, (size_t)n_pairs * mcap * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  r = finish(c, s);
+  if (r) return r;
+  if (s.h_flags[3]) return fail(c, VPL_E_CAPACITY, "a pair needs more than max_anchors=%d anchor points", c->lmp.max_anchors);
+  for (int p = 0; p < n_pairs; ++p) {
+    for (int i = 0; i < n_ref[p]; ++i) ref_to_cur[(size_t)p * cap + i] = s.h_r2c[(size_t)p * mcap + i];
+  }
+  return VPL_OK;
+}
+
+int vpl_debug_linematch_points(VplContext* c, int pair, float* kps_ref, float* kps_cur, uint8_t* status, float* err,
+                               int32_t* kp2line_cur, int cap, int32_t* n) {
+  int r = lm_check(c);
+  if (r) return r;
+  if (!n) return VPL_E_INVALID;
+  Slot& s = c->slots[0];
+  if (pair < 0 || pair >= s.lm_pairs) return fail(c, VPL_E_INVALID, "pair %d outside the last match", pair);
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaStreamSynchronize(s.stream));
+  int nk = 0;
+  CK(c, cudaMemcpy(&nk, s.lm.n_kp + pair, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = nk;
+  if (nk > cap) return fail(c, VPL_E_CAPACITY, "%d anchors > cap %d", nk, cap);
+  const size_t o = (size_t)pair * s.lm.cap_kp;
+  if (kps_ref) CK(c, cudaMemcpy(kps_ref, s.lm.kps + o, (size_t)nk * 8, cudaMemcpyDeviceToHost));
+  if (kps_cur) CK(c, cudaMemcpy(kps_cur, s.lm.nxt + o, (size_t)nk * 8, cudaMemcpyDeviceToHost));
+  if (status) CK(c, cudaMemcpy(status, s.lm.status + o, (size_t)nk, cudaMemcpyDeviceToHost));
+  if (err) CK(c, cudaMemcpy(err, s.lm.err + o, (size_t)nk * 4, cudaMemcpyDeviceToHost));
+  if (kp2line_cur) CK(c, cudaMemcpy(kp2line_cur, s.lm.kp2line + o, (size_t)nk * 4, cudaMemcpyDeviceToHost));
+  return VPL_OK;
+}
+
+// ---- fused: EDline on every frame + Matching(frame f-1, frame f) ---------------------------------
+int vpl_linefront_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                         int smoothed) {
+  int r = lm_check(c);
+  if (r) return r;
+  r = ed_check(c, n, w, h, smoothed);
+  if (r) return r;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (n == 0) return fail(c, VPL_E_INVALID, "empty batch");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  s.n = n; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 1; s.k = 0; s.ed_smoothed = smoothed ? 1 : 0;
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  run_edlines(c, s);
+  run_linematch(c, s, s.d_counts, n, n - 1, 1);
+  ed_enqueue_download(c, s);
+  if (n > 1) {
+    StageTimer t(c, s, VPL_STAGE_D2H);
+    CK(c, cudaMemcpyAsync(s.h_r2c, s.lm.r2c, (size_t)(n - 1) * c->cfg.max_lines * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    s.last_d2h_bytes += (int64_t)(n - 1) * c->cfg.max_lines * sizeof(int);
+  }
+  CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(c, cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  s.ed_batch = true;
+  s.lf_batch = true;
+  return VPL_OK;
+}
+
+int vpl_linefront_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight || !s.lf_batch) return fail(c, VPL_E_INVALID, "slot %d has no line front-end batch in flight", slot);
+  if (!lines || !counts || !prev_to_cur) return fail(c, VPL_E_INVALID, "null output");
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = finish(c, s);
+  s.ed_batch = false; s.lf_batch = false;
+  if (r) return r;
+  r = ed_deliver(c, s, lines, counts, cap, nullptr);
+  if (r) return r;
+  if (s.h_flags[3]) return fail(c, VPL_E_CAPACITY, "a frame pair needs more than max_anchors=%d anchor points", c->lmp.max_anchors);
+  const int mcap = c->cfg.max_lines;
+  for (int i = 0; i < cap; ++i) prev_to_cur[i] = -1;
+  for (int f = 1; f < s.n; ++f) {
+    int32_t* row = prev_to_cur + (size_t)f * cap;
+    const int np = s.h_counts[f - 1];
+    memcpy(row, s.h_r2c + (size_t)(f - 1) * mcap, (size_t)np * sizeof(int));
+    for (int i = np; i < cap; ++i) row[i] = -1;
+  }
+  return VPL_OK;
+}
+
+int vpl_linefront_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int smoothed,
+                        VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur) {
+  int r = lm_check(c);
+  if (r) return r;
+  r = ed_check(c, n, w, h, smoothed);
+  if (r) return r;
+  if (n == 0) return VPL_OK;
+  r = vpl_linefront_submit(c, 0, imgs, n, w, h, stride, smoothed);
+  if (r) return r;
+  return vpl_linefront_collect(c, 0, lines, counts, cap, prev_to_cur);
+}
+
+int vpl_linefront_run_resident(VplContext* c, int slot) {
+  int r = lm_check(c);
+  if (r) return r;
+  if (!c->ed_ready) return fail(c, VPL_E_INVALID, "call vpl_edlines_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no frames", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  run_edlines(c, s);
+  run_linematch(c, s, s.d_counts, s.n, s.n - 1, 1);
+  return VPL_OK;
+}
+
 // ---- raw stages for the parity tests -------------------------------------------
 int vpl_lsd_raw(VplContext* c, const uint8_t* img, int w, int h, size_t stride, VplSegment* out, int32_t* count,
                 int cap) {
-  int r = check_dims(c, 1, w, h, 1, 1);
+  int r = check_dims(c, 1, w, h, 1, 1, true);
   if (r) return r;
   if (!img || !out || !count) return fail(c, VPL_E_INVALID, "null argument");
   CK(c, cudaSetDevice(c->cfg.device));
@@ -1315,7 +1620,7 @@ int vpl_lsd_raw(VplContext* c, const uint8_t* img, int w, int h, size_t stride, 
 
 int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, size_t stride, void* out,
                     size_t out_bytes, int32_t* out_w, int32_t* out_h) {
-  int r = check_dims(c, 1, w, h, which == 1 ? 2 : 1, 2);
+  int r = check_dims(c, 1, w, h, which == 1 ? 2 : 1, 2, true);
   if (r) return r;
   if (!img || !out || !out_w || !out_h) return fail(c, VPL_E_INVALID, "null argument");
   if (which == 1 && c->cfg.max_octaves < 2) return fail(c, VPL_E_CAPACITY, "pyrDown stage needs max_octaves >= 2");

@@ -1,0 +1,498 @@
+// linematch.cu -- the reference's real line matcher on the device (sm_100a).
+//
+// Replaces LineMatching::Matching (/root/reference/line_matching/src/line_matching.cpp:605-690,
+// cited as lm.cpp), KLT::calc2D (klt.cpp:491-628) and LKTrackerInvoker2D::operator()
+// (lk_tracker_invoker_2d.cpp:28-480, cited as lk2d.cpp), which the tracker reaches through
+// match_line_match (feature_tracker/src/line_feature_tracker.cpp:115, :291-313) with
+// illumination_adapt = true, topological_filter = true and no affine models.
+// CPU restatement: oracle/orc_linematch.c (pinned bit for bit against the reference's own code).
+//
+// A "pair" p matches the lines of frame ref(p) = p*pstride to the lines of frame cur(p) = ref(p)+1
+// (pstride 1: consecutive frames of a sequence; 2: independent pairs).  Stages, each one launch
+// over the whole batch:
+//   klt_level0 / klt_pyrdown / klt_scharr   cv::buildOpticalFlowPyramid (13-px REFLECT_101 border
+//                     stored physically, so that windows never test bounds) and the Scharr
+//                     derivative with its zero border (klt.cpp:42-122, :613)              HBM-bound
+//   lm_anchor_kernel  anchors every `step` px along each reference line (lm.cpp:531-599)
+//   klt_track_kernel  per pyramid level, ONE THREAD PER ANCHOR: the reference's float sums over
+//                     the 13x13 window are sequential (y, x) single-precision accumulations, so
+//                     the window loop stays in one thread and the 32 lanes of a warp carry 32
+//                     anchors; windows live in thread-local memory; each source byte of a window
+//                     is loaded once (row-blended bilinear interpolation in exact integers)
+//   lm_vote_kernel    one CTA per pair: closest current line per tracked anchor (lm.cpp:48-86),
+//                     vote per reference line (:88-133), topological filter (:267-410, :656-665)
+// Bit-exact vs the oracle: integer window arithmetic, float/double sequences in the reference's
+// order with -fmad=false, IEEE sqrt/div.
+#include <float.h>
+#include <limits.h>
+
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+namespace {
+
+constexpr int WIN = 13;           // LineMatching::Matching sets 13x13 (lm.cpp:631)
+constexpr int NWIN = WIN * WIN;
+constexpr int W_BITS = 14;
+#define LM_DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))  // CV_DESCALE, klt.h:39
+
+__device__ __forceinline__ int cv_floor_d(float v) {  // SSE cvFloor: INT_MIN on NaN / overflow
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
+  return (int)floorf(v);
+}
+
+// ---- pyramid ---------------------------------------------------------------------------------
+__global__ void klt_level0_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr, KltGeom G, int w, int h) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int st = G.stride[0];
+  if (x >= st) return;
+  int sx = refl101(x - G.pad, w), sy = refl101(y - G.pad, h);
+  pyr[(size_t)f * G.img_frame + G.img_off[0] + (size_t)y * st + x] = img[(size_t)f * w * h + (size_t)sy * w + sx];
+}
+
+// level l (padded) from level l-1 (padded): cv::pyrDown to ((w+1)/2, (h+1)/2), then the border
+__global__ void klt_pyrdown_kernel(uint8_t* __restrict__ pyr, KltGeom G, int l) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int st = G.stride[l];
+  if (x >= st) return;
+  const int dx = refl101(x - G.pad, G.w[l]), dy = refl101(y - G.pad, G.h[l]);
+  const int sst = G.stride[l - 1];
+  const uint8_t* src = pyr + (size_t)f * G.img_frame + G.img_off[l - 1];
+  // source rows/cols 2d-2 .. 2d+2 lie inside the stored REFLECT_101 border of level l-1, except
+  // beyond its far edge when the size is odd (2d+2 can reach w+1 <= w+pad-1): still inside
+  int s = 0;
+#pragma unroll
+  for (int j = -2; j <= 2; j++) {
+    const uint8_t* row = src + (size_t)(2 * dy + j + G.pad) * sst + (2 * dx + G.pad);
+    const int kj = j == 0 ? 6 : (j == -1 || j == 1) ? 4 : 1;
+    s += kj * (row[-2] + 4 * row[-1] + 6 * row[0] + 4 * row[1] + row[2]);
+  }
+  pyr[(size_t)f * G.img_frame + G.img_off[l] + (size_t)y * st + x] = (uint8_t)((s + 128) >> 8);
+}
+
+// KLT::calcSharrDeriv + copyMakeBorder(BORDER_CONSTANT): zero outside the level
+__global__ void klt_scharr_kernel(const uint8_t* __restrict__ pyr, short2* __restrict__ deriv, KltGeom G, int l) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int st = G.stride[l];
+  if (x >= st) return;
+  short2 o = make_short2(0, 0);
+  const int ix = x - G.pad, iy = y - G.pad;
+  if (ix >= 0 && ix < G.w[l] && iy >= 0 && iy < G.h[l]) {
+    const uint8_t* p = pyr + (size_t)f * G.img_frame + G.img_off[l] + (size_t)y * st + x;
+    int a = p[-st - 1], b = p[-st], c = p[-st + 1], d = p[-1], e = p[1], g = p[st - 1], hh = p[st], i = p[st + 1];
+    // dIx = [3 10 3]^T (rows) x [-1 0 1];  dIy = [-1 0 1]^T x [3 10 3]
+    o.x = (short)(((c + i) * 3 + e * 10) - ((a + g) * 3 + d * 10));
+    o.y = (short)(((g - a) + (i - c)) * 3 + (hh - b) * 10);
+  }
+  deriv[(size_t)f * G.deriv_frame + G.deriv_off[l] + (size_t)y * st + x] = o;
+}
+
+// ---- anchors, lm.cpp:531-599 --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lm_anchor_kernel(const VplLine* __restrict__ lines, const int* __restrict__ counts,
+                                                        int cap, LmBuffers B, LmParams P, int pstride) {
+  const int p = blockIdx.x;
+  const int fr = p * pstride;
+  const int n = min(counts[fr], cap);
+  const VplLine* L = lines + (size_t)fr * cap;
+  int* kp_start = B.kp_start + (size_t)p * (cap + 1);
+  // exclusive scan of the per-line anchor counts (iter_num + 2), chunks of 1024 lines
+  int base = 0;
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    int i = c0 + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (i + k < n) ? (int)(L[i + k].length / P.step) + 2 : 0;
+    int t = v[0] + v[1] + v[2] + v[3];
+    // block scan over 256 partial sums
+    __shared__ int s_part[256];
+    s_part[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      int a = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += a;
+      __syncthreads();
+    }
+    int ex = base + s_part[threadIdx.x] - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i + k < n) kp_start[i + k] = ex;
+      ex += v[k];
+    }
+    base += s_part[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    kp_start[n] = base;
+    B.n_kp[p] = base <= B.cap_kp ? base : 0;
+    if (base > B.cap_kp) atomicExch(B.overflow, 1);
+  }
+  __syncthreads();
+  if (base > B.cap_kp) return;
+  float2* kps = B.kps + (size_t)p * B.cap_kp;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const VplLine l = L[i];
+    float x1 = l.endpoint[0], y1 = l.endpoint[1], x2 = l.endpoint[2], y2 = l.endpoint[3];
+    float px = x1, py = y1, len = l.length;
+    float dirx = (x2 - x1) / len, diry = (y2 - y1) / len;
+    float ddx = P.step * dirx, ddy = P.step * diry;
+    int iter = (int)(len / P.step);
+    int o = kp_start[i];
+    for (int j = 0; j <= iter; j++) {
+      kps[o++] = make_float2(px, py);
+      px += ddx; py += ddy;
+    }
+    kps[o] = make_float2(x2, y2);
+  }
+}
+
+// ---- per-point tracker ---------------------------------------------------------------------------
+struct Wts {
+  int w00, w01, w10, w11;
+};
+__device__ __forceinline__ Wts lk_weights(float a, float b) {  // lk2d.cpp:109-112
+  Wts w;
+  w.w00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+  w.w01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+  w.w10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+  w.w11 = (1 << W_BITS) - w.w00 - w.w01 - w.w10;
+  return w;
+}
+
+// bilinear 13x13 window of a padded u8 level at integer corner (ix, iy): every source byte is read
+// once; the sums are exact integers, so blending rows first changes nothing (lk2d.cpp:338-348).
+// Also returns the window's integer sum and sum of squares (for cv::meanStdDev).
+__device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, int st, int ix, int iy, const Wts& w,
+                                             short* __restrict__ out, int& sum, long long& sq) {
+  int top[WIN];
+  sum = 0;
+  sq = 0;
+  const uint8_t* row = img + (ptrdiff_t)iy * st + ix;
+#pragma unroll 1
+  for (int r = 0; r <= WIN; r++, row += st) {
+    int prev = row[0];
+#pragma unroll
+    for (int x = 0; x < WIN; x++) {
+      int cur = row[x + 1];
+      int t = prev * w.w00 + cur * w.w01;   // this row as the upper row of window row r
+      int b = prev * w.w10 + cur * w.w11;   // ... and as the lower row of window row r-1
+      if (r > 0) {
+        int v = LM_DESCALE(top[x] + b, W_BITS - 5);
+        out[(r - 1) * WIN + x] = (short)v;
+        sum += v;
+        sq += v * v;
+      }
+      top[x] = t;
+      prev = cur;
+    }
+  }
+}
+
+__device__ __forceinline__ void lk_norm_params(int si, long long qi, int sj, long long qj, float& alpha, float& beta) {
+  // getImageNormParams (klt.cpp:4-10) over cv::meanStdDev of two CV_16S windows
+  const double scale = 1.0 / NWIN;
+  double mi = si * scale, mj = sj * scale;
+  double vi = (double)qi * scale - mi * mi, vj = (double)qj * scale - mj * mj;
+  double sdi = sqrt(vi > 0 ? vi : 0), sdj = sqrt(vj > 0 ? vj : 0);
+  alpha = (float)(sdi / sdj);
+  beta = (float)(mi - alpha * mj);
+}
+
+__global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ deriv,
+                                                        KltGeom G, LmBuffers B, LmParams P, int level, int pstride,
+                                                        int n_pairs) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs || i >= B.n_kp[p]) return;
+  const size_t k = (size_t)p * B.cap_kp + i;
+  const int fr = p * pstride, fc = fr + 1;
+  const int st = G.stride[level], lw = G.w[level], lh = G.h[level];
+  // pointers to pixel (0,0) of the level inside its padded buffer
+  const uint8_t* I = pyr + (size_t)fr * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
+  const uint8_t* J = pyr + (size_t)fc * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
+  const short2* dI = deriv + (size_t)fr * G.deriv_frame + G.deriv_off[level] + (size_t)G.pad * st + G.pad;
+
+  const float half = (WIN - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const float scale = (float)(1. / (1 << level));
+  const float2 prev = B.kps[k];
+  float px = prev.x * scale, py = prev.y * scale, nx, ny;
+  if (level == G.top) {  // flags == 0, lk2d.cpp:51-56
+    nx = px; ny = py;
+    B.status[k] = 1;
+    B.err[k] = 0.f;
+  } else {
+    float2 q = B.nxt[k];
+    nx = q.x * 2.f; ny = q.y * 2.f;
+  }
+  B.nxt[k] = make_float2(nx, ny);  // lk2d.cpp:61
+  px -= half; py -= half;
+  const int ipx = cv_floor_d(px), ipy = cv_floor_d(py);
+  if (ipx < -WIN || ipx >= lw || ipy < -WIN || ipy >= lh) {  // lk2d.cpp:91-99
+    if (level == 0) { B.status[k] = 0; B.err[k] = 0.f; }
+    return;
+  }
+  short Iw[NWIN], Jw[NWIN];
+  short2 dIw[NWIN];
+  int sI;
+  long long qI;
+  Wts w = lk_weights(px - ipx, py - ipy);
+  lk_sample_u8(I, st, ipx, ipy, w, Iw, sI, qI);
+  float iA11 = 0, iA12 = 0, iA22 = 0;
+  {  // derivative window + structure tensor, lk2d.cpp:117-149 (sums in (y, x) order)
+    int tx[WIN], ty[WIN];
+    const short2* row = dI + (ptrdiff_t)ipy * st + ipx;
+#pragma unroll 1
+    for (int r = 0; r <= WIN; r++, row += st) {
+      short2 pv = row[0];
+#pragma unroll
+      for (int x = 0; x < WIN; x++) {
+        short2 cv = row[x + 1];
+        int t0 = pv.x * w.w00 + cv.x * w.w01, b0 = pv.x * w.w10 + cv.x * w.w11;
+        int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
+        if (r > 0) {
+          int ixv = LM_DESCALE(tx[x] + b0, W_BITS), iyv = LM_DESCALE(ty[x] + b1, W_BITS);
+          dIw[(r - 1) * WIN + x] = make_short2((short)ixv, (short)iyv);
+          iA11 += (float)(ixv * ixv);
+          iA12 += (float)(ixv * iyv);
+          iA22 += (float)(iyv * iyv);
+        }
+        tx[x] = t0; ty[x] = t1;
+        pv = cv;
+      }
+    }
+  }
+  const float A11 = iA11 * FLT_SCALE, A12 = iA12 * FLT_SCALE, A22 = iA22 * FLT_SCALE;
+  float D = A11 * A22 - A12 * A12;
+  const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * WIN * WIN);
+  if (min_eig < P.min_eig || D < FLT_EPSILON) {  // lk2d.cpp:294-298
+    if (level == 0) B.status[k] = 0;
+    return;
+  }
+  D = 1.f / D;
+  float outx = nx, outy = ny;  // value of nextPts[ptidx] (untouched if the loop leaves at once)
+  nx -= half; ny -= half;
+  float pdx = 0.f, pdy = 0.f;
+  bool ok = B.status[k] != 0;
+  int j;
+  for (j = 0; j < P.max_count; j++) {  // lk2d.cpp:321-418
+    const int inx = cv_floor_d(nx), iny = cv_floor_d(ny);
+    if (inx < -half || inx >= lw || iny < -half || iny >= lh) {
+      if (level == 0) ok = false;
+      break;
+    }
+    w = lk_weights(nx - inx, ny - iny);
+    int sJ;
+    long long qJ;
+    lk_sample_u8(J, st, inx, iny, w, Jw, sJ, qJ);
+    float alpha = 1.0f, beta = 0.0f;
+    if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
+    float ib1 = 0, ib2 = 0;
+#pragma unroll 1
+    for (int t = 0; t < NWIN; t++) {  // lk2d.cpp:364-376
+      float diff = alpha * Jw[t] + beta - Iw[t];
+      short2 d = dIw[t];
+      ib1 += diff * d.x;
+      ib2 += diff * d.y;
+    }
+    const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
+    const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+    nx += dx; ny += dy;
+    outx = nx + half; outy = ny + half;
+    if ((double)dx * dx + (double)dy * dy <= P.eps2) break;  // lk2d.cpp:405
+    if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) {  // lk2d.cpp:410-414
+      outx -= dx * 0.5f; outy -= dy * 0.5f;
+      break;
+    }
+    pdx = dx; pdy = dy;
+  }
+  B.nxt[k] = make_float2(outx, outy);
+  if (level != 0) return;
+  if (j == P.max_count) ok = false;  // lk2d.cpp:422
+  if (ok) {  // final error, lk2d.cpp:429-478
+    const float ex = outx - half, ey = outy - half;
+    const int iex = cv_floor_d(ex), iey = cv_floor_d(ey);
+    if (iex < -WIN || iex >= lw || iey < -WIN || iey >= lh) {
+      ok = false;
+    } else {
+      w = lk_weights(ex - iex, ey - iey);
+      int sJ;
+      long long qJ;
+      lk_sample_u8(J, st, iex, iey, w, Jw, sJ, qJ);
+      float alpha = 1.0f, beta = 0.0f;
+      if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
+      float errval = 0.f;
+#pragma unroll 1
+      for (int t = 0; t < NWIN; t++) errval += fabsf(alpha * Jw[t] + beta - Iw[t]);
+      B.err[k] = errval * 1.f / (32 * WIN * WIN);
+    }
+  }
+  B.status[k] = ok ? 1 : 0;
+}
+
+// ---- closest line, vote, topological filter -------------------------------------------------------
+__device__ __forceinline__ float point_line_distance(float x, float y, const float4 e) {  // lm.cpp:21-41
+  float v_x = e.z - e.x, v_y = e.w - e.y;
+  float u_x = e.x - x, u_y = e.y - y;
+  float t = -(v_x * u_x + v_y * u_y) / (v_x * v_x + v_y * v_y);
+  if (t < 0) t = 0;
+  else if (t > 1) t = 1;
+  float d_x = t * v_x + u_x, d_y = t * v_y + u_y;
+  return sqrtf(d_x * d_x + d_y * d_y);
+}
+
+__global__ void __launch_bounds__(256) lm_vote_kernel(const VplLine* __restrict__ lines, const int* __restrict__ counts,
+                                                      int cap, LmBuffers B, LmParams P, int pstride) {
+  extern __shared__ unsigned char smem[];
+  float4* s_end = reinterpret_cast<float4*>(smem);          // cap: endpoints of the current lines
+  int* s_r2c = reinterpret_cast<int*>(s_end + cap);          // cap
+  int* s_viol = s_r2c + cap;                                 // cap
+  __shared__ int s_match_num;
+  const int p = blockIdx.x;
+  const int fr = p * pstride, fc = fr + 1;
+  const int n_ref = min(counts[fr], cap), n_cur = min(counts[fc], cap);
+  const VplLine* Lr = lines + (size_t)fr * cap;
+  const VplLine* Lc = lines + (size_t)fc * cap;
+  int* r2c_out = B.r2c + (size_t)p * cap;
+  if (n_ref == 0 || n_cur == 0) {  // Matching returns false, lm.cpp:621: nothing is matched
+    for (int i = threadIdx.x; i < n_ref; i += blockDim.x) r2c_out[i] = -1;
+    if (threadIdx.x == 0) B.matched[p] = 0;
+    return;
+  }
+  for (int i = threadIdx.x; i < n_cur; i += blockDim.x)
+    s_end[i] = make_float4(Lc[i].endpoint[0], Lc[i].endpoint[1], Lc[i].endpoint[2], Lc[i].endpoint[3]);
+  if (threadIdx.x == 0) s_match_num = 0;
+  __syncthreads();
+  const int n_kp = B.n_kp[p];
+  const size_t kb = (size_t)p * B.cap_kp;
+  int* kp2line = B.kp2line + kb;
+  // ClosestLine, lm.cpp:48-86
+  for (int i = threadIdx.x; i < n_kp; i += blockDim.x) {
+    int label = -1;
+    if (B.status[kb + i] && !(B.err[kb + i] > P.klt_err)) {
+      const float2 pt = B.nxt[kb + i];
+      int min_idx = -1;
+      float min_d = 1000000;
+      for (int j = 0; j < n_cur; j++) {
+        float d = point_line_distance(pt.x, pt.y, s_end[j]);
+        if (d < min_d) { min_d = d; min_idx = j; }
+      }
+      if (min_d < P.closest) label = min_idx;
+    }
+    kp2line[i] = label;
+  }
+  __syncthreads();
+  // Point2Line, lm.cpp:88-133: the most voted current line of each reference line (lowest index
+  // among equals, as the reference's `count[j] > max_value` scan)
+  const int* kp_start = B.kp_start + (size_t)p * (cap + 1);
+  for (int i = threadIdx.x; i < n_ref; i += blockDim.x) {
+    const int a = kp_start[i], kn = kp_start[i + 1] - a;
+    int max_value = 0, max_idx = 0;
+    for (int u = 0; u < kn; u++) {
+      const int lu = kp2line[a + u];
+      if (lu < 0) continue;
+      int c = 0;
+      for (int v = 0; v < kn; v++) c += kp2line[a + v] == lu;
+      if (c > max_value || (c == max_value && lu < max_idx)) { max_value = c; max_idx = lu; }
+    }
+    int m = -1;
+    if (!(max_value <= 2 || (float)max_value / kn < P.ratio || Lc[max_idx].length > Lr[i].length * P.dist_ratio ||
+          Lc[max_idx].length < Lr[i].length / P.dist_ratio))
+      m = max_idx;
+    s_r2c[i] = m;
+    s_viol[i] = 0;
+    if (m >= 0) atomicAdd(&s_match_num, 1);
+  }
+  __syncthreads();
+  if (P.topo) {  // TopologicalFilter, lm.cpp:267-410
+    for (int r1 = threadIdx.x; r1 < n_ref; r1 += blockDim.x) {
+      const int c1 = s_r2c[r1];
+      if (c1 < 0) continue;
+      const double a_1 = Lr[r1].equation[0], b_1 = Lr[r1].equation[1], c_1 = Lr[r1].equation[2];
+      double a_2 = Lc[c1].equation[0], b_2 = Lc[c1].equation[1], c_2 = Lc[c1].equation[2];
+      if ((fabs(a_1 - a_2) + fabs(b_1 - b_2)) > (fabs(a_1 + a_2) + fabs(b_1 + b_2))) { a_2 = -a_2; b_2 = -b_2; c_2 = -c_2; }
+      const double n1 = sqrt(a_1 * a_1 + b_1 * b_1), n2 = sqrt(a_2 * a_2 + b_2 * b_2);
+      for (int r2 = 0; r2 < n_ref; r2++) {
+        if (r2 == r1) continue;
+        const int c2 = s_r2c[r2];
+        if (c2 < 0) continue;
+        const float lr2 = Lr[r2].length;
+        if (fabsf(lr2 - Lc[c2].length) / lr2 > P.topo_len) continue;
+        // SidenessCheck, lm.cpp:412-446
+        const double px_1 = Lr[r2].center[0], py_1 = Lr[r2].center[1];
+        const double px_2 = Lc[c2].center[0], py_2 = Lc[c2].center[1];
+        const float d1 = (float)((px_1 * a_1 + py_1 * b_1 + c_1) / n1);
+        const float d2 = (float)((px_2 * a_2 + py_2 * b_2 + c_2) / n2);
+        if (d1 * d2 < 0 && fabsf(d1) > P.topo_dist && fabsf(d2) > P.topo_dist) {
+          atomicAdd(&s_viol[r1], 1);
+          atomicAdd(&s_viol[r2], 1);
+        }
+      }
+    }
+    __syncthreads();
+    float threshold = P.topo_viol * (s_match_num - 1);
+    if (threshold < 2) threshold = 2;
+    for (int i = threadIdx.x; i < n_ref; i += blockDim.x)
+      if (s_viol[i] > threshold) s_r2c[i] = -1;  // lm.cpp:656-665
+    __syncthreads();
+  }
+  int matched = 0;
+  for (int i = threadIdx.x; i < n_ref; i += blockDim.x) {
+    r2c_out[i] = s_r2c[i];
+    matched += s_r2c[i] >= 0;
+  }
+  // block count of the matches (for the caller's statistics)
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if (matched) atomicAdd(&s_cnt, matched);
+  __syncthreads();
+  if (threadIdx.x == 0) B.matched[p] = s_cnt;
+}
+
+}  // namespace
+
+void launch_klt_pyramid(const uint8_t* img, uint8_t* pyr, short2* deriv, const KltGeom& G, int w, int h, int batch,
+                        cudaStream_t st) {
+  {
+    dim3 grid((G.stride[0] + 255) / 256, h + 2 * G.pad, batch);
+    klt_level0_kernel<<<grid, 256, 0, st>>>(img, pyr, G, w, h);
+  }
+  for (int l = 1; l <= G.top; l++) {
+    dim3 grid((G.stride[l] + 127) / 128, G.h[l] + 2 * G.pad, batch);
+    klt_pyrdown_kernel<<<grid, 128, 0, st>>>(pyr, G, l);
+  }
+  for (int l = 0; l <= G.top; l++) {
+    dim3 grid((G.stride[l] + 255) / 256, G.h[l] + 2 * G.pad, batch);
+    klt_scharr_kernel<<<grid, 256, 0, st>>>(pyr, deriv, G, l);
+  }
+}
+
+void launch_lm_anchors(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P,
+                       int pstride, int n_pairs, cudaStream_t st) {
+  lm_anchor_kernel<<<n_pairs, 256, 0, st>>>(lines, counts, cap, B, P, pstride);
+}
+
+void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G, const LmBuffers& B, const LmParams& P,
+                      int pstride, int n_pairs, cudaStream_t st) {
+  dim3 grid((B.cap_kp + 127) / 128, n_pairs);
+  for (int level = G.top; level >= 0; level--)
+    klt_track_kernel<<<grid, 128, 0, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
+}
+
+void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
+                    int n_pairs, cudaStream_t st) {
+  size_t smem = (size_t)cap * (sizeof(float4) + 2 * sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaFuncSetAttribute(lm_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  lm_vote_kernel<<<n_pairs, 256, smem, st>>>(lines, counts, cap, B, P, pstride);
+}
+
+}  // namespace vpl

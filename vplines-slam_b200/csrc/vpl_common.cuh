@@ -204,6 +204,48 @@ void launch_ed_fit(const EdBuffers& B, const EdGeom& G, double fit_thr, const sh
                    int batch, cudaStream_t st);
 void launch_ed_compact(const EdBuffers& B, const EdGeom& G, VplLine* out, int* counts, int cap, int* overflow,
                        int batch, cudaStream_t st);
+// ---- line matching (linematch.cu) ------------------------------------------------------------
+constexpr int kKltMaxLevels = 4;  // maxLevel 3 (line_matching.cpp:14)
+// Pyramid of one frame: every level stored with a `pad`-pixel border (REFLECT_101 for the image,
+// zero for the Scharr pair), levels back to back.
+struct KltGeom {
+  int pad;                         // = window size 13
+  int top;                         // highest level built (cv::buildOpticalFlowPyramid's return)
+  int w[kKltMaxLevels], h[kKltMaxLevels], stride[kKltMaxLevels];
+  size_t img_off[kKltMaxLevels];   // bytes from the frame's pyramid base
+  size_t deriv_off[kKltMaxLevels]; // short2 elements from the frame's derivative base
+  size_t img_frame, deriv_frame;   // per-frame sizes (bytes / short2 elements)
+};
+struct LmParams {
+  int step;
+  float closest, ratio, dist_ratio, klt_err;
+  int max_count;
+  double eps2;
+  float min_eig;
+  float topo_dist, topo_len, topo_viol;
+  int illum, topo;
+};
+struct LmBuffers {   // per pair p (cap_kp anchors, cap lines)
+  int cap_kp;
+  float2* kps;       // anchors on the reference lines
+  float2* nxt;       // tracked positions
+  uint8_t* status;
+  float* err;
+  int* kp2line;      // closest current line per anchor
+  int* kp_start;     // (cap + 1) per pair: first anchor of each reference line
+  int* n_kp;
+  int* r2c;          // cap per pair: reference line -> current line
+  int* matched;      // number of matches per pair
+  int* overflow;
+};
+void launch_klt_pyramid(const uint8_t* img, uint8_t* pyr, short2* deriv, const KltGeom& G, int w, int h, int batch,
+                        cudaStream_t st);
+void launch_lm_anchors(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P,
+                       int pstride, int n_pairs, cudaStream_t st);
+void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G, const LmBuffers& B, const LmParams& P,
+                      int pstride, int n_pairs, cudaStream_t st);
+void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
+                    int n_pairs, cudaStream_t st);
 #ifdef VPL_DEBUG_NFA
 void debug_set_cand(int c);
 #endif
