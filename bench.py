@@ -48,7 +48,12 @@ WORKLOADS = {
     # node's parameters, smoothed=true) on the C2 frames / on the reference's bundled frames
     "E1": dict(name="E1_edlines_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2"),
     "E1r": dict(name="E1r_edlines_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1"),
+    # SURVEY 8f-1 + 8f-2: the reference's whole per-frame line front end as it really runs
+    # (readImage: EDline on every frame + LineMatching::Matching(prev, cur), line_feature_tracker.cpp:87, :115)
+    "E2": dict(name="E2_edlines_kltmatch_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2", match=True),
+    "E2r": dict(name="E2r_edlines_kltmatch_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1", match=True),
 }
+LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, LineFeatureTracker::readImage) at 752x480"
 ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
 
@@ -143,26 +148,29 @@ def cpu_baseline(unique, seconds=12.0, threads=None, octaves=1, name=WORKLOAD):
             "single_thread_frames_per_s": 1.0 / per_frame}
 
 
-def ed_cpu_baseline(unique, seconds=10.0, threads=None, name="E1"):
+def ed_cpu_baseline(unique, seconds=10.0, threads=None, name="E1", match=False):
     """EDLines on the host cores: the reference's own edline_detector.cpp (oracle/_ref, built in the
     authoring container against oracle/cvshim) when that library travelled here, else the oracle port."""
     from oracle import oracle as O
     O.build()
     use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_linefront.so"))
     threads = threads or os.cpu_count() or 1
+    run = O.linefront_sequence if match else O.edline_sequence
     t = time.time()
-    O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)
+    run(unique[:8], threads=1, use_ref=use_ref)
     per_frame = max((time.time() - t) / 8, 1e-4)
     n = int(max(threads * 4, min(seconds / per_frame * threads, 16384)))
     frames = tile_frames(unique, n)
     t = time.time()
-    total = O.edline_sequence(frames, threads=threads, use_ref=use_ref)
+    total = run(frames, threads=threads, use_ref=use_ref)
     dt = time.time() - t
-    what = ("the reference's own line_matching/src/edline_detector.cpp compiled against oracle/cvshim (OpenCV stand-in)"
-            if use_ref else "CPU oracle port of edline_detector.cpp (oracle/orc_edlines.c)")
+    src = "edline_detector.cpp" + (" + line_matching.cpp + lk_tracker_invoker_2d.cpp" if match else "")
+    what = (f"the reference's own line_matching/src/{src} compiled against oracle/cvshim (OpenCV stand-in)"
+            if use_ref else f"CPU oracle port of {src} (oracle/orc_edlines.c, orc_linematch.c)")
     return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": f"{n} frames of {name} ({total} lines) in {dt:.1f}s; {what}, one detector per thread, "
-                      f"{threads} threads over contiguous frame chunks",
+            "sample": f"{n} frames of {name} ({total} {'matched lines' if match else 'lines'}) in {dt:.1f}s; {what}, "
+                      f"one detector{'/matcher' if match else ''} per thread, {threads} threads over contiguous frame "
+                      f"chunks{' with a one-frame halo' if match else ''}",
             "single_thread_frames_per_s": 1.0 / per_frame}
 
 
@@ -173,24 +181,26 @@ def run_reference_edlines(args):
     unique = make_frames(min(args.unique, 32), args.seed, args.workload)
     use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_linefront.so"))
     threads = os.cpu_count() or 1
+    match = bool(wl.get("match"))
+    run = O.linefront_sequence if match else O.edline_sequence
     t = time.time()
-    O.edline_sequence(unique[:8], threads=1, use_ref=use_ref)
+    run(unique[:8], threads=1, use_ref=use_ref)
     per_frame = max((time.time() - t) / 8, 1e-4)
     n = int(max(threads * 4, min(5.0 / per_frame * threads, 16384)))
     frames = tile_frames(unique, n)
     for _ in range(args.warmup):
-        O.edline_sequence(frames[:max(threads, n // 4)], threads=threads, use_ref=use_ref)
+        run(frames[:max(threads, n // 4)], threads=threads, use_ref=use_ref)
     t0 = time.time()
     for _ in range(args.steps):
-        O.edline_sequence(frames, threads=threads, use_ref=use_ref)
+        run(frames, threads=threads, use_ref=use_ref)
     dt = time.time() - t0
     fps = n * args.steps / dt
     kind = "reference" if use_ref else "port"
-    line = {"impl": "reference", "metric": ED_METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": LF_METRIC if match else ED_METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16/f64", "data": "synthetic",
             "config": {"workload": wl["name"], "frames_per_step": n,
-                       "note": "edline_detector.cpp of the reference compiled against oracle/cvshim" if use_ref
+                       "note": "the reference's own line_matching/src sources compiled against oracle/cvshim" if use_ref
                        else "CPU oracle port (oracle/_ref not present)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                              "sample": f"{n} frames/step x {args.steps} steps"},
@@ -201,22 +211,50 @@ def run_reference_edlines(args):
 
 
 def run_edlines(args, torch, dist, rank, local_rank, world):
-    """--workload E1 / E1r: EDLineDetector::EDline (tracker-node parameters, smoothed=true) over a batch."""
+    """--workload E1 / E1r: EDLineDetector::EDline (tracker-node parameters, smoothed=true) over a batch;
+    E2 / E2r: the same followed by LineMatching::Matching(frame f-1, frame f) for every frame (fused)."""
     vpl = importlib.import_module("vplines_slam_b200")
     capi = vpl.capi
     wl = WORKLOADS[args.workload]
     W, H = wl["w"], wl["h"]
     B, S, cap = args.batch, args.slots, (args.max_lines or wl["max_lines"])
+    match = bool(wl.get("match"))
     unique = make_frames(args.unique, args.seed, args.workload)
-    host_buf = tile_frames(unique, B)
-    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap, max_batch=B,
-                       num_slots=S, blur_first=True, profile=True)
+    # E2: every step submits its B frames plus the last frame of the previous step in front (one-frame
+    # overlap), so that each consecutive pair of the sequence is matched exactly once
+    NB = B + 1 if match else B
+    host_buf = np.ascontiguousarray(np.concatenate([unique[-1:], tile_frames(unique, B)])) if match else tile_frames(unique, B)
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap, max_batch=NB,
+                       num_slots=S, blur_first=True, profile=True, lsd_path=False)
     param = capi.EDLineParam()
     ctx.edlines_configure(param)
+    if match:
+        ctx.linematch_configure(capi.LineMatchParam())
     ctx.host_register(host_buf)
-    lines = [np.zeros((B, cap), capi.LINE_DTYPE) for _ in range(S)]
-    counts = [np.zeros(B, np.int32) for _ in range(S)]
-    status = [np.zeros(B, np.int32) for _ in range(S)]
+    lines = [np.zeros((NB, cap), capi.LINE_DTYPE) for _ in range(S)]
+    counts = [np.zeros(NB, np.int32) for _ in range(S)]
+    status = [np.zeros(NB, np.int32) for _ in range(S)]
+    p2c = [np.zeros((NB, cap), np.int32) for _ in range(S)] if match else None
+    matched = [0]
+
+    def submit(s, frames):
+        if match:
+            ctx.linefront_submit(s, frames, smoothed=True)
+        else:
+            ctx.edlines_submit(s, frames, smoothed=True)
+
+    def collect(s):
+        if match:
+            ctx.linefront_collect_into(s, lines[s], counts[s], cap, p2c[s])
+            matched[0] = int((p2c[s][1:] >= 0).sum())
+        else:
+            ctx.edlines_collect_into(s, lines[s], counts[s], cap, status[s])
+
+    def resident(s):
+        if match:
+            ctx.linefront_run_resident(s)
+        else:
+            ctx.edlines_run_resident(s)
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,13 +268,13 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
             s = i % S
             if len(pending) == S:
                 ps = pending.pop(0)
-                ctx.edlines_collect_into(ps, lines[ps], counts[ps], cap, status[ps])
-            ctx.edlines_submit(s, host_buf, smoothed=True)
+                collect(ps)
+            submit(s, host_buf)
             pending.append(s)
         while pending:
             ps = pending.pop(0)
-            ctx.edlines_collect_into(ps, lines[ps], counts[ps], cap, status[ps])
-        return int(counts[ps].sum())
+            collect(ps)
+        return int(counts[ps][NB - B:].sum())
 
     e2e_steps(max(args.warmup, S))
     barrier()
@@ -251,21 +289,22 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
-    ctx.edlines_submit(0, host_buf[:1], smoothed=True)  # frame 0's edge pixels, for the byte counts below
+    ctx.edlines_submit(0, host_buf[NB - B:NB - B + 1], smoothed=True)  # one frame's edge pixels, for the byte counts below
     ctx.edlines_collect_into(0, lines[0], counts[0], cap, status[0])
     xy0, _ = ctx.edge_chains(0, W, H)
-    ctx.edlines_submit(0, host_buf, smoothed=True)       # leave a full batch resident in slot 0 again
-    ctx.edlines_collect_into(0, lines[0], counts[0], cap, status[0])
+    submit(0, host_buf)       # leave a full batch resident in slot 0 again
+    collect(0)
+    anchors = int(len(ctx.linematch_points(0)["status"])) if match else 0
 
     for w in range(max(args.warmup, S)):
-        ctx.edlines_run_resident(w % S)
+        resident(w % S)
     ctx.sync()
     ctx.reset_stage_times()
     l0 = ctx.kernel_launches()
     barrier()
     ev0.record()
     for i in range(args.steps):
-        ctx.edlines_run_resident(i % S)
+        resident(i % S)
     ctx.sync()
     ev1.record()
     barrier()
@@ -291,34 +330,49 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
            "ed_anchor": 6.0 * P / (param.scanIntervals ** 2) + P / (param.scanIntervals ** 2) / 8,
            "ed_walk": 20.0 * edge_px,                              # 3 u16 reads + mark + record, re-pack r+w
            "ed_fit": 20.0 * edge_px}                               # chain pixel 3 x 4 B + Sobel pair 2 x 4 B
+    launches_of = {"ed_grad": 2, "ed_anchor": 1, "ed_walk": 1, "ed_fit": 2}
+    kernels_of = {"ed_grad": "blur5_sobel_kernel+ed_gmap_kernel", "ed_anchor": "ed_anchor_kernel",
+                  "ed_walk": "ed_walk_kernel", "ed_fit": "ed_fit_kernel+ed_compact_kernel"}
+    if match:
+        # padded pyramid (4 levels, 13-px border) ~ 1.5 P bytes: written once, read by the next level and by
+        # the Scharr pass, which writes 4 B per padded pixel: ~ 1 + 3 x 1.5 + 6 = 11.5 P;
+        # tracker: per anchor, level and iteration one 14x14 u8 window (196 B) + once per level the
+        # 14x14 Scharr window (784 B) and the reference window: ~ 4 levels x (980 + ~8 x 196) B
+        alg.update({"lm_pyramid": 11.5 * P, "lm_track": anchors * 4 * (980.0 + 8 * 196.0), "lm_vote": anchors * 24.0})
+        launches_of.update({"lm_pyramid": 8, "lm_track": 5, "lm_vote": 1})
+        kernels_of.update({"lm_pyramid": "klt_level0/pyrdown/scharr kernels", "lm_track": "lm_anchor_kernel+klt_track_kernel",
+                           "lm_vote": "lm_vote_kernel"})
     ed = {k: stage[k] for k in alg}
     dom = max(ed, key=lambda k: ed[k][0])
     peak, peak_kind = measured_peak()
-    launches_in_stage = {"ed_grad": 2, "ed_anchor": 1, "ed_walk": 1, "ed_fit": 2}[dom]
+    launches_in_stage = launches_of[dom]
     dur = ed[dom][0] / max(ed[dom][1] / launches_in_stage, 1)
     achieved = alg[dom] * B / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
     tot = max(sum(x[0] for x in stage.values()), 1e-9)
-    roofline = {"bound": "hbm", "kernel": {"ed_grad": "blur5_sobel_kernel+ed_gmap_kernel", "ed_anchor": "ed_anchor_kernel",
-                                           "ed_walk": "ed_walk_kernel", "ed_fit": "ed_fit_kernel+ed_compact_kernel"}[dom],
+    roofline = {"bound": "hbm", "kernel": kernels_of[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "ms_per_launch": dur,
                 "algorithmic_bytes_per_launch": alg[dom] * B,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items() if v[1]},
                 "stage_share": {k: round(v[0] / tot, 4) for k, v in stage.items() if v[1]}}
-    line = {"metric": ED_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": LF_METRIC if match else ED_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/s16/f64", "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
+            "vs_baseline": None, "dtype": "u8/s16/f32/f64" if match else "u8/s16/f64", "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
             "config": {"workload": wl["name"], "frames_per_step": B, "width": W, "height": H, "slots": S, "max_lines": cap,
                        "unique_frames": len(unique), "parallelism": f"frames x{world}", "smoothed": True,
                        "edline_param": [param.ksize, param.sigma, param.gradientThreshold, param.anchorThreshold,
                                         param.scanIntervals, param.minLineLen, param.lineFitErrThreshold],
                        "lines_per_frame": round(n_lines / B, 1), "edge_px_frame0": int(edge_px),
+                       "matched_lines_per_frame": round(matched[0] / B, 1) if match else None,
+                       "anchors_pair0": anchors if match else None,
+                       "overlap": "each step submits B+1 frames (the previous step's last frame first)" if match else None,
                        "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (B * W * H / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": d2h_bytes},
+                    "h2d_bytes_per_step": NB * W * H, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
     if rank == 0:
-        line["cpu_baseline"] = ed_cpu_baseline(unique, name=wl["name"]) if (world == 1 and not args.no_cpu_baseline) else None
+        line["cpu_baseline"] = (ed_cpu_baseline(unique, name=wl["name"], match=match)
+                                if (world == 1 and not args.no_cpu_baseline) else None)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

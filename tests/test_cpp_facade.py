@@ -11,9 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "vplines-slam_b200")
 
 
-def build_facade(tmp_path):
-    exe = str(tmp_path / "test_facade")
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_facade.cpp"),
+def build_facade(tmp_path, name="test_facade"):
+    exe = str(tmp_path / name)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-L", PKG, "-lvplines_b200", f"-Wl,-rpath,{PKG}"]
     subprocess.check_call(cmd)
     return exe
@@ -69,3 +69,45 @@ def test_facade_matches_ctypes_path(vpl, orc, tmp_path):
     assert int(mb.group(1)) == sum(len(k) for k in kls)
     exp_matched = sum(len(ds[i]) for i in range(1, 5) if len(ds[i - 1]))
     assert int(mb.group(2)) == exp_matched
+
+
+def fnv(data):
+    d = 1469598103934665603
+    for v in data:
+        d = ((d ^ int(v)) * 1099511628211) % (1 << 64)
+    return d
+
+
+def line_digest(lines):
+    raw = np.ascontiguousarray(lines).view(np.uint8).reshape(len(lines), 56)[:, :52]
+    return fnv(raw.reshape(-1))
+
+
+def test_reference_named_facade_compiles_and_fails_loudly_without_gpu(vpl, tmp_path):
+    exe = build_facade(tmp_path, "test_refseam")
+    assert subprocess.run([exe, "--compile-only"]).returncode == 0
+    if vpl.capi.device_count() == 0:
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU path" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_named_facade_matches_oracle(vpl, orc, tmp_path):
+    """EDLineDetector::EDline / LineMatching::Matching of compat/line_matching_b200.hpp, used as the
+    tracker uses the reference's classes, against the CPU oracle (= the reference's own code)."""
+    exe = build_facade(tmp_path, "test_refseam")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a, b = make_image(320, 240, 0), make_image(320, 240, 2)
+    p = orc.EDLineParam(minLineLen=20)
+    la, lb = orc.edline_detect(a, p, True), orc.edline_detect(b, p, True)
+    r2c = orc.line_matching(a, b, la, lb)
+    m = re.search(r"ok=(\d) lines_a=(\d+) lines_b=(\d+) digest_a=(\d+) digest_b=(\d+) matched=(\d+) match_digest=(\d+)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) == 1 and int(m.group(2)) == len(la) and int(m.group(3)) == len(lb)
+    assert int(m.group(4)) == line_digest(la) and int(m.group(5)) == line_digest(lb)
+    assert int(m.group(6)) == int((r2c >= 0).sum()) and int(m.group(7)) == fnv(r2c + 7)
+    assert len(la) > 5 and (r2c >= 0).sum() > 3
+    m2 = re.search(r"unsmoothed_lines=(\d+) unsmoothed_digest=(\d+) empty_returns=(\d)", r.stdout)
+    lu = orc.edline_detect(a, p, False)
+    assert int(m2.group(1)) == len(lu) and int(m2.group(2)) == line_digest(lu) and m2.group(3) == "0"

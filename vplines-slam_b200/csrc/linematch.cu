@@ -17,8 +17,9 @@
 //   klt_track_kernel  per pyramid level, ONE THREAD PER ANCHOR: the reference's float sums over
 //                     the 13x13 window are sequential (y, x) single-precision accumulations, so
 //                     the window loop stays in one thread and the 32 lanes of a warp carry 32
-//                     anchors; windows live in thread-local memory; each source byte of a window
-//                     is loaded once (row-blended bilinear interpolation in exact integers)
+//                     anchors; the windows live in shared memory ([element][lane], 43 KB per warp);
+//                     each source byte of a window is loaded once (row-blended bilinear
+//                     interpolation in exact integers)
 //   lm_vote_kernel    one CTA per pair: closest current line per tracked anchor (lm.cpp:48-86),
 //                     vote per reference line (:88-133), topological filter (:267-410, :656-665)
 // Bit-exact vs the oracle: integer window arithmetic, float/double sequences in the reference's
@@ -36,6 +37,9 @@ constexpr int WIN = 13;           // LineMatching::Matching sets 13x13 (lm.cpp:6
 constexpr int NWIN = WIN * WIN;
 constexpr int W_BITS = 14;
 #define LM_DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))  // CV_DESCALE, klt.h:39
+
+// exact int -> float for |v| < 2^22 without the conversion unit: 1.5 * 2^23 + v is exact
+__device__ __forceinline__ float small_int_to_float(int v) { return __int_as_float(0x4B400000 + v) - 12582912.0f; }
 
 __device__ __forceinline__ int cv_floor_d(float v) {  // SSE cvFloor: INT_MIN on NaN / overflow
   if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
@@ -166,6 +170,7 @@ __device__ __forceinline__ Wts lk_weights(float a, float b) {  // lk2d.cpp:109-1
 // bilinear 13x13 window of a padded u8 level at integer corner (ix, iy): every source byte is read
 // once; the sums are exact integers, so blending rows first changes nothing (lk2d.cpp:338-348).
 // Also returns the window's integer sum and sum of squares (for cv::meanStdDev).
+// Window element t of lane l lives at win[t * 32 + l] (shared memory, conflict-free).
 __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, int st, int ix, int iy, const Wts& w,
                                              short* __restrict__ out, int& sum, long long& sq) {
   int top[WIN];
@@ -175,6 +180,7 @@ __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, in
 #pragma unroll 1
   for (int r = 0; r <= WIN; r++, row += st) {
     int prev = row[0];
+    unsigned rq = 0;  // 13 * 8160^2 < 2^31
 #pragma unroll
     for (int x = 0; x < WIN; x++) {
       int cur = row[x + 1];
@@ -182,13 +188,14 @@ __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, in
       int b = prev * w.w10 + cur * w.w11;   // ... and as the lower row of window row r-1
       if (r > 0) {
         int v = LM_DESCALE(top[x] + b, W_BITS - 5);
-        out[(r - 1) * WIN + x] = (short)v;
+        out[((r - 1) * WIN + x) * 32] = (short)v;
         sum += v;
-        sq += v * v;
+        rq += (unsigned)(v * v);
       }
       top[x] = t;
       prev = cur;
     }
+    sq += rq;
   }
 }
 
@@ -202,12 +209,19 @@ __device__ __forceinline__ void lk_norm_params(int si, long long qi, int sj, lon
   beta = (float)(mi - alpha * mj);
 }
 
-__global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ deriv,
-                                                        KltGeom G, LmBuffers B, LmParams P, int level, int pstride,
-                                                        int n_pairs) {
+// One warp per CTA; the three 13x13 windows of its 32 anchors (reference patch, its Scharr pair,
+// current patch: 1352 B per anchor) live in shared memory, 43 KB per CTA, 5 CTAs per SM.
+constexpr int kTrackSmem = NWIN * 32 * (2 + 2 + 4);
+__global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ deriv,
+                                                       KltGeom G, LmBuffers B, LmParams P, int level, int pstride,
+                                                       int n_pairs) {
+  extern __shared__ __align__(16) unsigned char s_win[];
   const int p = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs || i >= B.n_kp[p]) return;
+  short* Iw = reinterpret_cast<short*>(s_win) + threadIdx.x;
+  short* Jw = Iw + NWIN * 32;
+  short2* dIw = reinterpret_cast<short2*>(s_win + NWIN * 32 * 4) + threadIdx.x;
   const size_t k = (size_t)p * B.cap_kp + i;
   const int fr = p * pstride, fc = fr + 1;
   const int st = G.stride[level], lw = G.w[level], lh = G.h[level];
@@ -236,8 +250,6 @@ __global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restric
     if (level == 0) { B.status[k] = 0; B.err[k] = 0.f; }
     return;
   }
-  short Iw[NWIN], Jw[NWIN];
-  short2 dIw[NWIN];
   int sI;
   long long qI;
   Wts w = lk_weights(px - ipx, py - ipy);
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restric
         int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
         if (r > 0) {
           int ixv = LM_DESCALE(tx[x] + b0, W_BITS), iyv = LM_DESCALE(ty[x] + b1, W_BITS);
-          dIw[(r - 1) * WIN + x] = make_short2((short)ixv, (short)iyv);
+          dIw[((r - 1) * WIN + x) * 32] = make_short2((short)ixv, (short)iyv);
           iA11 += (float)(ixv * ixv);
           iA12 += (float)(ixv * iyv);
           iA22 += (float)(iyv * iyv);
@@ -292,12 +304,12 @@ __global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restric
     float alpha = 1.0f, beta = 0.0f;
     if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
     float ib1 = 0, ib2 = 0;
-#pragma unroll 1
+#pragma unroll 13
     for (int t = 0; t < NWIN; t++) {  // lk2d.cpp:364-376
-      float diff = alpha * Jw[t] + beta - Iw[t];
-      short2 d = dIw[t];
-      ib1 += diff * d.x;
-      ib2 += diff * d.y;
+      float diff = alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]);
+      short2 d = dIw[t * 32];
+      ib1 += diff * small_int_to_float(d.x);
+      ib2 += diff * small_int_to_float(d.y);
     }
     const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
     const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
@@ -327,7 +339,8 @@ __global__ void __launch_bounds__(128) klt_track_kernel(const uint8_t* __restric
       if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
       float errval = 0.f;
 #pragma unroll 1
-      for (int t = 0; t < NWIN; t++) errval += fabsf(alpha * Jw[t] + beta - Iw[t]);
+      for (int t = 0; t < NWIN; t++)
+        errval += fabsf(alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]));
       B.err[k] = errval * 1.f / (32 * WIN * WIN);
     }
   }
@@ -479,19 +492,19 @@ void launch_lm_anchors(const VplLine* lines, const int* counts, int cap, const L
 
 void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G, const LmBuffers& B, const LmParams& P,
                       int pstride, int n_pairs, cudaStream_t st) {
-  dim3 grid((B.cap_kp + 127) / 128, n_pairs);
+  // per device, so set on every batch (a process may drive several GPUs)
+  cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrackSmem);
+  cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dim3 grid((B.cap_kp + 31) / 32, n_pairs);
   for (int level = G.top; level >= 0; level--)
-    klt_track_kernel<<<grid, 128, 0, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
+    klt_track_kernel<<<grid, 32, kTrackSmem, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
 }
 
 void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
                     int n_pairs, cudaStream_t st) {
   size_t smem = (size_t)cap * (sizeof(float4) + 2 * sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaFuncSetAttribute(lm_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  // static + dynamic shared memory above 48 KB needs the opt-in (cap 2048 is exactly 48 KB of dynamic)
+  if (smem > 40 * 1024) cudaFuncSetAttribute(lm_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lm_vote_kernel<<<n_pairs, 256, smem, st>>>(lines, counts, cap, B, P, pstride);
 }
 
