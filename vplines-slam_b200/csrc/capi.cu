@@ -657,7 +657,7 @@ LmParams lm_params(const VplLineMatchParam& p) {
 void lm_free(Slot& s) {
   cudaFree(s.lm_pyr); cudaFree(s.lm_deriv); cudaFree(s.lm.kps); cudaFree(s.lm.nxt); cudaFree(s.lm.status);
   cudaFree(s.lm.err); cudaFree(s.lm.kp2line); cudaFree(s.lm.kp_start); cudaFree(s.lm.n_kp); cudaFree(s.lm.r2c);
-  cudaFree(s.lm.matched); cudaFree(s.d_lm_counts);
+  cudaFree(s.lm.matched); cudaFree(s.lm.pair_off); cudaFree(s.lm.queue); cudaFree(s.d_lm_counts);
   cudaFreeHost(s.h_r2c);
   s.lm_pyr = nullptr; s.lm_deriv = nullptr; s.lm = LmBuffers{}; s.h_r2c = nullptr; s.d_lm_counts = nullptr;
 }
@@ -680,7 +680,7 @@ void run_linematch(VplContext* c, Slot& s, const int* d_counts, int n_frames, in
     StageTimer t(c, s, VPL_STAGE_LM_TRACK);
     launch_lm_anchors(s.d_lines, d_counts, cap, s.lm, P, pstride, n_pairs, s.stream);
     launch_klt_track(s.lm_pyr, s.lm_deriv, G, s.lm, P, pstride, n_pairs, s.stream);
-    t.launches(2 + G.top);
+    t.launches(3 + G.top);
   }
   {
     StageTimer t(c, s, VPL_STAGE_LM_VOTE);
@@ -1423,6 +1423,8 @@ int vpl_linematch_configure(VplContext* c, const VplLineMatchParam* p) {
     CK(c, dmalloc(&s.lm.n_kp, B));
     CK(c, dmalloc(&s.lm.r2c, B * cap));
     CK(c, dmalloc(&s.lm.matched, B));
+    CK(c, dmalloc(&s.lm.pair_off, B + 1));
+    CK(c, dmalloc(&s.lm.queue, (size_t)kKltMaxLevels));
     CK(c, dmalloc(&s.d_lm_counts, B));
     CK(c, hmalloc(&s.h_r2c, B * cap));
     if (!s.d_lines) {  // line storage is shared with the EDLines detector

@@ -17,7 +17,8 @@
 //   klt_track_kernel  per pyramid level, ONE THREAD PER ANCHOR: the reference's float sums over
 //                     the 13x13 window are sequential (y, x) single-precision accumulations, so
 //                     the window loop stays in one thread and the 32 lanes of a warp carry 32
-//                     anchors; the windows live in shared memory ([element][lane], 43 KB per warp);
+//                     anchors; persistent warps refill idle lanes from a queue over all pairs (the
+//                     iteration count varies from 2 to 30); the windows live in shared memory ([element][lane], 43 KB per warp);
 //                     each source byte of a window is loaded once (row-blended bilinear
 //                     interpolation in exact integers)
 //   lm_vote_kernel    one CTA per pair: closest current line per tracked anchor (lm.cpp:48-86),
@@ -209,142 +210,209 @@ __device__ __forceinline__ void lk_norm_params(int si, long long qi, int sj, lon
   beta = (float)(mi - alpha * mj);
 }
 
-// One warp per CTA; the three 13x13 windows of its 32 anchors (reference patch, its Scharr pair,
-// current patch: 1352 B per anchor) live in shared memory, 43 KB per CTA, 5 CTAs per SM.
+// exclusive prefix of the per-pair anchor counts: the work queue of the tracker runs over all pairs
+__global__ void __launch_bounds__(1024) lm_pair_offsets_kernel(const int* __restrict__ n_kp, int n_pairs,
+                                                               int* __restrict__ pair_off) {
+  __shared__ int s_part[1024];
+  const int per = (n_pairs + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, n_pairs);
+  int t = 0;
+  for (int i = lo; i < hi; i++) t += n_kp[i];
+  s_part[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int ex = s_part[threadIdx.x] - t;
+  for (int i = lo; i < hi; i++) {
+    pair_off[i] = ex;
+    ex += n_kp[i];
+  }
+  if (threadIdx.x == 1023) pair_off[n_pairs] = s_part[1023];
+}
+
+// Persistent warps, one per CTA; the three 13x13 windows of a lane's anchor (reference patch, its
+// Scharr pair, current patch: 1352 B) live in shared memory, 43 KB per CTA, 5 CTAs per SM.
+//
+// The number of LK iterations varies a lot between anchors (mean 4-9, but 4-7 % run all 30), so a
+// warp that takes 32 anchors and waits for the slowest spends two thirds of its issue slots on
+// idle lanes.  Instead every lane is a small state machine (idle / iterating / final error) and
+// the warp pulls new anchors from a queue over all pairs of the batch whenever kRefill lanes are
+// idle; one trip of the loop = one window sampling + one accumulation pass for every busy lane,
+// whatever its phase.  Per-anchor arithmetic is untouched, so results do not depend on the schedule.
 constexpr int kTrackSmem = NWIN * 32 * (2 + 2 + 4);
+constexpr int kRefill = 8;
 __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ deriv,
                                                        KltGeom G, LmBuffers B, LmParams P, int level, int pstride,
                                                        int n_pairs) {
   extern __shared__ __align__(16) unsigned char s_win[];
-  const int p = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs || i >= B.n_kp[p]) return;
-  short* Iw = reinterpret_cast<short*>(s_win) + threadIdx.x;
+  const int lane = threadIdx.x;
+  short* Iw = reinterpret_cast<short*>(s_win) + lane;
   short* Jw = Iw + NWIN * 32;
-  short2* dIw = reinterpret_cast<short2*>(s_win + NWIN * 32 * 4) + threadIdx.x;
-  const size_t k = (size_t)p * B.cap_kp + i;
-  const int fr = p * pstride, fc = fr + 1;
+  short2* dIw = reinterpret_cast<short2*>(s_win + NWIN * 32 * 4) + lane;
+  const int total = B.pair_off[n_pairs];
+  int* queue = B.queue + level;
   const int st = G.stride[level], lw = G.w[level], lh = G.h[level];
-  // pointers to pixel (0,0) of the level inside its padded buffer
-  const uint8_t* I = pyr + (size_t)fr * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
-  const uint8_t* J = pyr + (size_t)fc * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
-  const short2* dI = deriv + (size_t)fr * G.deriv_frame + G.deriv_off[level] + (size_t)G.pad * st + G.pad;
-
   const float half = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
   const float scale = (float)(1. / (1 << level));
-  const float2 prev = B.kps[k];
-  float px = prev.x * scale, py = prev.y * scale, nx, ny;
-  if (level == G.top) {  // flags == 0, lk2d.cpp:51-56
-    nx = px; ny = py;
-    B.status[k] = 1;
-    B.err[k] = 0.f;
-  } else {
-    float2 q = B.nxt[k];
-    nx = q.x * 2.f; ny = q.y * 2.f;
-  }
-  B.nxt[k] = make_float2(nx, ny);  // lk2d.cpp:61
-  px -= half; py -= half;
-  const int ipx = cv_floor_d(px), ipy = cv_floor_d(py);
-  if (ipx < -WIN || ipx >= lw || ipy < -WIN || ipy >= lh) {  // lk2d.cpp:91-99
-    if (level == 0) { B.status[k] = 0; B.err[k] = 0.f; }
-    return;
-  }
-  int sI;
-  long long qI;
-  Wts w = lk_weights(px - ipx, py - ipy);
-  lk_sample_u8(I, st, ipx, ipy, w, Iw, sI, qI);
-  float iA11 = 0, iA12 = 0, iA22 = 0;
-  {  // derivative window + structure tensor, lk2d.cpp:117-149 (sums in (y, x) order)
-    int tx[WIN], ty[WIN];
-    const short2* row = dI + (ptrdiff_t)ipy * st + ipx;
-#pragma unroll 1
-    for (int r = 0; r <= WIN; r++, row += st) {
-      short2 pv = row[0];
-#pragma unroll
-      for (int x = 0; x < WIN; x++) {
-        short2 cv = row[x + 1];
-        int t0 = pv.x * w.w00 + cv.x * w.w01, b0 = pv.x * w.w10 + cv.x * w.w11;
-        int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
-        if (r > 0) {
-          int ixv = LM_DESCALE(tx[x] + b0, W_BITS), iyv = LM_DESCALE(ty[x] + b1, W_BITS);
-          dIw[((r - 1) * WIN + x) * 32] = make_short2((short)ixv, (short)iyv);
-          iA11 += (float)(ixv * ixv);
-          iA12 += (float)(ixv * iyv);
-          iA22 += (float)(iyv * iyv);
+
+  int phase = 0;  // 0 idle, 1 iterating, 2 final error (level 0 only)
+  size_t k = 0;
+  const uint8_t* J = nullptr;
+  float nx = 0, ny = 0, pdx = 0, pdy = 0, outx = 0, outy = 0, A11 = 0, A12 = 0, A22 = 0, D = 0;
+  int j = 0, sI = 0;
+  long long qI = 0;
+  bool exhausted = false;
+
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, phase == 0);
+    if (!exhausted && (__popc(idle) >= kRefill || idle == 0xffffffffu)) {
+      const int cnt = __popc(idle);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(queue, cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + cnt >= total) exhausted = true;
+      const int t = base + __popc(idle & ((1u << lane) - 1u));
+      if (phase == 0 && t < total) {
+        // ---- set-up of anchor t at this level, lk2d.cpp:45-300 ----
+        int lo = 0, hi = n_pairs;  // largest p with pair_off[p] <= t
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (B.pair_off[mid] <= t) lo = mid; else hi = mid;
         }
-        tx[x] = t0; ty[x] = t1;
-        pv = cv;
+        const int p = lo, i = t - B.pair_off[lo];
+        k = (size_t)p * B.cap_kp + i;
+        const int fr = p * pstride, fc = fr + 1;
+        // pointers to pixel (0,0) of the level inside its padded buffer
+        const uint8_t* I = pyr + (size_t)fr * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
+        J = pyr + (size_t)fc * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
+        const short2* dI = deriv + (size_t)fr * G.deriv_frame + G.deriv_off[level] + (size_t)G.pad * st + G.pad;
+        const float2 prev = B.kps[k];
+        float px = prev.x * scale, py = prev.y * scale;
+        if (level == G.top) {  // flags == 0, lk2d.cpp:51-56
+          nx = px; ny = py;
+          B.status[k] = 1;
+          B.err[k] = 0.f;
+        } else {
+          float2 q = B.nxt[k];
+          nx = q.x * 2.f; ny = q.y * 2.f;
+        }
+        B.nxt[k] = make_float2(nx, ny);  // lk2d.cpp:61
+        px -= half; py -= half;
+        const int ipx = cv_floor_d(px), ipy = cv_floor_d(py);
+        if (ipx < -WIN || ipx >= lw || ipy < -WIN || ipy >= lh) {  // lk2d.cpp:91-99
+          if (level == 0) { B.status[k] = 0; B.err[k] = 0.f; }
+        } else {
+          const Wts w = lk_weights(px - ipx, py - ipy);
+          lk_sample_u8(I, st, ipx, ipy, w, Iw, sI, qI);
+          float iA11 = 0, iA12 = 0, iA22 = 0;
+          {  // derivative window + structure tensor, lk2d.cpp:117-149 (sums in (y, x) order)
+            int tx[WIN], ty[WIN];
+            const short2* row = dI + (ptrdiff_t)ipy * st + ipx;
+#pragma unroll 1
+            for (int r = 0; r <= WIN; r++, row += st) {
+              short2 pv = row[0];
+#pragma unroll
+              for (int x = 0; x < WIN; x++) {
+                short2 cv = row[x + 1];
+                int t0 = pv.x * w.w00 + cv.x * w.w01, b0 = pv.x * w.w10 + cv.x * w.w11;
+                int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
+                if (r > 0) {
+                  int ixv = LM_DESCALE(tx[x] + b0, W_BITS), iyv = LM_DESCALE(ty[x] + b1, W_BITS);
+                  dIw[((r - 1) * WIN + x) * 32] = make_short2((short)ixv, (short)iyv);
+                  iA11 += (float)(ixv * ixv);
+                  iA12 += (float)(ixv * iyv);
+                  iA22 += (float)(iyv * iyv);
+                }
+                tx[x] = t0; ty[x] = t1;
+                pv = cv;
+              }
+            }
+          }
+          A11 = iA11 * FLT_SCALE; A12 = iA12 * FLT_SCALE; A22 = iA22 * FLT_SCALE;
+          D = A11 * A22 - A12 * A12;
+          const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * WIN * WIN);
+          if (min_eig < P.min_eig || D < FLT_EPSILON) {  // lk2d.cpp:294-298
+            if (level == 0) B.status[k] = 0;
+          } else {
+            D = 1.f / D;
+            outx = nx; outy = ny;  // value of nextPts[ptidx] (untouched if the loop leaves at once)
+            nx -= half; ny -= half;
+            pdx = 0.f; pdy = 0.f;
+            j = 0;
+            phase = P.max_count > 0 ? 1 : 3;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (phase == 3) {  // maxCount == 0: the loop body never runs, j == maxCount
+      if (level == 0) B.status[k] = 0;
+      phase = 0;
+    }
+    if (__ballot_sync(0xffffffffu, phase != 0) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    if (phase != 0) {
+      // ---- one trip: an LK iteration (lk2d.cpp:321-418) or the final error (:429-478) ----
+      const float sx = phase == 1 ? nx : outx - half, sy = phase == 1 ? ny : outy - half;
+      const int isx = cv_floor_d(sx), isy = cv_floor_d(sy);
+      const bool outside = phase == 1 ? (isx < -half || isx >= lw || isy < -half || isy >= lh)
+                                      : (isx < -WIN || isx >= lw || isy < -WIN || isy >= lh);
+      bool finished = false, ok = true;
+      if (outside) {
+        if (phase == 2) { B.status[k] = 0; phase = 0; }
+        else { finished = true; ok = false; }  // lk2d.cpp:326-330
+      } else {
+        const Wts w = lk_weights(sx - isx, sy - isy);
+        int sJ;
+        long long qJ;
+        lk_sample_u8(J, st, isx, isy, w, Jw, sJ, qJ);
+        float alpha = 1.0f, beta = 0.0f;
+        if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
+        float ib1 = 0, ib2 = 0, errval = 0;
+#pragma unroll 13
+        for (int t = 0; t < NWIN; t++) {  // lk2d.cpp:364-376 and :467-476, each sum in (y, x) order
+          float diff = alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]);
+          short2 d = dIw[t * 32];
+          ib1 += diff * small_int_to_float(d.x);
+          ib2 += diff * small_int_to_float(d.y);
+          errval += fabsf(diff);
+        }
+        if (phase == 2) {
+          B.err[k] = errval * 1.f / (32 * WIN * WIN);
+          B.status[k] = 1;
+          phase = 0;
+        } else {
+          const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
+          const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+          nx += dx; ny += dy;
+          outx = nx + half; outy = ny + half;
+          if ((double)dx * dx + (double)dy * dy <= P.eps2) {  // lk2d.cpp:405
+            finished = true;
+          } else if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) {  // lk2d.cpp:410-414
+            outx -= dx * 0.5f; outy -= dy * 0.5f;
+            finished = true;
+          } else {
+            pdx = dx; pdy = dy;
+            if (++j == P.max_count) { finished = true; ok = false; }  // lk2d.cpp:422
+          }
+        }
+      }
+      if (finished) {
+        B.nxt[k] = make_float2(outx, outy);
+        if (level != 0) phase = 0;
+        else if (ok) phase = 2;
+        else { B.status[k] = 0; phase = 0; }
       }
     }
+    __syncwarp();
   }
-  const float A11 = iA11 * FLT_SCALE, A12 = iA12 * FLT_SCALE, A22 = iA22 * FLT_SCALE;
-  float D = A11 * A22 - A12 * A12;
-  const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * WIN * WIN);
-  if (min_eig < P.min_eig || D < FLT_EPSILON) {  // lk2d.cpp:294-298
-    if (level == 0) B.status[k] = 0;
-    return;
-  }
-  D = 1.f / D;
-  float outx = nx, outy = ny;  // value of nextPts[ptidx] (untouched if the loop leaves at once)
-  nx -= half; ny -= half;
-  float pdx = 0.f, pdy = 0.f;
-  bool ok = B.status[k] != 0;
-  int j;
-  for (j = 0; j < P.max_count; j++) {  // lk2d.cpp:321-418
-    const int inx = cv_floor_d(nx), iny = cv_floor_d(ny);
-    if (inx < -half || inx >= lw || iny < -half || iny >= lh) {
-      if (level == 0) ok = false;
-      break;
-    }
-    w = lk_weights(nx - inx, ny - iny);
-    int sJ;
-    long long qJ;
-    lk_sample_u8(J, st, inx, iny, w, Jw, sJ, qJ);
-    float alpha = 1.0f, beta = 0.0f;
-    if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
-    float ib1 = 0, ib2 = 0;
-#pragma unroll 13
-    for (int t = 0; t < NWIN; t++) {  // lk2d.cpp:364-376
-      float diff = alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]);
-      short2 d = dIw[t * 32];
-      ib1 += diff * small_int_to_float(d.x);
-      ib2 += diff * small_int_to_float(d.y);
-    }
-    const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
-    const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
-    nx += dx; ny += dy;
-    outx = nx + half; outy = ny + half;
-    if ((double)dx * dx + (double)dy * dy <= P.eps2) break;  // lk2d.cpp:405
-    if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) {  // lk2d.cpp:410-414
-      outx -= dx * 0.5f; outy -= dy * 0.5f;
-      break;
-    }
-    pdx = dx; pdy = dy;
-  }
-  B.nxt[k] = make_float2(outx, outy);
-  if (level != 0) return;
-  if (j == P.max_count) ok = false;  // lk2d.cpp:422
-  if (ok) {  // final error, lk2d.cpp:429-478
-    const float ex = outx - half, ey = outy - half;
-    const int iex = cv_floor_d(ex), iey = cv_floor_d(ey);
-    if (iex < -WIN || iex >= lw || iey < -WIN || iey >= lh) {
-      ok = false;
-    } else {
-      w = lk_weights(ex - iex, ey - iey);
-      int sJ;
-      long long qJ;
-      lk_sample_u8(J, st, iex, iey, w, Jw, sJ, qJ);
-      float alpha = 1.0f, beta = 0.0f;
-      if (P.illum) lk_norm_params(sI, qI, sJ, qJ, alpha, beta);
-      float errval = 0.f;
-#pragma unroll 1
-      for (int t = 0; t < NWIN; t++)
-        errval += fabsf(alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]));
-      B.err[k] = errval * 1.f / (32 * WIN * WIN);
-    }
-  }
-  B.status[k] = ok ? 1 : 0;
 }
 
 // ---- closest line, vote, topological filter -------------------------------------------------------
@@ -495,9 +563,14 @@ void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G,
   // per device, so set on every batch (a process may drive several GPUs)
   cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrackSmem);
   cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  dim3 grid((B.cap_kp + 31) / 32, n_pairs);
+  cudaMemsetAsync(B.queue, 0, kKltMaxLevels * sizeof(int), st);
+  lm_pair_offsets_kernel<<<1, 1024, 0, st>>>(B.n_kp, n_pairs, B.pair_off);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int warps = sms * 5;  // 5 resident CTAs of 43 KB per SM
   for (int level = G.top; level >= 0; level--)
-    klt_track_kernel<<<grid, 32, kTrackSmem, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
+    klt_track_kernel<<<warps, 32, kTrackSmem, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
 }
 
 void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,

@@ -236,6 +236,8 @@ struct LmBuffers {   // per pair p (cap_kp anchors, cap lines)
   int* n_kp;
   int* r2c;          // cap per pair: reference line -> current line
   int* matched;      // number of matches per pair
+  int* pair_off;     // n_pairs + 1: exclusive prefix of n_kp (the tracker's work queue runs over all pairs)
+  int* queue;        // kKltMaxLevels counters: next work item per pyramid level
   int* overflow;
 };
 void launch_klt_pyramid(const uint8_t* img, uint8_t* pyr, short2* deriv, const KltGeom& G, int w, int h, int batch,
