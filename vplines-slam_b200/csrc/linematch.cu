@@ -27,6 +27,7 @@
 // order with -fmad=false, IEEE sqrt/div.
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "vpl_common.cuh"
 
@@ -178,13 +179,25 @@ __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, in
   sum = 0;
   sq = 0;
   const uint8_t* row = img + (ptrdiff_t)iy * st + ix;
+  // software pipeline: the bytes of row r+1 are in flight while row r is blended
+  unsigned char nxt[WIN + 1];
+#pragma unroll
+  for (int x = 0; x <= WIN; x++) nxt[x] = row[x];
 #pragma unroll 1
-  for (int r = 0; r <= WIN; r++, row += st) {
-    int prev = row[0];
+  for (int r = 0; r <= WIN; r++) {
+    unsigned char cur_row[WIN + 1];
+#pragma unroll
+    for (int x = 0; x <= WIN; x++) cur_row[x] = nxt[x];
+    row += st;
+    if (r < WIN) {
+#pragma unroll
+      for (int x = 0; x <= WIN; x++) nxt[x] = row[x];
+    }
+    int prev = cur_row[0];
     unsigned rq = 0;  // 13 * 8160^2 < 2^31
 #pragma unroll
     for (int x = 0; x < WIN; x++) {
-      int cur = row[x + 1];
+      int cur = cur_row[x + 1];
       int t = prev * w.w00 + cur * w.w01;   // this row as the upper row of window row r
       int b = prev * w.w10 + cur * w.w11;   // ... and as the lower row of window row r-1
       if (r > 0) {
@@ -240,14 +253,13 @@ __global__ void __launch_bounds__(1024) lm_pair_offsets_kernel(const int* __rest
 // The number of LK iterations varies a lot between anchors (mean 4-9, but 4-7 % run all 30), so a
 // warp that takes 32 anchors and waits for the slowest spends two thirds of its issue slots on
 // idle lanes.  Instead every lane is a small state machine (idle / iterating / final error) and
-// the warp pulls new anchors from a queue over all pairs of the batch whenever kRefill lanes are
-// idle; one trip of the loop = one window sampling + one accumulation pass for every busy lane,
+// the warp pulls new anchors from a queue over all pairs of the batch whenever kRefill (16) lanes
+// are idle (the set-up of a new anchor runs divergently, so it should not run for too few lanes); one trip of the loop = one window sampling + one accumulation pass for every busy lane,
 // whatever its phase.  Per-anchor arithmetic is untouched, so results do not depend on the schedule.
 constexpr int kTrackSmem = NWIN * 32 * (2 + 2 + 4);
-constexpr int kRefill = 8;
 __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict__ pyr, const short2* __restrict__ deriv,
                                                        KltGeom G, LmBuffers B, LmParams P, int level, int pstride,
-                                                       int n_pairs) {
+                                                       int n_pairs, int kRefill) {
   extern __shared__ __align__(16) unsigned char s_win[];
   const int lane = threadIdx.x;
   short* Iw = reinterpret_cast<short*>(s_win) + lane;
@@ -313,12 +325,23 @@ __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict
           {  // derivative window + structure tensor, lk2d.cpp:117-149 (sums in (y, x) order)
             int tx[WIN], ty[WIN];
             const short2* row = dI + (ptrdiff_t)ipy * st + ipx;
+            short2 nx2[WIN + 1];
+#pragma unroll
+            for (int x = 0; x <= WIN; x++) nx2[x] = row[x];
 #pragma unroll 1
-            for (int r = 0; r <= WIN; r++, row += st) {
-              short2 pv = row[0];
+            for (int r = 0; r <= WIN; r++) {
+              short2 cr[WIN + 1];
+#pragma unroll
+              for (int x = 0; x <= WIN; x++) cr[x] = nx2[x];
+              row += st;
+              if (r < WIN) {
+#pragma unroll
+                for (int x = 0; x <= WIN; x++) nx2[x] = row[x];
+              }
+              short2 pv = cr[0];
 #pragma unroll
               for (int x = 0; x < WIN; x++) {
-                short2 cv = row[x + 1];
+                short2 cv = cr[x + 1];
                 int t0 = pv.x * w.w00 + cv.x * w.w01, b0 = pv.x * w.w10 + cv.x * w.w11;
                 int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
                 if (r > 0) {
@@ -569,8 +592,14 @@ void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int warps = sms * 5;  // 5 resident CTAs of 43 KB per SM
+  static int refill = 0;      // idle lanes that trigger a refill (VPL_KLT_REFILL: tuning experiments)
+  if (!refill) {
+    const char* e = getenv("VPL_KLT_REFILL");
+    refill = e ? atoi(e) : 16;  // measured on B200: 4 -> 25.8k, 8 -> 29.2k, 16 -> 32.2k, 22 -> 31.9k, 28 -> 29.3k, 32 -> 24.6k frames/s (E2)
+    if (refill < 1 || refill > 32) refill = 16;
+  }
   for (int level = G.top; level >= 0; level--)
-    klt_track_kernel<<<warps, 32, kTrackSmem, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs);
+    klt_track_kernel<<<warps, 32, kTrackSmem, st>>>(pyr, deriv, G, B, P, level, pstride, n_pairs, refill);
 }
 
 void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
