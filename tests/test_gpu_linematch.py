@@ -142,3 +142,49 @@ def test_linematch_edge_cases(ctx, vpl, orc, mh04, synth):
 def test_lsd_entry_points_refused_without_lsd_path(ctx, vpl, mh04):
     with pytest.raises(vpl.VplError):
         ctx.lsd_detect_batch(mh04[:1])
+
+
+@pytest.mark.parametrize("shape,scan,minlen", [((720, 1280), 2, 35), ((207, 331), 1, 15), ((40, 52), 2, 10)])
+def test_linefront_other_geometries(vpl, orc, synth, mh04, shape, scan, minlen):
+    """D455-shaped 1280x720 frames, an odd size scanned at every pixel, and an image so small that the
+    pyramid has two levels (26x20 is the last one above the 13-px window): fused EDLines + matching ==
+    oracle, bit for bit."""
+    h, w = shape
+    if h < 100:
+        frames = np.ascontiguousarray(mh04[5:8, 150:150 + h, 350:350 + w])
+    else:
+        big = synth.sequence(3, w=max(w, 376), h=max(h, 240), seed=900 + h, n_quads=14, n_strokes=24)
+        frames = np.ascontiguousarray(big[:, :h, :w])
+    pe = orc.EDLineParam(minLineLen=minlen, scanIntervals=scan)
+    with vpl.Context(max_width=w, max_height=h, max_lines=1024, max_batch=4, num_slots=1, lsd_path=False) as c:
+        c.edlines_configure(vpl.capi.EDLineParam(minLineLen=minlen, scanIntervals=scan))
+        c.linematch_configure(vpl.capi.LineMatchParam(max_anchors=16384))
+        lines, p2c = c.linefront_batch(frames, smoothed=False)
+    exp_lines = [orc.edline_detect(f, pe, False) for f in frames]
+    matched = 0
+    for f in range(len(frames)):
+        assert lines[f].tobytes() == exp_lines[f].tobytes(), f"lines {f}"
+        if f:
+            exp = orc.line_matching(frames[f - 1], frames[f], exp_lines[f - 1], exp_lines[f])
+            if exp is None:
+                assert (p2c[f] == -1).all()
+            else:
+                assert np.array_equal(p2c[f], exp), f"match {f}"
+                matched += int((exp >= 0).sum())
+    assert sum(len(l) for l in exp_lines) > 0
+
+
+def test_linematch_non_default_parameters(ctx, vpl, orc, mh04):
+    """step 6, looser thresholds, 2 pyramid levels, 10 iterations: the parameter plumbing."""
+    kw = dict(step=6, closest_line_threshold=1.0, line_matching_ratio=0.3, line_distance_error_ratio=2.0,
+              klt_error_threshold=25.0, max_level=1, max_count=10, epsilon=0.01, min_eig=1e-3,
+              topo_distance_threshold=10.0, topo_length_ratio=0.3, topo_violation_ratio=0.1)
+    ctx.linematch_configure(vpl.capi.LineMatchParam(max_anchors=8192, **kw))
+    p = orc.EDLineParam()
+    la, lb = orc.edline_detect(mh04[4], p, True), orc.edline_detect(mh04[5], p, True)
+    got = ctx.linematch_batch([mh04[4]], [mh04[5]], [as_capi(vpl, la)], [as_capi(vpl, lb)])[0]
+    d = ctx.linematch_points(0)
+    exp, de = orc.line_matching(mh04[4], mh04[5], la, lb, param=orc.LineMatchParam(**kw), details=True)
+    for k in ("kps_ref", "kps_cur", "status", "err", "kp2line"):
+        assert same_bits(d[k], de[k]), k
+    assert np.array_equal(got, exp) and (exp >= 0).sum() > 20
