@@ -91,8 +91,7 @@ __global__ void ed_anchor_kernel(const uint16_t* __restrict__ gmap, unsigned* __
 
 // ---- smart routing ---------------------------------------------------------------------------
 struct WalkMem {
-  unsigned last_x, last_y;  // ed.cpp:184-185
-  int pfx, pfy;             // centre of the last prefetched strip
+  int pfx, pfy;  // centre of the last prefetched strip
 };
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -118,50 +117,52 @@ __device__ __forceinline__ void ed_prefetch_strip(const uint16_t* __restrict__ g
 // lockstep on identical state (SIMT issues one instruction stream either way; the loads are
 // broadcasts).  Every lane stores the edge mark it will read back later; lane 0 records the pixel.
 // Returns the number of pixels recorded, or -1 if `cap` would be exceeded.
-__device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsigned x, unsigned y, int last_dir,
+//
+// The reference's four-way case analysis is folded into arithmetic on a direction code
+// (0 right, 1 left, 2 down, 3 up; bit 1 = vertical, bit 0 = negative):
+//   - a horizontal pixel reached by a vertical move (or the reverse) turns towards the side the last
+//     move drifted to: the reference tests `x > lastX` / `y > lastY`, and lastX/lastY always hold the
+//     previous pixel of the same walk when they are read, so that is the sign of the last step;
+//   - the three candidates are idx + dmain + {dperp, 0, -dperp}: for a horizontal move dmain = +-1 and
+//     candidate 1 is the upper one (dperp = -W), for a vertical move dmain = +-W and candidate 1 is
+//     the right one (dperp = +1), exactly the reference's gValue1 / gValue2 / gValue3.
+//
+// (Tried and dropped: edge marks as a bitmap in shared memory with a read-only gradient map.  The
+// step time is the dependent ALU chain, not the loads, and 45 KB per walker cuts the walkers per SM
+// from 28 to 4: 10 ms -> 39 ms per 4096 frames.)
+__device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsigned x0, unsigned y0, int last_dir,
                                     uint32_t* __restrict__ out, int cap, WalkMem& wm, int lane) {
   int n = 0;
-  int idx = (int)y * W + (int)x;
+  int x = (int)x0, y = (int)y0;
+  int idx = y * W + x;
   unsigned v = g[idx];
+  int ld = last_dir == RIGHT ? 0 : last_dir == LEFT ? 1 : last_dir == DOWN ? 2 : 3;
+  int ddx = 0, ddy = 0;  // last step (never read before the first step has set it)
   while ((v & kG) != 0 && !(v & kEdge)) {
     if (n >= cap) return -1;
     g[idx] = (uint16_t)(v | kEdge);
-    if (lane == 0) out[n] = x | (y << 16);
+    if (lane == 0) out[n] = (unsigned)x | ((unsigned)y << 16);
     n++;
-    int should_go = 0;
-    int dmain, dperp, mx, my, px, py;
-    if (v & kDir) {  // horizontal pixel: go left or right
-      if (last_dir == UP || last_dir == DOWN) should_go = x > wm.last_x ? RIGHT : LEFT;
-      wm.last_x = x; wm.last_y = y;
-      if (last_dir == RIGHT || should_go == RIGHT) {
-        if (x == (unsigned)W - 1 || y == 0 || y == (unsigned)H - 1) break;
-        mx = 1; last_dir = RIGHT;
-      } else {
-        if (x == 0 || y == 0 || y == (unsigned)H - 1) break;
-        mx = -1; last_dir = LEFT;
-      }
-      my = 0; px = 0; py = -1;  // candidate 1 = up-, candidate 3 = down-
-      dmain = mx; dperp = -W;
-    } else {  // vertical pixel: go up or down
-      if (last_dir == RIGHT || last_dir == LEFT) should_go = y > wm.last_y ? DOWN : UP;
-      wm.last_x = x; wm.last_y = y;
-      if (last_dir == DOWN || should_go == DOWN) {
-        if (x == 0 || x == (unsigned)W - 1 || y == (unsigned)H - 1) break;
-        my = 1; last_dir = DOWN;
-      } else {
-        if (x == 0 || x == (unsigned)W - 1 || y == 0) break;
-        my = -1; last_dir = UP;
-      }
-      mx = 0; px = 1; py = 0;  // candidate 1 = -right, candidate 3 = -left
-      dmain = my * W; dperp = 1;
-    }
-    int i2 = idx + dmain;
-    unsigned v1 = g[i2 + dperp], v2 = g[i2], v3 = g[i2 - dperp];
-    ed_prefetch_strip(g, W, H, (int)x, (int)y, mx, my, lane, wm);
-    unsigned g1 = v1 & 0xffu, g2 = v2 & 0xffu, g3 = v3 & 0xffu;  // the (unsigned char) casts, ed.cpp:231-233
-    if (g1 >= g2 && g1 >= g3) { x += mx + px; y += my + py; idx = i2 + dperp; v = v1; }
-    else if (g3 >= g2 && g3 >= g1) { x += mx - px; y += my - py; idx = i2 - dperp; v = v3; }
-    else { x += mx; y += my; idx = i2; v = v2; }
+    const int h = (int)(v >> 15) & 1;  // 1 = horizontal pixel
+    int go = ld;
+    if (h == (ld >> 1)) go = h ? (ddx > 0 ? 0 : 1) : (ddy > 0 ? 2 : 3);  // ed.cpp:217-223 / :264-270
+    const int sgn = 1 - 2 * (go & 1);
+    const bool hz = go < 2;
+    // image border: the three candidates must exist (ed.cpp:227, :245, :274, :292)
+    const int a = hz ? x : y, amax = hz ? W : H, bq = hz ? y : x, bmax = hz ? H : W;
+    if ((unsigned)(a + sgn) >= (unsigned)amax || (unsigned)(bq - 1) >= (unsigned)(bmax - 2)) break;
+    const int dmain = hz ? sgn : sgn * W, dperp = hz ? -W : 1;
+    const int i2 = idx + dmain;
+    const unsigned v1 = g[i2 + dperp], v2 = g[i2], v3 = g[i2 - dperp];
+    if ((n & 3) == 0) ed_prefetch_strip(g, W, H, x, y, hz ? sgn : 0, hz ? 0 : sgn, lane, wm);
+    const unsigned g1 = v1 & 0xffu, g2 = v2 & 0xffu, g3 = v3 & 0xffu;  // the (unsigned char) casts, ed.cpp:231-233
+    const int sel = (g1 >= g2 && g1 >= g3) ? 1 : ((g3 >= g2 && g3 >= g1) ? -1 : 0);
+    idx = i2 + sel * dperp;
+    v = sel > 0 ? v1 : (sel < 0 ? v3 : v2);
+    ddx = hz ? sgn : sel;
+    ddy = hz ? -sel : sgn;
+    x += ddx; y += ddy;
+    ld = go;
   }
   return n;
 }
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(32) ed_walk_kernel(EdBuffers B, EdGeom G, int 
   int status = 1;
   if (B.n_anchor[f] > G.cap_px) status = -1;  // ed.cpp:166-169
   int off1 = 0, off2 = 0, n_edge = 0, k = 0;
-  WalkMem wm = {0u, 0u, -1000000, -1000000};
+  WalkMem wm = {-1000000, -1000000};
   for (int base = 0; status == 1 && base < G.bm_words; base += 32) {
     // expand the set bits of 32 words into the anchor list (column-major order = bit order)
     unsigned word = (base + lane < G.bm_words) ? bm[base + lane] : 0u;
@@ -531,6 +532,7 @@ void launch_ed_anchor(const EdBuffers& B, const EdGeom& G, int anchor_thresh, in
 
 void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st) {
   ed_walk_kernel<<<batch, 32, 0, st>>>(B, G, G.min_len, batch);
+
 }
 
 void launch_ed_fit(const EdBuffers& B, const EdGeom& G, double fit_thr, const short2* grad, const double* lgam,
