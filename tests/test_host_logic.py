@@ -52,6 +52,71 @@ class OracleContext:
             matches[i, :len(k_)] = m
 
 
+class OracleLineContext:
+    """Quacks like capi.Context's linefront_submit / linefront_collect_into, computing with the oracle
+    restatement of the reference's EDLines + LineMatching."""
+
+    def __init__(self, orc, capi, max_batch=4, num_slots=2, max_lines=512):
+        self.orc, self.capi = orc, capi
+        self.max_batch, self.num_slots, self.max_lines = max_batch, num_slots, max_lines
+        self.pending = {}
+        self.submitted = []
+        self.param = orc.EDLineParam(minLineLen=15)
+
+    def linefront_submit(self, slot, frames, smoothed=True):
+        assert slot not in self.pending and 1 <= len(frames) <= self.max_batch
+        lines = [self.orc.edline_detect(f, self.param, smoothed) for f in frames]
+        p2c = [None] + [self.orc.line_matching(frames[i - 1], frames[i], lines[i - 1], lines[i]) for i in range(1, len(frames))]
+        self.pending[slot] = (lines, p2c)
+        self.submitted.append(len(frames))
+        return len(frames)
+
+    def linefront_collect_into(self, slot, lines, counts, cap, p2c):
+        ls, ms = self.pending.pop(slot)
+        p2c[:] = -1
+        for i, l in enumerate(ls):
+            counts[i] = len(l)
+            lines[i, :len(l)] = l.view(self.capi.LINE_DTYPE)
+            if i and ms[i] is not None:
+                p2c[i, :len(ms[i])] = ms[i]
+
+
+def _line_front_expected(orc, frames, param):
+    lines = [orc.edline_detect(f, param, True) for f in frames]
+    p2c = [np.zeros(0, np.int32)]
+    for i in range(1, len(frames)):
+        m = orc.line_matching(frames[i - 1], frames[i], lines[i - 1], lines[i])
+        p2c.append(np.full(len(lines[i - 1]), -1, np.int32) if m is None else m)
+    return lines, p2c
+
+
+def test_line_front_driver_overlaps_batches_by_one_frame(vpl, orc, synth):
+    frames = synth.sequence(8, w=192, h=128, seed=6, n_quads=6, n_strokes=10)
+    ctx = OracleLineContext(orc, vpl.capi, max_batch=3, num_slots=2)
+    lines, p2c = vpl.LineFrontEnd(ctx).run(frames)
+    # 8 frames in batches of 3 with a one-frame overlap: [0,1,2] [2,3,4] [4,5,6] [6,7]
+    assert ctx.submitted == [3, 3, 3, 2] and len(lines) == 8
+    el, em = _line_front_expected(orc, frames, ctx.param)
+    for f in range(8):
+        assert lines[f].tobytes() == el[f].tobytes()
+        assert np.array_equal(p2c[f], em[f]), f
+
+
+def test_line_front_sharded_run_equals_single_run(vpl, orc, synth):
+    frames = synth.sequence(9, w=160, h=120, seed=9, n_quads=5, n_strokes=8)
+    el, em = _line_front_expected(orc, frames, orc.EDLineParam(minLineLen=15))
+    for world in (1, 2, 3):
+        lines, p2c = [], []
+        for r in range(world):
+            s, e, halo = vpl.shard_range(len(frames), r, world)
+            a, b = vpl.LineFrontEnd(OracleLineContext(orc, vpl.capi, max_batch=4)).run(frames, s, e, halo)
+            lines += a
+            p2c += b
+        assert len(lines) == 9
+        for f in range(9):
+            assert lines[f].tobytes() == el[f].tobytes() and np.array_equal(p2c[f], em[f]), (world, f)
+
+
 def test_shard_range_partitions_every_pair_once(vpl):
     for n in (1, 2, 7, 100, 20000):
         for world in (1, 2, 3, 4, 8):
@@ -114,8 +179,11 @@ def _gloo_worker(rank, world, port, q):
     frames = synth.sequence(6, w=160, h=120, seed=21, n_quads=5, n_strokes=8)
     s, e, halo = vpl.shard_range(len(frames), rank, world)
     kls, descs, ms = vpl.FrontEnd(OracleContext(O, vpl.capi, max_batch=2), k=1).run(frames, s, e, halo)
+    # the reference's real front end (EDLines + KLT line matching) through the same sharding
+    ll, pp = vpl.LineFrontEnd(OracleLineContext(O, vpl.capi, max_batch=3)).run(frames, s, e, halo)
     # no data-path collective: the host only gathers results (here: per-frame line counts and match sums)
-    mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum())] for k, m in zip(kls, ms)], dtype=torch.int64)
+    mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())]
+                         for k, m, l, p in zip(kls, ms, ll, pp)], dtype=torch.int64)
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64))
     pad = torch.zeros((len(frames), 2), dtype=torch.int64)
@@ -141,5 +209,7 @@ def test_two_rank_gloo_gather(vpl, orc, synth):
         assert p.exitcode == 0
     frames = synth.sequence(6, w=160, h=120, seed=21, n_quads=5, n_strokes=8)
     kls, descs, ms = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=8), k=1).run(frames)
-    exp = np.array([[len(k), int(m["trainIdx"].astype(np.int64).sum())] for k, m in zip(kls, ms)])
+    ll, pp = vpl.LineFrontEnd(OracleLineContext(orc, vpl.capi, max_batch=8)).run(frames)
+    exp = np.array([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())]
+                    for k, m, l, p in zip(kls, ms, ll, pp)])
     assert np.array_equal(got, exp)

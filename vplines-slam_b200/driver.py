@@ -64,3 +64,53 @@ class FrontEnd:
         while pending:
             collect(*pending.pop(0))
         return out_kl, out_desc, out_m
+
+
+class LineFrontEnd:
+    """The reference's real per-frame loop (EDline on every frame + Matching(prev, cur),
+    line_feature_tracker.cpp:87, :115) over a frame sequence through Context.linefront_submit /
+    linefront_collect_into.  Batches, and shards of different ranks, overlap by one frame (the
+    device matches frame f against frame f-1 inside a batch), so that every consecutive pair of the
+    sequence is matched exactly once and no state crosses batches."""
+
+    def __init__(self, ctx, smoothed=True):
+        self.ctx = ctx
+        self.smoothed = smoothed
+
+    def run(self, frames, start=0, end=None, halo=0):
+        """Frames [start, end) (plus `halo` frames in front, only there to be matched against).
+        Returns (lines per frame, prev_to_cur per frame); the match row of frame 0 of the sequence
+        is empty."""
+        ctx = self.ctx
+        end = len(frames) if end is None else end
+        lo = start - halo
+        B, S, cap = ctx.max_batch, ctx.num_slots, ctx.max_lines
+        assert B >= 2, "a batch must hold the overlap frame and at least one new frame"
+        bufs = [dict(lines=np.zeros((B, cap), capi.LINE_DTYPE), counts=np.zeros(B, np.int32),
+                     p2c=np.zeros((B, cap), np.int32)) for _ in range(S)]
+        out_lines, out_p2c = [], []
+        pending = []  # (slot, first_frame, n, first_is_overlap)
+
+        def collect(slot, f0, n, overlap):
+            b = bufs[slot]
+            ctx.linefront_collect_into(slot, b["lines"], b["counts"], cap, b["p2c"])
+            for i in range(1 if overlap else 0, n):
+                c = b["counts"][i]
+                out_lines.append(b["lines"][i, :c].copy())
+                out_p2c.append(b["p2c"][i, :b["counts"][i - 1]].copy() if i else b["p2c"][0, :0].copy())
+
+        slot = 0
+        f = start         # next frame whose results are still to be produced
+        while f < end:
+            overlap = f > lo              # a frame to match against precedes f: start the batch on it
+            first = f - 1 if overlap else f
+            n = min(B, end - first)
+            if len(pending) == S:
+                collect(*pending.pop(0))
+            ctx.linefront_submit(slot, frames[first:first + n], smoothed=self.smoothed)
+            pending.append((slot, first, n, overlap))
+            slot = (slot + 1) % S
+            f = first + n
+        while pending:
+            collect(*pending.pop(0))
+        return out_lines, out_p2c
