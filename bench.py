@@ -339,8 +339,8 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
         # tracker: per anchor, level and iteration one 14x14 u8 window (196 B) + once per level the
         # 14x14 Scharr window (784 B) and the reference window: ~ 4 levels x (980 + ~8 x 196) B
         alg.update({"lm_pyramid": 11.5 * P, "lm_track": anchors * 4 * (980.0 + 8 * 196.0), "lm_vote": anchors * 24.0})
-        launches_of.update({"lm_pyramid": 8, "lm_track": 5, "lm_vote": 1})
-        kernels_of.update({"lm_pyramid": "klt_level0/pyrdown/scharr kernels", "lm_track": "lm_anchor_kernel+klt_track_kernel",
+        launches_of.update({"lm_pyramid": 8, "lm_track": 6, "lm_vote": 1})
+        kernels_of.update({"lm_pyramid": "klt_level0/pyrdown/scharr kernels", "lm_track": "klt_track_kernel x4 levels (+ anchors, offsets)",
                            "lm_vote": "lm_vote_kernel"})
     ed = {k: stage[k] for k in alg}
     dom = max(ed, key=lambda k: ed[k][0])
@@ -349,8 +349,15 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     dur = ed[dom][0] / max(ed[dom][1] / launches_in_stage, 1)
     achieved = alg[dom] * B / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
     tot = max(sum(x[0] for x in stage.values()), 1e-9)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "klt_track_traffic.json")
+    if dom == "lm_track" and os.path.exists(tp) and wl["frames"] == "C2":
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (4 level launches), per frame
+            traffic = float(json.load(open(tp))["dram_bytes_per_frame"]) * B
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": kernels_of[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "ms_per_launch": dur,
                 "algorithmic_bytes_per_launch": alg[dom] * B,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items() if v[1]},
