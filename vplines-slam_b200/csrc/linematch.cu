@@ -40,8 +40,18 @@ constexpr int NWIN = WIN * WIN;
 constexpr int W_BITS = 14;
 #define LM_DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))  // CV_DESCALE, klt.h:39
 
-// exact int -> float for |v| < 2^22 without the conversion unit: 1.5 * 2^23 + v is exact
-__device__ __forceinline__ float small_int_to_float(int v) { return __int_as_float(0x4B400000 + v) - 12582912.0f; }
+// two unsigned 16-bit integers (lo | hi << 16) -> two floats, minus `bias`, without the conversion
+// unit: the 16 bits are spliced under the exponent of 1.5 * 2^23 (exact), then ONE packed add
+// subtracts 1.5 * 2^23 + bias from both (exact: every value involved is an integer below 2^24).
+__device__ __forceinline__ void u16x2_to_float(unsigned packed, float neg_magic_bias, float& lo, float& hi) {
+  const unsigned a = __byte_perm(packed, 0x4B400000u, 0x7610), b = __byte_perm(packed, 0x4B400000u, 0x7632);
+  unsigned long long in, nb, out;
+  const unsigned nbits = __float_as_uint(neg_magic_bias);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(in) : "r"(a), "r"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nb) : "r"(nbits));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(out) : "l"(in), "l"(nb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(out));
+}
 
 __device__ __forceinline__ int cv_floor_d(float v) {  // SSE cvFloor: INT_MIN on NaN / overflow
   if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
@@ -172,9 +182,10 @@ __device__ __forceinline__ Wts lk_weights(float a, float b) {  // lk2d.cpp:109-1
 // bilinear 13x13 window of a padded u8 level at integer corner (ix, iy): every source byte is read
 // once; the sums are exact integers, so blending rows first changes nothing (lk2d.cpp:338-348).
 // Also returns the window's integer sum and sum of squares (for cv::meanStdDev).
-// Window element t of lane l lives at win[t * 32 + l] (shared memory, conflict-free).
+// Window element t of lane l lives in the 32-bit word win[t * 32 + l] (shared memory, conflict-free):
+// reference patch in the low half, current patch in the high half; `out` points at the lane's half.
 __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, int st, int ix, int iy, const Wts& w,
-                                             short* __restrict__ out, int& sum, long long& sq) {
+                                             unsigned short* __restrict__ out, int& sum, long long& sq) {
   int top[WIN];
   sum = 0;
   sq = 0;
@@ -202,7 +213,7 @@ __device__ __forceinline__ void lk_sample_u8(const uint8_t* __restrict__ img, in
       int b = prev * w.w10 + cur * w.w11;   // ... and as the lower row of window row r-1
       if (r > 0) {
         int v = LM_DESCALE(top[x] + b, W_BITS - 5);
-        out[((r - 1) * WIN + x) * 32] = (short)v;
+        out[((r - 1) * WIN + x) * 64] = (unsigned short)v;
         sum += v;
         rq += (unsigned)(v * v);
       }
@@ -262,9 +273,10 @@ __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict
                                                        int n_pairs, int kRefill) {
   extern __shared__ __align__(16) unsigned char s_win[];
   const int lane = threadIdx.x;
-  short* Iw = reinterpret_cast<short*>(s_win) + lane;
-  short* Jw = Iw + NWIN * 32;
-  short2* dIw = reinterpret_cast<short2*>(s_win + NWIN * 32 * 4) + lane;
+  unsigned* IJw = reinterpret_cast<unsigned*>(s_win) + lane;          // {I, J} as two u16 (values 0..8160)
+  unsigned short* Iw = reinterpret_cast<unsigned short*>(IJw);
+  unsigned short* Jw = Iw + 1;
+  unsigned* dIw = reinterpret_cast<unsigned*>(s_win + NWIN * 32 * 4) + lane;  // {dIx, dIy} + 32768 as two u16
   const int total = B.pair_off[n_pairs];
   int* queue = B.queue + level;
   const int st = G.stride[level], lw = G.w[level], lh = G.h[level];
@@ -346,10 +358,14 @@ __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict
                 int t1 = pv.y * w.w00 + cv.y * w.w01, b1 = pv.y * w.w10 + cv.y * w.w11;
                 if (r > 0) {
                   int ixv = LM_DESCALE(tx[x] + b0, W_BITS), iyv = LM_DESCALE(ty[x] + b1, W_BITS);
-                  dIw[((r - 1) * WIN + x) * 32] = make_short2((short)ixv, (short)iyv);
-                  iA11 += (float)(ixv * ixv);
-                  iA12 += (float)(ixv * iyv);
-                  iA22 += (float)(iyv * iyv);
+                  dIw[((r - 1) * WIN + x) * 32] = (unsigned)(ixv + 32768) | ((unsigned)(iyv + 32768) << 16);
+                  // |ixv|, |iyv| <= 4080 (Scharr of u8, convex blend): the products are below 2^24, so the
+                  // float product of the converted factors IS (float)(ixval * ixval) -- no I2F needed
+                  const float fx = __int_as_float(0x4B400000 + ixv) - 12582912.0f;
+                  const float fy = __int_as_float(0x4B400000 + iyv) - 12582912.0f;
+                  iA11 += fx * fx;
+                  iA12 += fx * fy;
+                  iA22 += fy * fy;
                 }
                 tx[x] = t0; ty[x] = t1;
                 pv = cv;
@@ -401,10 +417,12 @@ __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict
         float ib1 = 0, ib2 = 0, errval = 0;
 #pragma unroll 13
         for (int t = 0; t < NWIN; t++) {  // lk2d.cpp:364-376 and :467-476, each sum in (y, x) order
-          float diff = alpha * small_int_to_float(Jw[t * 32]) + beta - small_int_to_float(Iw[t * 32]);
-          short2 d = dIw[t * 32];
-          ib1 += diff * small_int_to_float(d.x);
-          ib2 += diff * small_int_to_float(d.y);
+          float fi, fj, fdx, fdy;
+          u16x2_to_float(IJw[t * 32], -12582912.0f, fi, fj);
+          u16x2_to_float(dIw[t * 32], -(12582912.0f + 32768.0f), fdx, fdy);
+          float diff = alpha * fj + beta - fi;
+          ib1 += diff * fdx;
+          ib2 += diff * fdy;
           errval += fabsf(diff);
         }
         if (phase == 2) {
