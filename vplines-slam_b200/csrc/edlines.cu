@@ -37,6 +37,7 @@ constexpr unsigned kDir = 0x8000u;   // set = Horizontal (|dx| < |dy|), ed.cpp:5
 enum { UP = 1, RIGHT = 2, DOWN = 3, LEFT = 4 };  // ed.cpp:7-10
 constexpr int kTryTime = 6;                      // ed.cpp:11
 constexpr int kSkipEdgePoint = 2;                // ed.cpp:12
+constexpr unsigned kSearchMaxLen = 160;          // longest minLineLen handled by the lane-parallel window search
 
 __device__ __forceinline__ unsigned gmap_value(short2 d, int grad_thresh) {
   int ax = abs((int)d.x), ay = abs((int)d.y);
@@ -320,6 +321,7 @@ __device__ __forceinline__ void ed_fit_solve(const float a[4], const float v[2],
 __global__ void __launch_bounds__(128) ed_fit_kernel(EdBuffers B, EdGeom G, int min_len, double thr,
                                                      const short2* __restrict__ grad, const double* __restrict__ lgam) {
   __shared__ double s_sq[4][32];
+  __shared__ uint32_t s_pts[4][64 + kSearchMaxLen];
   const int f = blockIdx.y;
   if (B.status[f] != 1) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(128) ed_fit_kernel(EdBuffers B, EdGeom G, int 
   uint8_t* valid = B.slot_valid + (size_t)f * G.nslots;
   const unsigned m = (unsigned)min_len;
   double* sq = s_sq[warp];
+  uint32_t* spts = s_pts[warp];
 
   for (int e = blockIdx.x * 4 + warp; e < n_chain; e += gridDim.x * 4) {
     unsigned S = sid[e];
@@ -340,7 +343,64 @@ __global__ void __launch_bounds__(128) ed_fit_kernel(EdBuffers B, EdGeom G, int 
     float ata[4], atv[2];
     while (E > S + m) {  // ed.cpp:987
       bool horizontal = false;
-      while (E > S + m) {  // find an initial segment, ed.cpp:989-995
+      if (m <= kSearchMaxLen) {
+        // find an initial segment, ed.cpp:989-995.  The reference tries the windows starting at
+        // S, S+2, S+4, ... one after the other and stops at the first whose fit error passes; the
+        // windows are independent, so the 32 lanes try 32 consecutive starts at once (each lane its
+        // own exact integer sums and its own in-order residual sum) and the lowest passing lane wins.
+        bool found = false;
+        while (E > S + m) {
+          const unsigned span = min(E - S, 62u + m);
+          for (unsigned i = lane; i < span; i += 32) spts[i] = xy[S + i];
+          __syncwarp();
+          const unsigned o = 2u * lane;
+          const bool cand = E > S + o + m;
+          bool hz = false;
+          double q0 = 0, q1 = 0, ferr = 0;
+          float a[4] = {0, 0, 0, 0}, v2[2] = {0, 0};
+          if (cand) {
+            const unsigned p0 = spts[o];
+            hz = (g[(p0 >> 16) * G.w + (p0 & 0xffff)] & kDir) != 0;
+            int su = 0, sv = 0;
+            long long luu = 0, luv = 0;
+            for (unsigned i = 0; i < m; i++) {
+              const unsigned p = spts[o + i];
+              const int x = p & 0xffff, y = p >> 16;
+              const int u = hz ? x : y, vv = hz ? y : x;
+              luu += (long long)u * u; luv += (long long)u * vv; su += u; sv += vv;
+            }
+            a[0] = (float)(double)luu; a[1] = (float)(double)su; a[2] = a[1]; a[3] = (float)(double)(int)m;
+            v2[0] = (float)(double)luv; v2[1] = (float)(double)sv;
+            ed_fit_solve(a, v2, q0, q1);
+            double err = 0;  // squared residuals in pixel order, ed.cpp:767-770
+            for (unsigned i = 0; i < m; i++) {
+              const unsigned p = spts[o + i];
+              const double x = (double)(p & 0xffff), y = (double)(p >> 16);
+              const double c = hz ? y - x * q0 - q1 : x - y * q0 - q1;
+              err += c * c;
+            }
+            ferr = sqrt(err);
+          }
+          const unsigned okm = __ballot_sync(0xffffffffu, cand && ferr <= thr);
+          const unsigned candm = __ballot_sync(0xffffffffu, cand);
+          __syncwarp();
+          if (okm) {
+            const int l = __ffs(okm) - 1;
+            S += 2u * (unsigned)l;
+            eq0 = __shfl_sync(0xffffffffu, q0, l); eq1 = __shfl_sync(0xffffffffu, q1, l);
+            fit_err = __shfl_sync(0xffffffffu, ferr, l);
+#pragma unroll
+            for (int t = 0; t < 4; t++) ata[t] = __shfl_sync(0xffffffffu, a[t], l);
+            atv[0] = __shfl_sync(0xffffffffu, v2[0], l); atv[1] = __shfl_sync(0xffffffffu, v2[1], l);
+            horizontal = __shfl_sync(0xffffffffu, (int)hz, l) != 0;
+            found = true;
+            break;
+          }
+          S += 2u * (unsigned)__popc(candm);  // every candidate of this round failed
+        }
+        if (!found) break;  // the last attempt failed: lineFitErr > threshold, ed.cpp:996
+      } else {
+      while (E > S + m) {  // find an initial segment, ed.cpp:989-995 (window too long for the lane-parallel search)
         unsigned p0 = xy[S];
         horizontal = (g[(p0 >> 16) * G.w + (p0 & 0xffff)] & kDir) != 0;
         ed_normal_sums(xy, S, S + m, horizontal, lane, ata, atv);
@@ -366,6 +426,7 @@ __global__ void __launch_bounds__(128) ed_fit_kernel(EdBuffers B, EdGeom G, int 
         fit_err = sqrt(err);
         if (fit_err <= thr) break;
         S += kSkipEdgePoint;
+      }
       }
       if (fit_err > thr) break;  // ed.cpp:996
       // extend, ed.cpp:1008-1039 / :1090-1120
