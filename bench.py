@@ -326,13 +326,11 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     # roofline of the dominant EDLines kernel; algorithmic bytes per frame:
     P = W * H
     edge_px = float(len(xy0))  # frame 0 of the last batch (frames are a tiling of `unique`)
-    alg = {"ed_grad": 12.0 * P,                                   # blur/copy+Sobel: r P, w P + 4P; gmap: r 4P, w 2P
-           "ed_anchor": 6.0 * P / (param.scanIntervals ** 2) + P / (param.scanIntervals ** 2) / 8,
+    alg = {"ed_grad": 7.0 * P,                                    # Sobel + map + anchors, one pass: r P, w 4P + 2P
            "ed_walk": 20.0 * edge_px,                              # 3 u16 reads + mark + record, re-pack r+w
            "ed_fit": 20.0 * edge_px}                               # chain pixel 3 x 4 B + Sobel pair 2 x 4 B
-    launches_of = {"ed_grad": 2, "ed_anchor": 1, "ed_walk": 1, "ed_fit": 2}
-    kernels_of = {"ed_grad": "blur5_sobel_kernel+ed_gmap_kernel", "ed_anchor": "ed_anchor_kernel",
-                  "ed_walk": "ed_walk_kernel", "ed_fit": "ed_fit_kernel+ed_compact_kernel"}
+    launches_of = {"ed_grad": 1, "ed_walk": 1, "ed_fit": 2}
+    kernels_of = {"ed_grad": "ed_grad_anchor_kernel", "ed_walk": "ed_walk_kernel", "ed_fit": "ed_fit_kernel+ed_compact_kernel"}
     if match:
         # padded pyramid (4 levels, 13-px border) ~ 1.5 P bytes: written once, read by the next level and by
         # the Scharr pass, which writes 4 B per padded pixel: ~ 1 + 3 x 1.5 + 6 = 11.5 P;

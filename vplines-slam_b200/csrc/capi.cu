@@ -561,14 +561,16 @@ void run_edlines(VplContext* c, Slot& s) {
   cudaMemsetAsync(s.d_flags + 2, 0, sizeof(int), s.stream);
   {
     StageTimer t(c, s, VPL_STAGE_ED_GRAD);
-    // Sobel pair (and the 5x5 blur when the caller's image is not smoothed yet), ed.cpp:82-126
-    launch_blur5_sobel(s.d_img, s.oct[0].pyr, s.oct[0].grad, s.w, s.h, s.n, s.ed_smoothed ? 0 : 1, s.stream);
-    launch_ed_gmap(s.oct[0].grad, s.ed.gmap, (size_t)s.n * s.w * s.h, (int)(short)p.gradientThreshold, s.stream);
-    t.launches(2);
-  }
-  {
-    StageTimer t(c, s, VPL_STAGE_ED_ANCHOR);
-    launch_ed_anchor(s.ed, G, (int)(unsigned char)p.anchorThreshold, s.n, s.stream);
+    // ed.cpp:82-83: the 5x5 blur only when the caller's image is not smoothed yet (-> oct[0].pyr);
+    // then Sobel pair + gradient map + anchors in one pass (ed.cpp:125-164)
+    const uint8_t* smooth = s.d_img;
+    if (!s.ed_smoothed) {
+      launch_blur5_sobel(s.d_img, s.oct[0].pyr, s.oct[0].grad, s.w, s.h, s.n, 1, s.stream);
+      smooth = s.oct[0].pyr;
+      t.launches(1);
+    }
+    launch_ed_grad_anchor(smooth, s.oct[0].grad, s.ed, G, (int)(short)p.gradientThreshold,
+                          (int)(unsigned char)p.anchorThreshold, s.n, s.stream);
     t.launches(1);
   }
   {

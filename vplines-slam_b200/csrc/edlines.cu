@@ -6,9 +6,9 @@
 // oracle/orc_edlines.c (pinned bit for bit against the reference's own code).
 //
 // Stages (batch of B frames, all of them one launch over the whole batch):
-//   ed_gmap_kernel    |dx|+|dy| -> threshold -> /4 (round half even) + direction bit, one u16 per
-//                     pixel, from the Sobel pair the pyramid kernel already wrote   (ed.cpp:128-136)
-//   ed_anchor_kernel  anchor test on the scan grid -> column-major bitmap           (ed.cpp:148-164)
+//   ed_grad_anchor_kernel  Sobel pair, |dx|+|dy| -> threshold -> /4 (round half even) + direction bit
+//                     (one u16 per pixel) and the anchor test on the scan grid -> column-major
+//                     bitmap, one tiled pass over the image                          (ed.cpp:125-164)
 //   ed_walk_kernel    smart routing.  Chains are claimed in anchor order and a walk stops at any
 //                     earlier edge pixel, so it is sequential per frame: ONE WARP PER FRAME.  The warp
 //                     expands the anchor bitmap 32 words at a time, tests 32 anchors for "already
@@ -48,46 +48,112 @@ __device__ __forceinline__ unsigned gmap_value(short2 d, int grad_thresh) {
   return (unsigned)q | (ax < ay ? kDir : 0u);
 }
 
-__global__ void ed_gmap_kernel(const short2* __restrict__ grad, uint16_t* __restrict__ gmap, size_t total,
-                               int grad_thresh) {
-  size_t quads = total >> 2;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += stride) {
-    int4 v = reinterpret_cast<const int4*>(grad)[i];
-    short2 a = *reinterpret_cast<short2*>(&v.x), b = *reinterpret_cast<short2*>(&v.y);
-    short2 c = *reinterpret_cast<short2*>(&v.z), d = *reinterpret_cast<short2*>(&v.w);
-    uint2 o;
-    o.x = gmap_value(a, grad_thresh) | (gmap_value(b, grad_thresh) << 16);
-    o.y = gmap_value(c, grad_thresh) | (gmap_value(d, grad_thresh) << 16);
-    reinterpret_cast<uint2*>(gmap)[i] = o;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
-    size_t i = (quads << 2) + threadIdx.x;
-    gmap[i] = (uint16_t)gmap_value(grad[i], grad_thresh);
-  }
+// Sobel pair, gradient map and anchor bitmap in one pass over the (already smoothed) image
+// (ed.cpp:125-164).  A CTA takes a 64x16 tile: the image tile with a 2-pixel REFLECT_101 halo goes to
+// shared memory, the map is computed on the tile plus a 1-pixel ring (an anchor compares with its
+// neighbours' map values), and only grid points inside the tile are tested.
+// Bit (ix*nH + iy) of the frame's bitmap = anchor at (1 + ix*scan, 1 + iy*scan): the bitmap is in
+// the reference's column-major visiting order.
+constexpr int GT_W = 64, GT_H = 16, GT_THREADS = 256;
+constexpr int GT_SW = GT_W + 8;  // shared image row: columns x0-4 .. x0+GT_W+3 (word aligned)
+
+__device__ __forceinline__ short2 sobel_at(const uint8_t* p) {  // p -> centre pixel in s_img
+  const int a = p[-GT_SW - 1], b = p[-GT_SW], c = p[-GT_SW + 1], d = p[-1], e = p[1];
+  const int g = p[GT_SW - 1], h = p[GT_SW], i = p[GT_SW + 1];
+  return make_short2((short)((c + 2 * e + i) - (a + 2 * d + g)), (short)((g + 2 * h + i) - (a + 2 * b + c)));
 }
 
-// one thread per scan-grid point, x fastest (coalesced reads); bit (ix*nH + iy) of the frame's
-// bitmap = anchor, i.e. the bitmap is in the reference's column-major visiting order
-__global__ void ed_anchor_kernel(const uint16_t* __restrict__ gmap, unsigned* __restrict__ bitmap,
-                                 int* __restrict__ n_anchor, EdGeom G, int anchor_thresh) {
-  int f = blockIdx.y;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= G.nW * G.nH) return;
-  int iy = t / G.nW, ix = t - iy * G.nW;
-  int x = 1 + ix * G.scan, y = 1 + iy * G.scan;
-  const uint16_t* g = gmap + (size_t)f * G.w * G.h;
-  int i = y * G.w + x;
-  unsigned v = g[i];
-  int gv = v & kG;
-  int a, b;
-  if (v & kDir) { a = g[i - G.w] & kG; b = g[i + G.w] & kG; }
-  else { a = g[i - 1] & kG; b = g[i + 1] & kG; }
-  if (gv >= a + anchor_thresh && gv >= b + anchor_thresh) {
-    int bit = ix * G.nH + iy;
-    atomicOr(&bitmap[(size_t)f * G.bm_words + (bit >> 5)], 1u << (bit & 31));
-    atomicAdd(&n_anchor[f], 1);
+__global__ void __launch_bounds__(GT_THREADS) ed_grad_anchor_kernel(const uint8_t* __restrict__ img,
+                                                                    short2* __restrict__ grad,
+                                                                    uint16_t* __restrict__ gmap,
+                                                                    unsigned* __restrict__ bitmap,
+                                                                    int* __restrict__ n_anchor, EdGeom G,
+                                                                    int grad_thresh, int anchor_thresh) {
+  __shared__ __align__(16) uint8_t s_img[GT_H + 4][GT_SW];  // rows y0-2 .. y0+GT_H+1
+  __shared__ __align__(8) uint16_t s_g[GT_H + 2][GT_W + 4];  // map at (x0-1 .. x0+GT_W, y0-1 .. y0+GT_H), column c = x - x0 + 1
+  const int f = blockIdx.z, w = G.w, h = G.h;
+  const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+  const uint8_t* src = img + (size_t)f * w * h;
+  // image tile: 18 words per row x 20 rows; whole words inside the image are loaded as such
+  const bool vec_ok = (w & 3) == 0;
+  for (int i = threadIdx.x; i < (GT_H + 4) * (GT_SW / 4); i += GT_THREADS) {
+    const int r = i / (GT_SW / 4), cw = i - r * (GT_SW / 4);
+    const int y = refl101(y0 + r - 2, h), x = x0 - 4 + 4 * cw;
+    unsigned v;
+    if (vec_ok && x >= 0 && x + 3 < w) {
+      v = *reinterpret_cast<const unsigned*>(src + (size_t)y * w + x);
+    } else {
+      const uint8_t* row = src + (size_t)y * w;
+      v = (unsigned)row[refl101(x, w)] | ((unsigned)row[refl101(x + 1, w)] << 8) | ((unsigned)row[refl101(x + 2, w)] << 16) |
+          ((unsigned)row[refl101(x + 3, w)] << 24);
+    }
+    *reinterpret_cast<unsigned*>(&s_img[r][4 * cw]) = v;
   }
+  __syncthreads();
+  const size_t fo = (size_t)f * w * h;
+  {  // interior: 4 adjacent pixels per thread, 128-bit / 64-bit stores
+    const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;  // pixel (x0 + c4 .. +3, y0 + r)
+    const int x = x0 + c4, y = y0 + r;
+    short2 dv[4];
+    unsigned gv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      dv[k] = sobel_at(&s_img[r + 2][c4 + k + 4]);
+      gv[k] = gmap_value(dv[k], grad_thresh);
+      s_g[r + 1][c4 + k + 1] = (uint16_t)gv[k];
+    }
+    if (y < h) {
+      if (vec_ok && x + 3 < w) {
+        int4 o;
+        o.x = *reinterpret_cast<int*>(&dv[0]); o.y = *reinterpret_cast<int*>(&dv[1]);
+        o.z = *reinterpret_cast<int*>(&dv[2]); o.w = *reinterpret_cast<int*>(&dv[3]);
+        *reinterpret_cast<int4*>(grad + fo + (size_t)y * w + x) = o;
+        uint2 m;
+        m.x = gv[0] | (gv[1] << 16); m.y = gv[2] | (gv[3] << 16);
+        *reinterpret_cast<uint2*>(gmap + fo + (size_t)y * w + x) = m;
+      } else {
+        for (int k = 0; k < 4; k++)
+          if (x + k < w) {
+            grad[fo + (size_t)y * w + x + k] = dv[k];
+            gmap[fo + (size_t)y * w + x + k] = (uint16_t)gv[k];
+          }
+      }
+    }
+  }
+  // ring of map values around the tile (needed by the anchors on the tile's edge)
+  if (threadIdx.x < 2 * (GT_W + 2) + 2 * GT_H) {
+    int r, c;  // s_g coordinates
+    const int t = threadIdx.x;
+    if (t < GT_W + 2) { r = 0; c = t; }
+    else if (t < 2 * (GT_W + 2)) { r = GT_H + 1; c = t - (GT_W + 2); }
+    else if (t < 2 * (GT_W + 2) + GT_H) { r = 1 + t - 2 * (GT_W + 2); c = 0; }
+    else { r = 1 + t - 2 * (GT_W + 2) - GT_H; c = GT_W + 1; }
+    s_g[r][c] = (uint16_t)gmap_value(sobel_at(&s_img[r + 1][c + 3]), grad_thresh);
+  }
+  __syncthreads();
+  // anchors: grid points (1 + ix*scan, 1 + iy*scan) with 1 <= x <= w-2, 1 <= y <= h-2 inside this tile
+  const int scan = G.scan;
+  const int ix_lo = x0 <= 1 ? 0 : (x0 - 1 + scan - 1) / scan, iy_lo = y0 <= 1 ? 0 : (y0 - 1 + scan - 1) / scan;
+  const int ix_hi = min(G.nW, (min(x0 + GT_W, w - 1) - 1 + scan - 1) / scan);  // exclusive
+  const int iy_hi = min(G.nH, (min(y0 + GT_H, h - 1) - 1 + scan - 1) / scan);
+  const int nx = ix_hi - ix_lo, ny = iy_hi - iy_lo;
+  int found = 0;
+  for (int i = threadIdx.x; i < nx * ny; i += GT_THREADS) {
+    const int jy = i / nx, jx = i - jy * nx;
+    const int ix = ix_lo + jx, iy = iy_lo + jy;
+    const int c = 1 + ix * scan - x0 + 1, r = 1 + iy * scan - y0 + 1;  // position in s_g
+    const unsigned v = s_g[r][c];
+    const int gv = v & kG;
+    int a, b;
+    if (v & kDir) { a = s_g[r - 1][c] & kG; b = s_g[r + 1][c] & kG; }
+    else { a = s_g[r][c - 1] & kG; b = s_g[r][c + 1] & kG; }
+    if (gv >= a + anchor_thresh && gv >= b + anchor_thresh) {
+      const int bit = ix * G.nH + iy;
+      atomicOr(&bitmap[(size_t)f * G.bm_words + (bit >> 5)], 1u << (bit & 31));
+      found++;
+    }
+  }
+  if (found) atomicAdd(&n_anchor[f], found);
 }
 
 // ---- smart routing ---------------------------------------------------------------------------
@@ -574,21 +640,12 @@ __global__ void __launch_bounds__(32) ed_compact_kernel(EdBuffers B, EdGeom G, V
 
 }  // namespace
 
-void launch_ed_gmap(const short2* grad, uint16_t* gmap, size_t total, int grad_thresh, cudaStream_t st) {
-  size_t quads = (total + 3) / 4;
-  int blocks = (int)((quads + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  ed_gmap_kernel<<<blocks, 256, 0, st>>>(grad, gmap, total, grad_thresh);
-}
-
-void launch_ed_anchor(const EdBuffers& B, const EdGeom& G, int anchor_thresh, int batch, cudaStream_t st) {
+void launch_ed_grad_anchor(const uint8_t* img, short2* grad, const EdBuffers& B, const EdGeom& G, int grad_thresh,
+                           int anchor_thresh, int batch, cudaStream_t st) {
   cudaMemsetAsync(B.bitmap, 0, (size_t)batch * G.bm_words * sizeof(unsigned), st);
   cudaMemsetAsync(B.n_anchor, 0, (size_t)batch * sizeof(int), st);
-  int pts = G.nW * G.nH;
-  if (pts <= 0) return;
-  dim3 grid((pts + 255) / 256, batch);
-  ed_anchor_kernel<<<grid, 256, 0, st>>>(B.gmap, B.bitmap, B.n_anchor, G, anchor_thresh);
+  dim3 grid((G.w + GT_W - 1) / GT_W, (G.h + GT_H - 1) / GT_H, batch);
+  ed_grad_anchor_kernel<<<grid, GT_THREADS, 0, st>>>(img, grad, B.gmap, B.bitmap, B.n_anchor, G, grad_thresh, anchor_thresh);
 }
 
 void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st) {

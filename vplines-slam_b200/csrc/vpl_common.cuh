@@ -197,8 +197,9 @@ struct EdBuffers {
   VplLine* slots;      // B x nslots
   uint8_t* slot_valid; // B x nslots
 };
-void launch_ed_gmap(const short2* grad, uint16_t* gmap, size_t total, int grad_thresh, cudaStream_t st);
-void launch_ed_anchor(const EdBuffers& B, const EdGeom& G, int anchor_thresh, int batch, cudaStream_t st);
+// img: the smoothed frames (B x h x w); writes grad (Sobel pair), B.gmap, B.bitmap, B.n_anchor
+void launch_ed_grad_anchor(const uint8_t* img, short2* grad, const EdBuffers& B, const EdGeom& G, int grad_thresh,
+                           int anchor_thresh, int batch, cudaStream_t st);
 void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st);
 void launch_ed_fit(const EdBuffers& B, const EdGeom& G, double fit_thr, const short2* grad, const double* lgam,
                    int batch, cudaStream_t st);
