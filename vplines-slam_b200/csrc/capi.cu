@@ -623,11 +623,12 @@ KltGeom klt_geom(int w, int h, int max_level) {
   KltGeom G;
   memset(&G, 0, sizeof(G));
   G.pad = 13;
+  G.padx = 16;
   int cw = w, ch = h, level;
   size_t off = 0;
   if (max_level > kKltMaxLevels - 1) max_level = kKltMaxLevels - 1;
   for (level = 0; level <= max_level; ++level) {
-    G.w[level] = cw; G.h[level] = ch; G.stride[level] = cw + 2 * G.pad;
+    G.w[level] = cw; G.h[level] = ch; G.stride[level] = (G.padx + cw + G.pad + 15) & ~15;
     G.img_off[level] = off; G.deriv_off[level] = off;
     off += (size_t)G.stride[level] * (ch + 2 * G.pad);
     off = (off + 63) & ~(size_t)63;

@@ -59,13 +59,24 @@ __device__ __forceinline__ int cv_floor_d(float v) {  // SSE cvFloor: INT_MIN on
 }
 
 // ---- pyramid ---------------------------------------------------------------------------------
+// Level buffers: (h + 2 pad) rows of `stride` bytes (a multiple of 16); pixel (x, y) of the level is
+// at row y + pad, column x + padx (padx = 16), so that rows and pixel 0 are 16-byte aligned and the
+// kernels below move 4 pixels per thread.  Columns -pad .. w + pad - 1 hold valid border values.
 __global__ void klt_level0_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr, KltGeom G, int w, int h) {
   const int f = blockIdx.z;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int cw = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;  // word cw = columns 4cw .. 4cw+3
   const int st = G.stride[0];
-  if (x >= st) return;
-  int sx = refl101(x - G.pad, w), sy = refl101(y - G.pad, h);
-  pyr[(size_t)f * G.img_frame + G.img_off[0] + (size_t)y * st + x] = img[(size_t)f * w * h + (size_t)sy * w + sx];
+  if (4 * cw >= st) return;
+  const int sy = refl101(y - G.pad, h), x = 4 * cw - G.padx;
+  const uint8_t* row = img + (size_t)f * w * h + (size_t)sy * w;
+  unsigned v;
+  if ((w & 3) == 0 && x >= 0 && x + 3 < w) {
+    v = *reinterpret_cast<const unsigned*>(row + x);
+  } else {
+    v = (unsigned)row[refl101(x, w)] | ((unsigned)row[refl101(x + 1, w)] << 8) | ((unsigned)row[refl101(x + 2, w)] << 16) |
+        ((unsigned)row[refl101(x + 3, w)] << 24);
+  }
+  *reinterpret_cast<unsigned*>(pyr + (size_t)f * G.img_frame + G.img_off[0] + (size_t)y * st + 4 * cw) = v;
 }
 
 // level l (padded) from level l-1 (padded): cv::pyrDown to ((w+1)/2, (h+1)/2), then the border
@@ -74,37 +85,60 @@ __global__ void klt_pyrdown_kernel(uint8_t* __restrict__ pyr, KltGeom G, int l) 
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   const int st = G.stride[l];
   if (x >= st) return;
-  const int dx = refl101(x - G.pad, G.w[l]), dy = refl101(y - G.pad, G.h[l]);
+  const int dx = refl101(x - G.padx, G.w[l]), dy = refl101(y - G.pad, G.h[l]);
   const int sst = G.stride[l - 1];
   const uint8_t* src = pyr + (size_t)f * G.img_frame + G.img_off[l - 1];
-  // source rows/cols 2d-2 .. 2d+2 lie inside the stored REFLECT_101 border of level l-1, except
-  // beyond its far edge when the size is odd (2d+2 can reach w+1 <= w+pad-1): still inside
+  // source rows/cols 2d-2 .. 2d+2 lie inside the stored REFLECT_101 border of level l-1, also
+  // beyond its far edge when the size is odd (2d+2 can reach w+1 <= w+pad-1)
   int s = 0;
 #pragma unroll
   for (int j = -2; j <= 2; j++) {
-    const uint8_t* row = src + (size_t)(2 * dy + j + G.pad) * sst + (2 * dx + G.pad);
+    const uint8_t* row = src + (size_t)(2 * dy + j + G.pad) * sst + (2 * dx + G.padx);
     const int kj = j == 0 ? 6 : (j == -1 || j == 1) ? 4 : 1;
     s += kj * (row[-2] + 4 * row[-1] + 6 * row[0] + 4 * row[1] + row[2]);
   }
   pyr[(size_t)f * G.img_frame + G.img_off[l] + (size_t)y * st + x] = (uint8_t)((s + 128) >> 8);
 }
 
-// KLT::calcSharrDeriv + copyMakeBorder(BORDER_CONSTANT): zero outside the level
+// KLT::calcSharrDeriv + copyMakeBorder(BORDER_CONSTANT): zero outside the level.  4 pixels per
+// thread: 3 rows x 3 aligned words in, one 128-bit store out.
 __global__ void klt_scharr_kernel(const uint8_t* __restrict__ pyr, short2* __restrict__ deriv, KltGeom G, int l) {
   const int f = blockIdx.z;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int cw = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   const int st = G.stride[l];
-  if (x >= st) return;
-  short2 o = make_short2(0, 0);
-  const int ix = x - G.pad, iy = y - G.pad;
-  if (ix >= 0 && ix < G.w[l] && iy >= 0 && iy < G.h[l]) {
-    const uint8_t* p = pyr + (size_t)f * G.img_frame + G.img_off[l] + (size_t)y * st + x;
-    int a = p[-st - 1], b = p[-st], c = p[-st + 1], d = p[-1], e = p[1], g = p[st - 1], hh = p[st], i = p[st + 1];
-    // dIx = [3 10 3]^T (rows) x [-1 0 1];  dIy = [-1 0 1]^T x [3 10 3]
-    o.x = (short)(((c + i) * 3 + e * 10) - ((a + g) * 3 + d * 10));
-    o.y = (short)(((g - a) + (i - c)) * 3 + (hh - b) * 10);
+  if (4 * cw >= st) return;
+  const int iy = y - G.pad;
+  int4 o = make_int4(0, 0, 0, 0);
+  const int xb = 4 * cw - G.padx;  // level x of the first of the 4 pixels
+  if (iy >= 0 && iy < G.h[l] && xb + 3 >= 0 && xb < G.w[l]) {
+    const uint8_t* p = pyr + (size_t)f * G.img_frame + G.img_off[l] + (size_t)y * st + 4 * cw;
+    // bytes x-4 .. x+7 of the three rows (cw >= 1 whenever a pixel of the word is inside the level)
+    unsigned r0[3], r1[3], r2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      r0[k] = *reinterpret_cast<const unsigned*>(p - st + 4 * (k - 1));
+      r1[k] = *reinterpret_cast<const unsigned*>(p + 4 * (k - 1));
+      r2[k] = *reinterpret_cast<const unsigned*>(p + st + 4 * (k - 1));
+    }
+    int res[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      // byte j of the 12-byte span = column x-4+j; pixel k sits at j = 4 + k
+      auto at = [&](const unsigned* r, int j) { return (int)((r[j >> 2] >> (8 * (j & 3))) & 0xffu); };
+      const int j = 4 + k;
+      const int a = at(r0, j - 1), b = at(r0, j), c = at(r0, j + 1), d = at(r1, j - 1), e = at(r1, j + 1);
+      const int g = at(r2, j - 1), hh = at(r2, j), i = at(r2, j + 1);
+      short2 v = make_short2(0, 0);
+      if (xb + k >= 0 && xb + k < G.w[l]) {
+        // dIx = [3 10 3]^T (rows) x [-1 0 1];  dIy = [-1 0 1]^T x [3 10 3]
+        v.x = (short)(((c + i) * 3 + e * 10) - ((a + g) * 3 + d * 10));
+        v.y = (short)(((g - a) + (i - c)) * 3 + (hh - b) * 10);
+      }
+      res[k] = *reinterpret_cast<int*>(&v);
+    }
+    o = make_int4(res[0], res[1], res[2], res[3]);
   }
-  deriv[(size_t)f * G.deriv_frame + G.deriv_off[l] + (size_t)y * st + x] = o;
+  *reinterpret_cast<int4*>(deriv + (size_t)f * G.deriv_frame + G.deriv_off[l] + (size_t)y * st + 4 * cw) = o;
 }
 
 // ---- anchors, lm.cpp:531-599 --------------------------------------------------------------------
@@ -312,9 +346,9 @@ __global__ void __launch_bounds__(32) klt_track_kernel(const uint8_t* __restrict
         k = (size_t)p * B.cap_kp + i;
         const int fr = p * pstride, fc = fr + 1;
         // pointers to pixel (0,0) of the level inside its padded buffer
-        const uint8_t* I = pyr + (size_t)fr * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
-        J = pyr + (size_t)fc * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.pad;
-        const short2* dI = deriv + (size_t)fr * G.deriv_frame + G.deriv_off[level] + (size_t)G.pad * st + G.pad;
+        const uint8_t* I = pyr + (size_t)fr * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.padx;
+        J = pyr + (size_t)fc * G.img_frame + G.img_off[level] + (size_t)G.pad * st + G.padx;
+        const short2* dI = deriv + (size_t)fr * G.deriv_frame + G.deriv_off[level] + (size_t)G.pad * st + G.padx;
         const float2 prev = B.kps[k];
         float px = prev.x * scale, py = prev.y * scale;
         if (level == G.top) {  // flags == 0, lk2d.cpp:51-56
@@ -581,16 +615,16 @@ __global__ void __launch_bounds__(256) lm_vote_kernel(const VplLine* __restrict_
 void launch_klt_pyramid(const uint8_t* img, uint8_t* pyr, short2* deriv, const KltGeom& G, int w, int h, int batch,
                         cudaStream_t st) {
   {
-    dim3 grid((G.stride[0] + 255) / 256, h + 2 * G.pad, batch);
-    klt_level0_kernel<<<grid, 256, 0, st>>>(img, pyr, G, w, h);
+    dim3 grid((G.stride[0] / 4 + 127) / 128, h + 2 * G.pad, batch);
+    klt_level0_kernel<<<grid, 128, 0, st>>>(img, pyr, G, w, h);
   }
   for (int l = 1; l <= G.top; l++) {
     dim3 grid((G.stride[l] + 127) / 128, G.h[l] + 2 * G.pad, batch);
     klt_pyrdown_kernel<<<grid, 128, 0, st>>>(pyr, G, l);
   }
   for (int l = 0; l <= G.top; l++) {
-    dim3 grid((G.stride[l] + 255) / 256, G.h[l] + 2 * G.pad, batch);
-    klt_scharr_kernel<<<grid, 256, 0, st>>>(pyr, deriv, G, l);
+    dim3 grid((G.stride[l] / 4 + 127) / 128, G.h[l] + 2 * G.pad, batch);
+    klt_scharr_kernel<<<grid, 128, 0, st>>>(pyr, deriv, G, l);
   }
 }
 

@@ -210,7 +210,8 @@ constexpr int kKltMaxLevels = 4;  // maxLevel 3 (line_matching.cpp:14)
 // Pyramid of one frame: every level stored with a `pad`-pixel border (REFLECT_101 for the image,
 // zero for the Scharr pair), levels back to back.
 struct KltGeom {
-  int pad;                         // = window size 13
+  int pad;                         // border rows above/below and valid border columns: the window size, 13
+  int padx;                        // columns in front of pixel 0 (16: rows and pixel 0 stay 16-byte aligned)
   int top;                         // highest level built (cv::buildOpticalFlowPyramid's return)
   int w[kKltMaxLevels], h[kKltMaxLevels], stride[kKltMaxLevels];
   size_t img_off[kKltMaxLevels];   // bytes from the frame's pyramid base
