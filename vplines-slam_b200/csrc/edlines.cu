@@ -194,9 +194,11 @@ __device__ __forceinline__ void ed_prefetch_strip(const uint16_t* __restrict__ g
 //     candidate 1 is the upper one (dperp = -W), for a vertical move dmain = +-W and candidate 1 is
 //     the right one (dperp = +1), exactly the reference's gValue1 / gValue2 / gValue3.
 //
-// (Tried and dropped: edge marks as a bitmap in shared memory with a read-only gradient map.  The
-// step time is the dependent ALU chain, not the loads, and 45 KB per walker cuts the walkers per SM
-// from 28 to 4: 10 ms -> 39 ms per 4096 frames.)
+// (Tried and dropped: edge marks as a whole-frame bitmap in shared memory with a read-only gradient
+// map -- 45 KB per walker cuts the walkers per SM from 28 to 4: 10 ms -> 39 ms per 4096 frames; and
+// a 64 x 32 tile of the map in shared memory that follows the walker -- most walks are a few pixels
+// long, so the 4 KB tile reloads cost more than the L2 round trips they save: 4.3 -> 5.5 ms per 512
+// frames.  The loads after a mark store remain the top stall of this kernel.)
 __device__ __noinline__ int ed_walk(uint16_t* __restrict__ g, int W, int H, unsigned x0, unsigned y0, int last_dir,
                                     uint32_t* __restrict__ out, int cap, WalkMem& wm, int lane) {
   int n = 0;
