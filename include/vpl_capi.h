@@ -314,8 +314,8 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_MATCH 9
 #define VPL_STAGE_D2H 10
 #define VPL_STAGE_PREPROC 11  /* remap + CLAHE (optional)           */
-#define VPL_STAGE_ED_GRAD 12    /* EDLines: gradient/direction map */
-#define VPL_STAGE_ED_ANCHOR 13  /* anchor bitmap                   */
+#define VPL_STAGE_ED_GRAD 12    /* EDLines: Sobel pair, gradient/direction map, anchor bitmap */
+#define VPL_STAGE_ED_ANCHOR 13  /* (unused: the anchor test is fused into the pass above)     */
 #define VPL_STAGE_ED_WALK 14    /* smart routing (edge chains)     */
 #define VPL_STAGE_ED_FIT 15     /* line fit + validation + compaction */
 #define VPL_STAGE_LM_PYRAMID 16 /* line matching: KLT pyramids + Scharr */
