@@ -76,6 +76,7 @@ typedef unsigned char uchar;
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_16SC2 CV_MAKETYPE(CV_16S, 2)
 #define CV_AA 16
+#define CV_PI 3.1415926535897932384626433832795 /* opencv2/core/cvdef.h */
 #define CV_CPU_SSE2 3
 #define CV_Assert(expr)                                                        \
   do {                                                                         \
@@ -122,6 +123,7 @@ template <class T> static inline Point_<T> operator+(const Point_<T>& a, const P
 template <class T> static inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
 static inline Point_<float> operator*(const Point_<float>& a, float b) { return Point_<float>(a.x * b, a.y * b); }
 typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
 typedef Point_<int> Point;
 typedef Point_<int> Point2i;
 struct Rect {

@@ -369,3 +369,91 @@ def frontend_sequence(frames, num_octaves=1, max_lines=8192, threads=1):
     n, h, w = frames.shape
     return int(lib().orc_frontend_sequence_mt(_p(frames), n, w, h, int(num_octaves), int(max_lines),
                                               int(threads)))
+
+
+# ---- vanishing-point stage (orc_vp.c / oracle/_ref/libref_vp.so) -------------------
+VP_GRID_SHAPE = (90, 360)
+_REF_VP_SO = os.path.join(_HERE, "_ref", "libref_vp.so")
+_ref_vp = None
+
+
+class GRand:
+    """glibc srand()/rand() restated (orc_grand_*)."""
+
+    class _S(ctypes.Structure):
+        _fields_ = [("r", ctypes.c_int32 * 31), ("f", ctypes.c_int), ("b", ctypes.c_int)]
+
+    def __init__(self, seed):
+        self.s = GRand._S()
+        lib().orc_grand_seed(ctypes.byref(self.s), ctypes.c_uint(seed))
+
+    def next(self):
+        return int(lib().orc_grand_next(ctypes.byref(self.s)))
+
+
+def vp_hypothesis_count():
+    return int(lib().orc_vp_hypothesis_count())
+
+
+def vp_detect(lines, all_lines=None, f=460.0, cx=376.0, cy=240.0, seed=1, frame_count=0, math_mode=1, details=False):
+    """vanishing_point_detection::run_vanishing_point_detection -> (vps float64[3,3], vp_idx int32[n_all]);
+    details=True adds dict(grid, best_idx, pairs, flags).  math_mode 0 = libm (equals oracle/_ref bit for
+    bit), 1 = the shared deterministic functions (what the device computes)."""
+    L = lib(); L.orc_vp_detect.restype = ctypes.c_int
+    ln = np.ascontiguousarray(lines, LINE_DTYPE)
+    al = ln if all_lines is None else np.ascontiguousarray(all_lines, LINE_DTYPE)
+    vps = np.zeros((3, 3), np.float64); idx = np.full(len(al), -1, np.int32)
+    grid = np.zeros(VP_GRID_SHAPE, np.float64); best = ctypes.c_int32(); flags = ctypes.c_int32()
+    pairs = np.zeros((vp_hypothesis_count(), 2), np.int32)
+    rc = L.orc_vp_detect(_p(ln), len(ln), _p(al), len(al), ctypes.c_float(f), ctypes.c_float(cx), ctypes.c_float(cy),
+                         ctypes.c_uint(seed), int(frame_count), int(math_mode), _p(vps), _p(idx), _p(grid),
+                         ctypes.byref(best), _p(pairs), ctypes.byref(flags))
+    if rc:
+        raise ValueError("orc_vp_detect -> %d" % rc)
+    if details:
+        return vps, idx, dict(grid=grid, best_idx=best.value, pairs=pairs, flags=flags.value)
+    return vps, idx
+
+
+def ref_vp_available():
+    return os.path.exists(_REF_VP_SO) or os.path.isdir("/root/reference/feature_tracker/src")
+
+
+def ref_vp_lib():
+    global _ref_vp
+    if _ref_vp is None:
+        if not os.path.exists(_REF_VP_SO):
+            build_ref()
+        _ref_vp = ctypes.CDLL(_REF_VP_SO)
+        _ref_vp.ref_vp_detect.restype = ctypes.c_int
+        _ref_vp.ref_vp_sequence.restype = ctypes.c_longlong
+    return _ref_vp
+
+
+def ref_vp_detect(lines, all_lines=None, f=460.0, cx=376.0, cy=240.0, seed=1, frame_count=0):
+    """The same call through the reference's own vanishing_point_detection.cpp (oracle/_ref/libref_vp.so), its
+    time(NULL) answered with `seed`."""
+    ln = np.ascontiguousarray(lines, LINE_DTYPE)
+    al = ln if all_lines is None else np.ascontiguousarray(all_lines, LINE_DTYPE)
+    vps = np.zeros((3, 3), np.float64); idx = np.full(len(al), -1, np.int32)
+    rc = ref_vp_lib().ref_vp_detect(_p(ln), len(ln), _p(al), len(al), ctypes.c_float(f), ctypes.c_float(cx),
+                                    ctypes.c_float(cy), ctypes.c_uint(seed), int(frame_count), _p(vps), _p(idx))
+    if rc:
+        raise ValueError("ref_vp_detect -> %d" % rc)
+    return vps, idx
+
+
+def vp_sequence(lines, counts, seeds, f=460.0, cx=376.0, cy=240.0, frame_count0=0, math_mode=0, use_ref=False):
+    """Frames one after another (timing / sequence parity): lines (n, cap) LINE_DTYPE, counts (n,), seeds (n,)
+    -> (vps (n,3,3), vp_idx (n,cap), number of labelled lines)."""
+    lines = np.ascontiguousarray(lines, LINE_DTYPE); n, cap = lines.shape
+    counts = np.ascontiguousarray(counts, np.int32); seeds = np.ascontiguousarray(seeds, np.uint32)
+    vps = np.zeros((n, 3, 3), np.float64); idx = np.full((n, cap), 3, np.int32)
+    if use_ref:
+        tot = ref_vp_lib().ref_vp_sequence(_p(lines), _p(counts), n, cap, ctypes.c_float(f), ctypes.c_float(cx),
+                                           ctypes.c_float(cy), _p(seeds), _p(vps), _p(idx))
+    else:
+        L = lib(); L.orc_vp_sequence.restype = ctypes.c_int64
+        tot = L.orc_vp_sequence(_p(lines), _p(counts), n, cap, ctypes.c_float(f), ctypes.c_float(cx), ctypes.c_float(cy),
+                                _p(seeds), int(frame_count0), int(math_mode), _p(vps), _p(idx))
+    return vps, idx, int(tot)

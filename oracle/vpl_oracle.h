@@ -163,6 +163,27 @@ int orc_line_matching(const uint8_t* img_ref, const uint8_t* img_cur, int w, int
 int64_t orc_linefront_sequence_mt(const uint8_t* frames, int n_frames, int w, int h, const OrcEDLineParam* p,
                                   int smoothed, int n_threads);
 
+/* ---- vanishing-point stage after the path (orc_vp.c) ---- */
+typedef struct { int32_t r[31]; int f, b; } OrcGRand; /* glibc rand() state, TYPE_3 */
+void orc_grand_seed(OrcGRand* g, unsigned seed);      /* = srand(seed) */
+int32_t orc_grand_next(OrcGRand* g);                  /* = rand()      */
+#define ORC_VP_MAX_DRAWS 1000000
+#define ORC_VP_FLAG_LX_OOB 1 /* the reference would have read lx[] out of range on this frame */
+int orc_vp_hypothesis_count(void); /* "it" of getVPHypVia2Lines (105) */
+/* vanishing_point_detection::run_vanishing_point_detection(img, lines, all_lines, vps, local_vp_ids)
+ * after init(f, cx, cy, .).  seed: what time(NULL) returned; frame_count: calls made before this one.
+ * math_mode 0: libm, 1: the shared deterministic functions.  vps: 9 doubles (3 unit vectors);
+ * vp_idx: n_all labels 0..2, 3 = none.  Optional: grid (90 x 360 smoothed cells), best_idx
+ * (hypothesis index), pairs (2 per outer iteration), flags.  Returns 0, -1 (fewer than 2 lines), -2. */
+int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, int n_all, float f, float cx,
+                  float cy, unsigned seed, int frame_count, int math_mode, double* vps, int32_t* vp_idx,
+                  double* grid, int32_t* best_idx, int32_t* pairs, int32_t* flags);
+int64_t orc_vp_sequence(const OrcLine* lines, const int32_t* counts, int n_frames, int cap, float f, float cx, float cy,
+                        const uint32_t* seeds, int frame_count0, int math_mode, double* vps, int32_t* vp_idx);
+double orc_atan2_cr(double y, double x);
+double orc_atan_cr(double t);
+double orc_acos_cr(double x);
+
 /* Whole front end on a frame sequence (for the CPU baseline timing).  Returns
  * total keylines over the sequence (each frame is matched k=1 against the
  * previous one; results are discarded, this entry point exists for timing). */

@@ -1,0 +1,139 @@
+"""Oracle for SURVEY 8f-4 (vanishing_point_detection::run_vanishing_point_detection,
+oracle/orc_vp.c) pinned against the reference's OWN code: tests/golden/ref_vp.npz was produced by
+the reference's vanishing_point_detection.cpp compiled against oracle/cvshim with its time(NULL)
+answered by a stored seed (tests/golden/make_golden_vp.py); where that build exists it is also
+called live.  Bar: bit-exact in math_mode 0 (libm) -- the nine doubles of the three vanishing
+points and every line label; in math_mode 1 (the shared deterministic atan/acos/sincos the device
+uses) labels and the winning hypothesis identical, vanishing points within 1e-15."""
+import ctypes
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden_vp", os.path.join(HERE, "golden", "make_golden_vp.py"))
+mk = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mk)
+HAVE_REF = os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_vp.so"))
+NAMES = sorted(n[:-6] for n in np.load(os.path.join(HERE, "golden", "ref_vp.npz")).files if n.endswith("_lines")
+               and not n.endswith("_all_lines"))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "ref_vp.npz"))
+
+
+def case(gold, name):
+    f, cx, cy = (float(v) for v in gold[name + "_cam"])
+    seed, fc = (int(v) for v in gold[name + "_seed"])
+    return gold[name + "_lines"], gold[name + "_all_lines"], f, cx, cy, seed, fc
+
+
+def test_glibc_rand_restated(orc):
+    """orc_grand_* is srand()/rand() of the C library the reference links (TYPE_3 additive generator)."""
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (0, 1, 12345, 1729000000, 2147483648, 4000000000, 4294967295):
+        libc.srand(ctypes.c_uint(seed))
+        g = orc.GRand(seed)
+        assert [libc.rand() for _ in range(2000)] == [g.next() for _ in range(2000)]
+
+
+def test_hypothesis_count(orc):
+    assert orc.vp_hypothesis_count() == 105  # log(1 - 0.9999) / log(1 - 0.25 / 3), :93-97
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vp_golden(orc, gold, name):
+    ln, al, f, cx, cy, seed, fc = case(gold, name)
+    vps, idx, d = orc.vp_detect(ln, al, f, cx, cy, seed, fc, math_mode=0, details=True)
+    assert d["flags"] == 0
+    assert vps.tobytes() == gold[name + "_vps"].tobytes()
+    assert np.array_equal(idx, gold[name + "_vp_idx"])
+    # unit vectors, z >= 0 for the second and third (:153, :160)
+    assert np.allclose(np.linalg.norm(vps, axis=1), 1.0, atol=1e-12) and (vps[1:, 2] >= 0).all()
+    # the device's definition of the transcendental functions: same decisions
+    v1, i1, d1 = orc.vp_detect(ln, al, f, cx, cy, seed, fc, math_mode=1, details=True)
+    assert d1["best_idx"] == d["best_idx"] and np.array_equal(i1, idx)
+    assert np.abs(v1 - vps).max() <= 1e-15
+    assert np.allclose(d1["grid"], d["grid"], rtol=1e-13, atol=0)
+
+
+def test_vp_inputs_regenerate(orc, gold):
+    """The stored line sets are the oracle's EDLines of the committed frames / the seeded generator."""
+    inp = mk.inputs()
+    for name in ("mh04_4", "vertical_9", "manhattan"):
+        assert inp[name][0].tobytes() == gold[name + "_lines"].tobytes()
+        assert inp[name][1].tobytes() == gold[name + "_all_lines"].tobytes()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+def test_vp_live_reference_build(orc, mh04):
+    n_cmp = n_oob = 0
+    for k in (0, 5, 10, 13):
+        ln = orc.edline_detect(mh04[k])
+        for seed in (3, 1700000000 + 17 * k, 1690000000 + k):
+            for fc in (0, 2):
+                vps, idx, d = orc.vp_detect(ln, ln, 461.6, 363.0, 248.1, seed, fc, math_mode=0, details=True)
+                if d["flags"]:  # the reference reads lx[] out of range here (undefined behaviour)
+                    n_oob += 1
+                    continue
+                vr, ir = orc.ref_vp_detect(ln, ln, 461.6, 363.0, 248.1, seed, fc)
+                assert vps.tobytes() == vr.tobytes() and np.array_equal(idx, ir)
+                n_cmp += 1
+    assert n_cmp >= 12
+
+
+def test_vp_sphere_grid_properties(orc, gold):
+    ln, al, f, cx, cy, seed, fc = case(gold, "manhattan")
+    _, _, d = orc.vp_detect(ln, al, f, cx, cy, seed, fc, math_mode=1, details=True)
+    g = d["grid"]
+    assert g.shape == (90, 360) and (g >= 0).all()
+    assert (g[0] == 0).all() and (g[-1] == 0).all() and (g[:, 0] == 0).all() and (g[:, -1] == 0).all()  # :255-271
+    # the grid does not depend on the seed, the pairs do
+    _, _, d2 = orc.vp_detect(ln, al, f, cx, cy, seed + 1, fc, math_mode=1, details=True)
+    assert d2["grid"].tobytes() == g.tobytes() and not np.array_equal(d2["pairs"], d["pairs"])
+    assert (d["pairs"][:, 0] != d["pairs"][:, 1]).all() and d["pairs"].min() >= 0 and d["pairs"].max() < len(ln)
+
+
+def test_vp_frame_count_rule(orc, gold):
+    """frame_count > 0: vps[1] and vps[2] are swapped when |vps[1].y| <= 0.8 (:337-349); frame 0 never swaps."""
+    ln, al, f, cx, cy, seed, _ = case(gold, "mh04_8")
+    v0, _ = orc.vp_detect(ln, al, f, cx, cy, seed, 0)
+    v1, _ = orc.vp_detect(ln, al, f, cx, cy, seed, 5)
+    if abs(v0[1, 1]) > 0.8:
+        assert v1.tobytes() == v0.tobytes()
+    else:
+        assert v1[1].tobytes() == v0[2].tobytes() and v1[2].tobytes() == v0[1].tobytes() and v1[0].tobytes() == v0[0].tobytes()
+
+
+def test_vp_too_few_lines(orc, gold):
+    ln = gold["few_lines"]
+    with pytest.raises(ValueError):
+        orc.vp_detect(ln[:1])
+    vps, idx = orc.vp_detect(ln[:3])
+    assert idx.shape == (3,) and set(idx) <= {0, 1, 2, 3}
+
+
+def test_cr_atan_family_against_mpmath(orc):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    L = orc.lib()
+    for n in ("orc_atan2_cr", "orc_atan_cr", "orc_acos_cr"):
+        getattr(L, n).restype = ctypes.c_double
+    L.orc_atan2_cr.argtypes = [ctypes.c_double, ctypes.c_double]
+    L.orc_atan_cr.argtypes = [ctypes.c_double]
+    L.orc_acos_cr.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        y, x = (float(v) for v in rng.uniform(-1, 1, 2) * 10.0 ** rng.uniform(-5, 5, 2))
+        assert L.orc_atan2_cr(y, x) == float(mp.atan2(mp.mpf(y), mp.mpf(x)))
+        assert L.orc_atan_cr(y) == float(mp.atan(mp.mpf(y)))
+        u = float(rng.uniform(-1, 1))
+        assert L.orc_acos_cr(u) == float(mp.acos(mp.mpf(u)))
+    assert L.orc_atan2_cr(0.0, -1.0) == np.pi and L.orc_atan2_cr(-0.0, -1.0) == -np.pi
+    assert L.orc_atan2_cr(1.0, 0.0) == np.pi / 2 and L.orc_atan2_cr(0.0, 0.0) == 0.0
+    assert L.orc_atan_cr(float("inf")) == np.pi / 2 and L.orc_atan_cr(float("-inf")) == -np.pi / 2
+    assert L.orc_acos_cr(1.0) == 0.0 and L.orc_acos_cr(-1.0) == np.pi and np.isnan(L.orc_acos_cr(1.0000001))
