@@ -212,6 +212,40 @@ int vpl_linefront_collect(VplContext* ctx, int slot, VplLine* lines, int32_t* co
                           int32_t* prev_to_cur);
 int vpl_linefront_run_resident(VplContext* ctx, int slot);
 
+/* ---- vanishing_point_detection::run_vanishing_point_detection: the stage the tracker runs on the
+ *      matched lines of every frame (feature_tracker/src/vanishing_point_detection.cpp:37-65,
+ *      called at feature_tracker/src/line_feature_tracker.cpp:241 / :243) ------------------------ */
+/* = vanishing_point_detection::init(f, cx, cy, noiseRatio) (vanishing_point_detection.cpp:29-34; the
+ * noise ratio argument is shadowed by a local 0.5 at :93 and never read).  Allocates the sphere grids
+ * (2 x 259 KB per frame) and line scratch for max_batch frames of max_lines lines.  Call before the
+ * first detection, not while batches are in flight. */
+int vpl_vp_configure(VplContext* ctx, float f, float cx, float cy);
+/* n_frames independent calls of run_vanishing_point_detection(img, lines, all_lines, vps, local_vp_ids)
+ * (the image argument is only drawn on).  lines: n_frames * cap entries (frame i at + i*cap, n_lines[i]
+ * valid) -- the set the hypotheses and the sphere vote use; all_lines / n_all: the set that is
+ * classified (NULL = the same set: what readImage passes unless it found > 2 vertical lines).
+ * seeds[i]: what time(NULL) returned for frame i -- the reference seeds rand() with it on every call
+ * (:107).  frame_count0: calls the object made before frame 0 (frame i runs with frame_count0 + i; only
+ * 0 / not 0 matters, :337-349).  Outputs: vps n_frames * 9 doubles (three unit vectors), vp_idx
+ * n_frames * cap labels (0..2, 3 = none), optional line_vps n_frames * cap * 4 doubles (the Vector4d
+ * readImage stores per line, line_feature_tracker.cpp:246-262), optional status per frame:
+ * 0 ok, 1 ok but the reference itself would have read lx[] out of range on this frame (oracle/orc_vp.c),
+ * -1 fewer than 2 lines (nothing labelled, vps zero: readImage's "no vp lines" branch), -2 no
+ * non-degenerate line pair found. */
+int vpl_vp_detect_batch(VplContext* ctx, const VplLine* lines, const int32_t* n_lines, const VplLine* all_lines,
+                        const int32_t* n_all, int n_frames, int cap, const uint32_t* seeds, int frame_count0,
+                        double* vps, int32_t* vp_idx, double* line_vps, int32_t* status);
+/* The same, pipelined over the context's slots. */
+int vpl_vp_submit(VplContext* ctx, int slot, const VplLine* lines, const int32_t* n_lines, const VplLine* all_lines,
+                  const int32_t* n_all, int n_frames, int cap, const uint32_t* seeds, int frame_count0);
+int vpl_vp_collect(VplContext* ctx, int slot, int cap, double* vps, int32_t* vp_idx, double* line_vps,
+                   int32_t* status);
+/* Re-runs the stage on the lines already resident on the slot (measurement). */
+int vpl_vp_run_resident(VplContext* ctx, int slot);
+/* Stage outputs of frame `frame` of the last batch on slot 0: the smoothed 90 x 360 grid, the index of
+ * the winning hypothesis, the line pair of every outer iteration (2 x 105 ints).  Any may be NULL. */
+int vpl_debug_vp(VplContext* ctx, int frame, double* grid, int32_t* best_idx, int32_t* pairs);
+
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
  * keylines: n * cap entries, frame f at keylines + f*cap; counts[f] = number found
@@ -321,7 +355,11 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_LM_PYRAMID 16 /* line matching: KLT pyramids + Scharr */
 #define VPL_STAGE_LM_TRACK 17   /* anchors + pyramidal LK               */
 #define VPL_STAGE_LM_VOTE 18    /* closest line, vote, topological filter */
-#define VPL_NUM_STAGES 19
+#define VPL_STAGE_VP_PREP 19     /* vanishing points: line parameters, rand() pairs (+ grid clear) */
+#define VPL_STAGE_VP_VOTE 20     /* sphere-grid vote + 3x3 pass                                   */
+#define VPL_STAGE_VP_SCORE 21    /* 105 x 360 hypotheses built and scored                         */
+#define VPL_STAGE_VP_CLASSIFY 22 /* best hypothesis, line classification                          */
+#define VPL_NUM_STAGES 23
 /* Accumulated device milliseconds and launch counts per stage since the last
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);

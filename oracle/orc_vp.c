@@ -228,6 +228,7 @@ int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, i
       if (la == 90) la = 89;
       int lo = (int)(longitude / oneDegree);
       if (lo == 360) lo = 359;
+      if (la < 0 || la >= gridLA || lo < 0 || lo >= gridLO) continue; /* z < 0 (only with f < 0): out of the grid */
       lineLength += gridNew[la * gridLO + lo];
     }
     if (i == 0) memcpy(best, hyp, sizeof(best));

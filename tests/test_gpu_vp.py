@@ -1,0 +1,170 @@
+"""GPU parity for SURVEY 8f-4: the CUDA vanishing-point stage (vplines-slam_b200/csrc/vp.cu, through
+the C ABI vpl_vp_*) against (1) the golden vectors produced by the reference's own
+vanishing_point_detection.cpp (tests/golden/ref_vp.npz) and (2) the CPU oracle on seeded inputs.
+Bar: against the oracle in its device arithmetic (math_mode 1: the shared deterministic
+atan/acos/sincos) everything is bit-exact -- the smoothed sphere grid (32 400 doubles), the random
+line pairs, the winning hypothesis, the nine doubles of the vanishing points, every line label and
+the out-of-range flag; against the reference's own output (computed with libm) labels are identical
+and the vanishing points agree to 1e-15 (tolerance stated: unit vectors, i.e. <= 5 ulp)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EUROC = (461.6, 363.0, 248.1)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "ref_vp.npz"))
+
+
+NAMES = sorted(n[:-6] for n in np.load(os.path.join(HERE, "golden", "ref_vp.npz")).files
+               if n.endswith("_lines") and not n.endswith("_all_lines"))
+
+
+@pytest.fixture(scope="module")
+def ctx(vpl):
+    c = vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=2048, max_batch=64, num_slots=2,
+                    profile=True, lsd_path=False)
+    yield c
+    c.close()
+
+
+def as_capi(vpl, lines):
+    return np.ascontiguousarray(lines).view(vpl.capi.LINE_DTYPE).reshape(-1)
+
+
+def check_frame(orc, dev_vps, dev_idx, dev_status, dbg, ln, al, f, cx, cy, seed, fc):
+    vps, idx, d = orc.vp_detect(ln, al, f, cx, cy, seed, fc, math_mode=1, details=True)
+    assert dev_status == (d["flags"] & 1)
+    assert np.array_equal(dev_idx, idx)
+    assert dev_vps.tobytes() == vps.tobytes()
+    if dbg is not None:
+        assert dbg["best_idx"] == d["best_idx"]
+        assert np.array_equal(dbg["pairs"], d["pairs"])
+        assert dbg["grid"].tobytes() == d["grid"].tobytes()
+    return d
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vp_reference_golden(ctx, vpl, orc, gold, name):
+    f, cx, cy = (float(v) for v in gold[name + "_cam"])
+    seed, fc = (int(v) for v in gold[name + "_seed"])
+    ln, al = gold[name + "_lines"], gold[name + "_all_lines"]
+    ctx.vp_configure(f, cx, cy)
+    same = ln.tobytes() == al.tobytes()
+    vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, ln)], [seed], None if same else [as_capi(vpl, al)], frame_count0=fc)
+    # the reference's own output: same labels, vanishing points to 1e-15
+    assert st[0] == 0
+    assert np.array_equal(idx[0], gold[name + "_vp_idx"])
+    assert np.abs(vps[0] - gold[name + "_vps"]).max() <= 1e-15
+    # the oracle in the device's arithmetic: bit-exact, stage by stage
+    check_frame(orc, vps[0], idx[0], st[0], ctx.vp_debug(0), ln, al, f, cx, cy, seed, fc)
+
+
+def test_vp_batch_vs_oracle_many_seeds(ctx, vpl, orc, mh04):
+    """60 (frame, seed) combinations in one batch, frame_count running 0, 1, 2, ... inside the batch; includes
+    frames on which the reference reads lx[] out of range (status 1: repaired semantics of oracle/orc_vp.c)."""
+    ctx.vp_configure(*EUROC)
+    sets, seeds = [], []
+    for k in range(15):
+        ln = orc.edline_detect(mh04[k])
+        for s in range(4):
+            sets.append(ln); seeds.append(1700000000 + 97 * k + s)
+    vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, l) for l in sets], seeds, frame_count0=0)
+    n_flag = 0
+    for i, (ln, seed) in enumerate(zip(sets, seeds)):
+        d = check_frame(orc, vps[i], idx[i], st[i], ctx.vp_debug(i) if i % 7 == 0 else None, ln, ln, *EUROC, seed, i)
+        n_flag += d["flags"]
+    assert 0 < n_flag < len(sets)          # both kinds of frame were exercised
+    assert (np.concatenate(idx) != 3).sum() > 1000
+
+
+def test_vp_subset_lines_and_line_vps(ctx, vpl, orc, mh04):
+    """`lines` = the near-vertical subset, all_lines = everything (line_feature_tracker.cpp:241); per-line Vector4d."""
+    ctx.vp_configure(*EUROC)
+    subs, alls, seeds = [], [], []
+    for k in (1, 6, 11):
+        ln = orc.edline_detect(mh04[k])
+        e = ln["endpoint"]
+        vert = np.abs(e[:, 0] - e[:, 2]) < 0.35 * np.abs(e[:, 1] - e[:, 3])
+        subs.append(ln[vert]); alls.append(ln); seeds.append(40 + k)
+    vps, idx, st, lv = ctx.vp_detect_batch([as_capi(vpl, l) for l in subs], seeds, [as_capi(vpl, l) for l in alls],
+                                           frame_count0=4, with_line_vps=True)
+    for i in range(3):
+        check_frame(orc, vps[i], idx[i], st[i], ctx.vp_debug(i), subs[i], alls[i], *EUROC, seeds[i], 4 + i)
+        for j, lab in enumerate(idx[i]):  # line_feature_tracker.cpp:246-262
+            want = np.zeros(4) if lab == 3 else np.array([*vps[i][lab], vps[i][lab][2] / vps[i][lab][2]])
+            assert lv[i][j].tobytes() == want.tobytes()
+
+
+def test_vp_many_lines(ctx, vpl, orc):
+    """1500 synthetic segments towards three vanishing points (1.1 M pairs per frame; cells of the vote
+    receive thousands of additions in pair order), 1280x720 intrinsics."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mkvp", os.path.join(HERE, "golden", "make_golden_vp.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    ctx.vp_configure(640.0, 640.0, 360.0)
+    sets = [mk.manhattan_lines(1500, seed=21), mk.manhattan_lines(700, seed=22)]
+    seeds = [11, 1700001234]
+    vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, l) for l in sets], seeds, frame_count0=0)
+    for i in range(2):
+        check_frame(orc, vps[i], idx[i], st[i], ctx.vp_debug(i), sets[i], sets[i], 640.0, 640.0, 360.0, seeds[i], i)
+    assert (idx[0] != 3).sum() > 500
+
+
+def test_vp_degenerate_frames(ctx, vpl, orc, mh04):
+    """0 / 1 lines -> status -1, nothing labelled, vps zero (readImage's "no vp lines" branch); 2 and 3 lines run;
+    parallel lines only (every intersection has z == 0) -> status -2 where the reference would loop for ever."""
+    ctx.vp_configure(*EUROC)
+    ln = orc.edline_detect(mh04[3])
+    par = np.zeros(3, orc.LINE_DTYPE)
+    for i in range(3):
+        par["endpoint"][i] = (10, 20 + 30 * i, 210, 20 + 30 * i)
+    sets = [ln[:0], ln[:1], ln[:2], ln[:3], par, ln]
+    seeds = [5, 6, 7, 8, 9, 10]
+    vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, l) for l in sets], seeds, frame_count0=0)
+    assert list(st[:2]) == [-1, -1] and (vps[:2] == 0).all() and len(idx[0]) == 0 and list(idx[1]) == [3]
+    assert st[4] == -2 and (vps[4] == 0).all() and list(idx[4]) == [3, 3, 3]
+    with pytest.raises(ValueError):
+        orc.vp_detect(par, seed=9)
+    for i in (2, 3, 5):
+        check_frame(orc, vps[i], idx[i], st[i], None, sets[i], sets[i], *EUROC, seeds[i], i)
+
+
+def test_vp_submit_collect_two_slots(ctx, vpl, orc, mh04):
+    ctx.vp_configure(*EUROC)
+    L = vpl.capi.LINE_DTYPE
+    sets = [as_capi(vpl, orc.edline_detect(mh04[k])) for k in range(8)]
+    cap = max(len(s) for s in sets)
+    arr = np.zeros((8, cap), L); cnt = np.array([len(s) for s in sets], np.int32)
+    for i, s in enumerate(sets):
+        arr[i, :cnt[i]] = s
+    seeds = np.arange(900, 908, dtype=np.uint32)
+    ref_vps, ref_idx, ref_st = ctx.vp_detect_batch(sets, seeds, frame_count0=0)
+    ctx.vp_submit(0, arr[:4], cnt[:4], seeds[:4], 0)
+    ctx.vp_submit(1, np.ascontiguousarray(arr[4:]), cnt[4:], seeds[4:], 4)
+    for slot, lo in ((0, 0), (1, 4)):
+        vps = np.zeros((4, 3, 3)); idx = np.full((4, cap), -1, np.int32); st = np.zeros(4, np.int32)
+        ctx.vp_collect_into(slot, cap, vps, idx, st)
+        assert vps.tobytes() == ref_vps[lo:lo + 4].tobytes() and np.array_equal(st, ref_st[lo:lo + 4])
+        for i in range(4):
+            assert np.array_equal(idx[i, :cnt[lo + i]], ref_idx[lo + i])
+    t = ctx.stage_times()
+    assert t["vp_vote"][1] >= 2 and t["vp_score"][1] >= 1 and t["vp_classify"][1] >= 1
+
+
+def test_vp_errors(ctx, vpl):
+    c2 = vpl.Context(max_width=64, max_height=64, max_lines=16, max_batch=2, lsd_path=False)
+    with pytest.raises(vpl.capi.VplError):
+        c2.vp_detect_batch([np.zeros(3, vpl.capi.LINE_DTYPE)], [1])      # not configured
+    c2.vp_configure(100.0, 32.0, 32.0)
+    with pytest.raises(vpl.capi.VplError):
+        c2.vp_detect_batch([np.zeros(17, vpl.capi.LINE_DTYPE)], [1])     # more lines than max_lines
+    with pytest.raises(vpl.capi.VplError):
+        c2.vp_detect_batch([np.zeros(3, vpl.capi.LINE_DTYPE)] * 3, [1, 2, 3])  # more frames than max_batch
+    c2.close()

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libvplines_b200.so")
 
 VPL_OK, VPL_E_INVALID, VPL_E_CUDA, VPL_E_CAPACITY, VPL_E_NODEVICE = 0, -1, -2, -3, -4
 STAGES = ["h2d", "pyramid", "scale", "angle", "order", "region", "nfa", "pack", "lbd", "match", "d2h", "preproc",
-          "ed_grad", "ed_anchor", "ed_walk", "ed_fit", "lm_pyramid", "lm_track", "lm_vote"]
+          "ed_grad", "ed_anchor", "ed_walk", "ed_fit", "lm_pyramid", "lm_track", "lm_vote", "vp_prep", "vp_vote", "vp_score",
+          "vp_classify"]
 
 KEYLINE_DTYPE = np.dtype(
     [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
@@ -79,6 +80,7 @@ EXPORTS = [
     "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
     "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
+    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -149,6 +151,12 @@ def load():
     L.vpl_linefront_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32]
     L.vpl_linefront_collect.argtypes = [vp, i32, vp, vp, i32, vp]
     L.vpl_linefront_run_resident.argtypes = [vp, i32]
+    L.vpl_vp_configure.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    L.vpl_vp_detect_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
+    L.vpl_vp_submit.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, vp, i32]
+    L.vpl_vp_collect.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.vpl_vp_run_resident.argtypes = [vp, i32]
+    L.vpl_debug_vp.argtypes = [vp, i32, vp, vp, vp]
     _lib = L
     return L
 
@@ -426,6 +434,60 @@ class Context:
 
     def linefront_run_resident(self, slot):
         self._ck(self._L.vpl_linefront_run_resident(self._h, slot))
+
+    # -- vanishing points (vanishing_point_detection::run_vanishing_point_detection) ----------
+    def vp_configure(self, f, cx, cy):
+        """= vanishing_point_detection::init(f, cx, cy, .)."""
+        self._ck(self._L.vpl_vp_configure(self._h, float(f), float(cx), float(cy)))
+
+    @staticmethod
+    def _vp_pack(sets):
+        cap = max(1, max(len(a) for a in sets))
+        arr = np.zeros((len(sets), cap), LINE_DTYPE)
+        cnt = np.array([len(a) for a in sets], np.int32)
+        for i, a in enumerate(sets):
+            arr[i, :cnt[i]] = np.asarray(a).view(LINE_DTYPE).reshape(-1)
+        return arr, cnt
+
+    def vp_detect_batch(self, lines, seeds, all_lines=None, frame_count0=0, with_line_vps=False):
+        """lines / all_lines: one LINE_DTYPE array per frame (all_lines None = the same sets); seeds: what
+        time(NULL) returned per frame -> (vps (n,3,3) float64, [vp_idx per frame], status (n,) int32
+        [, line_vps per frame (k,4)])."""
+        n = len(lines)
+        la, na = self._vp_pack(list(lines) + (list(all_lines) if all_lines is not None else []))
+        cap = la.shape[1]
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        assert len(seeds) == n
+        vps = np.zeros((n, 3, 3), np.float64); idx = np.full((n, cap), -1, np.int32); st = np.zeros(n, np.int32)
+        lv = np.zeros((n, cap, 4), np.float64) if with_line_vps else None
+        al = la[n:] if all_lines is not None else None
+        nal = na[n:] if all_lines is not None else None
+        self._ck(self._L.vpl_vp_detect_batch(self._h, _ptr(la[:n]), _ptr(na[:n]), _ptr(al), _ptr(nal), n, cap,
+                                             _ptr(seeds), int(frame_count0), _ptr(vps), _ptr(idx), _ptr(lv), _ptr(st)))
+        cnt = nal if all_lines is not None else na[:n]
+        out = (vps, [idx[i, :cnt[i]].copy() for i in range(n)], st)
+        if with_line_vps:
+            out += ([lv[i, :cnt[i]].copy() for i in range(n)],)
+        return out
+
+    def vp_submit(self, slot, lines, n_lines, seeds, frame_count0=0):
+        """lines (n, cap) LINE_DTYPE, n_lines (n,) int32, seeds (n,) uint32: classified set = the same set."""
+        n, cap = lines.shape
+        self._ck(self._L.vpl_vp_submit(self._h, slot, _ptr(lines), _ptr(n_lines), None, None, n, cap, _ptr(seeds),
+                                       int(frame_count0)))
+        return n
+
+    def vp_collect_into(self, slot, cap, vps, vp_idx, status=None, line_vps=None):
+        self._ck(self._L.vpl_vp_collect(self._h, slot, cap, _ptr(vps), _ptr(vp_idx), _ptr(line_vps), _ptr(status)))
+
+    def vp_run_resident(self, slot):
+        self._ck(self._L.vpl_vp_run_resident(self._h, slot))
+
+    def vp_debug(self, frame, n_it=105):
+        """Stage outputs of `frame` of the last batch on slot 0 -> dict(grid, best_idx, pairs)."""
+        grid = np.zeros((90, 360), np.float64); best = C.c_int32(0); pairs = np.zeros((n_it, 2), np.int32)
+        self._ck(self._L.vpl_debug_vp(self._h, frame, _ptr(grid), C.byref(best), _ptr(pairs)))
+        return dict(grid=grid, best_idx=best.value, pairs=pairs)
 
     # -- raw stages ----------------------------------------------------------------
     def lsd_raw(self, img, cap=1 << 15):

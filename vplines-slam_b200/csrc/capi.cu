@@ -79,6 +79,25 @@ struct Slot {
   int lm_pairs = 0, lm_pstride = 1;
   VplSegment* d_seg = nullptr;
   int* d_seg_count = nullptr;
+  // vanishing points (allocated by vpl_vp_configure)
+  VpBuffers vp = {};
+  VplLine* d_vp_lines = nullptr;   // B x cap: the hypothesis / vote set
+  VplLine* d_vp_all = nullptr;     // B x cap: the classified set
+  int* d_vp_n = nullptr;           // 2 x B: n_lines, n_all
+  unsigned* d_vp_seeds = nullptr;  // B
+  double* d_vps = nullptr;         // B x 9
+  int* d_vp_idx = nullptr;         // B x cap
+  double* d_line_vps = nullptr;    // B x cap x 4
+  VplLine* h_vp_lines = nullptr;
+  VplLine* h_vp_all = nullptr;
+  int* h_vp_n = nullptr;
+  unsigned* h_vp_seeds = nullptr;
+  double* h_vps = nullptr;
+  int* h_vp_idx = nullptr;
+  double* h_line_vps = nullptr;
+  int* h_vp_status = nullptr;      // 2 x B: status, flags
+  bool vp_batch = false, vp_same = true;
+  int vp_n = 0, vp_fc0 = 0;
   // pinned host staging
   uint8_t* h_img = nullptr;
   VplKeyLine* h_kl = nullptr;
@@ -118,6 +137,9 @@ struct VplContext {
   VplEDLineParam edp;
   bool lm_ready = false;  // vpl_linematch_configure has run
   VplLineMatchParam lmp;
+  bool vp_ready = false;  // vpl_vp_configure has run
+  VpParams vpp;
+  double* d_vp_lambda = nullptr;
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -692,6 +714,48 @@ void run_linematch(VplContext* c, Slot& s, const int* d_counts, int n_frames, in
   }
 }
 
+void vp_free(Slot& s) {
+  cudaFree(s.vp.para); cudaFree(s.vp.length); cudaFree(s.vp.orient); cudaFree(s.vp.vp1); cudaFree(s.vp.pairs);
+  cudaFree(s.vp.rng); cudaFree(s.vp.status); cudaFree(s.vp.grid); cudaFree(s.vp.grid_new);
+  cudaFree(s.vp.part_best); cudaFree(s.vp.part_idx); cudaFree(s.vp.best_idx); cudaFree(s.vp.lx);
+  cudaFree(s.d_vp_lines); cudaFree(s.d_vp_all); cudaFree(s.d_vp_n); cudaFree(s.d_vp_seeds); cudaFree(s.d_vps);
+  cudaFree(s.d_vp_idx); cudaFree(s.d_line_vps);
+  cudaFreeHost(s.h_vp_lines); cudaFreeHost(s.h_vp_all); cudaFreeHost(s.h_vp_n); cudaFreeHost(s.h_vp_seeds);
+  cudaFreeHost(s.h_vps); cudaFreeHost(s.h_vp_idx); cudaFreeHost(s.h_line_vps); cudaFreeHost(s.h_vp_status);
+  s.vp = VpBuffers{};
+  s.d_vp_lines = s.d_vp_all = nullptr; s.d_vp_n = nullptr; s.d_vp_seeds = nullptr; s.d_vps = nullptr;
+  s.d_vp_idx = nullptr; s.d_line_vps = nullptr;
+  s.h_vp_lines = s.h_vp_all = nullptr; s.h_vp_n = nullptr; s.h_vp_seeds = nullptr; s.h_vps = nullptr;
+  s.h_vp_idx = nullptr; s.h_line_vps = nullptr; s.h_vp_status = nullptr;
+}
+
+// the stage on the n frames whose lines sit in d_vp_lines / d_vp_all
+void run_vp(VplContext* c, Slot& s) {
+  const int B = c->cfg.max_batch, cap = c->cfg.max_lines;
+  const VplLine* all = s.vp_same ? s.d_vp_lines : s.d_vp_all;
+  const int* n_all = s.vp_same ? s.d_vp_n : s.d_vp_n + B;
+  {
+    StageTimer t(c, s, VPL_STAGE_VP_PREP);
+    launch_vp_prepare(s.d_vp_lines, s.d_vp_n, cap, s.d_vp_seeds, s.vp, c->vpp, s.vp_n, s.stream);
+    t.launches(1);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_VP_VOTE);
+    launch_vp_vote(s.d_vp_n, cap, s.vp, c->vpp, s.vp_n, s.stream);
+    t.launches(2);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_VP_SCORE);
+    launch_vp_score(s.vp, c->vpp, s.vp_n, s.stream);
+    t.launches(1);
+  }
+  {
+    StageTimer t(c, s, VPL_STAGE_VP_CLASSIFY);
+    launch_vp_classify(all, n_all, cap, s.vp_fc0, s.vp, c->vpp, s.vp_n, s.d_vps, s.d_vp_idx, s.d_line_vps, s.stream);
+    t.launches(1);
+  }
+}
+
 int lm_check(VplContext* c) {
   if (!c) return VPL_E_INVALID;
   if (!c->lm_ready) return fail(c, VPL_E_INVALID, "call vpl_linematch_configure first");
@@ -733,6 +797,7 @@ void vpl_destroy(VplContext* c) {
   for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
   cudaFree(c->d_mapx); cudaFree(c->d_mapy); cudaFree(c->d_wtab);
   cudaFree(c->d_lgam);
+  cudaFree(c->d_vp_lambda);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut);
     for (int o = 0; o < kMaxOctaves; ++o) {
@@ -745,6 +810,7 @@ void vpl_destroy(VplContext* c) {
     cudaFree(s.d_offsets); cudaFree(s.d_kl_dense); cudaFree(s.d_desc_dense); cudaFree(s.d_match_dense);
     ed_free(s);
     lm_free(s);
+    vp_free(s);
     cudaFreeHost(s.h_offsets);
     cudaFreeHost(s.h_img); cudaFreeHost(s.h_kl); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_desc);
     cudaFreeHost(s.h_match); cudaFreeHost(s.h_flags);
@@ -1501,6 +1567,181 @@ int vpl_debug_linematch_points(VplContext* c, int pair, float* kps_ref, float* k
   if (status) CK(c, cudaMemcpy(status, s.lm.status + o, (size_t)nk, cudaMemcpyDeviceToHost));
   if (err) CK(c, cudaMemcpy(err, s.lm.err + o, (size_t)nk * 4, cudaMemcpyDeviceToHost));
   if (kp2line_cur) CK(c, cudaMemcpy(kp2line_cur, s.lm.kp2line + o, (size_t)nk * 4, cudaMemcpyDeviceToHost));
+  return VPL_OK;
+}
+
+// ---- vanishing points -----------------------------------------------------------------------------
+int vpl_vp_configure(VplContext* c, float f, float cx, float cy) {
+  if (!c) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots)
+    if (s.in_flight) return fail(c, VPL_E_INVALID, "vpl_vp_configure while a batch is in flight");
+  CK(c, cudaDeviceSynchronize());
+  c->vp_ready = false;
+  c->vpp.f = f; c->vpp.ppx = cx; c->vpp.ppy = cy;
+  {  // getVPHypVia2Lines' iteration count, as the reference computes it (vanishing_point_detection.cpp:93-97)
+    double noiseRatio = 0.5;
+    double p = 1.0 / 3.0 * pow(1.0 - noiseRatio, 2);
+    double confEfficience = 0.9999;
+    c->vpp.it = (int)(log(1 - confEfficience) / log(1.0 - p));
+  }
+  c->vpp.max_draws = 1000000;
+  const size_t B = (size_t)c->cfg.max_batch, cap = (size_t)c->cfg.max_lines, it = (size_t)c->vpp.it;
+  if (!c->d_vp_lambda) CK(c, dmalloc(&c->d_vp_lambda, 720));
+  launch_vp_lambda(c->d_vp_lambda, 0);
+  c->launches += 1;
+  CK(c, cudaDeviceSynchronize());
+  for (Slot& s : c->slots) {
+    vp_free(s);
+    CK(c, dmalloc(&s.vp.para, B * cap * 3));
+    CK(c, dmalloc(&s.vp.length, B * cap));
+    CK(c, dmalloc(&s.vp.orient, B * cap));
+    CK(c, dmalloc(&s.vp.vp1, B * it * 3));
+    CK(c, dmalloc(&s.vp.pairs, B * it * 2));
+    CK(c, dmalloc(&s.vp.rng, B * 33));
+    CK(c, dmalloc(&s.vp.status, 2 * B));
+    s.vp.flags = s.vp.status + B;
+    CK(c, dmalloc(&s.vp.grid, B * kVpCells));
+    CK(c, dmalloc(&s.vp.grid_new, B * kVpCells));
+    s.vp.lambda_sc = c->d_vp_lambda;
+    CK(c, dmalloc(&s.vp.part_best, B * kVpMaxSplits));
+    CK(c, dmalloc(&s.vp.part_idx, B * kVpMaxSplits));
+    CK(c, dmalloc(&s.vp.best_idx, B));
+    CK(c, dmalloc(&s.vp.lx, B * cap));
+    CK(c, dmalloc(&s.d_vp_lines, B * cap));
+    CK(c, dmalloc(&s.d_vp_all, B * cap));
+    CK(c, dmalloc(&s.d_vp_n, 2 * B));
+    CK(c, dmalloc(&s.d_vp_seeds, B));
+    CK(c, dmalloc(&s.d_vps, B * 9));
+    CK(c, dmalloc(&s.d_vp_idx, B * cap));
+    CK(c, dmalloc(&s.d_line_vps, B * cap * 4));
+    CK(c, hmalloc(&s.h_vp_lines, B * cap));
+    CK(c, hmalloc(&s.h_vp_all, B * cap));
+    CK(c, hmalloc(&s.h_vp_n, 2 * B));
+    CK(c, hmalloc(&s.h_vp_seeds, B));
+    CK(c, hmalloc(&s.h_vps, B * 9));
+    CK(c, hmalloc(&s.h_vp_idx, B * cap));
+    CK(c, hmalloc(&s.h_line_vps, B * cap * 4));
+    CK(c, hmalloc(&s.h_vp_status, 2 * B));
+    CK(c, cudaMemset(s.vp.status, 0, 2 * B * sizeof(int)));
+  }
+  c->vp_ready = true;
+  return VPL_OK;
+}
+
+int vpl_vp_submit(VplContext* c, int slot, const VplLine* lines, const int32_t* n_lines, const VplLine* all_lines,
+                  const int32_t* n_all, int n_frames, int cap, const uint32_t* seeds, int frame_count0) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (n_frames <= 0 || n_frames > c->cfg.max_batch) return fail(c, VPL_E_CAPACITY, "n_frames %d outside 1..max_batch %d", n_frames, c->cfg.max_batch);
+  if (!lines || !n_lines || !seeds || cap < 0 || (all_lines && !n_all)) return fail(c, VPL_E_INVALID, "null argument");
+  const int mcap = c->cfg.max_lines, B = c->cfg.max_batch;
+  for (int i = 0; i < n_frames; ++i) {
+    const int na = all_lines ? n_all[i] : n_lines[i];
+    if (n_lines[i] < 0 || na < 0 || n_lines[i] > cap || na > cap || n_lines[i] > mcap || na > mcap)
+      return fail(c, VPL_E_CAPACITY, "frame %d: %d / %d lines exceed cap %d or max_lines %d", i, n_lines[i], na, cap, mcap);
+  }
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  s.vp_n = n_frames; s.vp_fc0 = frame_count0; s.vp_same = all_lines == nullptr;
+  {
+    StageTimer t(c, s, VPL_STAGE_H2D);
+    for (int i = 0; i < n_frames; ++i) {
+      memcpy(s.h_vp_lines + (size_t)i * mcap, lines + (size_t)i * cap, (size_t)n_lines[i] * sizeof(VplLine));
+      s.h_vp_n[i] = n_lines[i];
+      s.h_vp_seeds[i] = seeds[i];
+      if (all_lines) {
+        memcpy(s.h_vp_all + (size_t)i * mcap, all_lines + (size_t)i * cap, (size_t)n_all[i] * sizeof(VplLine));
+        s.h_vp_n[B + i] = n_all[i];
+      }
+    }
+    // only the rows in use travel: one copy per frame would be launch-bound, so whole rows up to the longest count
+    CK(c, cudaMemcpyAsync(s.d_vp_lines, s.h_vp_lines, (size_t)n_frames * mcap * sizeof(VplLine), cudaMemcpyHostToDevice, s.stream));
+    if (all_lines)
+      CK(c, cudaMemcpyAsync(s.d_vp_all, s.h_vp_all, (size_t)n_frames * mcap * sizeof(VplLine), cudaMemcpyHostToDevice, s.stream));
+    CK(c, cudaMemcpyAsync(s.d_vp_n, s.h_vp_n, (size_t)2 * B * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+    CK(c, cudaMemcpyAsync(s.d_vp_seeds, s.h_vp_seeds, (size_t)n_frames * sizeof(unsigned), cudaMemcpyHostToDevice, s.stream));
+  }
+  run_vp(c, s);
+  {
+    StageTimer t(c, s, VPL_STAGE_D2H);
+    CK(c, cudaMemcpyAsync(s.h_vps, s.d_vps, (size_t)n_frames * 9 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaMemcpyAsync(s.h_vp_idx, s.d_vp_idx, (size_t)n_frames * mcap * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaMemcpyAsync(s.h_vp_status, s.vp.status, (size_t)2 * B * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  }
+  CK(c, cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  s.vp_batch = true;
+  return VPL_OK;
+}
+
+int vpl_vp_collect(VplContext* c, int slot, int cap, double* vps, int32_t* vp_idx, double* line_vps, int32_t* status) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight || !s.vp_batch) return fail(c, VPL_E_INVALID, "slot %d has no vanishing-point batch in flight", slot);
+  if (!vps || !vp_idx) return fail(c, VPL_E_INVALID, "null output");
+  CK(c, cudaSetDevice(c->cfg.device));
+  const int mcap = c->cfg.max_lines, B = c->cfg.max_batch, n = s.vp_n;
+  if (line_vps)  // the per-line Vector4d copies are optional and 32 bytes per line: fetched only on request
+    CK(c, cudaMemcpyAsync(s.h_line_vps, s.d_line_vps, (size_t)n * mcap * 4 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  int r = finish(c, s);
+  s.vp_batch = false;
+  if (r) return r;
+  memcpy(vps, s.h_vps, (size_t)n * 9 * sizeof(double));
+  const int* na = s.vp_same ? s.h_vp_n : s.h_vp_n + B;
+  for (int i = 0; i < n; ++i) {
+    if (na[i] > cap) return fail(c, VPL_E_CAPACITY, "frame %d: %d lines > cap %d", i, na[i], cap);
+    memcpy(vp_idx + (size_t)i * cap, s.h_vp_idx + (size_t)i * mcap, (size_t)na[i] * sizeof(int));
+    if (line_vps) memcpy(line_vps + (size_t)i * cap * 4, s.h_line_vps + (size_t)i * mcap * 4, (size_t)na[i] * 4 * sizeof(double));
+    if (status) status[i] = s.h_vp_status[i] != 0 ? s.h_vp_status[i] : (s.h_vp_status[B + i] & 1);
+  }
+  return VPL_OK;
+}
+
+int vpl_vp_detect_batch(VplContext* c, const VplLine* lines, const int32_t* n_lines, const VplLine* all_lines,
+                        const int32_t* n_all, int n_frames, int cap, const uint32_t* seeds, int frame_count0,
+                        double* vps, int32_t* vp_idx, double* line_vps, int32_t* status) {
+  if (!c) return VPL_E_INVALID;
+  if (n_frames == 0) return c->vp_ready ? VPL_OK : fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  int r = vpl_vp_submit(c, 0, lines, n_lines, all_lines, n_all, n_frames, cap, seeds, frame_count0);
+  if (r) return r;
+  return vpl_vp_collect(c, 0, cap, vps, vp_idx, line_vps, status);
+}
+
+int vpl_vp_run_resident(VplContext* c, int slot) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.vp_n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no lines", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  run_vp(c, s);
+  return VPL_OK;
+}
+
+int vpl_debug_vp(VplContext* c, int frame, double* grid, int32_t* best_idx, int32_t* pairs) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  Slot& s = c->slots[0];
+  if (frame < 0 || frame >= s.vp_n) return fail(c, VPL_E_INVALID, "frame %d outside the last batch", frame);
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaStreamSynchronize(s.stream));
+  if (grid) CK(c, cudaMemcpy(grid, s.vp.grid_new + (size_t)frame * kVpCells, kVpCells * sizeof(double), cudaMemcpyDeviceToHost));
+  if (best_idx) CK(c, cudaMemcpy(best_idx, s.vp.best_idx + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  if (pairs) CK(c, cudaMemcpy(pairs, s.vp.pairs + (size_t)frame * c->vpp.it * 2, (size_t)c->vpp.it * 2 * sizeof(int), cudaMemcpyDeviceToHost));
   return VPL_OK;
 }
 

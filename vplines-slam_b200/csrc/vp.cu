@@ -1,0 +1,514 @@
+// vp.cu -- the reference's vanishing-point stage on the device (sm_100a).
+//
+// Replaces vanishing_point_detection::run_vanishing_point_detection
+// (/root/reference/feature_tracker/src/vanishing_point_detection.cpp:37-65, cited as vp.cpp), which
+// LineFeatureTracker::readImage calls on every frame after matching
+// (feature_tracker/src/line_feature_tracker.cpp:233-262).  CPU restatement: oracle/orc_vp.c
+// (pinned bit for bit against the reference's own file compiled here); the device follows its
+// math_mode 1 bit for bit.
+//
+// Stages, each one launch over all frames of the batch:
+//   vp_prepare_kernel  lineinfo (vp.cpp:67-88): p1 x p2, the reference's "length"/"orientation"
+//                      per line in parallel; then ONE thread replays srand(seed) and the rand()
+//                      draws of getVPHypVia2Lines (:107-130) -- glibc's additive generator, whose
+//                      stream is sequential -- and keeps the 105 first vanishing points vp1
+//   vp_vote_kernel     getSphereGrids (:180-250), ONE WARP PER FRAME: the cells are double sums in
+//                      (i, j) pair order, so the pairs are taken 32 at a time in that order, each
+//                      lane computes its pair's cell and weight, and the lanes that hit the same
+//                      cell (__match_any_sync) are added by their lowest lane in lane order: the
+//                      sum of every cell is formed in exactly the sequential order
+//   vp_smooth_kernel   the 3x3 neighbourhood pass (:252-275), one thread per cell
+//   vp_score_kernel    getVPHypVia2Lines' 360 (vp2, vp3) per vp1 (:139-172) fused with
+//                      getBestVpsHyp's scoring (:278-329): one thread per hypothesis, nothing
+//                      is stored but the best (sum, index) per CTA; lowest index wins ties
+//   vp_classify_kernel best hypothesis recomputed, vps[1]/vps[2] rule (:331-349), per-line angles
+//                      in parallel, then ONE thread runs lines2Vps' sequential part (:412-497:
+//                      its decisions consume the same rand() stream)
+//
+// Exactness.  The vote weights and the hypotheses go through atan2 / atan / sin / cos / acos; the
+// oracle and the device share one deterministic definition of them (vpl_sincos.cuh, vpl_atan.cuh,
+// correctly rounded in practice).  Where a transcendental only selects a grid cell, the CUDA library
+// function is used first and the shared one only when the cell coordinate lies within 1e-9 of a
+// cell boundary (their difference is < 1e-13), which gives the same cell for a fraction of the
+// work; a hypothesis whose construction is numerically delicate (vp3.z ~ 0 decides a sign) is
+// recomputed with the shared functions.  -fmad=false, IEEE sqrt/div, sums in the reference's order.
+#include <limits.h>
+
+#include "vpl_atan.cuh"
+#include "vpl_common.cuh"
+
+namespace vpl {
+
+namespace {
+
+constexpr double kPi = 3.1415926535897932384626433832795;  // CV_PI
+constexpr int kLA = 90, kLO = 360, kCells = kLA * kLO;
+constexpr int kNumVp2 = 360;
+constexpr double kGuard = 1e-9;
+
+struct GRand {  // glibc random_r TYPE_3 state (what srand()/rand() run)
+  int r[31];
+  int f, b;
+};
+__device__ __forceinline__ int grand_next(GRand& g) {
+  const unsigned v = (unsigned)g.r[g.f] + (unsigned)g.r[g.b];
+  g.r[g.f] = (int)v;
+  if (++g.f >= 31) g.f = 0;
+  if (++g.b >= 31) g.b = 0;
+  return (int)(v >> 1);
+}
+__device__ void grand_seed(GRand& g, unsigned seed) {
+  if (seed == 0) seed = 1;
+  int word = (int)seed;
+  g.r[0] = (int)seed;
+  for (int i = 1; i < 31; ++i) {
+    const long long hi = word / 127773, lo = word % 127773;
+    const long long w = 16807 * lo - 2836 * hi;
+    word = (int)w;
+    if (word < 0) word += 2147483647;
+    g.r[i] = word;
+  }
+  g.f = 3;
+  g.b = 0;
+  for (int i = 0; i < 310; ++i) (void)grand_next(g);
+}
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 cross3(const V3& a, const V3& b) {
+  V3 r;
+  r.x = a.y * b.z - a.z * b.y;
+  r.y = a.z * b.x - a.x * b.z;
+  r.z = a.x * b.y - a.y * b.x;
+  return r;
+}
+__device__ __forceinline__ void normalize_pos_z(V3& v) {  // vp.cpp:150-153 / :157-160
+  if (v.z == 0.0) v.z = 0.0011;
+  const double N = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  const double s = 1.0 / N;
+  v.x *= s; v.y *= s; v.z *= s;
+  if (v.z < 0) { v.x *= -1.0; v.y *= -1.0; v.z *= -1.0; }
+}
+
+// cell coordinate of an angle: int(angle / accuracy); `risky` when the quotient is close to an integer
+__device__ __forceinline__ int cell_of(double ang, double acc, bool& risky) {
+  const double q = ang / acc;
+  const int c = (int)q;
+  const double fr = q - (double)c;
+  risky |= fr < kGuard || fr > 1.0 - kGuard;
+  return c;
+}
+
+// ---- lineinfo + the random line pairs -----------------------------------------------------------
+__global__ void __launch_bounds__(128) vp_prepare_kernel(const VplLine* __restrict__ lines, const int* __restrict__ n_lines,
+                                                         int cap, VpBuffers B, VpParams P, const unsigned* __restrict__ seeds) {
+  const int frame = blockIdx.x;
+  const int n = n_lines[frame];
+  __shared__ GRand g;
+  if (threadIdx.x == 0) B.flags[frame] = 0;
+  if (n < 2) {
+    if (threadIdx.x == 0) B.status[frame] = -1;
+    return;
+  }
+  const VplLine* L = lines + (size_t)frame * cap;
+  double* para = B.para + (size_t)frame * cap * 3;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x1 = L[i].endpoint[0], y1 = L[i].endpoint[1], x2 = L[i].endpoint[2], y2 = L[i].endpoint[3];
+    const V3 p1 = {(double)x1, (double)y1, 1.0}, p2 = {(double)x2, (double)y2, 1.0};
+    const V3 c = cross3(p1, p2);
+    para[3 * i] = c.x; para[3 * i + 1] = c.y; para[3 * i + 2] = c.z;
+    const double dx = (double)(x1 - y1);  // float differences of these operands, as the reference writes them (:79-80)
+    const double dy = (double)(x2 - y2);
+    B.length[(size_t)frame * cap + i] = sqrt(dx * dx + dy * dy);
+    double o = vpl_atan2_cr(dy, dx);
+    if (o < 0) o += kPi;
+    B.orient[(size_t)frame * cap + i] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  grand_seed(g, seeds[frame]);
+  long long draws = 0;
+  int st = 0;
+  double* vp1s = B.vp1 + (size_t)frame * P.it * 3;
+  int* pairs = B.pairs + (size_t)frame * P.it * 2;
+  for (int i = 0; i < P.it; ++i) {
+    const int idx1 = grand_next(g) % n;
+    int idx2 = grand_next(g) % n;
+    draws += 2;
+    while (idx2 == idx1) { idx2 = grand_next(g) % n; ++draws; }
+    if (draws > P.max_draws) { st = -2; break; }
+    const V3 a = {para[3 * idx1], para[3 * idx1 + 1], para[3 * idx1 + 2]};
+    const V3 b = {para[3 * idx2], para[3 * idx2 + 1], para[3 * idx2 + 2]};
+    const V3 v = cross3(a, b);
+    if (v.z == 0) { --i; continue; }
+    V3 vp1 = {v.x / v.z - P.ppx, v.y / v.z - P.ppy, P.f};
+    if (vp1.z == 0) vp1.z = 0.0011;
+    const double N = sqrt(vp1.x * vp1.x + vp1.y * vp1.y + vp1.z * vp1.z);
+    const double s = 1.0 / N;
+    vp1.x *= s; vp1.y *= s; vp1.z *= s;
+    vp1s[3 * i] = vp1.x; vp1s[3 * i + 1] = vp1.y; vp1s[3 * i + 2] = vp1.z;
+    pairs[2 * i] = idx1; pairs[2 * i + 1] = idx2;
+  }
+  int* gs = B.rng + (size_t)frame * 33;
+  for (int i = 0; i < 31; ++i) gs[i] = g.r[i];
+  gs[31] = g.f; gs[32] = g.b;
+  B.status[frame] = st;
+}
+
+// ---- getSphereGrids: the vote -------------------------------------------------------------------
+constexpr int kVoteWarps = 4;
+__global__ void __launch_bounds__(kVoteWarps * 32) vp_vote_kernel(const int* __restrict__ n_lines, int cap, VpBuffers B,
+                                                                  VpParams P, int n_frames) {
+  __shared__ double s_val[kVoteWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frame = blockIdx.x * kVoteWarps + warp;
+  if (frame >= n_frames || B.status[frame] != 0) return;
+  const int n = n_lines[frame];
+  const double* para = B.para + (size_t)frame * cap * 3;
+  const double* length = B.length + (size_t)frame * cap;
+  const double* orient = B.orient + (size_t)frame * cap;
+  double* grid = B.grid + (size_t)frame * kCells;
+  const double acc = 1.0 / 180.0 * kPi;         // angelAccuracy
+  const double tol = 60.0 / 180.0 * kPi;        // angelTolerance
+  for (int i = 0; i < n - 1; ++i) {
+    const V3 pi = {para[3 * i], para[3 * i + 1], para[3 * i + 2]};
+    const double li = length[i], oi = orient[i];
+    for (int jb = i + 1; jb < n; jb += 32) {
+      const int j = jb + lane;
+      int cell = -1;
+      double val = 0.0;
+      if (j < n) {
+        const V3 pj = {para[3 * j], para[3 * j + 1], para[3 * j + 2]};
+        const V3 pt = cross3(pi, pj);
+        double dev = fabs(oi - orient[j]);
+        dev = (kPi - dev < dev) ? kPi - dev : dev;
+        if (pt.z != 0 && !(dev > tol)) {
+          const double x = pt.x / pt.z, y = pt.y / pt.z;
+          const double X = x - P.ppx, Y = y - P.ppy, Z = P.f;
+          const double N = sqrt(X * X + Y * Y + Z * Z);
+          const double zn = Z / N;
+          bool risky = false;
+          double lat = acos(zn), lon = atan2(X, Y) + kPi;
+          int la = cell_of(lat, acc, risky), lo = cell_of(lon, acc, risky);
+          if (risky || !(lat == lat) || !(lon == lon)) {
+            lat = vpl_acos_cr(zn);
+            lon = vpl_atan2_cr(X, Y) + kPi;
+            la = (int)(lat / acc);
+            lo = (int)(lon / acc);
+          }
+          if (lat == lat && lon == lon) {
+            if (la >= kLA) la = kLA - 1;
+            if (lo >= kLO) lo = kLO - 1;
+            if (la >= 0 && lo >= 0) {
+              double s, c;
+              vpl_sincos_cr(2.0 * dev, &s, &c);
+              val = sqrt(li * length[j]) * (s + 0.2);
+              cell = la * kLO + lo;
+            }
+          }
+        }
+      }
+      s_val[warp][lane] = val;
+      __syncwarp();
+      const unsigned valid = __ballot_sync(0xffffffffu, cell >= 0);
+      if (cell >= 0) {
+        const unsigned m = __match_any_sync(valid, cell);
+        if ((__ffs(m) - 1) == lane) {  // lowest lane of the group adds its members in lane (= j) order
+          double a = grid[cell];
+          unsigned t = m;
+          while (t) {
+            const int src = __ffs(t) - 1;
+            t &= t - 1;
+            a += s_val[warp][src];
+          }
+          grid[cell] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- 3x3 pass -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vp_smooth_kernel(VpBuffers B, int n_frames) {
+  const int frame = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kCells || B.status[frame] != 0) return;
+  const double* g = B.grid + (size_t)frame * kCells;
+  const int i = c / kLO, j = c - i * kLO;
+  double out = 0.0;
+  if (i >= 1 && i < kLA - 1 && j >= 1 && j < kLO - 1) {
+    double tot = 0.0;
+#pragma unroll
+    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+      for (int b = -1; b <= 1; ++b) tot += g[(i + a) * kLO + (j + b)];
+    out = g[c] + tot / 9;
+  }
+  B.grid_new[(size_t)frame * kCells + c] = out;
+}
+
+// ---- hypotheses + scoring -----------------------------------------------------------------------
+// vp2 / vp3 of hypothesis (vp1, j) (vp.cpp:139-160).  CR: the shared deterministic functions.
+template <bool CR>
+__device__ __forceinline__ void make_hypothesis(const V3& vp1, double sl, double cl, V3& vp2, V3& vp3, bool& risky) {
+  const double k1 = vp1.x * sl + vp1.y * cl;
+  const double k2 = vp1.z;
+  const double t = -k2 / k1;
+  double Z, sp;
+  if (CR) {
+    const double phi = vpl_atan_cr(t);
+    vpl_sincos_cr(phi, &sp, &Z);
+  } else {
+    const double phi = atan(t);
+    sincos(phi, &sp, &Z);
+  }
+  vp2.x = sp * sl; vp2.y = sp * cl; vp2.z = Z;
+  normalize_pos_z(vp2);
+  vp3 = cross3(vp1, vp2);
+  if (!CR) risky |= fabs(vp3.z) < kGuard || !(t == t);
+  normalize_pos_z(vp3);
+}
+// sphere cell of a unit vector (vp.cpp:291-316); false = contributes nothing
+template <bool CR>
+__device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell, bool& risky) {
+  if (v.z == 0.0) return false;
+  double lat, lon;
+  if (CR) {
+    lat = vpl_acos_cr(v.z);
+    lon = vpl_atan2_cr(v.x, v.y) + kPi;
+  } else {
+    lat = acos(v.z);
+    lon = atan2(v.x, v.y) + kPi;
+    risky |= v.z > 1.0 - 1e-12 || !(lat == lat) || !(lon == lon);
+  }
+  if (!(lat == lat) || !(lon == lon)) return false;
+  int la, lo;
+  if (CR) { la = (int)(lat / one); lo = (int)(lon / one); }
+  else { la = cell_of(lat, one, risky); lo = cell_of(lon, one, risky); }
+  if (la == 90) la = 89;
+  if (lo == 360) lo = 359;
+  if (la < 0 || la >= kLA || lo < 0 || lo >= kLO) return false;
+  cell = la * kLO + lo;
+  return true;
+}
+template <bool CR>
+__device__ __forceinline__ double score_hypothesis(const double* __restrict__ g, const V3& vp1, int cell1, bool has1,
+                                                   double sl, double cl, bool& risky) {
+  V3 vp2, vp3;
+  make_hypothesis<CR>(vp1, sl, cl, vp2, vp3, risky);
+  double len = 0.0;
+  if (has1) len += g[cell1];
+  int c;
+  if (vp_cell<CR>(vp2, 1.0 / 180.0 * kPi, c, risky)) len += g[c];
+  if (vp_cell<CR>(vp3, 1.0 / 180.0 * kPi, c, risky)) len += g[c];
+  return len;
+}
+
+constexpr int kScoreThreads = 256;
+// grid (splits, frames): split s scores the outer iterations i = s, s + splits, ...
+__global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, VpParams P, int splits) {
+  const int frame = blockIdx.y, split = blockIdx.x;
+  if (B.status[frame] != 0) return;
+  const double* g = B.grid_new + (size_t)frame * kCells;
+  const double* vp1s = B.vp1 + (size_t)frame * P.it * 3;
+  const double one = 1.0 / 180.0 * kPi;
+  double best = 0.0;
+  int best_idx = INT_MAX;
+  for (int i = split; i < P.it; i += splits) {
+    const V3 vp1 = {vp1s[3 * i], vp1s[3 * i + 1], vp1s[3 * i + 2]};
+    int cell1 = 0;
+    bool r1 = false;
+    const bool has1 = vp_cell<true>(vp1, one, cell1, r1);
+    for (int j = threadIdx.x; j < kNumVp2; j += kScoreThreads) {
+      const double sl = B.lambda_sc[2 * j], cl = B.lambda_sc[2 * j + 1];
+      bool risky = false;
+      double len = score_hypothesis<false>(g, vp1, cell1, has1, sl, cl, risky);
+      if (risky) len = score_hypothesis<true>(g, vp1, cell1, has1, sl, cl, risky);
+      const int idx = i * kNumVp2 + j;
+      if (len > best) { best = len; best_idx = idx; }  // a thread's indices ascend: strict > keeps the lowest
+    }
+  }
+  // block arg-max, lowest index on ties
+  __shared__ double s_b[kScoreThreads / 32];
+  __shared__ int s_i[kScoreThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_down_sync(0xffffffffu, best, o);
+    const int oi = __shfl_down_sync(0xffffffffu, best_idx, o);
+    if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_b[warp] = best; s_i[warp] = best_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kScoreThreads / 32; ++w)
+      if (s_b[w] > best || (s_b[w] == best && s_i[w] < best_idx)) { best = s_b[w]; best_idx = s_i[w]; }
+    B.part_best[(size_t)frame * splits + split] = best;
+    B.part_idx[(size_t)frame * splits + split] = best_idx;
+  }
+}
+
+// ---- best hypothesis, vps[1]/vps[2] rule, lines2Vps ---------------------------------------------
+__device__ __forceinline__ float seg_angle(const VplLine& s) {  // vp.cpp:23-28: std::atan2(float, float)
+  if (s.endpoint[2] > s.endpoint[0])
+    return (float)vpl_atan2_cr((double)(s.endpoint[3] - s.endpoint[1]), (double)(s.endpoint[2] - s.endpoint[0]));
+  return (float)vpl_atan2_cr((double)(s.endpoint[1] - s.endpoint[3]), (double)(s.endpoint[0] - s.endpoint[2]));
+}
+
+__global__ void __launch_bounds__(128) vp_classify_kernel(const VplLine* __restrict__ all_lines, const int* __restrict__ n_all,
+                                                          int cap, VpBuffers B, VpParams P, int splits, int frame_count0,
+                                                          double* __restrict__ vps_out, int* __restrict__ vp_idx,
+                                                          double* __restrict__ line_vps) {
+  const int frame = blockIdx.x;
+  const int na = n_all[frame];
+  const int st = B.status[frame];
+  int* out_idx = vp_idx + (size_t)frame * cap;
+  double* out_lv = line_vps ? line_vps + (size_t)frame * cap * 4 : nullptr;
+  __shared__ double s_vps[9];
+  __shared__ double s_vp2d[6];
+  __shared__ GRand g;
+  if (st != 0) {  // the tracker's "no vp lines" branch (line_feature_tracker.cpp:266-276): nothing is labelled
+    for (int i = threadIdx.x; i < na; i += blockDim.x) {
+      out_idx[i] = 3;
+      if (out_lv) { out_lv[4 * i] = 0; out_lv[4 * i + 1] = 0; out_lv[4 * i + 2] = 0; out_lv[4 * i + 3] = 0; }
+    }
+    if (threadIdx.x < 9) vps_out[(size_t)frame * 9 + threadIdx.x] = 0.0;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    double best = 0.0;
+    int bi = INT_MAX;
+    for (int s = 0; s < splits; ++s) {
+      const double b = B.part_best[(size_t)frame * splits + s];
+      const int i = B.part_idx[(size_t)frame * splits + s];
+      if (b > best || (b == best && i < bi)) { best = b; bi = i; }
+    }
+    if (bi == INT_MAX) bi = 0;
+    B.best_idx[frame] = bi;
+    const int i = bi / kNumVp2, j = bi - i * kNumVp2;
+    const double* v1 = B.vp1 + ((size_t)frame * P.it + i) * 3;
+    const V3 vp1 = {v1[0], v1[1], v1[2]};
+    V3 vp2, vp3;
+    bool r = false;
+    make_hypothesis<true>(vp1, B.lambda_sc[2 * j], B.lambda_sc[2 * j + 1], vp2, vp3, r);
+    if (frame_count0 + frame != 0 && !(fabs(vp2.y) > 0.8)) { const V3 t = vp2; vp2 = vp3; vp3 = t; }  // :337-349
+    s_vps[0] = vp1.x; s_vps[1] = vp1.y; s_vps[2] = vp1.z;
+    s_vps[3] = vp2.x; s_vps[4] = vp2.y; s_vps[5] = vp2.z;
+    s_vps[6] = vp3.x; s_vps[7] = vp3.y; s_vps[8] = vp3.z;
+    for (int k = 0; k < 3; ++k) {  // :378-385
+      s_vp2d[2 * k] = s_vps[3 * k] * P.f / s_vps[3 * k + 2] + P.ppx;
+      s_vp2d[2 * k + 1] = s_vps[3 * k + 1] * P.f / s_vps[3 * k + 2] + P.ppy;
+    }
+    const int* gs = B.rng + (size_t)frame * 33;
+    for (int k = 0; k < 31; ++k) g.r[k] = gs[k];
+    g.f = gs[31]; g.b = gs[32];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) vps_out[(size_t)frame * 9 + threadIdx.x] = s_vps[threadIdx.x];
+  // per line, in parallel: the three angles (:388-411) and segAngle; stored over the line-info scratch
+  const VplLine* L = all_lines + (size_t)frame * cap;
+  double* ang = B.para + (size_t)frame * cap * 3;
+  double* sega = B.orient + (size_t)frame * cap;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
+    const double x1 = L[i].endpoint[0], y1 = L[i].endpoint[1], x2 = L[i].endpoint[2], y2 = L[i].endpoint[3];
+    const double xm = (x1 + x2) / 2.0, ym = (y1 + y2) / 2.0;
+    double v1x = x1 - x2, v1y = y1 - y2;
+    const double N1 = sqrt(v1x * v1x + v1y * v1y);
+    v1x /= N1; v1y /= N1;
+    for (int j = 0; j < 3; ++j) {
+      double v2x = s_vp2d[2 * j] - xm, v2y = s_vp2d[2 * j + 1] - ym;
+      const double N2 = sqrt(v2x * v2x + v2y * v2y);
+      v2x /= N2; v2y /= N2;
+      double cv = v1x * v2x + v1y * v2y;
+      if (cv > 1.0) cv = 1.0;
+      if (cv < -1.0) cv = -1.0;
+      double a = vpl_acos_cr(cv);
+      a = (kPi - a < a) ? kPi - a : a;
+      ang[3 * i + j] = a;
+    }
+    sega[i] = (double)seg_angle(L[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int* lx = B.lx + (size_t)frame * cap;
+  int nx = 0, ny = 0, nz = 0, flags = 0;
+  const double th = 1.0 / 180.0 * kPi;
+  for (int i = 0; i < na; ++i) {
+    double min_angle = 1000;
+    int best_j = 0;
+    for (int j = 0; j < 3; ++j) {
+      const double a = ang[3 * i + j];
+      if (a < min_angle) {
+        bool flag = false;
+        const int other = j == 0 ? ny : j == 1 ? nz : nx;
+        if (other > 1) {
+          const int idx = grand_next(g) % other;
+          if (idx < nx) {
+            const float cur = (float)sega[i], qry = (float)sega[lx[idx]];
+            const float d = fabsf(cur - qry);
+            if ((double)d < 0.175) flag = true;
+          } else {
+            flags |= 1;  // the reference reads lx[idx] out of range here
+          }
+        }
+        if (!flag) {
+          min_angle = a;
+          best_j = j;
+          if (j == 0) lx[nx++] = i;
+          else if (j == 1) ++ny;
+          else ++nz;
+        }
+      }
+    }
+    const int lab = min_angle < th ? best_j : 3;
+    out_idx[i] = lab;
+    if (out_lv) {  // line_feature_tracker.cpp:246-262
+      if (lab == 3) { out_lv[4 * i] = 0; out_lv[4 * i + 1] = 0; out_lv[4 * i + 2] = 0; out_lv[4 * i + 3] = 0; }
+      else {
+        out_lv[4 * i] = s_vps[3 * lab]; out_lv[4 * i + 1] = s_vps[3 * lab + 1]; out_lv[4 * i + 2] = s_vps[3 * lab + 2];
+        out_lv[4 * i + 3] = s_vps[3 * lab + 2] / s_vps[3 * lab + 2];
+      }
+    }
+  }
+  B.flags[frame] = flags;
+}
+
+__global__ void vp_lambda_kernel(double* sc) {  // sin / cos of j * (2 pi / 360), :99-101, :142
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kNumVp2) return;
+  const double step = 2.0 * kPi / kNumVp2;
+  double s, c;
+  vpl_sincos_cr(j * step, &s, &c);
+  sc[2 * j] = s; sc[2 * j + 1] = c;
+}
+
+}  // namespace
+
+void launch_vp_lambda(double* lambda_sc, cudaStream_t st) { vp_lambda_kernel<<<2, 192, 0, st>>>(lambda_sc); }
+
+int vp_score_splits(int n_frames) {  // enough CTAs to fill the machine at small batches
+  if (n_frames >= 1024) return 1;
+  if (n_frames >= 256) return 3;
+  return 15;
+}
+
+void launch_vp_prepare(const VplLine* lines, const int* n_lines, int cap, const unsigned* seeds, const VpBuffers& B,
+                       const VpParams& P, int n_frames, cudaStream_t st) {
+  cudaMemsetAsync(B.grid, 0, (size_t)n_frames * kCells * sizeof(double), st);
+  vp_prepare_kernel<<<n_frames, 128, 0, st>>>(lines, n_lines, cap, B, P, seeds);
+}
+void launch_vp_vote(const int* n_lines, int cap, const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st) {
+  vp_vote_kernel<<<(n_frames + kVoteWarps - 1) / kVoteWarps, kVoteWarps * 32, 0, st>>>(n_lines, cap, B, P, n_frames);
+  vp_smooth_kernel<<<dim3((kCells + 255) / 256, n_frames), 256, 0, st>>>(B, n_frames);
+}
+void launch_vp_score(const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st) {
+  const int splits = vp_score_splits(n_frames);
+  vp_score_kernel<<<dim3(splits, n_frames), kScoreThreads, 0, st>>>(B, P, splits);
+}
+void launch_vp_classify(const VplLine* all_lines, const int* n_all, int cap, int frame_count0, const VpBuffers& B,
+                        const VpParams& P, int n_frames, double* vps, int* vp_idx, double* line_vps, cudaStream_t st) {
+  vp_classify_kernel<<<n_frames, 128, 0, st>>>(all_lines, n_all, cap, B, P, vp_score_splits(n_frames), frame_count0, vps,
+                                               vp_idx, line_vps);
+}
+
+}  // namespace vpl

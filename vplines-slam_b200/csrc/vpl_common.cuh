@@ -250,6 +250,42 @@ void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G,
                       int pstride, int n_pairs, cudaStream_t st);
 void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
                     int n_pairs, cudaStream_t st);
+// ---- vanishing points (vp.cu) ---------------------------------------------------------------
+struct VpParams {
+  double f, ppx, ppy;   // vanishing_point_detection::init: floats stored in doubles
+  int it;               // outer iterations of getVPHypVia2Lines (105)
+  long long max_draws;  // give up (status -2) where the reference would redraw for ever
+};
+struct VpBuffers {      // per frame (cap lines)
+  double* para;         // cap x 3: p1 x p2 per line; reused for the three angles per line of all_lines
+  double* length;       // cap
+  double* orient;       // cap; reused for segAngle of all_lines
+  double* vp1;          // it x 3
+  int* pairs;           // it x 2 (the line pair of every outer iteration)
+  int* rng;             // 33: rand() state after the pair draws
+  int* status;          // 0, -1 (fewer than 2 lines), -2
+  int* flags;           // bit 0: the reference would have read lx[] out of range
+  double* grid;         // 90 x 360 votes
+  double* grid_new;     // 90 x 360 after the 3x3 pass
+  double* lambda_sc;    // 360 x (sin, cos) of j * 2 pi / 360 (one table per context)
+  double* part_best;    // kVpMaxSplits: best sum per CTA of the scoring kernel
+  int* part_idx;
+  int* best_idx;
+  int* lx;              // cap: indices of the lines put into lx by lines2Vps
+};
+constexpr int kVpMaxSplits = 15;
+constexpr int kVpCells = 90 * 360;
+void launch_vp_lambda(double* lambda_sc, cudaStream_t st);
+int vp_score_splits(int n_frames);
+// the stage = these four, in this order (each: the launches it makes)
+void launch_vp_prepare(const VplLine* lines, const int* n_lines, int cap, const unsigned* seeds, const VpBuffers& B,
+                       const VpParams& P, int n_frames, cudaStream_t st);                       // memset + 1
+void launch_vp_vote(const int* n_lines, int cap, const VpBuffers& B, const VpParams& P, int n_frames,
+                    cudaStream_t st);                                                           // 2
+void launch_vp_score(const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st);      // 1
+void launch_vp_classify(const VplLine* all_lines, const int* n_all, int cap, int frame_count0, const VpBuffers& B,
+                        const VpParams& P, int n_frames, double* vps, int* vp_idx, double* line_vps,
+                        cudaStream_t st);                                                       // 1
 #ifdef VPL_DEBUG_NFA
 void debug_set_cand(int c);
 #endif
