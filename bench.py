@@ -52,7 +52,14 @@ WORKLOADS = {
     # (readImage: EDline on every frame + LineMatching::Matching(prev, cur), line_feature_tracker.cpp:87, :115)
     "E2": dict(name="E2_edlines_kltmatch_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2", match=True),
     "E2r": dict(name="E2r_edlines_kltmatch_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1", match=True),
+    # the vanishing-point stage readImage runs on every frame's lines after matching
+    # (vanishing_point_detection::run_vanishing_point_detection, line_feature_tracker.cpp:233-262); the line sets
+    # are the EDLines of the C2 / mh04 frames
+    "V1": dict(name="V1_vanishing_points_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=256, frames="C2", vp=True),
+    "V1r": dict(name="V1r_vanishing_points_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=256, frames="C1", vp=True),
 }
+VP_METRIC = "vanishing-point stage frames/sec (vanishing_point_detection::run_vanishing_point_detection) on 752x480 line sets"
+EUROC_CAM = (461.6, 363.0, 248.1)  # fx, cx, cy of config/euroc/euroc_config.yaml
 LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, LineFeatureTracker::readImage) at 752x480"
 ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
@@ -385,11 +392,265 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     return 0
 
 
+def _vp_chunk(job):
+    """One host process: frames one after another through the reference's own vanishing_point_detection.cpp
+    (oracle/_ref/libref_vp.so) or, where that library did not travel, the oracle port (libm arithmetic)."""
+    lines, counts, seeds, use_ref = job
+    from oracle import oracle as O
+    _, _, tot = O.vp_sequence(lines, counts, seeds, *EUROC_CAM, frame_count0=1, math_mode=0, use_ref=use_ref)
+    return tot
+
+
+def vp_cpu_run(lines, counts, seeds, procs, use_ref):
+    """rand()/srand() are process-global in the reference's code, so the host cores are used as processes."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    n = len(counts)
+    cuts = [n * i // procs for i in range(procs + 1)]
+    jobs = [(lines[a:b], counts[a:b], seeds[a:b], use_ref) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    # an executor (not a Pool): a worker that dies raises BrokenProcessPool instead of hanging the bench
+    with ProcessPoolExecutor(len(jobs), mp_context=mp.get_context("fork")) as pool:
+        list(pool.map(int, [0] * len(jobs)))  # workers started before the clock
+        t = time.time()
+        tot = sum(pool.map(_vp_chunk, jobs, timeout=600))
+        dt = time.time() - t
+    return tot, dt
+
+
+def vp_cpu_baseline(u_lines, u_counts, u_seeds, seconds=10.0, name="V1"):
+    from oracle import oracle as O
+    O.build()
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_vp.so"))
+    procs = os.cpu_count() or 1
+    per_frame = max(vp_cpu_run(u_lines[:4], u_counts[:4], u_seeds[:4], 1, use_ref)[1] / 4, 1e-4)
+    n = int(max(procs * 4, min(seconds / per_frame * procs, 65536)))
+    reps = (n + len(u_counts) - 1) // len(u_counts)
+    lines = np.ascontiguousarray(np.concatenate([u_lines] * reps)[:n])
+    counts = np.ascontiguousarray(np.concatenate([u_counts] * reps)[:n]); seeds = np.ascontiguousarray(np.concatenate([u_seeds] * reps)[:n])
+    tot, dt = vp_cpu_run(lines, counts, seeds, procs, use_ref)
+    what = ("the reference's own feature_tracker/src/vanishing_point_detection.cpp compiled against oracle/cvshim, its "
+            "time(NULL) answered with the frame's seed" if use_ref else "CPU oracle port (oracle/orc_vp.c, libm arithmetic)")
+    return {"value": n / dt, "unit": "frames/s", "cores": procs, "kind": "reference" if use_ref else "port",
+            "sample": f"{n} line sets of {name} ({tot} labelled lines) in {dt:.1f}s; {what}; one object per process, "
+                      f"{procs} processes over contiguous chunks (rand() is process-global)",
+            "single_thread_frames_per_s": 1.0 / per_frame}
+
+
+def vp_inputs(ctx, capi, unique, cap):
+    """Line sets = the device's own EDLines of the distinct frames; one seed per set on which the reference does not
+    read lx[] out of range (device status 0; every frame of the bench is a later call of its object, frame_count > 0), so
+    that its code can be timed."""
+    ctx.edlines_configure(capi.EDLineParam())
+    sets = []
+    for a in range(0, len(unique), 32):
+        sets += ctx.edlines_detect_batch(unique[a:a + 32], smoothed=True)
+    n = len(sets)
+    seeds = np.zeros(n, np.uint32)
+    todo = list(range(n))
+    base = 1700000000
+    for attempt in range(64):
+        if not todo:
+            break
+        cand = np.array([base + 1009 * attempt + i for i in todo], np.uint32)
+        st = np.concatenate([ctx.vp_detect_batch([sets[i] for i in todo[a:a + 32]], cand[a:a + 32], frame_count0=1)[2]
+                             for a in range(0, len(todo), 32)])
+        ok = st == 0
+        for j, i in enumerate(todo):
+            if ok[j]:
+                seeds[i] = cand[j]
+        todo = [i for j, i in enumerate(todo) if not ok[j]]
+    keep = [i for i in range(n) if seeds[i] and len(sets[i]) > 2]
+    u_lines = np.zeros((len(keep), cap), capi.LINE_DTYPE)
+    u_counts = np.array([len(sets[i]) for i in keep], np.int32)
+    for r, i in enumerate(keep):
+        u_lines[r, :u_counts[r]] = sets[i]
+    return u_lines, u_counts, seeds[keep]
+
+
+def run_reference_vp(args):
+    """--impl reference --workload V1: needs the line sets, which bench.py takes from the device's EDLines; on a box
+    without a GPU the oracle's EDLines (bit-identical) stands in."""
+    from oracle import oracle as O
+    O.build()
+    wl = WORKLOADS[args.workload]
+    unique = make_frames(min(args.unique, 32), args.seed, args.workload)
+    cap = args.max_lines or wl["max_lines"]
+    sets = [O.edline_detect(f) for f in unique]
+    u_lines = np.zeros((len(sets), cap), O.LINE_DTYPE); u_counts = np.array([len(s) for s in sets], np.int32)
+    seeds = np.zeros(len(sets), np.uint32)
+    for i, s in enumerate(sets):
+        u_lines[i, :len(s)] = s
+        for k in range(64):  # a seed on which the reference's code does not read lx[] out of range
+            sd = 1700000000 + 1009 * k + i
+            if O.vp_detect(s, None, *EUROC_CAM, sd, 1, math_mode=0, details=True)[2]["flags"] == 0:
+                seeds[i] = sd
+                break
+    keep = (seeds != 0) & (u_counts > 2)
+    u_lines, u_counts, seeds = u_lines[keep], u_counts[keep], seeds[keep]
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_vp.so"))
+    procs = os.cpu_count() or 1
+    per_frame = max(vp_cpu_run(u_lines[:4], u_counts[:4], seeds[:4], 1, use_ref)[1] / 4, 1e-4)
+    n = int(max(procs * 4, min(5.0 / per_frame * procs, 65536)))
+    reps = (n + len(u_counts) - 1) // len(u_counts)
+    lines = np.ascontiguousarray(np.concatenate([u_lines] * reps)[:n])
+    counts = np.ascontiguousarray(np.concatenate([u_counts] * reps)[:n]); sd = np.ascontiguousarray(np.concatenate([seeds] * reps)[:n])
+    for _ in range(args.warmup):
+        vp_cpu_run(lines[:max(procs, n // 4)], counts[:max(procs, n // 4)], sd[:max(procs, n // 4)], procs, use_ref)
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += vp_cpu_run(lines, counts, sd, procs, use_ref)[1]
+    fps = n * args.steps / dt
+    kind = "reference" if use_ref else "port"
+    line = {"impl": "reference", "metric": VP_METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_step": n,
+                       "note": "the reference's own vanishing_point_detection.cpp compiled against oracle/cvshim" if use_ref
+                       else "CPU oracle port (oracle/_ref not present)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": kind, "sample": f"{n} line sets/step x {args.steps} steps"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_vp(args, torch, dist, rank, local_rank, world):
+    """--workload V1 / V1r: run_vanishing_point_detection on B line sets per step (lines == all_lines, what readImage
+    passes unless it found > 2 vertical lines)."""
+    vpl = importlib.import_module("vplines_slam_b200")
+    capi = vpl.capi
+    wl = WORKLOADS[args.workload]
+    W, H = wl["w"], wl["h"]
+    B, S, cap = args.batch, args.slots, (args.max_lines or wl["max_lines"])
+    unique = make_frames(args.unique, args.seed, args.workload)
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=1, max_lines=cap, max_batch=B,
+                       num_slots=S, blur_first=True, profile=True, lsd_path=False)
+    ctx.vp_configure(*EUROC_CAM)
+    u_lines, u_counts, u_seeds = vp_inputs(ctx, capi, unique, cap)
+    reps = (B + len(u_counts) - 1) // len(u_counts)
+    lines = np.ascontiguousarray(np.concatenate([u_lines] * reps)[:B])
+    counts = np.ascontiguousarray(np.concatenate([u_counts] * reps)[:B])
+    seeds = np.ascontiguousarray(np.concatenate([u_seeds] * reps)[:B])
+    vps = [np.zeros((B, 3, 3), np.float64) for _ in range(S)]
+    idx = [np.zeros((B, cap), np.int32) for _ in range(S)]
+    status = [np.zeros(B, np.int32) for _ in range(S)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_steps(n_steps):
+        pending = []
+        for i in range(n_steps):
+            s = i % S
+            if len(pending) == S:
+                ps = pending.pop(0)
+                ctx.vp_collect_into(ps, cap, vps[ps], idx[ps], status[ps])
+            ctx.vp_submit(s, lines, counts, seeds, frame_count0=1)
+            pending.append(s)
+        while pending:
+            ps = pending.pop(0)
+            ctx.vp_collect_into(ps, cap, vps[ps], idx[ps], status[ps])
+        return ps
+
+    e2e_steps(max(args.warmup, S))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    ps = e2e_steps(args.steps)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    labelled = int(sum((idx[ps][i, :counts[i]] != 3).sum() for i in range(B)))
+    assert (status[ps] == 0).all()
+
+    for w in range(max(args.warmup, S)):
+        ctx.vp_run_resident(w % S)
+    ctx.sync()
+    ctx.reset_stage_times()
+    l0 = ctx.kernel_launches()
+    barrier()
+    if args.profile_region:  # ncu --profile-from-start off captures only the resident steps
+        torch.cuda.cudart().cudaProfilerStart()
+    ev0.record()
+    for i in range(args.steps):
+        ctx.vp_run_resident(i % S)
+    ctx.sync()
+    ev1.record()
+    if args.profile_region:
+        torch.cuda.cudart().cudaProfilerStop()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - l0
+    stage = ctx.stage_times()
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+    frames_total = B * args.steps * world
+    value = frames_total / (dev_ms * 1e-3)
+    e2e_value = frames_total / (e2e_ms * 1e-3)
+
+    # algorithmic bytes per frame (DESIGN.md section 3): L lines, Np = L (L - 1) / 2 pairs, G = 90 x 360 cells of 8 B
+    Lm = float(counts.mean()); Np = float((counts.astype(np.float64) * (counts - 1) / 2).mean()); G = 90 * 360 * 8.0
+    alg = {"vp_prep": 16.0 * Lm + 40.0 * Lm + G,            # endpoints in, 5 doubles per line out, grid cleared
+           "vp_vote": 16.0 * Np + G + G,                    # one read-modify-write per voting pair; 3x3 pass: r G, w G
+           "vp_score": 105 * 360 * 3 * 8.0,                 # three cell reads per hypothesis
+           "vp_classify": 16.0 * Lm + 32.0 * Lm + 4.0 * Lm}  # endpoints, angles, labels
+    launches_of = {"vp_prep": 1, "vp_vote": 2, "vp_score": 1, "vp_classify": 1}
+    kernels_of = {"vp_prep": "vp_prepare_kernel (+ grid memset)", "vp_vote": "vp_vote_kernel + vp_smooth_kernel",
+                  "vp_score": "vp_score_kernel", "vp_classify": "vp_classify_kernel"}
+    st = {k: stage[k] for k in alg}
+    dom = max(st, key=lambda k: st[k][0])
+    peak, peak_kind = measured_peak()
+    dur = st[dom][0] / max(st[dom][1] / launches_of[dom], 1)
+    achieved = alg[dom] * B / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
+    tot = max(sum(x[0] for x in stage.values()), 1e-9)
+    roofline = {"bound": "hbm", "kernel": kernels_of[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "ms_per_launch": dur, "algorithmic_bytes_per_launch": alg[dom] * B,
+                "note": "FP64-arithmetic-bound (double-double atan/acos/sincos per pair and per hypothesis), not a streaming kernel; see DESIGN.md",
+                "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items() if v[1]},
+                "stage_share": {k: round(v[0] / tot, 4) for k, v in stage.items() if v[1]}}
+    h2d = int(B * cap * capi.LINE_DTYPE.itemsize + 2 * B * 4 + B * 4)
+    d2h = int(B * 72 + B * cap * 4 + 2 * B * 4)
+    line = {"metric": VP_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
+            "config": {"workload": wl["name"], "frames_per_step": B, "slots": S, "max_lines": cap, "unique_line_sets": int(len(u_counts)),
+                       "lines_per_frame": round(Lm, 1), "pairs_per_frame": round(Np, 1), "hypotheses_per_frame": 105 * 360,
+                       "labelled_lines_per_frame": round(labelled / B, 1), "camera": list(EUROC_CAM), "parallelism": f"frames x{world}",
+                       "seeds": "one per line set, chosen so that the reference's own code does not read lx[] out of range (device status 0)",
+                       "l2": "sphere grids per step (%.0f MB) exceed the 126 MB L2" % (2 * B * G / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+    if rank == 0:
+        line["cpu_baseline"] = (vp_cpu_baseline(u_lines, u_counts, u_seeds, name=wl["name"])
+                                if (world == 1 and not args.no_cpu_baseline) else None)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores, nothing else."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload.startswith("V"):
+        return run_reference_vp(args)
     if args.workload.startswith("E"):
         return run_reference_edlines(args)
     unique = make_frames(min(args.unique, 32), args.seed)
@@ -435,6 +696,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20240601)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the resident steps (for ncu --profile-from-start off; V workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -450,6 +713,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
+    if args.workload.startswith("V"):
+        return run_vp(args, torch, dist, rank, local_rank, world)
     if args.workload.startswith("E"):
         return run_edlines(args, torch, dist, rank, local_rank, world)
 

@@ -451,7 +451,7 @@ def vp_sequence(lines, counts, seeds, f=460.0, cx=376.0, cy=240.0, frame_count0=
     vps = np.zeros((n, 3, 3), np.float64); idx = np.full((n, cap), 3, np.int32)
     if use_ref:
         tot = ref_vp_lib().ref_vp_sequence(_p(lines), _p(counts), n, cap, ctypes.c_float(f), ctypes.c_float(cx),
-                                           ctypes.c_float(cy), _p(seeds), _p(vps), _p(idx))
+                                           ctypes.c_float(cy), _p(seeds), int(frame_count0), _p(vps), _p(idx))
     else:
         L = lib(); L.orc_vp_sequence.restype = ctypes.c_int64
         tot = L.orc_vp_sequence(_p(lines), _p(counts), n, cap, ctypes.c_float(f), ctypes.c_float(cx), ctypes.c_float(cy),

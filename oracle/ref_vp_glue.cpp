@@ -72,13 +72,25 @@ int ref_vp_detect(const RefVpLine* lines, int n_lines, const RefVpLine* all_line
 }
 
 /* n_frames frames one after another on one object (timing + sequence parity): frame i uses
- * lines + i*cap (counts[i] of them) as both `lines` and `all_lines`, seed seeds[i]. */
+ * lines + i*cap (counts[i] of them) as both `lines` and `all_lines`, seed seeds[i]; frame_count0 > 0: the
+ * object has made a call before frame 0. */
 long long ref_vp_sequence(const RefVpLine* lines, const int32_t* counts, int n_frames, int cap, float f, float cx,
-                          float cy, const uint32_t* seeds, double* vps, int32_t* vp_idx) {
+                          float cy, const uint32_t* seeds, int frame_count0, double* vps, int32_t* vp_idx) {
   vanishing_point_detection d;
   d.init(f, cx, cy, 0.5);
   cv::Mat img;
   long long labelled = 0;
+  if (frame_count0 > 0) { /* an object that has made a call before: warm-up call with nothing to classify */
+    for (int i = 0; i < n_frames; ++i) {
+      if (counts[i] < 3) continue;
+      std::vector<Line> L = to_lines(lines + (size_t)i * cap, counts[i]), none;
+      std::vector<Eigen::Vector3d> v0;
+      std::vector<int> id0;
+      g_fixed_time = (time_t)seeds[i];
+      d.run_vanishing_point_detection(img, L, none, v0, id0);
+      break;
+    }
+  }
   for (int i = 0; i < n_frames; ++i) {
     if (counts[i] < 3) continue;
     std::vector<Line> L = to_lines(lines + (size_t)i * cap, counts[i]);

@@ -13,6 +13,10 @@ using vplines::ref::EDLineDetector;
 using vplines::ref::EDLineParam;
 using vplines::ref::Line;
 using vplines::ref::LineMatching;
+using vplines::ref::Vector3d;
+using vplines::ref::vanishing_point_detection;
+
+static uint32_t fixed_seed() { return 1700000123u; }
 
 static void make_image(cv::Mat& m, int w, int h, int shift) {
   m.create(h, w, CV_8UC1);
@@ -67,6 +71,26 @@ int main(int argc, char** argv) {
     bool empty_ok = line_matching.Matching(a, b, none, cur_lsd, r, *(cv::Mat*)nullptr, *(cv::Mat*)nullptr, *(cv::Mat*)nullptr, true, true, 0);
     std::printf("REFSEAM unsmoothed_lines=%zu unsmoothed_digest=%lu empty_returns=%d\n", blurred.size(), digest_lines(blurred),
                 (int)empty_ok);
+    // the vanishing-point stage as readImage drives it (line_feature_tracker.cpp:233-262): two frames on one object
+    vanishing_point_detection vpdetect;
+    vpdetect.init(230.0f, 160.0f, 120.0f, 0.5);
+    vpdetect.seed_source = fixed_seed;
+    for (int frame = 0; frame < 2; ++frame) {
+      std::vector<Line>& L = frame ? cur_lsd : prev_lsd;
+      std::vector<Vector3d> _vps;
+      std::vector<int> local_vp_ids;
+      vpdetect.run_vanishing_point_detection(frame ? b : a, L, L, _vps, local_vp_ids);
+      unsigned long dv = 1469598103934665603ul;
+      for (const Vector3d& v : _vps) {
+        unsigned char buf[24];
+        std::memcpy(buf, v.v, 24);
+        for (unsigned char x : buf) dv = (dv ^ x) * 1099511628211ul;
+      }
+      unsigned long di = 1469598103934665603ul;
+      for (int v : local_vp_ids) di = (di ^ (unsigned long)v) * 1099511628211ul;
+      std::printf("REFSEAM vp frame=%d n=%zu vps_digest=%lu ids_digest=%lu status=%d\n", frame, local_vp_ids.size(), dv, di,
+                  vpdetect.last_status());
+    }
   } catch (const std::exception& e) {
     std::printf("REFSEAM error: %s\n", e.what());
     return 2;

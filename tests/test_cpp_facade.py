@@ -111,3 +111,10 @@ def test_reference_named_facade_matches_oracle(vpl, orc, tmp_path):
     m2 = re.search(r"unsmoothed_lines=(\d+) unsmoothed_digest=(\d+) empty_returns=(\d)", r.stdout)
     lu = orc.edline_detect(a, p, False)
     assert int(m2.group(1)) == len(lu) and int(m2.group(2)) == line_digest(lu) and m2.group(3) == "0"
+    # vanishing_point_detection::run_vanishing_point_detection on both frames' lines, one object (frame_count 0, 1)
+    for frame, ln in enumerate((la, lb)):
+        mv = re.search(r"vp frame=%d n=(\d+) vps_digest=(\d+) ids_digest=(\d+) status=(-?\d+)" % frame, r.stdout)
+        assert mv, r.stdout
+        vps, idx, d = orc.vp_detect(ln, None, 230.0, 160.0, 120.0, 1700000123, frame, math_mode=1, details=True)
+        assert int(mv.group(1)) == len(ln) and int(mv.group(2)) == fnv(vps.view(np.uint8).reshape(-1))
+        assert int(mv.group(3)) == fnv(idx) and int(mv.group(4)) == (d["flags"] & 1)

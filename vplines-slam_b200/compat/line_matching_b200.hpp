@@ -10,6 +10,9 @@
 //                                            K_ref, K_cur, T_cur_ref, illumination_adapt,
 //                                            topological_filter, debug_show, ...); }
 //                                                   line_matching.h:21-33, line_matching.cpp:605
+//     class  vanishing_point_detection { void init(f, cx, cy, noiseRatio);
+//                                        void run_vanishing_point_detection(img, lines, all_lines, vps, local_vp_ids); }
+//                                                   feature_tracker/include/vanishing_point_detection.h:44-84
 // Same names, argument meaning and return values, so the tracker's two seams
 // (edline_detect / match_line_match, line_feature_tracker.cpp:291-321) compile against it
 // unchanged -- put `using namespace vplines::ref;` (or the two `using` lines below) where the
@@ -18,6 +21,13 @@
 // threads the reference's own line ORDER is a race (edline_detector.cpp:1081-1083), here it is
 // always (edge chain, position).  There is no CPU fallback: every call throws
 // std::runtime_error(vpl_last_error()) when the device path fails.
+//
+// vanishing_point_detection: the reference seeds rand() with time(NULL) on every call
+// (vanishing_point_detection.cpp:107); so does this class, through seed_source (default: time(NULL)),
+// which a caller can replace to make runs repeatable.  Given the seed, the result is the reference's,
+// computed with correctly rounded atan/acos/sin/cos instead of libm's (tests/test_gpu_vp.py: labels
+// identical, vanishing points within 1e-15); where the reference would read its lx[] out of range
+// (:438-441, :456-459) no query is made (last_status() == 1).
 //
 // Deliberate differences, all outside what the tracker uses:
 //   - K_ref / K_cur / T_cur_ref are accepted and ignored: Matching() itself never reads them for the
@@ -29,6 +39,7 @@
 #include <algorithm>
 #include <array>
 #include <cstring>
+#include <ctime>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -63,6 +74,7 @@ struct RefCtx {
   VplEDLineParam edp{};
   VplLineMatchParam lmp{};
   bool ed_set = false, lm_set = false;
+  const void* vp_owner = nullptr;  // the vanishing_point_detection object whose intrinsics are configured
   ~RefCtx() { if (h) vpl_destroy(h); }
   static void check(VplContext* c, int r, const char* what) {
     if (r != VPL_OK) throw std::runtime_error(std::string(what) + ": " + vpl_last_error(c));
@@ -83,6 +95,7 @@ struct RefCtx {
     if (h) vpl_destroy(h);
     h = n; w = c.max_width; hh = c.max_height;
     ed_set = lm_set = false;
+    vp_owner = nullptr;
     return h;
   }
   static bool same(const VplEDLineParam& a, const VplEDLineParam& b) {
@@ -202,6 +215,82 @@ class LineMatching {
     }
   }
   VplLineMatchParam p_;
+};
+
+struct Vector3d {  // stands in for Eigen::Vector3d where Eigen is not available (any type with this
+  double v[3];     // constructor and operator() works: the method below is a template on it)
+  Vector3d() : v{0, 0, 0} {}
+  Vector3d(double a, double b, double c) : v{a, b, c} {}
+  double& operator()(int i) { return v[i]; }
+  const double& operator()(int i) const { return v[i]; }
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double z() const { return v[2]; }
+};
+
+class vanishing_point_detection {  // feature_tracker/include/vanishing_point_detection.h:44-84
+ public:
+  vanishing_point_detection() {}
+  void init(float _f, float _cx, float _cy, double _noiseRatio) {  // vanishing_point_detection.cpp:29-34
+    f = _f; pp_x = _cx; pp_y = _cy; noiseRatio = _noiseRatio;
+    f_ = _f; cx_ = _cx; cy_ = _cy;
+    configured_ = false;
+  }
+  // vps: three unit vectors; local_vp_ids: one label per entry of all_lines appended (0..2, 3 = none), as the
+  // reference's push_back.  Throws on a device failure and where the reference itself cannot proceed
+  // (fewer than 2 lines; no pair of lines that intersect).
+  template <class Vec3>
+  void run_vanishing_point_detection(const cv::Mat& /*img: only drawn on*/, std::vector<Line>& lines,
+                                     std::vector<Line>& all_lines, std::vector<Vec3>& vps, std::vector<int>& local_vp_ids) {
+    detail::RefCtx& c = detail::rctx();
+    VplContext* h = c.get(std::max(c.w, 64), std::max(c.hh, 64));
+    if (!configured_ || c.vp_owner != this) {
+      detail::RefCtx::check(h, vpl_vp_configure(h, f_, cx_, cy_), "vpl_vp_configure");
+      configured_ = true; c.vp_owner = this;
+    }
+    if (lines.size() > 2048 || all_lines.size() > 2048) throw std::runtime_error("vanishing_point_detection: more than 2048 lines");
+    const int cap = (int)std::max<size_t>(1, std::max(lines.size(), all_lines.size()));
+    std::vector<VplLine> a((size_t)cap), b((size_t)cap);
+    pack(lines, a);
+    pack(all_lines, b);
+    const int32_t na = (int32_t)lines.size(), nb = (int32_t)all_lines.size();
+    const uint32_t seed = seed_source ? seed_source() : (uint32_t)std::time(nullptr);
+    double out[9];
+    std::vector<int32_t> idx((size_t)cap, 3);
+    int32_t status = 0;
+    detail::RefCtx::check(h, vpl_vp_detect_batch(h, a.data(), &na, b.data(), &nb, 1, cap, &seed, frame_count, out, idx.data(),
+                                                 nullptr, &status),
+                          "vpl_vp_detect_batch");
+    last_status_ = status;
+    if (status < 0)
+      throw std::runtime_error(status == -1 ? "vanishing_point_detection: fewer than 2 lines"
+                                            : "vanishing_point_detection: no two lines intersect");
+    vps.clear();
+    for (int k = 0; k < 3; ++k) vps.push_back(Vec3(out[3 * k], out[3 * k + 1], out[3 * k + 2]));
+    for (int32_t i = 0; i < nb; ++i) local_vp_ids.push_back(idx[(size_t)i]);
+    frame_count++;
+  }
+  int last_status() const { return last_status_; }
+  uint32_t (*seed_source)() = nullptr;  // nullptr: time(NULL), as the reference
+
+  double pp_x = 0, pp_y = 0;  // the reference's cv::Point2d pp
+  double f = 0;
+  double noiseRatio = 0;
+
+ private:
+  static void pack(const std::vector<Line>& in, std::vector<VplLine>& out) {
+    for (size_t i = 0; i < in.size(); ++i) {
+      for (int k = 0; k < 4; ++k) out[i].endpoint[k] = in[i].line_endpoint[(size_t)k];
+      for (int k = 0; k < 3; ++k) out[i].equation[k] = in[i].line_equation[(size_t)k];
+      out[i].center[0] = in[i].center[0]; out[i].center[1] = in[i].center[1];
+      out[i].length = in[i].length;
+      out[i].reserved = 0;
+    }
+  }
+  float f_ = 0, cx_ = 0, cy_ = 0;
+  bool configured_ = false;
+  int frame_count = 0;
+  int last_status_ = 0;
 };
 
 }  // namespace ref
