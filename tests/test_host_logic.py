@@ -81,6 +81,66 @@ class OracleLineContext:
                 p2c[i, :len(ms[i])] = ms[i]
 
 
+class OracleVpContext:
+    """Quacks like capi.Context's vp_submit / vp_collect_into, computing with the oracle restatement of the
+    reference's vanishing-point stage (device arithmetic: math_mode 1)."""
+    CAM = (230.0, 80.0, 60.0)
+
+    def __init__(self, orc, capi, max_batch=4, num_slots=2, max_lines=256):
+        self.orc, self.capi = orc, capi
+        self.max_batch, self.num_slots, self.max_lines = max_batch, num_slots, max_lines
+        self.pending = {}
+        self.submitted = []
+
+    def vp_submit(self, slot, lines, n_lines, seeds, frame_count0=0):
+        assert slot not in self.pending and 1 <= len(n_lines) <= self.max_batch
+        out = []
+        for i in range(len(n_lines)):
+            ln = lines[i, :n_lines[i]]
+            if len(ln) < 2:
+                out.append((np.zeros((3, 3)), np.full(len(ln), 3, np.int32), -1))
+                continue
+            vps, idx, d = self.orc.vp_detect(ln, None, *self.CAM, int(seeds[i]), frame_count0 + i, math_mode=1, details=True)
+            out.append((vps, idx, d["flags"] & 1))
+        self.pending[slot] = out
+        self.submitted.append((len(n_lines), frame_count0))
+        return len(n_lines)
+
+    def vp_collect_into(self, slot, cap, vps, vp_idx, status=None, line_vps=None):
+        for i, (v, idx, st) in enumerate(self.pending.pop(slot)):
+            vps[i] = v
+            vp_idx[i, :len(idx)] = idx
+            if status is not None:
+                status[i] = st
+
+
+def _vp_inputs(orc, synth, n=7):
+    frames = synth.sequence(n, w=160, h=120, seed=33, n_quads=6, n_strokes=10)
+    sets = [orc.edline_detect(f, orc.EDLineParam(minLineLen=12), True) for f in frames]
+    sets[3] = sets[3][:1]  # a frame the tracker would not run the stage on
+    return sets, np.arange(500, 500 + n, dtype=np.uint32)
+
+
+def test_vanishing_point_driver_batches_and_shards(vpl, orc, synth):
+    sets, seeds = _vp_inputs(orc, synth)
+    exp = [orc.vp_detect(s, None, *OracleVpContext.CAM, int(sd), f, math_mode=1) if len(s) >= 2 else None
+           for f, (s, sd) in enumerate(zip(sets, seeds))]
+    ctx = OracleVpContext(orc, vpl.capi, max_batch=3, num_slots=2)
+    vps, idx, st = vpl.VanishingPoints(ctx).run(sets, seeds)
+    assert ctx.submitted == [(3, 0), (3, 3), (1, 6)] and st[3] == -1 and (vps[3] == 0).all()
+    for f, e in enumerate(exp):
+        if e is not None:
+            assert vps[f].tobytes() == e[0].tobytes() and np.array_equal(idx[f], e[1])
+    # frames shard without a halo: only frame 0 of the sequence is a first call, whichever rank holds it
+    for world in (2, 3):
+        got_v, got_i = [], []
+        for r in range(world):
+            s, e, _ = vpl.shard_range(len(sets), r, world)
+            v, i, _ = vpl.VanishingPoints(OracleVpContext(orc, vpl.capi, max_batch=2)).run(sets, seeds, s, e)
+            got_v += list(v); got_i += i
+        assert np.array(got_v).tobytes() == vps.tobytes() and all(np.array_equal(a, b) for a, b in zip(got_i, idx))
+
+
 def _line_front_expected(orc, frames, param):
     lines = [orc.edline_detect(f, param, True) for f in frames]
     p2c = [np.zeros(0, np.int32)]
@@ -181,9 +241,13 @@ def _gloo_worker(rank, world, port, q):
     kls, descs, ms = vpl.FrontEnd(OracleContext(O, vpl.capi, max_batch=2), k=1).run(frames, s, e, halo)
     # the reference's real front end (EDLines + KLT line matching) through the same sharding
     ll, pp = vpl.LineFrontEnd(OracleLineContext(O, vpl.capi, max_batch=3)).run(frames, s, e, halo)
+    # ... and the vanishing-point stage on the shard's own line sets (no halo)
+    sets = [O.edline_detect(f, O.EDLineParam(minLineLen=15), True) for f in frames]
+    _, vidx, _ = vpl.VanishingPoints(OracleVpContext(O, vpl.capi, max_batch=2)).run(sets, np.arange(70, 70 + len(frames)), s, e)
     # no data-path collective: the host only gathers results (here: per-frame line counts and match sums)
-    mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())]
-                         for k, m, l, p in zip(kls, ms, ll, pp)], dtype=torch.int64)
+    mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())
+                          + 100000 * int((v * np.arange(1, len(v) + 1)).sum())]
+                         for k, m, l, p, v in zip(kls, ms, ll, pp, vidx)], dtype=torch.int64)
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64))
     pad = torch.zeros((len(frames), 2), dtype=torch.int64)
@@ -210,6 +274,8 @@ def test_two_rank_gloo_gather(vpl, orc, synth):
     frames = synth.sequence(6, w=160, h=120, seed=21, n_quads=5, n_strokes=8)
     kls, descs, ms = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=8), k=1).run(frames)
     ll, pp = vpl.LineFrontEnd(OracleLineContext(orc, vpl.capi, max_batch=8)).run(frames)
-    exp = np.array([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())]
-                    for k, m, l, p in zip(kls, ms, ll, pp)])
+    _, vidx, _ = vpl.VanishingPoints(OracleVpContext(orc, vpl.capi, max_batch=8)).run(ll, np.arange(70, 70 + len(frames)))
+    exp = np.array([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())
+                     + 100000 * int((v * np.arange(1, len(v) + 1)).sum())]
+                    for k, m, l, p, v in zip(kls, ms, ll, pp, vidx)])
     assert np.array_equal(got, exp)

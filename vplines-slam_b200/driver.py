@@ -114,3 +114,52 @@ class LineFrontEnd:
         while pending:
             collect(*pending.pop(0))
         return out_lines, out_p2c
+
+
+class VanishingPoints:
+    """The vanishing-point stage readImage runs on every frame's lines after matching
+    (vanishing_point_detection::run_vanishing_point_detection, line_feature_tracker.cpp:233-262) over a
+    sequence of line sets through Context.vp_submit / vp_collect_into.  Frames are independent given their
+    seed and their position in the sequence (the object's frame_count: only frame 0 of the whole sequence
+    is a first call), so a shard is a plain contiguous range: no halo, no exchange."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def run(self, line_sets, seeds, start=0, end=None):
+        """line_sets: one LINE_DTYPE array per frame; seeds: what time(NULL) returned per frame.
+        Returns (vps (n,3,3), [labels per frame], status (n,)) for frames [start, end)."""
+        ctx = self.ctx
+        end = len(line_sets) if end is None else end
+        B, S, cap = ctx.max_batch, ctx.num_slots, ctx.max_lines
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        bufs = [dict(vps=np.zeros((B, 3, 3), np.float64), idx=np.zeros((B, cap), np.int32), st=np.zeros(B, np.int32))
+                for _ in range(S)]
+        out_vps, out_idx, out_st = [], [], []
+        pending = []  # (slot, first_frame, n)
+
+        def collect(slot, f0, n):
+            b = bufs[slot]
+            ctx.vp_collect_into(slot, cap, b["vps"], b["idx"], b["st"])
+            for i in range(n):
+                out_vps.append(b["vps"][i].copy())
+                out_idx.append(b["idx"][i, :len(line_sets[f0 + i])].copy())
+                out_st.append(int(b["st"][i]))
+
+        slot, f = 0, start
+        while f < end:
+            n = min(B, end - f)
+            if len(pending) == S:
+                collect(*pending.pop(0))
+            lines = np.zeros((n, cap), capi.LINE_DTYPE)
+            counts = np.zeros(n, np.int32)
+            for i in range(n):
+                counts[i] = len(line_sets[f + i])
+                lines[i, :counts[i]] = np.asarray(line_sets[f + i]).view(capi.LINE_DTYPE).reshape(-1)
+            ctx.vp_submit(slot, lines, counts, np.ascontiguousarray(seeds[f:f + n]), frame_count0=f)
+            pending.append((slot, f, n))
+            slot = (slot + 1) % S
+            f += n
+        while pending:
+            collect(*pending.pop(0))
+        return (np.array(out_vps).reshape(-1, 3, 3), out_idx, np.array(out_st, np.int32))
