@@ -457,3 +457,20 @@ def vp_sequence(lines, counts, seeds, f=460.0, cx=376.0, cy=240.0, frame_count0=
         tot = L.orc_vp_sequence(_p(lines), _p(counts), n, cap, ctypes.c_float(f), ctypes.c_float(cx), ctypes.c_float(cy),
                                 _p(seeds), int(frame_count0), int(math_mode), _p(vps), _p(idx))
     return vps, idx, int(tot)
+
+
+def line_cloud(lines, ids, line_vps, fx, fy, cx, cy, num_of_cam=1, cam=0):
+    """The PointCloud body of line_feature_tracker_node.cpp:64-153 -> dict(points (n,3), id, u, v, vp_x, vp_y, vp_z,
+    vp_z_inv) float32; line_vps: (n,4) float64 per-line Vector4d (None / empty = the vp.empty() branch)."""
+    ln = np.ascontiguousarray(lines, LINE_DTYPE); n = len(ln)
+    ids = np.ascontiguousarray(ids, np.int32)
+    lv = None if line_vps is None else np.ascontiguousarray(line_vps, np.float64)
+    out = np.zeros(10 * n, np.float32)
+    lib().orc_line_cloud(_p(ln), _p(ids), n, _p(lv) if lv is not None else None, 0 if lv is None else len(lv),
+                         ctypes.c_float(fx), ctypes.c_float(fy), ctypes.c_float(cx), ctypes.c_float(cy), int(num_of_cam),
+                         int(cam), _p(out))
+    names = ("id", "u", "v", "vp_x", "vp_y", "vp_z", "vp_z_inv")
+    d = {"points": out[:3 * n].reshape(n, 3).copy()}
+    for k, nm in enumerate(names):
+        d[nm] = out[3 * n + k * n:3 * n + (k + 1) * n].copy()
+    return d

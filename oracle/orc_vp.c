@@ -314,3 +314,27 @@ int64_t orc_vp_sequence(const OrcLine* lines, const int32_t* counts, int n_frame
   }
   return labelled;
 }
+
+/* The sensor_msgs::PointCloud img_callback publishes per frame (feature_tracker/src/line_feature_tracker_node.cpp:
+ * 64-153), for camera `cam` (the loop index i of :88), as the message body lays the numbers out: points (n x 3
+ * floats: undistorted first endpoint, z = 1), then the seven channels id_of_line, u_of_endpoint, v_of_endpoint,
+ * vp_x, vp_y, vp_z, vp_z_inv (n floats each).  The endpoints are LineFeatureTracker::undistortedLineEndPoints
+ * (line_feature_tracker.cpp:36-52: (x - cx) / fx in float).  As written in the reference, every line carries
+ * vp[i] -- the Vector4d of line number `cam`, not of line j (:108-114); line_vps == NULL or n_vps == 0 is the
+ * `vp.empty()` branch.  PARITY UNPINNED for the layout (ROS message types are not in this image): this restates
+ * the loop. */
+void orc_line_cloud(const OrcLine* lines, const int32_t* ids, int n, const double* line_vps, int n_vps, float fx,
+                    float fy, float cx, float cy, int num_of_cam, int cam, float* cloud) {
+  float* pts = cloud;
+  float* ch = cloud + 3 * (size_t)n;
+  for (int j = 0; j < n; ++j) {
+    pts[3 * j] = (lines[j].endpoint[0] - cx) / fx;
+    pts[3 * j + 1] = (lines[j].endpoint[1] - cy) / fy;
+    pts[3 * j + 2] = 1;
+    ch[0 * (size_t)n + j] = (float)(ids[j] * num_of_cam + cam);
+    ch[1 * (size_t)n + j] = (lines[j].endpoint[2] - cx) / fx;
+    ch[2 * (size_t)n + j] = (lines[j].endpoint[3] - cy) / fy;
+    for (int k = 0; k < 4; ++k)
+      ch[(3 + k) * (size_t)n + j] = (line_vps && n_vps > 0 && cam < n_vps) ? (float)line_vps[4 * cam + k] : 0.0f;
+  }
+}

@@ -180,6 +180,9 @@ int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, i
                   double* grid, int32_t* best_idx, int32_t* pairs, int32_t* flags);
 int64_t orc_vp_sequence(const OrcLine* lines, const int32_t* counts, int n_frames, int cap, float f, float cx, float cy,
                         const uint32_t* seeds, int frame_count0, int math_mode, double* vps, int32_t* vp_idx);
+/* line_feature_tracker_node.cpp:64-153: cloud = 3n point floats then 7 channels of n floats (see orc_vp.c) */
+void orc_line_cloud(const OrcLine* lines, const int32_t* ids, int n, const double* line_vps, int n_vps, float fx,
+                    float fy, float cx, float cy, int num_of_cam, int cam, float* cloud);
 double orc_atan2_cr(double y, double x);
 double orc_atan_cr(double t);
 double orc_acos_cr(double x);

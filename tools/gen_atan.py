@@ -12,7 +12,7 @@ produce the same bits.
 
 Method: octant reduction to q = min/max in [0, 1] (double-double division), q = c + ..., c = k/64,
 t = (q - c) / (1 + q c), atan q = atan c (table, double-double) + t (1 - t^2/3 + ... - t^18/19)
-in double-double, then the octant/quadrant reflections with a double-double pi.  acos x =
+in double-double (the terms from t^8 on in plain double), then the octant/quadrant reflections with a double-double pi.  acos x =
 atan2(sqrt((1 - x)(1 + x)), x) with the square root in double-double.  Only IEEE add/mul/fma/div/sqrt.
 
     python tools/gen_atan.py      # rewrites the two headers
@@ -79,8 +79,11 @@ VPL_SC_FN vpl_dd vpl_atan_dd01(vpl_dd q) {{
   vpl_dd den = vpl_dd_add(vpl_dd_make(1.0, 0.0), vpl_dd_mul(q, vpl_dd_make(c, 0.0)));
   vpl_dd t = vpl_dd_div(num, den);
   vpl_dd u = vpl_dd_mul(t, t);
-  vpl_dd p = vpl_dd_make(vpl_at_coef[9][0], vpl_at_coef[9][1]);
-  for (int i = 8; i >= 0; --i)
+  /* u <= 2^-14: the terms from u^4 on are below 2^-56 of the sum, a plain double carries them */
+  double tail = vpl_at_coef[9][0];
+  for (int i = 8; i >= 4; --i) tail = vpl_at_coef[i][0] + u.hi * tail;
+  vpl_dd p = vpl_dd_make(tail, 0.0);
+  for (int i = 3; i >= 0; --i)
     p = vpl_dd_add(vpl_dd_make(vpl_at_coef[i][0], vpl_at_coef[i][1]), vpl_dd_mul(u, p));
   return vpl_dd_add(vpl_dd_make(vpl_at_tab[k][0], vpl_at_tab[k][1]), vpl_dd_mul(t, p));
 }}

@@ -30,8 +30,9 @@
 // correctly rounded in practice).  Where a transcendental only selects a grid cell, the CUDA library
 // function is used first and the shared one only when the cell coordinate lies within 1e-9 of a
 // cell boundary (their difference is < 1e-13), which gives the same cell for a fraction of the
-// work; a hypothesis whose construction is numerically delicate (vp3.z ~ 0 decides a sign) is
-// recomputed with the shared functions.  -fmad=false, IEEE sqrt/div, sums in the reference's order.
+// work.  The hypotheses themselves are built with the shared functions: the longitude of every vp2 is a
+// whole number of degrees in exact arithmetic (see vp_cell), so its cell is decided by the last bits.
+// -fmad=false, IEEE sqrt/div, sums in the reference's order.
 #include <limits.h>
 
 #include "vpl_atan.cuh"
@@ -248,60 +249,61 @@ __global__ void __launch_bounds__(256) vp_smooth_kernel(VpBuffers B, int n_frame
 }
 
 // ---- hypotheses + scoring -----------------------------------------------------------------------
-// vp2 / vp3 of hypothesis (vp1, j) (vp.cpp:139-160).  CR: the shared deterministic functions.
-template <bool CR>
-__device__ __forceinline__ void make_hypothesis(const V3& vp1, double sl, double cl, V3& vp2, V3& vp3, bool& risky) {
+// The shared deterministic functions, out of line: the scoring kernel calls them for every hypothesis and
+// stays small enough for the instruction cache (inlined everywhere it was 7000 instructions and stalled on
+// instruction fetch).
+__device__ __noinline__ double atan_cr_ni(double t) { return vpl_atan_cr(t); }
+__device__ __noinline__ double atan2_cr_ni(double y, double x) { return vpl_atan2_cr(y, x); }
+__device__ __noinline__ double acos_cr_ni(double x) { return vpl_acos_cr(x); }
+__device__ __noinline__ void sincos_cr_ni(double a, double* s, double* c) { vpl_sincos_cr(a, s, c); }
+
+// vp2 / vp3 of hypothesis (vp1, j) (vp.cpp:139-160), in the shared arithmetic.
+__device__ __forceinline__ void make_hypothesis(const V3& vp1, double sl, double cl, V3& vp2, V3& vp3) {
   const double k1 = vp1.x * sl + vp1.y * cl;
   const double k2 = vp1.z;
-  const double t = -k2 / k1;
+  const double phi = atan_cr_ni(-k2 / k1);
   double Z, sp;
-  if (CR) {
-    const double phi = vpl_atan_cr(t);
-    vpl_sincos_cr(phi, &sp, &Z);
-  } else {
-    const double phi = atan(t);
-    sincos(phi, &sp, &Z);
-  }
+  sincos_cr_ni(phi, &sp, &Z);
   vp2.x = sp * sl; vp2.y = sp * cl; vp2.z = Z;
   normalize_pos_z(vp2);
   vp3 = cross3(vp1, vp2);
-  if (!CR) risky |= fabs(vp3.z) < kGuard || !(t == t);
   normalize_pos_z(vp3);
 }
-// sphere cell of a unit vector (vp.cpp:291-316); false = contributes nothing
-template <bool CR>
-__device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell, bool& risky) {
+// Sphere cell of a unit vector (vp.cpp:291-316); false = contributes nothing.  EXACT_LON: the longitude goes
+// through the shared atan2 unconditionally -- vp2 = (sin phi sin lambda, sin phi cos lambda, cos phi) has
+// longitude lambda_j (+ pi) = a whole number of degrees in exact arithmetic, i.e. it always sits ON a cell
+// boundary and the cell the reference picks is decided by the last bits of x, y and atan2.  Otherwise the CUDA
+// library function is used and the shared one only within 1e-9 of a boundary.
+template <bool EXACT_LON>
+__device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell) {
   if (v.z == 0.0) return false;
-  double lat, lon;
-  if (CR) {
-    lat = vpl_acos_cr(v.z);
-    lon = vpl_atan2_cr(v.x, v.y) + kPi;
+  bool risky = v.z > 1.0 - 1e-12;
+  double lat = acos(v.z);
+  int la = cell_of(lat, one, risky);
+  if (risky || !(lat == lat)) {
+    lat = acos_cr_ni(v.z);
+    la = (int)(lat / one);
+  }
+  double lon;
+  int lo;
+  if (EXACT_LON) {
+    lon = atan2_cr_ni(v.x, v.y) + kPi;
+    lo = (int)(lon / one);
   } else {
-    lat = acos(v.z);
+    risky = false;
     lon = atan2(v.x, v.y) + kPi;
-    risky |= v.z > 1.0 - 1e-12 || !(lat == lat) || !(lon == lon);
+    lo = cell_of(lon, one, risky);
+    if (risky || !(lon == lon)) {
+      lon = atan2_cr_ni(v.x, v.y) + kPi;
+      lo = (int)(lon / one);
+    }
   }
   if (!(lat == lat) || !(lon == lon)) return false;
-  int la, lo;
-  if (CR) { la = (int)(lat / one); lo = (int)(lon / one); }
-  else { la = cell_of(lat, one, risky); lo = cell_of(lon, one, risky); }
   if (la == 90) la = 89;
   if (lo == 360) lo = 359;
   if (la < 0 || la >= kLA || lo < 0 || lo >= kLO) return false;
   cell = la * kLO + lo;
   return true;
-}
-template <bool CR>
-__device__ __forceinline__ double score_hypothesis(const double* __restrict__ g, const V3& vp1, int cell1, bool has1,
-                                                   double sl, double cl, bool& risky) {
-  V3 vp2, vp3;
-  make_hypothesis<CR>(vp1, sl, cl, vp2, vp3, risky);
-  double len = 0.0;
-  if (has1) len += g[cell1];
-  int c;
-  if (vp_cell<CR>(vp2, 1.0 / 180.0 * kPi, c, risky)) len += g[c];
-  if (vp_cell<CR>(vp3, 1.0 / 180.0 * kPi, c, risky)) len += g[c];
-  return len;
 }
 
 constexpr int kScoreThreads = 256;
@@ -317,13 +319,16 @@ __global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, Vp
   for (int i = split; i < P.it; i += splits) {
     const V3 vp1 = {vp1s[3 * i], vp1s[3 * i + 1], vp1s[3 * i + 2]};
     int cell1 = 0;
-    bool r1 = false;
-    const bool has1 = vp_cell<true>(vp1, one, cell1, r1);
+    const bool has1 = vp_cell<true>(vp1, one, cell1);
     for (int j = threadIdx.x; j < kNumVp2; j += kScoreThreads) {
       const double sl = B.lambda_sc[2 * j], cl = B.lambda_sc[2 * j + 1];
-      bool risky = false;
-      double len = score_hypothesis<false>(g, vp1, cell1, has1, sl, cl, risky);
-      if (risky) len = score_hypothesis<true>(g, vp1, cell1, has1, sl, cl, risky);
+      V3 vp2, vp3;
+      make_hypothesis(vp1, sl, cl, vp2, vp3);
+      double len = 0.0;  // lineLength[i] += sphereGrid[..][..] for the three vanishing points, in this order
+      int c;
+      if (has1) len += g[cell1];
+      if (vp_cell<true>(vp2, one, c)) len += g[c];
+      if (vp_cell<false>(vp3, one, c)) len += g[c];
       const int idx = i * kNumVp2 + j;
       if (len > best) { best = len; best_idx = idx; }  // a thread's indices ascend: strict > keeps the lowest
     }
@@ -389,8 +394,7 @@ __global__ void __launch_bounds__(128) vp_classify_kernel(const VplLine* __restr
     const double* v1 = B.vp1 + ((size_t)frame * P.it + i) * 3;
     const V3 vp1 = {v1[0], v1[1], v1[2]};
     V3 vp2, vp3;
-    bool r = false;
-    make_hypothesis<true>(vp1, B.lambda_sc[2 * j], B.lambda_sc[2 * j + 1], vp2, vp3, r);
+    make_hypothesis(vp1, B.lambda_sc[2 * j], B.lambda_sc[2 * j + 1], vp2, vp3);
     if (frame_count0 + frame != 0 && !(fabs(vp2.y) > 0.8)) { const V3 t = vp2; vp2 = vp3; vp3 = t; }  // :337-349
     s_vps[0] = vp1.x; s_vps[1] = vp1.y; s_vps[2] = vp1.z;
     s_vps[3] = vp2.x; s_vps[4] = vp2.y; s_vps[5] = vp2.z;
