@@ -240,6 +240,16 @@ int vpl_vp_submit(VplContext* ctx, int slot, const VplLine* lines, const int32_t
                   const int32_t* n_all, int n_frames, int cap, const uint32_t* seeds, int frame_count0);
 int vpl_vp_collect(VplContext* ctx, int slot, int cap, double* vps, int32_t* vp_idx, double* line_vps,
                    int32_t* status);
+/* The sensor_msgs::PointCloud body img_callback publishes for every frame of the batch last collected from
+ * `slot` (feature_tracker/src/line_feature_tracker_node.cpp:64-153), for camera index `cam` of num_of_cam
+ * (NUM_OF_CAM; the loop variable i of :88): frame i's block starts at cloud + i*cap*10 and holds, for its
+ * n = n_all[i] lines, 3n point floats -- ((x1 - cx)/fx, (y1 - cy)/fy, 1): the first endpoint through
+ * LineFeatureTracker::undistortedLineEndPoints, line_feature_tracker.cpp:36-52 -- then the seven channels
+ * id_of_line (= line_ids * num_of_cam + cam), u_of_endpoint, v_of_endpoint (second endpoint), vp_x, vp_y, vp_z,
+ * vp_z_inv, n floats each.  As in the reference, every line carries vp[cam]: the Vector4d of line number `cam`
+ * (:108-114 index the per-line list with the camera index).  line_ids: n_frames * cap (the tracker's lineID). */
+int vpl_vp_pack_cloud(VplContext* ctx, int slot, const int32_t* line_ids, int cap, float fx, float fy, float cx, float cy,
+                      int num_of_cam, int cam, float* cloud);
 /* Re-runs the stage on the lines already resident on the slot (measurement). */
 int vpl_vp_run_resident(VplContext* ctx, int slot);
 /* Stage outputs of frame `frame` of the last batch on slot 0: the smoothed 90 x 360 grid, the index of

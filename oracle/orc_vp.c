@@ -34,6 +34,8 @@
 double orc_atan2_cr(double y, double x) { return vpl_atan2_cr(y, x); }
 double orc_atan_cr(double t) { return vpl_atan_cr(t); }
 double orc_acos_cr(double x) { return vpl_acos_cr(x); }
+double orc_sin_cr(double a) { return vpl_sin_cr(a); }
+void orc_sincos_cr(double a, double* s, double* c) { vpl_sincos_cr(a, s, c); }
 
 /* ---- glibc srandom_r / random_r, TYPE_3 (degree 31, separation 3): what srand()/rand() run ---- */
 void orc_grand_seed(OrcGRand* g, unsigned seed) {

@@ -186,6 +186,8 @@ void orc_line_cloud(const OrcLine* lines, const int32_t* ids, int n, const doubl
 double orc_atan2_cr(double y, double x);
 double orc_atan_cr(double t);
 double orc_acos_cr(double x);
+double orc_sin_cr(double a);
+void orc_sincos_cr(double a, double* s, double* c);
 
 /* Whole front end on a frame sequence (for the CPU baseline timing).  Returns
  * total keylines over the sequence (each frame is matched k=1 against the

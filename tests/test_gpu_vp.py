@@ -168,3 +168,22 @@ def test_vp_errors(ctx, vpl):
     with pytest.raises(vpl.capi.VplError):
         c2.vp_detect_batch([np.zeros(3, vpl.capi.LINE_DTYPE)] * 3, [1, 2, 3])  # more frames than max_batch
     c2.close()
+
+
+def test_vp_pointcloud_packing(ctx, vpl, orc, mh04):
+    """vpl_vp_pack_cloud against the oracle restatement of img_callback's packing loop: bit-exact floats."""
+    ctx.vp_configure(*EUROC)
+    sets = [orc.edline_detect(mh04[k]) for k in (2, 7)] + [orc.edline_detect(mh04[4])[:1]]
+    ids = [np.arange(len(s), dtype=np.int32) * 3 + 11 * (i + 1) for i, s in enumerate(sets)]
+    vps, idx, st, lv = ctx.vp_detect_batch([as_capi(vpl, l) for l in sets], [31, 32, 33], frame_count0=2, with_line_vps=True)
+    fx, fy, cx, cy = 461.6, 460.3, 363.0, 248.1
+    for ncam, cam in ((1, 0), (2, 1)):
+        got = ctx.vp_pack_cloud(ids, fx, fy, cx, cy, ncam, cam)
+        for i, s in enumerate(sets):
+            want = orc.line_cloud(s, ids[i], lv[i], fx, fy, cx, cy, ncam, cam)
+            for k in want:
+                assert got[i][k].tobytes() == want[k].tobytes(), (i, k)
+            assert (got[i]["points"][:, 2] == 1).all()
+    # every line carries the Vector4d of line number `cam` (the reference indexes the per-line list with the camera index)
+    g = ctx.vp_pack_cloud(ids, fx, fy, cx, cy, 1, 0)[0]
+    assert (g["vp_x"] == np.float32(lv[0][0][0])).all()

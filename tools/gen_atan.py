@@ -83,12 +83,13 @@ VPL_SC_FN vpl_dd vpl_atan_dd01(vpl_dd q) {{
   double tail = vpl_at_coef[9][0];
   for (int i = 8; i >= 4; --i) tail = vpl_at_coef[i][0] + u.hi * tail;
   vpl_dd p = vpl_dd_make(tail, 0.0);
+  VPL_SC_ROLLED
   for (int i = 3; i >= 0; --i)
     p = vpl_dd_add(vpl_dd_make(vpl_at_coef[i][0], vpl_at_coef[i][1]), vpl_dd_mul(u, p));
   return vpl_dd_add(vpl_dd_make(vpl_at_tab[k][0], vpl_at_tab[k][1]), vpl_dd_mul(t, p));
 }}
 /* atan2(y, x) of double-double arguments, as a double-double in (-pi, pi] */
-VPL_SC_FN vpl_dd vpl_atan2_dd(vpl_dd y, vpl_dd x) {{
+VPL_AT_CORE vpl_dd vpl_atan2_dd(vpl_dd y, vpl_dd x) {{
   int yneg = y.hi < 0.0, xneg = x.hi < 0.0;
   vpl_dd a = yneg ? vpl_dd_neg(y) : y;
   vpl_dd b = xneg ? vpl_dd_neg(x) : x;
@@ -132,9 +133,11 @@ VPL_SC_FN double vpl_acos_cr(double x) {{
     c_head = ("/* GENERATED by tools/gen_atan.py -- do not edit.  Deterministic double atan / atan2 / acos\n"
               " * (table + double-double Taylor; IEEE add/mul/fma/div/sqrt only). */\n")
     with open(os.path.join(ROOT, "oracle", "orc_atan.h"), "w") as f:
-        f.write(c_head + "#ifndef ORC_ATAN_H\n#define ORC_ATAN_H\n#include \"orc_sincos.h\"\n" + body + "#endif\n")
+        f.write(c_head + "#ifndef ORC_ATAN_H\n#define ORC_ATAN_H\n#include \"orc_sincos.h\"\n#define VPL_AT_CORE static inline\n" + body + "#endif\n")
     with open(os.path.join(ROOT, "vplines-slam_b200", "csrc", "vpl_atan.cuh"), "w") as f:
-        f.write(c_head + "#pragma once\n#include \"vpl_sincos.cuh\"\nnamespace vpl {\n" + body + "}  // namespace vpl\n")
+        f.write(c_head + "#pragma once\n#include \"vpl_sincos.cuh\"\n"
+                "/* one out-of-line copy per kernel image: atan, atan2 and acos all end in it */\n"
+                "#define VPL_AT_CORE static __device__ __noinline__\nnamespace vpl {\n" + body + "}  // namespace vpl\n")
     print("wrote oracle/orc_atan.h and vplines-slam_b200/csrc/vpl_atan.cuh")
 
 

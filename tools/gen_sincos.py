@@ -78,10 +78,17 @@ VPL_SC_FN void vpl_sincos_cr(double theta, double* s_out, double* c_out) {{
   p3.hi = -p3.hi; p3.lo = -p3.lo;
   r = vpl_dd_add(r, p3);
   vpl_dd r2 = vpl_dd_mul(r, r);
+  /* |r| <= pi/4: the terms from r^18 / r^19 on are below 2^-60 of the sums, a plain double carries them */
+  double ts = vpl_sc_sin[11][0], tc = vpl_sc_cos[11][0];
+  for (int i = 10; i >= 8; --i) {{
+    ts = vpl_sc_sin[i][0] + r2.hi * ts;
+    tc = vpl_sc_cos[i][0] + r2.hi * tc;
+  }}
   vpl_dd ps, pc;
-  ps.hi = vpl_sc_sin[11][0]; ps.lo = vpl_sc_sin[11][1];
-  pc.hi = vpl_sc_cos[11][0]; pc.lo = vpl_sc_cos[11][1];
-  for (int i = 10; i >= 0; --i) {{
+  ps.hi = ts; ps.lo = 0.0;
+  pc.hi = tc; pc.lo = 0.0;
+  VPL_SC_ROLLED
+  for (int i = 7; i >= 0; --i) {{
     vpl_dd cs; cs.hi = vpl_sc_sin[i][0]; cs.lo = vpl_sc_sin[i][1];
     vpl_dd cc; cc.hi = vpl_sc_cos[i][0]; cc.lo = vpl_sc_cos[i][1];
     ps = vpl_dd_add(cs, vpl_dd_mul(r2, ps));
@@ -99,17 +106,86 @@ VPL_SC_FN void vpl_sincos_cr(double theta, double* s_out, double* c_out) {{
     default: *s_out = -cv; *c_out = sv; break;
   }}
 }}
+
+/* sin(theta) alone: the same reduction and the same polynomial evaluation as above, only the one the quadrant needs
+ * (bit-identical to the sine of vpl_sincos_cr). */
+VPL_SC_FN double vpl_sin_cr(double theta) {{
+  double kd = rint(theta * VPL_SC_2OPI);
+  int k = (int)kd;
+  double t1 = theta - kd * VPL_SC_P1;
+  vpl_dd r = vpl_dd_two_sum(t1, -(kd * VPL_SC_P2));
+  vpl_dd p3; p3.hi = kd * VPL_SC_P3H; p3.lo = fma(kd, VPL_SC_P3H, -p3.hi) + kd * VPL_SC_P3L;
+  p3.hi = -p3.hi; p3.lo = -p3.lo;
+  r = vpl_dd_add(r, p3);
+  vpl_dd r2 = vpl_dd_mul(r, r);
+  double v;
+  if (k & 1) {{
+    double tc = vpl_sc_cos[11][0];
+    for (int i = 10; i >= 8; --i) tc = vpl_sc_cos[i][0] + r2.hi * tc;
+    vpl_dd pc; pc.hi = tc; pc.lo = 0.0;
+    VPL_SC_ROLLED
+  for (int i = 7; i >= 0; --i) {{
+      vpl_dd cc; cc.hi = vpl_sc_cos[i][0]; cc.lo = vpl_sc_cos[i][1];
+      pc = vpl_dd_add(cc, vpl_dd_mul(r2, pc));
+    }}
+    vpl_dd one; one.hi = 1.0; one.lo = 0.0;
+    vpl_dd cr = vpl_dd_add(one, vpl_dd_mul(r2, pc));
+    v = cr.hi + cr.lo;
+  }} else {{
+    double ts = vpl_sc_sin[11][0];
+    for (int i = 10; i >= 8; --i) ts = vpl_sc_sin[i][0] + r2.hi * ts;
+    vpl_dd ps; ps.hi = ts; ps.lo = 0.0;
+    VPL_SC_ROLLED
+  for (int i = 7; i >= 0; --i) {{
+      vpl_dd cs; cs.hi = vpl_sc_sin[i][0]; cs.lo = vpl_sc_sin[i][1];
+      ps = vpl_dd_add(cs, vpl_dd_mul(r2, ps));
+    }}
+    vpl_dd sr = vpl_dd_add(r, vpl_dd_mul(r, vpl_dd_mul(r2, ps)));
+    v = sr.hi + sr.lo;
+  }}
+  return (k & 2) ? -v : v;
+}}
 """
     head = ("/* GENERATED by tools/gen_sincos.py -- do not edit.  Deterministic double sincos\n"
             " * (double-double Taylor after Cody-Waite reduction; IEEE add/mul/fma only). */\n")
     with open(os.path.join(ROOT, "oracle", "orc_sincos.h"), "w") as f:
         f.write(head + "#ifndef ORC_SINCOS_H\n#define ORC_SINCOS_H\n#include <math.h>\n"
-                "#define VPL_SC_CONST const\n#define VPL_SC_FN static inline\n" + body + "#endif\n")
+                "#define VPL_SC_CONST const\n#define VPL_SC_FN static inline\n#define VPL_SC_ROLLED\n" + body + "#endif\n")
     with open(os.path.join(ROOT, "vplines-slam_b200", "csrc", "vpl_sincos.cuh"), "w") as f:
         f.write(head + "#pragma once\n#define VPL_SC_CONST __device__ const\n"
-                "#define VPL_SC_FN __device__ __forceinline__\nnamespace vpl {\n" + body + "}  // namespace vpl\n")
+                "#define VPL_SC_FN __device__ __forceinline__\n"
+                "#define VPL_SC_ROLLED _Pragma(\"unroll 1\") /* keeps the kernels that call this small enough for the instruction cache */\n"
+                "namespace vpl {\n" + body + "}  // namespace vpl\n")
     print("written")
 
 
+def check(n):
+    """Compares the oracle's build of these functions with mpmath (round to nearest)."""
+    import ctypes
+    import random
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    L = orc.lib()
+    L.orc_sin_cr.restype = ctypes.c_double; L.orc_sin_cr.argtypes = [ctypes.c_double]
+    L.orc_sincos_cr.argtypes = [ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    rnd = random.Random(11)
+    bad = [0, 0, 0]
+    s, c = ctypes.c_double(), ctypes.c_double()
+    for i in range(n):
+        t = rnd.uniform(-7, 7) if i % 3 else rnd.uniform(-1, 1) * 10.0 ** rnd.uniform(-8, 3)
+        L.orc_sincos_cr(t, ctypes.byref(s), ctypes.byref(c))
+        es, ec = float(mp.sin(mp.mpf(t))), float(mp.cos(mp.mpf(t)))
+        bad[0] += s.value != es
+        bad[1] += c.value != ec
+        bad[2] += L.orc_sin_cr(t) != s.value
+    print("misrounded of %d: sin %d, cos %d; vpl_sin_cr != sine of vpl_sincos_cr: %d" % (n, bad[0], bad[1], bad[2]))
+    return bad
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        check(int(sys.argv[2]))
+    else:
+        main()

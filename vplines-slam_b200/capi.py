@@ -80,7 +80,7 @@ EXPORTS = [
     "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
     "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
-    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp",
+    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -157,6 +157,7 @@ def load():
     L.vpl_vp_collect.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.vpl_vp_run_resident.argtypes = [vp, i32]
     L.vpl_debug_vp.argtypes = [vp, i32, vp, vp, vp]
+    L.vpl_vp_pack_cloud.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]
     _lib = L
     return L
 
@@ -479,6 +480,26 @@ class Context:
 
     def vp_collect_into(self, slot, cap, vps, vp_idx, status=None, line_vps=None):
         self._ck(self._L.vpl_vp_collect(self._h, slot, cap, _ptr(vps), _ptr(vp_idx), _ptr(line_vps), _ptr(status)))
+
+    def vp_pack_cloud(self, line_ids, fx, fy, cx, cy, num_of_cam=1, cam=0, slot=0):
+        """The PointCloud body of line_feature_tracker_node.cpp:64-153 for every frame of the batch last collected from
+        `slot`; line_ids: one int array per frame -> list of dict(points (n,3), id, u, v, vp_x, vp_y, vp_z, vp_z_inv)."""
+        n = len(line_ids)
+        cap = max(1, max(len(a) for a in line_ids))
+        ids = np.zeros((n, cap), np.int32)
+        for i, a in enumerate(line_ids):
+            ids[i, :len(a)] = a
+        cloud = np.zeros((n, cap * 10), np.float32)
+        self._ck(self._L.vpl_vp_pack_cloud(self._h, slot, _ptr(ids), cap, float(fx), float(fy), float(cx), float(cy),
+                                           int(num_of_cam), int(cam), _ptr(cloud)))
+        out = []
+        for i, a in enumerate(line_ids):
+            k = len(a)
+            d = {"points": cloud[i, :3 * k].reshape(k, 3).copy()}
+            for c_, nm in enumerate(("id", "u", "v", "vp_x", "vp_y", "vp_z", "vp_z_inv")):
+                d[nm] = cloud[i, 3 * k + c_ * k:3 * k + (c_ + 1) * k].copy()
+            out.append(d)
+        return out
 
     def vp_run_resident(self, slot):
         self._ck(self._L.vpl_vp_run_resident(self._h, slot))

@@ -88,6 +88,10 @@ struct Slot {
   double* d_vps = nullptr;         // B x 9
   int* d_vp_idx = nullptr;         // B x cap
   double* d_line_vps = nullptr;    // B x cap x 4
+  int* d_vp_ids = nullptr;         // B x cap: the tracker's line ids (PointCloud packing)
+  float* d_cloud = nullptr;        // B x cap x 10
+  int* h_vp_ids = nullptr;
+  float* h_cloud = nullptr;
   VplLine* h_vp_lines = nullptr;
   VplLine* h_vp_all = nullptr;
   int* h_vp_n = nullptr;
@@ -719,7 +723,9 @@ void vp_free(Slot& s) {
   cudaFree(s.vp.rng); cudaFree(s.vp.status); cudaFree(s.vp.grid); cudaFree(s.vp.grid_new);
   cudaFree(s.vp.part_best); cudaFree(s.vp.part_idx); cudaFree(s.vp.best_idx); cudaFree(s.vp.lx);
   cudaFree(s.d_vp_lines); cudaFree(s.d_vp_all); cudaFree(s.d_vp_n); cudaFree(s.d_vp_seeds); cudaFree(s.d_vps);
-  cudaFree(s.d_vp_idx); cudaFree(s.d_line_vps);
+  cudaFree(s.d_vp_idx); cudaFree(s.d_line_vps); cudaFree(s.d_vp_ids); cudaFree(s.d_cloud);
+  cudaFreeHost(s.h_vp_ids); cudaFreeHost(s.h_cloud);
+  s.d_vp_ids = nullptr; s.d_cloud = nullptr; s.h_vp_ids = nullptr; s.h_cloud = nullptr;
   cudaFreeHost(s.h_vp_lines); cudaFreeHost(s.h_vp_all); cudaFreeHost(s.h_vp_n); cudaFreeHost(s.h_vp_seeds);
   cudaFreeHost(s.h_vps); cudaFreeHost(s.h_vp_idx); cudaFreeHost(s.h_line_vps); cudaFreeHost(s.h_vp_status);
   s.vp = VpBuffers{};
@@ -1623,6 +1629,10 @@ int vpl_vp_configure(VplContext* c, float f, float cx, float cy) {
     CK(c, hmalloc(&s.h_vp_idx, B * cap));
     CK(c, hmalloc(&s.h_line_vps, B * cap * 4));
     CK(c, hmalloc(&s.h_vp_status, 2 * B));
+    CK(c, dmalloc(&s.d_vp_ids, B * cap));
+    CK(c, dmalloc(&s.d_cloud, B * cap * 10));
+    CK(c, hmalloc(&s.h_vp_ids, B * cap));
+    CK(c, hmalloc(&s.h_cloud, B * cap * 10));
     CK(c, cudaMemset(s.vp.status, 0, 2 * B * sizeof(int)));
   }
   c->vp_ready = true;
@@ -1714,6 +1724,37 @@ int vpl_vp_detect_batch(VplContext* c, const VplLine* lines, const int32_t* n_li
   int r = vpl_vp_submit(c, 0, lines, n_lines, all_lines, n_all, n_frames, cap, seeds, frame_count0);
   if (r) return r;
   return vpl_vp_collect(c, 0, cap, vps, vp_idx, line_vps, status);
+}
+
+int vpl_vp_pack_cloud(VplContext* c, int slot, const int32_t* line_ids, int cap, float fx, float fy, float cx, float cy,
+                      int num_of_cam, int cam, float* cloud) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (s.vp_n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no vanishing-point batch", slot);
+  if (!line_ids || !cloud || num_of_cam < 1 || cam < 0 || cam >= num_of_cam) return fail(c, VPL_E_INVALID, "bad argument");
+  CK(c, cudaSetDevice(c->cfg.device));
+  const int mcap = c->cfg.max_lines, B = c->cfg.max_batch, n = s.vp_n;
+  const int* na = s.vp_same ? s.h_vp_n : s.h_vp_n + B;
+  for (int i = 0; i < n; ++i) {
+    if (na[i] > cap) return fail(c, VPL_E_CAPACITY, "frame %d: %d lines > cap %d", i, na[i], cap);
+    memcpy(s.h_vp_ids + (size_t)i * mcap, line_ids + (size_t)i * cap, (size_t)na[i] * sizeof(int));
+  }
+  CK(c, cudaMemcpyAsync(s.d_vp_ids, s.h_vp_ids, (size_t)n * mcap * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  {
+    StageTimer t(c, s, VPL_STAGE_VP_CLASSIFY);
+    launch_vp_cloud(s.vp_same ? s.d_vp_lines : s.d_vp_all, s.vp_same ? s.d_vp_n : s.d_vp_n + B, mcap, s.d_vp_ids,
+                    s.d_line_vps, fx, fy, cx, cy, num_of_cam, cam, s.d_cloud, n, s.stream);
+    t.launches(1);
+  }
+  CK(c, cudaMemcpyAsync(s.h_cloud, s.d_cloud, (size_t)n * mcap * 10 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+  int r = finish(c, s);
+  if (r) return r;
+  for (int i = 0; i < n; ++i)
+    memcpy(cloud + (size_t)i * cap * 10, s.h_cloud + (size_t)i * mcap * 10, (size_t)na[i] * 10 * sizeof(float));
+  return VPL_OK;
 }
 
 int vpl_vp_run_resident(VplContext* c, int slot) {

@@ -200,9 +200,7 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vp_vote_kernel(const int* __r
             if (la >= kLA) la = kLA - 1;
             if (lo >= kLO) lo = kLO - 1;
             if (la >= 0 && lo >= 0) {
-              double s, c;
-              vpl_sincos_cr(2.0 * dev, &s, &c);
-              val = sqrt(li * length[j]) * (s + 0.2);
+              val = sqrt(li * length[j]) * (vpl_sin_cr(2.0 * dev) + 0.2);
               cell = la * kLO + lo;
             }
           }
@@ -307,31 +305,38 @@ __device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell) {
 }
 
 constexpr int kScoreThreads = 256;
-// grid (splits, frames): split s scores the outer iterations i = s, s + splits, ...
+// grid (splits, frames): split s scores the outer iterations [s it / splits, (s + 1) it / splits) -- a contiguous
+// range of 360 (i1 - i0) hypotheses dealt to the threads round robin (360 is not a multiple of the CTA, a loop
+// per outer iteration would leave half the warps waiting)
 __global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, VpParams P, int splits) {
   const int frame = blockIdx.y, split = blockIdx.x;
   if (B.status[frame] != 0) return;
   const double* g = B.grid_new + (size_t)frame * kCells;
   const double* vp1s = B.vp1 + (size_t)frame * P.it * 3;
   const double one = 1.0 / 180.0 * kPi;
+  const int i0 = P.it * split / splits, i1 = P.it * (split + 1) / splits;
+  __shared__ int s_cell1[128];  // cell of vp1 per outer iteration (-1: contributes nothing); it <= 128
+  for (int i = i0 + threadIdx.x; i < i1; i += kScoreThreads) {
+    const V3 vp1 = {vp1s[3 * i], vp1s[3 * i + 1], vp1s[3 * i + 2]};
+    int c = -1;
+    if (!vp_cell<true>(vp1, one, c)) c = -1;
+    s_cell1[i - i0] = c;
+  }
+  __syncthreads();
   double best = 0.0;
   int best_idx = INT_MAX;
-  for (int i = split; i < P.it; i += splits) {
+  for (int idx = i0 * kNumVp2 + threadIdx.x; idx < i1 * kNumVp2; idx += kScoreThreads) {
+    const int i = idx / kNumVp2, j = idx - i * kNumVp2;
     const V3 vp1 = {vp1s[3 * i], vp1s[3 * i + 1], vp1s[3 * i + 2]};
-    int cell1 = 0;
-    const bool has1 = vp_cell<true>(vp1, one, cell1);
-    for (int j = threadIdx.x; j < kNumVp2; j += kScoreThreads) {
-      const double sl = B.lambda_sc[2 * j], cl = B.lambda_sc[2 * j + 1];
-      V3 vp2, vp3;
-      make_hypothesis(vp1, sl, cl, vp2, vp3);
-      double len = 0.0;  // lineLength[i] += sphereGrid[..][..] for the three vanishing points, in this order
-      int c;
-      if (has1) len += g[cell1];
-      if (vp_cell<true>(vp2, one, c)) len += g[c];
-      if (vp_cell<false>(vp3, one, c)) len += g[c];
-      const int idx = i * kNumVp2 + j;
-      if (len > best) { best = len; best_idx = idx; }  // a thread's indices ascend: strict > keeps the lowest
-    }
+    const double sl = B.lambda_sc[2 * j], cl = B.lambda_sc[2 * j + 1];
+    V3 vp2, vp3;
+    make_hypothesis(vp1, sl, cl, vp2, vp3);
+    double len = 0.0;  // lineLength[i] += sphereGrid[..][..] for the three vanishing points, in this order
+    int c = s_cell1[i - i0];
+    if (c >= 0) len += g[c];
+    if (vp_cell<true>(vp2, one, c)) len += g[c];
+    if (vp_cell<false>(vp3, one, c)) len += g[c];
+    if (len > best) { best = len; best_idx = idx; }  // a thread's indices ascend: strict > keeps the lowest
   }
   // block arg-max, lowest index on ties
   __shared__ double s_b[kScoreThreads / 32];
@@ -477,6 +482,35 @@ __global__ void __launch_bounds__(128) vp_classify_kernel(const VplLine* __restr
   B.flags[frame] = flags;
 }
 
+// The PointCloud body img_callback publishes per frame (feature_tracker/src/line_feature_tracker_node.cpp:64-153):
+// n x 3 point floats (undistorted first endpoint of LineFeatureTracker::undistortedLineEndPoints,
+// line_feature_tracker.cpp:36-52, z = 1), then the channels id, u, v, vp_x, vp_y, vp_z, vp_z_inv (n floats
+// each).  As the reference writes it, every line carries vp[i] -- the Vector4d of line number `cam` (:108-114).
+__global__ void __launch_bounds__(128) vp_cloud_kernel(const VplLine* __restrict__ all_lines, const int* __restrict__ n_all,
+                                                       int cap, const int* __restrict__ ids, const double* __restrict__ line_vps,
+                                                       float fx, float fy, float cx, float cy, int num_of_cam, int cam,
+                                                       float* __restrict__ cloud) {
+  const int frame = blockIdx.x;
+  const int n = n_all[frame];
+  const VplLine* L = all_lines + (size_t)frame * cap;
+  float* pts = cloud + (size_t)frame * cap * 10;
+  float* ch = pts + 3 * (size_t)n;
+  const double* lv = line_vps + (size_t)frame * cap * 4;
+  float vp4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) vp4[k] = cam < n ? (float)lv[4 * cam + k] : 0.0f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    pts[3 * j] = (L[j].endpoint[0] - cx) / fx;
+    pts[3 * j + 1] = (L[j].endpoint[1] - cy) / fy;
+    pts[3 * j + 2] = 1.0f;
+    ch[j] = (float)(ids[(size_t)frame * cap + j] * num_of_cam + cam);
+    ch[(size_t)n + j] = (L[j].endpoint[2] - cx) / fx;
+    ch[2 * (size_t)n + j] = (L[j].endpoint[3] - cy) / fy;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ch[(3 + k) * (size_t)n + j] = vp4[k];
+  }
+}
+
 __global__ void vp_lambda_kernel(double* sc) {  // sin / cos of j * (2 pi / 360), :99-101, :142
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= kNumVp2) return;
@@ -487,6 +521,11 @@ __global__ void vp_lambda_kernel(double* sc) {  // sin / cos of j * (2 pi / 360)
 }
 
 }  // namespace
+
+void launch_vp_cloud(const VplLine* all_lines, const int* n_all, int cap, const int* ids, const double* line_vps, float fx,
+                     float fy, float cx, float cy, int num_of_cam, int cam, float* cloud, int n_frames, cudaStream_t st) {
+  vp_cloud_kernel<<<n_frames, 128, 0, st>>>(all_lines, n_all, cap, ids, line_vps, fx, fy, cx, cy, num_of_cam, cam, cloud);
+}
 
 void launch_vp_lambda(double* lambda_sc, cudaStream_t st) { vp_lambda_kernel<<<2, 192, 0, st>>>(lambda_sc); }
 

@@ -276,6 +276,8 @@ struct VpBuffers {      // per frame (cap lines)
 constexpr int kVpMaxSplits = 15;
 constexpr int kVpCells = 90 * 360;
 void launch_vp_lambda(double* lambda_sc, cudaStream_t st);
+void launch_vp_cloud(const VplLine* all_lines, const int* n_all, int cap, const int* ids, const double* line_vps, float fx,
+                     float fy, float cx, float cy, int num_of_cam, int cam, float* cloud, int n_frames, cudaStream_t st);
 int vp_score_splits(int n_frames);
 // the stage = these four, in this order (each: the launches it makes)
 void launch_vp_prepare(const VplLine* lines, const int* n_lines, int cap, const unsigned* seeds, const VpBuffers& B,
