@@ -832,16 +832,26 @@ def main():
     achieved = eng_bytes / (eng_dur * 1e-3) / 1e9 if eng_dur > 0 else 0.0
     stage_share = {k: round(v[0] / max(sum(x[0] for x in stage.values()), 1e-9), 4) for k, v in stage.items()}
     traffic = None
+    issue = None
     tp = os.path.join(ROOT, "profiles", "engine_traffic.json")
     if os.path.exists(tp) and args.workload == "C2":
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per frame
-            traffic = float(json.load(open(tp))["dram_bytes_per_frame"]) * B
+            et = json.load(open(tp))
+            traffic = float(et["dram_bytes_per_frame"]) * B
+            # supplementary yardstick for this issue-bound kernel: warp instructions per frame (same ncu capture) x
+            # frames / the launch duration measured live, against 148 SMs x 4 schedulers x the SM clock under load
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            ach = float(et["warp_inst_per_frame"]) * B / (eng_dur * 1e-3) if eng_dur > 0 else 0.0
+            issue = {"achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": 148 * 4 * sm_hz,
+                     "frac": ach / (148 * 4 * sm_hz), "warp_inst_per_frame": float(et["warp_inst_per_frame"]),
+                     "source": "profiles/engine_traffic.json (ncu smsp__inst_executed.sum per frame) x live launch time"}
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "region_engine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "ms_per_launch": eng_dur, "algorithmic_bytes_per_launch": eng_bytes,
                 "note": "latency-bound by the sequential seed/FIFO order of LSD region growing; see DESIGN.md",
+                "issue_rate": issue,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},
                 "stage_share": stage_share}
 

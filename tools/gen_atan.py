@@ -51,13 +51,14 @@ def main():
 {arr('vpl_at_tab', tab)}{arr('vpl_at_coef', coef)}
 VPL_SC_FN vpl_dd vpl_dd_make(double h, double l) {{ vpl_dd r; r.hi = h; r.lo = l; return r; }}
 VPL_SC_FN vpl_dd vpl_dd_neg(vpl_dd a) {{ a.hi = -a.hi; a.lo = -a.lo; return a; }}
-/* a / b, ~2^-100 relative */
+/* a / b, ~2^-100 relative: three quotient digits from ONE reciprocal (each residual is formed exactly) */
 VPL_SC_FN vpl_dd vpl_dd_div(vpl_dd a, vpl_dd b) {{
-  double q1 = a.hi / b.hi;
+  double rb = 1.0 / b.hi;
+  double q1 = a.hi * rb;
   vpl_dd r = vpl_dd_add(a, vpl_dd_neg(vpl_dd_mul(b, vpl_dd_make(q1, 0.0))));
-  double q2 = r.hi / b.hi;
+  double q2 = r.hi * rb;
   r = vpl_dd_add(r, vpl_dd_neg(vpl_dd_mul(b, vpl_dd_make(q2, 0.0))));
-  double q3 = r.hi / b.hi;
+  double q3 = r.hi * rb;
   vpl_dd q = vpl_dd_quick(q1, q2);
   return vpl_dd_add(q, vpl_dd_make(q3, 0.0));
 }}
@@ -71,7 +72,7 @@ VPL_SC_FN vpl_dd vpl_dd_sqrt(vpl_dd a) {{
   return vpl_dd_quick(x, r.hi / (2.0 * x));
 }}
 /* atan(q), q in [0, 1] as a double-double */
-VPL_SC_FN vpl_dd vpl_atan_dd01(vpl_dd q) {{
+VPL_AT_CORE vpl_dd vpl_atan_dd01(vpl_dd q) {{
   double kd = rint(q.hi * 64.0);
   int k = (int)kd;
   double c = kd * 0.015625;
@@ -89,7 +90,7 @@ VPL_SC_FN vpl_dd vpl_atan_dd01(vpl_dd q) {{
   return vpl_dd_add(vpl_dd_make(vpl_at_tab[k][0], vpl_at_tab[k][1]), vpl_dd_mul(t, p));
 }}
 /* atan2(y, x) of double-double arguments, as a double-double in (-pi, pi] */
-VPL_AT_CORE vpl_dd vpl_atan2_dd(vpl_dd y, vpl_dd x) {{
+VPL_SC_FN vpl_dd vpl_atan2_dd(vpl_dd y, vpl_dd x) {{
   int yneg = y.hi < 0.0, xneg = x.hi < 0.0;
   vpl_dd a = yneg ? vpl_dd_neg(y) : y;
   vpl_dd b = xneg ? vpl_dd_neg(x) : x;
@@ -114,12 +115,20 @@ VPL_SC_FN double vpl_atan2_cr(double y, double x) {{
   vpl_dd r = vpl_atan2_dd(vpl_dd_make(y, 0.0), vpl_dd_make(x, 0.0));
   return r.hi + r.lo;
 }}
-/* std::atan(double) */
+/* std::atan(double): atan2(t, 1) without the division by one */
 VPL_SC_FN double vpl_atan_cr(double t) {{
   if (t != t) return t;
   if (t == 0.0) return t;
-  vpl_dd r = vpl_atan2_dd(vpl_dd_make(t, 0.0), vpl_dd_make(1.0, 0.0));
-  return r.hi + r.lo;
+  double a = t < 0.0 ? -t : t;
+  vpl_dd r;
+  if (a <= 1.0) {{
+    r = vpl_atan_dd01(vpl_dd_make(a, 0.0));
+  }} else {{
+    vpl_dd q = a - a != 0.0 ? vpl_dd_make(0.0, 0.0) : vpl_dd_div(vpl_dd_make(1.0, 0.0), vpl_dd_make(a, 0.0));
+    r = vpl_dd_add(vpl_dd_make(VPL_AT_PIO2_H, VPL_AT_PIO2_L), vpl_dd_neg(vpl_atan_dd01(q)));
+  }}
+  double v = r.hi + r.lo;
+  return t < 0.0 ? -v : v;
 }}
 /* std::acos(double): NaN outside [-1, 1] */
 VPL_SC_FN double vpl_acos_cr(double x) {{
@@ -136,7 +145,7 @@ VPL_SC_FN double vpl_acos_cr(double x) {{
         f.write(c_head + "#ifndef ORC_ATAN_H\n#define ORC_ATAN_H\n#include \"orc_sincos.h\"\n#define VPL_AT_CORE static inline\n" + body + "#endif\n")
     with open(os.path.join(ROOT, "vplines-slam_b200", "csrc", "vpl_atan.cuh"), "w") as f:
         f.write(c_head + "#pragma once\n#include \"vpl_sincos.cuh\"\n"
-                "/* one out-of-line copy per kernel image: atan, atan2 and acos all end in it */\n"
+                "/* one out-of-line copy of the table + series per kernel image: atan, atan2 and acos all end in it */\n"
                 "#define VPL_AT_CORE static __device__ __noinline__\nnamespace vpl {\n" + body + "}  // namespace vpl\n")
     print("wrote oracle/orc_atan.h and vplines-slam_b200/csrc/vpl_atan.cuh")
 
