@@ -34,6 +34,7 @@
 // whole number of degrees in exact arithmetic (see vp_cell), so its cell is decided by the last bits.
 // -fmad=false, IEEE sqrt/div, sums in the reference's order.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "vpl_atan.cuh"
 #include "vpl_common.cuh"
@@ -156,6 +157,58 @@ __global__ void __launch_bounds__(128) vp_prepare_kernel(const VplLine* __restri
 }
 
 // ---- getSphereGrids: the vote -------------------------------------------------------------------
+// One pair (i, j): the cell its intersection falls in (-1: no vote) and its weight (vp.cpp:212-247).
+__device__ __forceinline__ void vote_pair(const V3& pi, double li, double oi, const V3& pj, double lj, double oj,
+                                          const VpParams& P, int& cell, double& val) {
+  const double acc = 1.0 / 180.0 * kPi;   // angelAccuracy
+  const double tol = 60.0 / 180.0 * kPi;  // angelTolerance
+  cell = -1;
+  val = 0.0;
+  const V3 pt = cross3(pi, pj);
+  double dev = fabs(oi - oj);
+  dev = (kPi - dev < dev) ? kPi - dev : dev;
+  if (pt.z == 0 || dev > tol) return;
+  const double x = pt.x / pt.z, y = pt.y / pt.z;
+  const double X = x - P.ppx, Y = y - P.ppy, Z = P.f;
+  const double N = sqrt(X * X + Y * Y + Z * Z);
+  const double zn = Z / N;
+  bool risky = false;
+  double lat = acos(zn), lon = atan2(X, Y) + kPi;
+  int la = cell_of(lat, acc, risky), lo = cell_of(lon, acc, risky);
+  if (risky || !(lat == lat) || !(lon == lon)) {
+    lat = vpl_acos_cr(zn);
+    lon = vpl_atan2_cr(X, Y) + kPi;
+    la = (int)(lat / acc);
+    lo = (int)(lon / acc);
+  }
+  if (!(lat == lat) || !(lon == lon)) return;
+  if (la >= kLA) la = kLA - 1;
+  if (lo >= kLO) lo = kLO - 1;
+  if (la < 0 || lo < 0) return;
+  val = sqrt(li * lj) * (vpl_sin_cr(2.0 * dev) + 0.2);
+  cell = la * kLO + lo;
+}
+// 32 votes of consecutive pairs added to the grid in lane (= pair) order: lanes with the same cell form a group,
+// its lowest lane adds the members in lane order; groups of different cells proceed in parallel.
+__device__ __forceinline__ void vote_add32(double* grid, int cell, const double* vals, int lane) {
+  const unsigned valid = __ballot_sync(0xffffffffu, cell >= 0);
+  if (cell >= 0) {
+    const unsigned m = __match_any_sync(valid, cell);
+    if ((__ffs(m) - 1) == lane) {
+      double a = grid[cell];
+      unsigned t = m;
+      while (t) {
+        const int src = __ffs(t) - 1;
+        t &= t - 1;
+        a += vals[src];
+      }
+      grid[cell] = a;
+    }
+  }
+  __syncwarp();
+}
+
+// Variant A, ONE WARP PER FRAME (large batches: every warp computes and adds, nothing waits on a barrier).
 constexpr int kVoteWarps = 4;
 __global__ void __launch_bounds__(kVoteWarps * 32) vp_vote_kernel(const int* __restrict__ n_lines, int cap, VpBuffers B,
                                                                   VpParams P, int n_frames) {
@@ -168,8 +221,6 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vp_vote_kernel(const int* __r
   const double* length = B.length + (size_t)frame * cap;
   const double* orient = B.orient + (size_t)frame * cap;
   double* grid = B.grid + (size_t)frame * kCells;
-  const double acc = 1.0 / 180.0 * kPi;         // angelAccuracy
-  const double tol = 60.0 / 180.0 * kPi;        // angelTolerance
   for (int i = 0; i < n - 1; ++i) {
     const V3 pi = {para[3 * i], para[3 * i + 1], para[3 * i + 2]};
     const double li = length[i], oi = orient[i];
@@ -179,51 +230,64 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vp_vote_kernel(const int* __r
       double val = 0.0;
       if (j < n) {
         const V3 pj = {para[3 * j], para[3 * j + 1], para[3 * j + 2]};
-        const V3 pt = cross3(pi, pj);
-        double dev = fabs(oi - orient[j]);
-        dev = (kPi - dev < dev) ? kPi - dev : dev;
-        if (pt.z != 0 && !(dev > tol)) {
-          const double x = pt.x / pt.z, y = pt.y / pt.z;
-          const double X = x - P.ppx, Y = y - P.ppy, Z = P.f;
-          const double N = sqrt(X * X + Y * Y + Z * Z);
-          const double zn = Z / N;
-          bool risky = false;
-          double lat = acos(zn), lon = atan2(X, Y) + kPi;
-          int la = cell_of(lat, acc, risky), lo = cell_of(lon, acc, risky);
-          if (risky || !(lat == lat) || !(lon == lon)) {
-            lat = vpl_acos_cr(zn);
-            lon = vpl_atan2_cr(X, Y) + kPi;
-            la = (int)(lat / acc);
-            lo = (int)(lon / acc);
-          }
-          if (lat == lat && lon == lon) {
-            if (la >= kLA) la = kLA - 1;
-            if (lo >= kLO) lo = kLO - 1;
-            if (la >= 0 && lo >= 0) {
-              val = sqrt(li * length[j]) * (vpl_sin_cr(2.0 * dev) + 0.2);
-              cell = la * kLO + lo;
-            }
-          }
-        }
+        vote_pair(pi, li, oi, pj, length[j], orient[j], P, cell, val);
       }
       s_val[warp][lane] = val;
       __syncwarp();
-      const unsigned valid = __ballot_sync(0xffffffffu, cell >= 0);
-      if (cell >= 0) {
-        const unsigned m = __match_any_sync(valid, cell);
-        if ((__ffs(m) - 1) == lane) {  // lowest lane of the group adds its members in lane (= j) order
-          double a = grid[cell];
-          unsigned t = m;
-          while (t) {
-            const int src = __ffs(t) - 1;
-            t &= t - 1;
-            a += s_val[warp][src];
-          }
-          grid[cell] = a;
-        }
-      }
-      __syncwarp();
+      vote_add32(grid, cell, s_val[warp], lane);
     }
+  }
+}
+
+// Variant B, ONE CTA PER FRAME (small batches, or many lines per frame: the latency of one frame's vote is what
+// counts).  Warps 1..7 compute the votes of seven consecutive 32-pair chunks per round into shared memory; warp 0
+// adds the chunks of the previous round to the grid, in chunk order -- the only warp that touches the grid, so
+// every cell still receives its additions in (i, j) order.  Two buffers, one barrier per round.
+constexpr int kVoteCtaWarps = 8, kVoteCompute = kVoteCtaWarps - 1;
+__global__ void __launch_bounds__(kVoteCtaWarps * 32) vp_vote_cta_kernel(const int* __restrict__ n_lines, int cap,
+                                                                         VpBuffers B, VpParams P) {
+  __shared__ double s_val[2][kVoteCompute][32];
+  __shared__ int s_cell[2][kVoteCompute][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frame = blockIdx.x;
+  if (B.status[frame] != 0) return;
+  const int n = n_lines[frame];
+  const double* para = B.para + (size_t)frame * cap * 3;
+  const double* length = B.length + (size_t)frame * cap;
+  const double* orient = B.orient + (size_t)frame * cap;
+  double* grid = B.grid + (size_t)frame * kCells;
+  int total = 0;  // 32-pair chunks of the frame: row i has ceil((n - 1 - i) / 32)
+  for (int i = 0; i < n - 1; ++i) total += (n - 1 - i + 31) >> 5;
+  const int rounds = (total + kVoteCompute - 1) / kVoteCompute;
+  // cursor of this compute warp: chunk number (warp - 1) of round 0
+  int ci = 0, cj = 1;
+  auto advance = [&](int steps) {
+    for (int s_ = 0; s_ < steps && ci < n - 1; ++s_) {
+      cj += 32;
+      if (cj >= n) { ++ci; cj = ci + 1; }
+    }
+  };
+  if (warp > 0) advance(warp - 1);
+  for (int r = 0; r <= rounds; ++r) {
+    if (warp > 0) {
+      if (r < rounds) {
+        int cell = -1;
+        double val = 0.0;
+        const int j = cj + lane;
+        if (ci < n - 1 && j < n) {
+          const V3 pi = {para[3 * ci], para[3 * ci + 1], para[3 * ci + 2]};
+          const V3 pj = {para[3 * j], para[3 * j + 1], para[3 * j + 2]};
+          vote_pair(pi, length[ci], orient[ci], pj, length[j], orient[j], P, cell, val);
+        }
+        s_cell[r & 1][warp - 1][lane] = cell;
+        s_val[r & 1][warp - 1][lane] = val;
+        advance(kVoteCompute);
+      }
+    } else if (r > 0) {
+      const int b = (r - 1) & 1;
+      for (int k = 0; k < kVoteCompute; ++k) vote_add32(grid, s_cell[b][k][lane], s_val[b][k], lane);
+    }
+    __syncthreads();
   }
 }
 
@@ -529,6 +593,14 @@ void launch_vp_cloud(const VplLine* all_lines, const int* n_all, int cap, const 
 
 void launch_vp_lambda(double* lambda_sc, cudaStream_t st) { vp_lambda_kernel<<<2, 192, 0, st>>>(lambda_sc); }
 
+// 0: one warp per frame, 1: one CTA per frame.  VPL_VP_VOTE=0/1 forces one (measurement).
+int vp_vote_variant(int n_frames) {
+  static const int forced = [] { const char* e = getenv("VPL_VP_VOTE"); return e ? atoi(e) : -1; }();
+  if (forced == 0 || forced == 1) return forced;
+  (void)n_frames;
+  return 0;  // TODO(measure): switch small batches to the CTA variant once it is validated on the device
+}
+
 int vp_score_splits(int n_frames) {  // enough CTAs to fill the machine at small batches
   if (n_frames >= 1024) return 1;
   if (n_frames >= 256) return 3;
@@ -541,7 +613,10 @@ void launch_vp_prepare(const VplLine* lines, const int* n_lines, int cap, const 
   vp_prepare_kernel<<<n_frames, 128, 0, st>>>(lines, n_lines, cap, B, P, seeds);
 }
 void launch_vp_vote(const int* n_lines, int cap, const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st) {
-  vp_vote_kernel<<<(n_frames + kVoteWarps - 1) / kVoteWarps, kVoteWarps * 32, 0, st>>>(n_lines, cap, B, P, n_frames);
+  if (vp_vote_variant(n_frames) == 0)
+    vp_vote_kernel<<<(n_frames + kVoteWarps - 1) / kVoteWarps, kVoteWarps * 32, 0, st>>>(n_lines, cap, B, P, n_frames);
+  else
+    vp_vote_cta_kernel<<<n_frames, kVoteCtaWarps * 32, 0, st>>>(n_lines, cap, B, P);
   vp_smooth_kernel<<<dim3((kCells + 255) / 256, n_frames), 256, 0, st>>>(B, n_frames);
 }
 void launch_vp_score(const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st) {
