@@ -57,7 +57,10 @@ WORKLOADS = {
     # are the EDLines of the C2 / mh04 frames
     "V1": dict(name="V1_vanishing_points_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=256, frames="C2", vp=True),
     "V1r": dict(name="V1r_vanishing_points_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=256, frames="C1", vp=True),
+    # SURVEY 8d / C4's matcher alone: brute-force Hamming kNN, 2000 x 2000 256-bit codes per frame pair, k = 2
+    "M4": dict(name="M4_hamming_knn_2000x2000_k2", w=64, h=64, octaves=1, k=2, max_lines=2000, lq=2000, lt=2000, matcher=True),
 }
+M_METRIC = "brute-force Hamming kNN matching frame-pairs/sec (BinaryDescriptorMatcher::knnMatch, 2000x2000 256-bit codes, k=2)"
 VP_METRIC = "vanishing-point stage frames/sec (vanishing_point_detection::run_vanishing_point_detection) on 752x480 line sets"
 EUROC_CAM = (461.6, 363.0, 248.1)  # fx, cx, cy of config/euroc/euroc_config.yaml
 LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, LineFeatureTracker::readImage) at 752x480"
@@ -644,6 +647,118 @@ def run_vp(args, torch, dist, rank, local_rank, world):
     return 0
 
 
+def run_matcher(args, torch, dist, rank, local_rank, world):
+    """--workload M4: BinaryDescriptorMatcher::knnMatch alone on B frame pairs of 2000 x 2000 codes (the matcher of
+    BASELINE.json configs[3]); reports the POPC-pipe utilisation SURVEY 8d asks for next to the contract's roofline."""
+    vpl = importlib.import_module("vplines_slam_b200")
+    capi = vpl.capi
+    wl = WORKLOADS[args.workload]
+    Lq, Lt, K = wl["lq"], wl["lt"], wl["k"]
+    B = min(args.batch, 512)
+    rng = np.random.default_rng(args.seed + rank)
+    q = rng.integers(0, 256, (B, Lq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (B, Lt, 32), dtype=np.uint8)
+    t[:, ::7] = q[:, ::7]  # planted exact matches (distance 0) and, with them, ties between candidates
+    ctx = capi.Context(device=local_rank, max_width=wl["w"], max_height=wl["h"], max_octaves=1, max_lines=max(Lq, Lt),
+                       max_batch=B, num_slots=1, blur_first=True, profile=True)
+    nq, nt = np.full(B, Lq, np.int32), np.full(B, Lt, np.int32)
+    res = np.zeros((B, Lq, K), capi.DMATCH_DTYPE)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        ctx.match_batch_into(q, nq, t, nt, K, res)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ctx.match_batch_into(q, nq, t, nt, K, res)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    assert (res["trainIdx"][:, ::7, 0] == np.arange(0, Lq, 7)).all() and (res["distance"][:, ::7, 0] == 0).all()
+    for _ in range(max(args.warmup, 1)):
+        ctx.match_run_resident(K)
+    ctx.sync()
+    ctx.reset_stage_times()
+    l0 = ctx.kernel_launches()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ctx.match_run_resident(K)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - l0
+    stage = ctx.stage_times()
+    clocks = sampler.stop()
+    popc_peak = ctx.popc_peak()
+    if dist is not None:
+        tt = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(tt[0]), float(tt[1])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+    total = B * args.steps * world
+    value = total / (dev_ms * 1e-3)
+    e2e_value = total / (e2e_ms * 1e-3)
+    dur = stage["match"][0] / max(stage["match"][1], 1)
+    alg = (32.0 * (Lq + Lt) + 16.0 * K * Lq) * B        # codes in, DMatch out (SURVEY 8d)
+    popc = 8.0 * Lq * Lt * B                               # popc32 per launch
+    peak, peak_kind = measured_peak()
+    achieved = alg / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "hamming_knn_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "ms_per_launch": dur, "algorithmic_bytes_per_launch": alg,
+                "note": "integer-pipe (POPC) bound, not HBM: see popc",
+                "popc": {"achieved_popc32_per_s": popc / (dur * 1e-3) if dur > 0 else 0.0, "peak_popc32_per_s": popc_peak,
+                         "frac": (popc / (dur * 1e-3) / popc_peak) if dur > 0 and popc_peak > 0 else None,
+                         "popc32_per_launch": popc,
+                         "peak_source": "vpl_debug_popc_peak: micro-benchmark kernel on this device (8 independent popc chains per thread)"}}
+    line = {"metric": M_METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (xor/popc)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "pairs_per_step": B, "queries": Lq, "train": Lt, "k": K, "parallelism": f"pairs x{world}",
+                       "codes": "uniform random 256-bit codes, every 7th train code equal to its query (exact matches and ties)",
+                       "l2": "descriptor sets per step (%.0f MB) fit the 126 MB L2: the kernel is compute-bound, its inputs are re-read from "
+                             "shared-memory tiles" % (B * (Lq + Lt) * 32 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(B * (Lq + Lt) * 32 + 8 * B), "d2h_bytes_per_step": int(B * Lq * K * 16)},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import oracle as O
+            O.build()
+            threads = os.cpu_count() or 1
+            t0 = time.time(); O.hamming_knn(q[0], t[0], K); per = max(time.time() - t0, 1e-4)
+            n = int(max(threads, min(10.0 / per * threads, B)))
+            t0 = time.time()
+            with ThreadPoolExecutor(threads) as ex:  # the C call releases the GIL
+                list(ex.map(lambda i: O.hamming_knn(q[i % B], t[i % B], K), range(n)))
+            dt = time.time() - t0
+            cb = {"value": n / dt, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+                  "sample": f"{n} pairs of {Lq}x{Lt} codes in {dt:.1f}s; oracle brute force (orc_hamming_knn, 64-bit popcount), "
+                            f"{threads} threads", "single_thread_pairs_per_s": 1.0 / per}
+        line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores, nothing else."""
     rank = int(os.environ.get("RANK", "0"))
@@ -715,6 +830,8 @@ def main():
 
     if args.workload.startswith("V"):
         return run_vp(args, torch, dist, rank, local_rank, world)
+    if args.workload.startswith("M"):
+        return run_matcher(args, torch, dist, rank, local_rank, world)
     if args.workload.startswith("E"):
         return run_edlines(args, torch, dist, rank, local_rank, world)
 

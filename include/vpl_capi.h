@@ -286,6 +286,13 @@ int vpl_match_batch(VplContext* ctx, const uint8_t* q, const int32_t* nq, int ca
                     const uint8_t* t, const int32_t* nt, int cap_t, int n_pairs, int k,
                     VplDMatch* out);
 
+/* Re-runs the matcher on the descriptor sets left resident by the last vpl_match_batch (measurement). */
+int vpl_match_run_resident(VplContext* ctx, int k);
+/* POPC throughput of the device in popc32 per second, measured with a micro-benchmark kernel (8 independent
+ * popc chains per thread, 8 resident CTAs of 256 threads per SM): the denominator for the matcher's
+ * integer-pipe utilisation. */
+int vpl_debug_popc_peak(VplContext* ctx, double* popc32_per_s);
+
 /* ---- the fused path: detect + compute + match(t, t-1), one batch ----------- */
 /* Equivalent to the three calls above on n consecutive frames with everything
  * kept in HBM in between.  matches: n*cap*k entries; frame f (f>=1) is matched

@@ -80,7 +80,7 @@ EXPORTS = [
     "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
     "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
-    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud",
+    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -157,6 +157,8 @@ def load():
     L.vpl_vp_collect.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.vpl_vp_run_resident.argtypes = [vp, i32]
     L.vpl_debug_vp.argtypes = [vp, i32, vp, vp, vp]
+    L.vpl_match_run_resident.argtypes = [vp, i32]
+    L.vpl_debug_popc_peak.argtypes = [vp, vp]
     L.vpl_vp_pack_cloud.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]
     _lib = L
     return L
@@ -282,6 +284,20 @@ class Context:
         return [out[i, :nq[i]].copy() for i in range(n)]
 
     # -- fused front end ---------------------------------------------------------
+    def match_batch_into(self, q, nq, t, nt, k, out):
+        """The C call as it is: q (n, cap_q, 32) u8, nq (n,) i32, t (n, cap_t, 32), nt, out (n, cap_q, k) DMATCH_DTYPE."""
+        self._ck(self._L.vpl_match_batch(self._h, _ptr(q), _ptr(nq), q.shape[1], _ptr(t), _ptr(nt), t.shape[1], q.shape[0], k,
+                                         _ptr(out)))
+
+    def match_run_resident(self, k=1):
+        self._ck(self._L.vpl_match_run_resident(self._h, int(k)))
+
+    def popc_peak(self):
+        """Measured POPC throughput of the device, popc32 per second."""
+        v = C.c_double(0.0)
+        self._ck(self._L.vpl_debug_popc_peak(self._h, C.byref(v)))
+        return v.value
+
     def frontend_batch(self, frames, scale=2, num_octaves=1, k=1, chain=False, cap=None):
         ptrs, keep, n, w, h, stride = _img_ptrs(frames)
         cap = cap or self.max_lines

@@ -111,6 +111,7 @@ struct Slot {
   int* h_flags = nullptr;
   // state of the batch in flight
   int n = 0, w = 0, h = 0, num_octaves = 0, scale = 2, k = 0;
+  int m_pairs = 0, m_cap_q = 0, m_cap_t = 0;  // geometry of the last standalone match (vpl_match_run_resident)
   bool in_flight = false;
   int last_consumer = -1;  // slot whose match reads our last_desc
 };
@@ -1314,12 +1315,60 @@ int vpl_match_batch(VplContext* c, const uint8_t* q, const int32_t* nq, int cap_
     launch_hamming_knn(d_q, d_nq, cap_q, d_t, d_nt, cap_t, n_pairs, k, s.d_match, s.stream);
     tm.launches(1);
   }
+  s.m_pairs = n_pairs; s.m_cap_q = cap_q; s.m_cap_t = cap_t;
   const size_t ob = (size_t)n_pairs * cap_q * k * sizeof(VplDMatch);
   CK(c, cudaMemcpyAsync(s.h_match, s.d_match, ob, cudaMemcpyDeviceToHost, s.stream));
   int r = finish(c, s);
   if (r) return r;
   for (int p = 0; p < n_pairs; ++p)
     memcpy(out + (size_t)p * cap_q * k, s.h_match + (size_t)p * cap_q * k, (size_t)nq[p] * k * sizeof(VplDMatch));
+  return VPL_OK;
+}
+
+int vpl_match_run_resident(VplContext* c, int k) {
+  if (!c) return VPL_E_INVALID;
+  Slot& s = c->slots[0];
+  if (s.m_pairs <= 0) return fail(c, VPL_E_INVALID, "no descriptor sets resident: call vpl_match_batch first");
+  if (k < 1 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 1..%d", k, c->max_k);
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot 0 in flight");
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  StageTimer tm(c, s, VPL_STAGE_MATCH);
+  launch_hamming_knn(s.d_desc, s.d_counts, s.m_cap_q, reinterpret_cast<uint8_t*>(s.d_kl), s.oct[0].n_ord, s.m_cap_t, s.m_pairs, k,
+                     s.d_match, s.stream);
+  tm.launches(1);
+  return VPL_OK;
+}
+
+int vpl_debug_popc_peak(VplContext* c, double* popc32_per_s) {
+  if (!c || !popc32_per_s) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  cudaDeviceProp prop;
+  CK(c, cudaGetDeviceProperties(&prop, c->cfg.device));
+  unsigned* d = nullptr;
+  CK(c, cudaMalloc((void**)&d, 256));
+  cudaEvent_t e0, e1;
+  CK(c, cudaEventCreate(&e0));
+  CK(c, cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // first pass warms up
+    cudaEventRecord(e0, 0);
+    launch_popc_peak(d, blocks, iters, 0);
+    cudaEventRecord(e1, 0);
+    CK(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  c->launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *popc32_per_s = best;
   return VPL_OK;
 }
 

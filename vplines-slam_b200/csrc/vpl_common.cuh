@@ -250,6 +250,7 @@ void launch_klt_track(const uint8_t* pyr, const short2* deriv, const KltGeom& G,
                       int pstride, int n_pairs, cudaStream_t st);
 void launch_lm_vote(const VplLine* lines, const int* counts, int cap, const LmBuffers& B, const LmParams& P, int pstride,
                     int n_pairs, cudaStream_t st);
+void launch_popc_peak(unsigned* out, int blocks, int iters, cudaStream_t st);
 // ---- vanishing points (vp.cu) ---------------------------------------------------------------
 struct VpParams {
   double f, ppx, ppy;   // vanishing_point_detection::init: floats stored in doubles
