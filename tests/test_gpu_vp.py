@@ -187,3 +187,64 @@ def test_vp_pointcloud_packing(ctx, vpl, orc, mh04):
     # every line carries the Vector4d of line number `cam` (the reference indexes the per-line list with the camera index)
     g = ctx.vp_pack_cloud(ids, fx, fy, cx, cy, 1, 0)[0]
     assert (g["vp_x"] == np.float32(lv[0][0][0])).all()
+
+
+def _fuzz_sets(orc, rng, n_sets):
+    """Line sets with the degenerate shapes a tracker can hand over: duplicates and collinear segments (intersections
+    with z == 0, redrawn pairs), zero-length segments (NaN directions), axis-parallel bundles (no two lines intersect),
+    far-away coordinates, very few lines."""
+    sets = []
+    for s in range(n_sets):
+        n = int(rng.integers(2, 60))
+        ln = np.zeros(n, orc.LINE_DTYPE)
+        e = rng.uniform(0, 700, (n, 4)).astype(np.float32)
+        kind = s % 6
+        if kind == 1:                       # half of the segments duplicated
+            e[n // 2:] = e[:n - n // 2]
+        elif kind == 2:                     # collinear runs on a few carrier lines
+            for i in range(n):
+                a, b = rng.uniform(0, 600, 2)
+                k = i % 3
+                e[i] = (a, 50 + 100 * k + 0.25 * a, b, 50 + 100 * k + 0.25 * b)
+        elif kind == 3:                     # some zero-length segments
+            e[::4, 2:] = e[::4, :2]
+        elif kind == 4:                     # integer endpoints, many exactly parallel
+            e = np.round(e / 50) * 50
+            e[:, 3] = e[:, 1] + (e[:, 2] - e[:, 0])
+        elif kind == 5:                     # far away / tiny
+            e[: n // 3] *= 1e4
+            e[n // 3: 2 * n // 3] *= 1e-3
+        ln["endpoint"] = e
+        ln["center"] = (e[:, :2] + e[:, 2:]) / 2
+        ln["length"] = np.hypot(e[:, 2] - e[:, 0], e[:, 3] - e[:, 1])
+        sets.append(ln)
+    return sets
+
+
+def test_vp_fuzz_degenerate_line_sets(ctx, vpl, orc):
+    """120 degenerate line sets, device vs oracle (device arithmetic): status, labels, vanishing points and the whole
+    grid bit for bit -- NaNs included (a zero-length segment has no direction: its three angles are NaN, label 3)."""
+    ctx.vp_configure(*EUROC)
+    rng = np.random.default_rng(2024)
+    sets = _fuzz_sets(orc, rng, 120)
+    seeds = rng.integers(1, 2**32 - 1, len(sets), dtype=np.uint64).astype(np.uint32)
+    n_err = n_ok = 0
+    for lo in range(0, len(sets), 60):
+        chunk = sets[lo:lo + 60]
+        vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, l) for l in chunk], seeds[lo:lo + 60], frame_count0=lo)
+        for i, ln in enumerate(chunk):
+            try:
+                ev, ei, d = orc.vp_detect(ln, None, *EUROC, int(seeds[lo + i]), lo + i, math_mode=1, details=True)
+            except ValueError:              # the oracle gave up (-2: no two lines intersect)
+                assert st[i] == -2 and (idx[i] == 3).all() and (vps[i] == 0).all()
+                n_err += 1
+                continue
+            assert st[i] == (d["flags"] & 1), (lo + i, st[i], d["flags"])
+            assert np.array_equal(idx[i], ei), lo + i
+            a, b = vps[i], ev
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and a[~np.isnan(a)].tobytes() == b[~np.isnan(b)].tobytes(), lo + i
+            if i % 5 == 0:
+                g = ctx.vp_debug(i)["grid"]
+                assert np.array_equal(np.isnan(g), np.isnan(d["grid"])) and g[~np.isnan(g)].tobytes() == d["grid"][~np.isnan(g)].tobytes()
+            n_ok += 1
+    assert n_ok >= 90
