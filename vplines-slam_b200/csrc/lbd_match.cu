@@ -62,10 +62,12 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
            uint8_t* __restrict__ desc_, float* __restrict__ fdesc_) {
   __shared__ float s_row[LBD_WARPS][LSP_H][8];
   __shared__ float s_des[LBD_WARPS][72];
+  __shared__ float s_band[LBD_WARPS][8][NUM_OF_BANDS];
   const int f = blockIdx.y;
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = blockIdx.x * LBD_WARPS + wi;
-  if (li >= counts[f]) return;
+  // a frame's lines are dealt to a fixed number of warps (a grid sized by the capacity launched mostly empty CTAs)
+  const int n_lines = counts[f];
+  for (int li = blockIdx.x * LBD_WARPS + wi; li < n_lines; li += gridDim.x * LBD_WARPS) {
   const VplKeyLine kl = kl_[(size_t)f * cap + li];
   const int o = kl.octave;
   const int realWidth = A.w[o], realHeight = A.h[o];
@@ -118,7 +120,6 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
   // band sums: accumulator a = q*9 + b, rows in ascending order
   const float invN2 = (float)(1.0 / (WIDTH_OF_BAND * 2.0));
   const float invN3 = (float)(1.0 / (WIDTH_OF_BAND * 3.0));
-  __shared__ float s_band[LBD_WARPS][8][NUM_OF_BANDS];
   for (int a = lane; a < 72; a += 32) {
     int q = a / NUM_OF_BANDS, b = a - q * NUM_OF_BANDS;
     bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
@@ -188,11 +189,14 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
       if (f1[b] > f2[b]) r += (1u << b);
     desc_[((size_t)f * cap + li) * 32 + lane] = (uint8_t)r;
   }
+  __syncwarp();
+  }  // next line of this warp
 }
 
 void launch_lbd(const LbdArgs& a, const VplKeyLine* kl, const int* counts, int cap, uint8_t* desc, float* fdesc,
                 int batch, cudaStream_t st) {
-  dim3 grid((cap + LBD_WARPS - 1) / LBD_WARPS, batch);
+  constexpr int kCtasPerFrame = 48;  // 192 lines per pass; frames with more lines take further passes
+  dim3 grid(min((cap + LBD_WARPS - 1) / LBD_WARPS, kCtasPerFrame), batch);
   lbd_kernel<<<grid, LBD_WARPS * 32, 0, st>>>(a, kl, counts, cap, desc, fdesc);
 }
 
