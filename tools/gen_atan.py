@@ -86,7 +86,7 @@ VPL_AT_CORE vpl_dd vpl_atan_dd01(vpl_dd q) {{
   vpl_dd p = vpl_dd_make(tail, 0.0);
   VPL_SC_ROLLED
   for (int i = 3; i >= 0; --i)
-    p = vpl_dd_add(vpl_dd_make(vpl_at_coef[i][0], vpl_at_coef[i][1]), vpl_dd_mul(u, p));
+    p = vpl_dd_add_ord(vpl_dd_make(vpl_at_coef[i][0], vpl_at_coef[i][1]), vpl_dd_mul(u, p));
   return vpl_dd_add(vpl_dd_make(vpl_at_tab[k][0], vpl_at_tab[k][1]), vpl_dd_mul(t, p));
 }}
 /* atan2(y, x) of double-double arguments, as a double-double in (-pi, pi] */

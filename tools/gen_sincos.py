@@ -5,8 +5,8 @@ Why it exists: a rectangle's edges pass through the centres of its extreme pixel
 rect_nfa's ceil()/trunc() row limits sit within an ulp of integers and a 1-ulp change in
 dx = cos(theta), dy = sin(theta) moves pixels in or out of the rectangle.  libm and the
 CUDA math library both differ from the correctly rounded value by up to an ulp, in
-different places.  Both sides therefore use this one definition: double-double Taylor
-evaluation after a 3-term Cody-Waite reduction, built only from IEEE add/mul/fma, which
+different places.  Both sides therefore use this one definition: a 3-term Cody-Waite reduction, a second
+reduction by a 27-entry double-double table of sin/cos(m/32) and short double-double Taylor series, built only from IEEE add/mul/fma, which
 yields the correctly rounded result unless the true value lies within ~1e-22 (relative)
 of a rounding midpoint.  It agrees with glibc wherever glibc is itself correctly rounded.
 
@@ -44,6 +44,14 @@ def main():
     sin_c = [split(mp.mpf((-1) ** k) / mp.factorial(2 * k + 1)) for k in range(1, 13)]  # r^3 .. r^25
     cos_c = [split(mp.mpf((-1) ** k) / mp.factorial(2 * k)) for k in range(1, 13)]      # r^2 .. r^24
 
+    tab = []
+    for m in range(27):
+        sh, sl = split(mp.sin(mp.mpf(m) / 32))
+        ch, cl = split(mp.cos(mp.mpf(m) / 32))
+        tab.append((sh, sl, ch, cl))
+    tab_txt = ("static VPL_SC_CONST double vpl_sc_tab[27][4] = {\n" +
+               ",\n".join("  {%s, %s, %s, %s}" % tuple(float.hex(v) for v in t) for t in tab) + "};\n")
+
     def arr(name, c):
         return ("static VPL_SC_CONST double %s[%d][2] = {\n" % (name, len(c)) +
                 ",\n".join("  {%s, %s}" % (float.hex(h), float.hex(l)) for h, l in c) + "};\n")
@@ -55,7 +63,8 @@ def main():
 #define VPL_SC_P3H {float.hex(P3h)}
 #define VPL_SC_P3L {float.hex(P3l)}
 #define VPL_SC_2OPI {float.hex(two_over_pi)}
-{arr('vpl_sc_sin', sin_c)}{arr('vpl_sc_cos', cos_c)}
+{arr('vpl_sc_sin', sin_c)}{arr('vpl_sc_cos', cos_c)}/* sin(m/32), cos(m/32), m = 0..26, as double-doubles */
+{tab_txt}
 typedef struct {{ double hi, lo; }} vpl_dd;
 
 VPL_SC_FN vpl_dd vpl_dd_two_sum(double a, double b) {{
@@ -67,37 +76,69 @@ VPL_SC_FN vpl_dd vpl_dd_add(vpl_dd a, vpl_dd b) {{
 VPL_SC_FN vpl_dd vpl_dd_mul(vpl_dd a, vpl_dd b) {{
   double p = a.hi * b.hi; double e = fma(a.hi, b.hi, -p); e = e + (a.hi * b.lo + a.lo * b.hi); return vpl_dd_quick(p, e); }}
 
-/* sin and cos of theta (|theta| < 1e4), correctly rounded in practice. */
-VPL_SC_FN void vpl_sincos_cr(double theta, double* s_out, double* c_out) {{
-  double kd = rint(theta * VPL_SC_2OPI);
-  int k = (int)kd;
-  /* r = theta - k*pi/2 in double-double */
-  double t1 = theta - kd * VPL_SC_P1;              /* exact */
-  vpl_dd r = vpl_dd_two_sum(t1, -(kd * VPL_SC_P2)); /* kd*P2 exact */
-  vpl_dd p3; p3.hi = kd * VPL_SC_P3H; p3.lo = fma(kd, VPL_SC_P3H, -p3.hi) + kd * VPL_SC_P3L;
-  p3.hi = -p3.hi; p3.lo = -p3.lo;
-  r = vpl_dd_add(r, p3);
-  vpl_dd r2 = vpl_dd_mul(r, r);
-  /* |r| <= pi/4: the terms from r^18 / r^19 on are below 2^-60 of the sums, a plain double carries them */
-  double ts = vpl_sc_sin[11][0], tc = vpl_sc_cos[11][0];
-  for (int i = 10; i >= 8; --i) {{
-    ts = vpl_sc_sin[i][0] + r2.hi * ts;
-    tc = vpl_sc_cos[i][0] + r2.hi * tc;
+/* a + b for |a.hi| >= |b.hi| (a Horner coefficient and the smaller product): the exact sum of the high parts needs
+ * no branch-free two_sum; same result, three operations fewer */
+VPL_SC_FN vpl_dd vpl_dd_add_ord(vpl_dd a, vpl_dd b) {{
+  vpl_dd s = vpl_dd_quick(a.hi, b.hi); double e = s.lo + (a.lo + b.lo); return vpl_dd_quick(s.hi, e); }}
+
+/* sin r and cos r for a double-double |r| <= pi/4 (+ rounding): r = c + d, c = m/32 from a table of double-double
+ * sin c / cos c, |d| <= 1/64: sin d and cos d from three double-double Taylor steps (the terms from d^9 / d^8 on
+ * are below 2^-63 of the sums, a plain double carries them), then the angle-addition formulas. */
+VPL_SC_FN void vpl_sincos_dd(vpl_dd r, vpl_dd* s_out, vpl_dd* c_out, int want) {{
+  double md = rint(r.hi * 32.0);
+  int m = (int)md;
+  int a = m < 0 ? -m : m;
+  vpl_dd mc; mc.hi = -(md * 0.03125); mc.lo = 0.0;
+  vpl_dd d = vpl_dd_add(r, mc);
+  vpl_dd d2 = vpl_dd_mul(d, d);
+  double ts = vpl_sc_sin[6][0], tc = vpl_sc_cos[6][0];
+  VPL_SC_ROLLED
+  for (int i = 5; i >= 3; --i) {{
+    ts = vpl_sc_sin[i][0] + d2.hi * ts;
+    tc = vpl_sc_cos[i][0] + d2.hi * tc;
   }}
   vpl_dd ps, pc;
   ps.hi = ts; ps.lo = 0.0;
   pc.hi = tc; pc.lo = 0.0;
   VPL_SC_ROLLED
-  for (int i = 7; i >= 0; --i) {{
+  for (int i = 2; i >= 0; --i) {{
     vpl_dd cs; cs.hi = vpl_sc_sin[i][0]; cs.lo = vpl_sc_sin[i][1];
     vpl_dd cc; cc.hi = vpl_sc_cos[i][0]; cc.lo = vpl_sc_cos[i][1];
-    ps = vpl_dd_add(cs, vpl_dd_mul(r2, ps));
-    pc = vpl_dd_add(cc, vpl_dd_mul(r2, pc));
+    ps = vpl_dd_add_ord(cs, vpl_dd_mul(d2, ps));
+    pc = vpl_dd_add_ord(cc, vpl_dd_mul(d2, pc));
   }}
-  /* sin r = r + r*r2*ps ; cos r = 1 + r2*pc */
-  vpl_dd sr = vpl_dd_add(r, vpl_dd_mul(r, vpl_dd_mul(r2, ps)));
+  /* sin d = d + d*d2*ps ; cos d = 1 + d2*pc */
+  vpl_dd sd = vpl_dd_add(d, vpl_dd_mul(d, vpl_dd_mul(d2, ps)));
   vpl_dd one; one.hi = 1.0; one.lo = 0.0;
-  vpl_dd cr = vpl_dd_add(one, vpl_dd_mul(r2, pc));
+  vpl_dd cd = vpl_dd_add_ord(one, vpl_dd_mul(d2, pc));
+  vpl_dd S, C;
+  S.hi = vpl_sc_tab[a][0]; S.lo = vpl_sc_tab[a][1];
+  C.hi = vpl_sc_tab[a][2]; C.lo = vpl_sc_tab[a][3];
+  if (m < 0) {{ S.hi = -S.hi; S.lo = -S.lo; }}
+  if (want & 1) *s_out = vpl_dd_add(vpl_dd_mul(S, cd), vpl_dd_mul(C, sd));
+  if (want & 2) {{
+    vpl_dd t = vpl_dd_mul(S, sd); t.hi = -t.hi; t.lo = -t.lo;
+    *c_out = vpl_dd_add(vpl_dd_mul(C, cd), t);
+  }}
+}}
+
+/* theta - k pi/2 as a double-double, k = rint(theta 2/pi) */
+VPL_SC_FN vpl_dd vpl_sc_reduce(double theta, int* k_out) {{
+  double kd = rint(theta * VPL_SC_2OPI);
+  *k_out = (int)kd;
+  double t1 = theta - kd * VPL_SC_P1;              /* exact */
+  vpl_dd r = vpl_dd_two_sum(t1, -(kd * VPL_SC_P2)); /* kd*P2 exact */
+  vpl_dd p3; p3.hi = kd * VPL_SC_P3H; p3.lo = fma(kd, VPL_SC_P3H, -p3.hi) + kd * VPL_SC_P3L;
+  p3.hi = -p3.hi; p3.lo = -p3.lo;
+  return vpl_dd_add(r, p3);
+}}
+
+/* sin and cos of theta (|theta| < 1e4), correctly rounded in practice. */
+VPL_SC_FN void vpl_sincos_cr(double theta, double* s_out, double* c_out) {{
+  int k;
+  vpl_dd r = vpl_sc_reduce(theta, &k);
+  vpl_dd sr, cr;
+  vpl_sincos_dd(r, &sr, &cr, 3);
   double sv = sr.hi + sr.lo, cv = cr.hi + cr.lo;
   switch (k & 3) {{
     case 0: *s_out = sv; *c_out = cv; break;
@@ -107,42 +148,14 @@ VPL_SC_FN void vpl_sincos_cr(double theta, double* s_out, double* c_out) {{
   }}
 }}
 
-/* sin(theta) alone: the same reduction and the same polynomial evaluation as above, only the one the quadrant needs
- * (bit-identical to the sine of vpl_sincos_cr). */
+/* sin(theta) alone (bit-identical to the sine of vpl_sincos_cr): only the combination the quadrant needs */
 VPL_SC_FN double vpl_sin_cr(double theta) {{
-  double kd = rint(theta * VPL_SC_2OPI);
-  int k = (int)kd;
-  double t1 = theta - kd * VPL_SC_P1;
-  vpl_dd r = vpl_dd_two_sum(t1, -(kd * VPL_SC_P2));
-  vpl_dd p3; p3.hi = kd * VPL_SC_P3H; p3.lo = fma(kd, VPL_SC_P3H, -p3.hi) + kd * VPL_SC_P3L;
-  p3.hi = -p3.hi; p3.lo = -p3.lo;
-  r = vpl_dd_add(r, p3);
-  vpl_dd r2 = vpl_dd_mul(r, r);
+  int k;
+  vpl_dd r = vpl_sc_reduce(theta, &k);
+  vpl_dd sr, cr;
   double v;
-  if (k & 1) {{
-    double tc = vpl_sc_cos[11][0];
-    for (int i = 10; i >= 8; --i) tc = vpl_sc_cos[i][0] + r2.hi * tc;
-    vpl_dd pc; pc.hi = tc; pc.lo = 0.0;
-    VPL_SC_ROLLED
-  for (int i = 7; i >= 0; --i) {{
-      vpl_dd cc; cc.hi = vpl_sc_cos[i][0]; cc.lo = vpl_sc_cos[i][1];
-      pc = vpl_dd_add(cc, vpl_dd_mul(r2, pc));
-    }}
-    vpl_dd one; one.hi = 1.0; one.lo = 0.0;
-    vpl_dd cr = vpl_dd_add(one, vpl_dd_mul(r2, pc));
-    v = cr.hi + cr.lo;
-  }} else {{
-    double ts = vpl_sc_sin[11][0];
-    for (int i = 10; i >= 8; --i) ts = vpl_sc_sin[i][0] + r2.hi * ts;
-    vpl_dd ps; ps.hi = ts; ps.lo = 0.0;
-    VPL_SC_ROLLED
-  for (int i = 7; i >= 0; --i) {{
-      vpl_dd cs; cs.hi = vpl_sc_sin[i][0]; cs.lo = vpl_sc_sin[i][1];
-      ps = vpl_dd_add(cs, vpl_dd_mul(r2, ps));
-    }}
-    vpl_dd sr = vpl_dd_add(r, vpl_dd_mul(r, vpl_dd_mul(r2, ps)));
-    v = sr.hi + sr.lo;
-  }}
+  if (k & 1) {{ vpl_sincos_dd(r, &sr, &cr, 2); v = cr.hi + cr.lo; }}
+  else {{ vpl_sincos_dd(r, &sr, &cr, 1); v = sr.hi + sr.lo; }}
   return (k & 2) ? -v : v;
 }}
 """

@@ -95,8 +95,10 @@ __device__ __forceinline__ void normalize_pos_z(V3& v) {  // vp.cpp:150-153 / :1
 }
 
 // cell coordinate of an angle: int(angle / accuracy); `risky` when the quotient is close to an integer
+// (only used where a miss falls back to the exact quotient, so the product with the reciprocal -- within 2 ulp of
+// ang / acc -- serves)
 __device__ __forceinline__ int cell_of(double ang, double acc, bool& risky) {
-  const double q = ang / acc;
+  const double q = ang * (1.0 / acc);  // acc is a compile-time constant at every call site
   const int c = (int)q;
   const double fr = q - (double)c;
   risky |= fr < kGuard || fr > 1.0 - kGuard;
