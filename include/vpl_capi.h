@@ -255,6 +255,9 @@ int vpl_vp_run_resident(VplContext* ctx, int slot);
 /* Stage outputs of frame `frame` of the last batch on slot 0: the smoothed 90 x 360 grid, the index of
  * the winning hypothesis, the line pair of every outer iteration (2 x 105 ints).  Any may be NULL. */
 int vpl_debug_vp(VplContext* ctx, int frame, double* grid, int32_t* best_idx, int32_t* pairs);
+/* The score (sum of its three cells) of every hypothesis of that frame: 105 * 360 doubles, index = outer iteration *
+ * 360 + angle index (lineLength[] of getBestVpsHyp, vanishing_point_detection.cpp:285-318). */
+int vpl_debug_vp_scores(VplContext* ctx, int frame, double* scores);
 
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.

@@ -405,13 +405,14 @@ def vp_detect(lines, all_lines=None, f=460.0, cx=376.0, cy=240.0, seed=1, frame_
     vps = np.zeros((3, 3), np.float64); idx = np.full(len(al), -1, np.int32)
     grid = np.zeros(VP_GRID_SHAPE, np.float64); best = ctypes.c_int32(); flags = ctypes.c_int32()
     pairs = np.zeros((vp_hypothesis_count(), 2), np.int32)
+    scores = np.zeros(vp_hypothesis_count() * 360, np.float64) if details else None
     rc = L.orc_vp_detect(_p(ln), len(ln), _p(al), len(al), ctypes.c_float(f), ctypes.c_float(cx), ctypes.c_float(cy),
                          ctypes.c_uint(seed), int(frame_count), int(math_mode), _p(vps), _p(idx), _p(grid),
-                         ctypes.byref(best), _p(pairs), ctypes.byref(flags))
+                         ctypes.byref(best), _p(pairs), ctypes.byref(flags), _p(scores) if scores is not None else None)
     if rc:
         raise ValueError("orc_vp_detect -> %d" % rc)
     if details:
-        return vps, idx, dict(grid=grid, best_idx=best.value, pairs=pairs, flags=flags.value)
+        return vps, idx, dict(grid=grid, best_idx=best.value, pairs=pairs, flags=flags.value, scores=scores)
     return vps, idx
 
 

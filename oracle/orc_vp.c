@@ -126,7 +126,7 @@ static void vp_hypothesis(const M* m, V3 vp1, int j, double* out) {
 
 int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, int n_all, float f_, float cx_,
                   float cy_, unsigned seed, int frame_count, int math_mode, double* vps, int32_t* vp_idx,
-                  double* grid_out, int32_t* best_idx, int32_t* pairs_out, int32_t* flags) {
+                  double* grid_out, int32_t* best_idx, int32_t* pairs_out, int32_t* flags, double* scores_out) {
   const M mm = {math_mode}; const M* m = &mm;
   const double f = f_, ppx = cx_, ppy = cy_; /* init(): float arguments stored in doubles (:29-34) */
   if (flags) *flags = 0;
@@ -233,6 +233,7 @@ int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, i
       if (la < 0 || la >= gridLA || lo < 0 || lo >= gridLO) continue; /* z < 0 (only with f < 0): out of the grid */
       lineLength += gridNew[la * gridLO + lo];
     }
+    if (scores_out) scores_out[i] = lineLength;
     if (i == 0) memcpy(best, hyp, sizeof(best));
     if (lineLength > maxLength) { maxLength = lineLength; bestIdx = i; memcpy(best, hyp, sizeof(best)); }
   }
@@ -311,7 +312,7 @@ int64_t orc_vp_sequence(const OrcLine* lines, const int32_t* counts, int n_frame
     int32_t fl;
     if (counts[i] < 3) continue;
     if (orc_vp_detect(lines + (size_t)i * cap, counts[i], lines + (size_t)i * cap, counts[i], f, cx, cy, seeds[i],
-                      frame_count0 + i, math_mode, vps + 9 * (size_t)i, vp_idx + (size_t)i * cap, 0, 0, 0, &fl) == 0)
+                      frame_count0 + i, math_mode, vps + 9 * (size_t)i, vp_idx + (size_t)i * cap, 0, 0, 0, &fl, 0) == 0)
       for (int k = 0; k < counts[i]; ++k) labelled += vp_idx[(size_t)i * cap + k] != 3;
   }
   return labelled;

@@ -174,10 +174,11 @@ int orc_vp_hypothesis_count(void); /* "it" of getVPHypVia2Lines (105) */
  * after init(f, cx, cy, .).  seed: what time(NULL) returned; frame_count: calls made before this one.
  * math_mode 0: libm, 1: the shared deterministic functions.  vps: 9 doubles (3 unit vectors);
  * vp_idx: n_all labels 0..2, 3 = none.  Optional: grid (90 x 360 smoothed cells), best_idx
- * (hypothesis index), pairs (2 per outer iteration), flags.  Returns 0, -1 (fewer than 2 lines), -2. */
+ * (hypothesis index), pairs (2 per outer iteration), flags, scores (the sum of every
+ * hypothesis, 360 per outer iteration).  Returns 0, -1 (fewer than 2 lines), -2. */
 int orc_vp_detect(const OrcLine* lines, int n_lines, const OrcLine* all_lines, int n_all, float f, float cx,
                   float cy, unsigned seed, int frame_count, int math_mode, double* vps, int32_t* vp_idx,
-                  double* grid, int32_t* best_idx, int32_t* pairs, int32_t* flags);
+                  double* grid, int32_t* best_idx, int32_t* pairs, int32_t* flags, double* scores);
 int64_t orc_vp_sequence(const OrcLine* lines, const int32_t* counts, int n_frames, int cap, float f, float cx, float cy,
                         const uint32_t* seeds, int frame_count0, int math_mode, double* vps, int32_t* vp_idx);
 /* line_feature_tracker_node.cpp:64-153: cloud = 3n point floats then 7 channels of n floats (see orc_vp.c) */

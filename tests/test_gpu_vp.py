@@ -38,7 +38,7 @@ def as_capi(vpl, lines):
     return np.ascontiguousarray(lines).view(vpl.capi.LINE_DTYPE).reshape(-1)
 
 
-def check_frame(orc, dev_vps, dev_idx, dev_status, dbg, ln, al, f, cx, cy, seed, fc):
+def check_frame(orc, dev_vps, dev_idx, dev_status, dbg, ln, al, f, cx, cy, seed, fc, scores=None):
     vps, idx, d = orc.vp_detect(ln, al, f, cx, cy, seed, fc, math_mode=1, details=True)
     assert dev_status == (d["flags"] & 1)
     assert np.array_equal(dev_idx, idx)
@@ -47,6 +47,8 @@ def check_frame(orc, dev_vps, dev_idx, dev_status, dbg, ln, al, f, cx, cy, seed,
         assert dbg["best_idx"] == d["best_idx"]
         assert np.array_equal(dbg["pairs"], d["pairs"])
         assert dbg["grid"].tobytes() == d["grid"].tobytes()
+    if scores is not None:  # every one of the 37 800 hypotheses read the same three cells
+        assert scores.tobytes() == d["scores"].tobytes()
     return d
 
 
@@ -63,7 +65,7 @@ def test_vp_reference_golden(ctx, vpl, orc, gold, name):
     assert np.array_equal(idx[0], gold[name + "_vp_idx"])
     assert np.abs(vps[0] - gold[name + "_vps"]).max() <= 1e-15
     # the oracle in the device's arithmetic: bit-exact, stage by stage
-    check_frame(orc, vps[0], idx[0], st[0], ctx.vp_debug(0), ln, al, f, cx, cy, seed, fc)
+    check_frame(orc, vps[0], idx[0], st[0], ctx.vp_debug(0), ln, al, f, cx, cy, seed, fc, scores=ctx.vp_scores(0))
 
 
 def test_vp_batch_vs_oracle_many_seeds(ctx, vpl, orc, mh04):
@@ -78,7 +80,8 @@ def test_vp_batch_vs_oracle_many_seeds(ctx, vpl, orc, mh04):
     vps, idx, st = ctx.vp_detect_batch([as_capi(vpl, l) for l in sets], seeds, frame_count0=0)
     n_flag = 0
     for i, (ln, seed) in enumerate(zip(sets, seeds)):
-        d = check_frame(orc, vps[i], idx[i], st[i], ctx.vp_debug(i) if i % 7 == 0 else None, ln, ln, *EUROC, seed, i)
+        d = check_frame(orc, vps[i], idx[i], st[i], ctx.vp_debug(i) if i % 7 == 0 else None, ln, ln, *EUROC, seed, i,
+                        scores=ctx.vp_scores(i) if i % 3 == 0 else None)
         n_flag += d["flags"]
     assert 0 < n_flag < len(sets)          # both kinds of frame were exercised
     assert (np.concatenate(idx) != 3).sum() > 1000

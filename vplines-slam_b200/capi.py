@@ -80,7 +80,7 @@ EXPORTS = [
     "vpl_edlines_collect", "vpl_edlines_run_resident", "vpl_debug_edge_chains",
     "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
-    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak",
+    "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -157,6 +157,7 @@ def load():
     L.vpl_vp_collect.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.vpl_vp_run_resident.argtypes = [vp, i32]
     L.vpl_debug_vp.argtypes = [vp, i32, vp, vp, vp]
+    L.vpl_debug_vp_scores.argtypes = [vp, i32, vp]
     L.vpl_match_run_resident.argtypes = [vp, i32]
     L.vpl_debug_popc_peak.argtypes = [vp, vp]
     L.vpl_vp_pack_cloud.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]
@@ -525,6 +526,12 @@ class Context:
         grid = np.zeros((90, 360), np.float64); best = C.c_int32(0); pairs = np.zeros((n_it, 2), np.int32)
         self._ck(self._L.vpl_debug_vp(self._h, frame, _ptr(grid), C.byref(best), _ptr(pairs)))
         return dict(grid=grid, best_idx=best.value, pairs=pairs)
+
+    def vp_scores(self, frame, n_it=105):
+        """Score of every hypothesis of `frame` of the last batch on slot 0 -> float64 (n_it * 360,)."""
+        sc = np.zeros(n_it * 360, np.float64)
+        self._ck(self._L.vpl_debug_vp_scores(self._h, frame, _ptr(sc)))
+        return sc
 
     # -- raw stages ----------------------------------------------------------------
     def lsd_raw(self, img, cap=1 << 15):

@@ -1835,6 +1835,26 @@ int vpl_debug_vp(VplContext* c, int frame, double* grid, int32_t* best_idx, int3
   return VPL_OK;
 }
 
+int vpl_debug_vp_scores(VplContext* c, int frame, double* scores) {
+  if (!c || !scores) return VPL_E_INVALID;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  Slot& s = c->slots[0];
+  if (frame < 0 || frame >= s.vp_n) return fail(c, VPL_E_INVALID, "frame %d outside the last batch", frame);
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaStreamSynchronize(s.stream));
+  const size_t n = (size_t)c->vpp.it * 360;
+  double* d = nullptr;
+  CK(c, cudaMalloc((void**)&d, n * sizeof(double)));
+  CK(c, cudaMemsetAsync(d, 0, n * sizeof(double), s.stream));
+  launch_vp_scores_debug(s.vp, c->vpp, s.vp_n, frame, d, s.stream);
+  c->launches += 1;
+  cudaError_t e = cudaMemcpyAsync(scores, d, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(c, VPL_E_CUDA, "vpl_debug_vp_scores: %s", cudaGetErrorString(e));
+  return VPL_OK;
+}
+
 // ---- fused: EDline on every frame + Matching(frame f-1, frame f) ---------------------------------
 int vpl_linefront_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
                          int smoothed) {

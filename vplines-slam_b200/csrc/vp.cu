@@ -325,7 +325,7 @@ __device__ __noinline__ double acos_cr_ni(double x) { return vpl_acos_cr(x); }
 __device__ __noinline__ void sincos_cr_ni(double a, double* s, double* c) { vpl_sincos_cr(a, s, c); }
 
 // vp2 / vp3 of hypothesis (vp1, j) (vp.cpp:139-160), in the shared arithmetic.
-__device__ __forceinline__ void make_hypothesis(const V3& vp1, double sl, double cl, V3& vp2, V3& vp3) {
+__device__ __forceinline__ double make_hypothesis(const V3& vp1, double sl, double cl, V3& vp2, V3& vp3) {
   const double k1 = vp1.x * sl + vp1.y * cl;
   const double k2 = vp1.z;
   const double phi = atan_cr_ni(-k2 / k1);
@@ -335,17 +335,20 @@ __device__ __forceinline__ void make_hypothesis(const V3& vp1, double sl, double
   normalize_pos_z(vp2);
   vp3 = cross3(vp1, vp2);
   normalize_pos_z(vp3);
+  return phi;
 }
 // Sphere cell of a unit vector (vp.cpp:291-316); false = contributes nothing.  EXACT_LON: the longitude goes
 // through the shared atan2 unconditionally -- vp2 = (sin phi sin lambda, sin phi cos lambda, cos phi) has
 // longitude lambda_j (+ pi) = a whole number of degrees in exact arithmetic, i.e. it always sits ON a cell
 // boundary and the cell the reference picks is decided by the last bits of x, y and atan2.  Otherwise the CUDA
 // library function is used and the shared one only within 1e-9 of a boundary.
+// lat_hint >= 0: a value known to be within 1e-12 of acos(v.z) (vp2.z = cos(phi) up to the rounding of the
+// normalisation, so its latitude is |phi| unless phi is tiny) -- it replaces the library acos on the guarded path.
 template <bool EXACT_LON>
-__device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell) {
+__device__ __forceinline__ bool vp_cell(const V3& v, double one, int& cell, double lat_hint = -1.0) {
   if (v.z == 0.0) return false;
   bool risky = v.z > 1.0 - 1e-12;
-  double lat = acos(v.z);
+  double lat = lat_hint >= 0.0 ? lat_hint : acos(v.z);
   int la = cell_of(lat, one, risky);
   if (risky || !(lat == lat)) {
     lat = acos_cr_ni(v.z);
@@ -377,8 +380,9 @@ constexpr int kScoreThreads = 256;
 // grid (splits, frames): split s scores the outer iterations [s it / splits, (s + 1) it / splits) -- a contiguous
 // range of 360 (i1 - i0) hypotheses dealt to the threads round robin (360 is not a multiple of the CTA, a loop
 // per outer iteration would leave half the warps waiting)
-__global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, VpParams P, int splits) {
-  const int frame = blockIdx.y, split = blockIdx.x;
+__global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, VpParams P, int splits, int frame0,
+                                                                 double* __restrict__ scores) {
+  const int frame = frame0 + blockIdx.y, split = blockIdx.x;
   if (B.status[frame] != 0) return;
   const double* g = B.grid_new + (size_t)frame * kCells;
   const double* vp1s = B.vp1 + (size_t)frame * P.it * 3;
@@ -399,12 +403,13 @@ __global__ void __launch_bounds__(kScoreThreads) vp_score_kernel(VpBuffers B, Vp
     const V3 vp1 = {vp1s[3 * i], vp1s[3 * i + 1], vp1s[3 * i + 2]};
     const double sl = B.lambda_sc[2 * j], cl = B.lambda_sc[2 * j + 1];
     V3 vp2, vp3;
-    make_hypothesis(vp1, sl, cl, vp2, vp3);
+    const double phi = fabs(make_hypothesis(vp1, sl, cl, vp2, vp3));
     double len = 0.0;  // lineLength[i] += sphereGrid[..][..] for the three vanishing points, in this order
     int c = s_cell1[i - i0];
     if (c >= 0) len += g[c];
-    if (vp_cell<true>(vp2, one, c)) len += g[c];
+    if (vp_cell<true>(vp2, one, c, phi > 1e-3 ? phi : -1.0)) len += g[c];
     if (vp_cell<false>(vp3, one, c)) len += g[c];
+    if (scores) scores[idx] = len;  // parity hook (vpl_debug_vp_scores): nullptr on the product path
     if (len > best) { best = len; best_idx = idx; }  // a thread's indices ascend: strict > keeps the lowest
   }
   // block arg-max, lowest index on ties
@@ -626,7 +631,12 @@ void launch_vp_vote(const int* n_lines, int cap, const VpBuffers& B, const VpPar
 }
 void launch_vp_score(const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st) {
   const int splits = vp_score_splits(n_frames);
-  vp_score_kernel<<<dim3(splits, n_frames), kScoreThreads, 0, st>>>(B, P, splits);
+  vp_score_kernel<<<dim3(splits, n_frames), kScoreThreads, 0, st>>>(B, P, splits, 0, nullptr);
+}
+// every hypothesis' score of one frame of the last batch (parity hook); leaves the per-CTA bests as they were
+void launch_vp_scores_debug(const VpBuffers& B, const VpParams& P, int n_frames, int frame, double* scores, cudaStream_t st) {
+  const int splits = vp_score_splits(n_frames);
+  vp_score_kernel<<<dim3(splits, 1), kScoreThreads, 0, st>>>(B, P, splits, frame, scores);
 }
 void launch_vp_classify(const VplLine* all_lines, const int* n_all, int cap, int frame_count0, const VpBuffers& B,
                         const VpParams& P, int n_frames, double* vps, int* vp_idx, double* line_vps, cudaStream_t st) {

@@ -286,6 +286,7 @@ void launch_vp_prepare(const VplLine* lines, const int* n_lines, int cap, const 
 void launch_vp_vote(const int* n_lines, int cap, const VpBuffers& B, const VpParams& P, int n_frames,
                     cudaStream_t st);                                                           // 2
 void launch_vp_score(const VpBuffers& B, const VpParams& P, int n_frames, cudaStream_t st);      // 1
+void launch_vp_scores_debug(const VpBuffers& B, const VpParams& P, int n_frames, int frame, double* scores, cudaStream_t st);
 void launch_vp_classify(const VplLine* all_lines, const int* n_all, int cap, int frame_count0, const VpBuffers& B,
                         const VpParams& P, int n_frames, double* vps, int* vp_idx, double* line_vps,
                         cudaStream_t st);                                                       // 1
