@@ -52,6 +52,12 @@ WORKLOADS = {
     # (readImage: EDline on every frame + LineMatching::Matching(prev, cur), line_feature_tracker.cpp:87, :115)
     "E2": dict(name="E2_edlines_kltmatch_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2", match=True),
     "E2r": dict(name="E2r_edlines_kltmatch_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1", match=True),
+    # SURVEY 8f-1..4 chained: readImage's whole line pipeline on raw frames in one pass over the device
+    # (remap + CLAHE -> EDline -> Matching(prev, cur) -> vanishing points on each frame's lines), vpl_readimage_*
+    "R1": dict(name="R1_readimage_line_pipeline_mh04_real_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C1",
+               match=True, full=True),
+    "R1s": dict(name="R1s_readimage_line_pipeline_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2",
+                match=True, full=True),
     # the vanishing-point stage readImage runs on every frame's lines after matching
     # (vanishing_point_detection::run_vanishing_point_detection, line_feature_tracker.cpp:233-262); the line sets
     # are the EDLines of the C2 / mh04 frames
@@ -63,6 +69,8 @@ WORKLOADS = {
 M_METRIC = "brute-force Hamming kNN matching frame-pairs/sec (BinaryDescriptorMatcher::knnMatch, 2000x2000 256-bit codes, k=2)"
 VP_METRIC = "vanishing-point stage frames/sec (vanishing_point_detection::run_vanishing_point_detection) on 752x480 line sets"
 EUROC_CAM = (461.6, 363.0, 248.1)  # fx, cx, cy of config/euroc/euroc_config.yaml
+RI_METRIC = ("reference line pipeline frames/sec (LineFeatureTracker::readImage: remap + CLAHE, EDLines, KLT line matching, "
+             "vanishing points) at 752x480")
 LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, LineFeatureTracker::readImage) at 752x480"
 ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
@@ -229,6 +237,7 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     W, H = wl["w"], wl["h"]
     B, S, cap = args.batch, args.slots, (args.max_lines or wl["max_lines"])
     match = bool(wl.get("match"))
+    full = bool(wl.get("full"))  # R1: pre-processing in front, vanishing points behind (vpl_readimage_*)
     unique = make_frames(args.unique, args.seed, args.workload)
     # E2: every step submits its B frames plus the last frame of the previous step in front (one-frame
     # overlap), so that each consecutive pair of the sequence is matched exactly once
@@ -240,6 +249,13 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     ctx.edlines_configure(param)
     if match:
         ctx.linematch_configure(capi.LineMatchParam())
+    if full:
+        ctx.vp_configure(*EUROC_CAM)
+        ctx.set_preprocess(*euroc_maps(W, H), clahe_clip=3.0, clahe_tiles=8)
+        seeds = (1700000000 + np.arange(NB)).astype(np.uint32)
+        vps = [np.zeros((NB, 3, 3), np.float64) for _ in range(S)]
+        vp_idx = [np.zeros((NB, cap), np.int32) for _ in range(S)]
+        vp_st = [np.zeros(NB, np.int32) for _ in range(S)]
     ctx.host_register(host_buf)
     lines = [np.zeros((NB, cap), capi.LINE_DTYPE) for _ in range(S)]
     counts = [np.zeros(NB, np.int32) for _ in range(S)]
@@ -248,20 +264,27 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
     matched = [0]
 
     def submit(s, frames):
-        if match:
+        if full:
+            ctx.readimage_submit(s, frames, seeds[:len(frames)], smoothed=True, frame_count0=1)
+        elif match:
             ctx.linefront_submit(s, frames, smoothed=True)
         else:
             ctx.edlines_submit(s, frames, smoothed=True)
 
     def collect(s):
-        if match:
+        if full:
+            ctx.readimage_collect_into(s, lines[s], counts[s], cap, p2c[s], vps[s], vp_idx[s], vp_st[s])
+            matched[0] = int((p2c[s][1:] >= 0).sum())
+        elif match:
             ctx.linefront_collect_into(s, lines[s], counts[s], cap, p2c[s])
             matched[0] = int((p2c[s][1:] >= 0).sum())
         else:
             ctx.edlines_collect_into(s, lines[s], counts[s], cap, status[s])
 
     def resident(s):
-        if match:
+        if full:
+            ctx.readimage_run_resident(s)
+        elif match:
             ctx.linefront_run_resident(s)
         else:
             ctx.edlines_run_resident(s)
@@ -350,6 +373,14 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
         launches_of.update({"lm_pyramid": 8, "lm_track": 6, "lm_vote": 1})
         kernels_of.update({"lm_pyramid": "klt_level0/pyrdown/scharr kernels", "lm_track": "klt_track_kernel x4 levels (+ anchors, offsets)",
                            "lm_vote": "lm_vote_kernel"})
+    if full:
+        cm = counts[0][NB - B:].astype(np.float64)
+        Lm, Np, G = float(cm.mean()), float((cm * (cm - 1) / 2).mean()), 90 * 360 * 8.0
+        alg.update({"preproc": 13.0 * P,  # remap: maps 8P + r P + w P; CLAHE: r 2P + w P
+                    "vp_prep": 56.0 * Lm + G, "vp_vote": 16.0 * Np + 2 * G, "vp_score": 105 * 360 * 3 * 8.0, "vp_classify": 52.0 * Lm})
+        launches_of.update({"preproc": 3, "vp_prep": 1, "vp_vote": 2, "vp_score": 1, "vp_classify": 1})
+        kernels_of.update({"preproc": "remap_kernel + clahe_lut_kernel + clahe_apply_kernel", "vp_prep": "vp_prepare_kernel",
+                           "vp_vote": "vp_vote_kernel + vp_smooth_kernel", "vp_score": "vp_score_kernel", "vp_classify": "vp_classify_kernel"})
     ed = {k: stage[k] for k in alg}
     dom = max(ed, key=lambda k: ed[k][0])
     peak, peak_kind = measured_peak()
@@ -370,7 +401,7 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
                 "algorithmic_bytes_per_launch": alg[dom] * B,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items() if v[1]},
                 "stage_share": {k: round(v[0] / tot, 4) for k, v in stage.items() if v[1]}}
-    line = {"metric": LF_METRIC if match else ED_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": RI_METRIC if full else LF_METRIC if match else ED_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/s16/f32/f64" if match else "u8/s16/f64", "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
             "config": {"workload": wl["name"], "frames_per_step": B, "width": W, "height": H, "slots": S, "max_lines": cap,
@@ -381,18 +412,94 @@ def run_edlines(args, torch, dist, rank, local_rank, world):
                        "matched_lines_per_frame": round(matched[0] / B, 1) if match else None,
                        "anchors_pair0": anchors if match else None,
                        "overlap": "each step submits B+1 frames (the previous step's last frame first)" if match else None,
+                       "pipeline": ("remap (EuRoC cam0 maps) + CLAHE(3.0, 8x8) -> EDLines -> Matching(f-1, f) -> vanishing points on each "
+                                    "frame's own lines (lines == all_lines), one pass over the device; labelled lines/frame %.1f"
+                                    % ((vp_idx[0][NB - B:] != 3)[np.arange(cap)[None, :] < counts[0][NB - B:, None]].sum() / B)) if full else None,
                        "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (B * W * H / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": NB * W * H, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
     if rank == 0:
-        line["cpu_baseline"] = (ed_cpu_baseline(unique, name=wl["name"], match=match)
-                                if (world == 1 and not args.no_cpu_baseline) else None)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = (readimage_cpu_baseline(unique, name=wl["name"]) if full
+                                    else ed_cpu_baseline(unique, name=wl["name"], match=match))
+        else:
+            line["cpu_baseline"] = None
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def euroc_maps(w=752, h=480):
+    """Radial-tangential undistortion maps of EuRoC cam0 (config/euroc/euroc_config.yaml), what initUndistortRectifyMap gives."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    k1, k2, p1, p2 = -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05
+    x = (xx - cx) / fx; y = (yy - cy) / fy; r2 = x * x + y * y; rad = 1 + k1 * r2 + k2 * r2 * r2
+    mapx = ((x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)) * fx + cx).astype(np.float32)
+    mapy = ((y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y) * fy + cy).astype(np.float32)
+    return mapx, mapy
+
+
+def readimage_cpu_baseline(unique, seconds=8.0, name="R1"):
+    """The same four stages on the host cores, each with the reference's own code where it exists: cv2.remap + cv2 CLAHE (what
+    readImage calls; the oracle's bit-identical port if cv2 is missing), the reference's EDLines + line matching
+    (oracle/_ref/libref_linefront.so, threads), the reference's vanishing-point stage (oracle/_ref/libref_vp.so, processes).
+    The stages run one after the other over the same n frames; value = n / the sum of their times."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.build()
+    threads = os.cpu_count() or 1
+    use_lf = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_linefront.so"))
+    use_vp = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_vp.so"))
+    mapx, mapy = euroc_maps()
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        clahe_of = lambda: cv2.createCLAHE(3.0, (8, 8))
+        pre_one = lambda f: clahe_of().apply(cv2.remap(f, mapx, mapy, cv2.INTER_LINEAR))
+        pre_kind = "cv2.remap + cv2.createCLAHE(3.0, 8x8)"
+    except Exception:
+        pre_one = lambda f: O.clahe(O.remap_linear(f, mapx, mapy), 3.0, 8)
+        pre_kind = "oracle port of remap + CLAHE"
+    t = time.time()
+    pre_u = [pre_one(f) for f in unique[:4]]
+    O.linefront_sequence(np.ascontiguousarray(pre_u), threads=1, use_ref=use_lf)
+    per_frame = max((time.time() - t) / 4, 1e-3) * 1.3
+    n = int(max(threads * 4, min(seconds / per_frame * threads, 8192)))
+    frames = tile_frames(unique, n)
+    t0 = time.time()
+    with ThreadPoolExecutor(threads) as ex:
+        pre = np.ascontiguousarray(list(ex.map(pre_one, frames)))
+    t_pre = time.time() - t0
+    t0 = time.time()
+    matched = O.linefront_sequence(pre, threads=threads, use_ref=use_lf)
+    t_lf = time.time() - t0
+    # line sets of the distinct pre-processed frames (the detector's output is not returned by the timing entry point)
+    sets = [O.edline_detect(f) for f in pre[:len(unique)]]
+    cap = max(len(x) for x in sets) + 1
+    u_lines = np.zeros((len(sets), cap), O.LINE_DTYPE); u_counts = np.array([len(x) for x in sets], np.int32)
+    seeds = np.zeros(len(sets), np.uint32)
+    for i, x in enumerate(sets):
+        u_lines[i, :len(x)] = x
+        for k in range(64):  # a seed on which the reference's code does not read lx[] out of range
+            sd = 1700000000 + 1009 * k + i
+            if len(x) > 2 and O.vp_detect(x, None, *EUROC_CAM, sd, 1, math_mode=0, details=True)[2]["flags"] == 0:
+                seeds[i] = sd
+                break
+    keep = seeds != 0
+    u_lines, u_counts, seeds = u_lines[keep], u_counts[keep], seeds[keep]
+    reps = (n + len(u_counts) - 1) // len(u_counts)
+    _, t_vp = vp_cpu_run(np.ascontiguousarray(np.concatenate([u_lines] * reps)[:n]), np.ascontiguousarray(np.concatenate([u_counts] * reps)[:n]),
+                         np.ascontiguousarray(np.concatenate([seeds] * reps)[:n]), threads, use_vp)
+    tot = t_pre + t_lf + t_vp
+    return {"value": n / tot, "unit": "frames/s", "cores": threads, "kind": "reference" if (use_lf and use_vp) else "port",
+            "sample": f"{n} frames of {name}: {pre_kind} {t_pre:.1f}s ({threads} threads) + the reference's own EDLines + line matching "
+                      f"{t_lf:.1f}s ({threads} threads, {matched} matched lines) + the reference's own vanishing-point stage {t_vp:.1f}s "
+                      f"({threads} processes), one stage after the other",
+            "stage_seconds": {"preprocess": t_pre, "edlines_matching": t_lf, "vanishing_points": t_vp}}
 
 
 def _vp_chunk(job):
@@ -766,6 +873,19 @@ def run_reference(args):
         return 0
     if args.workload.startswith("V"):
         return run_reference_vp(args)
+    if args.workload.startswith("R"):
+        wl = WORKLOADS[args.workload]
+        unique = make_frames(min(args.unique, 32), args.seed, args.workload)
+        cb = None
+        for _ in range(max(args.steps, 1)):  # every step is one bounded sample of the four stages
+            cb = readimage_cpu_baseline(unique, seconds=5.0, name=wl["name"])
+        line = {"impl": "reference", "metric": RI_METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/s16/f32/f64", "data": "synthetic" if wl["frames"] == "C2" else "reference frames",
+                "config": {"workload": wl["name"], "note": cb["sample"]}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
     if args.workload.startswith("E"):
         return run_reference_edlines(args)
     unique = make_frames(min(args.unique, 32), args.seed)
@@ -832,7 +952,7 @@ def main():
         return run_vp(args, torch, dist, rank, local_rank, world)
     if args.workload.startswith("M"):
         return run_matcher(args, torch, dist, rank, local_rank, world)
-    if args.workload.startswith("E"):
+    if args.workload.startswith("E") or args.workload.startswith("R"):
         return run_edlines(args, torch, dist, rank, local_rank, world)
 
     vpl = importlib.import_module("vplines_slam_b200")

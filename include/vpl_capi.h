@@ -259,6 +259,21 @@ int vpl_debug_vp(VplContext* ctx, int frame, double* grid, int32_t* best_idx, in
  * 360 + angle index (lineLength[] of getBestVpsHyp, vanishing_point_detection.cpp:285-318). */
 int vpl_debug_vp_scores(VplContext* ctx, int frame, double* scores);
 
+/* ---- LineFeatureTracker::readImage's line pipeline, fused, for n consecutive frames in one pass over the device
+ *      (feature_tracker/src/line_feature_tracker.cpp:56-288): remap + CLAHE (:62-68, when vpl_set_preprocess
+ *      configured them) -> EDline (:87) -> Matching(frame f-1, frame f) (:115) -> run_vanishing_point_detection on
+ *      each frame's own detected lines (lines == all_lines, what :243 passes on a frame whose lines are all new; the
+ *      tracker's bookkeeping of tracked / new lines between :120 and :230 is host logic and stays with the caller).
+ *      The lines never leave the device between the stages.  Needs vpl_edlines_configure, vpl_linematch_configure
+ *      and vpl_vp_configure.  seeds / frame_count0 as vpl_vp_detect_batch; the other arguments and outputs as
+ *      vpl_linefront_* and vpl_vp_collect (vp_idx: n * cap labels, one per detected line). -------------------- */
+int vpl_readimage_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                         int smoothed, const uint32_t* seeds, int frame_count0);
+int vpl_readimage_collect(VplContext* ctx, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur,
+                          double* vps, int32_t* vp_idx, int32_t* vp_status);
+/* Re-runs the whole pipeline on the frames resident on the slot (from the raw frames when pre-processing is on). */
+int vpl_readimage_run_resident(VplContext* ctx, int slot);
+
 /* ---- LSDDetector::detect (replaces edline_detect, linefeature_tracker.h:74) -- */
 /* imgs: n host pointers to CV_8UC1 images of w x h with row pitch `stride` bytes.
  * keylines: n * cap entries, frame f at keylines + f*cap; counts[f] = number found

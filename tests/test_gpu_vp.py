@@ -251,3 +251,37 @@ def test_vp_fuzz_degenerate_line_sets(ctx, vpl, orc):
                 assert np.array_equal(np.isnan(g), np.isnan(d["grid"])) and g[~np.isnan(g)].tobytes() == d["grid"][~np.isnan(g)].tobytes()
             n_ok += 1
     assert n_ok >= 90
+
+
+def test_readimage_fused_pipeline(vpl, orc, mh04):
+    """vpl_readimage_*: remap + CLAHE -> EDLines -> Matching(f-1, f) -> vanishing points on each frame's own lines, one
+    pass over the device, against the oracle chain stage by stage (bit-exact), with and without pre-processing; the
+    resident re-run reproduces the submitted run."""
+    from test_oracle_preproc import euroc_maps
+    mapx, mapy = euroc_maps()
+    frames = mh04[3:8]
+    seeds = np.arange(77, 77 + len(frames), dtype=np.uint32)
+    p = orc.EDLineParam()
+    with vpl.Context(max_width=752, max_height=480, max_lines=512, max_batch=8, num_slots=2, lsd_path=False) as c:
+        c.edlines_configure(vpl.capi.EDLineParam())
+        c.linematch_configure(vpl.capi.LineMatchParam())
+        c.vp_configure(*EUROC)
+        for pre in (False, True):
+            if pre:
+                c.set_preprocess(mapx, mapy, clahe_clip=3.0, clahe_tiles=8)
+                src = [orc.clahe(orc.remap_linear(f, mapx, mapy), 3.0, 8) for f in frames]
+            else:
+                src = list(frames)
+            lines, p2c, vps, idx, st = c.readimage_batch(frames, seeds, smoothed=True, frame_count0=0)
+            el = [orc.edline_detect(f, p, True) for f in src]
+            for f in range(len(frames)):
+                assert lines[f].tobytes() == el[f].tobytes(), (pre, f)
+                if f:
+                    assert np.array_equal(p2c[f], orc.line_matching(src[f - 1], src[f], el[f - 1], el[f])), (pre, f)
+                ev, ei, d = orc.vp_detect(el[f], None, *EUROC, int(seeds[f]), f, math_mode=1, details=True)
+                assert vps[f].tobytes() == ev.tobytes() and np.array_equal(idx[f], ei) and st[f] == (d["flags"] & 1), (pre, f)
+            # resident re-run (from the raw frames when pre-processing is on), then the same outputs again
+            c.readimage_run_resident(0)
+            c.sync()
+            v2, i2, s2 = c.vp_detect_batch([as_capi(vpl, l) for l in el], seeds, frame_count0=0)
+            assert v2.tobytes() == vps.tobytes() and all(np.array_equal(a, b) for a, b in zip(i2, idx))

@@ -81,6 +81,7 @@ EXPORTS = [
     "vpl_linematch_default_param", "vpl_linematch_configure", "vpl_linematch_batch", "vpl_debug_linematch_points",
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
+    "vpl_readimage_submit", "vpl_readimage_collect", "vpl_readimage_run_resident",
     "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
 ]
 
@@ -158,6 +159,9 @@ def load():
     L.vpl_vp_run_resident.argtypes = [vp, i32]
     L.vpl_debug_vp.argtypes = [vp, i32, vp, vp, vp]
     L.vpl_debug_vp_scores.argtypes = [vp, i32, vp]
+    L.vpl_readimage_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32, vp, i32]
+    L.vpl_readimage_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.vpl_readimage_run_resident.argtypes = [vp, i32]
     L.vpl_match_run_resident.argtypes = [vp, i32]
     L.vpl_debug_popc_peak.argtypes = [vp, vp]
     L.vpl_vp_pack_cloud.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]
@@ -526,6 +530,33 @@ class Context:
         grid = np.zeros((90, 360), np.float64); best = C.c_int32(0); pairs = np.zeros((n_it, 2), np.int32)
         self._ck(self._L.vpl_debug_vp(self._h, frame, _ptr(grid), C.byref(best), _ptr(pairs)))
         return dict(grid=grid, best_idx=best.value, pairs=pairs)
+
+    # -- fused: readImage's line pipeline (pre-processing, EDLines, matching, vanishing points) --------------
+    def readimage_submit(self, slot, frames, seeds, smoothed=True, frame_count0=0):
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        assert len(seeds) == n
+        self._ck(self._L.vpl_readimage_submit(self._h, slot, ptrs, n, w, h, stride, int(bool(smoothed)), _ptr(seeds),
+                                              int(frame_count0)))
+        return n
+
+    def readimage_collect_into(self, slot, lines, counts, cap, prev_to_cur, vps, vp_idx, vp_status=None):
+        self._ck(self._L.vpl_readimage_collect(self._h, slot, _ptr(lines), _ptr(counts), cap, _ptr(prev_to_cur), _ptr(vps),
+                                               _ptr(vp_idx), _ptr(vp_status)))
+
+    def readimage_run_resident(self, slot):
+        self._ck(self._L.vpl_readimage_run_resident(self._h, slot))
+
+    def readimage_batch(self, frames, seeds, smoothed=True, frame_count0=0, cap=None):
+        """-> (lines per frame, prev_to_cur per frame, vps (n,3,3), labels per frame, status (n,))."""
+        n = self.readimage_submit(0, frames, seeds, smoothed, frame_count0)
+        cap = cap or self.max_lines
+        lines = np.zeros((n, cap), LINE_DTYPE); counts = np.zeros(n, np.int32); p2c = np.full((n, cap), -1, np.int32)
+        vps = np.zeros((n, 3, 3), np.float64); idx = np.full((n, cap), -1, np.int32); st = np.zeros(n, np.int32)
+        self.readimage_collect_into(0, lines, counts, cap, p2c, vps, idx, st)
+        return ([lines[f, :counts[f]].copy() for f in range(n)],
+                [p2c[f, :counts[f - 1]].copy() if f else p2c[0, :0].copy() for f in range(n)],
+                vps, [idx[f, :counts[f]].copy() for f in range(n)], st)
 
     def vp_scores(self, frame, n_it=105):
         """Score of every hypothesis of `frame` of the last batch on slot 0 -> float64 (n_it * 360,)."""

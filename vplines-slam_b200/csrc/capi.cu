@@ -46,6 +46,7 @@ struct Slot {
   bool ev_used[VPL_NUM_STAGES];
   uint8_t* d_img = nullptr;
   uint8_t* d_pre = nullptr;   // remap output (pre-processing scratch)
+  uint8_t* d_raw = nullptr;   // raw frames as uploaded, kept when pre-processing is on (resident re-runs of the fused path)
   uint8_t* d_lut = nullptr;   // CLAHE tile LUTs, B x 256 tiles max x 256
   OctBuf oct[kMaxOctaves];
   VplKeyLine* d_kl = nullptr;
@@ -502,6 +503,24 @@ bool in_registered_range(const VplContext* c, const uint8_t* p, size_t bytes) {
   return false;
 }
 
+// remap + CLAHE of n frames at `src` into d_img (readImage, line_feature_tracker.cpp:62-68)
+int run_preprocess(VplContext* c, Slot& s, const uint8_t* src, int n, int w, int h) {
+  StageTimer t(c, s, VPL_STAGE_PREPROC);
+  const uint8_t* cur = src;
+  if (c->pre_remap) {
+    launch_remap(src, s.d_pre, c->d_mapx, c->d_mapy, c->d_wtab, w, h, n, s.stream);
+    t.launches(1);
+    cur = s.d_pre;
+  }
+  if (c->pre_clip > 0.0) {
+    launch_clahe(cur, s.d_img, s.d_lut, w, h, c->pre_clip, c->pre_tiles, n, s.stream);  // in place when cur == d_img
+    t.launches(2);
+  } else if (cur != s.d_img) {
+    CK(c, cudaMemcpyAsync(s.d_img, cur, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
+  }
+  return VPL_OK;
+}
+
 int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
   if (stride < (size_t)w) return fail(c, VPL_E_INVALID, "stride %zu < width %d", stride, w);
   for (int f = 0; f < n; ++f)
@@ -518,19 +537,9 @@ int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int
   if (c->pre_remap || c->pre_clip > 0.0) {
     if (w != c->pre_w || h != c->pre_h)
       return fail(c, VPL_E_INVALID, "pre-processing was configured for %dx%d images, got %dx%d", c->pre_w, c->pre_h, w, h);
-    StageTimer t(c, s, VPL_STAGE_PREPROC);
-    const uint8_t* cur = s.d_img;
-    if (c->pre_remap) {
-      launch_remap(s.d_img, s.d_pre, c->d_mapx, c->d_mapy, c->d_wtab, w, h, n, s.stream);
-      t.launches(1);
-      cur = s.d_pre;
-    }
-    if (c->pre_clip > 0.0) {
-      launch_clahe(cur, s.d_img, s.d_lut, w, h, c->pre_clip, c->pre_tiles, n, s.stream);  // in place when cur == d_img
-      t.launches(2);
-    } else {
-      CK(c, cudaMemcpyAsync(s.d_img, s.d_pre, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
-    }
+    if (s.d_raw)  // keep the raw frames: the fused path can be re-run on them
+      CK(c, cudaMemcpyAsync(s.d_raw, s.d_img, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
+    return run_preprocess(c, s, s.d_img, n, w, h);
   }
   return VPL_OK;
 }
@@ -737,30 +746,34 @@ void vp_free(Slot& s) {
 }
 
 // the stage on the n frames whose lines sit in d_vp_lines / d_vp_all
-void run_vp(VplContext* c, Slot& s) {
-  const int B = c->cfg.max_batch, cap = c->cfg.max_lines;
-  const VplLine* all = s.vp_same ? s.d_vp_lines : s.d_vp_all;
-  const int* n_all = s.vp_same ? s.d_vp_n : s.d_vp_n + B;
+void run_vp_on(VplContext* c, Slot& s, const VplLine* lines, const int* n_lines, const VplLine* all, const int* n_all,
+               int n_frames, int frame_count0) {
+  const int cap = c->cfg.max_lines;
   {
     StageTimer t(c, s, VPL_STAGE_VP_PREP);
-    launch_vp_prepare(s.d_vp_lines, s.d_vp_n, cap, s.d_vp_seeds, s.vp, c->vpp, s.vp_n, s.stream);
+    launch_vp_prepare(lines, n_lines, cap, s.d_vp_seeds, s.vp, c->vpp, n_frames, s.stream);
     t.launches(1);
   }
   {
     StageTimer t(c, s, VPL_STAGE_VP_VOTE);
-    launch_vp_vote(s.d_vp_n, cap, s.vp, c->vpp, s.vp_n, s.stream);
+    launch_vp_vote(n_lines, cap, s.vp, c->vpp, n_frames, s.stream);
     t.launches(2);
   }
   {
     StageTimer t(c, s, VPL_STAGE_VP_SCORE);
-    launch_vp_score(s.vp, c->vpp, s.vp_n, s.stream);
+    launch_vp_score(s.vp, c->vpp, n_frames, s.stream);
     t.launches(1);
   }
   {
     StageTimer t(c, s, VPL_STAGE_VP_CLASSIFY);
-    launch_vp_classify(all, n_all, cap, s.vp_fc0, s.vp, c->vpp, s.vp_n, s.d_vps, s.d_vp_idx, s.d_line_vps, s.stream);
+    launch_vp_classify(all, n_all, cap, frame_count0, s.vp, c->vpp, n_frames, s.d_vps, s.d_vp_idx, s.d_line_vps, s.stream);
     t.launches(1);
   }
+}
+void run_vp(VplContext* c, Slot& s) {
+  const int B = c->cfg.max_batch;
+  run_vp_on(c, s, s.d_vp_lines, s.d_vp_n, s.vp_same ? s.d_vp_lines : s.d_vp_all, s.vp_same ? s.d_vp_n : s.d_vp_n + B, s.vp_n,
+            s.vp_fc0);
 }
 
 int lm_check(VplContext* c) {
@@ -806,7 +819,7 @@ void vpl_destroy(VplContext* c) {
   cudaFree(c->d_lgam);
   cudaFree(c->d_vp_lambda);
   for (Slot& s : c->slots) {
-    cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut);
+    cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
       cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.ord);
@@ -1853,6 +1866,102 @@ int vpl_debug_vp_scores(VplContext* c, int frame, double* scores) {
   cudaFree(d);
   if (e != cudaSuccess) return fail(c, VPL_E_CUDA, "vpl_debug_vp_scores: %s", cudaGetErrorString(e));
   return VPL_OK;
+}
+
+// ---- fused: readImage's line pipeline for n consecutive frames ------------------------------------
+// (remap + CLAHE) -> EDline -> Matching(f-1, f) -> run_vanishing_point_detection on each frame's own lines
+static int ri_enqueue(VplContext* c, Slot& s) {
+  run_edlines(c, s);
+  run_linematch(c, s, s.d_counts, s.n, s.n - 1, 1);
+  run_vp_on(c, s, s.d_lines, s.d_counts, s.d_lines, s.d_counts, s.n, s.vp_fc0);
+  return VPL_OK;
+}
+
+int vpl_readimage_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                         int smoothed, const uint32_t* seeds, int frame_count0) {
+  int r = lm_check(c);
+  if (r) return r;
+  r = ed_check(c, n, w, h, smoothed);
+  if (r) return r;
+  if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (n == 0 || !seeds) return fail(c, VPL_E_INVALID, "empty batch or no seeds");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  if ((c->pre_remap || c->pre_clip > 0.0) && !s.d_raw)
+    CK(c, dmalloc(&s.d_raw, (size_t)c->cfg.max_batch * c->cfg.max_width * c->cfg.max_height));
+  s.n = n; s.w = w; s.h = h; s.num_octaves = 1; s.scale = 1; s.k = 0; s.ed_smoothed = smoothed ? 1 : 0;
+  s.vp_n = n; s.vp_fc0 = frame_count0; s.vp_same = true;
+  memcpy(s.h_vp_seeds, seeds, (size_t)n * sizeof(uint32_t));
+  CK(c, cudaMemcpyAsync(s.d_vp_seeds, s.h_vp_seeds, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+  r = upload(c, s, imgs, n, w, h, stride);
+  if (r) return r;
+  ri_enqueue(c, s);
+  ed_enqueue_download(c, s);
+  {
+    StageTimer t(c, s, VPL_STAGE_D2H);
+    const int B = c->cfg.max_batch, mcap = c->cfg.max_lines;
+    if (n > 1) {
+      CK(c, cudaMemcpyAsync(s.h_r2c, s.lm.r2c, (size_t)(n - 1) * mcap * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      s.last_d2h_bytes += (int64_t)(n - 1) * mcap * sizeof(int);
+    }
+    CK(c, cudaMemcpyAsync(s.h_vps, s.d_vps, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaMemcpyAsync(s.h_vp_idx, s.d_vp_idx, (size_t)n * mcap * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaMemcpyAsync(s.h_vp_status, s.vp.status, (size_t)2 * B * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    s.last_d2h_bytes += (int64_t)n * (72 + (int64_t)mcap * 4) + 2 * B * 4;
+  }
+  CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(c, cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  s.ed_batch = true;
+  s.lf_batch = true;
+  s.vp_batch = true;
+  return VPL_OK;
+}
+
+int vpl_readimage_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur, double* vps,
+                          int32_t* vp_idx, int32_t* vp_status) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight || !s.lf_batch || !s.vp_batch) return fail(c, VPL_E_INVALID, "slot %d has no readImage batch in flight", slot);
+  if (!vps || !vp_idx) return fail(c, VPL_E_INVALID, "null output");
+  const int n = s.n, mcap = c->cfg.max_lines, B = c->cfg.max_batch;
+  s.vp_batch = false;
+  int r = vpl_linefront_collect(c, slot, lines, counts, cap, prev_to_cur);
+  if (r) return r;
+  memcpy(vps, s.h_vps, (size_t)n * 9 * sizeof(double));
+  for (int i = 0; i < n; ++i) {
+    memcpy(vp_idx + (size_t)i * cap, s.h_vp_idx + (size_t)i * mcap, (size_t)std::min(counts[i], cap) * sizeof(int));
+    if (vp_status) vp_status[i] = s.h_vp_status[i] != 0 ? s.h_vp_status[i] : (s.h_vp_status[B + i] & 1);
+  }
+  return VPL_OK;
+}
+
+int vpl_readimage_run_resident(VplContext* c, int slot) {
+  int r = lm_check(c);
+  if (r) return r;
+  if (!c->ed_ready || !c->vp_ready) return fail(c, VPL_E_INVALID, "configure EDLines, line matching and the vanishing points first");
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (s.n <= 0 || s.vp_n != s.n) return fail(c, VPL_E_INVALID, "slot %d holds no readImage batch", slot);
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.profile) {
+    bool any = false;
+    for (int i = 0; i < VPL_NUM_STAGES; ++i) any |= s.ev_used[i];
+    if (any) { cudaStreamSynchronize(s.stream); harvest_times(c, s); }
+  }
+  if ((c->pre_remap || c->pre_clip > 0.0) && s.d_raw) {
+    r = run_preprocess(c, s, s.d_raw, s.n, s.w, s.h);
+    if (r) return r;
+  }
+  return ri_enqueue(c, s);
 }
 
 // ---- fused: EDline on every frame + Matching(frame f-1, frame f) ---------------------------------
