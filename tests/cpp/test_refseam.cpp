@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../vplines-slam_b200/compat/line_matching_b200.hpp"
+#include "../../vplines-slam_b200/compat/vplines_batch.hpp"
 
 using vplines::ref::EDLineDetector;
 using vplines::ref::EDLineParam;
@@ -90,6 +91,39 @@ int main(int argc, char** argv) {
       for (int v : local_vp_ids) di = (di ^ (unsigned long)v) * 1099511628211ul;
       std::printf("REFSEAM vp frame=%d n=%zu vps_digest=%lu ids_digest=%lu status=%d\n", frame, local_vp_ids.size(), dv, di,
                   vpdetect.last_status());
+    }
+    // C++ batch driver of the fused readImage pipeline: 5 frames in batches of 3 (one-frame overlap), whole run vs two
+    // shards (one-frame halo): same lines, matches, vanishing points and labels
+    {
+      std::vector<cv::Mat> seq(5);
+      std::vector<const uint8_t*> ptrs;
+      for (int i = 0; i < 5; ++i) { make_image(seq[(size_t)i], 320, 240, 2 * i); ptrs.push_back(seq[(size_t)i].data); }
+      const uint32_t seeds[5] = {900, 901, 902, 903, 904};
+      VplEDLineParam ed = {5, 1.0f, 30, 5, 2, 20, 1.8};
+      VplLineMatchParam lm;
+      vpl_linematch_default_param(&lm);
+      auto run = [&](int world, unsigned long& dg, long& nlines, long& nmatch, long& nlab) {
+        dg = 1469598103934665603ul; nlines = nmatch = nlab = 0;
+        for (int r = 0; r < world; ++r) {
+          int64_t s0, e0; int halo;
+          vplines::shard_range(5, r, world, s0, e0, halo);
+          vplines::BatchReadImage be(0, 320, 240, 512, 3, 2, ed, lm, 230.0f, 160.0f, 120.0f);
+          be.run(ptrs.data(), 320, seeds, s0, e0, halo, true, [&](int64_t f, const vplines::LineFrameResult& fr) {
+            nlines += (long)fr.lines.size();
+            auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) dg = (dg ^ b[i]) * 1099511628211ul; };
+            mix(&f, sizeof(f));
+            for (const VplLine& l : fr.lines) mix(&l, 52);
+            for (int v : fr.prev_to_cur) { mix(&v, 4); nmatch += v >= 0; }
+            mix(fr.vps, 72);
+            for (int v : fr.vp_idx) { mix(&v, 4); nlab += v != 3; }
+          });
+        }
+      };
+      unsigned long d1, d2; long a1, b1, c1, a2, b2, c2;
+      run(1, d1, a1, b1, c1);
+      run(2, d2, a2, b2, c2);
+      std::printf("REFSEAM readimage lines=%ld matched=%ld labelled=%ld digest=%lu sharded_equal=%d\n", a1, b1, c1, d1,
+                  (int)(d1 == d2 && a1 == a2 && b1 == b2 && c1 == c2));
     }
   } catch (const std::exception& e) {
     std::printf("REFSEAM error: %s\n", e.what());

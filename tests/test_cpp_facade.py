@@ -118,3 +118,11 @@ def test_reference_named_facade_matches_oracle(vpl, orc, tmp_path):
         vps, idx, d = orc.vp_detect(ln, None, 230.0, 160.0, 120.0, 1700000123, frame, math_mode=1, details=True)
         assert int(mv.group(1)) == len(ln) and int(mv.group(2)) == fnv(vps.view(np.uint8).reshape(-1))
         assert int(mv.group(3)) == fnv(idx) and int(mv.group(4)) == (d["flags"] & 1)
+    # the C++ batch driver of the fused readImage pipeline: whole run == two shards == the oracle chain
+    mr = re.search(r"readimage lines=(\d+) matched=(\d+) labelled=(\d+) digest=(\d+) sharded_equal=(\d)", r.stdout)
+    assert mr and mr.group(5) == "1", r.stdout
+    seq = [make_image(320, 240, 2 * i) for i in range(5)]
+    ls = [orc.edline_detect(f, p, True) for f in seq]
+    nmatch = sum(int((orc.line_matching(seq[i - 1], seq[i], ls[i - 1], ls[i]) >= 0).sum()) for i in range(1, 5))
+    nlab = sum(int((orc.vp_detect(ls[i], None, 230.0, 160.0, 120.0, 900 + i, i, math_mode=1)[1] != 3).sum()) for i in range(5))
+    assert int(mr.group(1)) == sum(len(x) for x in ls) and int(mr.group(2)) == nmatch and int(mr.group(3)) == nlab

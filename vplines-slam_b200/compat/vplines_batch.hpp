@@ -91,4 +91,92 @@ class BatchFrontEnd {
   std::vector<int32_t> counts_;
 };
 
+// ---- readImage's whole line pipeline over a frame sequence (vpl_readimage_*) ---------------------------------
+// What LineFeatureTracker::readImage does per frame (feature_tracker/src/line_feature_tracker.cpp:56-288), for a
+// sequence: remap + CLAHE (when set_preprocess was called), EDline, Matching(previous frame, frame), vanishing
+// points on the frame's own lines.  Batches, and shards of different ranks, overlap by one frame so that every
+// consecutive pair is matched exactly once; the vanishing points of the overlap frame are computed twice and
+// delivered once.  seeds[f]: what time(NULL) returned for frame f (the reference seeds rand() with it).
+struct LineFrameResult {
+  std::vector<VplLine> lines;
+  std::vector<int32_t> prev_to_cur;  // one entry per line of the PREVIOUS frame (-1: unmatched); empty for frame 0
+  double vps[9];                     // three unit vectors
+  std::vector<int32_t> vp_idx;       // one label per line: 0..2, 3 = none
+  int32_t vp_status;                 // see vpl_vp_detect_batch
+};
+
+class BatchReadImage {
+ public:
+  BatchReadImage(int device, int width, int height, int max_lines, int max_batch, int num_slots, const VplEDLineParam& ed,
+                 const VplLineMatchParam& lm, float f, float cx, float cy)
+      : w_(width), h_(height), cap_(max_lines), batch_(max_batch), slots_(num_slots) {
+    if (max_batch < 2) throw std::runtime_error("vplines_b200: a batch must hold the overlap frame and one new frame");
+    VplConfig c;
+    vpl_default_config(&c);
+    c.device = device; c.max_width = width; c.max_height = height; c.max_octaves = 1;
+    c.max_lines = max_lines; c.max_batch = max_batch; c.num_slots = num_slots; c.lsd_path = 0;
+    if (vpl_create(&c, &ctx_) != VPL_OK) throw std::runtime_error(std::string("vplines_b200: ") + vpl_last_error(nullptr));
+    check(vpl_edlines_configure(ctx_, &ed));
+    check(vpl_linematch_configure(ctx_, &lm));
+    check(vpl_vp_configure(ctx_, f, cx, cy));
+    lines_.resize((size_t)max_batch * max_lines);
+    p2c_.resize((size_t)max_batch * max_lines);
+    idx_.resize((size_t)max_batch * max_lines);
+    counts_.resize((size_t)max_batch);
+    status_.resize((size_t)max_batch);
+    vps_.resize((size_t)max_batch * 9);
+  }
+  ~BatchReadImage() { if (ctx_) vpl_destroy(ctx_); }
+  BatchReadImage(const BatchReadImage&) = delete;
+  BatchReadImage& operator=(const BatchReadImage&) = delete;
+  VplContext* context() { return ctx_; }
+  // undistortion maps (w x h floats each, or both null) and CLAHE clip limit (<= 0: off), readImage :62-68
+  void set_preprocess(const float* mapx, const float* mapy, double clahe_clip, int clahe_tiles = 8) {
+    check(vpl_set_preprocess(ctx_, mapx, mapy, w_, h_, clahe_clip, clahe_tiles));
+  }
+
+  // Processes frames [start - halo, end); calls sink(frame_index, result) for frames [start, end) in order.
+  void run(const uint8_t* const* frames, size_t stride, const uint32_t* seeds, int64_t start, int64_t end, int halo,
+           bool smoothed, const std::function<void(int64_t, const LineFrameResult&)>& sink) {
+    struct Pending { int slot; int64_t first; int n; bool overlap; };
+    std::vector<Pending> pending;
+    const int64_t lo = start - halo;
+    auto collect = [&](const Pending& p) {
+      check(vpl_readimage_collect(ctx_, p.slot, lines_.data(), counts_.data(), cap_, p2c_.data(), vps_.data(), idx_.data(),
+                                  status_.data()));
+      for (int i = p.overlap ? 1 : 0; i < p.n; ++i) {
+        LineFrameResult r;
+        const int c = counts_[(size_t)i];
+        r.lines.assign(lines_.begin() + (size_t)i * cap_, lines_.begin() + (size_t)i * cap_ + c);
+        if (i > 0) r.prev_to_cur.assign(p2c_.begin() + (size_t)i * cap_, p2c_.begin() + (size_t)i * cap_ + counts_[(size_t)i - 1]);
+        std::copy(vps_.begin() + (size_t)i * 9, vps_.begin() + (size_t)i * 9 + 9, r.vps);
+        r.vp_idx.assign(idx_.begin() + (size_t)i * cap_, idx_.begin() + (size_t)i * cap_ + c);
+        r.vp_status = status_[(size_t)i];
+        sink(p.first + i, r);
+      }
+    };
+    int slot = 0;
+    for (int64_t f = start; f < end;) {
+      const bool overlap = f > lo;  // a frame to match against precedes f: the batch starts on it
+      const int64_t first = overlap ? f - 1 : f;
+      const int n = (int)std::min<int64_t>(batch_, end - first);
+      if ((int)pending.size() == slots_) { collect(pending.front()); pending.erase(pending.begin()); }
+      // frame_count0 = index of the batch's first frame: only frame 0 of the whole sequence is a first call
+      check(vpl_readimage_submit(ctx_, slot, frames + first, n, w_, h_, stride, smoothed ? 1 : 0, seeds + first, (int)first));
+      pending.push_back({slot, first, n, overlap});
+      slot = (slot + 1) % slots_;
+      f = first + n;
+    }
+    for (const Pending& p : pending) collect(p);
+  }
+
+ private:
+  void check(int r) { if (r != VPL_OK) throw std::runtime_error(std::string("vplines_b200: ") + vpl_last_error(ctx_)); }
+  VplContext* ctx_ = nullptr;
+  int w_, h_, cap_, batch_, slots_;
+  std::vector<VplLine> lines_;
+  std::vector<int32_t> p2c_, idx_, counts_, status_;
+  std::vector<double> vps_;
+};
+
 }  // namespace vplines
