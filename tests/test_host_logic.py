@@ -114,6 +114,59 @@ class OracleVpContext:
                 status[i] = st
 
 
+class OraclePipelineContext(OracleLineContext):
+    """Quacks like capi.Context's readimage_submit / readimage_collect_into: the oracle's EDLines + matching, then the
+    oracle's vanishing-point stage (device arithmetic) on each frame's own lines."""
+    CAM = (230.0, 80.0, 60.0)
+
+    def readimage_submit(self, slot, frames, seeds, smoothed=True, frame_count0=0):
+        self.linefront_submit(slot, frames, smoothed)
+        lines, p2c = self.pending[slot]
+        vp = []
+        for i, ln in enumerate(lines):
+            if len(ln) < 2:
+                vp.append((np.zeros((3, 3)), np.full(len(ln), 3, np.int32), -1))
+            else:
+                v, idx, d = self.orc.vp_detect(ln, None, *self.CAM, int(seeds[i]), frame_count0 + i, math_mode=1, details=True)
+                vp.append((v, idx, d["flags"] & 1))
+        self.pending[slot] = (lines, p2c, vp)
+        self.submitted[-1] = (len(frames), frame_count0)
+
+    def readimage_collect_into(self, slot, lines, counts, cap, p2c, vps, vp_idx, vp_status=None):
+        ls, ms, vp = self.pending[slot]
+        self.pending[slot] = (ls, ms)
+        self.linefront_collect_into(slot, lines, counts, cap, p2c)
+        for i, (v, idx, st) in enumerate(vp):
+            vps[i] = v
+            vp_idx[i, :len(idx)] = idx
+            if vp_status is not None:
+                vp_status[i] = st
+
+
+def test_line_pipeline_driver_batches_and_shards(vpl, orc, synth):
+    frames = synth.sequence(8, w=192, h=128, seed=6, n_quads=6, n_strokes=10)
+    seeds = np.arange(300, 308, dtype=np.uint32)
+    ctx = OraclePipelineContext(orc, vpl.capi, max_batch=3, num_slots=2)
+    lines, p2c, vps, idx, st = vpl.LinePipeline(ctx).run(frames, seeds)
+    # 8 frames in batches of 3 with a one-frame overlap; frame_count0 = index of the batch's first frame
+    assert ctx.submitted == [(3, 0), (3, 2), (3, 4), (2, 6)] and len(lines) == 8
+    el, em = _line_front_expected(orc, frames, ctx.param)
+    for f in range(8):
+        assert lines[f].tobytes() == el[f].tobytes() and np.array_equal(p2c[f], em[f])
+        if len(el[f]) >= 2:
+            ev, ei = orc.vp_detect(el[f], None, *OraclePipelineContext.CAM, int(seeds[f]), f, math_mode=1)
+            assert vps[f].tobytes() == ev.tobytes() and np.array_equal(idx[f], ei), f
+    for world in (2, 3):
+        got = [[], [], [], []]
+        for r in range(world):
+            s, e, halo = vpl.shard_range(len(frames), r, world)
+            a, b, v, i, _ = vpl.LinePipeline(OraclePipelineContext(orc, vpl.capi, max_batch=4)).run(frames, seeds, s, e, halo)
+            got[0] += a; got[1] += b; got[2] += list(v); got[3] += i
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(got[0], lines))
+        assert all(np.array_equal(x, y) for x, y in zip(got[1], p2c))
+        assert np.array(got[2]).tobytes() == vps.tobytes() and all(np.array_equal(x, y) for x, y in zip(got[3], idx))
+
+
 def _vp_inputs(orc, synth, n=7):
     frames = synth.sequence(n, w=160, h=120, seed=33, n_quads=6, n_strokes=10)
     sets = [orc.edline_detect(f, orc.EDLineParam(minLineLen=12), True) for f in frames]
@@ -244,6 +297,10 @@ def _gloo_worker(rank, world, port, q):
     # ... and the vanishing-point stage on the shard's own line sets (no halo)
     sets = [O.edline_detect(f, O.EDLineParam(minLineLen=15), True) for f in frames]
     _, vidx, _ = vpl.VanishingPoints(OracleVpContext(O, vpl.capi, max_batch=2)).run(sets, np.arange(70, 70 + len(frames)), s, e)
+    # ... and the fused pipeline driver over the same shard: same lines, matches and labels as the separate drivers
+    pl = vpl.LinePipeline(OraclePipelineContext(O, vpl.capi, max_batch=3)).run(frames, np.arange(70, 70 + len(frames)), s, e, halo)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(pl[0], ll)) and all(np.array_equal(a, b) for a, b in zip(pl[1], pp))
+    assert all(np.array_equal(a, b) for a, b in zip(pl[3], vidx))
     # no data-path collective: the host only gathers results (here: per-frame line counts and match sums)
     mine = torch.tensor([[len(k), int(m["trainIdx"].astype(np.int64).sum()) + 1000 * len(l) + 7 * int((p >= 0).sum())
                           + 100000 * int((v * np.arange(1, len(v) + 1)).sum())]

@@ -10,4 +10,4 @@ from . import capi  # noqa: F401
 from .capi import Context, VplError  # noqa: F401
 from .line_descriptor import (BinaryDescriptor, BinaryDescriptorMatcher, DMatch, KeyLine,  # noqa: F401
                               LSDDetector)
-from .driver import FrontEnd, LineFrontEnd, VanishingPoints, shard_range  # noqa: F401
+from .driver import FrontEnd, LineFrontEnd, LinePipeline, VanishingPoints, shard_range  # noqa: F401

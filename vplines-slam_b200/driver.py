@@ -163,3 +163,58 @@ class VanishingPoints:
         while pending:
             collect(*pending.pop(0))
         return (np.array(out_vps).reshape(-1, 3, 3), out_idx, np.array(out_st, np.int32))
+
+
+class LinePipeline:
+    """readImage's whole line pipeline over a frame sequence through Context.readimage_submit /
+    readimage_collect_into (remap + CLAHE when configured, EDline, Matching(previous frame, frame), vanishing
+    points on the frame's own lines; line_feature_tracker.cpp:56-288).  Batches, and shards of different
+    ranks, overlap by one frame so that every consecutive pair is matched exactly once; the overlap frame's
+    vanishing points are computed twice and delivered once.  frame_count0 of a batch is the index of its first
+    frame: only frame 0 of the whole sequence is the object's first call."""
+
+    def __init__(self, ctx, smoothed=True):
+        self.ctx = ctx
+        self.smoothed = smoothed
+
+    def run(self, frames, seeds, start=0, end=None, halo=0):
+        """Frames [start, end) (plus `halo` frames in front, only there to be matched against).  Returns
+        (lines per frame, prev_to_cur per frame, vps (n,3,3), labels per frame, status (n,))."""
+        ctx = self.ctx
+        end = len(frames) if end is None else end
+        lo = start - halo
+        B, S, cap = ctx.max_batch, ctx.num_slots, ctx.max_lines
+        assert B >= 2, "a batch must hold the overlap frame and at least one new frame"
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        bufs = [dict(lines=np.zeros((B, cap), capi.LINE_DTYPE), counts=np.zeros(B, np.int32), p2c=np.zeros((B, cap), np.int32),
+                     vps=np.zeros((B, 3, 3), np.float64), idx=np.zeros((B, cap), np.int32), st=np.zeros(B, np.int32))
+                for _ in range(S)]
+        out_lines, out_p2c, out_vps, out_idx, out_st = [], [], [], [], []
+        pending = []  # (slot, first_frame, n, first_is_overlap)
+
+        def collect(slot, f0, n, overlap):
+            b = bufs[slot]
+            ctx.readimage_collect_into(slot, b["lines"], b["counts"], cap, b["p2c"], b["vps"], b["idx"], b["st"])
+            for i in range(1 if overlap else 0, n):
+                c = b["counts"][i]
+                out_lines.append(b["lines"][i, :c].copy())
+                out_p2c.append(b["p2c"][i, :b["counts"][i - 1]].copy() if i else b["p2c"][0, :0].copy())
+                out_vps.append(b["vps"][i].copy())
+                out_idx.append(b["idx"][i, :c].copy())
+                out_st.append(int(b["st"][i]))
+
+        slot = 0
+        f = start
+        while f < end:
+            overlap = f > lo
+            first = f - 1 if overlap else f
+            n = min(B, end - first)
+            if len(pending) == S:
+                collect(*pending.pop(0))
+            ctx.readimage_submit(slot, frames[first:first + n], seeds[first:first + n], smoothed=self.smoothed, frame_count0=first)
+            pending.append((slot, first, n, overlap))
+            slot = (slot + 1) % S
+            f = first + n
+        while pending:
+            collect(*pending.pop(0))
+        return out_lines, out_p2c, np.array(out_vps).reshape(-1, 3, 3), out_idx, np.array(out_st, np.int32)
