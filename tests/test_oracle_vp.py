@@ -137,3 +137,32 @@ def test_cr_atan_family_against_mpmath(orc):
     assert L.orc_atan2_cr(1.0, 0.0) == np.pi / 2 and L.orc_atan2_cr(0.0, 0.0) == 0.0
     assert L.orc_atan_cr(float("inf")) == np.pi / 2 and L.orc_atan_cr(float("-inf")) == -np.pi / 2
     assert L.orc_acos_cr(1.0) == 0.0 and L.orc_acos_cr(-1.0) == np.pi and np.isnan(L.orc_acos_cr(1.0000001))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+def test_vp_live_reference_sequence_on_one_object(orc, mh04):
+    """Twelve frames one after another on ONE reference object (its frame_count runs 0, 1, 2, ...: the vps[1]/vps[2] rule
+    applies from the second call on) against the oracle's sequence entry point, libm arithmetic: bit-exact.  Seeds are
+    chosen per frame so that the reference does not read lx[] out of range (its behaviour there is undefined)."""
+    sets, seeds = [], []
+    for k in range(12):
+        ln = orc.edline_detect(mh04[k])
+        for s in range(200):
+            sd = 1650000000 + 37 * k + s
+            if orc.vp_detect(ln, None, 461.6, 363.0, 248.1, sd, k, math_mode=0, details=True)[2]["flags"] == 0:
+                break
+        else:
+            pytest.skip("no clean seed")
+        sets.append(ln); seeds.append(sd)
+    cap = max(len(s) for s in sets)
+    lines = np.zeros((len(sets), cap), orc.LINE_DTYPE)
+    counts = np.array([len(s) for s in sets], np.int32)
+    for i, s in enumerate(sets):
+        lines[i, :len(s)] = s
+    v_ref, i_ref, n_ref = orc.vp_sequence(lines, counts, seeds, 461.6, 363.0, 248.1, frame_count0=0, use_ref=True)
+    v_orc, i_orc, n_orc = orc.vp_sequence(lines, counts, seeds, 461.6, 363.0, 248.1, frame_count0=0, math_mode=0, use_ref=False)
+    assert v_ref.tobytes() == v_orc.tobytes() and np.array_equal(i_ref, i_orc) and n_ref == n_orc > 100
+    # and frame by frame through the single-call door
+    for k in (0, 5, 11):
+        v, i = orc.vp_detect(sets[k], None, 461.6, 363.0, 248.1, seeds[k], k, math_mode=0)
+        assert v.tobytes() == v_ref[k].tobytes() and np.array_equal(i, i_ref[k, :len(i)])
