@@ -171,6 +171,9 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, uint32_t sp_ang,
 // ---------------------------------------------------------------------------
 // region2rect + get_theta (A.5).  Sequential double sums in list order.
 // ---------------------------------------------------------------------------
+#ifdef VPL_ENGINE_OUTLINE_MATH
+__device__ __noinline__ void sincos_cr_outlined(double a, double* s, double* c) { vpl_sincos_cr(a, s, c); }
+#endif
 __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
   const int lane = e.lane;
   double x = 0, y = 0, sum = 0;
@@ -252,7 +255,11 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
   // rect_nfa's row limits sit within an ulp of integers (the rectangle edges pass through
   // the centres of its extreme pixels), so the last bit of dx, dy decides pixel membership.
   double dx, dy;
+#ifdef VPL_ENGINE_OUTLINE_MATH  // experiment for the next round (build with VPL_EXTRA_NVCC=-DVPL_ENGINE_OUTLINE_MATH): the
+  sincos_cr_outlined(theta, &dy, &dx);  // same function out of line, to shrink region2rect's 40 KB of straight-line SASS
+#else
   vpl_sincos_cr(theta, &dy, &dx);
+#endif
   // length / width: min and max are order-free
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int j = lane; j < n; j += 32) {
