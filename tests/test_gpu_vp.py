@@ -285,3 +285,55 @@ def test_readimage_fused_pipeline(vpl, orc, mh04):
             c.sync()
             v2, i2, s2 = c.vp_detect_batch([as_capi(vpl, l) for l in el], seeds, frame_count0=0)
             assert v2.tobytes() == vps.tobytes() and all(np.array_equal(a, b) for a, b in zip(i2, idx))
+
+
+def test_slot_batch_kinds_and_cloud_after_readimage(vpl, orc, mh04):
+    """Every collect requires its own kind of batch; vpl_vp_pack_cloud after a vpl_readimage_* batch packs the lines
+    that batch's vanishing-point stage classified (the frame's detected lines), not the stale vpl_vp_submit buffers;
+    vpl_frontend_run_resident validates k and the kind of the resident batch."""
+    frames = mh04[3:6]
+    seeds = np.arange(5, 5 + len(frames), dtype=np.uint32)
+    fx, fy, cx, cy = 461.6, 460.3, 363.0, 248.1
+    with vpl.Context(max_width=752, max_height=480, max_lines=512, max_batch=4, num_slots=2, lsd_path=False) as c:
+        c.edlines_configure(vpl.capi.EDLineParam())
+        c.linematch_configure(vpl.capi.LineMatchParam())
+        c.vp_configure(*EUROC)
+        # pack_cloud before any vanishing-point batch: refused, nothing read
+        with pytest.raises(vpl.capi.VplError):
+            c.vp_pack_cloud([np.zeros(3, np.int32)], fx, fy, cx, cy)
+        lines, p2c, vps, idx, st = c.readimage_batch(frames, seeds, smoothed=True, frame_count0=0)
+        ids = [np.arange(len(l), dtype=np.int32) * 2 + 7 for l in lines]
+        got = c.vp_pack_cloud(ids, fx, fy, cx, cy, 1, 0)
+        el = [orc.edline_detect(f, orc.EDLineParam(), True) for f in frames]
+        v2, i2, s2, lv = c.vp_detect_batch([as_capi(vpl, l) for l in el], seeds, frame_count0=0, with_line_vps=True)
+        assert v2.tobytes() == vps.tobytes()
+        for i, s in enumerate(el):
+            want = orc.line_cloud(s, ids[i], lv[i], fx, fy, cx, cy, 1, 0)
+            for k in want:
+                assert got[i][k].tobytes() == want[k].tobytes(), (i, k)
+        # a readImage batch in flight is not a line-front-end / EDLines / vanishing-point batch
+        n = c.readimage_submit(1, frames, seeds)
+        cap = c.max_lines
+        ln = np.zeros((n, cap), vpl.capi.LINE_DTYPE); cnt = np.zeros(n, np.int32); pc = np.full((n, cap), -1, np.int32)
+        vv = np.zeros((n, 3, 3)); ii = np.full((n, cap), -1, np.int32)
+        with pytest.raises(vpl.capi.VplError):
+            c.linefront_collect_into(1, ln, cnt, cap, pc)
+        with pytest.raises(vpl.capi.VplError):
+            c.edlines_collect_into(1, ln, cnt, cap)
+        with pytest.raises(vpl.capi.VplError):
+            c.vp_collect_into(1, cap, vv, ii)
+        c.readimage_collect_into(1, ln, cnt, cap, pc, vv, ii)
+        assert vv.tobytes() == vps.tobytes() and all(ln[f, :cnt[f]].tobytes() == lines[f].tobytes() for f in range(n))
+        # nothing is left in flight and the slot can be reused for any kind
+        got_lines = c.edlines_detect_batch(frames[:1], smoothed=True)
+        assert got_lines[0].tobytes() == el[0].tobytes()
+    with vpl.Context(max_width=752, max_height=480, max_lines=1024, max_batch=2, num_slots=1) as c:
+        with pytest.raises(vpl.capi.VplError):
+            c.run_resident(0, k=1)                     # nothing resident
+        c.frontend_batch(frames[:2], scale=2, num_octaves=1, k=1)
+        with pytest.raises(vpl.capi.VplError):
+            c.run_resident(0, k=9)                     # k > max_k would overrun the match rows
+        with pytest.raises(vpl.capi.VplError):
+            c.run_resident(0, k=-1)
+        c.run_resident(0, k=2)
+        c.sync()

@@ -37,6 +37,9 @@ struct OctBuf {
   unsigned int* maxq = nullptr;
 };
 
+// What the batch in flight on a slot is (exactly one; every collect requires its own kind).
+enum BatchKind { BK_NONE = 0, BK_FRONTEND, BK_EDLINES, BK_LINEFRONT, BK_VP, BK_READIMAGE };
+
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;        // everything of the batch finished
@@ -69,14 +72,12 @@ struct Slot {
   VplLine* h_lines = nullptr;
   int* h_ed_status = nullptr;
   int ed_smoothed = 1;
-  bool ed_batch = false;  // the batch in flight on this slot is an EDLines batch
   // line matching (allocated by vpl_linematch_configure)
   uint8_t* lm_pyr = nullptr;
   short2* lm_deriv = nullptr;
   LmBuffers lm = {};
   int* h_r2c = nullptr;
   int* d_lm_counts = nullptr;  // line counts of the standalone match call (2 per pair)
-  bool lf_batch = false;       // the batch in flight is a fused EDLines + matching batch
   int lm_pairs = 0, lm_pstride = 1;
   VplSegment* d_seg = nullptr;
   int* d_seg_count = nullptr;
@@ -101,8 +102,12 @@ struct Slot {
   int* h_vp_idx = nullptr;
   double* h_line_vps = nullptr;
   int* h_vp_status = nullptr;      // 2 x B: status, flags
-  bool vp_batch = false, vp_same = true;
+  bool vp_same = true;
   int vp_n = 0, vp_fc0 = 0;
+  // the line set the slot's last vanishing-point run classified (vpl_vp_pack_cloud packs exactly that)
+  const VplLine* vp_src_lines = nullptr;  // device, B x max_lines
+  const int* vp_src_n = nullptr;          // device, B
+  const int* vp_src_hn = nullptr;         // host copy of the counts (valid after the collect)
   // pinned host staging
   uint8_t* h_img = nullptr;
   VplKeyLine* h_kl = nullptr;
@@ -114,6 +119,8 @@ struct Slot {
   int n = 0, w = 0, h = 0, num_octaves = 0, scale = 2, k = 0;
   int m_pairs = 0, m_cap_q = 0, m_cap_t = 0;  // geometry of the last standalone match (vpl_match_run_resident)
   bool in_flight = false;
+  int kind = BK_NONE;       // kind of the batch in flight
+  int resident = BK_NONE;   // kind of the batch whose frames / lines the slot still holds (run_resident re-runs it)
   int last_consumer = -1;  // slot whose match reads our last_desc
 };
 
@@ -549,6 +556,7 @@ int finish(VplContext* c, Slot& s) {
   CK(c, cudaGetLastError());
   harvest_times(c, s);
   s.in_flight = false;
+  s.kind = BK_NONE;
   return VPL_OK;
 }
 
@@ -980,6 +988,8 @@ int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int
   enqueue_dense_download(c, s);
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
+  s.kind = BK_FRONTEND;
+  s.resident = BK_FRONTEND;
   CK(c, cudaGetLastError());
   return VPL_OK;
 }
@@ -989,7 +999,7 @@ int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t*
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
+  if (!s.in_flight || s.kind != BK_FRONTEND) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
   if (r) return r;
@@ -1026,7 +1036,7 @@ int vpl_frontend_collect_dense(VplContext* c, int slot, int32_t* counts, VplKeyL
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || s.ed_batch) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
+  if (!s.in_flight || s.kind != BK_FRONTEND) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
   if (r) return r;
@@ -1070,10 +1080,14 @@ int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
   if (!c->cfg.lsd_path) return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0");
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (s.n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no frames: submit+collect a batch first", slot);
+  if (k < 0 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 0..%d", k, c->max_k);
+  if (s.n <= 0 || s.resident != BK_FRONTEND)
+    return fail(c, VPL_E_INVALID, "slot %d holds no front-end frames: submit+collect a front-end batch first", slot);
   if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight", slot);
+  int r = check_dims(c, s.n, s.w, s.h, s.num_octaves, s.scale, true);
+  if (r) return r;
   CK(c, cudaSetDevice(c->cfg.device));
-  int r = enqueue_frontend(c, slot, k, 0);
+  r = enqueue_frontend(c, slot, k, 0);
   if (r) return r;
   CK(c, cudaGetLastError());
   return VPL_OK;
@@ -1454,7 +1468,8 @@ int vpl_edlines_submit(VplContext* c, int slot, const uint8_t* const* imgs, int 
   ed_enqueue_download(c, s);
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
-  s.ed_batch = true;
+  s.kind = BK_EDLINES;
+  s.resident = BK_EDLINES;
   return VPL_OK;
 }
 
@@ -1462,11 +1477,10 @@ int vpl_edlines_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || !s.ed_batch || s.lf_batch) return fail(c, VPL_E_INVALID, "slot %d has no EDLines batch in flight", slot);
+  if (!s.in_flight || s.kind != BK_EDLINES) return fail(c, VPL_E_INVALID, "slot %d has no EDLines batch in flight", slot);
   if (!lines || !counts) return fail(c, VPL_E_INVALID, "null output");
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
-  s.ed_batch = false;
   if (r) return r;
   return ed_deliver(c, s, lines, counts, cap, status);
 }
@@ -1679,6 +1693,7 @@ int vpl_vp_configure(VplContext* c, float f, float cx, float cy) {
     CK(c, dmalloc(&s.d_vp_lines, B * cap));
     CK(c, dmalloc(&s.d_vp_all, B * cap));
     CK(c, dmalloc(&s.d_vp_n, 2 * B));
+    CK(c, cudaMemset(s.d_vp_n, 0, (size_t)2 * B * sizeof(int)));
     CK(c, dmalloc(&s.d_vp_seeds, B));
     CK(c, dmalloc(&s.d_vps, B * 9));
     CK(c, dmalloc(&s.d_vp_idx, B * cap));
@@ -1750,7 +1765,11 @@ int vpl_vp_submit(VplContext* c, int slot, const VplLine* lines, const int32_t* 
   }
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
-  s.vp_batch = true;
+  s.kind = BK_VP;
+  s.resident = BK_VP;
+  s.vp_src_lines = s.vp_same ? s.d_vp_lines : s.d_vp_all;
+  s.vp_src_n = s.vp_same ? s.d_vp_n : s.d_vp_n + B;
+  s.vp_src_hn = s.vp_same ? s.h_vp_n : s.h_vp_n + B;
   return VPL_OK;
 }
 
@@ -1758,14 +1777,13 @@ int vpl_vp_collect(VplContext* c, int slot, int cap, double* vps, int32_t* vp_id
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || !s.vp_batch) return fail(c, VPL_E_INVALID, "slot %d has no vanishing-point batch in flight", slot);
+  if (!s.in_flight || s.kind != BK_VP) return fail(c, VPL_E_INVALID, "slot %d has no vanishing-point batch in flight", slot);
   if (!vps || !vp_idx) return fail(c, VPL_E_INVALID, "null output");
   CK(c, cudaSetDevice(c->cfg.device));
   const int mcap = c->cfg.max_lines, B = c->cfg.max_batch, n = s.vp_n;
   if (line_vps)  // the per-line Vector4d copies are optional and 32 bytes per line: fetched only on request
     CK(c, cudaMemcpyAsync(s.h_line_vps, s.d_line_vps, (size_t)n * mcap * 4 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   int r = finish(c, s);
-  s.vp_batch = false;
   if (r) return r;
   memcpy(vps, s.h_vps, (size_t)n * 9 * sizeof(double));
   const int* na = s.vp_same ? s.h_vp_n : s.h_vp_n + B;
@@ -1795,19 +1813,21 @@ int vpl_vp_pack_cloud(VplContext* c, int slot, const int32_t* line_ids, int cap,
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
   if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
-  if (s.vp_n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no vanishing-point batch", slot);
+  if (s.vp_n <= 0 || !s.vp_src_lines || !s.vp_src_n || !s.vp_src_hn)
+    return fail(c, VPL_E_INVALID, "slot %d holds no collected vanishing-point batch", slot);
   if (!line_ids || !cloud || num_of_cam < 1 || cam < 0 || cam >= num_of_cam) return fail(c, VPL_E_INVALID, "bad argument");
   CK(c, cudaSetDevice(c->cfg.device));
-  const int mcap = c->cfg.max_lines, B = c->cfg.max_batch, n = s.vp_n;
-  const int* na = s.vp_same ? s.h_vp_n : s.h_vp_n + B;
+  const int mcap = c->cfg.max_lines, n = s.vp_n;
+  const int* na = s.vp_src_hn;  // counts of the line set the last vanishing-point run classified
   for (int i = 0; i < n; ++i) {
+    if (na[i] < 0 || na[i] > mcap) return fail(c, VPL_E_INVALID, "frame %d: stale line count %d", i, na[i]);
     if (na[i] > cap) return fail(c, VPL_E_CAPACITY, "frame %d: %d lines > cap %d", i, na[i], cap);
     memcpy(s.h_vp_ids + (size_t)i * mcap, line_ids + (size_t)i * cap, (size_t)na[i] * sizeof(int));
   }
   CK(c, cudaMemcpyAsync(s.d_vp_ids, s.h_vp_ids, (size_t)n * mcap * sizeof(int), cudaMemcpyHostToDevice, s.stream));
   {
     StageTimer t(c, s, VPL_STAGE_VP_CLASSIFY);
-    launch_vp_cloud(s.vp_same ? s.d_vp_lines : s.d_vp_all, s.vp_same ? s.d_vp_n : s.d_vp_n + B, mcap, s.d_vp_ids,
+    launch_vp_cloud(s.vp_src_lines, s.vp_src_n, mcap, s.d_vp_ids,
                     s.d_line_vps, fx, fy, cx, cy, num_of_cam, cam, s.d_cloud, n, s.stream);
     t.launches(1);
   }
@@ -1824,7 +1844,8 @@ int vpl_vp_run_resident(VplContext* c, int slot) {
   if (!c->vp_ready) return fail(c, VPL_E_INVALID, "call vpl_vp_configure first");
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (s.vp_n <= 0) return fail(c, VPL_E_INVALID, "slot %d holds no lines", slot);
+  if (s.vp_n <= 0 || s.resident != BK_VP) return fail(c, VPL_E_INVALID, "slot %d holds no vanishing-point line sets", slot);
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   if (c->cfg.profile) {
     bool any = false;
@@ -1867,6 +1888,8 @@ int vpl_debug_vp_scores(VplContext* c, int frame, double* scores) {
   if (e != cudaSuccess) return fail(c, VPL_E_CUDA, "vpl_debug_vp_scores: %s", cudaGetErrorString(e));
   return VPL_OK;
 }
+
+static int linefront_collect_impl(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur);
 
 // ---- fused: readImage's line pipeline for n consecutive frames ------------------------------------
 // (remap + CLAHE) -> EDline -> Matching(f-1, f) -> run_vanishing_point_detection on each frame's own lines
@@ -1919,9 +1942,11 @@ int vpl_readimage_submit(VplContext* c, int slot, const uint8_t* const* imgs, in
   CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
-  s.ed_batch = true;
-  s.lf_batch = true;
-  s.vp_batch = true;
+  s.kind = BK_READIMAGE;
+  s.resident = BK_READIMAGE;
+  s.vp_src_lines = s.d_lines;   // the stage ran on each frame's own detected lines
+  s.vp_src_n = s.d_counts;
+  s.vp_src_hn = s.h_counts;
   return VPL_OK;
 }
 
@@ -1930,11 +1955,10 @@ int vpl_readimage_collect(VplContext* c, int slot, VplLine* lines, int32_t* coun
   if (!c) return VPL_E_INVALID;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (!s.in_flight || !s.lf_batch || !s.vp_batch) return fail(c, VPL_E_INVALID, "slot %d has no readImage batch in flight", slot);
+  if (!s.in_flight || s.kind != BK_READIMAGE) return fail(c, VPL_E_INVALID, "slot %d has no readImage batch in flight", slot);
   if (!vps || !vp_idx) return fail(c, VPL_E_INVALID, "null output");
   const int n = s.n, mcap = c->cfg.max_lines, B = c->cfg.max_batch;
-  s.vp_batch = false;
-  int r = vpl_linefront_collect(c, slot, lines, counts, cap, prev_to_cur);
+  int r = linefront_collect_impl(c, slot, lines, counts, cap, prev_to_cur);
   if (r) return r;
   memcpy(vps, s.h_vps, (size_t)n * 9 * sizeof(double));
   for (int i = 0; i < n; ++i) {
@@ -1950,7 +1974,8 @@ int vpl_readimage_run_resident(VplContext* c, int slot) {
   if (!c->ed_ready || !c->vp_ready) return fail(c, VPL_E_INVALID, "configure EDLines, line matching and the vanishing points first");
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
   Slot& s = c->slots[slot];
-  if (s.n <= 0 || s.vp_n != s.n) return fail(c, VPL_E_INVALID, "slot %d holds no readImage batch", slot);
+  if (s.n <= 0 || s.vp_n != s.n || s.resident != BK_READIMAGE) return fail(c, VPL_E_INVALID, "slot %d holds no readImage batch", slot);
+  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
   if (c->cfg.profile) {
     bool any = false;
@@ -1995,20 +2020,17 @@ int vpl_linefront_submit(VplContext* c, int slot, const uint8_t* const* imgs, in
   CK(c, cudaMemcpyAsync(s.h_flags, s.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
-  s.ed_batch = true;
-  s.lf_batch = true;
+  s.kind = BK_LINEFRONT;
+  s.resident = BK_LINEFRONT;
   return VPL_OK;
 }
 
-int vpl_linefront_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur) {
-  if (!c) return VPL_E_INVALID;
-  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+// delivery shared by vpl_linefront_collect and vpl_readimage_collect (the caller has checked the batch kind)
+static int linefront_collect_impl(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur) {
   Slot& s = c->slots[slot];
-  if (!s.in_flight || !s.lf_batch) return fail(c, VPL_E_INVALID, "slot %d has no line front-end batch in flight", slot);
   if (!lines || !counts || !prev_to_cur) return fail(c, VPL_E_INVALID, "null output");
   CK(c, cudaSetDevice(c->cfg.device));
   int r = finish(c, s);
-  s.ed_batch = false; s.lf_batch = false;
   if (r) return r;
   r = ed_deliver(c, s, lines, counts, cap, nullptr);
   if (r) return r;
@@ -2022,6 +2044,14 @@ int vpl_linefront_collect(VplContext* c, int slot, VplLine* lines, int32_t* coun
     for (int i = np; i < cap; ++i) row[i] = -1;
   }
   return VPL_OK;
+}
+
+int vpl_linefront_collect(VplContext* c, int slot, VplLine* lines, int32_t* counts, int cap, int32_t* prev_to_cur) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  Slot& s = c->slots[slot];
+  if (!s.in_flight || s.kind != BK_LINEFRONT) return fail(c, VPL_E_INVALID, "slot %d has no line front-end batch in flight", slot);
+  return linefront_collect_impl(c, slot, lines, counts, cap, prev_to_cur);
 }
 
 int vpl_linefront_batch(VplContext* c, const uint8_t* const* imgs, int n, int w, int h, size_t stride, int smoothed,

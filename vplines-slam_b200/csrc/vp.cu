@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(128) vp_cloud_kernel(const VplLine* __restrict
                                                        float fx, float fy, float cx, float cy, int num_of_cam, int cam,
                                                        float* __restrict__ cloud) {
   const int frame = blockIdx.x;
-  const int n = n_all[frame];
+  const int n = min(max(n_all[frame], 0), cap);  // never past the frame's row, whatever the count buffer holds
   const VplLine* L = all_lines + (size_t)frame * cap;
   float* pts = cloud + (size_t)frame * cap * 10;
   float* ch = pts + 3 * (size_t)n;
