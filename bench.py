@@ -147,6 +147,103 @@ def tile_frames(unique, n):
     return np.ascontiguousarray(np.concatenate([unique] * reps)[:n])
 
 
+def lsd_metric(wl):
+    return METRIC.replace("752x480", "%dx%d" % (wl["w"], wl["h"]))
+
+
+def lsd_config(args, wl, world):
+    """The `config` object of the LSD/LBD/match workloads: the same for the B200 arm and for --impl reference
+    (the reference arm runs a bounded sample of this workload; how many frames it actually ran is in its
+    cpu_baseline.sample and `sample_frames_per_step`)."""
+    W, H = wl["w"], wl["h"]
+    return {"workload": wl["name"], "frames_per_step": args.batch, "width": W, "height": H, "octaves": wl["octaves"],
+            "match_k": wl["k"], "unique_frames": args.unique, "slots": args.slots,
+            "max_lines": args.max_lines or wl["max_lines"], "parallelism": f"frames x{world}",
+            "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (args.batch * W * H / 1e6)}
+
+
+def verify_dense_step(frames, prev_frame, counts, kl, desc, mt, K, octaves, check):
+    """Parity of one collected step against the CPU oracle chain (LSDDetector::detect -> BinaryDescriptor::compute ->
+    match(frame, previous frame)): `frames` are the step's frames, `prev_frame` the frame frame 0 was matched
+    against (None: no chaining), counts/kl/desc/mt the dense outputs of vpl_frontend_collect_dense, `check` the
+    frame indices to compare.  KeyLines (17 fields), descriptors, match indices and distances must be bit-equal.
+    -> list of (frame, what) mismatches."""
+    from oracle import oracle as O
+    n = len(frames)
+    off = np.concatenate([[0], np.cumsum(np.asarray(counts[:n], np.int64))])
+    cache = {}
+
+    def orc(img, key):
+        if key not in cache:
+            ekl = O.lsd_detector_detect(img, 2, octaves)
+            cache[key] = (ekl, O.lbd_compute(img, ekl))
+        return cache[key]
+
+    bad = []
+    for f in check:
+        ekl, ed = orc(frames[f], f)
+        a, b = int(off[f]), int(off[f + 1])
+        if b - a != len(ekl) or kl[a:b].tobytes() != ekl.tobytes():
+            bad.append((f, "keylines"))
+            continue
+        if not np.array_equal(desc[a:b], ed):
+            bad.append((f, "descriptors"))
+            continue
+        if K <= 0:
+            continue
+        m = mt[a:b].reshape(b - a, K)
+        prev = frames[f - 1] if f > 0 else prev_frame
+        if prev is None:
+            if not ((m["trainIdx"] == -1).all() and (m["queryIdx"][:, 0] == np.arange(b - a)).all()):
+                bad.append((f, "no-match fill"))
+            continue
+        pkl, pd = orc(prev, f - 1 if f > 0 else "prev")
+        if len(pd) < K or len(ed) == 0:
+            continue
+        idx, dist = O.hamming_knn(ed, pd, K)
+        if not (np.array_equal(m["trainIdx"], idx) and np.array_equal(m["distance"].astype(np.int32), dist)
+                and (m["queryIdx"] == np.arange(b - a)[:, None]).all()):
+            bad.append((f, "matches"))
+    return bad
+
+
+def cv2_crosscheck(unique, octaves=1, k=1, n=8):
+    """BASELINE.md 3.2 / SURVEY 8(d): the stages cv2 4.13 covers (GaussianBlur 5x5 + LSD_REFINE_ADV per octave +
+    BFMatcher on 32-byte codes; it has no LBD), 1 thread and default threads, frames/s on `n` frames."""
+    try:
+        import cv2
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)}
+    out = {"version": cv2.__version__, "frames": n,
+           "stages": "GaussianBlur(5x5,1) + createLineSegmentDetector(LSD_REFINE_ADV).detect per octave + "
+                     "BFMatcher(NORM_HAMMING).knnMatch on L x 32 random bytes (cv2 has no LBD)"}
+    rng = np.random.default_rng(0)
+    default_threads = cv2.getNumThreads()
+    for label, th in (("one_thread", 1), ("default_threads", default_threads)):
+        cv2.setNumThreads(th)
+        det = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        prev = None
+        t = time.time()
+        for i in range(n):
+            img = unique[i % len(unique)]
+            b = cv2.GaussianBlur(img, (5, 5), 1)
+            L = 0
+            for o in range(octaves):
+                seg = det.detect(b)[0]
+                L += 0 if seg is None else len(seg)
+                if o + 1 < octaves:
+                    b = cv2.pyrDown(b)
+            d = rng.integers(0, 256, (max(L, 1), 32), dtype=np.uint8)
+            if prev is not None:
+                bf.knnMatch(d, prev, k=k)
+            prev = d
+        out[label + "_frames_per_s"] = n / (time.time() - t)
+    out["default_threads"] = default_threads
+    cv2.setNumThreads(default_threads)
+    return out
+
+
 def cpu_baseline(unique, seconds=12.0, threads=None, octaves=1, name=WORKLOAD):
     """The oracle (CPU port of the path) on the host cores: bounded sample of the same frames."""
     from oracle import oracle as O
@@ -888,30 +985,38 @@ def run_reference(args):
         return 0
     if args.workload.startswith("E"):
         return run_reference_edlines(args)
-    unique = make_frames(min(args.unique, 32), args.seed)
+    wl = WORKLOADS[args.workload]
+    OCT, K = wl["octaves"], wl["k"]
+    unique = make_frames(args.unique, args.seed, args.workload)
     from oracle import oracle as O
     O.build()
     threads = os.cpu_count() or 1
     t = time.time()
-    O.frontend_sequence(unique[:4], num_octaves=1, max_lines=4096, threads=1)
+    O.frontend_sequence(unique[:4], num_octaves=OCT, max_lines=16384, threads=1)
     per_frame = max((time.time() - t) / 4, 1e-3)
-    # bounded sample per step: ~6 s of wall time
-    n = int(max(threads * 2, min(6.0 / per_frame * threads, 2048)))
+    # bounded sample per step: ~6 s of wall time on the host cores
+    n = int(max(threads * 2, min(6.0 / per_frame * threads, args.batch)))
     frames = tile_frames(unique, n)
     for _ in range(args.warmup):
-        O.frontend_sequence(frames[:max(threads, n // 4)], num_octaves=1, max_lines=4096, threads=threads)
+        O.frontend_sequence(frames[:max(threads, n // 4)], num_octaves=OCT, max_lines=16384, threads=threads)
     t0 = time.time()
+    total = 0
     for _ in range(args.steps):
-        O.frontend_sequence(frames, num_octaves=1, max_lines=4096, threads=threads)
+        total = O.frontend_sequence(frames, num_octaves=OCT, max_lines=16384, threads=threads)
     dt = time.time() - t0
     fps = n * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": lsd_metric(wl),
+            "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": n, "octaves": 1, "match_k": 1,
-                       "note": "CPU oracle port; the reference's OpenCV-3.4 line_descriptor binary is not buildable here"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": lsd_config(args, wl, args.gpus),
+            "sample_frames_per_step": n, "lines_per_frame": round(total / max(n, 1), 1),
+            "note": "CPU oracle port (oracle/, -O3 -march=native, all host threads); the reference's OpenCV-3.4 "
+                    "line_descriptor binary is not buildable here (no OpenCV C++ / contrib); each step is a bounded "
+                    f"sample of {n} frames of the workload",
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} frames/step x {args.steps} steps"},
+                             "sample": f"{n} frames/step x {args.steps} steps of {wl['name']}",
+                             "single_thread_frames_per_s": 1.0 / per_frame},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -931,6 +1036,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20240601)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the last timed e2e step")
+    ap.add_argument("--parity-frames", type=int, default=6, help="frames of the last e2e step compared with the oracle")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the resident steps (for ncu --profile-from-start off; V workloads)")
     args = ap.parse_args()
@@ -1025,11 +1132,37 @@ def main():
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
 
-    # ---- value: batches resident in HBM, kernels only
+    # ---- parity of what the timed e2e region just produced (outside the timed regions, rank 0): frames of the last
+    # collected step against the CPU oracle chain, bit for bit
+    parity = None
+    if rank == 0 and not args.no_parity:
+        last_slot = (args.steps - 1) % S
+        last_frames = host_buf if (args.steps == 1 and halo == 1) else batch_frames
+        prev = batch_frames[-1] if args.steps > 1 else None
+        nb = len(last_frames)
+        check = sorted({0, 1, nb // 2, nb - 1} | set(range(2, 2 + max(0, args.parity_frames - 4))))
+        bad = verify_dense_step(last_frames, prev, counts[last_slot], kl[last_slot], desc[last_slot], mt[last_slot],
+                                K, OCT, [f for f in check if f < nb])
+        parity = {"checked": len(bad) == 0, "frames": len(check), "mismatches": [list(map(str, b)) for b in bad][:8],
+                  "what": "KeyLines (17 fields), 32-byte descriptors, match indices + distances of the last timed e2e "
+                          "step vs the CPU oracle chain, bit-exact"}
+
+    # ---- stage times: one pass of resident batches with the per-stage events on (not the headline: with the
+    # events on, a submit waits for the slot's previous batch)
     for w in range(max(args.warmup, S)):
         ctx.run_resident(w % S, k=K)
     ctx.sync()
     ctx.reset_stage_times()
+    for i in range(args.steps):
+        ctx.run_resident(i % S, k=K)
+    ctx.sync()
+    stage = ctx.stage_times()
+    ctx.set_profile(False)
+
+    # ---- value: batches resident in HBM, kernels only, stage events off
+    for w in range(S):
+        ctx.run_resident(w % S, k=K)
+    ctx.sync()
     l0 = ctx.kernel_launches()
     barrier()
     ev0.record()
@@ -1040,7 +1173,6 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = ctx.kernel_launches() - l0
-    stage = ctx.stage_times()
     clocks = sampler.stop()
 
     # max over ranks
@@ -1092,20 +1224,20 @@ def main():
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},
                 "stage_share": stage_share}
 
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": lsd_metric(wl), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": wl_name, "frames_per_step": B, "width": W, "height": H, "octaves": OCT, "match_k": K,
-                       "unique_frames": args.unique, "slots": S, "max_lines": cap, "parallelism": f"frames x{world}",
-                       "lines_per_frame": round(lines_last / B, 1),
-                       "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (B * W * H / 1e6)},
+            "config": lsd_config(args, wl, world), "lines_per_frame": round(lines_last / B, 1),
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
     if rank == 0:
+        line["parity_checked"] = bool(parity and parity["checked"])
+        line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(unique, octaves=OCT, name=wl_name)
+            line["cpu_baseline"]["cv2_crosscheck"] = cv2_crosscheck(unique, octaves=OCT, k=K)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

@@ -384,7 +384,7 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
 #define VPL_STAGE_D2H 10
 #define VPL_STAGE_PREPROC 11  /* remap + CLAHE (optional)           */
 #define VPL_STAGE_ED_GRAD 12    /* EDLines: Sobel pair, gradient/direction map, anchor bitmap */
-#define VPL_STAGE_ED_ANCHOR 13  /* (unused: the anchor test is fused into the pass above)     */
+#define VPL_STAGE_RESERVED13 13  /* reserved (keeps the stage numbering stable)                    */
 #define VPL_STAGE_ED_WALK 14    /* smart routing (edge chains)     */
 #define VPL_STAGE_ED_FIT 15     /* line fit + validation + compaction */
 #define VPL_STAGE_LM_PYRAMID 16 /* line matching: KLT pyramids + Scharr */
@@ -399,6 +399,9 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);
 int vpl_reset_stage_times(VplContext* ctx);
+/* Switch the per-stage event timing on or off (VplConfig.profile) between batches; waits for the slots' streams.
+ * With profiling on, a submit on a slot first waits for that slot's previous batch (its events are re-recorded). */
+int vpl_set_profile(VplContext* ctx, int on);
 /* Total kernels launched by this context since creation. */
 int64_t vpl_kernel_launches(const VplContext* ctx);
 

@@ -21,12 +21,27 @@ KEYLINE_DTYPE = np.dtype(
 assert KEYLINE_DTYPE.itemsize == 68
 
 
+def _cpu_stamp():
+    """ISA flags of this host: the library is built -march=native, so it must be rebuilt on another CPU."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((l.split(":", 1)[1] for l in f if l.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(" ".join(sorted(flags.split())).encode()).hexdigest()
+
+
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
-    if (not force and os.path.exists(_SO)
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    stamp = os.path.join(_HERE, "_build", "cpu.stamp")
+    same_cpu = os.path.exists(stamp) and open(stamp).read().strip() == _cpu_stamp()
+    if (not force and same_cpu and os.path.exists(_SO)
             and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs)):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+    with open(stamp, "w") as f:
+        f.write(_cpu_stamp())
     return _SO
 
 
@@ -36,8 +51,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op when the library is current for this CPU
         L = ctypes.CDLL(_SO)
         L.orc_fast_atan2.restype = ctypes.c_float
         L.orc_fast_atan2.argtypes = [ctypes.c_float, ctypes.c_float]

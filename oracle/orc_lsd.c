@@ -366,8 +366,11 @@ static double rect_nfa(const Lsd* L, const Rect* rec) {
     double left = (y <= y1c) ? o[0].x + ((double)y - o[0].y) * flstep : o[1].x + ((double)y - o[1].y) * slstep;
     double right = (y < y3c) ? o[0].x + ((double)y - o[0].y) * frstep : o[3].x + ((double)y - o[3].y) * srstep;
     int xs = (int)ceil(left), xe = (int)right;
+    /* same pixels as "for x = xs..xe: if (x < 0 || x >= w) continue", without walking the part of a
+     * near-horizontal edge's span that lies outside the image (it can be 2^31 columns long) */
+    if (xs < 0) xs = 0;
+    if (xe > L->w - 1) xe = L->w - 1;
     for (int x = xs; x <= xe; ++x) {
-      if (x < 0 || x >= L->w) continue;
       ++total_pts;
       if (is_aligned(L, x, y, rec->theta, rec->prec)) ++alg_pts;
     }

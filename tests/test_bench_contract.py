@@ -8,6 +8,8 @@ import sys
 
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "dtype",
         "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
@@ -32,6 +34,12 @@ def test_reference_arm_line(extra):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not extra:  # the headline workload: the very `config` object the B200 arm prints (bench.lsd_config)
+        import argparse
+        import bench
+        a = argparse.Namespace(batch=4096, unique=96, slots=2, max_lines=0)
+        assert d["config"] == bench.lsd_config(a, bench.WORKLOADS["C2"], 1)
+        assert d["metric"] == bench.METRIC and d["sample_frames_per_step"] >= 2
 
 
 def test_other_ranks_do_no_work():

@@ -351,3 +351,60 @@ def test_errors(ctx, vpl):
     with pytest.raises(RuntimeError):
         vpl.LSDDetector.createLSDDetector().detect(np.zeros((64, 64), np.float32), 2, 1)
     assert vpl.BinaryDescriptorMatcher().match(np.zeros((0, 32), np.uint8), np.zeros((4, 32), np.uint8)) == []
+
+
+def _bench_path(vpl, frames, n_batches, k, octaves, cap):
+    """The exact call sequence bench.py times end to end: caller frames pinned with vpl_host_register, batches
+    submitted to alternating slots with chaining, results collected in dense form into registered buffers."""
+    frames = np.ascontiguousarray(frames)
+    n, h, w = frames.shape
+    per = (n + n_batches - 1) // n_batches
+    S = 2
+    outs = []
+    with vpl.Context(max_width=w, max_height=h, max_octaves=octaves, max_lines=cap, max_batch=per, num_slots=S,
+                     blur_first=True, profile=True) as c:
+        c.host_register(frames)
+        rows = per * cap
+        kl = [np.zeros(rows, vpl.capi.KEYLINE_DTYPE) for _ in range(S)]
+        counts = [np.zeros(per, np.int32) for _ in range(S)]
+        desc = [np.zeros((rows, 32), np.uint8) for _ in range(S)]
+        mt = [np.zeros((rows, k), vpl.capi.DMATCH_DTYPE) for _ in range(S)]
+        for a in kl + desc + mt:
+            c.host_register(a)
+        pending = []
+
+        def collect():
+            ps, lo, hi = pending.pop(0)
+            total = c.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
+            outs.append((lo, hi, counts[ps][:hi - lo].copy(), kl[ps][:total].copy(), desc[ps][:total].copy(),
+                         mt[ps][:total].copy()))
+
+        for i in range(n_batches):
+            s = i % S
+            if len(pending) == S:
+                collect()
+            lo, hi = i * per, min(n, (i + 1) * per)
+            c.submit(s, frames[lo:hi], scale=2, num_octaves=octaves, k=k, chain=(i > 0))
+            pending.append((s, lo, hi))
+        while pending:
+            collect()
+    return outs
+
+
+@pytest.mark.parametrize("name,n,batches,k,octaves,cap", [("C2_euroc_752x480", 33, 3, 1, 1, 1024),
+                                                          ("C3_d455_1280x720", 9, 3, 2, 2, 2048)])
+def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves, cap):
+    """The headline configs through bench.py's own path (host_register + submit(chain) over three batches +
+    collect_dense) against the oracle chain: every KeyLine, descriptor and match of every frame bit-equal; the
+    first frame of a later batch is matched against the last frame of the batch before it."""
+    import bench
+    frames = np.ascontiguousarray(synth.config_sequence(name, n))
+    outs = _bench_path(vpl, frames, batches, k, octaves, cap)
+    assert [o[0] for o in outs] == [i * ((n + batches - 1) // batches) for i in range(batches)]
+    n_lines = 0
+    for lo, hi, counts, kl, desc, mt in outs:
+        prev = frames[lo - 1] if lo > 0 else None
+        bad = bench.verify_dense_step(frames[lo:hi], prev, counts, kl, desc, mt, k, octaves, list(range(hi - lo)))
+        assert bad == [], (name, lo, bad)
+        n_lines += int(counts.sum())
+    assert n_lines > 50 * n

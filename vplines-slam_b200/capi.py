@@ -82,7 +82,8 @@ EXPORTS = [
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
     "vpl_readimage_submit", "vpl_readimage_collect", "vpl_readimage_run_resident",
-    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_kernel_launches",
+    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_set_profile",
+    "vpl_kernel_launches",
 ]
 
 _lib = None
@@ -133,6 +134,7 @@ def load():
     L.vpl_debug_candidates.argtypes = [vp, vp, vp, i32]
     L.vpl_get_stage_times.argtypes = [vp, vp, vp]
     L.vpl_reset_stage_times.argtypes = [vp]
+    L.vpl_set_profile.argtypes = [vp, i32]
     L.vpl_kernel_launches.argtypes = [vp]
     L.vpl_kernel_launches.restype = C.c_int64
     L.vpl_edlines_default_param.argtypes = [C.POINTER(EDLineParam)]
@@ -605,6 +607,10 @@ class Context:
 
     def reset_stage_times(self):
         self._ck(self._L.vpl_reset_stage_times(self._h))
+
+    def set_profile(self, on):
+        """Per-stage CUDA-event timing on / off (with it on, a submit waits for the slot's previous batch)."""
+        self._ck(self._L.vpl_set_profile(self._h, int(bool(on))))
 
     def kernel_launches(self):
         return int(self._L.vpl_kernel_launches(self._h))

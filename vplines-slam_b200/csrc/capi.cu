@@ -2206,6 +2206,17 @@ int vpl_get_stage_times(VplContext* c, double* ms, int64_t* launches) {
   return VPL_OK;
 }
 
+int vpl_set_profile(VplContext* c, int on) {
+  if (!c) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  for (Slot& s : c->slots) {  // bank what the slots' events still hold before the switch
+    CK(c, cudaStreamSynchronize(s.stream));
+    harvest_times(c, s);
+  }
+  c->cfg.profile = on ? 1 : 0;
+  return VPL_OK;
+}
+
 int vpl_reset_stage_times(VplContext* c) {
   if (!c) return VPL_E_INVALID;
   memset(c->stage_ms, 0, sizeof(c->stage_ms));
