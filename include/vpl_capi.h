@@ -399,6 +399,13 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);
 int vpl_reset_stage_times(VplContext* ctx);
+/* Test hook: list entries per lane of the LSD region engine's rings (0 = default, 2*ws*hs/32 rounded down to a power
+ * of two).  Small values force the engine's fallbacks (undo of parked regions, whole-arena mode); results must not change. */
+int vpl_debug_set_engine_ring_cap(VplContext* ctx, int entries_per_lane);
+/* Which LSD region engine runs.  0 = the default (one warp per frame in the sequential seed order), 1 = the
+ * speculative engine (one warp per frame, 32 seeds in flight, committed in seed order; batches of at most 1024
+ * frames, larger ones use the default).  Both produce the sequential algorithm's results bit for bit. */
+int vpl_debug_set_engine(VplContext* ctx, int kind);
 /* Switch the per-stage event timing on or off (VplConfig.profile) between batches; waits for the slots' streams.
  * With profiling on, a submit on a slot first waits for that slot's previous batch (its events are re-recorded). */
 int vpl_set_profile(VplContext* ctx, int on);

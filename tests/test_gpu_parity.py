@@ -408,3 +408,40 @@ def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves
         assert bad == [], (name, lo, bad)
         n_lines += int(counts.sum())
     assert n_lines > 50 * n
+
+
+@pytest.mark.parametrize("cap", [64, 512, 4096])
+def test_engine_ring_capacity_fallbacks(vpl, orc, mh04, synth, cap):
+    """The speculative region engine with rings so small that its fallbacks run all the time (a region that does
+    not fit a lane's ring undoes what the lane has parked; one that does not fit at all runs alone with the whole
+    arena): KeyLines still equal the oracle's bit for bit."""
+    frames = np.stack([mh04[0], synth.config_sequence("C2_euroc_752x480", 1)[0]])
+    with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=4096, max_batch=2, num_slots=1) as c:
+        c.set_engine(1)
+        c.set_engine_ring_cap(cap)
+        kls = c.lsd_detect_batch(frames)
+        c.set_engine_ring_cap(0)
+        again = c.lsd_detect_batch(frames)
+    for f in range(2):
+        ekl = orc.lsd_detector_detect(frames[f], 2, 1)
+        assert kl_fields_equal(kls[f], ekl), (cap, f, len(kls[f]), len(ekl))
+        assert kl_fields_equal(again[f], ekl), f
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_both_region_engines_against_oracle(vpl, orc, mh04, synth, kind):
+    """The default (warp-cooperative, sequential seed order) and the speculative (32 seeds in flight) region engine both
+    reproduce the oracle's KeyLines bit for bit: real EuRoC frames, synthetic C2 frames, two octaves of a C3 frame."""
+    frames = np.concatenate([mh04[:6], synth.config_sequence("C2_euroc_752x480", 4)])
+    with vpl.Context(max_width=1280, max_height=720, max_octaves=2, max_lines=4096, max_batch=40, num_slots=1) as c:
+        c.set_engine(kind)
+        kls = c.lsd_detect_batch(frames)
+        for f in range(len(frames)):
+            assert kl_fields_equal(kls[f], orc.lsd_detector_detect(frames[f], 2, 1)), (kind, f)
+        c3 = synth.config_sequence("C3_d455_1280x720", 1)
+        k3 = c.lsd_detect_batch(c3, scale=2, num_octaves=2)
+        assert kl_fields_equal(k3[0], orc.lsd_detector_detect(c3[0], 2, 2)), kind
+        many = np.ascontiguousarray(np.concatenate([frames] * 4))
+        km = c.lsd_detect_batch(many)
+        for f in range(len(many)):
+            assert kl_fields_equal(km[f], kls[f % len(frames)]), (kind, f)

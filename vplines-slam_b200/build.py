@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvplines_b200.so")
-SOURCES = ["prims.cu", "preproc.cu", "lsd_front.cu", "lsd_engine.cu", "lsd_nfa.cu", "lbd_match.cu", "edlines.cu", "linematch.cu", "vp.cu", "capi.cu"]
+SOURCES = ["prims.cu", "preproc.cu", "lsd_front.cu", "lsd_engine.cu", "lsd_engine_spec.cu", "lsd_nfa.cu", "lbd_match.cu", "edlines.cu", "linematch.cu", "vp.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "4",

@@ -82,7 +82,7 @@ EXPORTS = [
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
     "vpl_readimage_submit", "vpl_readimage_collect", "vpl_readimage_run_resident",
-    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_set_profile",
+    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_set_profile", "vpl_debug_set_engine_ring_cap", "vpl_debug_set_engine",
     "vpl_kernel_launches",
 ]
 
@@ -135,6 +135,8 @@ def load():
     L.vpl_get_stage_times.argtypes = [vp, vp, vp]
     L.vpl_reset_stage_times.argtypes = [vp]
     L.vpl_set_profile.argtypes = [vp, i32]
+    L.vpl_debug_set_engine_ring_cap.argtypes = [vp, i32]
+    L.vpl_debug_set_engine.argtypes = [vp, i32]
     L.vpl_kernel_launches.argtypes = [vp]
     L.vpl_kernel_launches.restype = C.c_int64
     L.vpl_edlines_default_param.argtypes = [C.POINTER(EDLineParam)]
@@ -611,6 +613,14 @@ class Context:
     def set_profile(self, on):
         """Per-stage CUDA-event timing on / off (with it on, a submit waits for the slot's previous batch)."""
         self._ck(self._L.vpl_set_profile(self._h, int(bool(on))))
+
+    def set_engine_ring_cap(self, entries_per_lane):
+        """Test hook: ring capacity per lane of the LSD region engine (0 = default)."""
+        self._ck(self._L.vpl_debug_set_engine_ring_cap(self._h, int(entries_per_lane)))
+
+    def set_engine(self, kind):
+        """LSD region engine: 0 = default (warp-cooperative, sequential seed order), 1 = speculative (32 seeds in flight)."""
+        self._ck(self._L.vpl_debug_set_engine(self._h, int(kind)))
 
     def kernel_launches(self):
         return int(self._L.vpl_kernel_launches(self._h))

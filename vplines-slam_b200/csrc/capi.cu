@@ -23,12 +23,15 @@ namespace {
 
 thread_local std::string g_create_error;
 
+
 struct OctBuf {
   uint8_t* pyr = nullptr;
   short2* grad = nullptr;
   uint8_t* scl = nullptr;
   float* ang = nullptr;
-  Pix* pix = nullptr;
+  uint32_t* tag = nullptr;      // owner tags of the region engines
+  EngDesc* eng_desc = nullptr;  // parked transactions of the speculative region engine, spec_frames x 32 x kEngQ
+  RectCand* eng_rects = nullptr;
   int* ord = nullptr;
   int* n_ord = nullptr;
   RegEnt* reg = nullptr;
@@ -153,6 +156,9 @@ struct VplContext {
   bool vp_ready = false;  // vpl_vp_configure has run
   VpParams vpp;
   double* d_vp_lambda = nullptr;
+  int engine_ring_cap = 0;  // list entries per lane of the speculative region engine, 0 = 2*ws*hs/32 (vpl_debug_set_engine_ring_cap)
+  int engine_kind = 0;      // 0 = warp-cooperative engine (lsd_engine.cu), 1 = speculative engine (lsd_engine_spec.cu)
+  float2* d_cssn_lut = nullptr;  // (cosf, sinf) of the level-line angle by gradient differences, kLutN x kLutN
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
 };
@@ -288,11 +294,14 @@ void fill_engine_args(VplContext* c, Slot& s, EngineArgs& a) {
   a.overflow = s.d_flags;
   a.lgam = c->d_lgam;
   a.lgam_n = c->lgam_n;
+  a.lut = c->d_cssn_lut;
+  a.ring_cap = c->engine_ring_cap;  // 0 = default; vpl_debug_set_engine_ring_cap forces small rings (tests of the fallbacks)
   for (int o = 0; o < s.num_octaves; ++o) {
     int wo, ho, ws, hs;
     octave_geom(s.w, s.h, o, wo, ho, ws, hs);
     EngineOct& e = a.oct[o];
-    e.pix = s.oct[o].pix; e.ang = s.oct[o].ang; e.ord = s.oct[o].ord; e.n_ord = s.oct[o].n_ord;
+    e.ang = s.oct[o].ang; e.ord = s.oct[o].ord; e.n_ord = s.oct[o].n_ord;
+    e.tag = s.oct[o].tag; e.scl = s.oct[o].scl; e.desc = s.oct[o].eng_desc; e.rects = s.oct[o].eng_rects;
     e.reg = s.oct[o].reg; e.cand = s.oct[o].cand; e.n_cand = s.oct[o].n_cand;
     e.ws = ws; e.hs = hs;
     e.log_nt = 5 * (log10((double)ws) + log10((double)hs)) / 2 + log10(11.0);
@@ -317,7 +326,7 @@ void run_lsd(VplContext* c, Slot& s) {
   {
     StageTimer t(c, s, VPL_STAGE_ANGLE);
     for (int o = 0; o < s.num_octaves; ++o)
-      launch_ll_angle(s.oct[o].scl, s.oct[o].ang, s.oct[o].pix, s.oct[o].maxq, ws[o], hs[o], s.n, c->lc.rho, s.stream);
+      launch_ll_angle(s.oct[o].scl, s.oct[o].ang, s.oct[o].tag, s.oct[o].maxq, ws[o], hs[o], s.n, c->lc.rho, s.stream);
     t.launches(s.num_octaves);
   }
   {
@@ -331,7 +340,10 @@ void run_lsd(VplContext* c, Slot& s) {
   fill_engine_args(c, s, a);
   {
     StageTimer t(c, s, VPL_STAGE_REGION);
-    launch_region_engine(a, s.stream);
+    // default: the warp-cooperative engine; vpl_debug_set_engine(ctx, 1): the speculative one (its parking buffers
+    // are sized for kSpecMaxBatch frames)
+    if (c->engine_kind == 1 && s.n <= kSpecMaxBatch) launch_region_engine_spec(a, s.stream);
+    else launch_region_engine(a, s.stream);
     t.launches(1);
   }
   {
@@ -825,12 +837,13 @@ void vpl_destroy(VplContext* c) {
   for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
   cudaFree(c->d_mapx); cudaFree(c->d_mapy); cudaFree(c->d_wtab);
   cudaFree(c->d_lgam);
+  cudaFree(c->d_cssn_lut);
   cudaFree(c->d_vp_lambda);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
-      cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.ord);
+      cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.tag); cudaFree(b.eng_desc); cudaFree(b.eng_rects); cudaFree(b.ord);
       cudaFree(b.n_ord); cudaFree(b.reg); cudaFree(b.cand); cudaFree(b.n_cand); cudaFree(b.maxq);
     }
     cudaFree(s.d_kl); cudaFree(s.d_counts); cudaFree(s.d_desc); cudaFree(s.d_match); cudaFree(s.d_last_desc);
@@ -907,6 +920,11 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     for (int m = 1; m < c->lgam_n; ++m) tab[m] = host_log_gamma((double)m);
     CKC(cudaMalloc((void**)&c->d_lgam, tab.size() * sizeof(double)));
     CKC(cudaMemcpy(c->d_lgam, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (cfg->lsd_path) {
+      CKC(cudaMalloc((void**)&c->d_cssn_lut, (size_t)kLutN * kLutN * sizeof(float2)));
+      launch_cssn_lut(c->d_cssn_lut, 0);
+      CKC(cudaGetLastError());
+    }
   }
   const size_t B = (size_t)cfg->max_batch, cap = (size_t)cfg->max_lines;
   const size_t P0 = (size_t)cfg->max_width * cfg->max_height;
@@ -933,7 +951,12 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
       if (!cfg->lsd_path) continue;  // EDLines / KLT front end only: pyramid image + Sobel pair of octave 0 suffice
       CKC(dmalloc(&b.scl, B * So));
       CKC(dmalloc(&b.ang, B * So));
-      CKC(dmalloc(&b.pix, B * So));
+      CKC(dmalloc(&b.tag, B * So));
+      {  // the speculative engine only ever runs on batches of at most kSpecMaxBatch frames
+        const size_t sb = std::min<size_t>(B, (size_t)kSpecMaxBatch);
+        CKC(dmalloc(&b.eng_desc, sb * 32 * kEngQ));
+        CKC(dmalloc(&b.eng_rects, sb * 32 * kEngQ));
+      }
       CKC(dmalloc(&b.ord, B * So));
       CKC(dmalloc(&b.reg, B * So));
       CKC(dmalloc(&b.n_ord, B));
@@ -2153,7 +2176,7 @@ int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, 
       launch_scale08(s.oct[0].pyr, s.oct[0].scl, w, h, ws, hs, 1, s.stream);
       c->launches += 1;
       if (which == 3) { src = s.oct[0].scl; bytes = (size_t)ws * hs; *out_w = ws; *out_h = hs; break; }
-      launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].pix, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
+      launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].tag, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
       c->launches += 1;
       if (which == 4) { src = s.oct[0].ang; bytes = (size_t)ws * hs * sizeof(float); *out_w = ws; *out_h = hs; break; }
       launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, s.oct[0].reg, (size_t)ws * hs * sizeof(RegEnt), ws,
@@ -2203,6 +2226,20 @@ int vpl_get_stage_times(VplContext* c, double* ms, int64_t* launches) {
     if (ms) ms[i] = c->stage_ms[i];
     if (launches) launches[i] = c->stage_launches[i];
   }
+  return VPL_OK;
+}
+
+int vpl_debug_set_engine_ring_cap(VplContext* c, int entries_per_lane) {
+  if (!c) return VPL_E_INVALID;
+  if (entries_per_lane != 0 && entries_per_lane < 64) return fail(c, VPL_E_INVALID, "ring capacity must be 0 (default) or >= 64 entries");
+  c->engine_ring_cap = entries_per_lane;
+  return VPL_OK;
+}
+
+int vpl_debug_set_engine(VplContext* c, int kind) {
+  if (!c) return VPL_E_INVALID;
+  if (kind < 0 || kind > 1) return fail(c, VPL_E_INVALID, "engine kind must be 0 (default, warp-cooperative) or 1 (speculative)");
+  c->engine_kind = kind;
   return VPL_OK;
 }
 

@@ -11,10 +11,10 @@
 // sequential by definition (first-come pixel ownership, running float32 mean
 // angle, double sums in list order), so the warp keeps exactly that order and
 // uses its 32 lanes for everything that is order-free:
-//   * seed scan: 32 ordered seeds per step, one 128-bit gather each;
-//   * growth: the 8 neighbours of up to four FIFO pixels are gathered with one
-//     128-bit load per lane (32 lanes); acceptance is then resolved in lane order,
-//     which is exactly the sequential (FIFO, yy, xx) order;
+//   * seed scan: 32 ordered seeds per step, one tag gather each;
+//   * growth: the 8 neighbours of up to four FIFO pixels are gathered by the 32 lanes (4-byte
+//     angle + 4-byte owner tag each; candidates also fetch their (cos, sin) from the table);
+//     acceptance is then resolved in lane order, which is exactly the sequential (FIFO, yy, xx) order;
 //   * rectangle sums: per-entry products in parallel, the additions themselves in
 //     list order (shuffle broadcast) so the double results equal the sequential
 //     sums bit for bit;
@@ -32,8 +32,11 @@ namespace vpl {
 constexpr int RING = 256;  // per-warp FIFO window kept in shared memory
 
 struct Eng {
-  Pix* pix;
-  RegEnt* reg;
+  const float* ang;    // level-line angle in degrees per pixel (read-only)
+  uint32_t* tag;       // 0 = undefined, 0xFFFFFFFF = free, 1 = used
+  const uint8_t* scl;  // scaled image: gradient differences of a pixel (-> q, (cos, sin) table)
+  const float2* lut;   // (cosf, sinf) by gradient differences
+  uint32_t* reg;       // region list: x | y << 16 per entry
   int* ring;  // shared memory, RING ints
   double* bc;    // shared memory, 32 doubles  } broadcast buffers for the in-order sums
   double2* bc2;  // shared memory, 32 double2  }
@@ -71,21 +74,14 @@ __device__ __forceinline__ bool aligned_rad(double a, double theta, double prec)
 // region_grow (A.4).  Returns the region size; reg[0..n) holds the region in
 // acceptance order; *reg_angle_out is the final running angle.
 // ---------------------------------------------------------------------------
-__device__ __noinline__ int region_grow(const Eng& e, int seed, uint32_t sp_ang, uint32_t sp_q, double prec,
+__device__ __noinline__ int region_grow(const Eng& e, int seed_xy, float seed_deg, double prec,
                                         double* reg_angle_out) {
   const int lane = e.lane, ws = e.ws, hs = e.hs;
-  Pix* pix = e.pix;
-  // seed: defined and currently unused; its record was fetched by the caller
-  Pix sp;
-  sp.ang = sp_ang; sp.q = sp_q; sp.cs = 0.f; sp.sn = 0.f;
-  float seed_deg = __uint_as_float(sp.ang & 0x7fffffffu);
-  const int seed_y = seed / ws, seed_x = seed - seed_y * ws;
-  const int seed_xy = seed_x | (seed_y << 16);
+  uint32_t* tag = e.tag;
+  // seed: defined and currently free
   if (lane == 0) {
-    pix[seed].ang = sp.ang | kUsedBit;
-    RegEnt r;
-    r.idx = seed; r.ang = seed_deg; r.q = sp.q; r.pad = (uint32_t)seed_xy;
-    e.reg[0] = r;
+    tag[(seed_xy >> 16) * ws + (seed_xy & 0xffff)] = 1u;
+    e.reg[0] = (uint32_t)seed_xy;
     e.ring[0] = seed_xy;
   }
   // The running region angle is always (double)reg_deg * DEG2RAD with reg_deg the float32
@@ -115,22 +111,24 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, uint32_t sp_ang,
     if (take > 4) take = 4;
     const bool act = (g < take);
     int nidx = -1, nxy = 0;
-    uint32_t ab = 0xffffffffu;
-    float cs = 0.f, sn = 0.f;
-    uint32_t q = 0;
+    uint32_t tg = 0u;
+    float adeg = 0.f, cs = 0.f, sn = 0.f;
     if (act) {
       int j = i + g;
-      int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : (int)e.reg[j].pad;  // packed x | y << 16
+      int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : (int)e.reg[j];  // packed x | y << 16
       int nx = (cur & 0xffff) + ddx, ny = (cur >> 16) + ddy;
       if (nx >= 0 && nx < ws && ny >= 0 && ny < hs) {
         nidx = ny * ws + nx;
         nxy = nx | (ny << 16);
-        Pix p = pix[nidx];
-        ab = p.ang; cs = p.cs; sn = p.sn; q = p.q;
+        tg = tag[nidx];
+        adeg = __ldg(e.ang + nidx);
       }
     }
-    bool cand = (nidx >= 0) && !(ab & kUsedBit);
-    const float adeg = __uint_as_float(ab);
+    bool cand = (nidx >= 0) && tg == kTagFree;
+    if (cand) {  // what an acceptance adds to the float32 sums: fetched by every candidate lane at once
+      const float2 v = pixel_cssn(e.lut, e.scl, ws, nxy & 0xffff, nxy >> 16);
+      cs = v.x; sn = v.y;
+    }
     // resolve acceptances in lane order == sequential order
     while (true) {
       bool al = false;
@@ -145,10 +143,8 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed, uint32_t sp_ang,
       int f = __ffs(m) - 1;
       int accxy = __shfl_sync(0xffffffffu, nxy, f);
       if (lane == f) {
-        pix[nidx].ang = ab | kUsedBit;
-        RegEnt r;
-        r.idx = nidx; r.ang = adeg; r.q = q; r.pad = (uint32_t)nxy;
-        e.reg[n] = r;
+        tag[nidx] = 1u;
+        e.reg[n] = (uint32_t)nxy;
         e.ring[n & (RING - 1)] = nxy;
       }
       float fcs = __shfl_sync(0xffffffffu, cs, f);
@@ -181,9 +177,9 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
     int j = base + lane;
     double wx = 0, wy = 0, wt = 0;
     if (j < n) {
-      RegEnt r = e.reg[j];
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
-      wt = sqrt((double)(int)r.q / 4.0);
+      const uint32_t r = e.reg[j];
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
+      wt = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
       wx = (double)px * wt;
       wy = (double)py * wt;
     }
@@ -217,9 +213,9 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
     int j = base + lane;
     double t1 = 0, t2 = 0, t3 = 0;
     if (j < n) {
-      RegEnt r = e.reg[j];
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
-      double weight = sqrt((double)(int)r.q / 4.0);
+      const uint32_t r = e.reg[j];
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
+      double weight = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
       double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * weight;
       t2 = dx * dx * weight;
@@ -263,8 +259,8 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
   // length / width: min and max are order-free
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int j = lane; j < n; j += 32) {
-    RegEnt r = e.reg[j];
-    int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
+    const uint32_t r = e.reg[j];
+    int px = (int)(r & 0xffffu), py = (int)(r >> 16);
     double regdx = (double)px - x, regdy = (double)py - y;
     double l = regdx * dx + regdy * dy;
     double w = regdy * dx - regdx * dy;
@@ -302,10 +298,10 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
     int j = base + lane;
     bool in = false;
     if (j < n) {
-      RegEnt r = e.reg[j];
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
+      const uint32_t r = e.reg[j];
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
       in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
-      if (!in) e.pix[r.idx].ang &= ~kUsedBit;
+      if (!in) e.tag[py * e.ws + px] = kTagFree;
     }
     n_in += __popc(__ballot_sync(0xffffffffu, in));
   }
@@ -315,11 +311,10 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
   for (int top = n; top > n_in; top -= 32) {
     int j = top - 1 - lane;
     bool in = false;
-    RegEnt r;
-    r.idx = 0; r.ang = 0; r.q = 0; r.pad = 0;
+    uint32_t r = 0;
     if (j >= n_in) {
       r = e.reg[j];
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
       in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
     }
     unsigned m = __ballot_sync(0xffffffffu, in);
@@ -335,8 +330,8 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
     int j = base + lane;
     bool hole = false;
     if (j < n_in) {
-      RegEnt r = e.reg[j];
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
+      const uint32_t r = e.reg[j];
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
       hole = dist_sq_d(xc, yc, (double)px, (double)py) > radSq;
     }
     unsigned m = __ballot_sync(0xffffffffu, hole);
@@ -350,7 +345,7 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
 
 __device__ bool reduce_region_radius(const Eng& e, int& n, double reg_angle, double prec, double p, RectCand& rec,
                                      double density, double density_th) {
-  uint32_t s0 = e.reg[0].pad;
+  uint32_t s0 = e.reg[0];
   int xc_i = (int)(s0 & 0xffffu), yc_i = (int)(s0 >> 16);
   double xc = (double)xc_i, yc = (double)yc_i;
   double radSq1 = dist_sq_d(xc, yc, rec.x1, rec.y1);
@@ -371,10 +366,11 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
   const int lane = e.lane;
   double density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
   if (density >= density_th) return true;
-  RegEnt r0 = e.reg[0];
-  int xc_i = (int)(r0.pad & 0xffffu), yc_i = (int)(r0.pad >> 16);
+  const uint32_t r0 = e.reg[0];
+  int xc_i = (int)(r0 & 0xffffu), yc_i = (int)(r0 >> 16);
   double xc = (double)xc_i, yc = (double)yc_i;
-  double ang_c = (double)r0.ang * VPL_DEG2RAD;
+  const float seed_deg = e.ang[yc_i * e.ws + xc_i];
+  double ang_c = (double)seed_deg * VPL_DEG2RAD;
   double sum = 0, s_sum = 0;
   int cnt = 0;
   for (int base = 0; base < n; base += 32) {
@@ -382,12 +378,12 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
     bool flag = false;
     double ang_d = 0, sq = 0;
     if (j < n) {
-      RegEnt r = e.reg[j];
-      e.pix[r.idx].ang &= ~kUsedBit;
-      int px = (int)(r.pad & 0xffffu), py = (int)(r.pad >> 16);
+      const uint32_t r = e.reg[j];
+      int px = (int)(r & 0xffffu), py = (int)(r >> 16);
+      e.tag[py * e.ws + px] = kTagFree;
       if (dist_d(xc, yc, (double)px, (double)py) < rec.width) {
         flag = true;
-        ang_d = angle_diff_signed_d((double)r.ang * VPL_DEG2RAD, ang_c);
+        ang_d = angle_diff_signed_d((double)e.ang[py * e.ws + px] * VPL_DEG2RAD, ang_c);
         sq = ang_d * ang_d;
       }
     }
@@ -403,7 +399,7 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
   __syncwarp();
   double mean_angle = sum / (double)cnt;
   double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(e, r0.idx, __float_as_uint(r0.ang), r0.q, tau, &reg_angle);
+  n = region_grow(e, (int)r0, seed_deg, tau, &reg_angle);
   if (n < 2) return false;
   region2rect(e, n, reg_angle, prec, p, rec);
   density = (double)n / (dist_d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
@@ -423,8 +419,11 @@ region_engine_kernel(EngineArgs A) {
   const EngineOct& O = A.oct[blockIdx.y];
   const size_t npx = (size_t)O.ws * O.hs;
   Eng e;
-  e.pix = O.pix + (size_t)f * npx;
-  e.reg = O.reg + (size_t)f * npx;
+  e.ang = O.ang + (size_t)f * npx;
+  e.tag = O.tag + (size_t)f * npx;
+  e.scl = O.scl + (size_t)f * npx;
+  e.lut = A.lut;
+  e.reg = reinterpret_cast<uint32_t*>(O.reg + (size_t)f * npx);
   e.ring = s_ring;
   e.bc = s_bc;
   e.bc2 = s_bc2;
@@ -441,17 +440,17 @@ region_engine_kernel(EngineArgs A) {
   for (int base = 0; base < n_ord; base += 32) {
     int my = (base + lane < n_ord) ? ord[base + lane] : -1;
     bool free_ = false;
-    if (my >= 0) free_ = !(e.pix[my].ang & kUsedBit);
+    if (my >= 0) free_ = e.tag[my] == kTagFree;
     unsigned todo = __ballot_sync(0xffffffffu, free_);
     while (todo) {
       int l = __ffs(todo) - 1;
       todo &= todo - 1;
       int seed = __shfl_sync(0xffffffffu, my, l);
       // the seed may have been absorbed by a region grown earlier in this chunk
-      Pix sp = e.pix[seed];
-      if (sp.ang & kUsedBit) continue;
+      if (e.tag[seed] != kTagFree) continue;
+      const int sy = seed / e.ws, sx = seed - sy * e.ws;
       double reg_angle;
-      int n = region_grow(e, seed, sp.ang, sp.q, prec, &reg_angle);
+      int n = region_grow(e, sx | (sy << 16), e.ang[seed], prec, &reg_angle);
       if (n < O.min_reg_size) continue;
       RectCand rec;
       region2rect(e, n, reg_angle, prec, p, rec);

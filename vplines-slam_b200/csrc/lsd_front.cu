@@ -20,14 +20,13 @@ __device__ __forceinline__ void grad2x2(const uint8_t* __restrict__ s, int ws, i
 }
 
 // ---------------------------------------------------------------------------
-// K3.  Four consecutive pixels per thread.  Writes ang (4 B) and the engine record pix (16 B)
-// of every pixel, reduces max(gx^2+gy^2) per frame with one atomicMax per warp.
-// Algorithmic bytes: read S, write 20 S.
+// K3.  Four pixels per thread.  Writes the angle (4 B) and the owner tag (4 B) of every pixel and reduces
+// max(gx^2+gy^2) per frame with one atomicMax per warp.  Algorithmic bytes: read S, write 8 S.
 // ---------------------------------------------------------------------------
-constexpr int LLA_PX = 4;  // consecutive pixels per thread
+constexpr int LLA_PX = 4;  // pixels per thread
 
 __global__ void __launch_bounds__(256)
-ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* __restrict__ pix,
+ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, uint32_t* __restrict__ tag,
                 unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
   // pixel k of a thread is x0 + 32 k: every load/store instruction of the warp is contiguous
   const int x0 = blockIdx.x * (32 * LLA_PX) + (threadIdx.x & 31);
@@ -50,9 +49,6 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
       const int x = x0 + 32 * k;
       if (x >= ws) break;
       float a = kNotDefDeg;
-      Pix u;
-      u.ang = __float_as_uint(kNotDefDeg);
-      u.cs = 0.f; u.sn = 0.f; u.q = 0u;
       if (x < ws - 1 && has_next_row) {
         int DA = pd[k] - pa[k], BC = pb[k] - pc[k];
         int gx = DA + BC, gy = DA - BC;
@@ -63,17 +59,10 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
         if (!(norm <= rho)) {
           q = max(q, qq);
           a = fast_atan2_deg((float)gx, (float)-gy);
-          // cos(float(angle)) / sin(float(angle)) of the radian angle, float overloads:
-          // correctly rounded float of the double function.
-          float ar = (float)((double)a * VPL_DEG2RAD);
-          u.ang = __float_as_uint(a);
-          u.cs = (float)cos((double)ar);  // sincos() measured slower here (1033 vs 978 us per 512 frames)
-          u.sn = (float)sin((double)ar);
-          u.q = qq;
         }
       }
       ang[fo + (size_t)y * ws + x] = a;
-      pix[fo + (size_t)y * ws + x] = u;
+      tag[fo + (size_t)y * ws + x] = (a == kNotDefDeg) ? 0u : kTagFree;
     }
   }
   // warp max -> one atomic per warp
@@ -82,10 +71,27 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
   if ((threadIdx.x & 31) == 0 && q > 0) atomicMax(maxq + blockIdx.z, q);
 }
 
-void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
+void launch_ll_angle(const uint8_t* scl, float* ang, uint32_t* tag, unsigned int* maxq, int ws, int hs,
                      int batch, double rho, cudaStream_t st) {
   dim3 grid((ws + 32 * LLA_PX - 1) / (32 * LLA_PX), (hs + 7) / 8, batch);
-  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, maxq, ws, hs, rho);
+  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, tag, maxq, ws, hs, rho);
+}
+
+// (cosf, sinf) of the level-line angle as a function of the two gradient differences DA = d - a, BC = b - c of a
+// pixel's 2x2 block (each in [-255, 255]): what region_grow adds to its float32 sums when it accepts the pixel,
+// cos(float(angle)) / sin(float(angle)) with the float overloads = the correctly rounded float of the double
+// function of the float radian angle.  One table per context (2 MB, L2-resident) instead of 8 bytes per pixel.
+__global__ void cssn_lut_kernel(float2* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLutN * kLutN) return;
+  const int DA = i / kLutN - 255, BC = i % kLutN - 255;
+  const int gx = DA + BC, gy = DA - BC;
+  const float a = fast_atan2_deg((float)gx, (float)-gy);
+  const float ar = (float)((double)a * VPL_DEG2RAD);
+  lut[i] = make_float2((float)cos((double)ar), (float)sin((double)ar));
+}
+void launch_cssn_lut(float2* lut, cudaStream_t st) {
+  cssn_lut_kernel<<<(kLutN * kLutN + 255) / 256, 256, 0, st>>>(lut);
 }
 
 // ---------------------------------------------------------------------------

@@ -5,12 +5,15 @@
 //   pyr[o]   B x Ho x Wo     u8      Gaussian pyramid (octave 0 = blur5(img) if blur_first)
 //   grad[o]  B x Ho x Wo     short2  Sobel (dx,dy) of pyr[o]            (LBD)
 //   scl[o]   B x Hs x Ws     u8      LSD working image: blur7 + 0.8 resize
-//   ang[o]   B x Hs x Ws     f32     level-line angle in degrees, -1024 = NOTDEF (read-only
-//                                    copy for the NFA scans)
-//   pix[o]   B x Hs x Ws     16 B    {angle bits | USED bit31, cosf, sinf, gx^2+gy^2}: one
-//                                    128-bit gather per neighbour in the region engine
+//   ang[o]   B x Hs x Ws     f32     level-line angle in degrees, -1024 = NOTDEF (read-only after ll_angle:
+//                                    region engines and NFA scans)
+//   tag[o]   B x Hs x Ws     u32     owner tag of the region engines: 0 = undefined, 0xFFFFFFFF = free, else the
+//                                    rank of the owning seed (speculative engine) / 1 = used (sequential engine)
 //   ord[o]   B x Hs x Ws     i32     pseudo-ordered seed list (defined pixels only)
-//   reg[o]   B x Hs x Ws     16 B    region scratch of the frame's engine warp
+//   reg[o]   B x Hs x Ws     8 B     region lists: an arena of 2 x Hs x Ws packed pixel coordinates (x | y << 16);
+//                                    the ordering kernel keeps its u16 bins there before the engine runs
+//   (cos, sin) of a pixel's angle come from a 511 x 511 table indexed by its two gradient differences (one per
+//   context, L2-resident), gx^2+gy^2 is recomputed from scl: no per-pixel record beyond ang and tag
 //   cand[o]  B x cap         rects   post-refine rectangles in seed order
 //   keylines B x cap x 68 B, desc B x cap x 32 B, matches B x cap x k
 #pragma once
@@ -26,20 +29,44 @@ constexpr int kBins = 1024;
 constexpr float kNotDefDeg = -1024.0f;
 constexpr uint32_t kUsedBit = 0x80000000u;
 
-// Per-pixel record of the region engine.  ang: float bits of the level-line angle
-// in degrees ([0,360]); NOTDEF is -1024.0f (bit31 set, so "not a candidate");
-// bit31 set on a defined pixel = USED.  q = gx^2+gy^2 (modgrad = sqrt(q/4)).
-struct __align__(16) Pix {
-  uint32_t ang;
-  float cs, sn;
-  uint32_t q;
+constexpr uint32_t kTagFree = 0xFFFFFFFFu;  // tag of a defined pixel no region owns
+constexpr int kLutN = 511;                  // (cos, sin) table: [DA + 255][BC + 255], DA = d - a, BC = b - c of the 2x2 block
+
+// Region scratch of a frame: B x Hs x Ws of these 8-byte units = an arena of 2 x Hs x Ws list entries (one
+// uint32 each: x | y << 16); the ordering kernel keeps its u16 bins there before the engine runs.
+struct __align__(8) RegEnt {
+  uint32_t a, b;
 };
 
-struct __align__(16) RegEnt {
-  int idx;
-  float ang;  // degrees
-  uint32_t q;
-  uint32_t pad;
+// 2x2 gradient differences of a defined pixel (x < ws-1, y < hs-1) of the scaled image
+__device__ __forceinline__ void pixel_dabc(const uint8_t* __restrict__ scl, int ws, int x, int y, int& DA, int& BC) {
+  const uint8_t* r0 = scl + (size_t)y * ws + x;
+  const int a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r0 + ws), d = __ldg(r0 + ws + 1);
+  DA = d - a;
+  BC = b - c;
+}
+// gx^2 + gy^2 of a defined pixel (modgrad = sqrt(q / 4))
+__device__ __forceinline__ int pixel_q(const uint8_t* __restrict__ scl, int ws, int x, int y) {
+  int DA, BC;
+  pixel_dabc(scl, ws, x, y, DA, BC);
+  const int gx = DA + BC, gy = DA - BC;
+  return gx * gx + gy * gy;
+}
+// (cosf, sinf) of a defined pixel's level-line angle
+__device__ __forceinline__ float2 pixel_cssn(const float2* __restrict__ lut, const uint8_t* __restrict__ scl, int ws, int x,
+                                             int y) {
+  int DA, BC;
+  pixel_dabc(scl, ws, x, y, DA, BC);
+  return __ldg(lut + (DA + 255) * kLutN + (BC + 255));
+}
+// A parked transaction of the region engine (finished, waiting for the commit pointer): where its pixel
+// lists lie in the lane's ring, what it depends on, what to do at commit.
+constexpr int kEngQ = 16;     // parked transactions per lane (power of two)
+constexpr int kEngDeps = 4;   // recorded dependencies per transaction
+struct __align__(16) EngDesc {
+  int pos, start, ext, flags;
+  int dep[kEngDeps];
+  int nd, pad0, pad1, pad2;
 };
 
 // A rectangle candidate produced by the region engine (cv lsd.cpp `struct rect`).
@@ -110,15 +137,20 @@ void launch_pyrdown(const uint8_t* src, uint8_t* dst, int w, int h, int batch, c
 void launch_sobel(const uint8_t* src, short2* grad, int w, int h, int batch, cudaStream_t st);
 void launch_scale08(const uint8_t* src, uint8_t* dst, int w, int h, int ws, int hs, int batch,
                     cudaStream_t st);
-void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, unsigned int* maxq, int ws, int hs,
+void launch_ll_angle(const uint8_t* scl, float* ang, uint32_t* tag, unsigned int* maxq, int ws, int hs,
                      int batch, double rho, cudaStream_t st);
+// (cosf, sinf) of the level-line angle for every pair of gradient differences: kLutN x kLutN float2
+void launch_cssn_lut(float2* lut, cudaStream_t st);
 // scratch: >= 2*ws*hs bytes per frame, frames `scratch_stride` bytes apart (the region
 // scratch `reg` is free until the engine runs and is used for this)
 void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, void* scratch,
                   size_t scratch_stride, int ws, int hs, int batch, double rho, cudaStream_t st);
 struct EngineOct {
-  Pix* pix;          // B x hs x ws
-  const float* ang;  // B x hs x ws (NFA kernel)
+  uint32_t* tag;     // B x hs x ws owner tags: 0 = undefined, 0xFFFFFFFF = free
+  const uint8_t* scl;  // B x hs x ws scaled image (gradient differences of accepted pixels)
+  EngDesc* desc;     // B x 32 x kEngQ (speculative engine)
+  RectCand* rects;   // B x 32 x kEngQ (speculative engine)
+  const float* ang;  // B x hs x ws level-line angle in degrees
   const int* ord;    // B x hs x ws
   const int* n_ord;  // B
   RegEnt* reg;       // B x hs x ws
@@ -137,8 +169,17 @@ struct EngineArgs {
   int* overflow;  // set to 1 if a frame produced more than cand_cap candidates
   const double* lgam;  // lgam[m] = log_gamma((double)m) for the NFA kernel
   int lgam_n;
+  int ring_cap;        // list entries per lane of the speculative engine (0 = 2*ws*hs/32; tests force small values)
+  const float2* lut;   // (cosf, sinf) table, kLutN x kLutN
 };
+// Two region engines with identical results (both bit-equal to the sequential CPU algorithm):
+//   lsd_engine.cu (default): one warp per frame keeps the sequential seed order and spends its lanes on the
+//     order-free work inside a step;
+//   lsd_engine_spec.cu (opt-in, batches of at most kSpecMaxBatch frames): one warp per frame, 32 speculative seeds
+//     in flight, committed in seed order.
 void launch_region_engine(const EngineArgs& a, cudaStream_t st);
+void launch_region_engine_spec(const EngineArgs& a, cudaStream_t st);
+constexpr int kSpecMaxBatch = 1024;
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st);
 struct PackArgs {
   const RectCand* cand[kMaxOctaves];
