@@ -29,12 +29,15 @@ struct OctBuf {
   short2* grad = nullptr;
   uint8_t* scl = nullptr;
   float* ang = nullptr;
-  uint32_t* tag = nullptr;      // owner tags of the region engines
-  EngDesc* eng_desc = nullptr;  // parked transactions of the speculative region engine, spec_frames x 32 x kEngQ
+  Pix* pix = nullptr;           // 16-byte engine record per scaled pixel
+  // speculative region engine (allocated at its first use, for kSpecMaxBatch frames)
+  uint32_t* spec_tag = nullptr;
+  uint32_t* spec_arena = nullptr;
+  EngDesc* eng_desc = nullptr;
   RectCand* eng_rects = nullptr;
   int* ord = nullptr;
   int* n_ord = nullptr;
-  RegEnt* reg = nullptr;
+  uint32_t* reg = nullptr;      // region list of the default engine (4 B per scaled pixel); u16 bins of the ordering kernel before
   RectCand* cand = nullptr;
   int* n_cand = nullptr;
   unsigned int* maxq = nullptr;
@@ -158,6 +161,7 @@ struct VplContext {
   double* d_vp_lambda = nullptr;
   int engine_ring_cap = 0;  // list entries per lane of the speculative region engine, 0 = 2*ws*hs/32 (vpl_debug_set_engine_ring_cap)
   int engine_kind = 0;      // 0 = warp-cooperative engine (lsd_engine.cu), 1 = speculative engine (lsd_engine_spec.cu)
+  float* d_fdesc = nullptr;      // float descriptors of vpl_lbd_compute_float_batch (allocated at its first use)
   float2* d_cssn_lut = nullptr;  // (cosf, sinf) of the level-line angle by gradient differences, kLutN x kLutN
   int prev_slot = -1;  // slot of the previously submitted batch (for chaining)
   bool have_prev = false;
@@ -300,8 +304,8 @@ void fill_engine_args(VplContext* c, Slot& s, EngineArgs& a) {
     int wo, ho, ws, hs;
     octave_geom(s.w, s.h, o, wo, ho, ws, hs);
     EngineOct& e = a.oct[o];
-    e.ang = s.oct[o].ang; e.ord = s.oct[o].ord; e.n_ord = s.oct[o].n_ord;
-    e.tag = s.oct[o].tag; e.scl = s.oct[o].scl; e.desc = s.oct[o].eng_desc; e.rects = s.oct[o].eng_rects;
+    e.ang = s.oct[o].ang; e.ord = s.oct[o].ord; e.n_ord = s.oct[o].n_ord; e.pix = s.oct[o].pix;
+    e.tag = s.oct[o].spec_tag; e.arena = s.oct[o].spec_arena; e.desc = s.oct[o].eng_desc; e.rects = s.oct[o].eng_rects;
     e.reg = s.oct[o].reg; e.cand = s.oct[o].cand; e.n_cand = s.oct[o].n_cand;
     e.ws = ws; e.hs = hs;
     e.log_nt = 5 * (log10((double)ws) + log10((double)hs)) / 2 + log10(11.0);
@@ -326,14 +330,14 @@ void run_lsd(VplContext* c, Slot& s) {
   {
     StageTimer t(c, s, VPL_STAGE_ANGLE);
     for (int o = 0; o < s.num_octaves; ++o)
-      launch_ll_angle(s.oct[o].scl, s.oct[o].ang, s.oct[o].tag, s.oct[o].maxq, ws[o], hs[o], s.n, c->lc.rho, s.stream);
+      launch_ll_angle(s.oct[o].scl, s.oct[o].ang, s.oct[o].pix, c->d_cssn_lut, s.oct[o].maxq, ws[o], hs[o], s.n, c->lc.rho, s.stream);
     t.launches(s.num_octaves);
   }
   {
     StageTimer t(c, s, VPL_STAGE_ORDER);
     for (int o = 0; o < s.num_octaves; ++o)
       launch_order(s.oct[o].scl, s.oct[o].maxq, s.oct[o].ord, s.oct[o].n_ord, s.oct[o].reg,
-                   (size_t)ws[o] * hs[o] * sizeof(RegEnt), ws[o], hs[o], s.n, c->lc.rho, s.stream);
+                   (size_t)ws[o] * hs[o] * sizeof(uint32_t), ws[o], hs[o], s.n, c->lc.rho, s.stream);
     t.launches(s.num_octaves);
   }
   EngineArgs a;
@@ -342,7 +346,7 @@ void run_lsd(VplContext* c, Slot& s) {
     StageTimer t(c, s, VPL_STAGE_REGION);
     // default: the warp-cooperative engine; vpl_debug_set_engine(ctx, 1): the speculative one (its parking buffers
     // are sized for kSpecMaxBatch frames)
-    if (c->engine_kind == 1 && s.n <= kSpecMaxBatch) launch_region_engine_spec(a, s.stream);
+    if (c->engine_kind == 1 && s.n <= kSpecMaxBatch && s.oct[0].spec_tag) launch_region_engine_spec(a, s.stream);
     else launch_region_engine(a, s.stream);
     t.launches(1);
   }
@@ -838,12 +842,13 @@ void vpl_destroy(VplContext* c) {
   cudaFree(c->d_mapx); cudaFree(c->d_mapy); cudaFree(c->d_wtab);
   cudaFree(c->d_lgam);
   cudaFree(c->d_cssn_lut);
+  cudaFree(c->d_fdesc);
   cudaFree(c->d_vp_lambda);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
-      cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.tag); cudaFree(b.eng_desc); cudaFree(b.eng_rects); cudaFree(b.ord);
+      cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.spec_tag); cudaFree(b.spec_arena); cudaFree(b.eng_desc); cudaFree(b.eng_rects); cudaFree(b.ord);
       cudaFree(b.n_ord); cudaFree(b.reg); cudaFree(b.cand); cudaFree(b.n_cand); cudaFree(b.maxq);
     }
     cudaFree(s.d_kl); cudaFree(s.d_counts); cudaFree(s.d_desc); cudaFree(s.d_match); cudaFree(s.d_last_desc);
@@ -951,12 +956,7 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
       if (!cfg->lsd_path) continue;  // EDLines / KLT front end only: pyramid image + Sobel pair of octave 0 suffice
       CKC(dmalloc(&b.scl, B * So));
       CKC(dmalloc(&b.ang, B * So));
-      CKC(dmalloc(&b.tag, B * So));
-      {  // the speculative engine only ever runs on batches of at most kSpecMaxBatch frames
-        const size_t sb = std::min<size_t>(B, (size_t)kSpecMaxBatch);
-        CKC(dmalloc(&b.eng_desc, sb * 32 * kEngQ));
-        CKC(dmalloc(&b.eng_rects, sb * 32 * kEngQ));
-      }
+      CKC(dmalloc(&b.pix, B * So));
       CKC(dmalloc(&b.ord, B * So));
       CKC(dmalloc(&b.reg, B * So));
       CKC(dmalloc(&b.n_ord, B));
@@ -1301,19 +1301,17 @@ int vpl_lbd_compute_float_batch(VplContext* c, const uint8_t* const* imgs, int n
   if (!c) return VPL_E_INVALID;
   if (!keylines || !counts || !fdesc) return fail(c, VPL_E_INVALID, "null argument");
   const size_t mc = (size_t)c->cfg.max_lines;
-  // float rows live in the octave-0 region scratch (16 B per scaled pixel per frame), which is idle here
   std::vector<uint8_t> bytes((size_t)std::max(n, 1) * cap * 32);
-  int wo, ho, ws, hs;
-  octave_geom(w, h, 0, wo, ho, ws, hs);
-  if (mc * 72 * sizeof(float) > (size_t)ws * hs * sizeof(RegEnt))
-    return fail(c, VPL_E_CAPACITY, "max_lines too large for the float-descriptor scratch at this image size");
+  if (!c->d_fdesc) {  // 72 floats per line: a scratch of its own, allocated at the first use of this call
+    CK(c, cudaSetDevice(c->cfg.device));
+    CK(c, dmalloc(&c->d_fdesc, (size_t)c->cfg.max_batch * mc * 72));
+  }
   // run the byte path first (validates arguments, uploads, builds the pyramid), then re-run LBD with the float sink
   int r = vpl_lbd_compute_batch(c, imgs, n, w, h, stride, keylines, counts, cap, bytes.data());
   if (r) return r;
   if (n == 0) return VPL_OK;
   Slot& s = c->slots[0];
-  // frames are `ws*hs*sizeof(RegEnt)` apart in the scratch, rows mc*72 floats: use a compact stride of mc*72 floats
-  float* d_f = reinterpret_cast<float*>(s.oct[0].reg);
+  float* d_f = c->d_fdesc;
   run_lbd(c, s, s.num_octaves, d_f);
   std::vector<float> tmp((size_t)n * mc * 72);
   CK(c, cudaMemcpyAsync(tmp.data(), d_f, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
@@ -2176,10 +2174,10 @@ int vpl_debug_stage(VplContext* c, int which, const uint8_t* img, int w, int h, 
       launch_scale08(s.oct[0].pyr, s.oct[0].scl, w, h, ws, hs, 1, s.stream);
       c->launches += 1;
       if (which == 3) { src = s.oct[0].scl; bytes = (size_t)ws * hs; *out_w = ws; *out_h = hs; break; }
-      launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].tag, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
+      launch_ll_angle(s.oct[0].scl, s.oct[0].ang, s.oct[0].pix, c->d_cssn_lut, s.oct[0].maxq, ws, hs, 1, c->lc.rho, s.stream);
       c->launches += 1;
       if (which == 4) { src = s.oct[0].ang; bytes = (size_t)ws * hs * sizeof(float); *out_w = ws; *out_h = hs; break; }
-      launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, s.oct[0].reg, (size_t)ws * hs * sizeof(RegEnt), ws,
+      launch_order(s.oct[0].scl, s.oct[0].maxq, s.oct[0].ord, s.oct[0].n_ord, s.oct[0].reg, (size_t)ws * hs * sizeof(uint32_t), ws,
                    hs, 1, c->lc.rho, s.stream);
       c->launches += 1;
       CK(c, cudaMemcpyAsync(&n_ord, s.oct[0].n_ord, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -2239,6 +2237,25 @@ int vpl_debug_set_engine_ring_cap(VplContext* c, int entries_per_lane) {
 int vpl_debug_set_engine(VplContext* c, int kind) {
   if (!c) return VPL_E_INVALID;
   if (kind < 0 || kind > 1) return fail(c, VPL_E_INVALID, "engine kind must be 0 (default, warp-cooperative) or 1 (speculative)");
+  if (kind == 1) {
+    if (!c->cfg.lsd_path) return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0");
+    CK(c, cudaSetDevice(c->cfg.device));
+    // the speculative engine keeps owner tags, a two-list arena and its parking buffers per frame: allocated here,
+    // for batches of at most kSpecMaxBatch frames
+    const size_t sb = std::min<size_t>((size_t)c->cfg.max_batch, (size_t)kSpecMaxBatch);
+    const size_t P0 = (size_t)c->cfg.max_width * c->cfg.max_height;
+    for (Slot& s : c->slots)
+      for (int o = 0; o < c->cfg.max_octaves; ++o) {
+        OctBuf& b = s.oct[o];
+        if (b.spec_tag) continue;
+        size_t Po = (P0 >> (2 * o)) + 64;
+        size_t So = (size_t)((double)Po * 0.64) + 2 * (size_t)(c->cfg.max_width + c->cfg.max_height) + 64;
+        CK(c, dmalloc(&b.spec_tag, sb * So));
+        CK(c, dmalloc(&b.spec_arena, sb * So * 2));
+        CK(c, dmalloc(&b.eng_desc, sb * 32 * kEngQ));
+        CK(c, dmalloc(&b.eng_rects, sb * 32 * kEngQ));
+      }
+  }
   c->engine_kind = kind;
   return VPL_OK;
 }

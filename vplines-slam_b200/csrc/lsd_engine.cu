@@ -11,9 +11,9 @@
 // sequential by definition (first-come pixel ownership, running float32 mean
 // angle, double sums in list order), so the warp keeps exactly that order and
 // uses its 32 lanes for everything that is order-free:
-//   * seed scan: 32 ordered seeds per step, one tag gather each;
-//   * growth: the 8 neighbours of up to four FIFO pixels are gathered by the 32 lanes (4-byte
-//     angle + 4-byte owner tag each; candidates also fetch their (cos, sin) from the table);
+//   * seed scan: 32 ordered seeds per step, one gather each;
+//   * growth: the 8 neighbours of up to four FIFO pixels are gathered with one 128-bit load per lane
+//     (angle with the used flag in its sign bit, cos, sin, gradient differences);
 //     acceptance is then resolved in lane order, which is exactly the sequential (FIFO, yy, xx) order;
 //   * rectangle sums: per-entry products in parallel, the additions themselves in
 //     list order (shuffle broadcast) so the double results equal the sequential
@@ -32,10 +32,7 @@ namespace vpl {
 constexpr int RING = 256;  // per-warp FIFO window kept in shared memory
 
 struct Eng {
-  const float* ang;    // level-line angle in degrees per pixel (read-only)
-  uint32_t* tag;       // 0 = undefined, 0xFFFFFFFF = free, 1 = used
-  const uint8_t* scl;  // scaled image: gradient differences of a pixel (-> q, (cos, sin) table)
-  const float2* lut;   // (cosf, sinf) by gradient differences
+  Pix* pix;            // {angle bits | used bit31, cosf, sinf, packed gradient differences} per pixel
   uint32_t* reg;       // region list: x | y << 16 per entry
   int* ring;  // shared memory, RING ints
   double* bc;    // shared memory, 32 doubles  } broadcast buffers for the in-order sums
@@ -77,10 +74,10 @@ __device__ __forceinline__ bool aligned_rad(double a, double theta, double prec)
 __device__ __noinline__ int region_grow(const Eng& e, int seed_xy, float seed_deg, double prec,
                                         double* reg_angle_out) {
   const int lane = e.lane, ws = e.ws, hs = e.hs;
-  uint32_t* tag = e.tag;
-  // seed: defined and currently free
+  Pix* pix = e.pix;
+  // seed: defined and currently unused
   if (lane == 0) {
-    tag[(seed_xy >> 16) * ws + (seed_xy & 0xffff)] = 1u;
+    pix[(seed_xy >> 16) * ws + (seed_xy & 0xffff)].ang = __float_as_uint(seed_deg) | kUsedBit;
     e.reg[0] = (uint32_t)seed_xy;
     e.ring[0] = seed_xy;
   }
@@ -111,8 +108,8 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed_xy, float seed_de
     if (take > 4) take = 4;
     const bool act = (g < take);
     int nidx = -1, nxy = 0;
-    uint32_t tg = 0u;
-    float adeg = 0.f, cs = 0.f, sn = 0.f;
+    uint32_t ab = 0xffffffffu;
+    float cs = 0.f, sn = 0.f;
     if (act) {
       int j = i + g;
       int cur = (n - j <= RING) ? e.ring[j & (RING - 1)] : (int)e.reg[j];  // packed x | y << 16
@@ -120,15 +117,12 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed_xy, float seed_de
       if (nx >= 0 && nx < ws && ny >= 0 && ny < hs) {
         nidx = ny * ws + nx;
         nxy = nx | (ny << 16);
-        tg = tag[nidx];
-        adeg = __ldg(e.ang + nidx);
+        const Pix p = pix[nidx];  // one 128-bit gather: angle, used flag and what an acceptance adds to the sums
+        ab = p.ang; cs = p.cs; sn = p.sn;
       }
     }
-    bool cand = (nidx >= 0) && tg == kTagFree;
-    if (cand) {  // what an acceptance adds to the float32 sums: fetched by every candidate lane at once
-      const float2 v = pixel_cssn(e.lut, e.scl, ws, nxy & 0xffff, nxy >> 16);
-      cs = v.x; sn = v.y;
-    }
+    bool cand = (nidx >= 0) && !(ab & kUsedBit);
+    const float adeg = __uint_as_float(ab);
     // resolve acceptances in lane order == sequential order
     while (true) {
       bool al = false;
@@ -143,7 +137,7 @@ __device__ __noinline__ int region_grow(const Eng& e, int seed_xy, float seed_de
       int f = __ffs(m) - 1;
       int accxy = __shfl_sync(0xffffffffu, nxy, f);
       if (lane == f) {
-        tag[nidx] = 1u;
+        pix[nidx].ang = ab | kUsedBit;
         e.reg[n] = (uint32_t)nxy;
         e.ring[n & (RING - 1)] = nxy;
       }
@@ -179,7 +173,7 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
     if (j < n) {
       const uint32_t r = e.reg[j];
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
-      wt = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
+      wt = sqrt((double)dabc_q(e.pix[py * e.ws + px].dabc) / 4.0);
       wx = (double)px * wt;
       wy = (double)py * wt;
     }
@@ -215,7 +209,7 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
     if (j < n) {
       const uint32_t r = e.reg[j];
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
-      double weight = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
+      double weight = sqrt((double)dabc_q(e.pix[py * e.ws + px].dabc) / 4.0);
       double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * weight;
       t2 = dx * dx * weight;
@@ -301,7 +295,7 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
       const uint32_t r = e.reg[j];
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
       in = !(dist_sq_d(xc, yc, (double)px, (double)py) > radSq);
-      if (!in) e.tag[py * e.ws + px] = kTagFree;
+      if (!in) e.pix[py * e.ws + px].ang &= ~kUsedBit;
     }
     n_in += __popc(__ballot_sync(0xffffffffu, in));
   }
@@ -369,7 +363,7 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
   const uint32_t r0 = e.reg[0];
   int xc_i = (int)(r0 & 0xffffu), yc_i = (int)(r0 >> 16);
   double xc = (double)xc_i, yc = (double)yc_i;
-  const float seed_deg = e.ang[yc_i * e.ws + xc_i];
+  const float seed_deg = __uint_as_float(e.pix[yc_i * e.ws + xc_i].ang & ~kUsedBit);
   double ang_c = (double)seed_deg * VPL_DEG2RAD;
   double sum = 0, s_sum = 0;
   int cnt = 0;
@@ -380,10 +374,11 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
     if (j < n) {
       const uint32_t r = e.reg[j];
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
-      e.tag[py * e.ws + px] = kTagFree;
+      const uint32_t au = e.pix[py * e.ws + px].ang & ~kUsedBit;
+      e.pix[py * e.ws + px].ang = au;
       if (dist_d(xc, yc, (double)px, (double)py) < rec.width) {
         flag = true;
-        ang_d = angle_diff_signed_d((double)e.ang[py * e.ws + px] * VPL_DEG2RAD, ang_c);
+        ang_d = angle_diff_signed_d((double)__uint_as_float(au) * VPL_DEG2RAD, ang_c);
         sq = ang_d * ang_d;
       }
     }
@@ -419,11 +414,8 @@ region_engine_kernel(EngineArgs A) {
   const EngineOct& O = A.oct[blockIdx.y];
   const size_t npx = (size_t)O.ws * O.hs;
   Eng e;
-  e.ang = O.ang + (size_t)f * npx;
-  e.tag = O.tag + (size_t)f * npx;
-  e.scl = O.scl + (size_t)f * npx;
-  e.lut = A.lut;
-  e.reg = reinterpret_cast<uint32_t*>(O.reg + (size_t)f * npx);
+  e.pix = O.pix + (size_t)f * npx;
+  e.reg = O.reg + (size_t)f * npx;
   e.ring = s_ring;
   e.bc = s_bc;
   e.bc2 = s_bc2;
@@ -440,17 +432,18 @@ region_engine_kernel(EngineArgs A) {
   for (int base = 0; base < n_ord; base += 32) {
     int my = (base + lane < n_ord) ? ord[base + lane] : -1;
     bool free_ = false;
-    if (my >= 0) free_ = e.tag[my] == kTagFree;
+    if (my >= 0) free_ = !(e.pix[my].ang & kUsedBit);
     unsigned todo = __ballot_sync(0xffffffffu, free_);
     while (todo) {
       int l = __ffs(todo) - 1;
       todo &= todo - 1;
       int seed = __shfl_sync(0xffffffffu, my, l);
       // the seed may have been absorbed by a region grown earlier in this chunk
-      if (e.tag[seed] != kTagFree) continue;
+      const uint32_t sa = e.pix[seed].ang;
+      if (sa & kUsedBit) continue;
       const int sy = seed / e.ws, sx = seed - sy * e.ws;
       double reg_angle;
-      int n = region_grow(e, sx | (sy << 16), e.ang[seed], prec, &reg_angle);
+      int n = region_grow(e, sx | (sy << 16), __uint_as_float(sa), prec, &reg_angle);
       if (n < O.min_reg_size) continue;
       RectCand rec;
       region2rect(e, n, reg_angle, prec, p, rec);

@@ -47,6 +47,8 @@
 #include "vpl_common.cuh"
 #include "vpl_sincos.cuh"
 
+#include <algorithm>
+
 namespace vpl {
 
 namespace {
@@ -63,8 +65,7 @@ enum { DF_CAND = 1, DF_VAL = 2, DF_DEAD = 4 };
 struct Eng {
   uint32_t* tag;      // owner tag per pixel
   const float* ang;   // level-line angle in degrees per pixel (read-only)
-  const uint8_t* scl; // scaled image: gradient differences of a pixel (-> q, (cos, sin) table)
-  const float2* lut;  // (cosf, sinf) by gradient differences
+  const Pix* pix;     // engine records: (cosf, sinf) and the packed gradient differences of a pixel
   uint32_t* arena;    // 2*ws*hs list entries (x | y << 16)
   EngDesc* desc;      // 32 lanes x kEngQ parked descriptors
   RectCand* rects;    // 32 lanes x kEngQ staged rectangles
@@ -167,7 +168,7 @@ __device__ __noinline__ void region2rect(const Eng& e, const ListRef& L, int off
     if (j < n) {
       const uint32_t r = L.at(off + j);
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
-      wt = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
+      wt = sqrt((double)dabc_q(e.pix[py * e.ws + px].dabc) / 4.0);
       wx = (double)px * wt;
       wy = (double)py * wt;
     }
@@ -201,7 +202,7 @@ __device__ __noinline__ void region2rect(const Eng& e, const ListRef& L, int off
     if (j < n) {
       const uint32_t r = L.at(off + j);
       int px = (int)(r & 0xffffu), py = (int)(r >> 16);
-      double weight = sqrt((double)pixel_q(e.scl, e.ws, px, py) / 4.0);
+      double weight = sqrt((double)dabc_q(e.pix[py * e.ws + px].dabc) / 4.0);
       double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * weight;
       t2 = dx * dx * weight;
@@ -656,9 +657,8 @@ region_engine_spec_kernel(EngineArgs A) {
   Eng e;
   e.tag = O.tag + (size_t)f * npx;
   e.ang = O.ang + (size_t)f * npx;
-  e.scl = O.scl + (size_t)f * npx;
-  e.lut = A.lut;
-  e.arena = reinterpret_cast<uint32_t*>(O.reg + (size_t)f * npx);
+  e.pix = O.pix + (size_t)f * npx;
+  e.arena = O.arena + (size_t)f * 2 * npx;
   e.desc = O.desc + (size_t)f * 32 * kEngQ;
   e.rects = O.rects + (size_t)f * 32 * kEngQ;
   e.ord = O.ord + (size_t)f * npx;
@@ -964,9 +964,9 @@ region_engine_spec_kernel(EngineArgs A) {
             const int ax = cx + (kk % 3 - 1), ay = cy + (kk / 3 - 1);
             lbase[(g_base + n) & lmask] = (uint32_t)ax | ((uint32_t)ay << 16);
             ++n;
-            const float2 cs = pixel_cssn(e.lut, e.scl, e.ws, ax, ay);
-            sumdx += cs.x;
-            sumdy += cs.y;
+            const Pix pr = e.pix[nidx[k]];
+            sumdx += pr.cs;
+            sumdy += pr.sn;
             reg_deg = fast_atan2_deg(sumdy, sumdx);
           }
         }
@@ -1055,7 +1055,17 @@ region_engine_spec_kernel(EngineArgs A) {
   if (lane == 0) O.n_cand[f] = c.n_cand < A.cand_cap ? c.n_cand : A.cand_cap;
 }
 
+// owner tags of a batch from its angle plane: 0 = undefined, FREE otherwise
+__global__ void spec_tag_init_kernel(const float* __restrict__ ang, uint32_t* __restrict__ tag, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    tag[i] = ang[i] == kNotDefDeg ? 0u : kTagFree;
+}
+
 void launch_region_engine_spec(const EngineArgs& a, cudaStream_t st) {
+  for (int o = 0; o < a.num_octaves; ++o) {
+    const size_t n = (size_t)a.batch * a.oct[o].ws * a.oct[o].hs;
+    spec_tag_init_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(a.oct[o].ang, a.oct[o].tag, n);
+  }
   dim3 grid(a.batch, a.num_octaves);
   region_engine_spec_kernel<<<grid, 32, 0, st>>>(a);
 }

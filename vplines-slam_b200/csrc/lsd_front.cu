@@ -20,14 +20,15 @@ __device__ __forceinline__ void grad2x2(const uint8_t* __restrict__ s, int ws, i
 }
 
 // ---------------------------------------------------------------------------
-// K3.  Four pixels per thread.  Writes the angle (4 B) and the owner tag (4 B) of every pixel and reduces
-// max(gx^2+gy^2) per frame with one atomicMax per warp.  Algorithmic bytes: read S, write 8 S.
+// K3.  Four pixels per thread.  Writes the angle (4 B) and the 16-byte engine record of every pixel and reduces
+// max(gx^2+gy^2) per frame with one atomicMax per warp.  Algorithmic bytes: read S, write 8 S; the
+// record is a design cost on top of that (20 S written).
 // ---------------------------------------------------------------------------
 constexpr int LLA_PX = 4;  // pixels per thread
 
 __global__ void __launch_bounds__(256)
-ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, uint32_t* __restrict__ tag,
-                unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
+ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* __restrict__ pix,
+                const float2* __restrict__ lut, unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
   // pixel k of a thread is x0 + 32 k: every load/store instruction of the warp is contiguous
   const int x0 = blockIdx.x * (32 * LLA_PX) + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -49,8 +50,10 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, uint32
       const int x = x0 + 32 * k;
       if (x >= ws) break;
       float a = kNotDefDeg;
+      uint32_t w = 0u;
       if (x < ws - 1 && has_next_row) {
         int DA = pd[k] - pa[k], BC = pb[k] - pc[k];
+        w = (uint32_t)(DA + 255) | ((uint32_t)(BC + 255) << 16);
         int gx = DA + BC, gy = DA - BC;
         unsigned int qq = (unsigned int)(gx * gx + gy * gy);
         // sqrt(q/4) <= rho = 5.2262... for every q < 100 (sqrt(25) = 5): skip the FP64 work there;
@@ -62,7 +65,14 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, uint32
         }
       }
       ang[fo + (size_t)y * ws + x] = a;
-      tag[fo + (size_t)y * ws + x] = (a == kNotDefDeg) ? 0u : kTagFree;
+      // engine record: (cos, sin) of the angle from the context's table (no FP64 work here)
+      Pix u;
+      u.ang = __float_as_uint(a); u.cs = 0.f; u.sn = 0.f; u.dabc = w;
+      if (a != kNotDefDeg) {
+        const float2 v = dabc_cssn(lut, w);
+        u.cs = v.x; u.sn = v.y;
+      }
+      pix[fo + (size_t)y * ws + x] = u;
     }
   }
   // warp max -> one atomic per warp
@@ -71,10 +81,10 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, uint32
   if ((threadIdx.x & 31) == 0 && q > 0) atomicMax(maxq + blockIdx.z, q);
 }
 
-void launch_ll_angle(const uint8_t* scl, float* ang, uint32_t* tag, unsigned int* maxq, int ws, int hs,
-                     int batch, double rho, cudaStream_t st) {
+void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, const float2* lut, unsigned int* maxq,
+                     int ws, int hs, int batch, double rho, cudaStream_t st) {
   dim3 grid((ws + 32 * LLA_PX - 1) / (32 * LLA_PX), (hs + 7) / 8, batch);
-  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, tag, maxq, ws, hs, rho);
+  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, lut, maxq, ws, hs, rho);
 }
 
 // (cosf, sinf) of the level-line angle as a function of the two gradient differences DA = d - a, BC = b - c of a

@@ -5,15 +5,18 @@
 //   pyr[o]   B x Ho x Wo     u8      Gaussian pyramid (octave 0 = blur5(img) if blur_first)
 //   grad[o]  B x Ho x Wo     short2  Sobel (dx,dy) of pyr[o]            (LBD)
 //   scl[o]   B x Hs x Ws     u8      LSD working image: blur7 + 0.8 resize
-//   ang[o]   B x Hs x Ws     f32     level-line angle in degrees, -1024 = NOTDEF (read-only after ll_angle:
-//                                    region engines and NFA scans)
-//   tag[o]   B x Hs x Ws     u32     owner tag of the region engines: 0 = undefined, 0xFFFFFFFF = free, else the
-//                                    rank of the owning seed (speculative engine) / 1 = used (sequential engine)
+//   ang[o]   B x Hs x Ws     f32     level-line angle in degrees ([0, 360]), -1024 = NOTDEF (read-only: NFA scans,
+//                                    the speculative engine)
+//   pix[o]   B x Hs x Ws     16 B    engine record {angle bits | USED bit31, cosf, sinf, packed gradient differences}:
+//                                    ONE 128-bit gather per neighbour and one level of dependent loads per growth
+//                                    step (measured: splitting it into 4-byte planes costs more sectors and more
+//                                    load levels than it saves bytes)
 //   ord[o]   B x Hs x Ws     i32     pseudo-ordered seed list (defined pixels only)
-//   reg[o]   B x Hs x Ws     8 B     region lists: an arena of 2 x Hs x Ws packed pixel coordinates (x | y << 16);
+//   reg[o]   B x Hs x Ws     u32     region list of the frame's engine warp: packed pixel coordinates (x | y << 16);
 //                                    the ordering kernel keeps its u16 bins there before the engine runs
-//   (cos, sin) of a pixel's angle come from a 511 x 511 table indexed by its two gradient differences (one per
-//   context, L2-resident), gx^2+gy^2 is recomputed from scl: no per-pixel record beyond ang and tag
+//   (cos, sin) of a pixel's angle come from a 511 x 511 table indexed by the two differences (one per context,
+//   2 MB, L2-resident), looked up once per pixel by ll_angle (no FP64 trigonometry per pixel); the region list
+//   carries coordinates only (round 1: 16 bytes per entry)
 //   cand[o]  B x cap         rects   post-refine rectangles in seed order
 //   keylines B x cap x 68 B, desc B x cap x 32 B, matches B x cap x k
 #pragma once
@@ -27,38 +30,30 @@ namespace vpl {
 constexpr int kMaxOctaves = 4;
 constexpr int kBins = 1024;
 constexpr float kNotDefDeg = -1024.0f;
-constexpr uint32_t kUsedBit = 0x80000000u;
 
-constexpr uint32_t kTagFree = 0xFFFFFFFFu;  // tag of a defined pixel no region owns
-constexpr int kLutN = 511;                  // (cos, sin) table: [DA + 255][BC + 255], DA = d - a, BC = b - c of the 2x2 block
-
-// Region scratch of a frame: B x Hs x Ws of these 8-byte units = an arena of 2 x Hs x Ws list entries (one
-// uint32 each: x | y << 16); the ordering kernel keeps its u16 bins there before the engine runs.
-struct __align__(8) RegEnt {
-  uint32_t a, b;
+constexpr uint32_t kUsedBit = 0x80000000u;   // ang plane: sign bit of a defined angle = used
+// Per-pixel record of the default region engine.  ang: float bits of the level-line angle in degrees ([0,360]);
+// NOTDEF is -1024.0f (bit31 set, so "not a candidate"); bit31 set on a defined pixel = USED.
+// dabc = (DA + 255) | (BC + 255) << 16, the pixel's gradient differences (gx^2+gy^2 = modgrad^2 * 4).
+struct __align__(16) Pix {
+  uint32_t ang;
+  float cs, sn;
+  uint32_t dabc;
 };
+constexpr uint32_t kTagFree = 0xFFFFFFFFu;   // speculative engine's owner tags: a defined pixel no region owns
+constexpr int kLutN = 511;                   // (cos, sin) table: [DA + 255][BC + 255], DA = d - a, BC = b - c of the 2x2 block
 
-// 2x2 gradient differences of a defined pixel (x < ws-1, y < hs-1) of the scaled image
-__device__ __forceinline__ void pixel_dabc(const uint8_t* __restrict__ scl, int ws, int x, int y, int& DA, int& BC) {
-  const uint8_t* r0 = scl + (size_t)y * ws + x;
-  const int a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r0 + ws), d = __ldg(r0 + ws + 1);
-  DA = d - a;
-  BC = b - c;
-}
-// gx^2 + gy^2 of a defined pixel (modgrad = sqrt(q / 4))
-__device__ __forceinline__ int pixel_q(const uint8_t* __restrict__ scl, int ws, int x, int y) {
-  int DA, BC;
-  pixel_dabc(scl, ws, x, y, DA, BC);
+// gx^2 + gy^2 from the packed gradient differences (modgrad = sqrt(q / 4))
+__device__ __forceinline__ int dabc_q(uint32_t w) {
+  const int DA = (int)(w & 0xffffu) - 255, BC = (int)(w >> 16) - 255;
   const int gx = DA + BC, gy = DA - BC;
   return gx * gx + gy * gy;
 }
-// (cosf, sinf) of a defined pixel's level-line angle
-__device__ __forceinline__ float2 pixel_cssn(const float2* __restrict__ lut, const uint8_t* __restrict__ scl, int ws, int x,
-                                             int y) {
-  int DA, BC;
-  pixel_dabc(scl, ws, x, y, DA, BC);
-  return __ldg(lut + (DA + 255) * kLutN + (BC + 255));
+// (cosf, sinf) of the level-line angle from the packed gradient differences
+__device__ __forceinline__ float2 dabc_cssn(const float2* __restrict__ lut, uint32_t w) {
+  return __ldg(lut + (w & 0xffffu) * kLutN + (w >> 16));
 }
+
 // A parked transaction of the region engine (finished, waiting for the commit pointer): where its pixel
 // lists lie in the lane's ring, what it depends on, what to do at commit.
 constexpr int kEngQ = 16;     // parked transactions per lane (power of two)
@@ -137,8 +132,8 @@ void launch_pyrdown(const uint8_t* src, uint8_t* dst, int w, int h, int batch, c
 void launch_sobel(const uint8_t* src, short2* grad, int w, int h, int batch, cudaStream_t st);
 void launch_scale08(const uint8_t* src, uint8_t* dst, int w, int h, int ws, int hs, int batch,
                     cudaStream_t st);
-void launch_ll_angle(const uint8_t* scl, float* ang, uint32_t* tag, unsigned int* maxq, int ws, int hs,
-                     int batch, double rho, cudaStream_t st);
+void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, const float2* lut, unsigned int* maxq,
+                     int ws, int hs, int batch, double rho, cudaStream_t st);
 // (cosf, sinf) of the level-line angle for every pair of gradient differences: kLutN x kLutN float2
 void launch_cssn_lut(float2* lut, cudaStream_t st);
 // scratch: >= 2*ws*hs bytes per frame, frames `scratch_stride` bytes apart (the region
@@ -146,14 +141,15 @@ void launch_cssn_lut(float2* lut, cudaStream_t st);
 void launch_order(const uint8_t* scl, const unsigned int* maxq, int* ord, int* n_ord, void* scratch,
                   size_t scratch_stride, int ws, int hs, int batch, double rho, cudaStream_t st);
 struct EngineOct {
-  uint32_t* tag;     // B x hs x ws owner tags: 0 = undefined, 0xFFFFFFFF = free
-  const uint8_t* scl;  // B x hs x ws scaled image (gradient differences of accepted pixels)
-  EngDesc* desc;     // B x 32 x kEngQ (speculative engine)
-  RectCand* rects;   // B x 32 x kEngQ (speculative engine)
+  Pix* pix;          // B x hs x ws engine records
+  uint32_t* tag;     // speculative engine only: kSpecMaxBatch x hs x ws owner tags (0 = undefined, 0xFFFFFFFF = free)
+  uint32_t* arena;   // speculative engine only: kSpecMaxBatch x 2 x hs x ws list entries
+  EngDesc* desc;     // speculative engine only: kSpecMaxBatch x 32 x kEngQ
+  RectCand* rects;   // speculative engine only: kSpecMaxBatch x 32 x kEngQ
   const float* ang;  // B x hs x ws level-line angle in degrees
   const int* ord;    // B x hs x ws
   const int* n_ord;  // B
-  RegEnt* reg;       // B x hs x ws
+  uint32_t* reg;     // B x hs x ws region list of the default engine
   RectCand* cand;    // B x cand_cap
   int* n_cand;       // B
   int ws, hs;
@@ -179,7 +175,7 @@ struct EngineArgs {
 //     in flight, committed in seed order.
 void launch_region_engine(const EngineArgs& a, cudaStream_t st);
 void launch_region_engine_spec(const EngineArgs& a, cudaStream_t st);
-constexpr int kSpecMaxBatch = 1024;
+constexpr int kSpecMaxBatch = 256;
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st);
 struct PackArgs {
   const RectCand* cand[kMaxOctaves];
