@@ -44,6 +44,10 @@ WORKLOADS = {
     "C1": dict(name="C1_mh04_real_752x480", w=752, h=480, octaves=1, k=1, max_lines=2048),
     "C3": dict(name="C3_d455_1280x720", w=1280, h=720, octaves=2, k=2, max_lines=2048),
     "C4": dict(name="C4_manhattan_1920x1080", w=1920, h=1080, octaves=1, k=2, max_lines=6144),
+    # BASELINE.json configs[4]: ONE sequence of 1280x720 frames (the C3 generator, seed + 1), 2 octaves, knnMatch k=2,
+    # strong-sharded by contiguous frame range + 1-frame halo over the ranks; results hashed per frame and compared
+    # with the same sequence run on one GPU
+    "C5": dict(name="C5_sharded_sequence_1280x720", w=1280, h=720, octaves=2, k=2, max_lines=2048, frames="C3", sharded=True),
     # the detector the reference really runs (EDLineDetector::EDline with the tracker
     # node's parameters, smoothed=true) on the C2 frames / on the reference's bundled frames
     "E1": dict(name="E1_edlines_euroc_752x480", w=752, h=480, octaves=1, k=0, max_lines=512, frames="C2"),
@@ -135,6 +139,8 @@ class ClockSampler:
 
 
 def make_frames(n_unique, seed, workload="C2"):
+    if WORKLOADS[workload].get("sharded"):
+        seed += 1  # C5 = the C3 generator with seed + 1
     workload = WORKLOADS[workload].get("frames", workload)
     if workload == "C1":  # the reference's bundled EuRoC MH_04 frames (tests/golden/mh04_frames.npz)
         return np.load(os.path.join(ROOT, "tests", "golden", "mh04_frames.npz"))["frames"]
@@ -158,7 +164,8 @@ def lsd_config(args, wl, world):
     W, H = wl["w"], wl["h"]
     return {"workload": wl["name"], "frames_per_step": args.batch, "width": W, "height": H, "octaves": wl["octaves"],
             "match_k": wl["k"], "unique_frames": args.unique, "slots": args.slots,
-            "max_lines": args.max_lines or wl["max_lines"], "parallelism": f"frames x{world}",
+            "max_lines": args.max_lines or wl["max_lines"],
+            "parallelism": f"frames x{world}" + (" (distinct frames per rank: seed + 7919 rank)" if world > 1 else ""),
             "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (args.batch * W * H / 1e6)}
 
 
@@ -963,6 +970,176 @@ def run_matcher(args, torch, dist, rank, local_rank, world):
     return 0
 
 
+def sharded_config(args, wl, world):
+    """`config` of the sharded-sequence workload (C5), the same for both arms."""
+    B = min(args.batch, 1024)
+    return {"workload": wl["name"], "total_frames": args.total_frames, "frames_per_batch": B, "width": wl["w"],
+            "height": wl["h"], "octaves": wl["octaves"], "match_k": wl["k"], "unique_frames": min(args.unique, 48),
+            "slots": args.slots, "max_lines": args.max_lines or wl["max_lines"],
+            "parallelism": f"frame ranges x{world}, 1-frame halo, no collective on the data path",
+            "l2": "every batch (%.0f MB of frames) exceeds the 126 MB L2" % (B * wl["w"] * wl["h"] / 1e6)}
+
+
+def frame_hashes(counts, kl, desc, mt, n):
+    """One 32-bit hash per frame of a collected step's dense outputs (KeyLines, descriptors, matches)."""
+    import zlib
+    off = np.concatenate([[0], np.cumsum(np.asarray(counts[:n], np.int64))])
+    out = np.zeros(n, np.uint32)
+    for f in range(n):
+        a, b = int(off[f]), int(off[f + 1])
+        h = zlib.crc32(kl[a:b].tobytes())
+        h = zlib.crc32(desc[a:b].tobytes(), h)
+        out[f] = zlib.crc32(mt[a:b].tobytes(), h) & 0xffffffff
+    return out
+
+
+def run_sharded_sequence(args, torch, dist, rank, local_rank, world):
+    """--workload C5: ONE sequence of `total` frames (1280x720, 2 octaves, knnMatch k=2), strong scaling: rank g owns
+    frames [g*total/G, (g+1)*total/G) and also processes frame start-1 (halo), so that every consecutive pair is
+    matched on exactly one GPU; no data-path collective.  A step = every rank's whole shard, batch by batch, host
+    buffers in and out through the C ABI.  After the timed region every rank hashes its per-frame results; rank 0
+    gathers them (the only collective, outside the timed region) and compares them with the hashes of the same
+    sequence run on ONE GPU (rank 0 alone, untimed): `identical_to_1gpu`."""
+    vpl = importlib.import_module("vplines_slam_b200")
+    capi = vpl.capi
+    driver = importlib.import_module("vplines-slam_b200.driver")
+    wl = WORKLOADS[args.workload]
+    W, H, OCT, K = wl["w"], wl["h"], wl["octaves"], wl["k"]
+    cap = args.max_lines or wl["max_lines"]
+    total = args.total_frames
+    B, S = min(args.batch, 1024), args.slots
+    unique = make_frames(min(args.unique, 48), args.seed, args.workload)
+    seq_len = len(unique)
+
+    def seq_frames(lo, hi):  # frames [lo, hi) of the global sequence (a tiling of the distinct frames)
+        idx = np.arange(lo, hi) % seq_len
+        return np.ascontiguousarray(unique[idx])
+
+    ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=OCT, max_lines=cap, max_batch=B + 1,
+                       num_slots=S, blur_first=True, profile=False)
+    rows = (B + 1) * cap
+    kl = [np.zeros(rows, capi.KEYLINE_DTYPE) for _ in range(S)]
+    counts = [np.zeros(B + 1, np.int32) for _ in range(S)]
+    desc = [np.zeros((rows, 32), np.uint8) for _ in range(S)]
+    mt = [np.zeros((rows, K), capi.DMATCH_DTYPE) for _ in range(S)]
+    for a in kl + desc + mt:
+        ctx.host_register(a)
+
+    def run_shard(start, end, halo, shard, want_hashes):
+        """frames [start, end) (+ halo frame in front) through submit/collect; shard = pinned host array of them."""
+        lo = start - halo
+        n = end - lo
+        hashes = np.zeros(end - start, np.uint32) if want_hashes else None
+        pending = []
+        lines = 0
+
+        def collect():
+            nonlocal lines
+            ps, b_lo, b_n, skip = pending.pop(0)
+            ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
+            lines += int(counts[ps][skip:b_n].sum())
+            if want_hashes:
+                hh = frame_hashes(counts[ps], kl[ps], desc[ps], mt[ps], b_n)
+                hashes[b_lo + skip - start:b_lo + b_n - start] = hh[skip:]
+
+        i = 0
+        bi = 0
+        while i < n:
+            first = bi == 0
+            b_n = min(B + (1 if first and halo else 0), n - i)
+            s = bi % S
+            if len(pending) == S:
+                collect()
+            ctx.submit(s, shard[i:i + b_n], scale=2, num_octaves=OCT, k=K, chain=not first)
+            pending.append((s, lo + i, b_n, 1 if first and halo else 0))
+            i += b_n
+            bi += 1
+        while pending:
+            collect()
+        return lines, hashes
+
+    start, end, halo = driver.shard_range(total, rank, world)
+    shard = seq_frames(start - halo, end)
+    ctx.host_register(shard)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        run_shard(start, end, halo, shard, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    lines = 0
+    for _ in range(args.steps):
+        lines, _ = run_shard(start, end, halo, shard, False)
+    ctx.sync()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop()
+    _, mine = run_shard(start, end, halo, shard, True)  # untimed: per-frame hashes of this rank's shard
+
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+        ln = torch.tensor([launches, lines], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches, lines = int(ln[0]), int(ln[1])
+        full = torch.zeros(total, device="cuda", dtype=torch.int64)
+        full[start:end] = torch.from_numpy(mine.astype(np.int64)).cuda()
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)  # shards are disjoint: the sum is the concatenation
+        gathered = full.cpu().numpy().astype(np.uint32)
+    else:
+        gathered = mine
+
+    identical = None
+    parity = None
+    if rank == 0:
+        # the same sequence on ONE GPU (this rank alone, its context, batches cut at other places)
+        whole = seq_frames(0, total) if world > 1 else shard
+        if world > 1:
+            ctx.host_register(whole)
+        _, ref = run_shard(0, total, 0, whole, True)
+        identical = bool(np.array_equal(ref, gathered))
+        if not args.no_parity:
+            # and a few frames of it against the CPU oracle chain
+            n0 = min(B, total)
+            ctx.submit(0, whole[:n0], scale=2, num_octaves=OCT, k=K, chain=False)
+            ctx.collect_dense_into(0, counts[0], kl[0], desc[0], mt[0])
+            check = sorted({0, 1, n0 // 2, n0 - 1})
+            bad = verify_dense_step(whole[:n0], None, counts[0], kl[0], desc[0], mt[0], K, OCT, check)
+            parity = {"checked": len(bad) == 0, "frames": len(check), "mismatches": [list(map(str, b)) for b in bad][:8]}
+
+    frames_total = total * args.steps
+    e2e_value = frames_total / (e2e_ms * 1e-3)
+    line = {"metric": lsd_metric(wl), "value": e2e_value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": e2e_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": sharded_config(args, wl, world),
+            "lines_per_frame": round(lines / max(total, 1), 1),
+            "note": "value = e2e: host buffers in and out through the C ABI (this workload has no resident variant)",
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": (total + world - 1) * W * H, "d2h_bytes_per_step": None},
+            "gpu_launches": launches, "identical_to_1gpu": identical, "parity_checked": bool(parity and parity["checked"]),
+            "parity": parity, "clocks": clocks, "cpu_baseline": None, "roofline": None}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores, nothing else."""
     rank = int(os.environ.get("RANK", "0"))
@@ -987,7 +1164,7 @@ def run_reference(args):
         return run_reference_edlines(args)
     wl = WORKLOADS[args.workload]
     OCT, K = wl["octaves"], wl["k"]
-    unique = make_frames(args.unique, args.seed, args.workload)
+    unique = make_frames(min(args.unique, 48) if wl.get("sharded") else args.unique, args.seed, args.workload)
     from oracle import oracle as O
     O.build()
     threads = os.cpu_count() or 1
@@ -1008,8 +1185,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": lsd_metric(wl),
             "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": lsd_config(args, wl, args.gpus),
+            "higher_is_better": True, "scaling": "strong" if wl.get("sharded") else "weak", "vs_baseline": None,
+            "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": sharded_config(args, wl, args.gpus) if wl.get("sharded") else lsd_config(args, wl, args.gpus),
             "sample_frames_per_step": n, "lines_per_frame": round(total / max(n, 1), 1),
             "note": "CPU oracle port (oracle/, -O3 -march=native, all host threads); the reference's OpenCV-3.4 "
                     "line_descriptor binary is not buildable here (no OpenCV C++ / contrib); each step is a bounded "
@@ -1034,6 +1212,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--unique", type=int, default=96, help="distinct synthetic frames generated (tiled to fill a batch)")
     ap.add_argument("--seed", type=int, default=20240601)
+    ap.add_argument("--total-frames", type=int, default=8192, help="C5: length of the sharded sequence")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the last timed e2e step")
@@ -1061,6 +1240,8 @@ def main():
         return run_matcher(args, torch, dist, rank, local_rank, world)
     if args.workload.startswith("E") or args.workload.startswith("R"):
         return run_edlines(args, torch, dist, rank, local_rank, world)
+    if WORKLOADS[args.workload].get("sharded"):
+        return run_sharded_sequence(args, torch, dist, rank, local_rank, world)
 
     vpl = importlib.import_module("vplines_slam_b200")
     capi = vpl.capi
@@ -1069,13 +1250,22 @@ def main():
     B, S, cap, K = args.batch, args.slots, (args.max_lines or wl["max_lines"]), wl["k"]
     wl_name = wl["name"]
 
-    # weak scaling: every rank owns `steps*batch` frames of the sequence; its shard starts one
-    # frame early (halo) so that the pair across the shard boundary is matched exactly once.
-    # the sequence is a tiling of `unique` distinct frames, so every rank's shard holds the same frames
-    unique = make_frames(args.unique, args.seed, args.workload)
+    # weak scaling: every rank owns `steps*batch` frames of the job's sequence, and DISTINCT ones: rank r's part is a
+    # tiling of `unique` frames drawn with seed + 7919 r (the real-frame workload rotates the bundled frames by r).
+    # Its shard starts one frame early (halo = the last frame of rank r-1's part) so that the pair across the shard
+    # boundary is matched exactly once, on rank r.
+    def rank_frames(r):
+        u = make_frames(args.unique, args.seed + 7919 * r, args.workload)
+        return np.roll(u, -r, axis=0) if WORKLOADS[args.workload].get("frames", args.workload) == "C1" else u
+
+    unique = rank_frames(rank)
     halo = 1 if rank > 0 else 0
+    halo_frame = unique[-1:]
+    if rank > 0:
+        prev = rank_frames(rank - 1)
+        halo_frame = prev[(B - 1) % len(prev)][None]
     # one pinned host buffer: [halo frame | B frames]; the shard's first step starts at the halo
-    host_buf = np.ascontiguousarray(np.concatenate([unique[-1:], tile_frames(unique, B)]))
+    host_buf = np.ascontiguousarray(np.concatenate([halo_frame, tile_frames(unique, B)]))
     batch_frames = host_buf[1:]
 
     ctx = capi.Context(device=local_rank, max_width=W, max_height=H, max_octaves=OCT, max_lines=cap,
