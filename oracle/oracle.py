@@ -489,3 +489,55 @@ def line_cloud(lines, ids, line_vps, fx, fy, cx, cy, num_of_cam=1, cam=0):
     for k, nm in enumerate(names):
         d[nm] = out[3 * n + k * n:3 * n + (k + 1) * n].copy()
     return d
+
+
+# ---- the reference's own LineFeatureTracker::readImage (oracle/_ref/libref_tracker.so) -----------
+_REF_TR_SO = os.path.join(_HERE, "_ref", "libref_tracker.so")
+_ref_tr = None
+
+
+def ref_tracker_available():
+    return os.path.exists(_REF_TR_SO) or os.path.isdir("/root/reference/feature_tracker/src")
+
+
+def ref_tracker_lib():
+    global _ref_tr
+    if _ref_tr is None:
+        if not os.path.exists(_REF_TR_SO):
+            build_ref()
+        _ref_tr = ctypes.CDLL(_REF_TR_SO)
+        _ref_tr.ref_tracker_create.restype = ctypes.c_void_p
+        _ref_tr.ref_tracker_read.restype = ctypes.c_int
+    return _ref_tr
+
+
+class RefTracker:
+    """The reference's LineFeatureTracker (its own line_feature_tracker.cpp), set up as its node's main() does.
+    One object per process at a time (the reference reads its parameters from globals)."""
+
+    def __init__(self, mapx, mapy, fx, fy, cx, cy, equalize=True, max_h_lines=25, max_v_lines=25, min_line_length=35.0,
+                 line_fit_err=1.8):
+        L = ref_tracker_lib()
+        self.mapx = np.ascontiguousarray(mapx, np.float32); self.mapy = np.ascontiguousarray(mapy, np.float32)
+        h, w = self.mapx.shape
+        self.h = L.ref_tracker_create(_p(self.mapx), _p(self.mapy), w, h, ctypes.c_float(fx), ctypes.c_float(fy),
+                                      ctypes.c_float(cx), ctypes.c_float(cy), int(bool(equalize)), int(max_h_lines),
+                                      int(max_v_lines), ctypes.c_float(min_line_length), ctypes.c_float(line_fit_err))
+        self.h = ctypes.c_void_p(self.h)
+
+    def close(self):
+        if self.h:
+            ref_tracker_lib().ref_tracker_destroy(self.h)
+            self.h = None
+
+    def read(self, raw, seed, cap=4096):
+        raw = _u8(raw); hh, w = raw.shape
+        lines = np.zeros(cap, LINE_DTYPE); ids = np.zeros(cap, np.int32); vps = np.zeros((cap, 4), np.float64)
+        t_cnt = np.zeros(cap, np.int32)
+        n_vps = ctypes.c_int32(); n_t = ctypes.c_int32(); ex = ctypes.c_int32()
+        n = ref_tracker_lib().ref_tracker_read(self.h, _p(raw), w, hh, ctypes.c_uint(seed), cap, _p(lines), _p(ids), _p(vps),
+                                               ctypes.byref(n_vps), _p(t_cnt), ctypes.byref(n_t), ctypes.byref(ex))
+        if n < 0:
+            raise ValueError("ref_tracker_read: cap %d too small" % cap)
+        return dict(lines=lines[:n].copy(), ids=ids[:n].tolist(), vps=vps[:n_vps.value].copy(),
+                    t_cnt=t_cnt[:n_t.value].tolist(), lines_exit=bool(ex.value))

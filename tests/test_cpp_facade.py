@@ -126,3 +126,13 @@ def test_reference_named_facade_matches_oracle(vpl, orc, tmp_path):
     nmatch = sum(int((orc.line_matching(seq[i - 1], seq[i], ls[i - 1], ls[i]) >= 0).sum()) for i in range(1, 5))
     nlab = sum(int((orc.vp_detect(ls[i], None, 230.0, 160.0, 120.0, 900 + i, i, math_mode=1)[1] != 3).sum()) for i in range(5))
     assert int(mr.group(1)) == sum(len(x) for x in ls) and int(mr.group(2)) == nmatch and int(mr.group(3)) == nlab
+
+
+def test_tracker_facade_compiles_and_fails_loudly_without_gpu(vpl, tmp_path):
+    """compat/linefeature_tracker_b200.hpp (the reference's LineFeatureTracker over the C ABI) compiles without OpenCV;
+    without a device it refuses to run (no CPU path)."""
+    exe = build_facade(tmp_path, "test_tracker")
+    assert subprocess.run([exe, "--compile-only"]).returncode == 0
+    if vpl.capi.device_count() == 0:
+        r = subprocess.run([exe, "in.bin", "out.bin"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU path" in r.stdout
