@@ -73,6 +73,27 @@ int main(int argc, char** argv) {
       }
       std::printf("FACADE batch lines=%ld matched=%ld digest=%lu sharded_equal=%d\n", lines[0], matched[0], dg[0],
                   (int)(dg[0] == dg[1] && lines[0] == lines[1] && matched[0] == matched[1]));
+      // the in-process multi-GPU driver: one host thread + one context per device (as many devices as the box has,
+      // at least two contexts), ordered host gather
+      {
+        unsigned long dm = 1469598103934665603ul;
+        long lm = 0, mm = 0;
+        std::vector<int> devs;
+        const int nd = vpl_device_count();
+        for (int d = 0; d < (nd > 1 ? nd : 2); ++d) devs.push_back(nd > 1 ? d : 0);
+        if (devs.size() > 5) devs.resize(5);
+        vplines::MultiGpuFrontEnd mg(devs, 320, 240, 1, 2048, 2, 2);
+        int64_t expect = 0;
+        bool ordered = true;
+        mg.run(ptrs.data(), 320, 5, 2, 1, [&](int64_t f, const vplines::FrameResult& r) {
+          ordered = ordered && f == expect++;
+          lm += (long)r.keylines.size();
+          for (uint8_t b : r.descriptors) dm = (dm ^ b) * 1099511628211ul;
+          for (const VplDMatch& m : r.matches) { mm += m.trainIdx >= 0; dm = (dm ^ (unsigned long)(m.trainIdx + 7)) * 1099511628211ul; }
+        });
+        std::printf("FACADE multigpu world=%d equal=%d ordered=%d\n", mg.world(), (int)(dm == dg[0] && lm == lines[0] && mm == matched[0]),
+                    (int)(ordered && expect == 5));
+      }
     }
     cv::Mat f32(4, 4, CV_32FC1);
     try {

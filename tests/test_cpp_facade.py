@@ -13,7 +13,7 @@ PKG = os.path.join(ROOT, "vplines-slam_b200")
 
 def build_facade(tmp_path, name="test_facade"):
     exe = str(tmp_path / name)
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-L", PKG, "-lvplines_b200", f"-Wl,-rpath,{PKG}"]
     subprocess.check_call(cmd)
     return exe
@@ -69,6 +69,9 @@ def test_facade_matches_ctypes_path(vpl, orc, tmp_path):
     assert int(mb.group(1)) == sum(len(k) for k in kls)
     exp_matched = sum(len(ds[i]) for i in range(1, 5) if len(ds[i - 1]))
     assert int(mb.group(2)) == exp_matched
+    # in-process multi-GPU driver (std::thread + context per device, ordered host gather) == the single run
+    mg = re.search(r"multigpu world=(\d+) equal=(\d) ordered=(\d)", out)
+    assert mg and int(mg.group(1)) >= 2 and mg.group(2) == "1" and mg.group(3) == "1", out
 
 
 def fnv(data):

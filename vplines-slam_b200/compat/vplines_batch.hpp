@@ -8,9 +8,12 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <exception>
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vpl_capi.h"
@@ -89,6 +92,52 @@ class BatchFrontEnd {
   std::vector<uint8_t> desc_;
   std::vector<VplDMatch> matches_;
   std::vector<int32_t> counts_;
+};
+
+// ---- one process, several GPUs -----------------------------------------------------------
+// One host thread + one context + its streams per GPU: the sequence is cut into contiguous frame ranges, GPU g also
+// processes frame start_g - 1 (halo) so that every consecutive pair is matched on exactly one GPU, and the host
+// gathers: results are delivered to `sink` in frame order after all shards have finished.  No collective, no peer
+// copy.  `devices` may name a device more than once (two contexts on one GPU: how the single-GPU tests exercise it).
+class MultiGpuFrontEnd {
+ public:
+  MultiGpuFrontEnd(const std::vector<int>& devices, int width, int height, int octaves, int max_lines, int max_batch,
+                   int num_slots = 2) {
+    if (devices.empty()) throw std::runtime_error("vplines_b200: no device given");
+    for (int d : devices) shards_.emplace_back(new BatchFrontEnd(d, width, height, octaves, max_lines, max_batch, num_slots));
+  }
+  int world() const { return (int)shards_.size(); }
+
+  // frames [0, n_frames); sink(frame_index, result) is called for every frame, in order, from the calling thread
+  void run(const uint8_t* const* frames, size_t stride, int64_t n_frames, int scale, int k,
+           const std::function<void(int64_t, const FrameResult&)>& sink) {
+    const int G = world();
+    std::vector<std::vector<FrameResult>> out((size_t)G);
+    std::vector<std::exception_ptr> err((size_t)G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+      th.emplace_back([&, g] {
+        try {
+          int64_t s, e;
+          int halo;
+          shard_range(n_frames, g, G, s, e, halo);
+          out[(size_t)g].reserve((size_t)(e - s));
+          shards_[(size_t)g]->run(frames, stride, s, e, halo, scale, k,
+                                  [&](int64_t, const FrameResult& r) { out[(size_t)g].push_back(r); });
+        } catch (...) {
+          err[(size_t)g] = std::current_exception();
+        }
+      });
+    for (std::thread& t : th) t.join();
+    for (const std::exception_ptr& e : err)
+      if (e) std::rethrow_exception(e);
+    int64_t f = 0;
+    for (int g = 0; g < G; ++g)
+      for (const FrameResult& r : out[(size_t)g]) sink(f++, r);
+  }
+
+ private:
+  std::vector<std::unique_ptr<BatchFrontEnd>> shards_;
 };
 
 // ---- readImage's whole line pipeline over a frame sequence (vpl_readimage_*) ---------------------------------
