@@ -27,6 +27,8 @@
 #include "vpl_common.cuh"
 #include "vpl_sincos.cuh"
 
+#include <cstdlib>
+
 namespace vpl {
 
 constexpr int RING = 256;  // per-warp FIFO window kept in shared memory
@@ -405,12 +407,19 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
 // ---------------------------------------------------------------------------
 // The engine kernel: blockDim = 32 (one warp), grid = (batch, num_octaves).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-region_engine_kernel(EngineArgs A) {
-  __shared__ int s_ring[RING];
-  __shared__ double s_bc[32];
-  __shared__ double2 s_bc2[32];
-  const int f = blockIdx.x;
+// WPB warps (= frames) per block; the warps of a block are independent.  An SM holds at most 32 blocks, so more than 32
+// resident engine warps need multi-warp blocks and fewer registers per thread (MINB = blocks per SM asked of ptxas).
+template <int WPB>
+__device__ __forceinline__ void region_engine_body(const EngineArgs& A) {
+  __shared__ int s_ring_[WPB][RING];
+  __shared__ double s_bc_[WPB][32];
+  __shared__ double2 s_bc2_[WPB][32];
+  const int wib = threadIdx.x >> 5;
+  int* s_ring = s_ring_[wib];
+  double* s_bc = s_bc_[wib];
+  double2* s_bc2 = s_bc2_[wib];
+  const int f = blockIdx.x * WPB + wib;
+  if (f >= A.batch) return;
   const EngineOct& O = A.oct[blockIdx.y];
   const size_t npx = (size_t)O.ws * O.hs;
   Eng e;
@@ -420,7 +429,7 @@ region_engine_kernel(EngineArgs A) {
   e.bc = s_bc;
   e.bc2 = s_bc2;
   e.ws = O.ws; e.hs = O.hs;
-  e.lane = threadIdx.x;
+  e.lane = threadIdx.x & 31;
   const int lane = e.lane;
   const int* ord = O.ord + (size_t)f * npx;
   const int n_ord = O.n_ord[f];
@@ -462,9 +471,38 @@ region_engine_kernel(EngineArgs A) {
   if (lane == 0) O.n_cand[f] = n_cand < A.cand_cap ? n_cand : A.cand_cap;
 }
 
+// Measured on B200 (C2, frames/s kernels-only at 4096 / 8192 frames per batch, same box, profiles/r02_engine_occupancy_variants.txt):
+//   1 frame/block,  32 blocks/SM (64 regs, 32 warps/SM)   the round-1 shape
+//   1 frame/block, no register cap (94 regs, 21 warps/SM) 44.4 k / 46.3 k
+//   2 frames/block, 21 blocks/SM (40 regs, 42 warps/SM)    49.5 k / 51.0 k   <- default
+//   2 frames/block, 25 blocks/SM (32 regs, 50 warps/SM)    51.8 k / 53.0 k   (more spills; within the box-to-box noise of the default)
+//   4 frames/block, 12 blocks/SM (40 regs, 48 warps/SM)    50.2 k / 52.5 k
+//   4 frames/block, 10 blocks/SM (48 regs, 40 warps/SM)    48.5 k / 52.0 k
+__global__ void __launch_bounds__(32, 32) region_engine_kernel(EngineArgs A) { region_engine_body<1>(A); }
+__global__ void __launch_bounds__(64, 21) region_engine_kernel_w2(EngineArgs A) { region_engine_body<2>(A); }
+__global__ void __launch_bounds__(64, 25) region_engine_kernel_w2b(EngineArgs A) { region_engine_body<2>(A); }
+__global__ void __launch_bounds__(128, 12) region_engine_kernel_w4(EngineArgs A) { region_engine_body<4>(A); }
+__global__ void __launch_bounds__(128, 10) region_engine_kernel_w4b(EngineArgs A) { region_engine_body<4>(A); }
+
 void launch_region_engine(const EngineArgs& a, cudaStream_t st) {
+  // VPL_ENGINE_VARIANT selects one of the builds above for measurement (0: 1 frame/block, 1: the default, 2..4)
+  static const int variant = [] { const char* v = getenv("VPL_ENGINE_VARIANT"); return v ? atoi(v) : 1; }();
   dim3 grid(a.batch, a.num_octaves);
-  region_engine_kernel<<<grid, 32, 0, st>>>(a);
+  if (variant == 1) {
+    grid.x = (a.batch + 1) / 2;
+    region_engine_kernel_w2<<<grid, 64, 0, st>>>(a);
+  } else if (variant == 2) {
+    grid.x = (a.batch + 1) / 2;
+    region_engine_kernel_w2b<<<grid, 64, 0, st>>>(a);
+  } else if (variant == 3) {
+    grid.x = (a.batch + 3) / 4;
+    region_engine_kernel_w4<<<grid, 128, 0, st>>>(a);
+  } else if (variant == 4) {
+    grid.x = (a.batch + 3) / 4;
+    region_engine_kernel_w4b<<<grid, 128, 0, st>>>(a);
+  } else {
+    region_engine_kernel<<<grid, 32, 0, st>>>(a);
+  }
 }
 
 }  // namespace vpl
