@@ -10,6 +10,10 @@
 // one grid covering the whole batch.
 #include "vpl_common.cuh"
 
+#include <cstdlib>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
 namespace vpl {
 
 // ---------------------------------------------------------------------------
@@ -89,6 +93,50 @@ constexpr int B5_IH = B5_TH + 6;  // y0-3 .. y0+TH+2
 constexpr int B5_OW = B5_IW - 4;  // blurred tile: 68 columns, column c <-> gx = x0-2+c
 constexpr int B5_OH = B5_IH - 4;  // 34 rows, row r <-> gy = y0-1+r
 
+// Sobel 3x3 of the blurred tile + the stores: each thread handles 4 consecutive pixels of a row.
+__device__ __forceinline__ void blur5_sobel_store(const uint8_t (*s_bl)[B5_IW], uint8_t* __restrict__ pyr,
+                                                  short2* __restrict__ grad, size_t frame, int x0, int y0, int w, int h,
+                                                  int tid) {
+  const bool wordable = ((w & 3) == 0);
+  // output pixel (x0+c+k, y0+r) is blurred column c+k+2, row r+1 of s_bl
+  for (int i = tid; i < B5_TH * (B5_TW / 4); i += B5_THREADS) {
+    int r = i >> 4, c = 4 * (i & 15);  // B5_TW / 4 == 16
+    int gy = y0 + r, gx = x0 + c;
+    if (gy >= h || gx >= w) continue;
+    // bytes c .. c+7 of the three rows; the window needed is columns c+1 .. c+6
+    uint2 ra, rm, rb;  // (c is a multiple of 4 only: two 32-bit loads per row)
+    ra.x = *reinterpret_cast<const uint32_t*>(&s_bl[r][c]);     ra.y = *reinterpret_cast<const uint32_t*>(&s_bl[r][c + 4]);
+    rm.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c]); rm.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c + 4]);
+    rb.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c]); rb.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c + 4]);
+    int C[6], D[6];  // column sums a+2m+b and column differences b-a for columns c+1 .. c+6
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int bi = j + 1;
+      const int a = (bi < 4) ? (int)((ra.x >> (8 * bi)) & 0xff) : (int)((ra.y >> (8 * (bi - 4))) & 0xff);
+      const int m = (bi < 4) ? (int)((rm.x >> (8 * bi)) & 0xff) : (int)((rm.y >> (8 * (bi - 4))) & 0xff);
+      const int b = (bi < 4) ? (int)((rb.x >> (8 * bi)) & 0xff) : (int)((rb.y >> (8 * (bi - 4))) & 0xff);
+      C[j] = a + 2 * m + b;
+      D[j] = b - a;
+    }
+    short2 g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = make_short2((short)(C[k + 2] - C[k]), (short)(D[k] + 2 * D[k + 1] + D[k + 2]));
+    const uint32_t packed = __byte_perm(rm.x, rm.y, 0x5432);  // blurred centre pixels c+2 .. c+5
+    size_t o = frame + (size_t)gy * w + gx;
+    if (wordable && gx + 3 < w) {
+      *reinterpret_cast<uint32_t*>(pyr + o) = packed;
+      *reinterpret_cast<uint4*>(grad + o) =
+          make_uint4(*reinterpret_cast<uint32_t*>(&g[0]), *reinterpret_cast<uint32_t*>(&g[1]),
+                     *reinterpret_cast<uint32_t*>(&g[2]), *reinterpret_cast<uint32_t*>(&g[3]));
+    } else {
+      for (int k = 0; k < 4 && gx + k < w; ++k) {
+        pyr[o + k] = (uint8_t)(packed >> (8 * k));
+        grad[o + k] = g[k];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(B5_THREADS)
 blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
                    short2* __restrict__ grad, int w, int h, int do_blur) {
@@ -133,49 +181,122 @@ blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
     __syncthreads();
   }
 
-  // ---- Sobel + stores: each thread handles 4 consecutive pixels of a row.
-  // output pixel (x0+c+k, y0+r) is blurred column c+k+2, row r+1 of s_bl
-  for (int i = tid; i < B5_TH * (B5_TW / 4); i += B5_THREADS) {
-    int r = i >> 4, c = 4 * (i & 15);  // B5_TW / 4 == 16
-    int gy = y0 + r, gx = x0 + c;
-    if (gy >= h || gx >= w) continue;
-    // bytes c .. c+7 of the three rows; the window needed is columns c+1 .. c+6
-    uint2 ra, rm, rb;  // (c is a multiple of 4 only: two 32-bit loads per row)
-    ra.x = *reinterpret_cast<const uint32_t*>(&s_bl[r][c]);     ra.y = *reinterpret_cast<const uint32_t*>(&s_bl[r][c + 4]);
-    rm.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c]); rm.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 1][c + 4]);
-    rb.x = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c]); rb.y = *reinterpret_cast<const uint32_t*>(&s_bl[r + 2][c + 4]);
-    int C[6], D[6];  // column sums a+2m+b and column differences b-a for columns c+1 .. c+6
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int bi = j + 1;
-      const int a = (bi < 4) ? (int)((ra.x >> (8 * bi)) & 0xff) : (int)((ra.y >> (8 * (bi - 4))) & 0xff);
-      const int m = (bi < 4) ? (int)((rm.x >> (8 * bi)) & 0xff) : (int)((rm.y >> (8 * (bi - 4))) & 0xff);
-      const int b = (bi < 4) ? (int)((rb.x >> (8 * bi)) & 0xff) : (int)((rb.y >> (8 * (bi - 4))) & 0xff);
-      C[j] = a + 2 * m + b;
-      D[j] = b - a;
-    }
-    short2 g[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) g[k] = make_short2((short)(C[k + 2] - C[k]), (short)(D[k] + 2 * D[k + 1] + D[k + 2]));
-    const uint32_t packed = __byte_perm(rm.x, rm.y, 0x5432);  // blurred centre pixels c+2 .. c+5
-    size_t o = frame + (size_t)gy * w + gx;
-    if (wordable && gx + 3 < w) {
-      *reinterpret_cast<uint32_t*>(pyr + o) = packed;
-      *reinterpret_cast<uint4*>(grad + o) =
-          make_uint4(*reinterpret_cast<uint32_t*>(&g[0]), *reinterpret_cast<uint32_t*>(&g[1]),
-                     *reinterpret_cast<uint32_t*>(&g[2]), *reinterpret_cast<uint32_t*>(&g[3]));
-    } else {
-      for (int k = 0; k < 4 && gx + k < w; ++k) {
-        pyr[o + k] = (uint8_t)(packed >> (8 * k));
-        grad[o + k] = g[k];
-      }
+  blur5_sobel_store(s_bl, pyr, grad, frame, x0, y0, w, h, tid);
+}
+
+// ---------------------------------------------------------------------------
+// The same kernel with the input tile brought in by the TMA unit: one cp.async.bulk.tensor.3d per CTA moves the
+// 96 x 38-byte box (x0-16 .. x0+79, y0-3 .. y0+34) of frame z into shared memory and signals an mbarrier; elements
+// outside the image arrive as zeros and are then overwritten with their BORDER_REFLECT_101 mirror images, which lie in
+// the same tile (the halo is 4 pixels, the margins 12 and more).  No per-thread address arithmetic, no refl101 per
+// byte.  The unit wants the box to start on a 16-byte boundary of the row (measured on B200: any other inner
+// coordinate raises "illegal instruction", tools/probe/), hence x0-16 and a width of 96 for the 72 bytes used, and
+// a row pitch that is a multiple of 16 bytes (w % 16 == 0), otherwise the kernel above runs.
+// ---------------------------------------------------------------------------
+constexpr int B5T_PITCH = 96;  // box width in bytes (multiple of 16)
+constexpr int B5T_X = 16;      // tile column c <-> gx = x0 - B5T_X + c; the columns used are B5T_X-4 .. B5T_X+67
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(B5_THREADS)
+blur5_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ pyr, short2* __restrict__ grad,
+                       int w, int h, int do_blur) {
+  __shared__ __align__(128) uint8_t s_in[B5_IH][B5T_PITCH];
+  __shared__ __align__(16) uint16_t s_v[B5_OH][B5_IW];
+  __shared__ __align__(16) uint8_t s_bl[B5_OH][B5_IW];
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const size_t frame = (size_t)blockIdx.z * w * h;
+  const int x0 = blockIdx.x * B5_TW, y0 = blockIdx.y * B5_TH;
+  const int tid = threadIdx.x;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(B5_IH * B5T_PITCH) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(&s_in[0][0])),
+        "l"(&tmap), "r"(x0 - B5T_X), "r"(y0 - 3), "r"((int)blockIdx.z), "r"(bar)
+        : "memory");
+  }
+  {  // every thread waits for the box (phase 0 of the barrier)
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(0)
+          : "memory");
     }
   }
+  // BORDER_REFLECT_101 for the tiles that stick out of the image: out-of-range elements take the value of their mirror
+  // image, an in-range element of the same tile (sources are never written here: no hazard)
+  if (x0 - 4 < 0 || x0 + B5_TW + 4 > w || y0 - 3 < 0 || y0 + B5_TH + 3 > h) {
+    for (int i = tid; i < B5_IH * B5_IW; i += B5_THREADS) {
+      const int r = i / B5_IW, c = B5T_X - 4 + (i - r * B5_IW);
+      const int gx = x0 - B5T_X + c, gy = y0 - 3 + r;
+      if (gx < 0 || gx >= w || gy < 0 || gy >= h) {
+        const int sx = refl101(gx, w) - (x0 - B5T_X), sy = refl101(gy, h) - (y0 - 3);
+        // a mirror image outside the box belongs to a pixel no output of this tile depends on
+        s_in[r][c] = (sx >= 0 && sx < B5T_PITCH && sy >= 0 && sy < B5_IH) ? s_in[sy][sx] : (uint8_t)0;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (do_blur) {
+    blur5_tile_packed<14, 62, 104>(&s_in[0][B5T_X - 4], B5T_PITCH, B5_IH, B5_IW / 4, &s_v[0][0], B5_IW, &s_bl[0][0], B5_IW,
+                                   tid, B5_THREADS);
+  } else {
+    for (int i = tid; i < B5_OH * (B5_OW / 4); i += B5_THREADS) {
+      int r = i / (B5_OW / 4), c = 4 * (i % (B5_OW / 4));
+      uint32_t lo = *reinterpret_cast<const uint32_t*>(&s_in[r + 2][c + B5T_X - 4]);
+      uint32_t hi = *reinterpret_cast<const uint32_t*>(&s_in[r + 2][c + B5T_X]);
+      *reinterpret_cast<uint32_t*>(&s_bl[r][c]) = __byte_perm(lo, hi, 0x5432);
+    }
+    __syncthreads();
+  }
+  blur5_sobel_store(s_bl, pyr, grad, frame, x0, y0, w, h, tid);
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda); nullptr if the driver does not have it
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
 }
 
 void launch_blur5_sobel(const uint8_t* img, uint8_t* pyr, short2* grad, int w, int h, int batch,
                         int do_blur, cudaStream_t st) {
   dim3 grid((w + B5_TW - 1) / B5_TW, (h + B5_TH - 1) / B5_TH, batch);
+  static const bool no_tma = getenv("VPL_NO_TMA") != nullptr;  // measurement: force the per-thread tile loads
+  TmapEncodeFn enc = no_tma ? nullptr : tmap_encoder();
+  if (enc && (w % 16) == 0 && (((size_t)w * h) % 16) == 0 && ((uintptr_t)img % 16) == 0 && w >= 16 && h >= 8) {
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)w, (cuuint64_t)w * h};  // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {B5T_PITCH, B5_IH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      blur5_sobel_tma_kernel<<<grid, B5_THREADS, 0, st>>>(tm, pyr, grad, w, h, do_blur);
+      return;
+    }
+  }
   blur5_sobel_kernel<<<grid, B5_THREADS, 0, st>>>(img, pyr, grad, w, h, do_blur);
 }
 
