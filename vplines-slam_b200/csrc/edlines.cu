@@ -26,6 +26,7 @@
 #include <float.h>
 
 #include "vpl_common.cuh"
+#include "vpl_tma.cuh"
 
 namespace vpl {
 
@@ -57,39 +58,54 @@ __device__ __forceinline__ unsigned gmap_value(short2 d, int grad_thresh) {
 constexpr int GT_W = 64, GT_H = 16, GT_THREADS = 256;
 constexpr int GT_SW = GT_W + 8;  // shared image row: columns x0-4 .. x0+GT_W+3 (word aligned)
 
-__device__ __forceinline__ short2 sobel_at(const uint8_t* p) {  // p -> centre pixel in s_img
-  const int a = p[-GT_SW - 1], b = p[-GT_SW], c = p[-GT_SW + 1], d = p[-1], e = p[1];
-  const int g = p[GT_SW - 1], h = p[GT_SW], i = p[GT_SW + 1];
+template <int PITCH>
+__device__ __forceinline__ short2 sobel_at(const uint8_t* p) {  // p -> centre pixel in the image tile of row pitch PITCH
+  const int a = p[-PITCH - 1], b = p[-PITCH], c = p[-PITCH + 1], d = p[-1], e = p[1];
+  const int g = p[PITCH - 1], h = p[PITCH], i = p[PITCH + 1];
   return make_short2((short)((c + 2 * e + i) - (a + 2 * d + g)), (short)((g + 2 * h + i) - (a + 2 * b + c)));
 }
 
-__global__ void __launch_bounds__(GT_THREADS) ed_grad_anchor_kernel(const uint8_t* __restrict__ img,
+// TMA = true: the image tile arrives through the TMA unit (box x0-16 .. x0+79, 96 bytes wide, zero-filled outside the
+// image, then reflected); false: per-thread loads (images whose pitch is not a multiple of 16 bytes).
+constexpr int GT_TP = 96, GT_TX = 16;
+template <bool TMA>
+__global__ void __launch_bounds__(GT_THREADS) ed_grad_anchor_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const uint8_t* __restrict__ img,
                                                                     short2* __restrict__ grad,
                                                                     uint16_t* __restrict__ gmap,
                                                                     unsigned* __restrict__ bitmap,
                                                                     int* __restrict__ n_anchor, EdGeom G,
                                                                     int grad_thresh, int anchor_thresh) {
-  __shared__ __align__(16) uint8_t s_img[GT_H + 4][GT_SW];  // rows y0-2 .. y0+GT_H+1
+  constexpr int P = TMA ? GT_TP : GT_SW;   // row pitch of the image tile
+  constexpr int X = TMA ? GT_TX : 4;       // tile column of image column x0
+  __shared__ __align__(128) uint8_t s_img[GT_H + 4][P];  // rows y0-2 .. y0+GT_H+1
   __shared__ __align__(8) uint16_t s_g[GT_H + 2][GT_W + 4];  // map at (x0-1 .. x0+GT_W, y0-1 .. y0+GT_H), column c = x - x0 + 1
+  __shared__ __align__(8) unsigned long long s_bar;
   const int f = blockIdx.z, w = G.w, h = G.h;
   const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
-  const uint8_t* src = img + (size_t)f * w * h;
-  // image tile: 18 words per row x 20 rows; whole words inside the image are loaded as such
   const bool vec_ok = (w & 3) == 0;
-  for (int i = threadIdx.x; i < (GT_H + 4) * (GT_SW / 4); i += GT_THREADS) {
-    const int r = i / (GT_SW / 4), cw = i - r * (GT_SW / 4);
-    const int y = refl101(y0 + r - 2, h), x = x0 - 4 + 4 * cw;
-    unsigned v;
-    if (vec_ok && x >= 0 && x + 3 < w) {
-      v = *reinterpret_cast<const unsigned*>(src + (size_t)y * w + x);
-    } else {
-      const uint8_t* row = src + (size_t)y * w;
-      v = (unsigned)row[refl101(x, w)] | ((unsigned)row[refl101(x + 1, w)] << 8) | ((unsigned)row[refl101(x + 2, w)] << 16) |
-          ((unsigned)row[refl101(x + 3, w)] << 24);
+  if (TMA) {
+    tma_load_box_3d(&tmap, &s_img[0][0], &s_bar, x0 - GT_TX, y0 - 2, f, (GT_H + 4) * GT_TP);
+    if (x0 - 4 < 0 || x0 + GT_W + 4 > w || y0 - 2 < 0 || y0 + GT_H + 2 > h)
+      tma_reflect_fix(&s_img[0][0], GT_TP, GT_H + 4, GT_TX - 4, GT_SW, x0 - GT_TX, y0 - 2, w, h, GT_THREADS);
+  } else {
+    const uint8_t* src = img + (size_t)f * w * h;
+    // image tile: 18 words per row x 20 rows; whole words inside the image are loaded as such
+    for (int i = threadIdx.x; i < (GT_H + 4) * (GT_SW / 4); i += GT_THREADS) {
+      const int r = i / (GT_SW / 4), cw = i - r * (GT_SW / 4);
+      const int y = refl101(y0 + r - 2, h), x = x0 - 4 + 4 * cw;
+      unsigned v;
+      if (vec_ok && x >= 0 && x + 3 < w) {
+        v = *reinterpret_cast<const unsigned*>(src + (size_t)y * w + x);
+      } else {
+        const uint8_t* row = src + (size_t)y * w;
+        v = (unsigned)row[refl101(x, w)] | ((unsigned)row[refl101(x + 1, w)] << 8) | ((unsigned)row[refl101(x + 2, w)] << 16) |
+            ((unsigned)row[refl101(x + 3, w)] << 24);
+      }
+      *reinterpret_cast<unsigned*>(&s_img[r][4 * cw]) = v;
     }
-    *reinterpret_cast<unsigned*>(&s_img[r][4 * cw]) = v;
+    __syncthreads();
   }
-  __syncthreads();
   const size_t fo = (size_t)f * w * h;
   {  // interior: 4 adjacent pixels per thread, 128-bit / 64-bit stores
     const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;  // pixel (x0 + c4 .. +3, y0 + r)
@@ -98,7 +114,7 @@ __global__ void __launch_bounds__(GT_THREADS) ed_grad_anchor_kernel(const uint8_
     unsigned gv[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      dv[k] = sobel_at(&s_img[r + 2][c4 + k + 4]);
+      dv[k] = sobel_at<P>(&s_img[r + 2][c4 + k + X]);
       gv[k] = gmap_value(dv[k], grad_thresh);
       s_g[r + 1][c4 + k + 1] = (uint16_t)gv[k];
     }
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(GT_THREADS) ed_grad_anchor_kernel(const uint8_
     else if (t < 2 * (GT_W + 2)) { r = GT_H + 1; c = t - (GT_W + 2); }
     else if (t < 2 * (GT_W + 2) + GT_H) { r = 1 + t - 2 * (GT_W + 2); c = 0; }
     else { r = 1 + t - 2 * (GT_W + 2) - GT_H; c = GT_W + 1; }
-    s_g[r][c] = (uint16_t)gmap_value(sobel_at(&s_img[r + 1][c + 3]), grad_thresh);
+    s_g[r][c] = (uint16_t)gmap_value(sobel_at<P>(&s_img[r + 1][c + X - 1]), grad_thresh);
   }
   __syncthreads();
   // anchors: grid points (1 + ix*scan, 1 + iy*scan) with 1 <= x <= w-2, 1 <= y <= h-2 inside this tile
@@ -647,7 +663,13 @@ void launch_ed_grad_anchor(const uint8_t* img, short2* grad, const EdBuffers& B,
   cudaMemsetAsync(B.bitmap, 0, (size_t)batch * G.bm_words * sizeof(unsigned), st);
   cudaMemsetAsync(B.n_anchor, 0, (size_t)batch * sizeof(int), st);
   dim3 grid((G.w + GT_W - 1) / GT_W, (G.h + GT_H - 1) / GT_H, batch);
-  ed_grad_anchor_kernel<<<grid, GT_THREADS, 0, st>>>(img, grad, B.gmap, B.bitmap, B.n_anchor, G, grad_thresh, anchor_thresh);
+  CUtensorMap tm;
+  if (make_u8_frames_tmap(&tm, img, G.w, G.h, batch, GT_TP, GT_H + 4))
+    ed_grad_anchor_kernel<true><<<grid, GT_THREADS, 0, st>>>(tm, img, grad, B.gmap, B.bitmap, B.n_anchor, G, grad_thresh, anchor_thresh);
+  else {
+    memset(&tm, 0, sizeof(tm));
+    ed_grad_anchor_kernel<false><<<grid, GT_THREADS, 0, st>>>(tm, img, grad, B.gmap, B.bitmap, B.n_anchor, G, grad_thresh, anchor_thresh);
+  }
 }
 
 void launch_ed_walk(const EdBuffers& B, const EdGeom& G, int batch, cudaStream_t st) {

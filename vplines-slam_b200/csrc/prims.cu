@@ -9,10 +9,7 @@
 // All are HBM-bound: shared-memory halo tiles, 32-bit/128-bit global accesses,
 // one grid covering the whole batch.
 #include "vpl_common.cuh"
-
-#include <cstdlib>
-
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+#include "vpl_tma.cuh"
 
 namespace vpl {
 
@@ -196,8 +193,6 @@ blur5_sobel_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr,
 constexpr int B5T_PITCH = 96;  // box width in bytes (multiple of 16)
 constexpr int B5T_X = 16;      // tile column c <-> gx = x0 - B5T_X + c; the columns used are B5T_X-4 .. B5T_X+67
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __global__ void __launch_bounds__(B5_THREADS)
 blur5_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ pyr, short2* __restrict__ grad,
                        int w, int h, int do_blur) {
@@ -209,44 +204,9 @@ blur5_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __rest
   const size_t frame = (size_t)blockIdx.z * w * h;
   const int x0 = blockIdx.x * B5_TW, y0 = blockIdx.y * B5_TH;
   const int tid = threadIdx.x;
-  const uint32_t bar = smem_u32(&s_bar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(B5_IH * B5T_PITCH) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(&s_in[0][0])),
-        "l"(&tmap), "r"(x0 - B5T_X), "r"(y0 - 3), "r"((int)blockIdx.z), "r"(bar)
-        : "memory");
-  }
-  {  // every thread waits for the box (phase 0 of the barrier)
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(0)
-          : "memory");
-    }
-  }
-  // BORDER_REFLECT_101 for the tiles that stick out of the image: out-of-range elements take the value of their mirror
-  // image, an in-range element of the same tile (sources are never written here: no hazard)
-  if (x0 - 4 < 0 || x0 + B5_TW + 4 > w || y0 - 3 < 0 || y0 + B5_TH + 3 > h) {
-    for (int i = tid; i < B5_IH * B5_IW; i += B5_THREADS) {
-      const int r = i / B5_IW, c = B5T_X - 4 + (i - r * B5_IW);
-      const int gx = x0 - B5T_X + c, gy = y0 - 3 + r;
-      if (gx < 0 || gx >= w || gy < 0 || gy >= h) {
-        const int sx = refl101(gx, w) - (x0 - B5T_X), sy = refl101(gy, h) - (y0 - 3);
-        // a mirror image outside the box belongs to a pixel no output of this tile depends on
-        s_in[r][c] = (sx >= 0 && sx < B5T_PITCH && sy >= 0 && sy < B5_IH) ? s_in[sy][sx] : (uint8_t)0;
-      }
-    }
-    __syncthreads();
-  }
+  tma_load_box_3d(&tmap, &s_in[0][0], &s_bar, x0 - B5T_X, y0 - 3, (int)blockIdx.z, B5_IH * B5T_PITCH);
+  if (x0 - 4 < 0 || x0 + B5_TW + 4 > w || y0 - 3 < 0 || y0 + B5_TH + 3 > h)
+    tma_reflect_fix(&s_in[0][0], B5T_PITCH, B5_IH, B5T_X - 4, B5_IW, x0 - B5T_X, y0 - 3, w, h, B5_THREADS);
 
   if (do_blur) {
     blur5_tile_packed<14, 62, 104>(&s_in[0][B5T_X - 4], B5T_PITCH, B5_IH, B5_IW / 4, &s_v[0][0], B5_IW, &s_bl[0][0], B5_IW,
@@ -263,41 +223,14 @@ blur5_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __rest
   blur5_sobel_store(s_bl, pyr, grad, frame, x0, y0, w, h, tid);
 }
 
-// cuTensorMapEncodeTiled through the runtime (no link against libcuda); nullptr if the driver does not have it
-typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TmapEncodeFn tmap_encoder() {
-  static TmapEncodeFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    (void)cudaGetLastError();
-    return (TmapEncodeFn)p;
-  }();
-  return fn;
-}
-
 void launch_blur5_sobel(const uint8_t* img, uint8_t* pyr, short2* grad, int w, int h, int batch,
                         int do_blur, cudaStream_t st) {
   dim3 grid((w + B5_TW - 1) / B5_TW, (h + B5_TH - 1) / B5_TH, batch);
-  static const bool no_tma = getenv("VPL_NO_TMA") != nullptr;  // measurement: force the per-thread tile loads
-  TmapEncodeFn enc = no_tma ? nullptr : tmap_encoder();
-  if (enc && (w % 16) == 0 && (((size_t)w * h) % 16) == 0 && ((uintptr_t)img % 16) == 0 && w >= 16 && h >= 8) {
-    CUtensorMap tm;
-    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
-    const cuuint64_t gstr[2] = {(cuuint64_t)w, (cuuint64_t)w * h};  // bytes, dimensions 1 and 2
-    const cuuint32_t box[3] = {B5T_PITCH, B5_IH, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-      blur5_sobel_tma_kernel<<<grid, B5_THREADS, 0, st>>>(tm, pyr, grad, w, h, do_blur);
-      return;
-    }
-  }
-  blur5_sobel_kernel<<<grid, B5_THREADS, 0, st>>>(img, pyr, grad, w, h, do_blur);
+  CUtensorMap tm;
+  if (make_u8_frames_tmap(&tm, img, w, h, batch, B5T_PITCH, B5_IH))
+    blur5_sobel_tma_kernel<<<grid, B5_THREADS, 0, st>>>(tm, pyr, grad, w, h, do_blur);
+  else
+    blur5_sobel_kernel<<<grid, B5_THREADS, 0, st>>>(img, pyr, grad, w, h, do_blur);
 }
 
 // ---------------------------------------------------------------------------
@@ -366,6 +299,12 @@ constexpr int SC_TW = 64, SC_TH = 16, SC_THREADS = 256;
 constexpr int SC_GH = 21;                // blurred block: columns sx0-2 .. sx0+81 (81 needed), rows sy0 .. sy0+20
 constexpr int SC_IW = 88, SC_IH = 25;   // input block: columns sx0-4 .. sx0+83 (22 words), rows sy0-2 .. sy0+22
 
+// blur of the staged block + the 0.8 resampling of one 64 x 16 destination tile; s_in(r, c) = source pixel
+// (sx0 - 4 + c, sy0 - 2 + r), row pitch in_pitch bytes
+__device__ __forceinline__ void scale08_tile(const uint8_t* s_in, int in_pitch, uint16_t (*s_v)[88], uint8_t (*s_g)[88],
+                                             uint8_t* __restrict__ dst, int dx0, int dy0, int sx0, int sy0, int w, int h,
+                                             int ws, int hs, int tid);
+
 __global__ void __launch_bounds__(SC_THREADS)
 scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int w, int h, int ws, int hs) {
   __shared__ __align__(16) uint8_t s_in[SC_IH][SC_IW];
@@ -394,7 +333,13 @@ scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int
     }
   }
   __syncthreads();
-  blur5_tile_packed<4, 56, 136>(&s_in[0][0], SC_IW, SC_IH, SC_IW / 4, &s_v[0][0], SC_IW, &s_g[0][0], SC_IW, tid, SC_THREADS);
+  scale08_tile(&s_in[0][0], SC_IW, s_v, s_g, dst, dx0, dy0, sx0, sy0, w, h, ws, hs, tid);
+}
+
+__device__ __forceinline__ void scale08_tile(const uint8_t* s_in, int in_pitch, uint16_t (*s_v)[88], uint8_t (*s_g)[88],
+                                             uint8_t* __restrict__ dst, int dx0, int dy0, int sx0, int sy0, int w, int h,
+                                             int ws, int hs, int tid) {
+  blur5_tile_packed<4, 56, 136>(s_in, in_pitch, SC_IH, SC_IW / 4, &s_v[0][0], SC_IW, &s_g[0][0], SC_IW, tid, SC_THREADS);
   for (int i = tid; i < SC_TH * SC_TW; i += SC_THREADS) {
     int r = i >> 6, c = i & 63;  // SC_TW == 64
     int dx = dx0 + c, dy = dy0 + r;
@@ -411,10 +356,32 @@ scale08_kernel(const uint8_t* __restrict__ src_, uint8_t* __restrict__ dst_, int
   }
 }
 
+// The same with the source block brought in by the TMA unit: sx0 is a multiple of 80 (dx0 of 64), so the box starts
+// at sx0 - 16 and is 112 bytes wide for the 88 used (columns 12 .. 99).
+constexpr int SCT_PITCH = 112, SCT_X = 16;
+__global__ void __launch_bounds__(SC_THREADS)
+scale08_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ dst_, int w, int h, int ws, int hs) {
+  __shared__ __align__(128) uint8_t s_in[SC_IH][SCT_PITCH];
+  __shared__ __align__(16) uint16_t s_v[SC_GH][SC_IW];
+  __shared__ __align__(16) uint8_t s_g[SC_GH][SC_IW];
+  __shared__ __align__(8) unsigned long long s_bar;
+  uint8_t* dst = dst_ + (size_t)blockIdx.z * ws * hs;
+  const int dx0 = blockIdx.x * SC_TW, dy0 = blockIdx.y * SC_TH;
+  const int sx0 = (10 * dx0 + 1) >> 3, sy0 = (10 * dy0 + 1) >> 3;
+  tma_load_box_3d(&tmap, &s_in[0][0], &s_bar, sx0 - SCT_X, sy0 - 2, (int)blockIdx.z, SC_IH * SCT_PITCH);
+  if (sx0 - 4 < 0 || sx0 + SC_IW - 4 > w || sy0 - 2 < 0 || sy0 - 2 + SC_IH > h)
+    tma_reflect_fix(&s_in[0][0], SCT_PITCH, SC_IH, SCT_X - 4, SC_IW, sx0 - SCT_X, sy0 - 2, w, h, SC_THREADS);
+  scale08_tile(&s_in[0][SCT_X - 4], SCT_PITCH, s_v, s_g, dst, dx0, dy0, sx0, sy0, w, h, ws, hs, threadIdx.x);
+}
+
 void launch_scale08(const uint8_t* src, uint8_t* dst, int w, int h, int ws, int hs, int batch,
                     cudaStream_t st) {
   dim3 grid((ws + SC_TW - 1) / SC_TW, (hs + SC_TH - 1) / SC_TH, batch);
-  scale08_kernel<<<grid, SC_THREADS, 0, st>>>(src, dst, w, h, ws, hs);
+  CUtensorMap tm;
+  if (make_u8_frames_tmap(&tm, src, w, h, batch, SCT_PITCH, SC_IH))
+    scale08_tma_kernel<<<grid, SC_THREADS, 0, st>>>(tm, dst, w, h, ws, hs);
+  else
+    scale08_kernel<<<grid, SC_THREADS, 0, st>>>(src, dst, w, h, ws, hs);
 }
 
 }  // namespace vpl
