@@ -1365,6 +1365,24 @@ def main():
     launches = ctx.kernel_launches() - l0
     clocks = sampler.stop()
 
+    # ---- latency of ONE frame through the same C ABI (host buffer in, host results out), outside the timed regions
+    latency = None
+    if rank == 0:
+        ctx.set_profile(True)
+        one = np.ascontiguousarray(batch_frames[:1])
+        for _ in range(2):
+            ctx.frontend_batch(one, scale=2, num_octaves=OCT, k=0)
+        ctx.reset_stage_times()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            ctx.frontend_batch(one, scale=2, num_octaves=OCT, k=0)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        st1 = ctx.stage_times()
+        latency = {"frames": 1, "e2e_ms_median": float(np.median(ts)), "region_engine_ms": st1["region"][0] / 5.0,
+                   "note": "vpl_frontend_batch on one frame: upload, every kernel, download; median of 5 calls"}
+        ctx.set_profile(False)
+
     # max over ranks
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
@@ -1408,6 +1426,8 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "region_engine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum per frame of the committed ncu --set full "
+                                  "capture (profiles/engine_traffic.json) x frames per launch; not measured in this run",
                 "ms_per_launch": eng_dur, "algorithmic_bytes_per_launch": eng_bytes,
                 "note": "latency-bound by the sequential seed/FIFO order of LSD region growing; see DESIGN.md",
                 "issue_rate": issue,
@@ -1421,7 +1441,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "latency": latency}
     if rank == 0:
         line["parity_checked"] = bool(parity and parity["checked"])
         line["parity"] = parity
