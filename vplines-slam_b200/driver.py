@@ -171,7 +171,15 @@ class LinePipeline:
     points on the frame's own lines; line_feature_tracker.cpp:56-288).  Batches, and shards of different
     ranks, overlap by one frame so that every consecutive pair is matched exactly once; the overlap frame's
     vanishing points are computed twice and delivered once.  frame_count0 of a batch is the index of its first
-    frame: only frame 0 of the whole sequence is the object's first call."""
+    frame: only frame 0 of the whole sequence is the object's first call.
+
+    This is the four pixel stages chained on every frame's RAW line set, not a replay of the tracker object:
+    in the reference the first image never reaches the vanishing-point call (it sits inside
+    `if (curframe_->vecLine.size() > 0)`, line_feature_tracker.cpp:109), so the stage's frame_count 0 falls on the SECOND
+    image and its vps[1] / vps[2] swap rule starts one frame later than here; the reference only calls the stage on
+    frames that keep more than 2 lines and does not count the others; and it matches against the previous frame's
+    SELECTED, re-ordered line set.  For those semantics use the tracker object (compat/linefeature_tracker_b200.hpp /
+    oracle.orc_tracker.Tracker), which restates that bookkeeping and is pinned against the reference's own readImage."""
 
     def __init__(self, ctx, smoothed=True):
         self.ctx = ctx
