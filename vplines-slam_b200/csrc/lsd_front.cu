@@ -105,17 +105,19 @@ void launch_cssn_lut(float2* lut, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
-// K4.  One 1024-thread CTA per frame.  Warp w owns a contiguous block of rows; phase A
+// K4.  One 512-thread CTA per frame (64 KB of counters: three CTAs share an SM; the kernel is bound by the latency of its
+// row loads, so frames in flight per SM are what counts -- round 1 ran one 1024-thread CTA with 128 KB per SM).
+// Warp w owns a contiguous block of rows; phase A
 // computes every pixel's bin (kept as u16 in a scratch plane) and builds per-warp
 // histograms in shared memory, phase B turns them into per-(warp,bin) output offsets
 // (bins descending, warps ascending => raster order inside a bin), phase C re-walks
 // the rows and scatters with a match_any rank.  No global atomics, deterministic.
 // Algorithmic bytes: read S (u8) + 2 S write + 2 S read (u16 bins), write 4 B per defined pixel.
 // ---------------------------------------------------------------------------
-constexpr int ORD_THREADS = 1024;
+constexpr int ORD_THREADS = 512;
 constexpr int ORD_WARPS = ORD_THREADS / 32;
 
-__global__ void __launch_bounds__(ORD_THREADS, 1)
+__global__ void __launch_bounds__(ORD_THREADS, 3)
 order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ maxq, int* __restrict__ ord,
              int* __restrict__ n_ord, uint16_t* __restrict__ bins_, size_t bins_stride, int ws, int hs, double rho) {
   extern __shared__ unsigned int s_cnt[];  // [ORD_WARPS][kBins]
@@ -168,26 +170,28 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
   }
   __syncthreads();
 
-  // phase B: thread b owns bin b.  total[b], then suffix scan over bins (descending order).
-  unsigned int total = 0;
-  for (int w = 0; w < ORD_WARPS; ++w) total += s_cnt[w * kBins + tid];
+  // phase B: thread t owns the bins 2t and 2t+1.  Totals, then suffix scan over bins (descending order).
+  const int b0 = 2 * tid, b1 = 2 * tid + 1;
+  unsigned int t0 = 0, t1 = 0;
+  for (int w = 0; w < ORD_WARPS; ++w) { t0 += s_cnt[w * kBins + b0]; t1 += s_cnt[w * kBins + b1]; }
+  const unsigned int total = t0 + t1;
   unsigned int v = total;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     unsigned int t = __shfl_down_sync(0xffffffffu, v, o);
     if (lane + o < 32) v += t;
   }
-  if (lane == 0) s_scan[wid] = v;  // sum of this warp's 32 bins
+  if (lane == 0) s_scan[wid] = v;  // sum of this warp's 64 bins
   __syncthreads();
   unsigned int higher = 0;  // points in the bins of higher warps
   for (int w = wid + 1; w < ORD_WARPS; ++w) higher += s_scan[w];
-  unsigned int start = higher + v - total;  // number of points in bins > b
+  const unsigned int start1 = higher + v - total;  // number of points in bins > b1
   if (tid == 0) n_ord[f] = (int)(higher + v);
-  unsigned int run = start;
+  unsigned int run1 = start1, run0 = start1 + t1;   // bin b1 comes before bin b0 (descending)
   for (int w = 0; w < ORD_WARPS; ++w) {
-    unsigned int c = s_cnt[w * kBins + tid];
-    s_cnt[w * kBins + tid] = run;
-    run += c;
+    unsigned int c1 = s_cnt[w * kBins + b1], c0 = s_cnt[w * kBins + b0];
+    s_cnt[w * kBins + b1] = run1; run1 += c1;
+    s_cnt[w * kBins + b0] = run0; run0 += c0;
   }
   __syncthreads();
 
