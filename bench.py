@@ -165,7 +165,8 @@ def lsd_config(args, wl, world):
     return {"workload": wl["name"], "frames_per_step": args.batch, "width": W, "height": H, "octaves": wl["octaves"],
             "match_k": wl["k"], "unique_frames": args.unique, "slots": args.slots,
             "max_lines": args.max_lines or wl["max_lines"],
-            "parallelism": f"frames x{world}" + (" (distinct frames per rank: seed + 7919 rank)" if world > 1 else ""),
+            "parallelism": f"frames x{world}" + (f" (rank r's frames: the {args.unique} distinct frames rotated by r*{args.unique}//{world})"
+                                                 if world > 1 else ""),
             "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (args.batch * W * H / 1e6)}
 
 
@@ -1217,6 +1218,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the last timed e2e step")
     ap.add_argument("--parity-frames", type=int, default=6, help="frames of the last e2e step compared with the oracle")
+    ap.add_argument("--no-upload-ahead", dest="upload_ahead", action="store_false",
+                    help="e2e: upload a slot's next batch only after its collect (round-1 behaviour)")
+    ap.add_argument("--stress-upload-passes", type=int, default=0,
+                    help="experiments: upload every batch this many extra times (a slow host link on one GPU)")
+    ap.add_argument("--e2e-only", action="store_true",
+                    help="experiments: print only the end-to-end figure (host buffers in and out) and exit")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the resident steps (for ncu --profile-from-start off; V workloads)")
     args = ap.parse_args()
@@ -1250,13 +1257,15 @@ def main():
     B, S, cap, K = args.batch, args.slots, (args.max_lines or wl["max_lines"]), wl["k"]
     wl_name = wl["name"]
 
-    # weak scaling: every rank owns `steps*batch` frames of the job's sequence, and DISTINCT ones: rank r's part is a
-    # tiling of `unique` frames drawn with seed + 7919 r (the real-frame workload rotates the bundled frames by r).
-    # Its shard starts one frame early (halo = the last frame of rank r-1's part) so that the pair across the shard
-    # boundary is matched exactly once, on rank r.
+    # weak scaling: every rank owns `steps*batch` frames of the job's sequence.  Ranks hold DIFFERENT frames at every
+    # position (rank r's part is the tiling of the `unique` frames rotated by r*unique//world) but the same multiset of
+    # frames as the 1-GPU run, so that v_N / (N v_1) compares equal loads: frames drawn with another seed per rank carry
+    # 209 to 278 lines per frame (oracle count over seeds + 7919 r), and the max over ranks then measures the content.
+    # A rank's shard starts one frame early (halo = the last frame of rank r-1's part) so that the pair across the
+    # shard boundary is matched exactly once, on rank r.
     def rank_frames(r):
-        u = make_frames(args.unique, args.seed + 7919 * r, args.workload)
-        return np.roll(u, -r, axis=0) if WORKLOADS[args.workload].get("frames", args.workload) == "C1" else u
+        u = make_frames(args.unique, args.seed, args.workload)
+        return np.roll(u, -((r * args.unique) // world), axis=0)
 
     unique = rank_frames(rank)
     halo = 1 if rank > 0 else 0
@@ -1287,16 +1296,27 @@ def main():
         torch.cuda.synchronize()
 
     def e2e_steps(n_steps, first_has_halo):
-        """n_steps batches through submit/collect, pipelined over the slots."""
+        """n_steps batches through submit/collect, pipelined over the slots.  With upload-ahead (the default) the
+        frames of batch i + slots go to the device (vpl_frontend_upload, a copy stream of its own) as soon as batch i
+        has been submitted, so the copy overlaps kernels instead of following the slot's collect."""
         pending = []
         lines = 0
+        ahead = [False] * S
         for i in range(n_steps):
             s = i % S
             if len(pending) == S:
                 ps = pending.pop(0)
                 ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
-            fr = host_buf if (i == 0 and first_has_halo) else batch_frames
-            ctx.submit(s, fr, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
+            if ahead[s]:
+                ctx.submit_uploaded(s, B, W, H, scale=2, num_octaves=OCT, k=K, chain=True)
+                ahead[s] = False
+            else:
+                fr = host_buf if (i == 0 and first_has_halo) else batch_frames
+                ctx.submit(s, fr, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
+            if args.upload_ahead and i + S < n_steps:
+                for _ in range(1 + args.stress_upload_passes):
+                    ctx.upload(s, batch_frames)
+                ahead[s] = True
             pending.append(s)
         while pending:
             ps = pending.pop(0)
@@ -1307,6 +1327,7 @@ def main():
     # ---- warm-up (also leaves a batch resident in every slot)
     e2e_steps(max(args.warmup, S), False)
     barrier()
+    ctx.reset_stage_times()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -1321,6 +1342,26 @@ def main():
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
+
+    if args.e2e_only:
+        sampler.stop()
+        st_e2e = ctx.stage_times()
+        per_rank = e2e_ms
+        if dist is not None:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [round(float(x[0]) / args.steps, 2) for x in allt]
+            e2e_ms = max(float(x[0]) for x in allt)
+        if rank == 0:
+            print(json.dumps({"e2e_only": True, "n_gpus": world, "slots": S, "frames_per_step": B, "steps": args.steps,
+                              "e2e_frames_per_s": B * args.steps * world / (e2e_ms * 1e-3),
+                              "upload_ahead": bool(args.upload_ahead),
+                              "rank0_h2d_ms_per_step": st_e2e["h2d"][0] / args.steps,
+                              "ms_per_step": e2e_ms / args.steps, "ms_per_step_by_rank": per_rank}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- parity of what the timed e2e region just produced (outside the timed regions, rank 0): frames of the last
     # collected step against the CPU oracle chain, bit for bit

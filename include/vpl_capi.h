@@ -330,6 +330,16 @@ int vpl_frontend_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, i
                         size_t stride, int scale, int num_octaves, int k, int chain);
 int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_t* counts, int cap,
                          uint8_t* desc, VplDMatch* matches);
+/* Upload ahead: copies the NEXT batch of slot s to the device on a copy stream of its own, into a
+ * second input buffer of the slot, and returns without waiting -- allowed while the slot's current
+ * batch is in flight, so the host-to-device copy of batch i+num_slots overlaps the kernels of batch
+ * i instead of following its collect.  The next vpl_frontend_submit on that slot takes these frames
+ * when it is called with imgs == NULL (n, w, h as uploaded).  The frames have to be contiguous
+ * (stride == w, imgs[f] == imgs[0] + f*w*h), inside a vpl_host_register range, and left untouched
+ * until that batch is collected.  (The reference has no counterpart: its readImage,
+ * feature_tracker/src/line_feature_tracker.cpp:52, is handed one decoded frame at a time.) */
+int vpl_frontend_upload(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h,
+                        size_t stride);
 
 /* Dense form of collect: the batch's KeyLines / descriptors / matches come back packed frame
  * after frame (frame f's rows start at sum(counts[0..f))), cap_total rows of capacity,

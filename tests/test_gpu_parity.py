@@ -353,9 +353,10 @@ def test_errors(ctx, vpl):
     assert vpl.BinaryDescriptorMatcher().match(np.zeros((0, 32), np.uint8), np.zeros((4, 32), np.uint8)) == []
 
 
-def _bench_path(vpl, frames, n_batches, k, octaves, cap):
+def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False):
     """The exact call sequence bench.py times end to end: caller frames pinned with vpl_host_register, batches
-    submitted to alternating slots with chaining, results collected in dense form into registered buffers."""
+    submitted to alternating slots with chaining (the frames of batch i + 2 uploaded ahead with vpl_frontend_upload
+    while batch i runs, if asked), results collected in dense form into registered buffers."""
     frames = np.ascontiguousarray(frames)
     n, h, w = frames.shape
     per = (n + n_batches - 1) // n_batches
@@ -379,27 +380,36 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap):
             outs.append((lo, hi, counts[ps][:hi - lo].copy(), kl[ps][:total].copy(), desc[ps][:total].copy(),
                          mt[ps][:total].copy()))
 
+        ahead = [False] * S
         for i in range(n_batches):
             s = i % S
             if len(pending) == S:
                 collect()
             lo, hi = i * per, min(n, (i + 1) * per)
-            c.submit(s, frames[lo:hi], scale=2, num_octaves=octaves, k=k, chain=(i > 0))
+            if ahead[s]:
+                c.submit_uploaded(s, hi - lo, w, h, scale=2, num_octaves=octaves, k=k, chain=True)
+                ahead[s] = False
+            else:
+                c.submit(s, frames[lo:hi], scale=2, num_octaves=octaves, k=k, chain=(i > 0))
+            if upload_ahead and i + S < n_batches:
+                c.upload(s, frames[(i + S) * per:min(n, (i + S + 1) * per)])
+                ahead[s] = True
             pending.append((s, lo, hi))
         while pending:
             collect()
     return outs
 
 
-@pytest.mark.parametrize("name,n,batches,k,octaves,cap", [("C2_euroc_752x480", 33, 3, 1, 1, 1024),
-                                                          ("C3_d455_1280x720", 9, 3, 2, 2, 2048)])
-def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves, cap):
+@pytest.mark.parametrize("name,n,batches,k,octaves,cap,ahead", [("C2_euroc_752x480", 33, 3, 1, 1, 1024, False),
+                                                                ("C2_euroc_752x480", 33, 5, 1, 1, 1024, True),
+                                                                ("C3_d455_1280x720", 9, 3, 2, 2, 2048, False)])
+def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves, cap, ahead):
     """The headline configs through bench.py's own path (host_register + submit(chain) over three batches +
     collect_dense) against the oracle chain: every KeyLine, descriptor and match of every frame bit-equal; the
     first frame of a later batch is matched against the last frame of the batch before it."""
     import bench
     frames = np.ascontiguousarray(synth.config_sequence(name, n))
-    outs = _bench_path(vpl, frames, batches, k, octaves, cap)
+    outs = _bench_path(vpl, frames, batches, k, octaves, cap, ahead)
     assert [o[0] for o in outs] == [i * ((n + batches - 1) // batches) for i in range(batches)]
     n_lines = 0
     for lo, hi, counts, kl, desc, mt in outs:
@@ -408,6 +418,25 @@ def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves
         assert bad == [], (name, lo, bad)
         n_lines += int(counts.sum())
     assert n_lines > 50 * n
+
+
+def test_upload_ahead_argument_errors(vpl, synth):
+    frames = np.ascontiguousarray(synth.config_sequence("C2_euroc_752x480", 4))
+    with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=1024, max_batch=4, num_slots=2) as c:
+        with pytest.raises(vpl.capi.VplError, match="no uploaded batch"):
+            c.submit_uploaded(0, 4, 752, 480)
+        with pytest.raises(vpl.capi.VplError, match="vpl_host_register"):
+            c.upload(0, frames)  # not pinned
+        c.host_register(frames)
+        c.upload(0, frames[:3])
+        with pytest.raises(vpl.capi.VplError, match="uploaded batch of 3 frames"):
+            c.submit_uploaded(0, 4, 752, 480)
+        c.submit_uploaded(0, 3, 752, 480, k=0)
+        kl = np.zeros(3 * 1024, vpl.capi.KEYLINE_DTYPE); counts = np.zeros(3, np.int32)
+        d = np.zeros((3 * 1024, 32), np.uint8); m = np.zeros((3 * 1024, 1), vpl.capi.DMATCH_DTYPE)
+        total = c.collect_dense_into(0, counts, kl, d, m)
+        ref = c.frontend_batch(frames[:3], k=0)[0]
+        assert total == sum(len(r) for r in ref) and kl[:len(ref[0])].tobytes() == ref[0].tobytes()
 
 
 @pytest.mark.parametrize("cap", [64, 512, 4096])

@@ -73,7 +73,7 @@ class LineMatchParam(C.Structure):
 EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_lbd_compute_float_batch", "vpl_match_batch", "vpl_frontend_batch",
-    "vpl_frontend_submit", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
+    "vpl_frontend_submit", "vpl_frontend_upload", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
     "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
     "vpl_set_preprocess", "vpl_preprocess_batch",
     "vpl_edlines_default_param", "vpl_edlines_configure", "vpl_edlines_detect_batch", "vpl_edlines_submit",
@@ -119,6 +119,7 @@ def load():
     L.vpl_match_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
     L.vpl_frontend_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32, i32, i32, i32]
+    L.vpl_frontend_upload.argtypes = [vp, i32, vp, i32, i32, i32, sz]
     L.vpl_frontend_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
     L.vpl_sync.argtypes = [vp]
@@ -323,6 +324,18 @@ class Context:
         ptrs, keep, n, w, h, stride = _img_ptrs(frames)
         self._ck(self._L.vpl_frontend_submit(self._h, slot, ptrs, n, w, h, stride, scale, num_octaves, k,
                                              int(chain)))
+        return n
+
+    def upload(self, slot, frames):
+        """Upload the slot's NEXT batch while its current one is in flight (vpl_frontend_upload); frames: a
+        contiguous (n, h, w) array inside a host_register range."""
+        ptrs, keep, n, w, h, stride = _img_ptrs(frames)
+        self._ck(self._L.vpl_frontend_upload(self._h, slot, ptrs, n, w, h, stride))
+        return n
+
+    def submit_uploaded(self, slot, n, w, h, scale=2, num_octaves=1, k=1, chain=False):
+        """vpl_frontend_submit with imgs == NULL: run the batch that `upload` staged on this slot."""
+        self._ck(self._L.vpl_frontend_submit(self._h, slot, None, n, w, h, w, scale, num_octaves, k, int(chain)))
         return n
 
     def collect_into(self, slot, kl, counts, cap, desc, matches):

@@ -54,6 +54,11 @@ struct Slot {
   cudaEvent_t ev[VPL_NUM_STAGES][2];
   bool ev_used[VPL_NUM_STAGES];
   uint8_t* d_img = nullptr;
+  // vpl_frontend_upload: the slot's NEXT batch, copied on a stream of its own while the current batch runs
+  uint8_t* d_img_next = nullptr;
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t uploaded = nullptr;
+  int staged_n = 0, staged_w = 0, staged_h = 0;
   uint8_t* d_pre = nullptr;   // remap output (pre-processing scratch)
   uint8_t* d_raw = nullptr;   // raw frames as uploaded, kept when pre-processing is on (resident re-runs of the fused path)
   uint8_t* d_lut = nullptr;   // CLAHE tile LUTs, B x 256 tiles max x 256
@@ -544,6 +549,18 @@ int run_preprocess(VplContext* c, Slot& s, const uint8_t* src, int n, int w, int
   return VPL_OK;
 }
 
+// what follows the host->device copy of a batch: the optional pre-processing of the frames now in d_img
+int after_upload(VplContext* c, Slot& s, int n, int w, int h) {
+  if (c->pre_remap || c->pre_clip > 0.0) {
+    if (w != c->pre_w || h != c->pre_h)
+      return fail(c, VPL_E_INVALID, "pre-processing was configured for %dx%d images, got %dx%d", c->pre_w, c->pre_h, w, h);
+    if (s.d_raw)  // keep the raw frames: the fused path can be re-run on them
+      CK(c, cudaMemcpyAsync(s.d_raw, s.d_img, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
+    return run_preprocess(c, s, s.d_img, n, w, h);
+  }
+  return VPL_OK;
+}
+
 int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
   if (stride < (size_t)w) return fail(c, VPL_E_INVALID, "stride %zu < width %d", stride, w);
   for (int f = 0; f < n; ++f)
@@ -557,14 +574,7 @@ int upload(VplContext* c, Slot& s, const uint8_t* const* imgs, int n, int w, int
     StageTimer t(c, s, VPL_STAGE_H2D);
     CK(c, cudaMemcpyAsync(s.d_img, direct ? imgs[0] : s.h_img, (size_t)n * w * h, cudaMemcpyHostToDevice, s.stream));
   }
-  if (c->pre_remap || c->pre_clip > 0.0) {
-    if (w != c->pre_w || h != c->pre_h)
-      return fail(c, VPL_E_INVALID, "pre-processing was configured for %dx%d images, got %dx%d", c->pre_w, c->pre_h, w, h);
-    if (s.d_raw)  // keep the raw frames: the fused path can be re-run on them
-      CK(c, cudaMemcpyAsync(s.d_raw, s.d_img, (size_t)n * w * h, cudaMemcpyDeviceToDevice, s.stream));
-    return run_preprocess(c, s, s.d_img, n, w, h);
-  }
-  return VPL_OK;
+  return after_upload(c, s, n, w, h);
 }
 
 int finish(VplContext* c, Slot& s) {
@@ -846,6 +856,9 @@ void vpl_destroy(VplContext* c) {
   cudaFree(c->d_vp_lambda);
   for (Slot& s : c->slots) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
+    cudaFree(s.d_img_next);
+    if (s.up_stream) cudaStreamDestroy(s.up_stream);
+    if (s.uploaded) cudaEventDestroy(s.uploaded);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
       cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.spec_tag); cudaFree(b.spec_arena); cudaFree(b.eng_desc); cudaFree(b.eng_rects); cudaFree(b.ord);
@@ -1003,8 +1016,22 @@ int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int
   CK(c, cudaSetDevice(c->cfg.device));
   Slot& s = c->slots[slot];
   if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (!imgs) {
+    // the frames were staged by vpl_frontend_upload: make its buffer the slot's input
+    if (s.staged_n == 0) return fail(c, VPL_E_INVALID, "imgs == NULL but slot %d holds no uploaded batch (vpl_frontend_upload)", slot);
+    if (s.staged_n != n || s.staged_w != w || s.staged_h != h)
+      return fail(c, VPL_E_INVALID, "slot %d holds an uploaded batch of %d frames %dx%d, submit asks for %d frames %dx%d",
+                  slot, s.staged_n, s.staged_w, s.staged_h, n, w, h);
+  }
   s.n = n; s.w = w; s.h = h; s.num_octaves = num_octaves; s.scale = scale; s.k = k;
-  r = upload(c, s, imgs, n, w, h, stride);
+  if (imgs) {
+    r = upload(c, s, imgs, n, w, h, stride);
+  } else {
+    std::swap(s.d_img, s.d_img_next);
+    s.staged_n = 0;
+    CK(c, cudaStreamWaitEvent(s.stream, s.uploaded, 0));
+    r = after_upload(c, s, n, w, h);
+  }
   if (r) return r;
   r = enqueue_frontend(c, slot, k, chain);
   if (r) return r;
@@ -1014,6 +1041,36 @@ int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int
   s.kind = BK_FRONTEND;
   s.resident = BK_FRONTEND;
   CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_frontend_upload(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride) {
+  if (!c) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (n <= 0 || n > c->cfg.max_batch || w <= 0 || h <= 0 || w > c->cfg.max_width || h > c->cfg.max_height)
+    return fail(c, VPL_E_INVALID, "upload of %d frames %dx%d outside the context's limits (%d frames %dx%d)", n, w, h,
+                c->cfg.max_batch, c->cfg.max_width, c->cfg.max_height);
+  if (stride != (size_t)w) return fail(c, VPL_E_INVALID, "vpl_frontend_upload takes dense frames (stride == width)");
+  for (int f = 0; f < n; ++f)
+    if (!imgs || !imgs[f]) return fail(c, VPL_E_INVALID, "null image pointer at frame %d", f);
+  for (int f = 1; f < n; ++f)
+    if (imgs[f] != imgs[0] + (size_t)f * w * h)
+      return fail(c, VPL_E_INVALID, "vpl_frontend_upload takes frames that are contiguous in memory (frame %d is not)", f);
+  // the copy runs while the slot's staging buffer may still feed the batch in flight: it has to come straight from
+  // the caller's memory, which therefore has to be pinned
+  if (!in_registered_range(c, imgs[0], (size_t)n * w * h))
+    return fail(c, VPL_E_INVALID, "vpl_frontend_upload takes frames in memory pinned through vpl_host_register");
+  CK(c, cudaSetDevice(c->cfg.device));
+  Slot& s = c->slots[slot];
+  if (!s.up_stream) {
+    CK(c, cudaStreamCreateWithFlags(&s.up_stream, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+    CK(c, dmalloc(&s.d_img_next, (size_t)c->cfg.max_batch * c->cfg.max_width * c->cfg.max_height));
+  }
+  // d_img_next was the input of the batch before the one in flight (collected, or never used): free to overwrite
+  CK(c, cudaMemcpyAsync(s.d_img_next, imgs[0], (size_t)n * w * h, cudaMemcpyHostToDevice, s.up_stream));
+  CK(c, cudaEventRecord(s.uploaded, s.up_stream));
+  s.staged_n = n; s.staged_w = w; s.staged_h = h;
   return VPL_OK;
 }
 
