@@ -1296,27 +1296,34 @@ def main():
         torch.cuda.synchronize()
 
     def e2e_steps(n_steps, first_has_halo):
-        """n_steps batches through submit/collect, pipelined over the slots.  With upload-ahead (the default) the
-        frames of batch i + slots go to the device (vpl_frontend_upload, a copy stream of its own) as soon as batch i
-        has been submitted, so the copy overlaps kernels instead of following the slot's collect."""
+        """n_steps batches through (upload,) submit and collect, pipelined over the slots.  With upload-ahead (the
+        default) every batch goes to the device through vpl_frontend_upload -- one copy stream for the context, so the
+        batches arrive in order -- up to `slots` batches ahead of the one being submitted: the copy of batch i + slots
+        overlaps the kernels of batch i instead of following the slot's collect."""
         pending = []
         lines = 0
-        ahead = [False] * S
+
+        def frames_of(i):
+            return host_buf if (i == 0 and first_has_halo) else batch_frames
+
+        def upload(i):
+            for _ in range(1 + args.stress_upload_passes):
+                ctx.upload(i % S, frames_of(i))
+
+        if args.upload_ahead:
+            for i in range(min(S, n_steps)):
+                upload(i)
         for i in range(n_steps):
             s = i % S
             if len(pending) == S:
                 ps = pending.pop(0)
                 ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
-            if ahead[s]:
-                ctx.submit_uploaded(s, B, W, H, scale=2, num_octaves=OCT, k=K, chain=True)
-                ahead[s] = False
+            if args.upload_ahead:
+                ctx.submit_uploaded(s, len(frames_of(i)), W, H, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
+                if i + S < n_steps:
+                    upload(i + S)
             else:
-                fr = host_buf if (i == 0 and first_has_halo) else batch_frames
-                ctx.submit(s, fr, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
-            if args.upload_ahead and i + S < n_steps:
-                for _ in range(1 + args.stress_upload_passes):
-                    ctx.upload(s, batch_frames)
-                ahead[s] = True
+                ctx.submit(s, frames_of(i), scale=2, num_octaves=OCT, k=K, chain=(i > 0))
             pending.append(s)
         while pending:
             ps = pending.pop(0)

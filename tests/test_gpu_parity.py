@@ -380,20 +380,23 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False):
             outs.append((lo, hi, counts[ps][:hi - lo].copy(), kl[ps][:total].copy(), desc[ps][:total].copy(),
                          mt[ps][:total].copy()))
 
-        ahead = [False] * S
+        def rng(i):
+            return i * per, min(n, (i + 1) * per)
+
+        if upload_ahead:
+            for i in range(min(S, n_batches)):
+                c.upload(i % S, frames[slice(*rng(i))])
         for i in range(n_batches):
             s = i % S
             if len(pending) == S:
                 collect()
-            lo, hi = i * per, min(n, (i + 1) * per)
-            if ahead[s]:
-                c.submit_uploaded(s, hi - lo, w, h, scale=2, num_octaves=octaves, k=k, chain=True)
-                ahead[s] = False
+            lo, hi = rng(i)
+            if upload_ahead:
+                c.submit_uploaded(s, hi - lo, w, h, scale=2, num_octaves=octaves, k=k, chain=(i > 0))
+                if i + S < n_batches:
+                    c.upload(s, frames[slice(*rng(i + S))])
             else:
                 c.submit(s, frames[lo:hi], scale=2, num_octaves=octaves, k=k, chain=(i > 0))
-            if upload_ahead and i + S < n_batches:
-                c.upload(s, frames[(i + S) * per:min(n, (i + S + 1) * per)])
-                ahead[s] = True
             pending.append((s, lo, hi))
         while pending:
             collect()

@@ -56,7 +56,6 @@ struct Slot {
   uint8_t* d_img = nullptr;
   // vpl_frontend_upload: the slot's NEXT batch, copied on a stream of its own while the current batch runs
   uint8_t* d_img_next = nullptr;
-  cudaStream_t up_stream = nullptr;
   cudaEvent_t uploaded = nullptr;
   int staged_n = 0, staged_w = 0, staged_h = 0;
   uint8_t* d_pre = nullptr;   // remap output (pre-processing scratch)
@@ -150,6 +149,7 @@ struct VplContext {
   double* d_lgam = nullptr;  // log_gamma table for the NFA kernel
   int lgam_n = 0;
   std::vector<std::pair<const uint8_t*, size_t>> pinned;  // vpl_host_register ranges
+  cudaStream_t up_stream = nullptr;  // vpl_frontend_upload: ONE copy stream for all slots, so uploads reach the device in call order
   // optional pre-processing (readImage: remap + CLAHE)
   float* d_mapx = nullptr;
   float* d_mapy = nullptr;
@@ -857,7 +857,6 @@ void vpl_destroy(VplContext* c) {
   for (Slot& s : c->slots) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
     cudaFree(s.d_img_next);
-    if (s.up_stream) cudaStreamDestroy(s.up_stream);
     if (s.uploaded) cudaEventDestroy(s.uploaded);
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
@@ -881,6 +880,7 @@ void vpl_destroy(VplContext* c) {
         if (s.ev[i][j]) cudaEventDestroy(s.ev[i][j]);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
   delete c;
 }
 
@@ -1062,14 +1062,14 @@ int vpl_frontend_upload(VplContext* c, int slot, const uint8_t* const* imgs, int
     return fail(c, VPL_E_INVALID, "vpl_frontend_upload takes frames in memory pinned through vpl_host_register");
   CK(c, cudaSetDevice(c->cfg.device));
   Slot& s = c->slots[slot];
-  if (!s.up_stream) {
-    CK(c, cudaStreamCreateWithFlags(&s.up_stream, cudaStreamNonBlocking));
+  if (!c->up_stream) CK(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  if (!s.d_img_next) {
     CK(c, cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
     CK(c, dmalloc(&s.d_img_next, (size_t)c->cfg.max_batch * c->cfg.max_width * c->cfg.max_height));
   }
   // d_img_next was the input of the batch before the one in flight (collected, or never used): free to overwrite
-  CK(c, cudaMemcpyAsync(s.d_img_next, imgs[0], (size_t)n * w * h, cudaMemcpyHostToDevice, s.up_stream));
-  CK(c, cudaEventRecord(s.uploaded, s.up_stream));
+  CK(c, cudaMemcpyAsync(s.d_img_next, imgs[0], (size_t)n * w * h, cudaMemcpyHostToDevice, c->up_stream));
+  CK(c, cudaEventRecord(s.uploaded, c->up_stream));
   s.staged_n = n; s.staged_w = w; s.staged_h = h;
   return VPL_OK;
 }
