@@ -165,6 +165,8 @@ def lsd_config(args, wl, world):
     return {"workload": wl["name"], "frames_per_step": args.batch, "width": W, "height": H, "octaves": wl["octaves"],
             "match_k": wl["k"], "unique_frames": args.unique, "slots": args.slots,
             "max_lines": args.max_lines or wl["max_lines"],
+            "e2e_pipeline": ("frames uploaded ahead on a copy stream" if args.upload_ahead else "upload at submit") +
+                            ("; the slots' batches submitted back to back" if args.e2e_together else "; one slot at a time"),
             "parallelism": f"frames x{world}" + (f" (rank r's frames: the {args.unique} distinct frames rotated by r*{args.unique}//{world})"
                                                  if world > 1 else ""),
             "l2": "inputs per step (%.0f MB) and per-step working set exceed the 126 MB L2" % (args.batch * W * H / 1e6)}
@@ -1207,7 +1209,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="frames per step")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per step (0: 4736 = 32 frames per SM for C2, so that the engine launches of the two slots "
+                         "fill the 64 warp slots of every SM; 4096 for the other workloads)")
     ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--max-lines", type=int, default=0, help="KeyLine capacity per frame (0 = workload default)")
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -1222,11 +1226,19 @@ def main():
                     help="e2e: upload a slot's next batch only after its collect (round-1 behaviour)")
     ap.add_argument("--stress-upload-passes", type=int, default=0,
                     help="experiments: upload every batch this many extra times (a slow host link on one GPU)")
+    ap.add_argument("--e2e-staggered", action="store_true",
+                    help="e2e: collect and resubmit one slot at a time (round-1 behaviour) instead of submitting the "
+                         "slots' batches back to back")
+    ap.add_argument("--e2e-no-chain", action="store_true", help="experiments: no match across batch boundaries in the e2e pass")
+    ap.add_argument("--e2e-no-profile", action="store_true", help="experiments: stage events off during the e2e pass")
     ap.add_argument("--e2e-only", action="store_true",
                     help="experiments: print only the end-to-end figure (host buffers in and out) and exit")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the resident steps (for ncu --profile-from-start off; V workloads)")
     args = ap.parse_args()
+    if args.batch == 0:
+        args.batch = 4736 if args.workload == "C2" else 4096
+    args.e2e_together = args.upload_ahead and not args.e2e_staggered
     if args.impl == "reference":
         return run_reference(args)
 
@@ -1313,13 +1325,32 @@ def main():
         if args.upload_ahead:
             for i in range(min(S, n_steps)):
                 upload(i)
+        if args.e2e_together:
+            # the slots' batches are submitted back to back and collected together: every kernel of the path then runs
+            # next to the SAME kernel of the other slot -- two engine launches side by side fill the SMs' warp slots,
+            # which is what the latency-bound engine needs (52.1 k against 47.2 k frames/s for one slot at a time,
+            # profiles/r02_engine_wave_runs.txt)
+            for g in range(0, n_steps, S):
+                while pending:
+                    ps = pending.pop(0)
+                    ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
+                grp = range(g, min(g + S, n_steps))
+                for i in grp:
+                    ctx.submit_uploaded(i % S, len(frames_of(i)), W, H, scale=2, num_octaves=OCT, k=K,
+                                        chain=(i > 0 and not args.e2e_no_chain))
+                    pending.append(i % S)
+                for i in grp:
+                    if i + S < n_steps:
+                        upload(i + S)
+            n_steps = 0
         for i in range(n_steps):
             s = i % S
             if len(pending) == S:
                 ps = pending.pop(0)
                 ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
             if args.upload_ahead:
-                ctx.submit_uploaded(s, len(frames_of(i)), W, H, scale=2, num_octaves=OCT, k=K, chain=(i > 0))
+                ctx.submit_uploaded(s, len(frames_of(i)), W, H, scale=2, num_octaves=OCT, k=K,
+                                    chain=(i > 0 and not args.e2e_no_chain))
                 if i + S < n_steps:
                     upload(i + S)
             else:
@@ -1335,6 +1366,8 @@ def main():
     e2e_steps(max(args.warmup, S), False)
     barrier()
     ctx.reset_stage_times()
+    if args.e2e_no_profile:
+        ctx.set_profile(False)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -1406,6 +1439,10 @@ def main():
     ev0.record()
     for i in range(args.steps):
         ctx.run_resident(i % S, k=K)
+        # same pacing as the e2e pass: the slots' batches start together (their engine launches run side by side);
+        # left to themselves the two streams drift apart and the engine shares the SMs with the streaming kernels
+        if args.e2e_together and (i + 1) % S == 0:
+            ctx.sync()
     ctx.sync()
     ev1.record()
     barrier()

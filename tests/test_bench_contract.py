@@ -37,7 +37,7 @@ def test_reference_arm_line(extra):
     if not extra:  # the headline workload: the very `config` object the B200 arm prints (bench.lsd_config)
         import argparse
         import bench
-        a = argparse.Namespace(batch=4096, unique=96, slots=2, max_lines=0)
+        a = argparse.Namespace(batch=4736, unique=96, slots=2, max_lines=0, upload_ahead=True, e2e_together=True)
         assert d["config"] == bench.lsd_config(a, bench.WORKLOADS["C2"], 1)
         assert d["metric"] == bench.METRIC and d["sample_frames_per_step"] >= 2
 

@@ -477,3 +477,31 @@ def test_both_region_engines_against_oracle(vpl, orc, mh04, synth, kind):
         km = c.lsd_detect_batch(many)
         for f in range(len(many)):
             assert kl_fields_equal(km[f], kls[f % len(frames)]), (kind, f)
+
+
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_region_engine_builds_selected_by_launch_size(variant):
+    """The register budgets of the default engine (1 / 2 / 4 frames per block; the 32-register build is what large
+    launches take) are the same algorithm: forced through VPL_ENGINE_VARIANT in a process of their own, each gives the
+    oracle's KeyLines bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, importlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import vplines_slam_b200 as vpl\n"
+        "from oracle import oracle as O\n"
+        "O.build(); O.lib()\n"
+        "synth = importlib.import_module('vplines-slam_b200.synth')\n"
+        "frames = np.ascontiguousarray(synth.config_sequence('C2_euroc_752x480', 5))\n"
+        "with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=4096, max_batch=8, num_slots=1) as c:\n"
+        "    kls = c.lsd_detect_batch(frames)\n"
+        "for f in range(len(frames)):\n"
+        "    e = O.lsd_detector_detect(frames[f], 2, 1)\n"
+        "    assert len(e) > 50 and kls[f].tobytes() == e.tobytes(), f\n"
+        "print('ok')\n" % root)
+    env = dict(os.environ, VPL_ENGINE_VARIANT=str(variant))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -474,10 +474,14 @@ __device__ __forceinline__ void region_engine_body(const EngineArgs& A) {
 // Measured on B200 (C2, frames/s kernels-only at 4096 / 8192 frames per batch, same box, profiles/r02_engine_occupancy_variants.txt):
 //   1 frame/block,  32 blocks/SM (64 regs, 32 warps/SM)   the round-1 shape
 //   1 frame/block, no register cap (94 regs, 21 warps/SM) 44.4 k / 46.3 k
-//   2 frames/block, 21 blocks/SM (40 regs, 42 warps/SM)    49.5 k / 51.0 k   <- default
-//   2 frames/block, 25 blocks/SM (32 regs, 50 warps/SM)    51.8 k / 53.0 k   (more spills; within the box-to-box noise of the default)
+//   2 frames/block, 21 blocks/SM (40 regs, 50 warps/SM)    49.5 k / 51.0 k   <- launches of up to 3700 warps
+//   2 frames/block, 25 blocks/SM (32 regs, 64 warps/SM)    51.8 k / 53.0 k   <- larger launches
 //   4 frames/block, 12 blocks/SM (40 regs, 48 warps/SM)    50.2 k / 52.5 k
 //   4 frames/block, 10 blocks/SM (48 regs, 40 warps/SM)    48.5 k / 52.0 k
+// The engine is bound by the latency of one frame's sequential growth, so what counts is how many frames an SM holds: at
+// 32 registers all 64 warp slots of an SM can be engine warps (148 x 64 = 9472 frames in flight on the device).  Two
+// 4736-frame batches submitted back to back (their engine launches run side by side) reach 52.1 k frames/s end to end,
+// against 47.9 k for the 40-register build, whose 50 warps per SM cannot hold both (profiles/r02_engine_wave_runs.txt).
 __global__ void __launch_bounds__(32, 32) region_engine_kernel(EngineArgs A) { region_engine_body<1>(A); }
 __global__ void __launch_bounds__(64, 21) region_engine_kernel_w2(EngineArgs A) { region_engine_body<2>(A); }
 __global__ void __launch_bounds__(64, 25) region_engine_kernel_w2b(EngineArgs A) { region_engine_body<2>(A); }
@@ -485,8 +489,11 @@ __global__ void __launch_bounds__(128, 12) region_engine_kernel_w4(EngineArgs A)
 __global__ void __launch_bounds__(128, 10) region_engine_kernel_w4b(EngineArgs A) { region_engine_body<4>(A); }
 
 void launch_region_engine(const EngineArgs& a, cudaStream_t st) {
-  // VPL_ENGINE_VARIANT selects one of the builds above for measurement (0: 1 frame/block, 1: the default, 2..4)
-  static const int variant = [] { const char* v = getenv("VPL_ENGINE_VARIANT"); return v ? atoi(v) : 1; }();
+  // VPL_ENGINE_VARIANT selects one of the builds above for measurement (0: 1 frame/block, 1: 40 registers, 2: 32 registers,
+  // 3, 4: four frames per block); unset, large launches take the 32-register build and small ones the 40-register one
+  // (fewer spills; two such launches side by side still fit the 50 warps per SM it can hold)
+  static const int forced = [] { const char* v = getenv("VPL_ENGINE_VARIANT"); return v ? atoi(v) : -1; }();
+  const int variant = forced >= 0 ? forced : (a.batch * a.num_octaves > 3700 ? 2 : 1);
   dim3 grid(a.batch, a.num_octaves);
   if (variant == 1) {
     grid.x = (a.batch + 1) / 2;
