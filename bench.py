@@ -79,6 +79,9 @@ LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, L
 ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
 
+E2E_TRACE = []  # --e2e-trace: host and device times of one group of the e2e pass
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -1229,6 +1232,9 @@ def main():
     ap.add_argument("--e2e-staggered", action="store_true",
                     help="e2e: collect and resubmit one slot at a time (round-1 behaviour) instead of submitting the "
                          "slots' batches back to back")
+    ap.add_argument("--e2e-trace", action="store_true", help="experiments: host/device times of one group of the e2e pass")
+    ap.add_argument("--timeline", action="store_true",
+                    help="print where the stages of one group of resident batches lie in time on the device, and exit")
     ap.add_argument("--e2e-no-chain", action="store_true", help="experiments: no match across batch boundaries in the e2e pass")
     ap.add_argument("--e2e-no-profile", action="store_true", help="experiments: stage events off during the e2e pass")
     ap.add_argument("--e2e-only", action="store_true",
@@ -1326,22 +1332,41 @@ def main():
             for i in range(min(S, n_steps)):
                 upload(i)
         if args.e2e_together:
-            # the slots' batches are submitted back to back and collected together: every kernel of the path then runs
-            # next to the SAME kernel of the other slot -- two engine launches side by side fill the SMs' warp slots,
-            # which is what the latency-bound engine needs (52.1 k against 47.2 k frames/s for one slot at a time,
+            # the slots' batches are submitted as a group (vpl_frontend_submit_group) and collected together: every
+            # kernel of the path then runs next to the SAME kernel of the other slot, and the engine launches start
+            # behind a barrier across the group -- two of them side by side fill the SMs' warp slots, which is what the
+            # latency-bound engine needs (52.1 k against 47.2 k frames/s for one slot at a time,
             # profiles/r02_engine_wave_runs.txt)
+            t_grp = time.perf_counter()
             for g in range(0, n_steps, S):
+                tc = []
                 while pending:
                     ps = pending.pop(0)
+                    tc0 = time.perf_counter()
                     ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
+                    tc.append(round((time.perf_counter() - tc0) * 1e3, 3))
                 grp = range(g, min(g + S, n_steps))
-                for i in grp:
-                    ctx.submit_uploaded(i % S, len(frames_of(i)), W, H, scale=2, num_octaves=OCT, k=K,
-                                        chain=(i > 0 and not args.e2e_no_chain))
-                    pending.append(i % S)
+                trace = args.e2e_trace and g == 2 * S and n_steps > 3 * S
+                if trace:
+                    tr = {"since_last_uploads_ms": (time.perf_counter() - t_grp) * 1e3, "each_collect_ms": tc}
+                    ctx.mark()
+                    t0 = time.perf_counter()
+                t_grp = time.perf_counter()
+                ctx.submit_group([i % S for i in grp], [len(frames_of(i)) for i in grp], W, H, scale=2, num_octaves=OCT,
+                                 k=K, chain=[(i > 0 and not args.e2e_no_chain) for i in grp])
+                pending.extend(i % S for i in grp)
+                if trace:
+                    tr["t_submits_ms"] = (time.perf_counter() - t0) * 1e3
                 for i in grp:
                     if i + S < n_steps:
                         upload(i + S)
+                if trace:
+                    tr["t_uploads_ms"] = (time.perf_counter() - t0) * 1e3
+                    tr["timeline"] = {str(sl): {k: [round(a, 2), round(b, 2)] for k, (a, b) in ctx.timeline(sl).items()}
+                                      for sl in range(S)}
+                    tr["t_chains_done_ms"] = (time.perf_counter() - t0) * 1e3
+                    E2E_TRACE.append(tr)
+                t_grp = time.perf_counter()
             n_steps = 0
         for i in range(n_steps):
             s = i % S
@@ -1383,6 +1408,24 @@ def main():
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
 
+    if args.timeline:
+        sampler.stop()
+        for rep in range(2):
+            ctx.sync()
+            ctx.mark()
+            if args.e2e_together:
+                ctx.run_resident_group(list(range(S)), k=K)
+            else:
+                for sl in range(S):
+                    ctx.run_resident(sl, k=K)
+            tl = {sl: ctx.timeline(sl) for sl in range(S)}
+        if rank == 0:
+            print(json.dumps({"timeline_ms": {str(sl): {k: [round(a, 2), round(b, 2)] for k, (a, b) in tl[sl].items()}
+                                              for sl in tl}, "frames_per_step": B, "slots": S}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     if args.e2e_only:
         sampler.stop()
         st_e2e = ctx.stage_times()
@@ -1398,7 +1441,8 @@ def main():
                               "e2e_frames_per_s": B * args.steps * world / (e2e_ms * 1e-3),
                               "upload_ahead": bool(args.upload_ahead),
                               "rank0_h2d_ms_per_step": st_e2e["h2d"][0] / args.steps,
-                              "ms_per_step": e2e_ms / args.steps, "ms_per_step_by_rank": per_rank}))
+                              "ms_per_step": e2e_ms / args.steps, "ms_per_step_by_rank": per_rank,
+                              "trace": E2E_TRACE[-1:]}))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -1437,12 +1481,13 @@ def main():
     l0 = ctx.kernel_launches()
     barrier()
     ev0.record()
-    for i in range(args.steps):
-        ctx.run_resident(i % S, k=K)
-        # same pacing as the e2e pass: the slots' batches start together (their engine launches run side by side);
-        # left to themselves the two streams drift apart and the engine shares the SMs with the streaming kernels
-        if args.e2e_together and (i + 1) % S == 0:
-            ctx.sync()
+    if args.e2e_together:
+        # same grouping as the e2e pass: the slots' batches are enqueued as a group, engine launches behind a barrier
+        for g in range(0, args.steps, S):
+            ctx.run_resident_group([i % S for i in range(g, min(g + S, args.steps))], k=K)
+    else:
+        for i in range(args.steps):
+            ctx.run_resident(i % S, k=K)
     ctx.sync()
     ev1.record()
     barrier()

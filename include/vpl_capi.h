@@ -340,6 +340,16 @@ int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_
  * feature_tracker/src/line_feature_tracker.cpp:52, is handed one decoded frame at a time.) */
 int vpl_frontend_upload(VplContext* ctx, int slot, const uint8_t* const* imgs, int n, int w, int h,
                         size_t stride);
+/* Group form of vpl_frontend_submit for batches staged with vpl_frontend_upload: the batches of
+ * slots[0..n_slots) (n[i] frames each, all w x h) are enqueued together, each on its slot's stream,
+ * with a device-side barrier across the group in front of the region engine -- the engine launches
+ * of the group then start together and fill the SMs' warp slots between them (the engine is bound
+ * by the latency of one frame's sequential growth and wants 64 warps per SM; next to another
+ * slot's streaming kernels both lose).  chain[i] as in vpl_frontend_submit; slot slots[i] is
+ * matched against slots[i-1] of the group.  Each slot is collected on its own
+ * (vpl_frontend_collect / _collect_dense).  Nothing is enqueued if any slot is not ready. */
+int vpl_frontend_submit_group(VplContext* ctx, int n_slots, const int* slots, const int* n, int w,
+                              int h, int scale, int num_octaves, int k, const int* chain);
 
 /* Dense form of collect: the batch's KeyLines / descriptors / matches come back packed frame
  * after frame (frame f's rows start at sum(counts[0..f))), cap_total rows of capacity,
@@ -361,6 +371,8 @@ int64_t vpl_last_d2h_bytes(const VplContext* ctx, int slot);
  * n frames already in the context's device input buffer of slot s (filled by the
  * last submit on that slot), leaves results in HBM, does not synchronise. */
 int vpl_frontend_run_resident(VplContext* ctx, int slot, int k);
+/* The same for a group of slots, with the barrier of vpl_frontend_submit_group. */
+int vpl_frontend_run_resident_group(VplContext* ctx, int n_slots, const int* slots, int k);
 int vpl_sync(VplContext* ctx);
 
 /* ---- raw stages, exported for the parity tests ------------------------------ */
@@ -409,6 +421,11 @@ int vpl_debug_candidates(VplContext* ctx, double* out, int32_t* count, int cap);
  * reset (cfg.profile must be 1).  ms/launches: arrays of VPL_NUM_STAGES. */
 int vpl_get_stage_times(VplContext* ctx, double* ms, int64_t* launches);
 int vpl_reset_stage_times(VplContext* ctx);
+/* Where the stages of a slot's last batch lie in time (profile on): vpl_debug_mark records the origin on slot 0's
+ * stream, vpl_debug_timeline waits for `slot` and returns start / end of each of its VPL_NUM_STAGES stages in ms after
+ * the origin (-1 for a stage that did not run).  How the batches of two slots overlap on the device: bench.py --timeline. */
+int vpl_debug_mark(VplContext* ctx);
+int vpl_debug_timeline(VplContext* ctx, int slot, double* start_ms, double* end_ms);
 /* Test hook: list entries per lane of the LSD region engine's rings (0 = default, 2*ws*hs/32 rounded down to a power
  * of two).  Small values force the engine's fallbacks (undo of parked regions, whole-arena mode); results must not change. */
 int vpl_debug_set_engine_ring_cap(VplContext* ctx, int entries_per_lane);

@@ -353,7 +353,7 @@ def test_errors(ctx, vpl):
     assert vpl.BinaryDescriptorMatcher().match(np.zeros((0, 32), np.uint8), np.zeros((4, 32), np.uint8)) == []
 
 
-def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False):
+def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, group=False):
     """The exact call sequence bench.py times end to end: caller frames pinned with vpl_host_register, batches
     submitted to alternating slots with chaining (the frames of batch i + 2 uploaded ahead with vpl_frontend_upload
     while batch i runs, if asked), results collected in dense form into registered buffers."""
@@ -386,6 +386,19 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False):
         if upload_ahead:
             for i in range(min(S, n_batches)):
                 c.upload(i % S, frames[slice(*rng(i))])
+        if group:
+            # bench.py's default: the slots' uploaded batches submitted as one group, collected together
+            for g in range(0, n_batches, S):
+                while pending:
+                    collect()
+                grp = list(range(g, min(g + S, n_batches)))
+                c.submit_group([i % S for i in grp], [rng(i)[1] - rng(i)[0] for i in grp], w, h, scale=2,
+                               num_octaves=octaves, k=k, chain=[i > 0 for i in grp])
+                pending.extend((i % S,) + rng(i) for i in grp)
+                for i in grp:
+                    if i + S < n_batches:
+                        c.upload(i % S, frames[slice(*rng(i + S))])
+            n_batches = 0
         for i in range(n_batches):
             s = i % S
             if len(pending) == S:
@@ -403,16 +416,18 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False):
     return outs
 
 
-@pytest.mark.parametrize("name,n,batches,k,octaves,cap,ahead", [("C2_euroc_752x480", 33, 3, 1, 1, 1024, False),
-                                                                ("C2_euroc_752x480", 33, 5, 1, 1, 1024, True),
-                                                                ("C3_d455_1280x720", 9, 3, 2, 2, 2048, False)])
+@pytest.mark.parametrize("name,n,batches,k,octaves,cap,ahead", [("C2_euroc_752x480", 33, 3, 1, 1, 1024, "no"),
+                                                                ("C2_euroc_752x480", 33, 5, 1, 1, 1024, "ahead"),
+                                                                ("C2_euroc_752x480", 33, 5, 1, 1, 1024, "group"),
+                                                                ("C3_d455_1280x720", 9, 3, 2, 2, 2048, "group"),
+                                                                ("C3_d455_1280x720", 9, 3, 2, 2, 2048, "no")])
 def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves, cap, ahead):
     """The headline configs through bench.py's own path (host_register + submit(chain) over three batches +
-    collect_dense) against the oracle chain: every KeyLine, descriptor and match of every frame bit-equal; the
+    collect_dense; with upload-ahead; with upload-ahead and group submits = the bench's default) against the oracle chain: every KeyLine, descriptor and match of every frame bit-equal; the
     first frame of a later batch is matched against the last frame of the batch before it."""
     import bench
     frames = np.ascontiguousarray(synth.config_sequence(name, n))
-    outs = _bench_path(vpl, frames, batches, k, octaves, cap, ahead)
+    outs = _bench_path(vpl, frames, batches, k, octaves, cap, ahead != "no", ahead == "group")
     assert [o[0] for o in outs] == [i * ((n + batches - 1) // batches) for i in range(batches)]
     n_lines = 0
     for lo, hi, counts, kl, desc, mt in outs:
@@ -434,6 +449,11 @@ def test_upload_ahead_argument_errors(vpl, synth):
         c.upload(0, frames[:3])
         with pytest.raises(vpl.capi.VplError, match="uploaded batch of 3 frames"):
             c.submit_uploaded(0, 4, 752, 480)
+        # a group is submitted whole or not at all: slot 1 has nothing uploaded, slot 0 keeps its batch
+        with pytest.raises(vpl.capi.VplError, match="slot 1 holds no uploaded batch"):
+            c.submit_group([0, 1], [3, 3], 752, 480)
+        with pytest.raises(vpl.capi.VplError, match="twice in the group"):
+            c.submit_group([0, 0], [3, 3], 752, 480)
         c.submit_uploaded(0, 3, 752, 480, k=0)
         kl = np.zeros(3 * 1024, vpl.capi.KEYLINE_DTYPE); counts = np.zeros(3, np.int32)
         d = np.zeros((3 * 1024, 32), np.uint8); m = np.zeros((3 * 1024, 1), vpl.capi.DMATCH_DTYPE)

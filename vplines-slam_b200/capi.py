@@ -73,7 +73,7 @@ class LineMatchParam(C.Structure):
 EXPORTS = [
     "vpl_default_config", "vpl_create", "vpl_destroy", "vpl_last_error", "vpl_version", "vpl_device_count",
     "vpl_lsd_detect_batch", "vpl_lbd_compute_batch", "vpl_lbd_compute_float_batch", "vpl_match_batch", "vpl_frontend_batch",
-    "vpl_frontend_submit", "vpl_frontend_upload", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
+    "vpl_frontend_submit", "vpl_frontend_upload", "vpl_frontend_submit_group", "vpl_frontend_run_resident_group", "vpl_frontend_collect", "vpl_frontend_run_resident", "vpl_sync", "vpl_lsd_raw",
     "vpl_host_register", "vpl_host_unregister", "vpl_last_d2h_bytes", "vpl_frontend_collect_dense",
     "vpl_set_preprocess", "vpl_preprocess_batch",
     "vpl_edlines_default_param", "vpl_edlines_configure", "vpl_edlines_detect_batch", "vpl_edlines_submit",
@@ -82,7 +82,7 @@ EXPORTS = [
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
     "vpl_readimage_submit", "vpl_readimage_collect", "vpl_readimage_run_resident",
-    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_set_profile", "vpl_debug_set_engine_ring_cap", "vpl_debug_set_engine",
+    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_debug_mark", "vpl_debug_timeline", "vpl_set_profile", "vpl_debug_set_engine_ring_cap", "vpl_debug_set_engine",
     "vpl_kernel_launches",
 ]
 
@@ -120,6 +120,8 @@ def load():
     L.vpl_frontend_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_submit.argtypes = [vp, i32, vp, i32, i32, i32, sz, i32, i32, i32, i32]
     L.vpl_frontend_upload.argtypes = [vp, i32, vp, i32, i32, i32, sz]
+    L.vpl_frontend_submit_group.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.vpl_frontend_run_resident_group.argtypes = [vp, i32, vp, i32]
     L.vpl_frontend_collect.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     L.vpl_frontend_run_resident.argtypes = [vp, i32, i32]
     L.vpl_sync.argtypes = [vp]
@@ -135,6 +137,8 @@ def load():
     L.vpl_debug_candidates.argtypes = [vp, vp, vp, i32]
     L.vpl_get_stage_times.argtypes = [vp, vp, vp]
     L.vpl_reset_stage_times.argtypes = [vp]
+    L.vpl_debug_mark.argtypes = [vp]
+    L.vpl_debug_timeline.argtypes = [vp, i32, vp, vp]
     L.vpl_set_profile.argtypes = [vp, i32]
     L.vpl_debug_set_engine_ring_cap.argtypes = [vp, i32]
     L.vpl_debug_set_engine.argtypes = [vp, i32]
@@ -337,6 +341,18 @@ class Context:
         """vpl_frontend_submit with imgs == NULL: run the batch that `upload` staged on this slot."""
         self._ck(self._L.vpl_frontend_submit(self._h, slot, None, n, w, h, w, scale, num_octaves, k, int(chain)))
         return n
+
+    def submit_group(self, slots, ns, w, h, scale=2, num_octaves=1, k=1, chain=None):
+        """vpl_frontend_submit_group: the uploaded batches of `slots` (ns[i] frames each) enqueued together, their
+        region-engine launches behind a barrier across the group."""
+        sl = np.ascontiguousarray(slots, np.int32)
+        nn = np.ascontiguousarray(ns, np.int32)
+        ch = np.ascontiguousarray([1] * len(sl) if chain is None else [int(bool(x)) for x in chain], np.int32)
+        self._ck(self._L.vpl_frontend_submit_group(self._h, len(sl), _ptr(sl), _ptr(nn), w, h, scale, num_octaves, k, _ptr(ch)))
+
+    def run_resident_group(self, slots, k=1):
+        sl = np.ascontiguousarray(slots, np.int32)
+        self._ck(self._L.vpl_frontend_run_resident_group(self._h, len(sl), _ptr(sl), int(k)))
 
     def collect_into(self, slot, kl, counts, cap, desc, matches):
         self._ck(self._L.vpl_frontend_collect(self._h, slot, _ptr(kl), _ptr(counts), cap, _ptr(desc),
@@ -619,6 +635,16 @@ class Context:
         ln = np.zeros(len(STAGES), np.int64)
         self._ck(self._L.vpl_get_stage_times(self._h, _ptr(ms), _ptr(ln)))
         return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(STAGES)}
+
+    def mark(self):
+        self._ck(self._L.vpl_debug_mark(self._h))
+
+    def timeline(self, slot):
+        """{stage: (start_ms, end_ms)} of the slot's last batch, relative to the last mark() (profile on)."""
+        a = np.zeros(len(STAGES), np.float64)
+        b = np.zeros(len(STAGES), np.float64)
+        self._ck(self._L.vpl_debug_timeline(self._h, slot, _ptr(a), _ptr(b)))
+        return {s: (float(a[i]), float(b[i])) for i, s in enumerate(STAGES) if a[i] >= 0}
 
     def reset_stage_times(self):
         self._ck(self._L.vpl_reset_stage_times(self._h))

@@ -51,6 +51,7 @@ struct Slot {
   cudaEvent_t done = nullptr;        // everything of the batch finished
   cudaEvent_t last_ready = nullptr;  // last-frame descriptors copied to last_desc
   cudaEvent_t match_done = nullptr;  // this slot's match kernels finished
+  cudaEvent_t front_done = nullptr;  // group submits: this slot's kernels before the region engine finished
   cudaEvent_t ev[VPL_NUM_STAGES][2];
   bool ev_used[VPL_NUM_STAGES];
   uint8_t* d_img = nullptr;
@@ -149,6 +150,7 @@ struct VplContext {
   double* d_lgam = nullptr;  // log_gamma table for the NFA kernel
   int lgam_n = 0;
   std::vector<std::pair<const uint8_t*, size_t>> pinned;  // vpl_host_register ranges
+  cudaEvent_t mark = nullptr;        // vpl_debug_mark: origin of vpl_debug_timeline
   cudaStream_t up_stream = nullptr;  // vpl_frontend_upload: ONE copy stream for all slots, so uploads reach the device in call order
   // optional pre-processing (readImage: remap + CLAHE)
   float* d_mapx = nullptr;
@@ -318,8 +320,10 @@ void fill_engine_args(VplContext* c, Slot& s, EngineArgs& a) {
   }
 }
 
-// LSD on the pyramid already in s.oct[*].pyr -> candidates validated (cand, n_cand)
-void run_lsd(VplContext* c, Slot& s) {
+// LSD on the pyramid already in s.oct[*].pyr -> candidates validated (cand, n_cand).  Two halves: everything up to the
+// pseudo-ordering (streaming kernels), then the region engine and the NFA validation; a group submit puts a barrier
+// between them so that the engine launches of the group's slots start together.
+void run_lsd_front(VplContext* c, Slot& s) {
   cudaMemsetAsync(s.d_flags, 0, 2 * sizeof(int), s.stream);
   int wo[kMaxOctaves], ho[kMaxOctaves], ws[kMaxOctaves], hs[kMaxOctaves];
   for (int o = 0; o < s.num_octaves; ++o) {
@@ -345,6 +349,9 @@ void run_lsd(VplContext* c, Slot& s) {
                    (size_t)ws[o] * hs[o] * sizeof(uint32_t), ws[o], hs[o], s.n, c->lc.rho, s.stream);
     t.launches(s.num_octaves);
   }
+}
+
+void run_lsd_back(VplContext* c, Slot& s) {
   EngineArgs a;
   fill_engine_args(c, s, a);
   {
@@ -360,6 +367,11 @@ void run_lsd(VplContext* c, Slot& s) {
     launch_rect_nfa(a, s.stream);
     t.launches(1);
   }
+}
+
+void run_lsd(VplContext* c, Slot& s) {
+  run_lsd_front(c, s);
+  run_lsd_back(c, s);
 }
 
 void run_pack(VplContext* c, Slot& s) {
@@ -440,9 +452,9 @@ __global__ void compact_outputs_kernel(const uint32_t* __restrict__ kl, const ui
   }
 }
 
-int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
+// The fused path of one slot in two halves (see run_lsd_front): pyramid .. pseudo-ordering, then engine .. match.
+void enqueue_frontend_front(VplContext* c, int slot) {
   Slot& s = c->slots[slot];
-  const int cap = c->cfg.max_lines;
   if (c->cfg.profile) {
     // the slot's stage events are about to be re-recorded: bank the previous batch's times
     bool any = false;
@@ -453,7 +465,13 @@ int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
     }
   }
   run_pyramid(c, s, c->cfg.blur_first ? 1 : 0);
-  run_lsd(c, s);
+  run_lsd_front(c, s);
+}
+
+int enqueue_frontend_back(VplContext* c, int slot, int k, int chain) {
+  Slot& s = c->slots[slot];
+  const int cap = c->cfg.max_lines;
+  run_lsd_back(c, s);
   run_pack(c, s);
   if (!c->cfg.blur_first) run_pyramid(c, s, 1);  // BinaryDescriptor always blurs its own pyramid
   run_lbd(c, s, s.num_octaves);
@@ -491,6 +509,30 @@ int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
   c->prev_slot = slot;
   c->have_prev = true;
   s.k = k;
+  return VPL_OK;
+}
+
+int enqueue_frontend(VplContext* c, int slot, int k, int chain) {
+  enqueue_frontend_front(c, slot);
+  return enqueue_frontend_back(c, slot, k, chain);
+}
+
+// The same for several slots at once: the first halves of all, then -- behind a barrier over the group's streams -- the
+// second halves, so that the region-engine launches start together and share the SMs with each other (a latency-bound
+// kernel that wants every warp slot) instead of with another slot's streaming kernels.
+int enqueue_frontend_group(VplContext* c, const int* slots, int n_slots, int k, const int* chain) {
+  for (int i = 0; i < n_slots; ++i) {
+    Slot& s = c->slots[slots[i]];
+    enqueue_frontend_front(c, slots[i]);
+    cudaEventRecord(s.front_done, s.stream);
+  }
+  for (int i = 0; i < n_slots; ++i) {
+    Slot& s = c->slots[slots[i]];
+    for (int j = 0; j < n_slots; ++j)
+      if (j != i) cudaStreamWaitEvent(s.stream, c->slots[slots[j]].front_done, 0);
+    int r = enqueue_frontend_back(c, slots[i], k, chain[i]);
+    if (r) return r;
+  }
   return VPL_OK;
 }
 
@@ -875,12 +917,14 @@ void vpl_destroy(VplContext* c) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.last_ready) cudaEventDestroy(s.last_ready);
     if (s.match_done) cudaEventDestroy(s.match_done);
+    if (s.front_done) cudaEventDestroy(s.front_done);
     for (int i = 0; i < VPL_NUM_STAGES; ++i)
       for (int j = 0; j < 2; ++j)
         if (s.ev[i][j]) cudaEventDestroy(s.ev[i][j]);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  if (c->mark) cudaEventDestroy(c->mark);
   delete c;
 }
 
@@ -954,6 +998,7 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&s.last_ready, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&s.match_done, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&s.front_done, cudaEventDisableTiming));
     for (int i = 0; i < VPL_NUM_STAGES; ++i)
       for (int j = 0; j < 2; ++j) CKC(cudaEventCreate(&s.ev[i][j]));
     CKC(dmalloc(&s.d_img, B * P0));
@@ -1006,8 +1051,10 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
 }
 
 // ---- fused path ---------------------------------------------------------------
-int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
-                        int scale, int num_octaves, int k, int chain) {
+// vpl_frontend_submit up to the kernels: argument checks, then the frames (uploaded now, or taken from the buffer that
+// vpl_frontend_upload filled) and the optional pre-processing
+static int submit_prepare(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                          int scale, int num_octaves, int k) {
   int r = check_dims(c, n, w, h, num_octaves, scale, true);
   if (r) return r;
   if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
@@ -1024,23 +1071,58 @@ int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int
                   slot, s.staged_n, s.staged_w, s.staged_h, n, w, h);
   }
   s.n = n; s.w = w; s.h = h; s.num_octaves = num_octaves; s.scale = scale; s.k = k;
-  if (imgs) {
-    r = upload(c, s, imgs, n, w, h, stride);
-  } else {
-    std::swap(s.d_img, s.d_img_next);
-    s.staged_n = 0;
-    CK(c, cudaStreamWaitEvent(s.stream, s.uploaded, 0));
-    r = after_upload(c, s, n, w, h);
-  }
-  if (r) return r;
-  r = enqueue_frontend(c, slot, k, chain);
-  if (r) return r;
+  if (imgs) return upload(c, s, imgs, n, w, h, stride);
+  std::swap(s.d_img, s.d_img_next);
+  s.staged_n = 0;
+  CK(c, cudaStreamWaitEvent(s.stream, s.uploaded, 0));
+  return after_upload(c, s, n, w, h);
+}
+
+static int submit_finish(VplContext* c, Slot& s) {
   enqueue_dense_download(c, s);
   CK(c, cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
   s.kind = BK_FRONTEND;
   s.resident = BK_FRONTEND;
   CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_frontend_submit(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                        int scale, int num_octaves, int k, int chain) {
+  int r = submit_prepare(c, slot, imgs, n, w, h, stride, scale, num_octaves, k);
+  if (r) return r;
+  r = enqueue_frontend(c, slot, k, chain);
+  if (r) return r;
+  return submit_finish(c, c->slots[slot]);
+}
+
+int vpl_frontend_submit_group(VplContext* c, int n_slots, const int* slots, const int* n, int w, int h, int scale,
+                              int num_octaves, int k, const int* chain) {
+  if (!c) return VPL_E_INVALID;
+  if (n_slots < 1 || n_slots > (int)c->slots.size() || !slots || !n || !chain)
+    return fail(c, VPL_E_INVALID, "bad group of %d slots", n_slots);
+  for (int i = 0; i < n_slots; ++i)
+    for (int j = 0; j < i; ++j)
+      if (slots[i] == slots[j]) return fail(c, VPL_E_INVALID, "slot %d twice in the group", slots[i]);
+  // check everything before touching anything: a group is submitted whole or not at all
+  for (int i = 0; i < n_slots; ++i) {
+    if (slots[i] < 0 || slots[i] >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slots[i]);
+    const Slot& s = c->slots[slots[i]];
+    if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slots[i]);
+    if (s.staged_n == 0 || s.staged_n != n[i] || s.staged_w != w || s.staged_h != h)
+      return fail(c, VPL_E_INVALID, "slot %d holds no uploaded batch of %d frames %dx%d (vpl_frontend_upload)", slots[i], n[i], w, h);
+  }
+  for (int i = 0; i < n_slots; ++i) {
+    int r = submit_prepare(c, slots[i], nullptr, n[i], w, h, (size_t)w, scale, num_octaves, k);
+    if (r) return r;
+  }
+  int r = enqueue_frontend_group(c, slots, n_slots, k, chain);
+  if (r) return r;
+  for (int i = 0; i < n_slots; ++i) {
+    r = submit_finish(c, c->slots[slots[i]]);
+    if (r) return r;
+  }
   return VPL_OK;
 }
 
@@ -1168,6 +1250,31 @@ int vpl_frontend_run_resident(VplContext* c, int slot, int k) {
   if (r) return r;
   CK(c, cudaSetDevice(c->cfg.device));
   r = enqueue_frontend(c, slot, k, 0);
+  if (r) return r;
+  CK(c, cudaGetLastError());
+  return VPL_OK;
+}
+
+int vpl_frontend_run_resident_group(VplContext* c, int n_slots, const int* slots, int k) {
+  if (!c) return VPL_E_INVALID;
+  if (!c->cfg.lsd_path) return fail(c, VPL_E_INVALID, "this context was created with lsd_path = 0");
+  if (n_slots < 1 || n_slots > (int)c->slots.size() || !slots) return fail(c, VPL_E_INVALID, "bad group of %d slots", n_slots);
+  if (k < 0 || k > c->max_k) return fail(c, VPL_E_INVALID, "k=%d outside 0..%d", k, c->max_k);
+  int chain[64] = {0};
+  if (n_slots > 64) return fail(c, VPL_E_INVALID, "group of %d slots", n_slots);
+  for (int i = 0; i < n_slots; ++i) {
+    if (slots[i] < 0 || slots[i] >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slots[i]);
+    for (int j = 0; j < i; ++j)
+      if (slots[i] == slots[j]) return fail(c, VPL_E_INVALID, "slot %d twice in the group", slots[i]);
+    Slot& s = c->slots[slots[i]];
+    if (s.n <= 0 || s.resident != BK_FRONTEND)
+      return fail(c, VPL_E_INVALID, "slot %d holds no front-end frames: submit+collect a front-end batch first", slots[i]);
+    if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight", slots[i]);
+    int r = check_dims(c, s.n, s.w, s.h, s.num_octaves, s.scale, true);
+    if (r) return r;
+  }
+  CK(c, cudaSetDevice(c->cfg.device));
+  int r = enqueue_frontend_group(c, slots, n_slots, k, chain);
   if (r) return r;
   CK(c, cudaGetLastError());
   return VPL_OK;
@@ -2332,6 +2439,34 @@ int vpl_reset_stage_times(VplContext* c) {
   if (!c) return VPL_E_INVALID;
   memset(c->stage_ms, 0, sizeof(c->stage_ms));
   memset(c->stage_launches, 0, sizeof(c->stage_launches));
+  return VPL_OK;
+}
+
+int vpl_debug_mark(VplContext* c) {
+  if (!c) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  if (!c->mark) CK(c, cudaEventCreate(&c->mark));
+  CK(c, cudaEventRecord(c->mark, c->slots[0].stream));
+  return VPL_OK;
+}
+
+int vpl_debug_timeline(VplContext* c, int slot, double* start_ms, double* end_ms) {
+  if (!c || !start_ms || !end_ms) return VPL_E_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slot);
+  if (!c->mark) return fail(c, VPL_E_INVALID, "vpl_debug_mark has not been called");
+  Slot& s = c->slots[slot];
+  CK(c, cudaSetDevice(c->cfg.device));
+  CK(c, cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < VPL_NUM_STAGES; ++i) {
+    start_ms[i] = end_ms[i] = -1.0;
+    if (!s.ev_used[i]) continue;
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, c->mark, s.ev[i][0]) == cudaSuccess &&
+        cudaEventElapsedTime(&b, c->mark, s.ev[i][1]) == cudaSuccess) {
+      start_ms[i] = a; end_ms[i] = b;
+    }
+  }
+  cudaGetLastError();
   return VPL_OK;
 }
 
