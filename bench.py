@@ -1580,6 +1580,9 @@ def main():
                     "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "latency": latency}
+    nfa_chk = ctx.nfa_stats()
+    if nfa_chk[0]:  # a -DVPL_NFA_CHECK build: the float32 early-exit test of nfa() against the double sequence
+        line["nfa_check"] = {"decisions": nfa_chk[0], "answered_in_float32": nfa_chk[1], "disagreements": nfa_chk[2]}
     if rank == 0:
         line["parity_checked"] = bool(parity and parity["checked"])
         line["parity"] = parity

@@ -424,6 +424,9 @@ int vpl_reset_stage_times(VplContext* ctx);
 /* Where the stages of a slot's last batch lie in time (profile on): vpl_debug_mark records the origin on slot 0's
  * stream, vpl_debug_timeline waits for `slot` and returns start / end of each of its VPL_NUM_STAGES stages in ms after
  * the origin (-1 for a stage that did not run).  How the batches of two slots overlap on the device: bench.py --timeline. */
+/* Counters of a library built with -DVPL_NFA_CHECK (zeros otherwise): early-exit decisions in the binomial tail of nfa(),
+ * how many the float32 test answered, how many of those disagree with the double sequence (lsd_nfa.cu nfa_exit_fast). */
+int vpl_debug_nfa_stats(VplContext* ctx, uint64_t* out4);
 int vpl_debug_mark(VplContext* ctx);
 int vpl_debug_timeline(VplContext* ctx, int slot, double* start_ms, double* end_ms);
 /* Test hook: list entries per lane of the LSD region engine's rings (0 = default, 2*ws*hs/32 rounded down to a power

@@ -25,8 +25,16 @@ def nvcc():
     return "nvcc"
 
 
+FLAGS_STAMP = os.path.join(HERE, "build", "nvcc_flags.txt")
+
+
 def needs_build():
     if not os.path.exists(OUT):
+        return True
+    try:  # built with other flags (VPL_EXTRA_NVCC)?
+        if open(FLAGS_STAMP).read() != " ".join(NVCC_FLAGS):
+            return True
+    except OSError:
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
@@ -55,6 +63,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = [nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.check_call(cmd)
+    with open(FLAGS_STAMP, "w") as f:
+        f.write(" ".join(NVCC_FLAGS))
     return OUT
 
 

@@ -82,7 +82,7 @@ EXPORTS = [
     "vpl_linefront_batch", "vpl_linefront_submit", "vpl_linefront_collect", "vpl_linefront_run_resident",
     "vpl_vp_configure", "vpl_vp_detect_batch", "vpl_vp_submit", "vpl_vp_collect", "vpl_vp_run_resident", "vpl_debug_vp", "vpl_vp_pack_cloud", "vpl_match_run_resident", "vpl_debug_popc_peak", "vpl_debug_vp_scores",
     "vpl_readimage_submit", "vpl_readimage_collect", "vpl_readimage_run_resident",
-    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_debug_mark", "vpl_debug_timeline", "vpl_set_profile", "vpl_debug_set_engine_ring_cap", "vpl_debug_set_engine",
+    "vpl_debug_stage", "vpl_debug_candidates", "vpl_get_stage_times", "vpl_reset_stage_times", "vpl_debug_mark", "vpl_debug_timeline", "vpl_debug_nfa_stats", "vpl_set_profile", "vpl_debug_set_engine_ring_cap", "vpl_debug_set_engine",
     "vpl_kernel_launches",
 ]
 
@@ -138,6 +138,7 @@ def load():
     L.vpl_get_stage_times.argtypes = [vp, vp, vp]
     L.vpl_reset_stage_times.argtypes = [vp]
     L.vpl_debug_mark.argtypes = [vp]
+    L.vpl_debug_nfa_stats.argtypes = [vp, vp]
     L.vpl_debug_timeline.argtypes = [vp, i32, vp, vp]
     L.vpl_set_profile.argtypes = [vp, i32]
     L.vpl_debug_set_engine_ring_cap.argtypes = [vp, i32]
@@ -635,6 +636,12 @@ class Context:
         ln = np.zeros(len(STAGES), np.int64)
         self._ck(self._L.vpl_get_stage_times(self._h, _ptr(ms), _ptr(ln)))
         return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(STAGES)}
+
+    def nfa_stats(self):
+        """(decisions, answered by the float32 test, disagreements, 0) of a -DVPL_NFA_CHECK build; zeros otherwise."""
+        v = np.zeros(4, np.uint64)
+        self._ck(self._L.vpl_debug_nfa_stats(self._h, _ptr(v)))
+        return [int(x) for x in v]
 
     def mark(self):
         self._ck(self._L.vpl_debug_mark(self._h))

@@ -2470,6 +2470,15 @@ int vpl_debug_timeline(VplContext* c, int slot, double* start_ms, double* end_ms
   return VPL_OK;
 }
 
+int vpl_debug_nfa_stats(VplContext* c, uint64_t* out4) {
+  if (!c || !out4) return VPL_E_INVALID;
+  CK(c, cudaSetDevice(c->cfg.device));
+  unsigned long long v[4];
+  nfa_check_stats(v);
+  for (int i = 0; i < 4; ++i) out4[i] = v[i];
+  return VPL_OK;
+}
+
 int64_t vpl_kernel_launches(const VplContext* c) { return c ? c->launches : 0; }
 
 }  // extern "C"

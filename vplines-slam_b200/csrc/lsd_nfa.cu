@@ -58,6 +58,39 @@ __device__ __forceinline__ double log_gamma_int(const LgamTab& T, int m) {
   return (m < T.n) ? __ldg(T.tab + m) : log_gamma_d((double)m);
 }
 
+// The early-exit test of the binomial tail, err < tolerance * |-log10(bin_tail) - LOG_NT| * bin_tail with
+// err = term * ((1 - mult^m) / (1 - mult) - 1), costs a double pow and a double log10 per iteration and decides a comparison
+// that is almost never close.  This evaluates both sides in float32 -- (mult - mult^m) / (1 - mult) * (term / bin_tail)
+// against tolerance * |log10(bin_tail) + LOG_NT| -- and answers only when they differ by more than 0.1 % (the float32
+// evaluation is good to 1e-5, the double one to 1e-6 of the true values in the range admitted here); inside the band, or
+// outside that range, the caller runs the double sequence as before.  Returns 1 (break), 0 (go on), -1 (undecided).
+// Built with -DVPL_NFA_CHECK the kernel runs both and counts disagreements (vpl_debug_nfa_stats).
+__device__ __forceinline__ int nfa_exit_fast(double term, double bin_tail, double mult, int m, double LOG_NT) {
+  const int hi = __double2hiint(bin_tail);
+  const int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0 || ex == 0x7ff) return -1;                       // subnormal / non-finite sum
+  if (!(mult > 1e-6 && mult < 0.5) || m < 2) return -1;         // keeps the double cancellation error below 1e-6 of E
+  const float mu = (float)mult;
+  const float pw = exp2f((float)m * __log2f(mu));               // mult^m, relative error < 2e-3 of a term that is <= mult / 2 of E's numerator
+  const float E = (mu - pw) / (1.f - mu);
+  double inv;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(bin_tail));
+  const float r = (float)(term * inv);                          // term / bin_tail in (0, 1]
+  if (!(r > 1e-30f)) return -1;
+  const unsigned mant = ((unsigned)(hi & 0xfffff) << 3) | ((unsigned)__double2loint(bin_tail) >> 29);
+  const float lg10 = ((float)(ex - 1023) + __log2f(__uint_as_float(0x3f800000u | mant))) * 0.30102999566f;
+  const float L = fabsf(-lg10 - (float)LOG_NT);
+  if (L < 1e-2f) return -1;                                     // |log10(bin_tail) + LOG_NT| near its zero: relative error unbounded
+  const float lhs = E * r, rhs = 0.1f * L;
+  if (lhs < rhs * 0.999f) return 1;
+  if (lhs > rhs * 1.001f) return 0;
+  return -1;
+}
+
+#ifdef VPL_NFA_CHECK
+__device__ unsigned long long g_nfa_stats[4];  // decisions, answered by the float32 test, disagreements, spare
+#endif
+
 // per-lane scalar; lanes may carry different (n,k,p)
 __device__ __noinline__ double nfa_d(int n, int k, double p, double LOG_NT, LgamTab T) {
   if (n == 0 || k == 0) return -LOG_NT;
@@ -78,8 +111,19 @@ __device__ __noinline__ double nfa_d(int n, int k, double p, double LOG_NT, Lgam
     term *= mult_term;
     bin_tail += term;
     if (bin_term < 1) {
+      const int fast = nfa_exit_fast(term, bin_tail, mult_term, n - i + 1, LOG_NT);
+#ifndef VPL_NFA_CHECK
+      if (fast == 1) break;
+      if (fast == 0) continue;
+#endif
       double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
-      if (err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+      const bool stop = err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail;
+#ifdef VPL_NFA_CHECK
+      atomicAdd(&g_nfa_stats[0], 1ull);
+      if (fast >= 0) atomicAdd(&g_nfa_stats[1], 1ull);
+      if (fast >= 0 && (fast == 1) != stop) atomicAdd(&g_nfa_stats[2], 1ull);
+#endif
+      if (stop) break;
     }
   }
   return -log10(bin_tail) - LOG_NT;
@@ -369,6 +413,15 @@ rect_nfa_kernel(EngineArgs A) {
 #ifdef VPL_DEBUG_NFA
 void debug_set_cand(int c) { cudaMemcpyToSymbol(g_dbg_cand, &c, sizeof(int)); }
 #endif
+
+// counters of the -DVPL_NFA_CHECK build (zeros otherwise): early-exit decisions, those the float32 test answered, disagreements
+void nfa_check_stats(unsigned long long out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+#ifdef VPL_NFA_CHECK
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_nfa_stats, 4 * sizeof(unsigned long long));
+#endif
+}
 
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st) {
   // ~16 CTAs per SM in flight over (frames x octaves); warps stride over a frame's candidates

@@ -177,6 +177,7 @@ void launch_region_engine(const EngineArgs& a, cudaStream_t st);
 void launch_region_engine_spec(const EngineArgs& a, cudaStream_t st);
 constexpr int kSpecMaxBatch = 256;
 void launch_rect_nfa(const EngineArgs& a, cudaStream_t st);
+void nfa_check_stats(unsigned long long out[4]);  // counters of the -DVPL_NFA_CHECK build, zeros otherwise
 struct PackArgs {
   const RectCand* cand[kMaxOctaves];
   const int* n_cand[kMaxOctaves];
