@@ -169,6 +169,7 @@ __device__ __noinline__ void sincos_cr_outlined(double a, double* s, double* c) 
 __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, double prec, double p, RectCand& rec) {
   const int lane = e.lane;
   double x = 0, y = 0, sum = 0;
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int j = base + lane;
     double wx = 0, wy = 0, wt = 0;
@@ -193,6 +194,7 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
         sum += e.bc[t + u];
       }
     }
+#pragma unroll 1
     for (; t < cnt; ++t) {
       double2 v = e.bc2[t];
       x += v.x;
@@ -205,6 +207,7 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
   y /= sum;
   // get_theta
   double Ixx = 0.0, Iyy = 0.0, Ixy = 0.0;
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int j = base + lane;
     double t1 = 0, t2 = 0, t3 = 0;
@@ -230,6 +233,7 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
         Ixy -= e.bc[t + u];
       }
     }
+#pragma unroll 1
     for (; t < cnt; ++t) {
       double2 v = e.bc2[t];
       Ixx += v.x;
@@ -254,6 +258,9 @@ __device__ __noinline__ void region2rect(const Eng& e, int n, double reg_angle, 
 #endif
   // length / width: min and max are order-free
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  // (not unrolled on purpose, like the tails above: ptxas made 850 instructions of this loop, and the function is
+  // straight-line code that every call streams through the instruction cache, next to 63 other warps elsewhere in the kernel)
+#pragma unroll 1
   for (int j = lane; j < n; j += 32) {
     const uint32_t r = e.reg[j];
     int px = (int)(r & 0xffffu), py = (int)(r >> 16);
@@ -290,6 +297,7 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
   const int lane = e.lane;
   const unsigned lt = (1u << lane) - 1u;
   int n_in = 0;
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int j = base + lane;
     bool in = false;
@@ -322,6 +330,7 @@ __device__ __noinline__ int compact_radius(const Eng& e, int n, double xc, doubl
   }
   // holes among the first n_in positions, ascending
   int kh = 0;
+#pragma unroll 1
   for (int base = 0; base < n_in; base += 32) {
     int j = base + lane;
     bool hole = false;
@@ -369,6 +378,7 @@ __device__ __noinline__ bool refine(const Eng& e, int& n, double reg_angle, doub
   double ang_c = (double)seed_deg * VPL_DEG2RAD;
   double sum = 0, s_sum = 0;
   int cnt = 0;
+#pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     int j = base + lane;
     bool flag = false;
