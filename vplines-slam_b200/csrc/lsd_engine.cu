@@ -31,7 +31,10 @@
 
 namespace vpl {
 
-constexpr int RING = 256;  // per-warp FIFO window kept in shared memory
+#ifndef VPL_ENGINE_RING
+#define VPL_ENGINE_RING 256
+#endif
+constexpr int RING = VPL_ENGINE_RING;  // per-warp FIFO window kept in shared memory
 
 struct Eng {
   Pix* pix;            // {angle bits | used bit31, cosf, sinf, packed gradient differences} per pixel
