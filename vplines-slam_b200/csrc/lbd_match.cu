@@ -88,21 +88,31 @@ lbd_kernel(LbdArgs A, const VplKeyLine* __restrict__ kl_, const int* __restrict_
   for (int hID = lane; hID < LSP_H; hID += 32) {
     float sCorX = sCorX0, sCorY = sCorY0;
     float pgdLRowSum = 0, ngdLRowSum = 0, pgdORowSum = 0, ngdORowSum = 0;
-    for (int wID = 0; wID < lengthOfLSP; ++wID) {
+    // The sample positions do not depend on the samples: four gathers are issued before the first of them is used
+    // (the row sums still take the samples one by one in wID order, the coordinates the same chain of float additions).
+    auto sample = [&](void) -> short2 {
       int tx = (int)(short)roundf(sCorX);
       int xCor = (tx < 0) ? 0 : (tx > imageWidth) ? imageWidth : tx;
       int ty = (int)(short)roundf(sCorY);
       int yCor = (ty < 0) ? 0 : (ty > imageHeight) ? imageHeight : ty;
-      short2 d = __ldg(g + yCor * realWidth + xCor);
+      sCorX += dL0;
+      sCorY += dL1;
+      return __ldg(g + yCor * realWidth + xCor);
+    };
+    auto accumulate = [&](short2 d) {
       float gDL = d.x * dL0 + d.y * dL1;
       float gDO = d.x * dO0 + d.y * dO1;
       if (gDL > 0) pgdLRowSum += gDL;
       else ngdLRowSum -= gDL;
       if (gDO > 0) pgdORowSum += gDO;
       else ngdORowSum -= gDO;
-      sCorX += dL0;
-      sCorY += dL1;
+    };
+    int wID = 0;
+    for (; wID + 4 <= lengthOfLSP; wID += 4) {
+      short2 d0 = sample(), d1 = sample(), d2 = sample(), d3 = sample();
+      accumulate(d0); accumulate(d1); accumulate(d2); accumulate(d3);
     }
+    for (; wID < lengthOfLSP; ++wID) accumulate(sample());
     float coef = c_gaussG[hID];
     pgdLRowSum = coef * pgdLRowSum;
     ngdLRowSum = coef * ngdLRowSum;
