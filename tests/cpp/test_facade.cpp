@@ -73,6 +73,32 @@ int main(int argc, char** argv) {
       }
       std::printf("FACADE batch lines=%ld matched=%ld digest=%lu sharded_equal=%d\n", lines[0], matched[0], dg[0],
                   (int)(dg[0] == dg[1] && lines[0] == lines[1] && matched[0] == matched[1]));
+      // the grouped fast path (contiguous frames, upload ahead, group submits): batches of 2 over 2 slots = 3 groups,
+      // whole and as two shards
+      {
+        std::vector<uint8_t> flat((size_t)5 * 320 * 240);
+        for (int i = 0; i < 5; ++i)
+          for (int y = 0; y < 240; ++y) std::copy(seq[(size_t)i].ptr(y), seq[(size_t)i].ptr(y) + 320, flat.begin() + ((size_t)i * 240 + y) * 320);
+        unsigned long dgg[2] = {1469598103934665603ul, 1469598103934665603ul};
+        long lg[2] = {0, 0}, mgm[2] = {0, 0};
+        auto mixg = [&](int which) {
+          return [&, which](int64_t, const vplines::FrameResult& r) {
+            lg[which] += (long)r.keylines.size();
+            for (uint8_t b : r.descriptors) dgg[which] = (dgg[which] ^ b) * 1099511628211ul;
+            for (const VplDMatch& m : r.matches) { mgm[which] += m.trainIdx >= 0; dgg[which] = (dgg[which] ^ (unsigned long)(m.trainIdx + 7)) * 1099511628211ul; }
+          };
+        };
+        vplines::BatchFrontEnd bg(0, 320, 240, 1, 2048, 2, 2);
+        bg.run_grouped(flat.data(), 0, 5, 0, 2, 1, mixg(0));
+        for (int rank = 0; rank < 2; ++rank) {
+          int64_t s, e; int halo;
+          vplines::shard_range(5, rank, 2, s, e, halo);
+          vplines::BatchFrontEnd shard(0, 320, 240, 1, 2048, 2, 2);
+          shard.run_grouped(flat.data(), s, e, halo, 2, 1, mixg(1));
+        }
+        std::printf("FACADE grouped equal=%d sharded_equal=%d\n", (int)(dgg[0] == dg[0] && lg[0] == lines[0] && mgm[0] == matched[0]),
+                    (int)(dgg[1] == dg[0] && lg[1] == lines[0] && mgm[1] == matched[0]));
+      }
       // the in-process multi-GPU driver: one host thread + one context per device (as many devices as the box has,
       // at least two contexts), ordered host gather
       {

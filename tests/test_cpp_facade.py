@@ -69,6 +69,9 @@ def test_facade_matches_ctypes_path(vpl, orc, tmp_path):
     assert int(mb.group(1)) == sum(len(k) for k in kls)
     exp_matched = sum(len(ds[i]) for i in range(1, 5) if len(ds[i - 1]))
     assert int(mb.group(2)) == exp_matched
+    # the grouped fast path (vpl_frontend_upload + vpl_frontend_submit_group over contiguous frames) == the single run
+    gg = re.search(r"grouped equal=(\d) sharded_equal=(\d)", out)
+    assert gg and gg.group(1) == "1" and gg.group(2) == "1", out
     # in-process multi-GPU driver (std::thread + context per device, ordered host gather) == the single run
     mg = re.search(r"multigpu world=(\d+) equal=(\d) ordered=(\d)", out)
     assert mg and int(mg.group(1)) >= 2 and mg.group(2) == "1" and mg.group(3) == "1", out
