@@ -164,6 +164,26 @@ def test_frontend_fused_equals_oracle_chain(ctx, orc, mh04):
         prev = edesc
 
 
+def test_frontend_grouped_driver_equals_plain_driver(vpl, mh04):
+    """FrontEnd.run_grouped (frames pinned once, uploaded ahead, group submits, dense collects) on the device: what
+    run() delivers (itself checked against the oracle chain above), whole and as two shards with the one-frame halo."""
+    frames = np.ascontiguousarray(mh04[:11])
+    with vpl.Context(max_width=752, max_height=480, max_octaves=1, max_lines=4096, max_batch=3, num_slots=2) as c:
+        fe = vpl.FrontEnd(c, scale=2, num_octaves=1, k=2)
+        ref = fe.run(frames)
+        got = fe.run_grouped(frames)
+        part = ([], [], [])
+        for r in range(2):
+            s, e, halo = vpl.shard_range(len(frames), r, 2)
+            out = fe.run_grouped(frames, s, e, halo)
+            for a, b in zip(part, out):
+                a.extend(b)
+    for a in (got, part):
+        for x, y in zip(ref, a):
+            assert len(x) == len(y) == len(frames)
+            assert all(p.tobytes() == q.tobytes() for p, q in zip(x, y))
+
+
 def test_screenshot_pair_5_10(ctx, orc, mh04):
     """C1's (5,10) pair: same pipeline through the OpenCV-shaped surface."""
     import vplines_slam_b200 as v

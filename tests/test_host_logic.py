@@ -22,6 +22,8 @@ class OracleContext:
         self.pending = {}
         self.prev_desc = None
         self.submitted = []
+        self.staged = {}
+        self.log = []
 
     def submit(self, slot, frames, scale=2, num_octaves=1, k=1, chain=False):
         assert slot not in self.pending and len(frames) <= self.max_batch
@@ -50,6 +52,39 @@ class OracleContext:
             kl[i, :len(k_)] = k_
             desc[i, :len(k_)] = d
             matches[i, :len(k_)] = m
+
+    # the upload-ahead / group-submit / dense-collect calls of run_grouped, with the C library's rules
+    def host_register(self, a):
+        self.registered = a
+
+    def host_unregister(self, a):
+        assert a is self.registered
+        self.registered = None
+
+    def upload(self, slot, frames):
+        assert getattr(self, "registered", None) is not None and np.shares_memory(frames, self.registered)
+        assert slot not in self.staged and len(frames) <= self.max_batch  # one uploaded batch per slot
+        self.staged[slot] = frames
+        self.log.append(("upload", slot, len(frames)))
+
+    def submit_group(self, slots, ns, w, h, scale=2, num_octaves=1, k=1, chain=None):
+        assert len(set(slots)) == len(slots)
+        for s_, n in zip(slots, ns):
+            assert s_ in self.staged and len(self.staged[s_]) == n and s_ not in self.pending
+        self.log.append(("group", tuple(slots), tuple(ns)))
+        for s_, c in zip(slots, chain):
+            self.submit(s_, self.staged.pop(s_), scale=scale, num_octaves=num_octaves, k=k, chain=c)
+
+    def collect_dense_into(self, slot, counts, kl, desc, matches):
+        off = 0
+        for i, (k_, d, m) in enumerate(self.pending.pop(slot)):
+            counts[i] = len(k_)
+            kl[off:off + len(k_)] = k_
+            desc[off:off + len(k_)] = d
+            matches[off:off + len(k_)] = m
+            off += len(k_)
+        self.log.append(("collect", slot))
+        return off
 
 
 class OracleLineContext:
@@ -261,6 +296,30 @@ def test_driver_pipelining_and_chaining(vpl, orc, synth):
             idx, _ = orc.hamming_knn(ed, prev, 2)
             assert np.array_equal(ms[f]["trainIdx"], idx)
         prev = ed
+
+
+def test_grouped_driver_equals_plain_driver(vpl, orc, synth):
+    """FrontEnd.run_grouped (upload ahead, group submits, dense collects) delivers what run() delivers, whole and
+    sharded, and keeps the C library's rules: one uploaded batch per slot, a slot collected before it is resubmitted,
+    uploads issued right after the group that frees the slot's second input buffer."""
+    frames = np.ascontiguousarray(synth.sequence(9, w=160, h=120, seed=8, n_quads=5, n_strokes=8))
+    full = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=4), k=1).run(frames)
+    ctx = OracleContext(orc, vpl.capi, max_batch=2, num_slots=2)
+    got = vpl.FrontEnd(ctx, k=1).run_grouped(frames)
+    assert ctx.log[:3] == [("upload", 0, 2), ("upload", 1, 2), ("group", (0, 1), (2, 2))]
+    assert ctx.log[3:5] == [("upload", 0, 2), ("upload", 1, 2)] and ctx.log[5:7] == [("collect", 0), ("collect", 1)]
+    assert ctx.log[-2:] == [("group", (0,), (1,)), ("collect", 0)] and ctx.registered is None
+    for world in (1, 2, 3):
+        part = ([], [], [])
+        for r in range(world):
+            s, e, halo = vpl.shard_range(len(frames), r, world)
+            out = vpl.FrontEnd(OracleContext(orc, vpl.capi, max_batch=2), k=1).run_grouped(frames, s, e, halo)
+            for a, b in zip(part, out):
+                a.extend(b)
+        for ref, a in ((full, got), (full, part)):
+            for x, y in zip(ref, a):
+                assert len(x) == len(y)
+                assert all(p.tobytes() == q.tobytes() for p, q in zip(x, y)), world
 
 
 def test_sharded_run_equals_single_run(vpl, orc, synth):

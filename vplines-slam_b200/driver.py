@@ -65,6 +65,59 @@ class FrontEnd:
             collect(*pending.pop(0))
         return out_kl, out_desc, out_m
 
+    def run_grouped(self, frames, start=0, end=None, halo=0):
+        """The same through the fast path of the batch API: `frames` is one contiguous
+        (n, h, w) uint8 array, pinned once; every batch is copied to the device ahead of its turn
+        (vpl_frontend_upload), the slots' batches are submitted as one group (vpl_frontend_submit_group: their
+        region-engine launches start together), results come back dense.  Same results and order as run()."""
+        ctx = self.ctx
+        frames = np.ascontiguousarray(frames)
+        end = len(frames) if end is None else end
+        lo = start - halo
+        B, S, cap, k = ctx.max_batch, ctx.num_slots, ctx.max_lines, self.k
+        h, w = frames.shape[1:]
+        batches = [(f, min(B, end - f)) for f in range(lo, end, B)]
+        bufs = [dict(kl=np.zeros(B * cap, capi.KEYLINE_DTYPE), counts=np.zeros(B, np.int32),
+                     desc=np.zeros((B * cap, 32), np.uint8), m=np.zeros((B * cap, max(k, 1)), capi.DMATCH_DTYPE))
+                for _ in range(S)]
+        out_kl, out_desc, out_m = [], [], []
+
+        def upload(bi):
+            f0, n = batches[bi]
+            ctx.upload(bi % S, frames[f0:f0 + n])
+
+        def collect(bi):
+            f0, n = batches[bi]
+            b = bufs[bi % S]
+            ctx.collect_dense_into(bi % S, b["counts"], b["kl"], b["desc"], b["m"])
+            off = 0
+            for i in range(n):
+                c = int(b["counts"][i])
+                if f0 + i >= start:  # (a halo frame is only there to be matched against)
+                    out_kl.append(b["kl"][off:off + c].copy())
+                    out_desc.append(b["desc"][off:off + c].copy())
+                    out_m.append(b["m"][off:off + c].copy())
+                off += c
+
+        ctx.host_register(frames)
+        try:
+            for bi in range(min(S, len(batches))):
+                upload(bi)
+            for g in range(0, len(batches), S):
+                for bi in range(max(g - S, 0), g):
+                    collect(bi)  # the previous group, in order
+                grp = range(g, min(g + S, len(batches)))
+                ctx.submit_group([bi % S for bi in grp], [batches[bi][1] for bi in grp], w, h, scale=self.scale,
+                                 num_octaves=self.num_octaves, k=k, chain=[bi > 0 for bi in grp])
+                for bi in grp:
+                    if bi + S < len(batches):
+                        upload(bi + S)
+            for bi in range((len(batches) - 1) // S * S if batches else 0, len(batches)):
+                collect(bi)
+        finally:
+            ctx.host_unregister(frames)
+        return out_kl, out_desc, out_m
+
 
 class LineFrontEnd:
     """The reference's real per-frame loop (EDline on every frame + Matching(prev, cur),
