@@ -28,7 +28,7 @@ constexpr int LLA_PX = 4;  // pixels per thread
 
 __global__ void __launch_bounds__(256)
 ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* __restrict__ pix,
-                const float2* __restrict__ lut, unsigned int* __restrict__ maxq, int ws, int hs, double rho) {
+                const float2* __restrict__ lut, unsigned int* __restrict__ maxq, int ws, int hs, unsigned int q_undef) {
   // pixel k of a thread is x0 + 32 k: every load/store instruction of the warp is contiguous
   const int x0 = blockIdx.x * (32 * LLA_PX) + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -56,10 +56,10 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
         w = (uint32_t)(DA + 255) | ((uint32_t)(BC + 255) << 16);
         int gx = DA + BC, gy = DA - BC;
         unsigned int qq = (unsigned int)(gx * gx + gy * gy);
-        // sqrt(q/4) <= rho = 5.2262... for every q < 100 (sqrt(25) = 5): skip the FP64 work there;
-        // q >= 100 takes the exact double comparison
-        double norm = (qq < 100u) ? 0.0 : sqrt((double)(int)qq / 4.0);
-        if (!(norm <= rho)) {
+        // cv2's test is norm <= rho with norm = sqrt(q / 4.0) in double.  q is an integer and the expression is monotone
+        // in it, so the test is q <= q_undef with q_undef the largest q for which the double expression holds -- found
+        // by evaluating that very expression on the host (launch_ll_angle): no FP64 work per pixel.
+        if (qq > q_undef) {
           q = max(q, qq);
           a = fast_atan2_deg((float)gx, (float)-gy);
         }
@@ -84,7 +84,11 @@ ll_angle_kernel(const uint8_t* __restrict__ scl, float* __restrict__ ang, Pix* _
 void launch_ll_angle(const uint8_t* scl, float* ang, Pix* pix, const float2* lut, unsigned int* maxq,
                      int ws, int hs, int batch, double rho, cudaStream_t st) {
   dim3 grid((ws + 32 * LLA_PX - 1) / (32 * LLA_PX), (hs + 7) / 8, batch);
-  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, lut, maxq, ws, hs, rho);
+  // largest integer q with sqrt((double)q / 4.0) <= rho, by the same IEEE operations the per-pixel test used (sqrt and
+  // the division by 4 are correctly rounded / exact on host and device alike); q <= 2 * 510^2
+  unsigned int q_undef = 0;
+  while (q_undef < 520200u && sqrt((double)(int)(q_undef + 1) / 4.0) <= rho) ++q_undef;
+  ll_angle_kernel<<<grid, 256, 0, st>>>(scl, ang, pix, lut, maxq, ws, hs, q_undef);
 }
 
 // (cosf, sinf) of the level-line angle as a function of the two gradient differences DA = d - a, BC = b - c of a
@@ -162,10 +166,7 @@ order_kernel(const uint8_t* __restrict__ scl, const unsigned int* __restrict__ m
         }
         bins[(size_t)y * ws + x] = (uint16_t)b;  // 0xffff = undefined
       }
-      if (__ballot_sync(0xffffffffu, b >= 0) == 0) continue;  // nothing to count in these 32 pixels
-      unsigned int grp = __match_any_sync(0xffffffffu, b);
-      if (b >= 0 && lane == (31 - __clz(grp))) mycnt[b] += __popc(grp);
-      __syncwarp();
+      if (b >= 0) atomicAdd(mycnt + b, 1u);  // the warp's own counters: a shared-memory atomic per defined pixel
     }
   }
   __syncthreads();
