@@ -79,9 +79,6 @@ LF_METRIC = "reference line front-end frames/sec (EDLines + KLT line matching, L
 ED_METRIC = "EDLines line detection frames/sec (the reference's EDLineDetector::EDline) at 752x480"
 
 
-E2E_TRACE = []  # --e2e-trace: host and device times of one group of the e2e pass
-
-
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -1232,11 +1229,11 @@ def main():
     ap.add_argument("--e2e-staggered", action="store_true",
                     help="e2e: collect and resubmit one slot at a time (round-1 behaviour) instead of submitting the "
                          "slots' batches back to back")
-    ap.add_argument("--e2e-trace", action="store_true", help="experiments: host/device times of one group of the e2e pass")
+    ap.add_argument("--e2e-collect-first", action="store_true",
+                    help="e2e: collect a group before the next one is submitted (one result generation per slot)")
     ap.add_argument("--timeline", action="store_true",
                     help="print where the stages of one group of resident batches lie in time on the device, and exit")
     ap.add_argument("--e2e-no-chain", action="store_true", help="experiments: no match across batch boundaries in the e2e pass")
-    ap.add_argument("--e2e-no-profile", action="store_true", help="experiments: stage events off during the e2e pass")
     ap.add_argument("--e2e-only", action="store_true",
                     help="experiments: print only the end-to-end figure (host buffers in and out) and exit")
     ap.add_argument("--profile-region", action="store_true",
@@ -1332,42 +1329,35 @@ def main():
             for i in range(min(S, n_steps)):
                 upload(i)
         if args.e2e_together:
-            # the slots' batches are submitted as a group (vpl_frontend_submit_group) and collected together: every
-            # kernel of the path then runs next to the SAME kernel of the other slot, and the engine launches start
-            # behind a barrier across the group -- two of them side by side fill the SMs' warp slots, which is what the
-            # latency-bound engine needs (52.1 k against 47.2 k frames/s for one slot at a time,
-            # profiles/r02_engine_wave_runs.txt)
-            t_grp = time.perf_counter()
-            for g in range(0, n_steps, S):
-                tc = []
-                while pending:
-                    ps = pending.pop(0)
-                    tc0 = time.perf_counter()
-                    ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
-                    tc.append(round((time.perf_counter() - tc0) * 1e3, 3))
-                grp = range(g, min(g + S, n_steps))
-                trace = args.e2e_trace and g == 2 * S and n_steps > 3 * S
-                if trace:
-                    tr = {"since_last_uploads_ms": (time.perf_counter() - t_grp) * 1e3, "each_collect_ms": tc}
-                    ctx.mark()
-                    t0 = time.perf_counter()
-                t_grp = time.perf_counter()
+            # the slots' batches are submitted as a group (vpl_frontend_submit_group): every kernel of the path then
+            # runs next to the SAME kernel of the other slot, and the engine launches start behind a barrier across the
+            # group -- two of them side by side fill the SMs' warp slots, which is what the latency-bound engine needs
+            # (52.1 k against 47.2 k frames/s for one slot at a time, profiles/r02_engine_wave_runs.txt).  Group g is
+            # submitted BEFORE group g-1 is collected (it queues behind it on the slots' streams and writes the slots'
+            # other result generation), so the download of g-1 and the host's turn-around overlap the kernels of g.
+            groups = [range(g, min(g + S, n_steps)) for g in range(0, n_steps, S)]
+
+            def submit(grp):
                 ctx.submit_group([i % S for i in grp], [len(frames_of(i)) for i in grp], W, H, scale=2, num_octaves=OCT,
                                  k=K, chain=[(i > 0 and not args.e2e_no_chain) for i in grp])
-                pending.extend(i % S for i in grp)
-                if trace:
-                    tr["t_submits_ms"] = (time.perf_counter() - t0) * 1e3
+
+            def collect(grp):
                 for i in grp:
-                    if i + S < n_steps:
-                        upload(i + S)
-                if trace:
-                    tr["t_uploads_ms"] = (time.perf_counter() - t0) * 1e3
-                    tr["timeline"] = {str(sl): {k: [round(a, 2), round(b, 2)] for k, (a, b) in ctx.timeline(sl).items()}
-                                      for sl in range(S)}
-                    tr["t_chains_done_ms"] = (time.perf_counter() - t0) * 1e3
-                    E2E_TRACE.append(tr)
-                t_grp = time.perf_counter()
-            n_steps = 0
+                    ctx.collect_dense_into(i % S, counts[i % S], kl[i % S], desc[i % S], mt[i % S])
+
+            submit(groups[0])
+            for gi in range(1, len(groups)):
+                for i in groups[gi]:
+                    upload(i)  # (the slot's second input buffer is free: group gi-2 has been collected)
+                if args.e2e_collect_first:
+                    collect(groups[gi - 1])
+                    submit(groups[gi])
+                else:
+                    submit(groups[gi])
+                    collect(groups[gi - 1])
+            collect(groups[-1])
+            lines = int(counts[(n_steps - 1) % S][:B].sum())
+            return lines
         for i in range(n_steps):
             s = i % S
             if len(pending) == S:
@@ -1388,11 +1378,10 @@ def main():
         return lines
 
     # ---- warm-up (also leaves a batch resident in every slot)
+    # (per-stage events off in the timed e2e pass: with them on, a submit waits for the slot's previous batch)
+    ctx.set_profile(False)
     e2e_steps(max(args.warmup, S), False)
     barrier()
-    ctx.reset_stage_times()
-    if args.e2e_no_profile:
-        ctx.set_profile(False)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -1410,6 +1399,7 @@ def main():
 
     if args.timeline:
         sampler.stop()
+        ctx.set_profile(True)
         for rep in range(2):
             ctx.sync()
             ctx.mark()
@@ -1428,7 +1418,6 @@ def main():
 
     if args.e2e_only:
         sampler.stop()
-        st_e2e = ctx.stage_times()
         per_rank = e2e_ms
         if dist is not None:
             t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -1440,9 +1429,7 @@ def main():
             print(json.dumps({"e2e_only": True, "n_gpus": world, "slots": S, "frames_per_step": B, "steps": args.steps,
                               "e2e_frames_per_s": B * args.steps * world / (e2e_ms * 1e-3),
                               "upload_ahead": bool(args.upload_ahead),
-                              "rank0_h2d_ms_per_step": st_e2e["h2d"][0] / args.steps,
-                              "ms_per_step": e2e_ms / args.steps, "ms_per_step_by_rank": per_rank,
-                              "trace": E2E_TRACE[-1:]}))
+                              "ms_per_step": e2e_ms / args.steps, "ms_per_step_by_rank": per_rank}))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -1472,6 +1459,7 @@ def main():
             for i in range(n):
                 ctx.run_resident(i % S, k=K)
 
+    ctx.set_profile(True)
     resident_steps(max(args.warmup, S))
     ctx.sync()
     ctx.reset_stage_times()

@@ -330,7 +330,15 @@ int vpl_frontend_submit(VplContext* ctx, int slot, const uint8_t* const* imgs, i
                         size_t stride, int scale, int num_octaves, int k, int chain);
 int vpl_frontend_collect(VplContext* ctx, int slot, VplKeyLine* keylines, int32_t* counts, int cap,
                          uint8_t* desc, VplDMatch* matches);
-/* Upload ahead: copies the NEXT batch of slot s to the device on a copy stream of its own, into a
+/* Two batches per slot: a batch staged with vpl_frontend_upload may be submitted (imgs == NULL, or
+ * vpl_frontend_submit_group) while the slot's previous front-end batch has not been collected yet.  Its kernels queue
+ * behind the previous batch's on the slot's stream and its results go to the slot's second result generation, so
+ * collecting the previous batch -- waiting for it, downloading its rows -- overlaps kernels.  Collects return the
+ * batches of a slot oldest first.  At most two uncollected batches per slot; the next vpl_frontend_upload on the slot
+ * needs the older one collected (it overwrites that batch's input buffer).  With per-stage events on
+ * (VplConfig.profile) a submit waits for the slot's previous batch, which serialises the two.
+ *
+ * Upload ahead: copies the NEXT batch of slot s to the device on a copy stream of its own, into a
  * second input buffer of the slot, and returns without waiting -- allowed while the slot's current
  * batch is in flight, so the host-to-device copy of batch i+num_slots overlaps the kernels of batch
  * i instead of following its collect.  The next vpl_frontend_submit on that slot takes these frames

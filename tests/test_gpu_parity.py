@@ -373,7 +373,7 @@ def test_errors(ctx, vpl):
     assert vpl.BinaryDescriptorMatcher().match(np.zeros((0, 32), np.uint8), np.zeros((4, 32), np.uint8)) == []
 
 
-def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, group=False):
+def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, group=False, profile=True):
     """The exact call sequence bench.py times end to end: caller frames pinned with vpl_host_register, batches
     submitted to alternating slots with chaining (the frames of batch i + 2 uploaded ahead with vpl_frontend_upload
     while batch i runs, if asked), results collected in dense form into registered buffers."""
@@ -383,7 +383,7 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, gro
     S = 2
     outs = []
     with vpl.Context(max_width=w, max_height=h, max_octaves=octaves, max_lines=cap, max_batch=per, num_slots=S,
-                     blur_first=True, profile=True) as c:
+                     blur_first=True, profile=profile) as c:
         c.host_register(frames)
         rows = per * cap
         kl = [np.zeros(rows, vpl.capi.KEYLINE_DTYPE) for _ in range(S)]
@@ -407,17 +407,27 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, gro
             for i in range(min(S, n_batches)):
                 c.upload(i % S, frames[slice(*rng(i))])
         if group:
-            # bench.py's default: the slots' uploaded batches submitted as one group, collected together
-            for g in range(0, n_batches, S):
-                while pending:
-                    collect()
-                grp = list(range(g, min(g + S, n_batches)))
+            # bench.py's default: the slots' uploaded batches submitted as one group; group g is submitted BEFORE group
+            # g-1 is collected (two result generations per slot), or after it (group == "collect_first")
+            groups = [list(range(g, min(g + S, n_batches))) for g in range(0, n_batches, S)]
+
+            def submit(grp):
                 c.submit_group([i % S for i in grp], [rng(i)[1] - rng(i)[0] for i in grp], w, h, scale=2,
                                num_octaves=octaves, k=k, chain=[i > 0 for i in grp])
                 pending.extend((i % S,) + rng(i) for i in grp)
-                for i in grp:
-                    if i + S < n_batches:
-                        c.upload(i % S, frames[slice(*rng(i + S))])
+
+            submit(groups[0])
+            for gi in range(1, len(groups)):
+                for i in groups[gi]:
+                    c.upload(i % S, frames[slice(*rng(i))])
+                if group == "collect_first":
+                    for _ in groups[gi - 1]:
+                        collect()
+                    submit(groups[gi])
+                else:
+                    submit(groups[gi])
+                    for _ in groups[gi - 1]:
+                        collect()
             n_batches = 0
         for i in range(n_batches):
             s = i % S
@@ -439,6 +449,8 @@ def _bench_path(vpl, frames, n_batches, k, octaves, cap, upload_ahead=False, gro
 @pytest.mark.parametrize("name,n,batches,k,octaves,cap,ahead", [("C2_euroc_752x480", 33, 3, 1, 1, 1024, "no"),
                                                                 ("C2_euroc_752x480", 33, 5, 1, 1, 1024, "ahead"),
                                                                 ("C2_euroc_752x480", 33, 5, 1, 1, 1024, "group"),
+                                                                ("C2_euroc_752x480", 33, 9, 1, 1, 1024, "group"),
+                                                                ("C2_euroc_752x480", 33, 5, 1, 1, 1024, "collect_first"),
                                                                 ("C3_d455_1280x720", 9, 3, 2, 2, 2048, "group"),
                                                                 ("C3_d455_1280x720", 9, 3, 2, 2, 2048, "no")])
 def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves, cap, ahead):
@@ -447,7 +459,9 @@ def test_bench_path_against_oracle(vpl, orc, synth, name, n, batches, k, octaves
     first frame of a later batch is matched against the last frame of the batch before it."""
     import bench
     frames = np.ascontiguousarray(synth.config_sequence(name, n))
-    outs = _bench_path(vpl, frames, batches, k, octaves, cap, ahead != "no", ahead == "group")
+    # (stage events off for the queued groups, as in bench.py's timed pass: with them on a submit waits for the slot)
+    outs = _bench_path(vpl, frames, batches, k, octaves, cap, ahead != "no",
+                       ahead if ahead in ("group", "collect_first") else False, profile=(ahead != "group"))
     assert [o[0] for o in outs] == [i * ((n + batches - 1) // batches) for i in range(batches)]
     n_lines = 0
     for lo, hi, counts, kl, desc, mt in outs:
@@ -474,12 +488,27 @@ def test_upload_ahead_argument_errors(vpl, synth):
             c.submit_group([0, 1], [3, 3], 752, 480)
         with pytest.raises(vpl.capi.VplError, match="twice in the group"):
             c.submit_group([0, 0], [3, 3], 752, 480)
+        with pytest.raises(vpl.capi.VplError, match="already holds an uploaded batch"):
+            c.upload(0, frames[:2])
         c.submit_uploaded(0, 3, 752, 480, k=0)
         kl = np.zeros(3 * 1024, vpl.capi.KEYLINE_DTYPE); counts = np.zeros(3, np.int32)
         d = np.zeros((3 * 1024, 32), np.uint8); m = np.zeros((3 * 1024, 1), vpl.capi.DMATCH_DTYPE)
         total = c.collect_dense_into(0, counts, kl, d, m)
         ref = c.frontend_batch(frames[:3], k=0)[0]
         assert total == sum(len(r) for r in ref) and kl[:len(ref[0])].tobytes() == ref[0].tobytes()
+        # two batches queued on one slot: the second one only from an upload, no third, collects come oldest first
+        c.upload(0, frames[:2]); c.submit_uploaded(0, 2, 752, 480, k=0)
+        with pytest.raises(vpl.capi.VplError, match="still in flight"):
+            c.submit(0, frames[:1], k=0)
+        c.upload(0, frames[2:4]); c.submit_uploaded(0, 2, 752, 480, k=0)
+        with pytest.raises(vpl.capi.VplError, match="two uncollected batches"):
+            c.upload(0, frames[:1])
+        t1 = c.collect_dense_into(0, counts, kl, d, m); first = kl[:t1].copy()
+        t2 = c.collect_dense_into(0, counts, kl, d, m); second = kl[:t2].copy()
+        with pytest.raises(vpl.capi.VplError, match="no front-end batch in flight"):
+            c.collect_dense_into(0, counts, kl, d, m)
+        ref4 = c.frontend_batch(frames, k=0)[0]
+        assert first.tobytes() == np.concatenate(ref4[:2]).tobytes() and second.tobytes() == np.concatenate(ref4[2:]).tobytes()
 
 
 @pytest.mark.parametrize("cap", [64, 512, 4096])

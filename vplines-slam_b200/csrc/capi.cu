@@ -74,6 +74,19 @@ struct Slot {
   uint8_t* d_desc_dense = nullptr;
   VplDMatch* d_match_dense = nullptr;
   int* h_offsets = nullptr;
+  // Results of a front-end batch as they wait for their collect.  Two generations per slot: a batch staged with
+  // vpl_frontend_upload may be submitted while the slot's previous batch is still uncollected (its kernels queue behind
+  // the previous batch's on the slot's stream and write the other generation), so that the previous batch's download
+  // and the host's turn-around overlap kernels.  res[0] is the slot's own set of buffers, res[1] is allocated on the
+  // first such submit.
+  struct FrontRes {
+    cudaEvent_t done = nullptr;
+    int* d_offsets = nullptr; VplKeyLine* d_kl_dense = nullptr; uint8_t* d_desc_dense = nullptr; VplDMatch* d_match_dense = nullptr;
+    int* h_counts = nullptr; int* h_offsets = nullptr; int* h_flags = nullptr;
+    int n = 0, k = 0;
+  } res[2];
+  unsigned gen_sub = 0, gen_col = 0;  // front-end batches submitted / collected on this slot (gen_sub - gen_col <= 2)
+  int pending_gen[2] = {0, 0};        // which generation batch number i (mod 2) wrote
   bool dense = false;                // this batch's outputs are downloaded in dense form at collect
   int64_t last_d2h_bytes = 0;
   int* d_flags = nullptr;  // [0] candidate overflow, [1] keyline overflow, [2] EDLines line overflow
@@ -151,6 +164,7 @@ struct VplContext {
   int lgam_n = 0;
   std::vector<std::pair<const uint8_t*, size_t>> pinned;  // vpl_host_register ranges
   cudaEvent_t mark = nullptr;        // vpl_debug_mark: origin of vpl_debug_timeline
+  cudaStream_t down_stream = nullptr;  // dense rows of a collected front-end batch (the slot's stream may be busy with the next one)
   cudaStream_t up_stream = nullptr;  // vpl_frontend_upload: ONE copy stream for all slots, so uploads reach the device in call order
   // optional pre-processing (readImage: remap + CLAHE)
   float* d_mapx = nullptr;
@@ -551,19 +565,20 @@ int enqueue_download(VplContext* c, Slot& s, bool kl, bool desc, bool match) {
 
 // compaction + download of counts/offsets; the dense rows themselves are fetched at collect,
 // once their total size is known
-void enqueue_dense_download(VplContext* c, Slot& s) {
+void enqueue_dense_download(VplContext* c, Slot& s, Slot::FrontRes& r) {
   StageTimer t(c, s, VPL_STAGE_D2H);
   const int cap = c->cfg.max_lines;
-  offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_counts, s.n, s.d_offsets);
+  offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_counts, s.n, r.d_offsets);
   compact_outputs_kernel<<<s.n, 256, 0, s.stream>>>(
       reinterpret_cast<const uint32_t*>(s.d_kl), reinterpret_cast<const uint32_t*>(s.d_desc),
-      reinterpret_cast<const uint32_t*>(s.d_match), s.d_counts, s.d_offsets, cap, s.k,
-      reinterpret_cast<uint32_t*>(s.d_kl_dense), reinterpret_cast<uint32_t*>(s.d_desc_dense),
-      reinterpret_cast<uint32_t*>(s.d_match_dense));
+      reinterpret_cast<const uint32_t*>(s.d_match), s.d_counts, r.d_offsets, cap, s.k,
+      reinterpret_cast<uint32_t*>(r.d_kl_dense), reinterpret_cast<uint32_t*>(r.d_desc_dense),
+      reinterpret_cast<uint32_t*>(r.d_match_dense));
   t.launches(2);
-  cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
-  cudaMemcpyAsync(s.h_offsets, s.d_offsets, (size_t)(s.n + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
-  cudaMemcpyAsync(s.h_flags, s.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(r.h_counts, s.d_counts, (size_t)s.n * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(r.h_offsets, r.d_offsets, (size_t)(s.n + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  cudaMemcpyAsync(r.h_flags, s.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+  r.n = s.n; r.k = s.k;
   s.dense = true;
 }
 
@@ -625,6 +640,22 @@ int finish(VplContext* c, Slot& s) {
   harvest_times(c, s);
   s.in_flight = false;
   s.kind = BK_NONE;
+  return VPL_OK;
+}
+
+// The oldest uncollected front-end batch of a slot: wait for ITS end (a younger batch may be queued behind it on the
+// slot's stream), mark it collected.  The dense rows are then fetched on the context's download stream.
+int finish_front(VplContext* c, Slot& s, Slot::FrontRes*& r) {
+  r = &s.res[s.pending_gen[s.gen_col & 1]];
+  CK(c, cudaEventSynchronize(r->done));
+  CK(c, cudaGetLastError());
+  ++s.gen_col;
+  if (s.gen_sub == s.gen_col) {  // nothing queued behind it: the slot is idle, its stage events can be read
+    harvest_times(c, s);
+    s.in_flight = false;
+    s.kind = BK_NONE;
+  }
+  if (!c->down_stream) CK(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
   return VPL_OK;
 }
 
@@ -900,6 +931,12 @@ void vpl_destroy(VplContext* c) {
     cudaFree(s.d_img); cudaFree(s.d_pre); cudaFree(s.d_lut); cudaFree(s.d_raw);
     cudaFree(s.d_img_next);
     if (s.uploaded) cudaEventDestroy(s.uploaded);
+    {
+      Slot::FrontRes& r1 = s.res[1];
+      cudaFree(r1.d_offsets); cudaFree(r1.d_kl_dense); cudaFree(r1.d_desc_dense); cudaFree(r1.d_match_dense);
+      cudaFreeHost(r1.h_counts); cudaFreeHost(r1.h_offsets); cudaFreeHost(r1.h_flags);
+      if (r1.done) cudaEventDestroy(r1.done);
+    }
     for (int o = 0; o < kMaxOctaves; ++o) {
       OctBuf& b = s.oct[o];
       cudaFree(b.pyr); cudaFree(b.grad); cudaFree(b.scl); cudaFree(b.ang); cudaFree(b.pix); cudaFree(b.spec_tag); cudaFree(b.spec_arena); cudaFree(b.eng_desc); cudaFree(b.eng_rects); cudaFree(b.ord);
@@ -924,6 +961,7 @@ void vpl_destroy(VplContext* c) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  if (c->down_stream) cudaStreamDestroy(c->down_stream);
   if (c->mark) cudaEventDestroy(c->mark);
   delete c;
 }
@@ -1038,6 +1076,11 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
     CKC(dmalloc(&s.d_desc_dense, B * cap * 32));
     CKC(dmalloc(&s.d_match_dense, B * cap * c->max_k));
     CKC(hmalloc(&s.h_offsets, B + 1));
+    {
+      Slot::FrontRes& r0 = s.res[0];
+      r0.done = s.done; r0.d_offsets = s.d_offsets; r0.d_kl_dense = s.d_kl_dense; r0.d_desc_dense = s.d_desc_dense;
+      r0.d_match_dense = s.d_match_dense; r0.h_counts = s.h_counts; r0.h_offsets = s.h_offsets; r0.h_flags = s.h_flags;
+    }
     CKC(dmalloc(&s.d_seg, (size_t)c->cand_cap));
     CKC(dmalloc(&s.d_seg_count, 1));
     CKC(hmalloc(&s.h_kl, B * cap));
@@ -1051,6 +1094,22 @@ int vpl_create(const VplConfig* cfg, VplContext** out) {
 }
 
 // ---- fused path ---------------------------------------------------------------
+// the second result generation of a slot (see Slot::FrontRes), allocated when a batch is first queued behind another
+static int ensure_second_generation(VplContext* c, Slot& s) {
+  Slot::FrontRes& r = s.res[1];
+  if (r.done) return VPL_OK;
+  const size_t B = (size_t)c->cfg.max_batch, cap = (size_t)c->cfg.max_lines;
+  CK(c, dmalloc(&r.d_offsets, B + 1));
+  CK(c, dmalloc(&r.d_kl_dense, B * cap));
+  CK(c, dmalloc(&r.d_desc_dense, B * cap * 32));
+  CK(c, dmalloc(&r.d_match_dense, B * cap * c->max_k));
+  CK(c, hmalloc(&r.h_counts, B));
+  CK(c, hmalloc(&r.h_offsets, B + 1));
+  CK(c, hmalloc(&r.h_flags, 4));
+  CK(c, cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
+  return VPL_OK;
+}
+
 // vpl_frontend_submit up to the kernels: argument checks, then the frames (uploaded now, or taken from the buffer that
 // vpl_frontend_upload filled) and the optional pre-processing
 static int submit_prepare(VplContext* c, int slot, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
@@ -1062,7 +1121,14 @@ static int submit_prepare(VplContext* c, int slot, const uint8_t* const* imgs, i
   if (n == 0) return fail(c, VPL_E_INVALID, "empty batch");
   CK(c, cudaSetDevice(c->cfg.device));
   Slot& s = c->slots[slot];
-  if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+  if (s.in_flight) {
+    // one more front-end batch may queue behind an uncollected one if its frames were uploaded ahead (the slot's
+    // staging buffer may still feed the batch in flight) -- it writes the slot's other result generation
+    if (!(s.kind == BK_FRONTEND && !imgs && s.gen_sub - s.gen_col < 2))
+      return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slot);
+    int r1 = ensure_second_generation(c, s);
+    if (r1) return r1;
+  }
   if (!imgs) {
     // the frames were staged by vpl_frontend_upload: make its buffer the slot's input
     if (s.staged_n == 0) return fail(c, VPL_E_INVALID, "imgs == NULL but slot %d holds no uploaded batch (vpl_frontend_upload)", slot);
@@ -1079,8 +1145,13 @@ static int submit_prepare(VplContext* c, int slot, const uint8_t* const* imgs, i
 }
 
 static int submit_finish(VplContext* c, Slot& s) {
-  enqueue_dense_download(c, s);
-  CK(c, cudaEventRecord(s.done, s.stream));
+  // generation 0 unless the slot's previous batch is still uncollected (then the one it did not write)
+  const int gi = (s.in_flight && s.kind == BK_FRONTEND) ? 1 - s.pending_gen[s.gen_col & 1] : 0;
+  Slot::FrontRes& r = s.res[gi];
+  enqueue_dense_download(c, s, r);
+  CK(c, cudaEventRecord(r.done, s.stream));
+  s.pending_gen[s.gen_sub & 1] = gi;
+  ++s.gen_sub;
   s.in_flight = true;
   s.kind = BK_FRONTEND;
   s.resident = BK_FRONTEND;
@@ -1109,7 +1180,8 @@ int vpl_frontend_submit_group(VplContext* c, int n_slots, const int* slots, cons
   for (int i = 0; i < n_slots; ++i) {
     if (slots[i] < 0 || slots[i] >= (int)c->slots.size()) return fail(c, VPL_E_INVALID, "bad slot %d", slots[i]);
     const Slot& s = c->slots[slots[i]];
-    if (s.in_flight) return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slots[i]);
+    if (s.in_flight && !(s.kind == BK_FRONTEND && s.gen_sub - s.gen_col < 2))
+      return fail(c, VPL_E_INVALID, "slot %d still in flight: collect it first", slots[i]);
     if (s.staged_n == 0 || s.staged_n != n[i] || s.staged_w != w || s.staged_h != h)
       return fail(c, VPL_E_INVALID, "slot %d holds no uploaded batch of %d frames %dx%d (vpl_frontend_upload)", slots[i], n[i], w, h);
   }
@@ -1149,7 +1221,11 @@ int vpl_frontend_upload(VplContext* c, int slot, const uint8_t* const* imgs, int
     CK(c, cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
     CK(c, dmalloc(&s.d_img_next, (size_t)c->cfg.max_batch * c->cfg.max_width * c->cfg.max_height));
   }
-  // d_img_next was the input of the batch before the one in flight (collected, or never used): free to overwrite
+  if (s.staged_n) return fail(c, VPL_E_INVALID, "slot %d already holds an uploaded batch: submit it first", slot);
+  // d_img_next was the input of the batch before the latest one submitted on this slot: collected (hence finished) as
+  // long as at most one batch is uncollected
+  if (s.kind == BK_FRONTEND && s.gen_sub - s.gen_col >= 2)
+    return fail(c, VPL_E_INVALID, "slot %d has two uncollected batches: collect the older one before uploading the next", slot);
   CK(c, cudaMemcpyAsync(s.d_img_next, imgs[0], (size_t)n * w * h, cudaMemcpyHostToDevice, c->up_stream));
   CK(c, cudaEventRecord(s.uploaded, c->up_stream));
   s.staged_n = n; s.staged_w = w; s.staged_h = h;
@@ -1163,33 +1239,36 @@ int vpl_frontend_collect(VplContext* c, int slot, VplKeyLine* keylines, int32_t*
   Slot& s = c->slots[slot];
   if (!s.in_flight || s.kind != BK_FRONTEND) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
-  int r = finish(c, s);
+  Slot::FrontRes* g = nullptr;
+  int r = finish_front(c, s, g);
   if (r) return r;
-  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
-  if (s.h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
+  const int n = g->n, k = g->k;
+  if (g->h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
+  if (g->h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
   if (counts) {
-    for (int f = 0; f < s.n; ++f) {
-      if (s.h_counts[f] > cap) return fail(c, VPL_E_CAPACITY, "frame %d has %d keylines > cap %d", f, s.h_counts[f], cap);
-      counts[f] = s.h_counts[f];
+    for (int f = 0; f < n; ++f) {
+      if (g->h_counts[f] > cap) return fail(c, VPL_E_CAPACITY, "frame %d has %d keylines > cap %d", f, g->h_counts[f], cap);
+      counts[f] = g->h_counts[f];
     }
   }
   // dense rows: now that the total is known, fetch exactly that much and scatter it into the
   // caller's frame-major layout
-  const size_t total = (size_t)s.h_offsets[s.n];
+  const size_t total = (size_t)g->h_offsets[n];
   if (total > 0) {
-    if (keylines) CK(c, cudaMemcpyAsync(s.h_kl, s.d_kl_dense, total * sizeof(VplKeyLine), cudaMemcpyDeviceToHost, s.stream));
-    if (desc) CK(c, cudaMemcpyAsync(s.h_desc, s.d_desc_dense, total * 32, cudaMemcpyDeviceToHost, s.stream));
-    if (matches && s.k > 0)
-      CK(c, cudaMemcpyAsync(s.h_match, s.d_match_dense, total * s.k * sizeof(VplDMatch), cudaMemcpyDeviceToHost, s.stream));
-    CK(c, cudaStreamSynchronize(s.stream));
+    cudaStream_t ds = c->down_stream;
+    if (keylines) CK(c, cudaMemcpyAsync(s.h_kl, g->d_kl_dense, total * sizeof(VplKeyLine), cudaMemcpyDeviceToHost, ds));
+    if (desc) CK(c, cudaMemcpyAsync(s.h_desc, g->d_desc_dense, total * 32, cudaMemcpyDeviceToHost, ds));
+    if (matches && k > 0)
+      CK(c, cudaMemcpyAsync(s.h_match, g->d_match_dense, total * k * sizeof(VplDMatch), cudaMemcpyDeviceToHost, ds));
+    CK(c, cudaStreamSynchronize(ds));
   }
-  for (int f = 0; f < s.n; ++f) {
-    const size_t off = (size_t)s.h_offsets[f], cnt = (size_t)s.h_counts[f];
+  for (int f = 0; f < n; ++f) {
+    const size_t off = (size_t)g->h_offsets[f], cnt = (size_t)g->h_counts[f];
     if (keylines) memcpy(keylines + (size_t)f * cap, s.h_kl + off, cnt * sizeof(VplKeyLine));
     if (desc) memcpy(desc + (size_t)f * cap * 32, s.h_desc + off * 32, cnt * 32);
-    if (matches && s.k > 0) memcpy(matches + (size_t)f * cap * s.k, s.h_match + off * s.k, cnt * s.k * sizeof(VplDMatch));
+    if (matches && k > 0) memcpy(matches + (size_t)f * cap * k, s.h_match + off * k, cnt * k * sizeof(VplDMatch));
   }
-  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)s.k * sizeof(VplDMatch)) + (2 * (size_t)s.n + 3) * sizeof(int));
+  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)k * sizeof(VplDMatch)) + (2 * (size_t)n + 3) * sizeof(int));
   return VPL_OK;
 }
 
@@ -1200,28 +1279,31 @@ int vpl_frontend_collect_dense(VplContext* c, int slot, int32_t* counts, VplKeyL
   Slot& s = c->slots[slot];
   if (!s.in_flight || s.kind != BK_FRONTEND) return fail(c, VPL_E_INVALID, "slot %d has no front-end batch in flight", slot);
   CK(c, cudaSetDevice(c->cfg.device));
-  int r = finish(c, s);
+  Slot::FrontRes* g = nullptr;
+  int r = finish_front(c, s, g);
   if (r) return r;
-  if (s.h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
-  if (s.h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
-  const size_t total = (size_t)s.h_offsets[s.n];
+  const int n = g->n, k = g->k;
+  if (g->h_flags[0]) return fail(c, VPL_E_CAPACITY, "a frame produced more than %d LSD candidates", c->cand_cap);
+  if (g->h_flags[1]) return fail(c, VPL_E_CAPACITY, "a frame produced more than max_lines=%d keylines", c->cfg.max_lines);
+  const size_t total = (size_t)g->h_offsets[n];
   if (total_out) *total_out = (int64_t)total;
   if ((int64_t)total > cap_total) return fail(c, VPL_E_CAPACITY, "%zu keylines in the batch > cap_total %lld", total, (long long)cap_total);
-  if (counts) memcpy(counts, s.h_counts, (size_t)s.n * sizeof(int));
+  if (counts) memcpy(counts, g->h_counts, (size_t)n * sizeof(int));
   struct Out { void* user; const void* dev; void* stage; size_t bytes; };
-  const Out outs[3] = {{keylines, s.d_kl_dense, s.h_kl, total * sizeof(VplKeyLine)},
-                       {desc, s.d_desc_dense, s.h_desc, total * 32},
-                       {(s.k > 0) ? matches : nullptr, s.d_match_dense, s.h_match, total * (size_t)s.k * sizeof(VplDMatch)}};
+  const Out outs[3] = {{keylines, g->d_kl_dense, s.h_kl, total * sizeof(VplKeyLine)},
+                       {desc, g->d_desc_dense, s.h_desc, total * 32},
+                       {(k > 0) ? matches : nullptr, g->d_match_dense, s.h_match, total * (size_t)k * sizeof(VplDMatch)}};
   bool direct[3] = {false, false, false};
   for (int i = 0; i < 3; ++i) {
     if (!outs[i].user || outs[i].bytes == 0) continue;
     direct[i] = in_registered_range(c, (const uint8_t*)outs[i].user, outs[i].bytes);
-    CK(c, cudaMemcpyAsync(direct[i] ? outs[i].user : outs[i].stage, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, s.stream));
+    CK(c, cudaMemcpyAsync(direct[i] ? outs[i].user : outs[i].stage, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost,
+                          c->down_stream));
   }
-  CK(c, cudaStreamSynchronize(s.stream));
+  CK(c, cudaStreamSynchronize(c->down_stream));
   for (int i = 0; i < 3; ++i)
     if (outs[i].user && outs[i].bytes && !direct[i]) memcpy(outs[i].user, outs[i].stage, outs[i].bytes);
-  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)s.k * sizeof(VplDMatch)) + (2 * (size_t)s.n + 3) * sizeof(int));
+  s.last_d2h_bytes = (int64_t)(total * (sizeof(VplKeyLine) + 32 + (size_t)k * sizeof(VplDMatch)) + (2 * (size_t)n + 3) * sizeof(int));
   return VPL_OK;
 }
 
