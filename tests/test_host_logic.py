@@ -23,6 +23,7 @@ class OracleContext:
         self.prev_desc = None
         self.submitted = []
         self.staged = {}
+        self.queued = {}
         self.log = []
 
     def submit(self, slot, frames, scale=2, num_octaves=1, k=1, chain=False):
@@ -64,20 +65,26 @@ class OracleContext:
     def upload(self, slot, frames):
         assert getattr(self, "registered", None) is not None and np.shares_memory(frames, self.registered)
         assert slot not in self.staged and len(frames) <= self.max_batch  # one uploaded batch per slot
+        assert len(self.queued.get(slot, [])) < 2  # the older of two uncollected batches still owns the buffer
         self.staged[slot] = frames
         self.log.append(("upload", slot, len(frames)))
 
     def submit_group(self, slots, ns, w, h, scale=2, num_octaves=1, k=1, chain=None):
         assert len(set(slots)) == len(slots)
         for s_, n in zip(slots, ns):
-            assert s_ in self.staged and len(self.staged[s_]) == n and s_ not in self.pending
+            # an uploaded batch may queue behind ONE uncollected batch of its slot
+            assert s_ in self.staged and len(self.staged[s_]) == n and len(self.queued.get(s_, [])) < 2
         self.log.append(("group", tuple(slots), tuple(ns)))
         for s_, c in zip(slots, chain):
+            held = self.pending.pop(s_, None)
             self.submit(s_, self.staged.pop(s_), scale=scale, num_octaves=num_octaves, k=k, chain=c)
+            self.queued.setdefault(s_, []).append(self.pending.pop(s_))
+            if held is not None:
+                self.pending[s_] = held
 
     def collect_dense_into(self, slot, counts, kl, desc, matches):
         off = 0
-        for i, (k_, d, m) in enumerate(self.pending.pop(slot)):
+        for i, (k_, d, m) in enumerate(self.queued[slot].pop(0)):  # oldest first
             counts[i] = len(k_)
             kl[off:off + len(k_)] = k_
             desc[off:off + len(k_)] = d
@@ -307,8 +314,10 @@ def test_grouped_driver_equals_plain_driver(vpl, orc, synth):
     ctx = OracleContext(orc, vpl.capi, max_batch=2, num_slots=2)
     got = vpl.FrontEnd(ctx, k=1).run_grouped(frames)
     assert ctx.log[:3] == [("upload", 0, 2), ("upload", 1, 2), ("group", (0, 1), (2, 2))]
-    assert ctx.log[3:5] == [("upload", 0, 2), ("upload", 1, 2)] and ctx.log[5:7] == [("collect", 0), ("collect", 1)]
-    assert ctx.log[-2:] == [("group", (0,), (1,)), ("collect", 0)] and ctx.registered is None
+    # group 1 is uploaded and submitted before group 0 is collected
+    assert ctx.log[3:8] == [("upload", 0, 2), ("upload", 1, 2), ("group", (0, 1), (2, 2)), ("collect", 0), ("collect", 1)]
+    assert ctx.log[-5:] == [("upload", 0, 1), ("group", (0,), (1,)), ("collect", 0), ("collect", 1), ("collect", 0)]
+    assert ctx.registered is None
     for world in (1, 2, 3):
         part = ([], [], [])
         for r in range(world):

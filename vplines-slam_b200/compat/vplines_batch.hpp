@@ -131,18 +131,23 @@ class BatchFrontEnd {
       }
     };
     try {
+      // group g is submitted BEFORE group g-1 is collected (it queues behind it on the slots' streams and writes the
+      // slots' other result generation): the download of g-1 and this thread's work on it overlap the kernels of g
       const size_t nb = bs.size(), S = (size_t)slots_;
-      for (size_t bi = 0; bi < std::min(S, nb); ++bi) upload(bi);
-      for (size_t g = 0; g < nb; g += S) {
-        for (size_t bi = g >= S ? g - S : 0; g >= S && bi < g; ++bi) collect(bi);  // the previous group, in order
+      auto submit = [&](size_t g) {
         const int m = (int)std::min(S, nb - g);
         std::vector<int> slots((size_t)m), ns((size_t)m), chain((size_t)m);
         for (int i = 0; i < m; ++i) { slots[(size_t)i] = i; ns[(size_t)i] = bs[g + (size_t)i].n; chain[(size_t)i] = (g + (size_t)i) > 0; }
         check(vpl_frontend_submit_group(ctx_, m, slots.data(), ns.data(), w_, h_, scale, octaves_, k, chain.data()));
-        for (int i = 0; i < m; ++i)
-          if (g + (size_t)i + S < nb) upload(g + (size_t)i + S);
+      };
+      for (size_t bi = 0; bi < std::min(S, nb); ++bi) upload(bi);
+      submit(0);
+      for (size_t g = S; g < nb; g += S) {
+        for (size_t bi = g; bi < std::min(g + S, nb); ++bi) upload(bi);  // (group g-2 is collected: the buffers are free)
+        submit(g);
+        for (size_t bi = g - S; bi < g; ++bi) collect(bi);
       }
-      for (size_t bi = nb - std::min(nb, (nb - 1) % S + 1); bi < nb; ++bi) collect(bi);  // the last group
+      for (size_t bi = (nb - 1) / S * S; bi < nb; ++bi) collect(bi);  // the last group
     } catch (...) {
       vpl_sync(ctx_);
       vpl_host_unregister(ctx_, frames + (size_t)lo * fb);

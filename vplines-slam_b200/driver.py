@@ -101,17 +101,23 @@ class FrontEnd:
 
         ctx.host_register(frames)
         try:
-            for bi in range(min(S, len(batches))):
-                upload(bi)
-            for g in range(0, len(batches), S):
-                for bi in range(max(g - S, 0), g):
-                    collect(bi)  # the previous group, in order
+            # group g is submitted BEFORE group g-1 is collected (two result generations per slot): the download of
+            # g-1 and the Python work on it overlap the kernels of g
+            def submit(g):
                 grp = range(g, min(g + S, len(batches)))
                 ctx.submit_group([bi % S for bi in grp], [batches[bi][1] for bi in grp], w, h, scale=self.scale,
                                  num_octaves=self.num_octaves, k=k, chain=[bi > 0 for bi in grp])
-                for bi in grp:
-                    if bi + S < len(batches):
-                        upload(bi + S)
+
+            for bi in range(min(S, len(batches))):
+                upload(bi)
+            if batches:
+                submit(0)
+            for g in range(S, len(batches), S):
+                for bi in range(g, min(g + S, len(batches))):
+                    upload(bi)  # (group g-2 is collected: the slot's second input buffer is free)
+                submit(g)
+                for bi in range(g - S, g):
+                    collect(bi)
             for bi in range((len(batches) - 1) // S * S if batches else 0, len(batches)):
                 collect(bi)
         finally:
