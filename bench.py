@@ -1207,8 +1207,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=0,
                     help="frames per step (0: 4736 = 32 frames per SM for C2, so that the engine launches of the two slots "
                          "fill the 64 warp slots of every SM; 4096 for the other workloads)")
