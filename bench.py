@@ -1211,7 +1211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=0,
                     help="frames per step (0: 4736 = 32 frames per SM for C2, so that the engine launches of the two slots "
-                         "fill the 64 warp slots of every SM; 2368 / 592 / 296 for C1 / C3 / C4; 4096 for the other workloads)")
+                         "fill the 64 warp slots of every SM; 4736 / 2368 / 1184 for C1 / C3 / C4; 4096 for the other workloads)")
     ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--max-lines", type=int, default=0, help="KeyLine capacity per frame (0 = workload default)")
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -1240,9 +1240,10 @@ def main():
                     help="cudaProfilerStart/Stop around the resident steps (for ncu --profile-from-start off; V workloads)")
     args = ap.parse_args()
     if args.batch == 0:
-        # frames per step that fit two slots in 180 GB: 32 / 16 / 4 / 2 frames per SM for the LSD workloads
-        # (9.4 MB of device state per 752x480 frame and octave-0 pixel count ~ that), 4096 for the others
-        args.batch = {"C2": 4736, "C1": 2368, "C3": 592, "C4": 296}.get(args.workload, 4096)
+        # frames per step for two slots in 180 GB (26 bytes of device state per pixel of every octave): 32 frames per SM
+        # for the 752x480 workloads, 16 for 1280x720 with two octaves (= 32 engine warps per SM and slot), 8 for
+        # 1920x1080; 4096 frames for the other workloads
+        args.batch = {"C2": 4736, "C1": 4736, "C3": 2368, "C4": 1184}.get(args.workload, 4096)
     args.e2e_together = args.upload_ahead and not args.e2e_staggered
     if args.impl == "reference":
         return run_reference(args)
