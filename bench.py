@@ -975,7 +975,7 @@ def run_matcher(args, torch, dist, rank, local_rank, world):
 
 def sharded_config(args, wl, world):
     """`config` of the sharded-sequence workload (C5), the same for both arms."""
-    B = min(args.batch, 1024)
+    B = min(args.batch, 2368)
     return {"workload": wl["name"], "total_frames": args.total_frames, "frames_per_batch": B, "width": wl["w"],
             "height": wl["h"], "octaves": wl["octaves"], "match_k": wl["k"], "unique_frames": min(args.unique, 48),
             "slots": args.slots, "max_lines": args.max_lines or wl["max_lines"],
@@ -1010,7 +1010,7 @@ def run_sharded_sequence(args, torch, dist, rank, local_rank, world):
     W, H, OCT, K = wl["w"], wl["h"], wl["octaves"], wl["k"]
     cap = args.max_lines or wl["max_lines"]
     total = args.total_frames
-    B, S = min(args.batch, 1024), args.slots
+    B, S = min(args.batch, 2368), args.slots
     unique = make_frames(min(args.unique, 48), args.seed, args.workload)
     seq_len = len(unique)
 
@@ -1029,36 +1029,51 @@ def run_sharded_sequence(args, torch, dist, rank, local_rank, world):
         ctx.host_register(a)
 
     def run_shard(start, end, halo, shard, want_hashes):
-        """frames [start, end) (+ halo frame in front) through submit/collect; shard = pinned host array of them."""
+        """frames [start, end) (+ halo frame in front) through the grouped pipeline of the batch API (uploads ahead,
+        the slots' batches submitted as a group, group g submitted before group g-1 is collected); shard = pinned
+        host array of them."""
         lo = start - halo
         n = end - lo
         hashes = np.zeros(end - start, np.uint32) if want_hashes else None
-        pending = []
         lines = 0
+        batches = []  # (offset in the shard, frames, leading halo frames to skip)
+        i = 0
+        while i < n:
+            first = not batches
+            b_n = min(B + (1 if first and halo else 0), n - i)
+            batches.append((i, b_n, 1 if first and halo else 0))
+            i += b_n
+        groups = [list(range(g, min(g + S, len(batches)))) for g in range(0, len(batches), S)]
 
-        def collect():
+        def upload(bi):
+            i0, b_n, _ = batches[bi]
+            ctx.upload(bi % S, shard[i0:i0 + b_n])
+
+        def submit(grp):
+            ctx.submit_group([bi % S for bi in grp], [batches[bi][1] for bi in grp], W, H, scale=2, num_octaves=OCT, k=K,
+                             chain=[bi > 0 for bi in grp])
+
+        def collect(bi):
             nonlocal lines
-            ps, b_lo, b_n, skip = pending.pop(0)
+            i0, b_n, skip = batches[bi]
+            ps = bi % S
             ctx.collect_dense_into(ps, counts[ps], kl[ps], desc[ps], mt[ps])
             lines += int(counts[ps][skip:b_n].sum())
             if want_hashes:
                 hh = frame_hashes(counts[ps], kl[ps], desc[ps], mt[ps], b_n)
-                hashes[b_lo + skip - start:b_lo + b_n - start] = hh[skip:]
+                hashes[lo + i0 + skip - start:lo + i0 + b_n - start] = hh[skip:]
 
-        i = 0
-        bi = 0
-        while i < n:
-            first = bi == 0
-            b_n = min(B + (1 if first and halo else 0), n - i)
-            s = bi % S
-            if len(pending) == S:
-                collect()
-            ctx.submit(s, shard[i:i + b_n], scale=2, num_octaves=OCT, k=K, chain=not first)
-            pending.append((s, lo + i, b_n, 1 if first and halo else 0))
-            i += b_n
-            bi += 1
-        while pending:
-            collect()
+        for bi in groups[0]:
+            upload(bi)
+        submit(groups[0])
+        for gi in range(1, len(groups)):
+            for bi in groups[gi]:
+                upload(bi)
+            submit(groups[gi])
+            for bi in groups[gi - 1]:
+                collect(bi)
+        for bi in groups[-1]:
+            collect(bi)
         return lines, hashes
 
     start, end, halo = driver.shard_range(total, rank, world)
@@ -1243,7 +1258,7 @@ def main():
         # frames per step for two slots in 180 GB (26 bytes of device state per pixel of every octave): 32 frames per SM
         # for the 752x480 workloads, 16 for 1280x720 with two octaves (= 32 engine warps per SM and slot), 8 for
         # 1920x1080; 4096 frames for the other workloads
-        args.batch = {"C2": 4736, "C1": 4736, "C3": 2368, "C4": 1184}.get(args.workload, 4096)
+        args.batch = {"C2": 4736, "C1": 4736, "C3": 2368, "C5": 2368, "C4": 1184}.get(args.workload, 4096)
     args.e2e_together = args.upload_ahead and not args.e2e_staggered
     if args.impl == "reference":
         return run_reference(args)
