@@ -5,11 +5,14 @@ Workload (BASELINE.json configs[1], "C2"): synthetic EuRoC-shaped 752x480 mono f
 single-octave LSDDetector::detect + BinaryDescriptor::compute + consecutive-frame
 match (k=1).  One STEP = one batch of --batch frames through the whole hot path.
 
-  value  whole-job frames/s with the batch already resident in HBM (kernels only,
-         results left in HBM), batches pipelined over the context's slots;
-  e2e    the same through the reference-facing C ABI with HOST buffers:
-         vpl_frontend_submit/collect, pinned staging + H2D + kernels + D2H inside the
-         timed region;
+  value  whole-job frames/s with the batches already resident in HBM (kernels only,
+         results left in HBM), the slots' batches enqueued as groups
+         (vpl_frontend_run_resident_group);
+  e2e    the same through the reference-facing C ABI with HOST buffers, everything inside
+         the timed region: frames in pinned caller memory copied to the device ahead of
+         their turn (vpl_frontend_upload), the slots' batches submitted as a group
+         (vpl_frontend_submit_group) before the previous group is collected, dense rows
+         downloaded into pinned caller buffers (vpl_frontend_collect_dense);
   roofline      dominant kernel (the LSD region engine): algorithmic bytes / its mean
                 launch duration (CUDA events on its own stream) vs the measured HBM peak;
   cpu_baseline  the CPU oracle (port of the path, oracle/) on the host cores, bounded sample.
